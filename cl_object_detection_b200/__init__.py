@@ -1,0 +1,12 @@
+"""B200-native detection-head path for the incremental-learning RetinaNet of EonianCoda/CL_object_detection.
+
+Host side mirrors the reference's Python interfaces (Anchors, calc_iou, FocalLoss, BBoxTransform, ClipBoxes,
+predict); the arithmetic runs in hand-written sm_100a CUDA kernels behind the C ABI in include/cldet.h.
+"""
+from ._lib import CldetError, LIB_PATH, load as load_library  # noqa: F401
+from .params import HeadParams  # noqa: F401
+from .anchors import Anchors, generate_anchors, num_anchors  # noqa: F401
+from .losses import FocalLoss, calc_iou, iou_assign  # noqa: F401
+
+__all__ = ['Anchors', 'generate_anchors', 'num_anchors', 'FocalLoss', 'calc_iou', 'iou_assign', 'HeadParams',
+           'CldetError', 'load_library', 'LIB_PATH']

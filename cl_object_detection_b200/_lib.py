@@ -1,0 +1,107 @@
+"""ctypes binding of libcldet.so (the C ABI declared in include/cldet.h).
+
+There is NO fallback: if the library is missing or a call fails, this module raises.  Nothing here
+imports the test oracle.
+"""
+import ctypes
+import os
+import threading
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_PKG, 'libcldet.so')
+
+_lock = threading.Lock()
+_lib = None
+
+
+class CldetError(RuntimeError):
+    pass
+
+
+class LossParams(ctypes.Structure):
+    """struct cldet_loss_params (include/cldet.h)."""
+    _fields_ = [('alpha', ctypes.c_float), ('gamma', ctypes.c_float), ('incremental', ctypes.c_int32),
+                ('past_class_num', ctypes.c_int32), ('ignore_past_class', ctypes.c_int32),
+                ('new_ignore_past_class', ctypes.c_int32), ('decrease_positive_by_iou', ctypes.c_int32),
+                ('enhance_on_new', ctypes.c_int32), ('decrease_positive', ctypes.c_float)]
+
+
+_P = ctypes.c_void_p
+_I = ctypes.c_int
+_L = ctypes.c_int64
+_F = ctypes.c_float
+_Z = ctypes.c_size_t
+
+# name -> (restype, argtypes).  Must list every function include/cldet.h declares (tests check this).
+SIGNATURES = {
+    'cldet_abi_version': (_I, []),
+    'cldet_status_string': (ctypes.c_char_p, [_I]),
+    'cldet_last_cuda_error': (ctypes.c_char_p, []),
+    'cldet_num_anchors': (_I, [_I, _I, ctypes.POINTER(_L)]),
+    'cldet_anchors': (_I, [_I, _I, _P, _P]),
+    'cldet_iou_assign': (_I, [_P, _L, _P, _I, _I, _I, _P, _P, _P, _P, _P, _P]),
+    'cldet_calc_iou': (_I, [_P, _L, _P, _I, _P, _P]),
+    'cldet_focal_loss_workspace_bytes': (_Z, [_I, _L]),
+    'cldet_focal_loss': (_I, [_P, _P, _P, _P, _I, _L, _I, _I, ctypes.POINTER(LossParams), _P, _P, _P, _P, _P, _P, _P,
+                              _P, _P, _P, _P, _Z, _P]),
+    'cldet_focal_loss_from_assignment': (_I, [_P, _P, _P, _P, _I, _L, _I, _I, ctypes.POINTER(LossParams), _P, _P, _P,
+                                              _P, _P, _P, _P, _P, _P, _P, _Z, _P]),
+    'cldet_focal_loss_reweight': (_I, [_P, _P, _P, _P, _I, _L, _I, _I, ctypes.POINTER(LossParams), _P, _P, _P, _P, _P,
+                                       _P, _P, _P]),
+    'cldet_decode_boxes': (_I, [_P, _P, _I, _L, _I, _I, _I, _P, _P]),
+    'cldet_clip_boxes': (_I, [_P, _L, _I, _I, _P]),
+    'cldet_decode_filter': (_I, [_P, _I, _P, _P, _I, _L, _I, _I, _I, _F, _P, _P, _L, _P, _P]),
+    'cldet_sort_workspace_bytes': (_Z, [_I, _L, _I]),
+    'cldet_sort_candidates': (_I, [_P, _P, _P, _I, _L, _L, _I, _P, _L, _P, _P, _Z, _P]),
+    'cldet_nms_workspace_bytes': (_Z, [_I, _L]),
+    'cldet_nms_sorted': (_I, [_P, _P, _I, _L, _L, _F, _I, _L, _P, _P, _P, _Z, _P]),
+    'cldet_batched_nms_workspace_bytes': (_Z, [_L]),
+    'cldet_batched_nms': (_I, [_P, _P, _P, _L, _F, _I, _L, _P, _P, _P, _Z, _P]),
+    'cldet_gather_detections': (_I, [_P, _P, _P, _I, _L, _L, _P, _P, _P, _P]),
+}
+
+
+# entry points declared in the header whose kernels are not in this build yet (emptied as they land)
+_PENDING = set()
+
+
+def load():
+    """Load libcldet.so once.  Raises CldetError if it has not been built (no fallback path exists)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    with _lock:
+        if _lib is not None:
+            return _lib
+        if not os.path.exists(LIB_PATH):
+            raise CldetError('%s is missing: build it with `python -m cl_object_detection_b200.build` '
+                             '(or __graft_entry__.build()). There is no CPU/PyTorch fallback for this path.' % LIB_PATH)
+        lib = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            try:
+                fn = getattr(lib, name)
+            except AttributeError as e:
+                if name in _PENDING:
+                    continue
+                raise CldetError('libcldet.so does not export %s (stale build?)' % name) from e
+            fn.restype = res
+            fn.argtypes = args
+        if lib.cldet_abi_version() != 1:
+            raise CldetError('libcldet.so ABI version mismatch')
+        _lib = lib
+    return _lib
+
+
+def check(status):
+    if status == 0:
+        return
+    lib = load()
+    msg = lib.cldet_status_string(status).decode()
+    if status == 3:
+        msg += ': ' + lib.cldet_last_cuda_error().decode()
+    raise CldetError('libcldet: ' + msg)
+
+
+def ptr(t):
+    """Device pointer of a tensor (None -> NULL)."""
+    return None if t is None else t.data_ptr()

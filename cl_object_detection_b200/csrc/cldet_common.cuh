@@ -1,0 +1,65 @@
+// Shared device/host helpers for libcldet (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "cldet.h"
+
+namespace cldet {
+
+// Thread-local record of the last failing CUDA call (no shared mutable state between host threads).
+void set_last_cuda_error(cudaError_t e);
+
+#define CLDET_CUDA_TRY(expr)                       \
+    do {                                           \
+        cudaError_t _e = (expr);                   \
+        if (_e != cudaSuccess) {                   \
+            ::cldet::set_last_cuda_error(_e);      \
+            return CLDET_ERR_CUDA;                 \
+        }                                          \
+    } while (0)
+
+#define CLDET_LAUNCH_CHECK() CLDET_CUDA_TRY(cudaPeekAtLastError())
+
+constexpr int kNumLevels = 5;
+constexpr int kAnchorsPerCell = 9;
+
+__host__ __device__ __forceinline__ uint32_t meta_pack(uint32_t state, uint32_t label, uint32_t raw_row) {
+    return (state & 3u) | ((label & 0x1fffu) << 3) | (raw_row << 16);
+}
+__host__ __device__ __forceinline__ uint32_t meta_state(uint32_t m) { return m & 3u; }
+__host__ __device__ __forceinline__ uint32_t meta_label(uint32_t m) { return (m >> 3) & 0x1fffu; }
+__host__ __device__ __forceinline__ uint32_t meta_row(uint32_t m) { return m >> 16; }
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ int warp_sum_int(int v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// Streaming 128-bit accesses: data touched exactly once, keep it out of L1.
+__device__ __forceinline__ float4 ld_stream_f4(const float4* p) {
+    float4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+                 : "l"(p));
+    return r;
+}
+__device__ __forceinline__ void st_stream_f4(float4* p, const float4& v) {
+    asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z),
+                 "f"(v.w)
+                 : "memory");
+}
+
+inline int sm_count() {
+    int dev = 0, n = 148;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    return n > 0 ? n : 148;
+}
+
+}  // namespace cldet

@@ -1,0 +1,790 @@
+// K4 decode+filter, K5 radix-select top-k + ordering, K6 bitmask NMS, for the eval-mode detection output.
+// Reference: retinanet/utils.py:102-126 (BBoxTransform), :134-144 (ClipBoxes); retinanet/model.py:507-550
+// (ResNet.predict); IL_method/persuado_label.py:99-127 (Labeler.predict); torchvision.ops.batched_nms
+// (0.26.0: ops/boxes.py _batched_nms_coordinate_trick/_batched_nms_vanilla + torchvision::nms).
+//
+// Compiled with -fmad=false: decoded boxes, scores and IoU compares must round exactly like the reference's
+// separate ATen ops, because keep indices / labels are integer outputs of those fp32 values.
+#include <math.h>
+
+#include <algorithm>
+
+#include "cldet_common.cuh"
+
+namespace cldet {
+
+__host__ __device__ __forceinline__ int64_t min64(int64_t a, int64_t b) { return a < b ? a : b; }
+
+// ------------------------------------------------------------------------------------------------
+// Box decode + clip (utils.py:102-126, 134-144); std = (0.1, 0.1, 0.2, 0.2), mean = 0.
+// ------------------------------------------------------------------------------------------------
+template <bool CLIP = true>
+__device__ __forceinline__ float4 decode_clip(const float4 an, const float4 d, float img_w, float img_h) {
+    const float w = an.z - an.x;
+    const float h = an.w - an.y;
+    const float cx = an.x + 0.5f * w;
+    const float cy = an.y + 0.5f * h;
+    const float dx = d.x * 0.1f + 0.0f;
+    const float dy = d.y * 0.1f + 0.0f;
+    const float dw = d.z * 0.2f + 0.0f;
+    const float dh = d.w * 0.2f + 0.0f;
+    const float pcx = cx + dx * w;
+    const float pcy = cy + dy * h;
+    const float pw = expf(dw) * w;
+    const float ph = expf(dh) * h;
+    float4 o;
+    o.x = pcx - 0.5f * pw;
+    o.y = pcy - 0.5f * ph;
+    o.z = pcx + 0.5f * pw;
+    o.w = pcy + 0.5f * ph;
+    if (CLIP) {
+        o.x = fmaxf(o.x, 0.0f);      // clamp(min=0)
+        o.y = fmaxf(o.y, 0.0f);
+        o.z = fminf(o.z, img_w);     // clamp(max=width)
+        o.w = fminf(o.w, img_h);
+    }
+    return o;
+}
+
+template <bool CLIP>
+__global__ void __launch_bounds__(256) decode_boxes_kernel(const float4* __restrict__ anchors, const float4* __restrict__ reg,
+                                                           int64_t A, int64_t total, float img_w, float img_h,
+                                                           float4* __restrict__ out) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x)
+        out[i] = decode_clip<CLIP>(anchors[i % A], reg[i], img_w, img_h);
+}
+
+// ClipBoxes.forward (utils.py:134-144), in place
+__global__ void __launch_bounds__(256) clip_boxes_kernel(float4* __restrict__ boxes, int64_t total, float img_w, float img_h) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        float4 b = boxes[i];
+        b.x = fmaxf(b.x, 0.0f);
+        b.y = fmaxf(b.y, 0.0f);
+        b.z = fminf(b.z, img_w);
+        b.w = fminf(b.w, img_h);
+        boxes[i] = b;
+    }
+}
+
+// ATen's CUDA sigmoid for float: 1 / (1 + exp(-x)), IEEE divide.
+__device__ __forceinline__ float sigmoid_exact(float x) { return __fdiv_rn(1.0f, 1.0f + expf(-x)); }
+
+// order-preserving float -> uint32 (larger float <=> larger uint)
+__device__ __forceinline__ uint32_t float_ordered(float f) {
+    const uint32_t b = __float_as_uint(f);
+    return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+// sort key: higher score first; equal scores: lower anchor index first.  All keys of one image are distinct.
+__device__ __forceinline__ uint64_t make_key(float score, int anchor) {
+    return ((uint64_t)float_ordered(score) << 32) | (uint64_t)(0xFFFFFFFFu - (uint32_t)anchor);
+}
+
+// ------------------------------------------------------------------------------------------------
+// K4: fused class-max + threshold + decode.  Block = 256 threads, R anchor rows of one image.
+//   phase 1: coalesced 128-bit sweep over the R*C logits; each vector's max goes to shared memory
+//   phase 2: one thread per row reduces its row's partials; rows whose max can pass the threshold re-read only the
+//            vectors that can hold the winning class, evaluate the exact sigmoid there (first-index tie rule of
+//            torch.max), decode + clip the box and join a block-aggregated append (one atomic per block).
+// Only survivors are decoded; the [N,A,C] sigmoid map and the [N,A,4] box tensor are never materialised.
+// ------------------------------------------------------------------------------------------------
+constexpr int kFilterThreads = 256;
+constexpr int kFilterMaxPartials = 8192;   // 32 KB of shared memory
+
+template <int VEC>
+__global__ void __launch_bounds__(kFilterThreads)
+decode_filter_kernel(const float* __restrict__ cls, int is_logits, const float4* __restrict__ reg,
+                     const float4* __restrict__ anchors, int64_t A, int C, int rows_per_block, float img_w, float img_h,
+                     float score_thresh, float prefilter, cldet_candidate* __restrict__ cand, uint64_t* __restrict__ keys,
+                     int64_t capacity, int32_t* __restrict__ counts) {
+    extern __shared__ float part[];
+    __shared__ int warp_tot[kFilterThreads / 32];
+    __shared__ int block_base;
+
+    const int j = blockIdx.y;
+    const int64_t a0 = (int64_t)blockIdx.x * rows_per_block;
+    const int nrows = (int)min64(rows_per_block, A - a0);
+    const int ppr = (C + VEC - 1) / VEC;
+    const int nvec = nrows * ppr;
+    const float* base = cls + ((int64_t)j * A + a0) * C;
+
+    // ---- phase 1 ----
+    if (VEC == 4) {
+        const float4* src = reinterpret_cast<const float4*>(base);
+        for (int v0 = threadIdx.x; v0 < nvec; v0 += kFilterThreads * 4) {
+            float4 x[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int v = v0 + u * kFilterThreads;
+                if (v < nvec) x[u] = ld_stream_f4(src + v);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int v = v0 + u * kFilterThreads;
+                if (v < nvec) part[v] = fmaxf(fmaxf(x[u].x, x[u].y), fmaxf(x[u].z, x[u].w));
+            }
+        }
+    } else {
+        for (int v = threadIdx.x; v < nvec; v += kFilterThreads) part[v] = base[v];
+    }
+    __syncthreads();
+
+    // ---- phase 2 ----
+    bool is_cand = false;
+    float best = 0.0f;
+    int best_c = 0;
+    const int r = threadIdx.x;
+    if (r < nrows) {
+        const float* p = part + r * ppr;
+        float m = p[0];
+        for (int k = 1; k < ppr; ++k) m = fmaxf(m, p[k]);
+        if (m > prefilter) {
+            // Which raw values can attain the row's maximum PROBABILITY?  For probabilities: only values == m.
+            // For logits: sigmoid is evaluated in fp32 and saturates, so every logit within 0.05 of the max (or above 10
+            // when the max is) is evaluated exactly; anything lower is smaller by >= 2e-6 relative, far beyond rounding.
+            const float t = is_logits ? ((m > 10.05f) ? 10.0f : m - 0.05f) : m;
+            const float* row = base + (int64_t)r * C;
+            best = -1.0f;
+            for (int k = 0; k < ppr; ++k) {
+                if (p[k] >= t) {
+#pragma unroll
+                    for (int e = 0; e < VEC; ++e) {
+                        const int c = k * VEC + e;
+                        if (c < C) {
+                            const float x = row[c];
+                            if (x >= t) {
+                                const float pr = is_logits ? sigmoid_exact(x) : x;
+                                if (pr > best) {          // strict: first maximal index, like torch.max(dim=1)
+                                    best = pr;
+                                    best_c = c;
+                                }
+                            }
+                        }
+                    }
+                }
+            }
+            is_cand = best > score_thresh;                // model.py:536  scores > 0.05
+        }
+    }
+    // block-aggregated append
+    const unsigned ballot = __ballot_sync(0xffffffffu, is_cand);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) warp_tot[warp] = __popc(ballot);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int tot = 0;
+#pragma unroll
+        for (int w = 0; w < kFilterThreads / 32; ++w) {
+            const int c = warp_tot[w];
+            warp_tot[w] = tot;
+            tot += c;
+        }
+        block_base = tot ? atomicAdd(&counts[j], tot) : 0;
+    }
+    __syncthreads();
+    if (is_cand) {
+        const int64_t slot = (int64_t)block_base + warp_tot[warp] + __popc(ballot & ((1u << lane) - 1u));
+        if (slot < capacity) {
+            const int64_t an = a0 + r;
+            const float4 b = decode_clip(anchors[an], reg[(int64_t)j * A + an], img_w, img_h);
+            cldet_candidate c;
+            c.x1 = b.x; c.y1 = b.y; c.x2 = b.z; c.y2 = b.w;
+            c.score = best; c.label = best_c; c.anchor = (int32_t)an; c.pad = 0;
+            cand[(int64_t)j * capacity + slot] = c;
+            keys[(int64_t)j * capacity + slot] = make_key(best, (int)an);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K5: top-k by radix select on the 32 score bits (3 passes of 11/11/10 bits), then exact ordering of the
+// survivors by the full 64-bit key with a tiled rank sort.  Everything is per image; no host sync.
+// select state per image: [0] prefix (score bits decided so far), [1] remaining k, [2] survivors written, [3] done flag
+// ------------------------------------------------------------------------------------------------
+constexpr int kSelBins = 2048;
+
+struct SelPass {
+    int shift;     // bit position of this digit inside the 32 score bits
+    int bits;      // digit width
+    int hi_bits;   // number of bits already decided (above this digit)
+};
+
+__global__ void select_init_kernel(const int32_t* __restrict__ counts, int64_t capacity, int topk, uint32_t* __restrict__ state,
+                                   uint32_t* __restrict__ hist, int N) {
+    const int j = blockIdx.x;
+    for (int b = threadIdx.x; b < kSelBins; b += blockDim.x) hist[(int64_t)j * kSelBins + b] = 0;
+    if (threadIdx.x == 0) {
+        const int64_t cnt = min64(counts[j], capacity);
+        uint32_t* st = state + 4 * j;
+        st[0] = 0;
+        st[2] = 0;
+        if (topk <= 0 || cnt <= topk) {   // keep everything
+            st[1] = 0;
+            st[3] = 1;
+        } else {
+            st[1] = (uint32_t)topk;
+            st[3] = 0;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256)
+select_hist_kernel(const uint64_t* __restrict__ keys, const int32_t* __restrict__ counts, int64_t capacity, SelPass ps,
+                   const uint32_t* __restrict__ state, uint32_t* __restrict__ hist) {
+    __shared__ uint32_t sh[kSelBins];
+    const int j = blockIdx.y;
+    const uint32_t* st = state + 4 * j;
+    if (st[3]) return;
+    const int64_t cnt = min64(counts[j], capacity);
+    if ((int64_t)blockIdx.x * blockDim.x >= cnt) return;
+    const int nb = 1 << ps.bits;
+    for (int b = threadIdx.x; b < nb; b += blockDim.x) sh[b] = 0;
+    __syncthreads();
+    const uint32_t prefix = st[0];
+    const uint64_t* k = keys + (int64_t)j * capacity;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < cnt; i += (int64_t)gridDim.x * blockDim.x) {
+        const uint32_t s = (uint32_t)(k[i] >> 32);
+        const bool match = ps.hi_bits == 0 || (s >> (32 - ps.hi_bits)) == (prefix >> (32 - ps.hi_bits));
+        if (match) atomicAdd(&sh[(s >> ps.shift) & (nb - 1)], 1u);
+    }
+    __syncthreads();
+    for (int b = threadIdx.x; b < nb; b += blockDim.x)
+        if (sh[b]) atomicAdd(&hist[(int64_t)j * kSelBins + b], sh[b]);
+}
+
+// one block per image: find the digit where the descending cumulative count crosses the remaining k
+__global__ void __launch_bounds__(256) select_pick_kernel(SelPass ps, uint32_t* __restrict__ state, uint32_t* __restrict__ hist) {
+    __shared__ uint32_t sh[kSelBins];
+    const int j = blockIdx.x;
+    uint32_t* st = state + 4 * j;
+    const int nb = 1 << ps.bits;
+    uint32_t* h = hist + (int64_t)j * kSelBins;
+    for (int b = threadIdx.x; b < nb; b += blockDim.x) {
+        sh[b] = h[b];
+        h[b] = 0;                       // ready for the next pass
+    }
+    __syncthreads();
+    if (threadIdx.x == 0 && !st[3]) {
+        uint32_t need = st[1];
+        int b = nb - 1;
+        for (; b > 0; --b) {
+            if (sh[b] >= need) break;
+            need -= sh[b];
+        }
+        st[0] |= (uint32_t)b << ps.shift;
+        st[1] = need;                   // how many to take from inside this bucket
+    }
+}
+
+// survivors: score bits > threshold always; == threshold: all of them (exact ties are cut after the ordering pass)
+__global__ void __launch_bounds__(256)
+select_compact_kernel(const cldet_candidate* __restrict__ cand, const uint64_t* __restrict__ keys,
+                      const int32_t* __restrict__ counts, int64_t capacity, uint32_t* __restrict__ state,
+                      cldet_candidate* __restrict__ out_cand, uint64_t* __restrict__ out_keys, int64_t out_capacity) {
+    __shared__ int warp_tot[8];
+    __shared__ int block_base;
+    const int j = blockIdx.y;
+    uint32_t* st = state + 4 * j;
+    const int64_t cnt = min64(counts[j], capacity);
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if ((int64_t)blockIdx.x * blockDim.x >= cnt) return;
+    const bool all = st[3] != 0;
+    const uint32_t thr = st[0];
+    bool take = false;
+    uint64_t key = 0;
+    if (i < cnt) {
+        key = keys[(int64_t)j * capacity + i];
+        take = all || (uint32_t)(key >> 32) >= thr;
+    }
+    const unsigned ballot = __ballot_sync(0xffffffffu, take);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) warp_tot[warp] = __popc(ballot);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int tot = 0;
+        for (int w = 0; w < 8; ++w) {
+            const int c = warp_tot[w];
+            warp_tot[w] = tot;
+            tot += c;
+        }
+        block_base = tot ? (int)atomicAdd(&st[2], (uint32_t)tot) : 0;
+    }
+    __syncthreads();
+    if (take) {
+        const int64_t slot = (int64_t)block_base + warp_tot[warp] + __popc(ballot & ((1u << lane) - 1u));
+        if (slot < out_capacity) {
+            out_cand[(int64_t)j * out_capacity + slot] = cand[(int64_t)j * capacity + i];
+            out_keys[(int64_t)j * out_capacity + slot] = key;
+        }
+    }
+}
+
+// Tiled rank sort: rank_i = #{ l : key_l > key_i } (keys are distinct).  Writes candidate i to position rank_i when
+// rank_i < limit (top-k cut), and the final count min(n, limit).
+__global__ void __launch_bounds__(256)
+rank_sort_kernel(const cldet_candidate* __restrict__ cand, const uint64_t* __restrict__ keys, const uint32_t* __restrict__ state,
+                 const int32_t* __restrict__ counts_in, int64_t in_capacity, int topk, cldet_candidate* __restrict__ sorted,
+                 int64_t out_capacity, int32_t* __restrict__ sorted_counts) {
+    __shared__ uint64_t tile[1024];
+    const int j = blockIdx.y;
+    int64_t n = state ? (int64_t)state[4 * j + 2] : (int64_t)counts_in[j];
+    n = min64(n, in_capacity);
+    const int64_t limit = (topk > 0) ? min64(n, topk) : n;
+    if (blockIdx.x == 0 && threadIdx.x == 0) sorted_counts[j] = (int32_t)min64(limit, out_capacity);
+    if ((int64_t)blockIdx.x * blockDim.x >= n) return;
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint64_t* k = keys + (int64_t)j * in_capacity;
+    const uint64_t mine = (i < n) ? k[i] : ~0ull;
+    int64_t rank = 0;
+    for (int64_t t0 = 0; t0 < n; t0 += 1024) {
+        const int m = (int)min64(1024, n - t0);
+        __syncthreads();
+        for (int t = threadIdx.x; t < m; t += blockDim.x) tile[t] = k[t0 + t];
+        __syncthreads();
+        int r = 0;
+#pragma unroll 8
+        for (int t = 0; t < m; ++t) r += (tile[t] > mine) ? 1 : 0;
+        rank += r;
+    }
+    if (i < n && rank < limit && rank < out_capacity) sorted[(int64_t)j * out_capacity + rank] = cand[(int64_t)j * in_capacity + i];
+}
+
+// ------------------------------------------------------------------------------------------------
+// K6: NMS.  (1) per-image max coordinate + mode (2) 64x64 suppression bitmask over the SORTED list
+// (3) sequential resolve, one block per image, 64 boxes per step.
+// nms_info per image: [0] max coordinate (float bits), [1] mode actually used (1 trick, 2 vanilla)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+nms_prepare_kernel(const cldet_candidate* __restrict__ sorted, const int32_t* __restrict__ counts, int64_t capacity, int mode,
+                   int64_t vanilla_numel_limit, uint32_t* __restrict__ info) {
+    __shared__ float red[8];
+    const int j = blockIdx.x;
+    const int n = (int)min64(counts[j], capacity);
+    float m = -INFINITY;
+    const cldet_candidate* c = sorted + (int64_t)j * capacity;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const cldet_candidate b = c[i];
+        m = fmaxf(m, fmaxf(fmaxf(b.x1, b.y1), fmaxf(b.x2, b.y2)));
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < 8; ++w) m = fmaxf(m, red[w]);
+        info[2 * j] = __float_as_uint(m);
+        int used = mode;
+        if (mode == 0) used = ((int64_t)n * 4 > vanilla_numel_limit) ? 2 : 1;   // torchvision ops/boxes.py batched_nms
+        info[2 * j + 1] = (uint32_t)used;
+    }
+}
+
+__device__ __forceinline__ bool suppresses(const float4 a, const float4 b, float thr) {
+    // torchvision nms: inter / ((area_a + area_b) - inter) > thr, all fp32, one rounding per op
+    const float area_a = (a.z - a.x) * (a.w - a.y);
+    const float area_b = (b.z - b.x) * (b.w - b.y);
+    const float w = fmaxf(fminf(a.z, b.z) - fmaxf(a.x, b.x), 0.0f);
+    const float h = fmaxf(fminf(a.w, b.w) - fmaxf(a.y, b.y), 0.0f);
+    const float inter = w * h;
+    if (!(inter > 0.0f)) return (inter / ((area_a + area_b) - inter)) > thr;   // 0/x or NaN: keep IEEE semantics
+    return __fdiv_rn(inter, (area_a + area_b) - inter) > thr;
+}
+
+__global__ void __launch_bounds__(64)
+nms_mask_kernel(const cldet_candidate* __restrict__ sorted, const int32_t* __restrict__ counts, int64_t capacity,
+                const uint32_t* __restrict__ info, float thr, uint64_t* __restrict__ mask, int64_t mask_stride_img,
+                int col_blocks_alloc) {
+    const int j = blockIdx.z;
+    const int n = (int)min64(counts[j], capacity);
+    const int row_blk = blockIdx.y, col_blk = blockIdx.x;
+    if (col_blk < row_blk) return;
+    if (row_blk * 64 >= n || col_blk * 64 >= n) return;
+    const int mode = (int)info[2 * j + 1];
+    const float off_unit = __uint_as_float(info[2 * j]) + 1.0f;       // max_coordinate + 1
+    const cldet_candidate* c = sorted + (int64_t)j * capacity;
+
+    __shared__ float4 cbox[64];
+    __shared__ int clab[64];
+    const int ci = col_blk * 64 + threadIdx.x;
+    if (ci < n) {
+        const cldet_candidate b = c[ci];
+        float4 v = make_float4(b.x1, b.y1, b.x2, b.y2);
+        if (mode == 1) {                                              // boxes + (label * (max + 1))[:, None]
+            const float off = (float)b.label * off_unit;
+            v.x += off; v.y += off; v.z += off; v.w += off;
+        }
+        cbox[threadIdx.x] = v;
+        clab[threadIdx.x] = b.label;
+    }
+    __syncthreads();
+    const int ri = row_blk * 64 + threadIdx.x;
+    if (ri >= n) return;
+    const cldet_candidate rb = c[ri];
+    float4 me = make_float4(rb.x1, rb.y1, rb.x2, rb.y2);
+    if (mode == 1) {
+        const float off = (float)rb.label * off_unit;
+        me.x += off; me.y += off; me.z += off; me.w += off;
+    }
+    const int ncol = min(64, n - col_blk * 64);
+    uint64_t bits = 0;
+    const int start = (row_blk == col_blk) ? threadIdx.x + 1 : 0;
+    for (int t = start; t < ncol; ++t) {
+        if (mode == 2 && clab[t] != rb.label) continue;
+        if (suppresses(me, cbox[t], thr)) bits |= 1ull << t;
+    }
+    mask[(int64_t)j * mask_stride_img + (int64_t)ri * col_blocks_alloc + col_blk] = bits;
+}
+
+__global__ void __launch_bounds__(256)
+nms_resolve_kernel(const int32_t* __restrict__ counts, int64_t capacity, const uint64_t* __restrict__ mask,
+                   int64_t mask_stride_img, int col_blocks_alloc, uint64_t* __restrict__ remv_ws, int32_t* __restrict__ keep,
+                   int32_t* __restrict__ keep_counts) {
+    __shared__ uint64_t kept_bits;
+    __shared__ int kept_total;
+    const int j = blockIdx.x;
+    const int n = (int)min64(counts[j], capacity);
+    const int col_blocks = (n + 63) / 64;
+    uint64_t* remv = remv_ws + (int64_t)j * col_blocks_alloc;
+    const uint64_t* m = mask + (int64_t)j * mask_stride_img;
+    for (int t = threadIdx.x; t < col_blocks; t += blockDim.x) remv[t] = 0;
+    if (threadIdx.x == 0) kept_total = 0;
+    __syncthreads();
+    for (int c = 0; c < col_blocks; ++c) {
+        const int rows = min(64, n - c * 64);
+        const int base = kept_total;     // written by lane 0 below, published by the barriers that end the iteration
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            const int lane = threadIdx.x;
+            // diagonal block words of rows lane and lane+32
+            const uint64_t d0 = (lane < rows) ? m[(int64_t)(c * 64 + lane) * col_blocks_alloc + c] : 0ull;
+            const uint64_t d1 = (lane + 32 < rows) ? m[(int64_t)(c * 64 + lane + 32) * col_blocks_alloc + c] : 0ull;
+            uint64_t cur = remv[c];
+            uint64_t kept = 0;
+            for (int b = 0; b < rows; ++b) {
+                const uint64_t w = __shfl_sync(0xffffffffu, (b < 32) ? d0 : d1, b & 31);
+                if (!((cur >> b) & 1ull)) {
+                    kept |= 1ull << b;
+                    cur |= w;
+                }
+            }
+            // ordered output of this chunk's survivors
+            const uint64_t lo_mask0 = (1ull << lane) - 1ull;
+            if ((kept >> lane) & 1ull) keep[(int64_t)j * capacity + base + __popcll(kept & lo_mask0)] = c * 64 + lane;
+            const uint64_t lo_mask1 = (1ull << (lane + 32)) - 1ull;
+            if ((kept >> (lane + 32)) & 1ull) keep[(int64_t)j * capacity + base + __popcll(kept & lo_mask1)] = c * 64 + lane + 32;
+            if (lane == 0) {
+                kept_bits = kept;
+                kept_total = base + __popcll(kept);
+            }
+        }
+        __syncthreads();
+        const uint64_t kept = kept_bits;
+        // every later column block absorbs the masks of the rows kept in this chunk
+        for (int t = c + 1 + threadIdx.x; t < col_blocks; t += blockDim.x) {
+            uint64_t acc = remv[t];
+            uint64_t k = kept;
+            while (k) {
+                const int b = __ffsll((long long)k) - 1;
+                k &= k - 1;
+                acc |= m[(int64_t)(c * 64 + b) * col_blocks_alloc + t];
+            }
+            remv[t] = acc;
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) keep_counts[j] = kept_total;
+}
+
+__global__ void __launch_bounds__(256)
+gather_detections_kernel(const cldet_candidate* __restrict__ sorted, const int32_t* __restrict__ keep,
+                         const int32_t* __restrict__ keep_counts, int64_t capacity, float* __restrict__ scores,
+                         int64_t* __restrict__ labels, float4* __restrict__ boxes) {
+    const int j = blockIdx.y;
+    const int n = (int)min64(keep_counts[j], capacity);
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const cldet_candidate c = sorted[(int64_t)j * capacity + keep[(int64_t)j * capacity + i]];
+    scores[(int64_t)j * capacity + i] = c.score;
+    labels[(int64_t)j * capacity + i] = (int64_t)c.label;
+    boxes[(int64_t)j * capacity + i] = make_float4(c.x1, c.y1, c.x2, c.y2);
+}
+
+// batched_nms on caller-provided arrays: pack -> (rank sort) -> NMS -> original indices
+__global__ void __launch_bounds__(256)
+pack_boxes_kernel(const float4* __restrict__ boxes, const float* __restrict__ scores, const int64_t* __restrict__ idxs, int64_t K,
+                  cldet_candidate* __restrict__ cand, uint64_t* __restrict__ keys, int32_t* __restrict__ count) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i == 0) *count = (int32_t)K;
+    if (i >= K) return;
+    const float4 b = boxes[i];
+    cldet_candidate c;
+    c.x1 = b.x; c.y1 = b.y; c.x2 = b.z; c.y2 = b.w;
+    c.score = scores[i];
+    c.label = idxs ? (int32_t)idxs[i] : 0;
+    c.anchor = (int32_t)i;
+    c.pad = 0;
+    cand[i] = c;
+    keys[i] = make_key(c.score, (int)i);
+}
+
+__global__ void __launch_bounds__(256)
+keep_to_original_kernel(const cldet_candidate* __restrict__ sorted, const int32_t* __restrict__ keep,
+                        const int32_t* __restrict__ keep_count, int64_t* __restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < *keep_count) out[i] = (int64_t)sorted[keep[i]].anchor;
+}
+
+static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+struct NmsWs {
+    uint32_t* info;
+    uint64_t* remv;
+    uint64_t* mask;
+    int col_blocks;
+    int64_t mask_stride_img;
+    size_t total;
+};
+
+static NmsWs nms_ws_layout(void* base, int N, int64_t max_count) {
+    NmsWs w;
+    w.col_blocks = (int)((max_count + 63) / 64);
+    if (w.col_blocks < 1) w.col_blocks = 1;
+    const int64_t rows = (int64_t)w.col_blocks * 64;
+    w.mask_stride_img = rows * w.col_blocks;
+    char* p = reinterpret_cast<char*>(base);
+    size_t off = 0;
+    w.info = reinterpret_cast<uint32_t*>(p + off);
+    off = align_up(off + (size_t)N * 2 * sizeof(uint32_t), 256);
+    w.remv = reinterpret_cast<uint64_t*>(p + off);
+    off = align_up(off + (size_t)N * w.col_blocks * sizeof(uint64_t), 256);
+    w.mask = reinterpret_cast<uint64_t*>(p + off);
+    off = align_up(off + (size_t)N * w.mask_stride_img * sizeof(uint64_t), 256);
+    w.total = off;
+    return w;
+}
+
+}  // namespace cldet
+
+using namespace cldet;
+
+extern "C" {
+
+int cldet_decode_boxes(const float* d_anchors, const float* d_reg, int num_images, int64_t num_anchors, int clip, int height,
+                       int width, float* d_boxes, void* stream) {
+    if (!d_anchors || !d_reg || !d_boxes || num_images <= 0 || num_anchors <= 0) return CLDET_ERR_INVALID_ARGUMENT;
+    const int64_t total = (int64_t)num_images * num_anchors;
+    const int blocks = (int)std::min<int64_t>((total + 255) / 256, (int64_t)sm_count() * 16);
+    if (clip)
+        decode_boxes_kernel<true><<<blocks, 256, 0, (cudaStream_t)stream>>>(
+            reinterpret_cast<const float4*>(d_anchors), reinterpret_cast<const float4*>(d_reg), num_anchors, total, (float)width,
+            (float)height, reinterpret_cast<float4*>(d_boxes));
+    else
+        decode_boxes_kernel<false><<<blocks, 256, 0, (cudaStream_t)stream>>>(
+            reinterpret_cast<const float4*>(d_anchors), reinterpret_cast<const float4*>(d_reg), num_anchors, total, (float)width,
+            (float)height, reinterpret_cast<float4*>(d_boxes));
+    CLDET_LAUNCH_CHECK();
+    return CLDET_OK;
+}
+
+int cldet_clip_boxes(float* d_boxes, int64_t num_boxes, int height, int width, void* stream) {
+    if (!d_boxes || num_boxes < 0) return CLDET_ERR_INVALID_ARGUMENT;
+    if (num_boxes == 0) return CLDET_OK;
+    const int blocks = (int)std::min<int64_t>((num_boxes + 255) / 256, (int64_t)sm_count() * 16);
+    clip_boxes_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<float4*>(d_boxes), num_boxes, (float)width,
+                                                                (float)height);
+    CLDET_LAUNCH_CHECK();
+    return CLDET_OK;
+}
+
+int cldet_decode_filter(const float* d_cls, int is_logits, const float* d_reg, const float* d_anchors, int num_images,
+                        int64_t num_anchors, int num_classes, int height, int width, float score_thresh,
+                        cldet_candidate* d_candidates, uint64_t* d_keys, int64_t capacity, int32_t* d_counts, void* stream) {
+    if (!d_cls || !d_reg || !d_anchors || !d_candidates || !d_keys || !d_counts) return CLDET_ERR_INVALID_ARGUMENT;
+    if (num_images <= 0 || num_images > 65535 || num_anchors <= 0 || num_classes <= 0 || capacity <= 0)
+        return CLDET_ERR_INVALID_ARGUMENT;
+    if (num_classes > kFilterMaxPartials) return CLDET_ERR_UNSUPPORTED;
+    const int vec = (num_classes % 4 == 0 && (((uintptr_t)d_cls) & 15) == 0) ? 4 : 1;
+    const int ppr = (num_classes + vec - 1) / vec;
+    int rows = std::min(kFilterThreads, std::max(1, kFilterMaxPartials / ppr));
+    if (rows > 64 && ppr >= 8) rows = 64;        // keep ~5 vectors per thread in flight for wide rows
+    // a pre-filter on the RAW maximum: a row can only pass if its best class probability exceeds the threshold
+    float prefilter;
+    if (is_logits) {
+        if (score_thresh <= 0.0f) prefilter = -INFINITY;
+        else if (score_thresh >= 1.0f) prefilter = INFINITY;
+        else prefilter = (float)(log((double)score_thresh / (1.0 - (double)score_thresh)) - 0.01);
+    } else {
+        prefilter = score_thresh;                // exact: the score IS the raw maximum
+    }
+    dim3 grid((unsigned)((num_anchors + rows - 1) / rows), (unsigned)num_images);
+    const size_t smem = (size_t)rows * ppr * sizeof(float);
+    cudaStream_t s = (cudaStream_t)stream;
+    if (vec == 4)
+        decode_filter_kernel<4><<<grid, kFilterThreads, smem, s>>>(
+            d_cls, is_logits, reinterpret_cast<const float4*>(d_reg), reinterpret_cast<const float4*>(d_anchors), num_anchors,
+            num_classes, rows, (float)width, (float)height, score_thresh, prefilter, d_candidates, d_keys, capacity, d_counts);
+    else
+        decode_filter_kernel<1><<<grid, kFilterThreads, smem, s>>>(
+            d_cls, is_logits, reinterpret_cast<const float4*>(d_reg), reinterpret_cast<const float4*>(d_anchors), num_anchors,
+            num_classes, rows, (float)width, (float)height, score_thresh, prefilter, d_candidates, d_keys, capacity, d_counts);
+    CLDET_LAUNCH_CHECK();
+    return CLDET_OK;
+}
+
+size_t cldet_sort_workspace_bytes(int num_images, int64_t max_count, int topk) {
+    if (num_images <= 0 || max_count < 0) return 0;
+    size_t off = align_up((size_t)num_images * 4 * sizeof(uint32_t), 256);            // select state
+    off = align_up(off + (size_t)num_images * kSelBins * sizeof(uint32_t), 256);      // histograms
+    if (topk > 0) {                                                                  // compacted survivors (with ties)
+        off = align_up(off + (size_t)num_images * max_count * sizeof(cldet_candidate), 256);
+        off = align_up(off + (size_t)num_images * max_count * sizeof(uint64_t), 256);
+    }
+    return off + 256;
+}
+
+int cldet_sort_candidates(const cldet_candidate* d_candidates, const uint64_t* d_keys, const int32_t* d_counts,
+                          int num_images, int64_t capacity, int64_t max_count, int topk, cldet_candidate* d_sorted,
+                          int64_t sorted_capacity, int32_t* d_sorted_counts, void* d_workspace, size_t workspace_bytes,
+                          void* stream) {
+    if (!d_candidates || !d_keys || !d_counts || !d_sorted || !d_sorted_counts || !d_workspace) return CLDET_ERR_INVALID_ARGUMENT;
+    if (num_images <= 0 || num_images > 65535 || capacity <= 0 || sorted_capacity <= 0) return CLDET_ERR_INVALID_ARGUMENT;
+    if (max_count > capacity) max_count = capacity;
+    if (max_count <= 0) {
+        CLDET_CUDA_TRY(cudaMemsetAsync(d_sorted_counts, 0, sizeof(int32_t) * num_images, (cudaStream_t)stream));
+        return CLDET_OK;
+    }
+    if (workspace_bytes < cldet_sort_workspace_bytes(num_images, max_count, topk)) return CLDET_ERR_WORKSPACE_TOO_SMALL;
+    cudaStream_t s = (cudaStream_t)stream;
+    char* p = reinterpret_cast<char*>(d_workspace);
+    uint32_t* state = reinterpret_cast<uint32_t*>(p);
+    size_t off = align_up((size_t)num_images * 4 * sizeof(uint32_t), 256);
+    uint32_t* hist = reinterpret_cast<uint32_t*>(p + off);
+    off = align_up(off + (size_t)num_images * kSelBins * sizeof(uint32_t), 256);
+    const int blocks_x = (int)std::min<int64_t>((max_count + 255) / 256, 4096);
+
+    if (topk > 0) {
+        cldet_candidate* sel_cand = reinterpret_cast<cldet_candidate*>(p + off);
+        off = align_up(off + (size_t)num_images * max_count * sizeof(cldet_candidate), 256);
+        uint64_t* sel_keys = reinterpret_cast<uint64_t*>(p + off);
+        select_init_kernel<<<num_images, 256, 0, s>>>(d_counts, capacity, topk, state, hist, num_images);
+        CLDET_LAUNCH_CHECK();
+        const SelPass passes[3] = {{21, 11, 0}, {10, 11, 11}, {0, 10, 22}};
+        for (int ps = 0; ps < 3; ++ps) {
+            dim3 g((unsigned)std::min(blocks_x, 64), (unsigned)num_images);
+            select_hist_kernel<<<g, 256, 0, s>>>(d_keys, d_counts, capacity, passes[ps], state, hist);
+            CLDET_LAUNCH_CHECK();
+            select_pick_kernel<<<num_images, 256, 0, s>>>(passes[ps], state, hist);
+            CLDET_LAUNCH_CHECK();
+        }
+        dim3 gc((unsigned)((max_count + 255) / 256), (unsigned)num_images);
+        select_compact_kernel<<<gc, 256, 0, s>>>(d_candidates, d_keys, d_counts, capacity, state, sel_cand, sel_keys, max_count);
+        CLDET_LAUNCH_CHECK();
+        rank_sort_kernel<<<gc, 256, 0, s>>>(sel_cand, sel_keys, state, nullptr, max_count, topk, d_sorted, sorted_capacity,
+                                             d_sorted_counts);
+        CLDET_LAUNCH_CHECK();
+    } else {
+        dim3 gc((unsigned)((max_count + 255) / 256), (unsigned)num_images);
+        rank_sort_kernel<<<gc, 256, 0, s>>>(d_candidates, d_keys, nullptr, d_counts, capacity, 0, d_sorted, sorted_capacity,
+                                             d_sorted_counts);
+        CLDET_LAUNCH_CHECK();
+    }
+    return CLDET_OK;
+}
+
+size_t cldet_nms_workspace_bytes(int num_images, int64_t max_count) {
+    if (num_images <= 0 || max_count < 0) return 0;
+    return nms_ws_layout(nullptr, num_images, max_count).total + 256;
+}
+
+int cldet_nms_sorted(const cldet_candidate* d_sorted, const int32_t* d_sorted_counts, int num_images, int64_t capacity,
+                     int64_t max_count, float iou_thresh, int mode, int64_t vanilla_numel_limit, int32_t* d_keep,
+                     int32_t* d_keep_counts, void* d_workspace, size_t workspace_bytes, void* stream) {
+    if (!d_sorted || !d_sorted_counts || !d_keep || !d_keep_counts || !d_workspace) return CLDET_ERR_INVALID_ARGUMENT;
+    if (num_images <= 0 || num_images > 65535 || capacity <= 0 || mode < 0 || mode > 2) return CLDET_ERR_INVALID_ARGUMENT;
+    if (max_count > capacity) max_count = capacity;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (max_count <= 0) {
+        CLDET_CUDA_TRY(cudaMemsetAsync(d_keep_counts, 0, sizeof(int32_t) * num_images, s));
+        return CLDET_OK;
+    }
+    if (workspace_bytes < cldet_nms_workspace_bytes(num_images, max_count)) return CLDET_ERR_WORKSPACE_TOO_SMALL;
+    const NmsWs w = nms_ws_layout(d_workspace, num_images, max_count);
+    if (w.col_blocks > 65535) return CLDET_ERR_UNSUPPORTED;
+    nms_prepare_kernel<<<num_images, 256, 0, s>>>(d_sorted, d_sorted_counts, capacity, mode, vanilla_numel_limit, w.info);
+    CLDET_LAUNCH_CHECK();
+    dim3 grid((unsigned)w.col_blocks, (unsigned)w.col_blocks, (unsigned)num_images);
+    nms_mask_kernel<<<grid, 64, 0, s>>>(d_sorted, d_sorted_counts, capacity, w.info, iou_thresh, w.mask, w.mask_stride_img,
+                                        w.col_blocks);
+    CLDET_LAUNCH_CHECK();
+    nms_resolve_kernel<<<num_images, 256, 0, s>>>(d_sorted_counts, capacity, w.mask, w.mask_stride_img, w.col_blocks, w.remv,
+                                                  d_keep, d_keep_counts);
+    CLDET_LAUNCH_CHECK();
+    return CLDET_OK;
+}
+
+int cldet_gather_detections(const cldet_candidate* d_sorted, const int32_t* d_keep, const int32_t* d_keep_counts,
+                            int num_images, int64_t capacity, int64_t max_keep, float* d_scores, int64_t* d_labels,
+                            float* d_boxes, void* stream) {
+    if (!d_sorted || !d_keep || !d_keep_counts || !d_scores || !d_labels || !d_boxes) return CLDET_ERR_INVALID_ARGUMENT;
+    if (num_images <= 0 || num_images > 65535 || capacity <= 0) return CLDET_ERR_INVALID_ARGUMENT;
+    if (max_keep > capacity) max_keep = capacity;
+    if (max_keep <= 0) return CLDET_OK;
+    dim3 grid((unsigned)((max_keep + 255) / 256), (unsigned)num_images);
+    gather_detections_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(d_sorted, d_keep, d_keep_counts, capacity, d_scores,
+                                                                    d_labels, reinterpret_cast<float4*>(d_boxes));
+    CLDET_LAUNCH_CHECK();
+    return CLDET_OK;
+}
+
+size_t cldet_batched_nms_workspace_bytes(int64_t num_boxes) {
+    if (num_boxes <= 0) return 256;
+    size_t off = 0;
+    off = align_up(off + (size_t)num_boxes * sizeof(cldet_candidate), 256);   // packed
+    off = align_up(off + (size_t)num_boxes * sizeof(uint64_t), 256);          // keys
+    off = align_up(off + (size_t)num_boxes * sizeof(cldet_candidate), 256);   // sorted
+    off = align_up(off + (size_t)num_boxes * sizeof(int32_t), 256);           // keep positions
+    off = align_up(off + 4 * sizeof(int32_t), 256);                           // counts
+    off += cldet_nms_workspace_bytes(1, num_boxes);
+    return off + 256;
+}
+
+int cldet_batched_nms(const float* d_boxes, const float* d_scores, const int64_t* d_idxs, int64_t num_boxes,
+                      float iou_thresh, int mode, int64_t vanilla_numel_limit, int64_t* d_keep, int32_t* d_keep_count,
+                      void* d_workspace, size_t workspace_bytes, void* stream) {
+    if (!d_keep_count || !d_workspace || num_boxes < 0 || mode < 0 || mode > 2) return CLDET_ERR_INVALID_ARGUMENT;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (num_boxes == 0) {
+        CLDET_CUDA_TRY(cudaMemsetAsync(d_keep_count, 0, sizeof(int32_t), s));
+        return CLDET_OK;
+    }
+    if (!d_boxes || !d_scores || !d_keep) return CLDET_ERR_INVALID_ARGUMENT;
+    if (num_boxes > 0x7fffffff) return CLDET_ERR_UNSUPPORTED;
+    if (workspace_bytes < cldet_batched_nms_workspace_bytes(num_boxes)) return CLDET_ERR_WORKSPACE_TOO_SMALL;
+    char* p = reinterpret_cast<char*>(d_workspace);
+    size_t off = 0;
+    cldet_candidate* packed = reinterpret_cast<cldet_candidate*>(p + off);
+    off = align_up(off + (size_t)num_boxes * sizeof(cldet_candidate), 256);
+    uint64_t* keys = reinterpret_cast<uint64_t*>(p + off);
+    off = align_up(off + (size_t)num_boxes * sizeof(uint64_t), 256);
+    cldet_candidate* sorted = reinterpret_cast<cldet_candidate*>(p + off);
+    off = align_up(off + (size_t)num_boxes * sizeof(cldet_candidate), 256);
+    int32_t* keep_pos = reinterpret_cast<int32_t*>(p + off);
+    off = align_up(off + (size_t)num_boxes * sizeof(int32_t), 256);
+    int32_t* cnts = reinterpret_cast<int32_t*>(p + off);   // [0] packed count, [1] sorted count
+    off = align_up(off + 4 * sizeof(int32_t), 256);
+    void* nms_ws = p + off;
+    const unsigned blocks = (unsigned)((num_boxes + 255) / 256);
+    pack_boxes_kernel<<<blocks, 256, 0, s>>>(reinterpret_cast<const float4*>(d_boxes), d_scores, d_idxs, num_boxes, packed, keys,
+                                             cnts);
+    CLDET_LAUNCH_CHECK();
+    dim3 g(blocks, 1);
+    rank_sort_kernel<<<g, 256, 0, s>>>(packed, keys, nullptr, cnts, num_boxes, 0, sorted, num_boxes, cnts + 1);
+    CLDET_LAUNCH_CHECK();
+    int rc = cldet_nms_sorted(sorted, cnts + 1, 1, num_boxes, num_boxes, iou_thresh, d_idxs ? mode : 1, vanilla_numel_limit,
+                              keep_pos, d_keep_count, nms_ws, workspace_bytes - off, stream);
+    if (rc) return rc;
+    keep_to_original_kernel<<<blocks, 256, 0, s>>>(sorted, keep_pos, d_keep_count, d_keep);
+    CLDET_LAUNCH_CHECK();
+    return CLDET_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,639 @@
+// K3: fused focal-loss + smooth-L1 forward AND backward in one pass over the [N,A,C] probabilities.
+// Reference: FocalLoss.forward, retinanet/losses.py:252-452, and the autograd graph it records.
+//
+// HBM traffic per image: read p (4 B/elt) + write dL/dp (4 B/elt) + 4 B/anchor assignment word
+// + 16 B/anchor dL/dreg write; regression inputs are touched for positive anchors only.
+// The dense [A,C] target matrix, the [A,G] IoU matrix and the ~25 elementwise temporaries of the
+// reference never exist.
+//
+// Parallel layout: grid = (blocks_per_image, N).  A block owns a contiguous chunk of anchors of ONE
+// image, so every reduction it produces belongs to one image: warp shuffle -> shared -> one partial
+// per block -> the last block of the image (threadfence + counter) adds the partials in a fixed order
+// in fp64.  Results are bit-reproducible run to run; there are no floating-point atomics.
+#include <math.h>
+
+#include "cldet_common.cuh"
+
+namespace cldet {
+
+constexpr int kLossThreads = 256;
+constexpr int kUnroll = 4;
+
+struct LossArgs {
+    const float* cls;
+    const float* reg;
+    const float4* anchors;
+    const float* ann;
+    int N;
+    int64_t A;
+    int C;
+    int G;
+    cldet_loss_params p;
+    const float* weights;        // [4][N] or null
+    const float* baked_weights;  // reweight mode only
+    float* gcls;
+    float* greg;
+    float* losses;               // [4][N]
+    const uint32_t* meta;
+    const float* iou_max;
+    const int32_t* npos;
+    uint8_t* bg_mask;
+    int32_t* status;
+    float* partials;             // [N][bpi][4]
+    unsigned int* counters;      // [N]
+    int anchors_per_block;
+    int bpi;
+    uint32_t div_magic;          // floor(2^32 / C) + 1, or 0 -> use a real division
+};
+
+// ln(q) for normal positive q (here q in [1e-4, 1]).  Range reduction to m in [2/3, 4/3), then
+// log1p(m-1) = f - f^2/2 + f^3 * P(f), P of degree 5 (least-squares minimax fit, 2.7e-7 max relative
+// error of the whole function in fp32 -- well inside the 1e-5 contract; libdevice logf costs ~2x).
+__device__ __forceinline__ float log_fast(float q) {
+    const int i = __float_as_int(q);
+    const int e = (i - 0x3f2aaaab) & 0xff800000;
+    const float m = __int_as_float(i - e);
+    const float fe = (float)(e >> 23);
+    const float f = m - 1.0f;
+    const float s = f * f;
+    float r = -1.492298990e-01f;
+    r = fmaf(r, f, 1.699251682e-01f);
+    r = fmaf(r, f, -1.650529057e-01f);
+    r = fmaf(r, f, 1.981773674e-01f);
+    r = fmaf(r, f, -2.500296831e-01f);
+    r = fmaf(r, f, 3.333675861e-01f);
+    r = fmaf(r, f, -0.5f);
+    r = fmaf(r, s, f);
+    return fmaf(fe, 0.693147182f, r);
+}
+
+template <bool GAMMA2>
+__device__ __forceinline__ void pow_and_dpow(float x, float gamma, float& pw, float& dpw) {
+    if (GAMMA2) {
+        pw = x * x;          // ATen evaluates pow(x, 2.0) as x*x
+        dpw = 2.0f * x;
+    } else {
+        pw = powf(x, gamma);
+        dpw = gamma * powf(x, gamma - 1.0f);
+    }
+}
+
+// Element with target 0 (losses.py:344-377 with t == 0):  l = a * p^g * (-ln(1-p)),
+// dl/dp = a * (g p^(g-1) * (-ln(1-p)) + p^g / (1-p)), zero outside the clamp pass-band [1e-4, 1-1e-4].
+template <bool GAMMA2, bool GRAD>
+__device__ __forceinline__ void neg_element(float p_raw, float alpha, float gamma, float scale, float& loss, float& grad) {
+    const float p = fminf(fmaxf(p_raw, 1e-4f), 0.9999f);
+    const float q = 1.0f - p;
+    const float nl = -log_fast(q);
+    float pw, dpw;
+    pow_and_dpow<GAMMA2>(p, gamma, pw, dpw);
+    loss = (alpha * pw) * nl;
+    if (GRAD) {
+        const float g = alpha * fmaf(dpw, nl, __fdividef(pw, q)) * scale;
+        grad = (p == p_raw) ? g : 0.0f;
+    }
+}
+
+// Element with target 1.  f is the focal-weight base of the three reference branches (losses.py:352-366).
+template <bool GAMMA2, bool GRAD>
+__device__ __forceinline__ void pos_element(float p_raw, const cldet_loss_params& lp, float iou_max, float scale,
+                                            float& loss, float& grad) {
+    const float p = fminf(fmaxf(p_raw, 1e-4f), 0.9999f);
+    float f, df;
+    if (!lp.incremental) {
+        f = 1.0f - p;
+        df = -1.0f;
+    } else if (lp.decrease_positive_by_iou) {
+        f = 1.0f - p;
+        df = -1.0f;
+        if (iou_max <= 0.7f) {                                           // mid_indices, losses.py:354
+            const float upper = fminf(fmaxf(iou_max + 0.2f, 1e-4f), 0.9999f);   // :361
+            if (p >= upper) {
+                f = 1e-4f;
+                df = 0.0f;
+            } else {
+                f = fabsf(p - upper);
+                df = -1.0f;                                              // sign(p - upper), p < upper
+            }
+        }
+    } else {
+        const float s = lp.decrease_positive;                            // :365-366
+        f = s - fminf(fmaxf(p, 0.0f), s);
+        df = (p >= 0.0f && p <= s) ? -1.0f : 0.0f;
+    }
+    const float nl = -logf(p);
+    float pw, dpw;
+    pow_and_dpow<GAMMA2>(f, lp.gamma, pw, dpw);
+    loss = (lp.alpha * pw) * nl;
+    if (GRAD) {
+        const float g = lp.alpha * (dpw * df * nl - pw / p) * scale;
+        grad = (p == p_raw) ? g : 0.0f;
+    }
+}
+
+struct ImageScales {
+    float s_bg;     // dL/dbg_j / max(npos,1)
+    float s_fg;
+    float s_reg;    // dL/dreg_j / (4 npos)
+    float s_enh;
+    float n;        // max(npos, 1)
+    int npos;
+};
+
+struct Acc {
+    float bg, fg, reg, enh;
+};
+
+// One element of the classification map.  `c` is the class column, `m` the anchor's assignment word.
+template <bool GAMMA2, bool VARIANTS, bool GRAD>
+__device__ __forceinline__ float cls_element(float p_raw, int c, uint32_t m, const LossArgs& a, const ImageScales& sc,
+                                             float iou_max, Acc& acc) {
+    const uint32_t st = meta_state(m);
+    float loss = 0.0f, grad = 0.0f;
+    if (st == CLDET_STATE_IGNORE) return 0.0f;
+    if (st == CLDET_STATE_EMPTY) {                       // losses.py:292-303: (1 - alpha), not normalised (n == 1)
+        neg_element<GAMMA2, GRAD>(p_raw, 1.0f - a.p.alpha, a.p.gamma, sc.s_bg, loss, grad);
+        acc.bg += loss;
+        return grad;
+    }
+    if (st == CLDET_STATE_POS) {
+        if ((uint32_t)c == meta_label(m)) {
+            pos_element<GAMMA2, GRAD>(p_raw, a.p, iou_max, sc.s_fg, loss, grad);
+            acc.fg += loss;
+            return grad;
+        }
+        neg_element<GAMMA2, GRAD>(p_raw, a.p.alpha, a.p.gamma, sc.s_bg, loss, grad);
+        acc.bg += loss;
+        return grad;
+    }
+    // background anchor
+    if (VARIANTS) {
+        const int past = a.p.past_class_num;
+        const bool old_col = c < past;
+        bool counted = true;
+        if (a.p.incremental && a.p.ignore_past_class && old_col)          // losses.py:319-327
+            counted = a.p.new_ignore_past_class && (m & CLDET_META_OLD_ACTIVE);
+        if (counted) {
+            neg_element<GAMMA2, GRAD>(p_raw, a.p.alpha, a.p.gamma, sc.s_bg, loss, grad);
+            acc.bg += loss;
+        }
+        if (a.p.incremental && a.p.enhance_on_new && !old_col) {          // losses.py:380-384
+            const float p = fminf(fmaxf(p_raw, 1e-4f), 0.9999f);
+            if (p > 0.05f) {
+                acc.enh += p * p;
+                if (GRAD && p == p_raw) grad += 2.0f * p * sc.s_enh;
+            }
+        }
+        return grad;
+    }
+    neg_element<GAMMA2, GRAD>(p_raw, a.p.alpha, a.p.gamma, sc.s_bg, loss, grad);
+    acc.bg += loss;
+    return grad;
+}
+
+__device__ __forceinline__ uint32_t fast_div(uint32_t x, uint32_t c, uint32_t magic) {
+    return magic ? __umulhi(x, magic) : x / c;
+}
+
+// Smooth-L1 on one positive anchor (losses.py:276-280, 398-437).  Returns the 4 losses summed; writes d/dreg.
+template <bool GRAD>
+__device__ __forceinline__ float reg_anchor(const LossArgs& a, int j, int64_t anchor, uint32_t m, float s_reg, float4& g) {
+    const float4 an = a.anchors[anchor];
+    const float* gt = a.ann + ((int64_t)j * a.G + meta_row(m)) * 5;
+    const float4 r = *reinterpret_cast<const float4*>(a.reg + ((int64_t)j * a.A + anchor) * 4);
+    // anchor geometry, reference op order, no contraction
+    const float aw = __fsub_rn(an.z, an.x);
+    const float ah = __fsub_rn(an.w, an.y);
+    const float acx = __fadd_rn(an.x, __fmul_rn(0.5f, aw));
+    const float acy = __fadd_rn(an.y, __fmul_rn(0.5f, ah));
+    float gw = __fsub_rn(gt[2], gt[0]);
+    float gh = __fsub_rn(gt[3], gt[1]);
+    const float gcx = __fadd_rn(gt[0], __fmul_rn(0.5f, gw));   // centre from the UN-clamped size (quirk Q4)
+    const float gcy = __fadd_rn(gt[1], __fmul_rn(0.5f, gh));
+    gw = fmaxf(gw, 1.0f);
+    gh = fmaxf(gh, 1.0f);
+    float t[4];
+    t[0] = __fdiv_rn(__fdiv_rn(__fsub_rn(gcx, acx), aw), 0.1f);
+    t[1] = __fdiv_rn(__fdiv_rn(__fsub_rn(gcy, acy), ah), 0.1f);
+    t[2] = __fdiv_rn(logf(__fdiv_rn(gw, aw)), 0.2f);
+    t[3] = __fdiv_rn(logf(__fdiv_rn(gh, ah)), 0.2f);
+    const float rr[4] = {r.x, r.y, r.z, r.w};
+    float gg[4];
+    float sum = 0.0f;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const float e = __fsub_rn(t[i], rr[i]);
+        const float d = fabsf(e);
+        const bool small = d <= (1.0f / 9.0f);
+        sum += small ? 4.5f * (d * d) : d - (0.5f / 9.0f);
+        if (GRAD) {
+            const float mag = small ? 9.0f * d : 1.0f;
+            const float sgn = (e > 0.0f) ? -1.0f : ((e < 0.0f) ? 1.0f : 0.0f);   // d|e|/dr = -sign(e)
+            gg[i] = sgn * mag * s_reg;
+        }
+    }
+    if (GRAD) g = make_float4(gg[0], gg[1], gg[2], gg[3]);
+    return sum;
+}
+
+// weights are stored [4][N]: row 0 dL/dbg_j, 1 dL/dfg_j, 2 dL/dreg_j, 3 dL/d(enhance term)
+__device__ __forceinline__ ImageScales image_scales(const float* w, int N, int j, int npos) {
+    ImageScales sc;
+    sc.npos = npos;
+    sc.n = fmaxf((float)npos, 1.0f);
+    if (w) {
+        sc.s_bg = w[j] / sc.n;
+        sc.s_fg = w[N + j] / sc.n;
+        sc.s_reg = npos > 0 ? w[2 * N + j] / (4.0f * (float)npos) : 0.0f;
+        sc.s_enh = w[3 * N + j];
+    } else {
+        sc.s_bg = sc.s_fg = sc.s_reg = sc.s_enh = 0.0f;
+    }
+    return sc;
+}
+
+// mode 0: everything (regression + classification, losses + grads)
+// mode 1: gradients only, classification + regression   (reweight: bg weight changed)
+// mode 2: gradients only, positive anchors only          (reweight: only fg / reg weight changed)
+template <int VEC, bool GAMMA2, bool VARIANTS, bool GRAD>
+__device__ __forceinline__ void process_chunk(const LossArgs& a, int j, int64_t a0, int64_t a1, const ImageScales& sc,
+                                              int mode, Acc& acc) {
+    const int tid = threadIdx.x;
+    const uint32_t* meta_j = a.meta + (int64_t)j * a.A;
+    const bool need_iou = VARIANTS && a.p.incremental && a.p.decrease_positive_by_iou;
+
+    // ---- regression rows + bg mask: one thread per anchor ----
+    for (int64_t an = a0 + tid; an < a1; an += kLossThreads) {
+        const uint32_t m = meta_j[an];
+        const uint32_t st = meta_state(m);
+        if (mode == 0 && a.bg_mask) a.bg_mask[(int64_t)j * a.A + an] = (st != CLDET_STATE_POS) ? 1 : 0;
+        float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (st == CLDET_STATE_POS) {
+            acc.reg += reg_anchor<GRAD>(a, j, an, m, sc.s_reg, g);
+            if (mode == 0 && a.status && meta_label(m) == CLDET_BAD_LABEL) *a.status = 1;
+            if (mode == 2 && GRAD) {
+                // only the target-1 element of this row depends on the fg weight
+                const uint32_t c = meta_label(m);
+                if (c < (uint32_t)a.C) {
+                    const int64_t idx = ((int64_t)j * a.A + an) * a.C + c;
+                    float l, gr;
+                    pos_element<GAMMA2, true>(a.cls[idx], a.p, need_iou ? a.iou_max[(int64_t)j * a.A + an] : 1.0f, sc.s_fg, l, gr);
+                    a.gcls[idx] = gr;
+                }
+            }
+        }
+        if (GRAD && (mode != 2 || st == CLDET_STATE_POS))
+            *reinterpret_cast<float4*>(a.greg + ((int64_t)j * a.A + an) * 4) = g;
+    }
+    if (mode == 2) return;
+
+    // ---- classification map: flat vectorised sweep over this chunk's (a1-a0)*C elements ----
+    const int64_t base = ((int64_t)j * a.A + a0) * a.C;
+    const uint32_t count = (uint32_t)((a1 - a0) * a.C);
+    const uint32_t C = (uint32_t)a.C;
+    if (VEC == 4) {
+        const float4* src = reinterpret_cast<const float4*>(a.cls + base);
+        float4* dst = GRAD ? reinterpret_cast<float4*>(a.gcls + base) : nullptr;
+        const uint32_t nvec = count >> 2;
+        for (uint32_t v0 = tid; v0 < nvec; v0 += kLossThreads * kUnroll) {
+            float4 x[kUnroll];
+            uint32_t mm[kUnroll];
+            uint32_t col[kUnroll];
+            uint32_t row[kUnroll];
+#pragma unroll
+            for (int u = 0; u < kUnroll; ++u) {
+                const uint32_t v = v0 + u * kLossThreads;
+                if (v < nvec) {
+                    const uint32_t e0 = v << 2;
+                    row[u] = fast_div(e0, C, a.div_magic);
+                    col[u] = e0 - row[u] * C;
+                    mm[u] = meta_j[a0 + row[u]];
+                    // ignored anchors contribute nothing: do not even read their probabilities
+                    if (meta_state(mm[u]) != CLDET_STATE_IGNORE) x[u] = ld_stream_f4(src + v);
+                    else x[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < kUnroll; ++u) {
+                const uint32_t v = v0 + u * kLossThreads;
+                if (v < nvec) {
+                    float iou = 1.0f;
+                    if (need_iou && meta_state(mm[u]) == CLDET_STATE_POS) iou = a.iou_max[(int64_t)j * a.A + a0 + row[u]];
+                    float4 g;
+                    g.x = cls_element<GAMMA2, VARIANTS, GRAD>(x[u].x, (int)col[u] + 0, mm[u], a, sc, iou, acc);
+                    g.y = cls_element<GAMMA2, VARIANTS, GRAD>(x[u].y, (int)col[u] + 1, mm[u], a, sc, iou, acc);
+                    g.z = cls_element<GAMMA2, VARIANTS, GRAD>(x[u].z, (int)col[u] + 2, mm[u], a, sc, iou, acc);
+                    g.w = cls_element<GAMMA2, VARIANTS, GRAD>(x[u].w, (int)col[u] + 3, mm[u], a, sc, iou, acc);
+                    if (GRAD) st_stream_f4(dst + v, g);
+                }
+            }
+        }
+    } else {
+        const float* src = a.cls + base;
+        float* dst = GRAD ? a.gcls + base : nullptr;
+        for (uint32_t e = tid; e < count; e += kLossThreads) {
+            const uint32_t row = fast_div(e, C, a.div_magic);
+            const uint32_t col = e - row * C;
+            const uint32_t m = meta_j[a0 + row];
+            float iou = 1.0f;
+            if (need_iou && meta_state(m) == CLDET_STATE_POS) iou = a.iou_max[(int64_t)j * a.A + a0 + row];
+            const float g = cls_element<GAMMA2, VARIANTS, GRAD>(src[e], (int)col, m, a, sc, iou, acc);
+            if (GRAD) dst[e] = g;
+        }
+    }
+}
+
+template <int VEC, bool GAMMA2, bool VARIANTS, bool GRAD>
+__global__ void __launch_bounds__(kLossThreads) focal_loss_kernel(const LossArgs a) {
+    __shared__ float red[4][kLossThreads / 32];
+    __shared__ double fin[4][kLossThreads / 32];
+    __shared__ bool is_last;
+
+    const int j = blockIdx.y;
+    const int64_t a0 = (int64_t)blockIdx.x * a.anchors_per_block;
+    const int64_t a1 = min(a.A, a0 + a.anchors_per_block);
+    const int npos = a.npos[j];
+    const ImageScales sc = image_scales(a.weights, a.N, j, npos);
+
+    Acc acc = {0.f, 0.f, 0.f, 0.f};
+    process_chunk<VEC, GAMMA2, VARIANTS, GRAD>(a, j, a0, a1, sc, 0, acc);
+
+    // block reduction of the four sums
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float v[4] = {warp_sum(acc.bg), warp_sum(acc.fg), warp_sum(acc.reg), warp_sum(acc.enh)};
+    if (lane == 0) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) red[k][warp] = v[k];
+    }
+    __syncthreads();
+    if (threadIdx.x < 4) {
+        float s = 0.f;
+#pragma unroll
+        for (int w = 0; w < kLossThreads / 32; ++w) s += red[threadIdx.x][w];
+        a.partials[((int64_t)j * a.bpi + blockIdx.x) * 4 + threadIdx.x] = s;
+        __threadfence();
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned int done = atomicAdd(&a.counters[j], 1u);
+        is_last = (done == (unsigned int)a.bpi - 1u);
+    }
+    __syncthreads();
+    if (!is_last) return;
+
+    // last block of image j: fixed-order fp64 sum of the per-block partials
+    __threadfence();
+    double s[4] = {0.0, 0.0, 0.0, 0.0};
+    const volatile float* part = a.partials + (int64_t)j * a.bpi * 4;
+    for (int b = threadIdx.x; b < a.bpi; b += kLossThreads) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) s[k] += (double)part[b * 4 + k];
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s[k] += __shfl_xor_sync(0xffffffffu, s[k], o);
+        if (lane == 0) fin[k][warp] = s[k];
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t[4] = {0.0, 0.0, 0.0, 0.0};
+        for (int w = 0; w < kLossThreads / 32; ++w) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) t[k] += fin[k][w];
+        }
+        float* out = a.losses + j;                                     // [4][N]
+        out[0] = (float)t[0] / sc.n;                                  // losses.py:395
+        out[a.N] = (float)t[1] / sc.n;                                // :396
+        out[2 * a.N] = npos > 0 ? (float)(t[2] / (4.0 * (double)npos)) : 0.0f;   // :437 mean over npos*4
+        out[3 * a.N] = (float)t[3];
+        a.counters[j] = 0;                                            // ready for the next call
+    }
+}
+
+// Backward with weights that differ from the ones baked in by the forward pass (see cldet.h).
+template <int VEC, bool GAMMA2, bool VARIANTS>
+__global__ void __launch_bounds__(kLossThreads) focal_reweight_kernel(const LossArgs a) {
+    const int j = blockIdx.y;
+    const float* wn = a.weights + j;
+    const float* wo = a.baked_weights + j;
+    const int N = a.N;
+    const bool bg_changed = (wn[0] != wo[0]) || (wn[3 * N] != wo[3 * N]);
+    const bool pos_changed = (wn[N] != wo[N]) || (wn[2 * N] != wo[2 * N]);
+    if (!bg_changed && !pos_changed) return;
+    const int64_t a0 = (int64_t)blockIdx.x * a.anchors_per_block;
+    const int64_t a1 = min(a.A, a0 + a.anchors_per_block);
+    const ImageScales sc = image_scales(a.weights, a.N, j, a.npos[j]);
+    Acc acc = {0.f, 0.f, 0.f, 0.f};
+    process_chunk<VEC, GAMMA2, VARIANTS, true>(a, j, a0, a1, sc, bg_changed ? 1 : 2, acc);
+}
+
+__global__ void copy_weights_kernel(const float* __restrict__ src, float* __restrict__ dst, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[i] = src[i];
+}
+
+// new_ignore_past_class pre-pass (losses.py:326-327): flag background anchors whose clamped old-class
+// probabilities sum to < 0.5.  fp32 sequential sum in column order.
+__global__ void __launch_bounds__(256) old_class_flag_kernel(const float* __restrict__ cls, int64_t A, int C, int past,
+                                                             uint32_t* __restrict__ meta) {
+    const int j = blockIdx.y;
+    const int64_t an = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (an >= A) return;
+    uint32_t m = meta[(int64_t)j * A + an] & ~CLDET_META_OLD_ACTIVE;
+    if (meta_state(m) == CLDET_STATE_BG) {
+        const float* row = cls + ((int64_t)j * A + an) * C;
+        float s = 0.0f;
+        for (int c = 0; c < past; ++c) s = __fadd_rn(s, fminf(fmaxf(row[c], 1e-4f), 0.9999f));
+        if (s < 0.5f) m |= CLDET_META_OLD_ACTIVE;
+    }
+    meta[(int64_t)j * A + an] = m;
+}
+
+struct LossPlan {
+    int anchors_per_block;
+    int bpi;
+    uint32_t div_magic;
+};
+
+static LossPlan make_plan(int N, int64_t A, int C) {
+    LossPlan pl;
+    int64_t apb = (32768 / C + 31) / 32 * 32;            // ~8k float4 per block
+    if (apb < 32) apb = 32;
+    if (apb > 4096) apb = 4096;
+    // small problems: keep at least ~4 blocks per SM in flight
+    const int64_t want_blocks = (int64_t)sm_count() * 4;
+    int64_t cap = ((int64_t)N * A / want_blocks + 31) / 32 * 32;
+    if (cap < 32) cap = 32;
+    if (apb > cap) apb = cap;
+    pl.anchors_per_block = (int)apb;
+    pl.bpi = (int)((A + apb - 1) / apb);
+    const uint64_t span = (uint64_t)apb * C;              // largest dividend + 1
+    const uint64_t magic = (1ull << 32) / (uint64_t)C + 1;
+    // __umulhi(x, magic) == x / C for all x < span iff span * (magic*C - 2^32) < 2^32
+    pl.div_magic = (span * (magic * (uint64_t)C - (1ull << 32)) < (1ull << 32) && magic < (1ull << 32)) ? (uint32_t)magic : 0u;
+    return pl;
+}
+
+struct Workspace {
+    float* partials;
+    unsigned int* counters;
+};
+
+static size_t workspace_bytes(int N, int64_t A) {
+    // worst case bpi: 32 anchors per block
+    const int64_t max_bpi = (A + 31) / 32;
+    return (size_t)N * max_bpi * 4 * sizeof(float) + (size_t)N * sizeof(unsigned int) + 256;
+}
+
+template <int VEC, bool GAMMA2, bool VARIANTS>
+static void launch_loss(const LossArgs& a, bool grad, dim3 grid, cudaStream_t s) {
+    if (grad) focal_loss_kernel<VEC, GAMMA2, VARIANTS, true><<<grid, kLossThreads, 0, s>>>(a);
+    else focal_loss_kernel<VEC, GAMMA2, VARIANTS, false><<<grid, kLossThreads, 0, s>>>(a);
+}
+
+template <int VEC>
+static void dispatch_loss(const LossArgs& a, bool grad, bool gamma2, bool variants, dim3 grid, cudaStream_t s) {
+    if (gamma2) {
+        if (variants) launch_loss<VEC, true, true>(a, grad, grid, s);
+        else launch_loss<VEC, true, false>(a, grad, grid, s);
+    } else {
+        if (variants) launch_loss<VEC, false, true>(a, grad, grid, s);
+        else launch_loss<VEC, false, false>(a, grad, grid, s);
+    }
+}
+
+template <int VEC>
+static void dispatch_reweight(const LossArgs& a, bool gamma2, bool variants, dim3 grid, cudaStream_t s) {
+    if (gamma2) {
+        if (variants) focal_reweight_kernel<VEC, true, true><<<grid, kLossThreads, 0, s>>>(a);
+        else focal_reweight_kernel<VEC, true, false><<<grid, kLossThreads, 0, s>>>(a);
+    } else {
+        if (variants) focal_reweight_kernel<VEC, false, true><<<grid, kLossThreads, 0, s>>>(a);
+        else focal_reweight_kernel<VEC, false, false><<<grid, kLossThreads, 0, s>>>(a);
+    }
+}
+
+static bool has_variants(const cldet_loss_params& p) {
+    return p.incremental && (p.ignore_past_class || p.decrease_positive_by_iou || p.enhance_on_new ||
+                             p.decrease_positive != 1.0f);
+}
+
+static int check_common(const float* d_cls, const float* d_anchors, const float* d_annotations, int N, int64_t A, int C, int G,
+                        const cldet_loss_params* params) {
+    if (!d_cls || !d_anchors || !d_annotations || !params) return CLDET_ERR_INVALID_ARGUMENT;
+    if (N <= 0 || N > 65535 || A <= 0 || C <= 0 || C > CLDET_MAX_CLASSES || G <= 0 || G > CLDET_MAX_GT_ROWS)
+        return CLDET_ERR_INVALID_ARGUMENT;
+    if (A * (int64_t)C >= (1ll << 40)) return CLDET_ERR_INVALID_ARGUMENT;
+    if (params->incremental && (params->past_class_num < 0 || params->past_class_num > C)) return CLDET_ERR_INVALID_ARGUMENT;
+    return CLDET_OK;
+}
+
+}  // namespace cldet
+
+using namespace cldet;
+
+extern "C" {
+
+size_t cldet_focal_loss_workspace_bytes(int num_images, int64_t num_anchors) {
+    if (num_images <= 0 || num_anchors <= 0) return 0;
+    return workspace_bytes(num_images, num_anchors);
+}
+
+int cldet_focal_loss_from_assignment(const float* d_cls, const float* d_reg, const float* d_anchors,
+                                     const float* d_annotations, int num_images, int64_t num_anchors, int num_classes,
+                                     int gt_rows, const cldet_loss_params* params, const float* d_weights,
+                                     float* d_grad_cls, float* d_grad_reg, float* d_losses, uint32_t* d_meta,
+                                     const float* d_iou_max, const int32_t* d_npos, uint8_t* d_bg_mask, int32_t* d_status,
+                                     void* d_workspace, size_t ws_bytes, void* stream) {
+    int rc = check_common(d_cls, d_anchors, d_annotations, num_images, num_anchors, num_classes, gt_rows, params);
+    if (rc) return rc;
+    if (!d_reg || !d_losses || !d_meta || !d_npos || !d_workspace) return CLDET_ERR_INVALID_ARGUMENT;
+    const bool grad = d_weights != nullptr;
+    if (grad != (d_grad_cls != nullptr) || grad != (d_grad_reg != nullptr)) return CLDET_ERR_INVALID_ARGUMENT;
+    if (params->incremental && params->decrease_positive_by_iou && !d_iou_max) return CLDET_ERR_INVALID_ARGUMENT;
+    if (ws_bytes < workspace_bytes(num_images, num_anchors)) return CLDET_ERR_WORKSPACE_TOO_SMALL;
+    if (((uintptr_t)d_cls | (uintptr_t)d_grad_cls | (uintptr_t)d_reg | (uintptr_t)d_grad_reg | (uintptr_t)d_anchors) & 15)
+        return CLDET_ERR_INVALID_ARGUMENT;
+    cudaStream_t s = (cudaStream_t)stream;
+
+    const LossPlan pl = make_plan(num_images, num_anchors, num_classes);
+    LossArgs a;
+    a.cls = d_cls; a.reg = d_reg; a.anchors = reinterpret_cast<const float4*>(d_anchors); a.ann = d_annotations;
+    a.N = num_images; a.A = num_anchors; a.C = num_classes; a.G = gt_rows; a.p = *params;
+    a.weights = d_weights; a.baked_weights = nullptr; a.gcls = d_grad_cls; a.greg = d_grad_reg; a.losses = d_losses;
+    a.meta = d_meta; a.iou_max = d_iou_max; a.npos = d_npos; a.bg_mask = d_bg_mask; a.status = d_status;
+    // workspace layout: [counters N | pad to 256 B | partials]
+    a.counters = reinterpret_cast<unsigned int*>(d_workspace);
+    const size_t off = ((size_t)num_images * sizeof(unsigned int) + 255) / 256 * 256;
+    a.partials = reinterpret_cast<float*>(reinterpret_cast<char*>(d_workspace) + off);
+    a.anchors_per_block = pl.anchors_per_block; a.bpi = pl.bpi; a.div_magic = pl.div_magic;
+
+    const bool variants = has_variants(*params);
+    if (params->incremental && params->ignore_past_class && params->new_ignore_past_class && params->past_class_num > 0) {
+        dim3 g((unsigned)((num_anchors + 255) / 256), (unsigned)num_images);
+        old_class_flag_kernel<<<g, 256, 0, s>>>(d_cls, num_anchors, num_classes, params->past_class_num, d_meta);
+        CLDET_LAUNCH_CHECK();
+    }
+    dim3 grid((unsigned)pl.bpi, (unsigned)num_images);
+    const bool gamma2 = params->gamma == 2.0f;
+    if (num_classes % 4 == 0) dispatch_loss<4>(a, grad, gamma2, variants, grid, s);
+    else dispatch_loss<1>(a, grad, gamma2, variants, grid, s);
+    CLDET_LAUNCH_CHECK();
+    return CLDET_OK;
+}
+
+int cldet_focal_loss(const float* d_cls, const float* d_reg, const float* d_anchors, const float* d_annotations,
+                     int num_images, int64_t num_anchors, int num_classes, int gt_rows,
+                     const cldet_loss_params* params, const float* d_weights,
+                     float* d_grad_cls, float* d_grad_reg, float* d_losses,
+                     uint32_t* d_meta, float* d_iou_max, int32_t* d_npos, int32_t* d_nvalid,
+                     uint8_t* d_bg_mask, int32_t* d_status,
+                     void* d_workspace, size_t ws_bytes, void* stream) {
+    int rc = check_common(d_cls, d_anchors, d_annotations, num_images, num_anchors, num_classes, gt_rows, params);
+    if (rc) return rc;
+    if (!d_npos || !d_nvalid || !d_meta || !d_workspace) return CLDET_ERR_INVALID_ARGUMENT;
+    if (ws_bytes < workspace_bytes(num_images, num_anchors)) return CLDET_ERR_WORKSPACE_TOO_SMALL;
+    cudaStream_t s = (cudaStream_t)stream;
+    CLDET_CUDA_TRY(cudaMemsetAsync(d_npos, 0, sizeof(int32_t) * num_images, s));
+    CLDET_CUDA_TRY(cudaMemsetAsync(d_workspace, 0, sizeof(unsigned int) * num_images, s));
+    if (d_status) CLDET_CUDA_TRY(cudaMemsetAsync(d_status, 0, sizeof(int32_t), s));
+    rc = cldet_iou_assign(d_anchors, num_anchors, d_annotations, num_images, gt_rows, num_classes, d_meta, nullptr,
+                          d_iou_max, d_npos, d_nvalid, stream);
+    if (rc) return rc;
+    return cldet_focal_loss_from_assignment(d_cls, d_reg, d_anchors, d_annotations, num_images, num_anchors, num_classes,
+                                            gt_rows, params, d_weights, d_grad_cls, d_grad_reg, d_losses, d_meta,
+                                            d_iou_max, d_npos, d_bg_mask, d_status, d_workspace, ws_bytes, stream);
+}
+
+int cldet_focal_loss_reweight(const float* d_cls, const float* d_reg, const float* d_anchors, const float* d_annotations,
+                              int num_images, int64_t num_anchors, int num_classes, int gt_rows,
+                              const cldet_loss_params* params, const float* d_new_weights, float* d_baked_weights,
+                              float* d_grad_cls, float* d_grad_reg, const uint32_t* d_meta, const float* d_iou_max,
+                              const int32_t* d_npos, void* stream) {
+    int rc = check_common(d_cls, d_anchors, d_annotations, num_images, num_anchors, num_classes, gt_rows, params);
+    if (rc) return rc;
+    if (!d_reg || !d_new_weights || !d_baked_weights || !d_grad_cls || !d_grad_reg || !d_meta || !d_npos)
+        return CLDET_ERR_INVALID_ARGUMENT;
+    if (params->incremental && params->decrease_positive_by_iou && !d_iou_max) return CLDET_ERR_INVALID_ARGUMENT;
+    cudaStream_t s = (cudaStream_t)stream;
+    const LossPlan pl = make_plan(num_images, num_anchors, num_classes);
+    LossArgs a;
+    a.cls = d_cls; a.reg = d_reg; a.anchors = reinterpret_cast<const float4*>(d_anchors); a.ann = d_annotations;
+    a.N = num_images; a.A = num_anchors; a.C = num_classes; a.G = gt_rows; a.p = *params;
+    a.weights = d_new_weights; a.baked_weights = d_baked_weights; a.gcls = d_grad_cls; a.greg = d_grad_reg;
+    a.losses = nullptr; a.meta = d_meta; a.iou_max = d_iou_max; a.npos = d_npos; a.bg_mask = nullptr; a.status = nullptr;
+    a.counters = nullptr; a.partials = nullptr;
+    a.anchors_per_block = pl.anchors_per_block; a.bpi = pl.bpi; a.div_magic = pl.div_magic;
+    dim3 grid((unsigned)pl.bpi, (unsigned)num_images);
+    const bool gamma2 = params->gamma == 2.0f;
+    const bool variants = has_variants(*params);
+    if (num_classes % 4 == 0) dispatch_reweight<4>(a, gamma2, variants, grid, s);
+    else dispatch_reweight<1>(a, gamma2, variants, grid, s);
+    CLDET_LAUNCH_CHECK();
+    copy_weights_kernel<<<(num_images * 4 + 255) / 256, 256, 0, s>>>(d_new_weights, d_baked_weights, num_images * 4);
+    CLDET_LAUNCH_CHECK();
+    return CLDET_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,185 @@
+"""Drop-in for the eval half of the detection head: retinanet/utils.py BBoxTransform (:82-126) and ClipBoxes
+(:129-144), the part of ResNet.predict after self.forward (retinanet/model.py:507-550), Labeler.predict
+(IL_method/persuado_label.py:99-127) and torchvision.ops.nms / batched_nms as called there (model.py:540).
+
+The pipeline is decode_filter (class max + sigmoid + threshold + decode of the survivors only) -> ordering
+(+ optional radix-select top-k) -> 64x64 bitmask NMS -> gather, all in libcldet.so.  The reference handles one
+image per call; `detect_batch` runs a whole batch through the same kernels at once.
+"""
+import torch
+import torch.nn as nn
+
+from . import _lib
+from .losses import _check_cuda_f32, _stream
+
+NMS_MODE_TORCHVISION = 0   # coordinate trick unless 4*K > limit (torchvision.ops.boxes.batched_nms)
+NMS_MODE_TRICK = 1
+NMS_MODE_VANILLA = 2
+CUDA_VANILLA_NUMEL_LIMIT = 100_000   # torchvision 0.26 on CUDA; 4000 on CPU
+_CAND_BYTES = 32
+
+
+class BBoxTransform(nn.Module):
+    """forward(boxes[1,A,4], deltas[N,A,4]) -> [N,A,4]; mean 0, std (0.1,0.1,0.2,0.2) (utils.py:82-126)."""
+
+    def __init__(self, mean=None, std=None):
+        super().__init__()
+        if mean is not None or std is not None:
+            raise NotImplementedError('only the reference defaults mean=0, std=(0.1,0.1,0.2,0.2) are implemented')
+
+    def forward(self, boxes, deltas):
+        return decode_boxes(boxes, deltas, clip_to=None)
+
+
+class ClipBoxes(nn.Module):
+    """forward(boxes, img): clamps IN PLACE like the reference (utils.py:134-144) and returns boxes."""
+
+    def __init__(self, width=None, height=None):
+        super().__init__()
+
+    def forward(self, boxes, img):
+        height, width = int(img.shape[2]), int(img.shape[3])
+        b = _check_cuda_f32('boxes', boxes)
+        if b.data_ptr() != boxes.data_ptr():
+            raise ValueError('ClipBoxes works in place and needs a contiguous float32 CUDA tensor')
+        with torch.cuda.device(b.device):
+            _lib.check(_lib.load().cldet_clip_boxes(b.data_ptr(), b.numel() // 4, height, width, _stream()))
+        return boxes
+
+
+def decode_boxes(anchors, deltas, clip_to=None):
+    """BBoxTransform (+ ClipBoxes when clip_to=(height, width))."""
+    anc = _check_cuda_f32('anchors', anchors).reshape(-1, 4)
+    d = _check_cuda_f32('deltas', deltas)
+    if d.dim() != 3 or d.shape[2] != 4 or d.shape[1] != anc.shape[0]:
+        raise ValueError('deltas must be [N,A,4] with A matching the anchors')
+    h, w = (0, 0) if clip_to is None else (int(clip_to[0]), int(clip_to[1]))
+    with torch.cuda.device(d.device):
+        out = torch.empty_like(d)
+        _lib.check(_lib.load().cldet_decode_boxes(anc.data_ptr(), d.data_ptr(), d.shape[0], d.shape[1],
+                                                  0 if clip_to is None else 1, h, w, out.data_ptr(), _stream()))
+    return out
+
+
+def _aligned(t):
+    return t if t.data_ptr() % 16 == 0 else t.clone()
+
+
+def batched_nms(boxes, scores, idxs, iou_threshold, mode=NMS_MODE_TORCHVISION,
+                vanilla_numel_limit=CUDA_VANILLA_NUMEL_LIMIT):
+    """torchvision.ops.batched_nms(boxes[K,4], scores[K], idxs[K], thr) -> int64 keep indices, score-descending
+    (ties by ascending index).  idxs=None gives torchvision.ops.nms."""
+    b = _aligned(_check_cuda_f32('boxes', boxes).reshape(-1, 4))
+    s = _check_cuda_f32('scores', scores)
+    k = b.shape[0]
+    if s.shape[0] != k:
+        raise ValueError('boxes and scores disagree')
+    lib = _lib.load()
+    with torch.cuda.device(b.device):
+        if k == 0:
+            return torch.empty(0, dtype=torch.int64, device=b.device)
+        i = None if idxs is None else idxs.to(torch.int64).contiguous()
+        ws_bytes = lib.cldet_batched_nms_workspace_bytes(k)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=b.device)
+        keep = torch.empty(k, dtype=torch.int64, device=b.device)
+        count = torch.empty(1, dtype=torch.int32, device=b.device)
+        _lib.check(lib.cldet_batched_nms(b.data_ptr(), s.data_ptr(), _lib.ptr(i), k, float(iou_threshold), int(mode),
+                                         int(vanilla_numel_limit), keep.data_ptr(), count.data_ptr(), ws.data_ptr(),
+                                         ws_bytes, _stream()))
+        return keep[:int(count.item())]
+
+
+def nms(boxes, scores, iou_threshold):
+    return batched_nms(boxes, scores, None, iou_threshold, mode=NMS_MODE_TRICK)
+
+
+def detect_batch(cls, regressions, anchors, height, width, is_logits=True, score_thresh=0.05, iou_threshold=0.5,
+                 pre_nms_topk=0, nms_mode=NMS_MODE_TORCHVISION, vanilla_numel_limit=CUDA_VANILLA_NUMEL_LIMIT,
+                 return_padded=False):
+    """Detection output for EVERY image of the batch.
+
+    cls [N,A,C] logits (is_logits=True: sigmoid is applied like model.py:507) or probabilities (Labeler.predict);
+    regressions [N,A,4]; anchors [1,A,4].  Returns a list of (scores[K'], labels[K'] int64, boxes[K',4]) per image in NMS
+    order, or with return_padded=True the dense tensors (scores[N,cap], labels[N,cap], boxes[N,cap,4], counts[N]) without
+    any per-image slicing.  pre_nms_topk > 0 keeps only the best k candidates per image before NMS (the reference has
+    no such stage; 0 reproduces it) and makes the whole pipeline free of host synchronisation until the final counts.
+    """
+    c = _check_cuda_f32('classifications', cls)
+    r = _aligned(_check_cuda_f32('regressions', regressions))
+    anc = _aligned(_check_cuda_f32('anchors', anchors).reshape(-1, 4))
+    if c.dim() != 3 or r.dim() != 3 or r.shape[2] != 4 or r.shape[:2] != c.shape[:2] or anc.shape[0] != c.shape[1]:
+        raise ValueError('expected cls [N,A,C], regressions [N,A,4], anchors [1,A,4]')
+    n, a, nc = c.shape
+    dev = c.device
+    lib = _lib.load()
+    topk = int(pre_nms_topk) if pre_nms_topk and pre_nms_topk > 0 else 0
+    with torch.cuda.device(dev):
+        st = _stream()
+        counts = torch.zeros(n, dtype=torch.int32, device=dev)
+        cand = torch.empty((n, a, _CAND_BYTES), dtype=torch.uint8, device=dev)
+        keys = torch.empty((n, a), dtype=torch.int64, device=dev)
+        _lib.check(lib.cldet_decode_filter(c.data_ptr(), int(bool(is_logits)), r.data_ptr(), anc.data_ptr(), n, a, nc,
+                                           int(height), int(width), float(score_thresh), cand.data_ptr(), keys.data_ptr(),
+                                           a, counts.data_ptr(), st))
+        if topk:
+            max_count, cap = a, min(topk, a)
+        else:
+            max_count = int(counts.max().item())     # the one mid-pipeline sync of the reference-faithful mode
+            cap = max_count
+        if cap == 0:
+            empty = (torch.empty(0, device=dev), torch.empty(0, dtype=torch.int64, device=dev), torch.empty((0, 4), device=dev))
+            if return_padded:
+                return (torch.empty((n, 0), device=dev), torch.empty((n, 0), dtype=torch.int64, device=dev),
+                        torch.empty((n, 0, 4), device=dev), torch.zeros(n, dtype=torch.int32, device=dev))
+            return [empty for _ in range(n)]
+        sorted_c = torch.empty((n, cap, _CAND_BYTES), dtype=torch.uint8, device=dev)
+        sorted_counts = torch.empty(n, dtype=torch.int32, device=dev)
+        sws_bytes = lib.cldet_sort_workspace_bytes(n, max_count, topk)
+        sws = torch.empty(sws_bytes, dtype=torch.uint8, device=dev)
+        _lib.check(lib.cldet_sort_candidates(cand.data_ptr(), keys.data_ptr(), counts.data_ptr(), n, a, max_count, topk,
+                                             sorted_c.data_ptr(), cap, sorted_counts.data_ptr(), sws.data_ptr(), sws_bytes, st))
+        nws_bytes = lib.cldet_nms_workspace_bytes(n, cap)
+        nws = torch.empty(nws_bytes, dtype=torch.uint8, device=dev)
+        keep = torch.empty((n, cap), dtype=torch.int32, device=dev)
+        keep_counts = torch.empty(n, dtype=torch.int32, device=dev)
+        _lib.check(lib.cldet_nms_sorted(sorted_c.data_ptr(), sorted_counts.data_ptr(), n, cap, cap, float(iou_threshold),
+                                        int(nms_mode), int(vanilla_numel_limit), keep.data_ptr(), keep_counts.data_ptr(),
+                                        nws.data_ptr(), nws_bytes, st))
+        scores = torch.empty((n, cap), dtype=torch.float32, device=dev)
+        labels = torch.empty((n, cap), dtype=torch.int64, device=dev)
+        boxes = torch.empty((n, cap, 4), dtype=torch.float32, device=dev)
+        _lib.check(lib.cldet_gather_detections(sorted_c.data_ptr(), keep.data_ptr(), keep_counts.data_ptr(), n, cap, cap,
+                                               scores.data_ptr(), labels.data_ptr(), boxes.data_ptr(), st))
+        if return_padded:
+            return scores, labels, boxes, keep_counts
+        kc = keep_counts.cpu().tolist()
+        return [(scores[j, :kc[j]], labels[j, :kc[j]], boxes[j, :kc[j]]) for j in range(n)]
+
+
+def predict_from_head(classification, regression, anchors, img_batch, thresh=None, **kw):
+    """The part of ResNet.predict after self.forward and the optional BiC correction (model.py:507-550): logits in,
+    [scores, labels(int64), boxes] of image 0 out, score-descending.  `thresh` is validated and then ignored exactly
+    like the reference (model.py:524-530 overwrites it with 0.05)."""
+    if thresh is not None and len(thresh) != classification.shape[2]:
+        raise ValueError('Parameter Thresh  must contain {} elements!'.format(classification.shape[2]))
+    h, w = int(img_batch.shape[2]), int(img_batch.shape[3])
+    s, l, b = detect_batch(classification[:1], regression[:1], anchors, h, w, is_logits=True, **kw)[0]
+    return [s, l, b]
+
+
+def predict(model, img_batch, thresh=None, method=None, bic=None, **kw):
+    """Drop-in for ResNet.predict (model.py:494): `ResNet.predict = cl_object_detection_b200.detect.predict`."""
+    classification, regression, anchors = model.forward(img_batch, return_feat=False, return_anchor=True, enable_act=False)
+    if bic:
+        classification = bic.bic_correction(classification)
+    return predict_from_head(classification, regression, anchors, img_batch, thresh, **kw)
+
+
+def labeler_predict(img_batch, classifications, regressions, anchors, **kw):
+    """Labeler.predict (persuado_label.py:99-127): probabilities in, (scores, boxes, labels) of image 0 out; empty
+    result = three empty float tensors like the reference's torch.tensor([])."""
+    h, w = int(img_batch.shape[2]), int(img_batch.shape[3])
+    s, l, b = detect_batch(classifications[:1], regressions[:1], anchors, h, w, is_logits=False, **kw)[0]
+    if s.shape[0] == 0:
+        return torch.tensor([]), torch.tensor([]), torch.tensor([])
+    return s, b, l

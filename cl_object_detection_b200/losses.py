@@ -1,0 +1,208 @@
+"""Drop-in for the loss half of the detection head: retinanet/losses.py calc_iou (:4-21) and
+FocalLoss.forward (:252-452), backed by the fused sm_100a kernels in libcldet.so.
+
+Differences in HOW (not WHAT): the per-image Python loop, the [A,G] IoU matrix, the dense [A,C] target
+matrix and ~200 eager kernels per image are replaced by two launches for the whole batch; the gradient
+w.r.t. the probabilities and the regression outputs is produced IN THE FORWARD PASS with the upstream
+weights the caller is expected to apply (IL_Loss takes .mean() of each term, losses.py:584-588), and
+autograd's backward only verifies those weights on the device and patches the (rare) images where they
+differ (clip_loss masking, losses.py:575-581).
+"""
+import torch
+import torch.nn as nn
+
+from . import _lib
+from .params import to_loss_params
+
+
+def _check_cuda_f32(name, t):
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise RuntimeError('%s must be a CUDA tensor: this path has no CPU implementation' % name)
+    if t.dtype != torch.float32:
+        raise TypeError('%s must be float32 (got %s)' % (name, t.dtype))
+    return t.contiguous()
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def calc_iou(a, b):
+    """Pairwise IoU [A,G] in fp32 with the reference's exact op order (losses.py:4-21)."""
+    a = _check_cuda_f32('a', a)
+    b = _check_cuda_f32('b', b)
+    if a.dim() != 2 or a.shape[1] != 4 or b.dim() != 2 or b.shape[1] != 4:
+        raise ValueError('calc_iou expects [A,4] and [G,4] boxes')
+    with torch.cuda.device(a.device):
+        out = torch.empty((a.shape[0], b.shape[0]), dtype=torch.float32, device=a.device)
+        _lib.check(_lib.load().cldet_calc_iou(a.data_ptr(), a.shape[0], b.data_ptr(), b.shape[0], out.data_ptr(), _stream()))
+    return out
+
+
+def iou_assign(anchors, annotations, num_classes, want_argmax=True, want_iou_max=True):
+    """Anchor-to-GT assignment for a batch (losses.py:287-288, 309-341) without touching the class map.
+
+    anchors [1,A,4] or [A,4]; annotations [N,G,5] (pad rows label == -1).
+    Returns dict(meta uint32-as-int32 [N,A], state uint8 [N,A] (0 bg, 1 pos, 2 ignore, 3 empty image),
+    argmax int32 [N,A] (compacted GT index, -1 for empty images), iou_max [N,A], npos int32 [N], nvalid int32 [N]).
+    """
+    anchors = _check_cuda_f32('anchors', anchors).reshape(-1, 4)
+    annotations = _check_cuda_f32('annotations', annotations)
+    if annotations.dim() != 3 or annotations.shape[2] != 5:
+        raise ValueError('annotations must be [N,G,5]')
+    n, g = annotations.shape[0], annotations.shape[1]
+    a = anchors.shape[0]
+    dev = anchors.device
+    with torch.cuda.device(dev):
+        meta = torch.empty((n, a), dtype=torch.int32, device=dev)
+        argmax = torch.empty((n, a), dtype=torch.int32, device=dev) if want_argmax else None
+        iou_max = torch.empty((n, a), dtype=torch.float32, device=dev) if want_iou_max else None
+        npos = torch.zeros(n, dtype=torch.int32, device=dev)
+        nvalid = torch.empty(n, dtype=torch.int32, device=dev)
+        _lib.check(_lib.load().cldet_iou_assign(anchors.data_ptr(), a, annotations.data_ptr(), n, g, int(num_classes),
+                                                meta.data_ptr(), _lib.ptr(argmax), _lib.ptr(iou_max), npos.data_ptr(),
+                                                nvalid.data_ptr(), _stream()))
+    return dict(meta=meta, state=(meta & 3).to(torch.uint8), label=(meta >> 3) & 0x1fff, argmax=argmax,
+                iou_max=iou_max, npos=npos, nvalid=nvalid)
+
+
+class _FocalLossFn(torch.autograd.Function):
+    """outputs: bg[N], fg[N], reg_per_image[N], enhance_per_image[N] (rows of the kernel's [4,N] result)."""
+
+    @staticmethod
+    def forward(ctx, cls, reg, anchors, annotations, lp, hint, want_bg_mask, check_labels):
+        lib = _lib.load()
+        n, a, c = cls.shape
+        g = annotations.shape[1]
+        dev = cls.device
+        need_grad = ctx.needs_input_grad[0] or ctx.needs_input_grad[1]
+        with torch.cuda.device(dev):
+            losses = torch.empty((4, n), dtype=torch.float32, device=dev)
+            meta = torch.empty((n, a), dtype=torch.int32, device=dev)
+            iou_max = torch.empty((n, a), dtype=torch.float32, device=dev) if lp.decrease_positive_by_iou else None
+            npos = torch.empty(n, dtype=torch.int32, device=dev)
+            nvalid = torch.empty(n, dtype=torch.int32, device=dev)
+            bg_mask = torch.empty((n, a), dtype=torch.uint8, device=dev) if want_bg_mask else None
+            status = torch.empty(1, dtype=torch.int32, device=dev) if check_labels else None
+            ws_bytes = lib.cldet_focal_loss_workspace_bytes(n, a)
+            ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+            if need_grad:
+                weights = hint.to(device=dev, dtype=torch.float32).clone()   # private: the reweight pass updates it
+                gcls = torch.empty_like(cls)
+                greg = torch.empty_like(reg)
+            else:
+                weights = gcls = greg = None
+            _lib.check(lib.cldet_focal_loss(
+                cls.data_ptr(), reg.data_ptr(), anchors.data_ptr(), annotations.data_ptr(), n, a, c, g, lp,
+                _lib.ptr(weights), _lib.ptr(gcls), _lib.ptr(greg), losses.data_ptr(), meta.data_ptr(), _lib.ptr(iou_max),
+                npos.data_ptr(), nvalid.data_ptr(), _lib.ptr(bg_mask), _lib.ptr(status), ws.data_ptr(), ws_bytes, _stream()))
+        if check_labels and int(status.item()) != 0:
+            raise IndexError('a GT label is outside [0, %d): the reference indexes the class dimension with it '
+                             '(losses.py:341)' % c)
+        ctx.lp = lp
+        ctx.shape = (n, a, c, g)
+        ctx.backward_calls = 0
+        if need_grad:
+            ctx.save_for_backward(cls, reg, anchors, annotations, weights, gcls, greg, meta, npos)
+            ctx.iou_max = iou_max
+        ctx.mark_non_differentiable(npos, nvalid)
+        outs = (losses[0], losses[1], losses[2], losses[3], npos, nvalid)
+        if want_bg_mask:
+            ctx.mark_non_differentiable(bg_mask)
+            outs = outs + (bg_mask,)
+        return outs
+
+    @staticmethod
+    def backward(ctx, g_bg, g_fg, g_reg, g_enh, *unused):
+        cls, reg, anchors, annotations, baked, gcls, greg, meta, npos = ctx.saved_tensors
+        n, a, c, g = ctx.shape
+        dev = cls.device
+        zero = None
+
+        def row(t):
+            nonlocal zero
+            if t is None:
+                if zero is None:
+                    zero = torch.zeros(n, dtype=torch.float32, device=dev)
+                return zero
+            return t.to(torch.float32)
+
+        with torch.cuda.device(dev):
+            new_w = torch.stack([row(g_bg), row(g_fg), row(g_reg), row(g_enh)]).contiguous()
+            iou_max = ctx.iou_max
+            _lib.check(_lib.load().cldet_focal_loss_reweight(
+                cls.data_ptr(), reg.data_ptr(), anchors.data_ptr(), annotations.data_ptr(), n, a, c, g, ctx.lp,
+                new_w.data_ptr(), baked.data_ptr(), gcls.data_ptr(), greg.data_ptr(), meta.data_ptr(), _lib.ptr(iou_max),
+                npos.data_ptr(), _stream()))
+        ctx.backward_calls += 1
+        if ctx.backward_calls > 1:   # the buffers may already be someone's .grad: hand out copies from now on
+            return gcls.clone(), greg.clone(), None, None, None, None, None, None
+        return gcls, greg, None, None, None, None, None, None
+
+
+class FocalLoss(nn.Module):
+    """Same call signature and result dict as the reference module (losses.py:252-253, 444-452).
+
+    forward(classifications[N,A,C] probs, regressions[N,A,4], anchors[1,A,4], annotations[N,G,5], cur_state, params,
+            progress=-1) -> {'cls_loss': (bg[N], fg[N]), 'reg_loss': [1], ['bg_masks': bool[M,A]],
+                             ['enhance_on_new_loss': scalar]}
+
+    `progress` is accepted and ignored: in the reference it only feeds a statement that has no effect
+    (losses.py:388-392 multiplies a temporary).  Inputs are never modified.
+
+    upstream_hint: the dL/d(term) the caller will apply -- 'mean' (1/N for bg, fg and the regression mean; what IL_Loss
+    does) or a [4,N] tensor (rows bg, fg, per-image reg, enhance).  A wrong hint costs a re-weighting pass in backward,
+    never a wrong gradient.
+    check_labels=True adds a host sync to raise IndexError on out-of-range GT labels like the reference does.
+    """
+
+    def __init__(self, upstream_hint='mean', check_labels=False):
+        super().__init__()
+        self.upstream_hint = upstream_hint
+        self.check_labels = check_labels
+        self._hint_cache = {}
+
+    def _hint(self, n, device):
+        if isinstance(self.upstream_hint, torch.Tensor):
+            if tuple(self.upstream_hint.shape) != (4, n):
+                raise ValueError('upstream_hint must be [4, N]')
+            return self.upstream_hint
+        if self.upstream_hint != 'mean':
+            raise ValueError("upstream_hint must be 'mean' or a [4,N] tensor")
+        key = (n, device.index)
+        w = self._hint_cache.get(key)
+        if w is None:
+            w = torch.full((4, n), 1.0 / n, dtype=torch.float32)
+            w[3] = 1.0
+            w = w.to(device)
+            self._hint_cache[key] = w
+        return w
+
+    def forward(self, classifications, regressions, anchors, annotations, cur_state: int, params, progress=-1):
+        cls = _check_cuda_f32('classifications', classifications)
+        reg = _check_cuda_f32('regressions', regressions)
+        anc = _check_cuda_f32('anchors', anchors)
+        ann = _check_cuda_f32('annotations', annotations)
+        if cls.dim() != 3 or reg.dim() != 3 or reg.shape[2] != 4 or reg.shape[:2] != cls.shape[:2]:
+            raise ValueError('classifications must be [N,A,C] and regressions [N,A,4]')
+        if anc.dim() != 3 or anc.shape[0] != 1 or anc.shape[1] != cls.shape[1] or anc.shape[2] != 4:
+            raise ValueError('anchors must be [1,A,4]')
+        if ann.dim() != 3 or ann.shape[0] != cls.shape[0] or ann.shape[2] != 5:
+            raise ValueError('annotations must be [N,G,5]')
+        if ann.shape[1] == 0:
+            raise ValueError('annotations needs at least one (possibly padding) row; the collater emits [N,1,5] of -1')
+        n, _, c = cls.shape
+        lp = to_loss_params(params, int(cur_state), c)
+        incremental = cur_state > 0
+        want_mask = bool(incremental and params['distill'])
+        outs = _FocalLossFn.apply(cls, reg, anc, ann, lp, self._hint(n, cls.device), want_mask, self.check_labels)
+        bg, fg, reg_j, enh_j, npos, nvalid = outs[:6]
+        result = {'cls_loss': (bg, fg), 'reg_loss': reg_j.mean(dim=0, keepdim=True)}   # losses.py:444-445
+        if incremental:
+            if params['distill']:
+                # the reference appends a mask only for images that have GT (quirk Q6): M <= N rows
+                result['bg_masks'] = outs[6].bool()[nvalid > 0]
+            if params['enhance_on_new']:
+                result['enhance_on_new_loss'] = enh_j.sum()
+        self.last_npos, self.last_nvalid = npos, nvalid
+        return result

@@ -1,0 +1,211 @@
+/*
+ * cldet.h -- C ABI of the B200-native detection-head path (libcldet.so).
+ *
+ * Every entry point takes plain pointers and sizes; there are no torch types here.  Device
+ * pointers are prefixed d_, host pointers h_.  `stream` is a cudaStream_t passed as void*.
+ * All functions return a cldet_status (0 = ok); none of them calls exit/abort, none
+ * allocates device memory behind the caller's back (workspaces are passed in), none keeps
+ * mutable global state, so calls are re-entrant and safe from several host threads
+ * (reference: evaluator.py:400-422 runs predict from up to 10 threads).
+ *
+ * Each function names the reference interface it replaces (paths relative to the
+ * reference checkout, EonianCoda/CL_object_detection).
+ */
+#ifndef CLDET_H_
+#define CLDET_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum cldet_status {
+    CLDET_OK = 0,
+    CLDET_ERR_INVALID_ARGUMENT = 1,   /* null pointer, negative extent, unsupported size */
+    CLDET_ERR_WORKSPACE_TOO_SMALL = 2,
+    CLDET_ERR_CUDA = 3,               /* a CUDA runtime call failed; see cldet_last_cuda_error() */
+    CLDET_ERR_UNSUPPORTED = 4
+} cldet_status;
+
+#define CLDET_ABI_VERSION 1
+
+int cldet_abi_version(void);
+const char* cldet_status_string(int status);
+/* cudaGetErrorString of the last failing CUDA call made by THIS thread inside libcldet (thread-local). */
+const char* cldet_last_cuda_error(void);
+
+/* ---------------------------------------------------------------------------------------
+ * Per-anchor assignment word written by cldet_iou_assign and read by the loss kernel.
+ *   bits  0..1  state: 0 background (IoU_max < 0.4), 1 positive (IoU_max >= 0.5), 2 ignore,
+ *               3 image has no valid GT row (reference branch losses.py:292-307)
+ *   bit   2     set by the new_ignore_past_class pre-pass: background anchor whose old-class columns count as
+ *               negatives (sum of old-class probabilities < 0.5, losses.py:326-327)
+ *   bits  3..15 class label of the assigned GT row (valid when state == 1; 0x1fff = label out of range)
+ *   bits 16..31 RAW row index (into annotations[j]) of the assigned GT (first maximal IoU)
+ * ------------------------------------------------------------------------------------- */
+#define CLDET_STATE_BG 0u
+#define CLDET_STATE_POS 1u
+#define CLDET_STATE_IGNORE 2u
+#define CLDET_STATE_EMPTY 3u
+#define CLDET_MAX_GT_ROWS 65536
+#define CLDET_MAX_CLASSES 8191
+#define CLDET_BAD_LABEL 0x1fffu
+#define CLDET_META_OLD_ACTIVE 4u
+
+/* ---- a1: Anchors.forward (retinanet/anchors.py:21-40; generate_anchors :42-73; shift :109-129) ----
+ * Levels 3..7, strides 8..128, sizes 32..512, ratios {0.5,1,2}, scales {1,2^(1/3),2^(2/3)}.
+ * fp64 arithmetic on the device, ONE final rounding to fp32 (bit-exact with the numpy reference). */
+int cldet_num_anchors(int height, int width, int64_t* out_num_anchors);
+int cldet_anchors(int height, int width, float* d_anchors /* [A,4] */, void* stream);
+
+/* ---- a2-a4: calc_iou + max/argmax + 0.4/0.5 thresholds (retinanet/losses.py:4-21, 287-288, 309-341) ----
+ * annotations: [N,G,5] fp32 rows (x1,y1,x2,y2,label); rows with label == -1 are padding and are
+ * skipped in order (the reference compacts them away, losses.py:287-288).  Pseudo-label rows merged by
+ * the dataset (dataloader.py:129-136) are ordinary rows here.
+ * Outputs (all device):
+ *   d_meta    [N,A] uint32   assignment word, see above
+ *   d_argmax  [N,A] int32    index into the COMPACTED GT list = reference IoU_argmax (may be NULL); -1 for empty images
+ *   d_iou_max [N,A] float    reference IoU_max (may be NULL unless the decrease_positive_by_IOU variant is used)
+ *   d_npos    [N]   int32    number of positive anchors per image; MUST be zero on entry (cldet_focal_loss does this)
+ *   d_nvalid  [N]   int32    number of valid GT rows per image
+ * num_classes is used only to flag out-of-range labels (CLDET_BAD_LABEL). */
+int cldet_iou_assign(const float* d_anchors, int64_t num_anchors, const float* d_annotations, int num_images,
+                     int gt_rows, int num_classes, uint32_t* d_meta, int32_t* d_argmax, float* d_iou_max,
+                     int32_t* d_npos, int32_t* d_nvalid, void* stream);
+
+/* Standalone pairwise IoU matrix [A,G] (calc_iou, losses.py:4-21; also its copies in IL_method/mas.py:15-32,
+ * weight_init.py:7-24).  For tests and the "next" callers; the loss path never materialises this matrix. */
+int cldet_calc_iou(const float* d_a, int64_t num_a, const float* d_b, int num_b, float* d_iou, void* stream);
+
+/* ---- a5-a8: FocalLoss.forward + its autograd backward (retinanet/losses.py:252-452) ---- */
+typedef struct cldet_loss_params {
+    float alpha;                       /* params['alpha'], default 0.25 */
+    float gamma;                       /* params['gamma'], default 2 (computed as x*x like ATen) */
+    int32_t incremental;               /* cur_state > 0 */
+    int32_t past_class_num;            /* params.states[cur_state]['num_past_class'] */
+    int32_t ignore_past_class;         /* losses.py:319-322 */
+    int32_t new_ignore_past_class;     /* :323-328 */
+    int32_t decrease_positive_by_iou;  /* :353-362 */
+    int32_t enhance_on_new;            /* :380-384 */
+    float decrease_positive;           /* :364-366, default 1.0 */
+} cldet_loss_params;
+
+/* Bytes of scratch cldet_focal_loss needs for (N, A). */
+size_t cldet_focal_loss_workspace_bytes(int num_images, int64_t num_anchors);
+
+/* One call = memset of the counters + IoU/assign kernel + fused loss/gradient kernel.
+ *   d_cls  [N,A,C] probabilities (post-sigmoid, as the reference passes them)   d_reg [N,A,4]
+ *   d_anchors [A,4]      d_annotations [N,G,5]
+ *   d_weights [4,N] (row-major, one row per term) upstream gradients per image: row 0 dL/d(bg_j), row 1 dL/d(fg_j),
+ *            row 2 dL/d(reg_j), row 3 dL/d(enhance term); reg_j is the per-image regression term, so a caller holding
+ *            dL/d(reg_loss[0]) passes that / N.
+ *            NULL = no gradients wanted (d_grad_* must then be NULL too).
+ *   d_grad_cls [N,A,C], d_grad_reg [N,A,4]: written completely (zeros where the reference's gradient is zero).
+ *            d_grad_cls may alias d_cls (in-place variant for a caller that no longer needs the probabilities).
+ *   d_losses [4,N]: rows bg_j, fg_j (each already divided by max(npos_j,1)), reg_j, enhance_on_new partial of image j.
+ *   d_meta [N,A] uint32 out (kept by the caller for the re-weighting pass); d_iou_max [N,A] out, may be NULL unless
+ *            params->decrease_positive_by_iou; d_npos / d_nvalid [N] out.
+ *   d_bg_mask [N,A] uint8 out, may be NULL: 1 where the anchor is NOT positive (reference 'bg_masks', losses.py:334-335).
+ *   d_status: int32[1] out, may be NULL; set non-zero when a positive anchor's label is outside [0,C) (reference raises, Q8). */
+int cldet_focal_loss(const float* d_cls, const float* d_reg, const float* d_anchors, const float* d_annotations,
+                     int num_images, int64_t num_anchors, int num_classes, int gt_rows,
+                     const cldet_loss_params* params, const float* d_weights,
+                     float* d_grad_cls, float* d_grad_reg, float* d_losses,
+                     uint32_t* d_meta, float* d_iou_max, int32_t* d_npos, int32_t* d_nvalid,
+                     uint8_t* d_bg_mask, int32_t* d_status,
+                     void* d_workspace, size_t workspace_bytes, void* stream);
+
+/* Loss/gradient stage alone, on an assignment produced earlier by cldet_iou_assign (same argument meaning).
+ * d_meta is read; with params->new_ignore_past_class its bit 2 is (re)written by a pre-pass over the old-class columns.
+ * The first num_images uint32 of the workspace must be zero on entry (they are left zero on return). */
+int cldet_focal_loss_from_assignment(const float* d_cls, const float* d_reg, const float* d_anchors,
+                                     const float* d_annotations, int num_images, int64_t num_anchors, int num_classes,
+                                     int gt_rows, const cldet_loss_params* params, const float* d_weights,
+                                     float* d_grad_cls, float* d_grad_reg, float* d_losses, uint32_t* d_meta,
+                                     const float* d_iou_max, const int32_t* d_npos, uint8_t* d_bg_mask, int32_t* d_status,
+                                     void* d_workspace, size_t workspace_bytes, void* stream);
+
+/* Backward with upstream weights that differ from the ones baked into d_grad_* by the forward call
+ * (IL_Loss's clip_loss masking, losses.py:575-581, is only known after the forward).  Per image and per term the
+ * kernel compares d_new_weights with d_baked_weights ON THE DEVICE (no host sync): images whose weights are unchanged
+ * are skipped; a changed fg/reg weight touches only that image's positive anchors; a changed bg weight recomputes the
+ * image.  d_baked_weights is updated to d_new_weights at the end. */
+int cldet_focal_loss_reweight(const float* d_cls, const float* d_reg, const float* d_anchors, const float* d_annotations,
+                              int num_images, int64_t num_anchors, int num_classes, int gt_rows,
+                              const cldet_loss_params* params, const float* d_new_weights, float* d_baked_weights,
+                              float* d_grad_cls, float* d_grad_reg, const uint32_t* d_meta, const float* d_iou_max,
+                              const int32_t* d_npos, void* stream);
+
+/* ---- a10-a13: eval-mode detection output (retinanet/utils.py:102-144 BBoxTransform/ClipBoxes;
+ *      retinanet/model.py:507-550 ResNet.predict; IL_method/persuado_label.py:99-127 Labeler.predict;
+ *      torchvision.ops.batched_nms at model.py:540) ---- */
+
+/* BBoxTransform.forward (utils.py:102-126) for every anchor of every image: [N,A,4]; clip != 0 also applies
+ * ClipBoxes.forward (utils.py:134-144: x1,y1 >= 0, x2 <= width, y2 <= height).  For callers that want the dense box
+ * tensor; the detection pipeline below decodes only the anchors that pass the score threshold. */
+int cldet_decode_boxes(const float* d_anchors, const float* d_reg, int num_images, int64_t num_anchors, int clip, int height,
+                       int width, float* d_boxes, void* stream);
+/* ClipBoxes.forward alone, in place on [num_boxes,4]. */
+int cldet_clip_boxes(float* d_boxes, int64_t num_boxes, int height, int width, void* stream);
+
+typedef struct cldet_candidate {   /* 32 bytes, one per anchor that passes the score threshold */
+    float x1, y1, x2, y2;          /* decoded, clipped box */
+    float score;                   /* max class probability */
+    int32_t label;                 /* first class index attaining it */
+    int32_t anchor;                /* anchor index inside the image */
+    int32_t pad;
+} cldet_candidate;
+
+/* Fused: per-anchor max/argmax over C classes (+sigmoid when is_logits), score > thresh filter, box decode + clip of
+ * the survivors only, append to a per-image candidate list.  d_candidates is [N, capacity]; d_keys [N, capacity] uint64
+ * receives each candidate's ordering key ((ordered score bits << 32) | ~anchor: larger key = earlier in the reference's
+ * stable score-descending order); d_counts [N] int32 must be zero on entry and receives the number of survivors (it can
+ * exceed capacity: the excess is dropped and the caller must treat that as an error).  Append order is arbitrary;
+ * cldet_sort_candidates orders it. */
+int cldet_decode_filter(const float* d_cls, int is_logits, const float* d_reg, const float* d_anchors, int num_images,
+                        int64_t num_anchors, int num_classes, int height, int width, float score_thresh,
+                        cldet_candidate* d_candidates, uint64_t* d_keys, int64_t capacity, int32_t* d_counts, void* stream);
+
+/* Order each image's candidates by (score descending, anchor ascending) -- the order torchvision's stable
+ * descending sort gives the reference's anchor-ordered candidate list -- and optionally keep only the first
+ * `topk` of them (topk <= 0: keep all; the reference has no top-k).  With topk > 0 a 3-pass radix
+ * select on the score bits finds the k-th score per image first, so only ~topk candidates are ordered.
+ * Writes the ordered list to d_sorted [N, sorted_capacity] and min(count, topk) to d_sorted_counts.
+ * max_count is an upper bound on d_counts[j] known to the host (e.g. after reading the counts, or `capacity`). */
+size_t cldet_sort_workspace_bytes(int num_images, int64_t max_count, int topk);
+int cldet_sort_candidates(const cldet_candidate* d_candidates, const uint64_t* d_keys, const int32_t* d_counts,
+                          int num_images, int64_t capacity, int64_t max_count, int topk, cldet_candidate* d_sorted,
+                          int64_t sorted_capacity, int32_t* d_sorted_counts, void* d_workspace, size_t workspace_bytes,
+                          void* stream);
+
+size_t cldet_nms_workspace_bytes(int num_images, int64_t max_count);
+
+/* Per-class greedy NMS over each image's SORTED candidate list (torchvision.ops.batched_nms semantics):
+ *   mode 0 = follow torchvision's rule (coordinate trick unless 4*count > vanilla_numel_limit),
+ *   mode 1 = always coordinate trick  (boxes + label*(max_coord+1) in fp32, then plain NMS),
+ *   mode 2 = always vanilla           (raw coordinates, only same-label pairs suppress).
+ * Suppress iff inter / ((area_i + area_j) - inter) > iou_thresh (strict, fp32, no FMA).
+ * Outputs: d_keep [N, capacity] int32 = positions (into the sorted list) of kept boxes in order; d_keep_counts [N]. */
+int cldet_nms_sorted(const cldet_candidate* d_sorted, const int32_t* d_sorted_counts, int num_images, int64_t capacity,
+                     int64_t max_count, float iou_thresh, int mode, int64_t vanilla_numel_limit, int32_t* d_keep,
+                     int32_t* d_keep_counts, void* d_workspace, size_t workspace_bytes, void* stream);
+
+/* torchvision.ops.nms / batched_nms on caller-provided boxes (drop-in for model.py:540, persuado_label.py:116):
+ * d_boxes [K,4], d_scores [K], d_idxs [K] int64 (NULL = plain nms).  d_keep [K] int64 receives ORIGINAL indices in
+ * score-descending order (ties by ascending index); *d_keep_count int32.  Workspace: cldet_batched_nms_workspace_bytes(K). */
+size_t cldet_batched_nms_workspace_bytes(int64_t num_boxes);
+int cldet_batched_nms(const float* d_boxes, const float* d_scores, const int64_t* d_idxs, int64_t num_boxes,
+                      float iou_thresh, int mode, int64_t vanilla_numel_limit, int64_t* d_keep, int32_t* d_keep_count,
+                      void* d_workspace, size_t workspace_bytes, void* stream);
+
+/* Gather the kept candidates into dense outputs: scores [N,capacity], labels [N,capacity] int64, boxes [N,capacity,4]. */
+int cldet_gather_detections(const cldet_candidate* d_sorted, const int32_t* d_keep, const int32_t* d_keep_counts,
+                            int num_images, int64_t capacity, int64_t max_keep, float* d_scores, int64_t* d_labels,
+                            float* d_boxes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CLDET_H_ */

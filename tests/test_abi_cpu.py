@@ -1,0 +1,77 @@
+"""CPU checks of the C-ABI boundary: the library builds/loads and exports every symbol include/cldet.h declares,
+the ctypes table covers the header, and the product path refuses to run without CUDA (no fallback)."""
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+import cl_object_detection_b200 as cld
+from cl_object_detection_b200 import _lib
+from oracle import head_oracle as O
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def header_functions():
+    text = open(os.path.join(ROOT, 'include', 'cldet.h')).read()
+    text = re.sub(r'/\*.*?\*/', '', text, flags=re.S)
+    return sorted(set(re.findall(r'\b(cldet_[a-z0-9_]+)\s*\(', text)))
+
+
+def test_library_exports_every_declared_symbol():
+    from cl_object_detection_b200.build import build_library
+    build_library()
+    lib = _lib.load()
+    names = header_functions()
+    assert len(names) >= 10
+    for n in names:
+        assert hasattr(lib, n), 'libcldet.so does not export %s' % n
+    assert set(names) == set(_lib.SIGNATURES), 'ctypes table and header disagree'
+    assert not _lib._PENDING
+    assert lib.cldet_abi_version() == 1
+    assert lib.cldet_status_string(0) == b'ok'
+
+
+def test_num_anchors_matches_oracle_without_gpu():
+    for hw in [(512, 512), (800, 1333), (1333, 1333), (33, 70), (608, 1024), (1, 1)]:
+        assert cld.num_anchors(*hw) == O.num_anchors(*hw)
+
+
+def test_argument_validation_without_gpu():
+    lib = _lib.load()
+    assert lib.cldet_anchors(0, 10, None, None) == 1
+    assert lib.cldet_focal_loss_workspace_bytes(0, 10) == 0
+    assert lib.cldet_focal_loss_workspace_bytes(2, 1000) > 0
+    assert lib.cldet_iou_assign(None, 10, None, 1, 1, 1, None, None, None, None, None, None) == 1
+
+
+def test_no_cpu_fallback():
+    fl = cld.FocalLoss()
+    p = cld.HeadParams()
+    with pytest.raises(RuntimeError, match='CUDA'):
+        fl(torch.rand(1, 9, 2), torch.rand(1, 9, 4), torch.rand(1, 9, 4), -torch.ones(1, 1, 5), 0, p)
+    with pytest.raises(RuntimeError, match='CUDA'):
+        cld.calc_iou(torch.rand(3, 4), torch.rand(2, 4))
+
+
+def test_product_does_not_import_oracle():
+    pkg = os.path.join(ROOT, 'cl_object_detection_b200')
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith(('.py', '.cu', '.cuh', '.h')):
+                src = open(os.path.join(dirpath, f)).read()
+                assert 'oracle' not in src.replace('test oracle', '').replace('the oracle', ''), f
+
+
+def test_params_translation_matches_reference_error_behaviour():
+    from cl_object_detection_b200.params import to_loss_params
+    p = cld.HeadParams([0, 15])
+    lp = to_loss_params(p, 1, 16)
+    assert lp.incremental == 1 and lp.past_class_num == 15 and abs(lp.alpha - 0.25) < 1e-7
+    p['decrease_positive'] = None
+    with pytest.raises(TypeError):
+        to_loss_params(p, 1, 16)
+    p['decrease_positive_by_IOU'] = True
+    assert to_loss_params(p, 1, 16).decrease_positive_by_iou == 1

@@ -1,0 +1,184 @@
+"""GPU parity tests of the eval half of the path (decode/clip, class max + threshold, top-k, per-class NMS) against the CPU
+oracle and the golden vectors of the unmodified reference / torchvision.  All calls go through the C ABI.
+
+Bars: labels, candidate sets and NMS keep indices BIT-EXACT; scores bit-exact against ATen's own sigmoid on the same device;
+decoded boxes within 2 ulp of the row's largest magnitude when compared with a CPU exp() (bit-exact vs the same-device exp).
+"""
+import numpy as np
+import pytest
+import torch
+
+import cl_object_detection_b200 as cld
+from cl_object_detection_b200 import detect as D
+from oracle import head_oracle as O
+from tests.helpers import load
+
+pytestmark = pytest.mark.gpu
+DEV = 'cuda:0'
+
+
+def cu(x):
+    return torch.from_numpy(np.ascontiguousarray(x)).to(DEV)
+
+
+def boxes_close(got, ref):
+    got, ref = np.asarray(got, np.float64), np.asarray(ref, np.float64)
+    assert got.shape == ref.shape
+    if got.size == 0:
+        return
+    scale = np.max(np.abs(ref), axis=-1, keepdims=True)
+    worst = float((np.abs(got - ref) / np.maximum(scale, 1e-30)).max())
+    assert worst <= 2.4e-7, worst
+
+
+def test_decode_and_clip_vs_golden_and_oracle():
+    g = load('decode')
+    h, w = int(g['h']), int(g['w'])
+    anchors = cld.generate_anchors(h, w, DEV)
+    dec = D.BBoxTransform()(anchors, cu(g['reg']))
+    boxes_close(dec.cpu().numpy(), g['decoded'])
+    boxes_close(dec.cpu().numpy(), O.bbox_transform(O.anchors_for_image(h, w), g['reg']))
+    # clip is exact given the same decoded input, and in place like the reference
+    t = cu(g['decoded']).clone()
+    out = D.ClipBoxes()(t, torch.zeros(2, 3, h, w))
+    assert out is t and np.array_equal(t.cpu().numpy(), g['clipped'])
+    both = D.decode_boxes(anchors, cu(g['reg']), clip_to=(h, w))
+    assert np.array_equal(both.cpu().numpy(), O.clip_boxes(dec.cpu().numpy(), h, w))
+    # same-device reference: torch's own exp on the GPU -> bit exact
+    a = anchors[0]
+    r = cu(g['reg'])
+    wd, hg = a[:, 2] - a[:, 0], a[:, 3] - a[:, 1]
+    cx, cy = a[:, 0] + 0.5 * wd, a[:, 1] + 0.5 * hg
+    pcx, pcy = cx + (r[:, :, 0] * 0.1 + 0) * wd, cy + (r[:, :, 1] * 0.1 + 0) * hg
+    pw, ph = torch.exp(r[:, :, 2] * 0.2 + 0) * wd, torch.exp(r[:, :, 3] * 0.2 + 0) * hg
+    ref = torch.stack([pcx - 0.5 * pw, pcy - 0.5 * ph, pcx + 0.5 * pw, pcy + 0.5 * ph], dim=2)
+    assert torch.equal(dec, ref)
+
+
+@pytest.mark.parametrize('t', range(5))
+def test_nms_golden_torchvision(t):
+    g = load('nms')
+    boxes, idxs = cu(g[f'boxes{t}']), cu(g[f'idxs{t}'])
+    tied, uniq = cu(g[f'scores{t}_tied']), cu(g[f'scores{t}_unique'])
+    assert np.array_equal(D.nms(boxes, tied, 0.5).cpu().numpy(), g[f'nms{t}'])
+    assert np.array_equal(D.nms(boxes, tied, 0.3).cpu().numpy(), g[f'nms{t}_thr03'])
+    assert np.array_equal(D.batched_nms(boxes, tied, idxs, 0.5, mode=D.NMS_MODE_TRICK).cpu().numpy(), g[f'trick{t}'])
+    assert np.array_equal(D.batched_nms(boxes, uniq, idxs, 0.5, mode=D.NMS_MODE_TRICK).cpu().numpy(), g[f'trick{t}_unique'])
+    assert np.array_equal(D.batched_nms(boxes, uniq, idxs, 0.5, mode=D.NMS_MODE_VANILLA).cpu().numpy(), g[f'vanilla{t}'])
+    # torchvision's own switch: numel > limit -> vanilla
+    auto = D.batched_nms(boxes, uniq, idxs, 0.5, vanilla_numel_limit=4000).cpu().numpy()
+    assert np.array_equal(auto, g[f'vanilla{t}'] if boxes.numel() > 4000 else g[f'trick{t}_unique'])
+
+
+@pytest.mark.parametrize('K,ncls,seed', [(0, 1, 0), (1, 1, 1), (63, 3, 2), (64, 3, 3), (65, 3, 4), (1000, 20, 5), (4097, 80, 6)])
+def test_nms_random_vs_oracle(K, ncls, seed):
+    rng = np.random.default_rng(seed)
+    x1, y1 = rng.uniform(0, 300, K), rng.uniform(0, 300, K)
+    boxes = np.stack([x1, y1, x1 + rng.uniform(2, 120, K), y1 + rng.uniform(2, 120, K)], 1).astype(np.float32).reshape(-1, 4)
+    scores = (np.round(rng.uniform(0.05, 1, K) * 50) / 50).astype(np.float32)      # heavy score ties
+    idxs = rng.integers(0, ncls, K)
+    for mode, rule in ((D.NMS_MODE_TRICK, None), (D.NMS_MODE_VANILLA, None)):
+        got = D.batched_nms(cu(boxes), cu(scores), cu(idxs), 0.5, mode=mode).cpu().numpy()
+        if mode == D.NMS_MODE_TRICK:
+            ref = O.batched_nms(boxes, scores, idxs, 0.5, 'cuda') if boxes.size <= 100000 else None
+        else:
+            ref = O.batched_nms(boxes, scores, idxs, 0.5, 'cpu') if boxes.size > 4000 else None
+        if ref is not None:
+            assert np.array_equal(got, ref)
+    if K:
+        assert np.array_equal(D.nms(cu(boxes), cu(scores), 0.5).cpu().numpy(), O.nms(boxes, scores, 0.5))
+
+
+def same_device_rule(name):
+    return dict(trick=4000, vanilla=4000, none=4000)[name]
+
+
+@pytest.mark.parametrize('name', ['trick', 'vanilla', 'none'])
+def test_predict_golden_reference(name):
+    """ResNet.predict / Labeler.predict outputs recorded from the unmodified reference (CPU run: torchvision switches to the
+    vanilla branch above 4000 coordinates, so the same limit is passed here)."""
+    g = load('predict_' + name)
+    h, w = int(g['h']), int(g['w'])
+    anchors = cld.generate_anchors(h, w, DEV)
+    img = torch.zeros(1, 3, h, w, device=DEV)
+    s, b, l = D.labeler_predict(img, cu(g['probs']), cu(g['reg']), anchors, vanilla_numel_limit=4000)
+    assert np.array_equal(s.cpu().numpy(), g['scores'])
+    assert np.array_equal(l.cpu().numpy(), g['labels']) and l.dtype == torch.int64
+    boxes_close(b.cpu().numpy(), g['boxes'])
+    # logits entry (ResNet.predict): sigmoid on the device; ATen's sigmoid on the same device must agree bit for bit
+    s2, l2, b2 = D.predict_from_head(cu(g['logits']), cu(g['reg']), anchors, img, vanilla_numel_limit=4000)
+    probs_dev = torch.sigmoid(cu(g['logits']))
+    ref = O.detect(probs_dev.cpu().numpy(), g['reg'], O.anchors_for_image(h, w), h, w, is_logits=False, device_rule='cpu')
+    assert np.array_equal(s2.cpu().numpy(), ref['scores'])
+    assert np.array_equal(l2.cpu().numpy(), ref['labels'])
+    boxes_close(b2.cpu().numpy(), ref['boxes'])
+    with pytest.raises(ValueError):
+        D.predict_from_head(cu(g['logits']), cu(g['reg']), anchors, img, thresh=[0.05])
+
+
+def test_predict_method_dropin_and_empty():
+    h, w, C = 64, 96, 6
+    anchors = cld.generate_anchors(h, w, DEV)
+    A = anchors.shape[1]
+    gen = torch.Generator(device=DEV).manual_seed(1)
+    logits = torch.randn(1, A, C, device=DEV, generator=gen) - 12.0      # nothing passes 0.05
+    reg = torch.randn(1, A, 4, device=DEV, generator=gen) * 0.3
+
+    class Model:
+        def forward(self, img_batch, return_feat=False, return_anchor=True, enable_act=False):
+            return logits, reg, anchors
+    img = torch.zeros(1, 3, h, w, device=DEV)
+    s, l, b = D.predict(Model(), img)
+    assert s.shape == (0,) and l.shape == (0,) and l.dtype == torch.int64 and b.shape == (0, 4)
+    out = D.labeler_predict(img, torch.sigmoid(logits), reg, anchors)
+    assert all(t.numel() == 0 for t in out)
+
+
+@pytest.mark.parametrize('C,topk,mu', [(80, 1000, -4.0), (80, 0, -7.5), (20, 300, -5.0), (7, 50, -3.0), (5, 0, -6.0)])
+def test_detect_batch_vs_oracle(C, topk, mu):
+    """Seeded batches incl. class counts that are not multiples of 4, top-k on/off, heavy exact score ties from saturated
+    logits; per-image results equal to the oracle's on the same-device sigmoid."""
+    h, w, N = 256, 320, 3
+    anchors = cld.generate_anchors(h, w, DEV)
+    A = anchors.shape[1]
+    gen = torch.Generator(device=DEV).manual_seed(C * 13 + topk)
+    logits = torch.randn(N, A, C, device=DEV, generator=gen) * 2 + mu
+    logits[0, :40] = 25.0                     # saturated rows: every class ties at 1.0 -> label 0, anchor-order ties
+    logits[1, 5, :] = -2.0                    # a full row of equal logits above the threshold
+    reg = torch.randn(N, A, 4, device=DEV, generator=gen) * 0.5
+    got = D.detect_batch(logits, reg, anchors, h, w, pre_nms_topk=topk)
+    probs = torch.sigmoid(logits).cpu().numpy()
+    oa = O.anchors_for_image(h, w)
+    for j in range(N):
+        ref = O.detect(probs, reg.cpu().numpy(), oa, h, w, is_logits=False, pre_nms_topk=topk, image=j)
+        s, l, b = got[j]
+        assert np.array_equal(s.cpu().numpy(), ref['scores']), (j, s.shape, ref['scores'].shape)
+        assert np.array_equal(l.cpu().numpy(), ref['labels'])
+        boxes_close(b.cpu().numpy(), ref['boxes'])
+    # padded form agrees with the list form
+    ps, pl, pb, pc = D.detect_batch(logits, reg, anchors, h, w, pre_nms_topk=topk, return_padded=True)
+    for j in range(N):
+        k = int(pc[j])
+        assert k == got[j][0].shape[0] and torch.equal(ps[j, :k], got[j][0]) and torch.equal(pb[j, :k], got[j][2])
+
+
+def test_full_size_coco_shape_topk1000():
+    """BASELINE config 4 shape (800x1333, C=80, top-1000, per-class NMS), N=2: oracle comparison + NMS invariants."""
+    h, w, C, N, topk = 800, 1333, 80, 2, 1000
+    anchors = cld.generate_anchors(h, w, DEV)
+    A = anchors.shape[1]
+    gen = torch.Generator(device=DEV).manual_seed(4)
+    logits = torch.randn(N, A, C, device=DEV, generator=gen) * 2 - 4
+    reg = torch.randn(N, A, 4, device=DEV, generator=gen) * 0.5
+    got = D.detect_batch(logits, reg, anchors, h, w, pre_nms_topk=topk)
+    probs = torch.sigmoid(logits[:1]).cpu().numpy()
+    ref = O.detect(probs, reg[:1].cpu().numpy(), O.anchors_for_image(h, w), h, w, is_logits=False, pre_nms_topk=topk)
+    s, l, b = got[0]
+    assert np.array_equal(s.cpu().numpy(), ref['scores']) and np.array_equal(l.cpu().numpy(), ref['labels'])
+    boxes_close(b.cpu().numpy(), ref['boxes'])
+    for s, l, b in got:
+        assert 0 < s.shape[0] <= topk
+        assert torch.all(s[:-1] >= s[1:])                        # score-descending
+        # idempotence: NMS of the output keeps everything
+        again = D.batched_nms(b, s, l, 0.5)
+        assert again.shape[0] == s.shape[0]

@@ -1,0 +1,298 @@
+"""GPU parity tests of the loss half of the path (anchors, IoU/assign, focal + smooth-L1 fwd/bwd) against the CPU oracle
+and against the golden vectors of the unmodified reference.  Everything goes through the C ABI (ctypes -> libcldet.so).
+
+Bars: anchors, IoU values, assignment state/argmax/npos: BIT-EXACT.  Losses and gradients: 1e-5 relative (north_star).
+"""
+import numpy as np
+import pytest
+import torch
+
+import cl_object_detection_b200 as cld
+from oracle import head_oracle as O
+from tests.helpers import FOCAL_CASES, golden_params, load, synth_gt, synth_head
+
+pytestmark = pytest.mark.gpu
+DEV = 'cuda:0'
+
+
+def cu(x):
+    return torch.from_numpy(np.ascontiguousarray(x)).to(DEV)
+
+
+def head_params(g):
+    return golden_params(g, cls=cld.HeadParams)
+
+
+def check_grad_cls(got, ref):
+    """zero pattern identical; elementwise 1e-5 relative (tiny absolute floor = 1e-12 of the largest gradient)."""
+    got, ref = np.asarray(got), np.asarray(ref)
+    same_zeros = bool(np.array_equal(got == 0, ref == 0))
+    assert same_zeros, 'zero-gradient pattern (ignore / out-of-band) differs'
+    err = float((np.abs(got - ref) / (np.abs(ref) + 1e-12 * np.abs(ref).max() + 1e-45)).max())
+    assert err < 1e-5, err
+
+
+def check_grad_reg(got, ref):
+    """Smooth-L1's quadratic zone has gradient 9*(t - r)*w: the subtraction cancels, so an ulp-level difference in the
+    target t (log / divide chain, |t| up to ~8) appears as an ABSOLUTE error of ~9*ulp(t)*w ~ 5e-6*w on entries that can
+    be arbitrarily small.  Bar: 1e-5 relative, plus 1e-5 of the gradient scale w (= max |grad|, the linear zone)."""
+    got, ref = np.asarray(got), np.asarray(ref)
+    same_zeros = bool(np.array_equal(got == 0, ref == 0))
+    assert same_zeros
+    excess = float((np.abs(got - ref) - 1e-5 * np.abs(ref)).max())
+    assert excess <= 1e-5 * float(np.abs(ref).max()), (excess, float(np.abs(ref).max()))
+
+
+def check_rel(got, ref, tol=1e-5):
+    got, ref = np.asarray(got, np.float64), np.asarray(ref, np.float64)
+    assert got.shape == ref.shape
+    ok = bool(np.all(np.abs(got - ref) <= tol * np.abs(ref) + 1e-30))
+    assert ok, (got, ref)
+
+
+@pytest.mark.parametrize('h,w', [(64, 96), (128, 160), (33, 70), (512, 512), (800, 1333), (1333, 1333), (608, 1024), (1, 1)])
+def test_anchors_bit_exact(h, w):
+    got = cld.generate_anchors(h, w, DEV).cpu().numpy()
+    assert np.array_equal(got, O.anchors_for_image(h, w))
+    m = cld.Anchors()
+    img = torch.zeros(2, 3, h, w, device=DEV)
+    assert m(img) is m(img)            # cached per (H, W)
+    assert torch.equal(m(img), cu(got))
+
+
+def test_calc_iou_bit_exact_golden_and_random():
+    g = load('calc_iou')
+    assert np.array_equal(cld.calc_iou(cu(g['a']), cu(g['b'])).cpu().numpy(), g['iou'])
+    rng = np.random.default_rng(7)
+    a = O.anchors_for_image(256, 320)[0]
+    b = synth_gt(rng, 1, 37, 256, 320, 5, exact=True)[0, :, :4]
+    assert np.array_equal(cld.calc_iou(cu(a), cu(b)).cpu().numpy(), O.calc_iou(a, b))
+
+
+def run_assign(anchors, ann, C):
+    out = cld.iou_assign(cu(anchors), cu(ann), C)
+    return {k: v.cpu().numpy() for k, v in out.items()}
+
+
+def check_assign(anchors, ann, C):
+    got = run_assign(anchors, ann, C)
+    for j in range(ann.shape[0]):
+        ref = O.assign(anchors[0], ann[j])
+        assert got['nvalid'][j] == ref['valid']
+        if ref['valid'] == 0:
+            assert np.all(got['state'][j] == 3) and np.all(got['argmax'][j] == -1) and got['npos'][j] == 0
+            continue
+        assert np.array_equal(got['state'][j], ref['state'])
+        assert np.array_equal(got['argmax'][j], ref['argmax'])
+        assert np.array_equal(got['iou_max'][j], ref['iou_max'])
+        assert got['npos'][j] == ref['npos']
+        pos = ref['state'] == 1
+        assert np.array_equal(got['label'][j][pos], ref['label'][pos])
+    return got
+
+
+@pytest.mark.parametrize('case', FOCAL_CASES)
+def test_assign_bit_exact_golden(case):
+    g = load('focal_' + case)
+    anchors = O.anchors_for_image(int(g['h']), int(g['w']))
+    got = run_assign(anchors, g['ann'], g['cls'].shape[2])
+    assert np.array_equal(got['state'], g['state'])          # straight from the reference
+    assert np.array_equal(got['argmax'], g['argmax'])
+    check_assign(anchors, g['ann'], g['cls'].shape[2])
+
+
+@pytest.mark.parametrize('h,w,C,N,G,exact', [(512, 512, 20, 2, 10, False), (512, 512, 16, 4, 20, False),
+                                             (800, 1333, 80, 2, 20, False), (1333, 1333, 80, 1, 100, True),
+                                             (320, 320, 3, 2, 700, True)])
+def test_assign_bit_exact_config_shapes(h, w, C, N, G, exact):
+    rng = np.random.default_rng(h * 7 + G)
+    anchors = O.anchors_for_image(h, w)
+    ann = synth_gt(rng, N, G, h, w, C, empty=(N - 1,) if N > 1 else (), exact=exact)
+    # interleave padding rows, exact duplicates (ties -> first index) and a box equal to an anchor (IoU == 1)
+    if G >= 10:
+        ann[0, 3] = -1
+        ann[0, 5] = ann[0, 1]
+        ann[0, 7, :4] = anchors[0, anchors.shape[1] // 2]
+    got = check_assign(anchors, ann, C)
+    assert got['npos'][0] > 0
+
+
+def run_focal(g, params, weights=None, hint='mean'):
+    h, w = int(g['h']), int(g['w'])
+    anchors = cld.generate_anchors(h, w, DEV)
+    cls = cu(g['cls']).requires_grad_(True)
+    reg = cu(g['reg']).requires_grad_(True)
+    cls0, reg0 = cls.detach().clone(), reg.detach().clone()
+    fl = cld.FocalLoss(upstream_hint=hint)
+    out = fl(cls, reg, anchors, cu(g['ann']), int(g['cur_state']), params, float(g['progress']))
+    bg, fg = out['cls_loss']
+    if weights is None:
+        loss = bg.mean() + fg.mean() + out['reg_loss'].mean()
+        if 'enhance_on_new_loss' in out:
+            loss = loss + out['enhance_on_new_loss']
+    else:
+        wb, wf, wr, we = weights
+        loss = (bg * cu(wb).float()).sum() + (fg * cu(wf).float()).sum() + wr * out['reg_loss'].sum()
+        if 'enhance_on_new_loss' in out:
+            loss = loss + we * out['enhance_on_new_loss']
+    loss.backward()
+    assert torch.equal(cls.detach(), cls0) and torch.equal(reg.detach(), reg0), 'inputs were modified'
+    return out, cls.grad.cpu().numpy(), reg.grad.cpu().numpy()
+
+
+@pytest.mark.parametrize('case', FOCAL_CASES)
+def test_focal_golden_reference_weights(case):
+    """Non-uniform upstream weights (exercises the device-side re-weighting pass) vs the reference's autograd."""
+    g = load('focal_' + case)
+    out, gc, gr = run_focal(g, head_params(g), weights=(g['wb'], g['wf'], float(g['wr']), float(g['we'])))
+    check_rel(out['cls_loss'][0].detach().cpu().numpy(), g['bg'])
+    check_rel(out['cls_loss'][1].detach().cpu().numpy(), g['fg'])
+    check_rel(out['reg_loss'].detach().cpu().numpy(), g['reg_loss'])
+    check_grad_cls(gc, g['grad_cls'])
+    check_grad_reg(gr, g['grad_reg'])
+    if 'bg_masks' in g:
+        assert np.array_equal(out['bg_masks'].cpu().numpy(), g['bg_masks'])
+    if 'enhance_on_new_loss' in g:
+        check_rel(out['enhance_on_new_loss'].detach().cpu().numpy(), g['enhance_on_new_loss'])
+
+
+@pytest.mark.parametrize('case', FOCAL_CASES)
+def test_focal_mean_weights_vs_oracle(case):
+    """The hinted fast path (gradients baked in the forward pass, backward is a no-op check) vs the oracle."""
+    g = load('focal_' + case)
+    out, gc, gr = run_focal(g, head_params(g))
+    anchors = O.anchors_for_image(int(g['h']), int(g['w']))
+    ref = O.focal_loss(g['cls'], g['reg'], anchors, g['ann'], int(g['cur_state']), golden_params(g), w_enh=1.0)
+    check_rel(out['cls_loss'][0].detach().cpu().numpy(), ref['bg'])
+    check_rel(out['cls_loss'][1].detach().cpu().numpy(), ref['fg'])
+    check_rel(out['reg_loss'].detach().cpu().numpy(), ref['reg_loss'])
+    check_grad_cls(gc, ref['grad_cls'])
+    check_grad_reg(gr, ref['grad_reg'])
+
+
+@pytest.mark.parametrize('C', [20, 16, 80, 7, 1, 6])
+def test_focal_random_shapes_vs_oracle(C):
+    """Seeded synthetic batches (SURVEY 8d generator), incl. class counts that are not multiples of 4 (scalar path)."""
+    rng = np.random.default_rng(100 + C)
+    h, w, N, G = 160, 192, 3, 12
+    anchors = O.anchors_for_image(h, w)
+    _, probs, reg = synth_head(rng, N, anchors.shape[1], C, mu=-3.0, sigma=2.5)
+    ann = synth_gt(rng, N, G, h, w, C, empty=(2,))
+    g = dict(h=h, w=w, cls=probs, reg=reg, ann=ann, cur_state=0, progress=-1)
+    out, gc, gr = run_focal(g, cld.HeadParams())
+    ref = O.focal_loss(probs, reg, anchors, ann, 0, O.OracleParams())
+    check_rel(out['cls_loss'][0].detach().cpu().numpy(), ref['bg'])
+    check_rel(out['cls_loss'][1].detach().cpu().numpy(), ref['fg'])
+    check_rel(out['reg_loss'].detach().cpu().numpy(), ref['reg_loss'])
+    check_grad_cls(gc, ref['grad_cls'])
+    check_grad_reg(gr, ref['grad_reg'])
+
+
+def test_focal_pseudo_label_config2_vs_oracle():
+    """BASELINE config 2: scenario 15+1, state 1, pseudo-label GT rows merged after the real ones, C=16, 512x512."""
+    rng = np.random.default_rng(2)
+    h = w = 512
+    N, G, C = 4, 20, 16
+    anchors = O.anchors_for_image(h, w)
+    _, probs, reg = synth_head(rng, N, anchors.shape[1], C)
+    ann = synth_gt(rng, N, G, h, w, C, empty=(1,), pseudo_split=15)
+    g = dict(h=h, w=w, cls=probs, reg=reg, ann=ann, cur_state=1, progress=0.5)
+    out, gc, gr = run_focal(g, cld.HeadParams([0, 15], persuado_label=True))
+    ref = O.focal_loss(probs, reg, anchors, ann, 1, O.OracleParams([0, 15], persuado_label=True), 0.5)
+    check_rel(out['cls_loss'][0].detach().cpu().numpy(), ref['bg'])
+    check_rel(out['cls_loss'][1].detach().cpu().numpy(), ref['fg'])
+    check_rel(out['reg_loss'].detach().cpu().numpy(), ref['reg_loss'])
+    check_grad_cls(gc, ref['grad_cls'])
+    check_grad_reg(gr, ref['grad_reg'])
+
+
+def test_focal_deterministic_and_no_grad_mode():
+    g = load('focal_state0_voc')
+    o1, gc1, gr1 = run_focal(g, head_params(g))
+    o2, gc2, gr2 = run_focal(g, head_params(g))
+    assert np.array_equal(gc1, gc2) and np.array_equal(gr1, gr2)
+    assert torch.equal(o1['cls_loss'][0], o2['cls_loss'][0]) and torch.equal(o1['reg_loss'], o2['reg_loss'])
+    with torch.no_grad():
+        anchors = cld.generate_anchors(int(g['h']), int(g['w']), DEV)
+        o3 = cld.FocalLoss()(cu(g['cls']), cu(g['reg']), anchors, cu(g['ann']), 0, head_params(g))
+    assert torch.equal(o3['cls_loss'][0], o1['cls_loss'][0].detach())
+    assert torch.equal(o3['cls_loss'][1], o1['cls_loss'][1].detach())
+
+
+def test_clip_loss_caller_pattern():
+    """IL_Loss with clip_loss (losses.py:575-581): fg[mask].mean() changes the fg weights after the forward pass;
+    only the positive anchors are patched.  Compare with the oracle under the same weights."""
+    g = load('focal_state0_voc')
+    h, w = int(g['h']), int(g['w'])
+    anchors = cld.generate_anchors(h, w, DEV)
+    cls = cu(g['cls']).requires_grad_(True)
+    reg = cu(g['reg']).requires_grad_(True)
+    out = cld.FocalLoss()(cls, reg, anchors, cu(g['ann']), 0, head_params(g))
+    bg, fg = out['cls_loss']
+    mask = fg >= 0.75                      # drops image 0 (0.7427) and the empty image, keeps image 2 (0.7722)
+    assert mask.sum().item() == 1
+    loss = bg.mean() + fg[mask].mean() + out['reg_loss'].mean()
+    loss.backward()
+    N = 3
+    ref = O.focal_loss(g['cls'], g['reg'], O.anchors_for_image(h, w), g['ann'], 0, golden_params(g),
+                       w_bg=np.full(N, 1 / N), w_fg=mask.cpu().numpy().astype(np.float64), w_reg=1.0)
+    check_grad_cls(cls.grad.cpu().numpy(), ref['grad_cls'])
+    check_grad_reg(reg.grad.cpu().numpy(), ref['grad_reg'])
+
+
+def test_error_behaviour():
+    g = load('focal_state0_allvalid')
+    anchors = cld.generate_anchors(int(g['h']), int(g['w']), DEV)
+    fl = cld.FocalLoss(check_labels=True)
+    ann = g['ann'].copy()
+    ann[0, np.nonzero(ann[0, :, 4] != -1)[0][0], 4] = 99          # label outside [0, C)
+    # make sure the bad row wins at least one positive anchor
+    ann[0, :, :4][ann[0, :, 4] == 99] = anchors[0, 100].cpu().numpy()
+    with pytest.raises(IndexError):
+        fl(cu(g['cls']), cu(g['reg']), anchors, cu(ann), 0, cld.HeadParams())
+    with pytest.raises(TypeError):
+        cld.FocalLoss()(cu(g['cls']).double(), cu(g['reg']), anchors, cu(g['ann']), 0, cld.HeadParams())
+    with pytest.raises(ValueError):
+        cld.FocalLoss()(cu(g['cls']), cu(g['reg'])[:, :-1], anchors, cu(g['ann']), 0, cld.HeadParams())
+    # the device is still healthy after the errors
+    out = cld.FocalLoss()(cu(g['cls']), cu(g['reg']), anchors, cu(g['ann']), 0, cld.HeadParams())
+    check_rel(out['cls_loss'][0].cpu().numpy(), g['bg'])
+
+
+def test_full_size_properties_coco_shape():
+    """BASELINE config 3 shape (800x1333, C=80, A=200700), N=2: size-independent properties + sampled oracle check."""
+    rng = np.random.default_rng(3)
+    h, w, C, N, G = 800, 1333, 80, 2, 20
+    A = O.num_anchors(h, w)
+    anchors = cld.generate_anchors(h, w, DEV)
+    gen = torch.Generator(device=DEV).manual_seed(3)
+    probs = torch.sigmoid(torch.randn(N, A, C, device=DEV, generator=gen) * 2 - 4)
+    reg = torch.randn(N, A, 4, device=DEV, generator=gen)
+    ann = synth_gt(rng, N, G, h, w, C)
+    asg = check_assign(O.anchors_for_image(h, w), ann, C)           # full-size assignment: bit exact
+    cls = probs.clone().requires_grad_(True)
+    r = reg.clone().requires_grad_(True)
+    out = cld.FocalLoss()(cls, r, anchors, cu(ann), 0, cld.HeadParams())
+    bg, fg = out['cls_loss']
+    (bg.mean() + fg.mean() + out['reg_loss'].mean()).backward()
+    state = torch.from_numpy(asg['state']).to(DEV)
+    # ignore anchors: exactly zero gradient rows; non-positive anchors: zero regression gradient
+    assert torch.all(cls.grad[state == 2] == 0)
+    assert torch.all(r.grad[state != 1] == 0)
+    assert torch.all(r.grad[state == 1].abs().sum(1) > 0)
+    # out-of-band probabilities: exactly zero gradient
+    oob = (probs < 1e-4) | (probs > 1 - 1e-4)
+    assert oob.any() and torch.all(cls.grad[oob] == 0)
+    # linearity in the upstream weights: doubling the loss doubles every gradient bit-for-bit (power-of-two scale)
+    cls2 = probs.clone().requires_grad_(True)
+    r2 = reg.clone().requires_grad_(True)
+    out2 = cld.FocalLoss()(cls2, r2, anchors, cu(ann), 0, cld.HeadParams())
+    (2 * (out2['cls_loss'][0].mean() + out2['cls_loss'][1].mean() + out2['reg_loss'].mean())).backward()
+    assert torch.equal(cls2.grad, 2 * cls.grad) and torch.equal(r2.grad, 2 * r.grad)
+    # oracle on image 0 only (N=1 slice, weights adjusted to the batch's 1/N)
+    ref = O.focal_loss(probs[:1].cpu().numpy(), reg[:1].cpu().numpy(), O.anchors_for_image(h, w), ann[:1], 0,
+                       O.OracleParams(), w_bg=[1 / N], w_fg=[1 / N], w_reg=1.0 / N)
+    check_rel(bg[:1].detach().cpu().numpy(), ref['bg'])
+    check_rel(fg[:1].detach().cpu().numpy(), ref['fg'])
+    check_grad_cls(cls.grad[:1].cpu().numpy(), ref['grad_cls'])
+    check_grad_reg(r.grad[:1].cpu().numpy(), ref['grad_reg'])
