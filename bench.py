@@ -1,0 +1,400 @@
+#!/usr/bin/env python
+"""Benchmark of the detection-head hot path (BASELINE.json metric: detection-head images/sec + % HBM roofline).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload loss|decode]
+
+Default workload = BASELINE config 3: COCO-shaped focal loss fwd+bwd, 16 x 800x1333, C=80, A=200700 per GPU
+(weak scaling: every rank processes its own 16 images; one NCCL all-gather of the per-image loss terms per step).
+A step = anchors cached -> IoU/assign -> fused focal + smooth-L1 loss AND gradients -> backward weight check.
+
+value : device-resident throughput through the C ABI (inputs already in HBM), CUDA-event timed, max over ranks.
+e2e   : the same metric through the public Python drop-in (FocalLoss.forward + autograd) with HOST inputs: every step
+        copies cls/reg/annotations from pinned host memory and reads the loss back.
+roofline: the fused loss kernel's algorithmic bytes / its own CUDA-event time inside the timed loop.
+cpu_baseline: the numpy oracle port of the reference timed on this box's host cores (bounded sample), rank 0 only.
+--impl reference: times that CPU port only (the reference is pure Python/torch and /root/reference is not on the box).
+"""
+import argparse
+import ctypes
+import json
+import os
+import statistics
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+H, W, C, N_PER_GPU, GMAX = 800, 1333, 80, 16, 20
+METRIC = 'detection-head images/sec (loss fwd+bwd: IoU assign + focal + smooth-L1, grads for cls and reg)'
+
+
+def synth_annotations(rng, n, gmax, h, w, c, empty=(0,)):
+    ann = np.full((n, gmax, 5), -1.0, np.float32)
+    for j in range(n):
+        if j in empty:
+            continue
+        g = int(rng.integers(1, gmax + 1))
+        x1 = rng.uniform(0, 0.7 * w, g)
+        y1 = rng.uniform(0, 0.7 * h, g)
+        bw = rng.uniform(16, 0.3 * w + 16, g)
+        bh = rng.uniform(16, 0.3 * h + 16, g)
+        ann[j, :g] = np.stack([x1, y1, x1 + bw, y1 + bh, rng.integers(0, c, g).astype(np.float64)], 1)
+    return ann
+
+
+def peak_hbm():
+    p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))['hbm_gbs']), 'measured (MEASURED_PEAKS.json)'
+        except Exception:
+            pass
+    return 6650.0, 'fallback (B200_PROFILING.md)'
+
+
+def ncu_traffic(kernel):
+    p = os.path.join(ROOT, 'profiles', 'traffic.json')
+    if os.path.exists(p):
+        try:
+            return json.load(open(p)).get(kernel)
+        except Exception:
+            return None
+    return None
+
+
+class ClockSampler:
+    """Polls NVML (the API behind nvidia-smi) for SM clock and throttle reasons while the timed region runs."""
+    REASONS = {0x4: 'sw_power_cap', 0x8: 'hw_slowdown', 0x20: 'sw_thermal_slowdown', 0x40: 'hw_thermal_slowdown',
+               0x80: 'hw_power_brake_slowdown', 0x2: 'applications_clocks_setting', 0x10: 'sync_boost'}
+
+    def __init__(self, index):
+        self.samples, self.reasons, self.ok = [], set(), False
+        self._stop = threading.Event()
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception:
+            self.max_mhz = None
+        self.t = None
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                self.samples.append(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM))
+                r = self.nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                for bit, name in self.REASONS.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.002)
+
+    def start(self):
+        if self.ok:
+            self._stop.clear()
+            self.t = threading.Thread(target=self._run, daemon=True)
+            self.t.start()
+
+    def stop(self):
+        if self.t is not None:
+            self._stop.set()
+            self.t.join()
+            self.t = None
+
+    def summary(self):
+        if not self.samples:
+            return {'sm_mhz': None, 'sm_max_mhz': self.max_mhz, 'reasons': sorted(self.reasons), 'samples': 0}
+        return {'sm_mhz': statistics.median(self.samples), 'sm_max_mhz': self.max_mhz, 'reasons': sorted(self.reasons),
+                'samples': len(self.samples)}
+
+
+# --------------------------------------------------------------------------------------------------------------
+# CPU port of the reference (oracle) -- used ONLY for the reported baseline / --impl reference
+# --------------------------------------------------------------------------------------------------------------
+def cpu_reference_step(images, anchors, threads):
+    """One pass of the reference algorithm (numpy port) over `images` = list of (probs[1,A',C], reg[1,A',4], ann[1,G,5])."""
+    from concurrent.futures import ThreadPoolExecutor
+    from oracle import head_oracle as O
+    params = O.OracleParams()
+    n = len(images)
+
+    def one(item):
+        p, r, a = item
+        out = O.focal_loss(p, r, anchors, a, 0, params, w_bg=[1.0 / n], w_fg=[1.0 / n], w_reg=1.0 / n)
+        return float(out['bg'][0]), float(out['fg'][0])
+    if threads <= 1:
+        return [one(it) for it in images]
+    with ThreadPoolExecutor(threads) as ex:
+        return list(ex.map(one, images))
+
+
+def make_cpu_images(count, frac=1.0, seed=1234):
+    """`count` COCO-shaped images; frac < 1 keeps only the first frac*A anchors of each (every anchor is independent
+    work, so throughput in images/s is (count*frac)/time)."""
+    from oracle import head_oracle as O
+    rng = np.random.default_rng(seed)
+    a_full = O.num_anchors(H, W)
+    a = max(1, int(a_full * frac))
+    anchors = O.anchors_for_image(H, W)[:, :a]
+    imgs = []
+    for i in range(count):
+        logits = rng.normal(-4.0, 2.0, (1, a, C)).astype(np.float32)
+        probs = (1.0 / (1.0 + np.exp(-logits))).astype(np.float32)
+        reg = rng.normal(0, 1, (1, a, 4)).astype(np.float32)
+        imgs.append((probs, reg, synth_annotations(rng, 1, GMAX, H, W, C, empty=())))
+    return imgs, anchors, a / a_full
+
+
+def time_cpu_reference(steps, warmup, images_per_step, threads, frac=1.0):
+    imgs, anchors, f = make_cpu_images(images_per_step, frac)
+    for _ in range(warmup):
+        cpu_reference_step(imgs, anchors, threads)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        cpu_reference_step(imgs, anchors, threads)
+    dt = time.perf_counter() - t0
+    return images_per_step * f * steps / dt, dt / steps, f
+
+
+def run_reference(args):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return 0
+    cores = os.cpu_count() or 1
+    threads = max(1, min(cores, 16))
+    images_per_step = threads
+    # keep the whole run to a few minutes: probe a quarter-size step, then pick the anchor fraction of the per-step sample
+    _, probe_step, f0 = time_cpu_reference(1, 0, images_per_step, threads, 0.25)
+    full_step = probe_step / f0
+    budget = 150.0
+    frac = max(0.02, min(1.0, budget / (full_step * (args.steps + args.warmup))))
+    val, per_step, f = time_cpu_reference(args.steps, args.warmup, images_per_step, threads, frac)
+    sample = ('%d images x %.0f%% of the anchors per step (800x1333, C=80, A=200700 full), numpy port of FocalLoss fwd+bwd, '
+              '%d threads' % (images_per_step, f * 100, threads))
+    line = {'impl': 'reference', 'metric': METRIC, 'value': val, 'unit': 'images/s', 'n_gpus': args.gpus, 'steps': args.steps,
+            'warmup': args.warmup, 'ms_per_step': per_step * 1e3, 'higher_is_better': True, 'scaling': 'weak',
+            'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+            'config': {'workload': 'coco_loss_fwd_bwd 800x1333 C=80 A=200700 G<=20 (BASELINE config 3)',
+                       'images_per_step': images_per_step * f},
+            'cpu_baseline': {'value': val, 'unit': 'images/s', 'cores': threads, 'kind': 'port', 'sample': sample,
+                             'host_cores': cores},
+            'e2e': {'value': val, 'unit': 'images/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+            'gpu_launches': 0}
+    print(json.dumps(line))
+    return 0
+
+
+# --------------------------------------------------------------------------------------------------------------
+# our arm
+# --------------------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    import cl_object_detection_b200 as cld
+    from cl_object_detection_b200 import _lib
+    from cl_object_detection_b200.params import to_loss_params
+
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    if not torch.cuda.is_available():
+        raise SystemExit('bench.py needs a CUDA device (there is no CPU fallback for the product path)')
+    torch.cuda.set_device(local_rank)
+    dev = torch.device('cuda', local_rank)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+    lib = _lib.load()
+
+    n = N_PER_GPU
+    anchors = cld.generate_anchors(H, W, dev)
+    a = anchors.shape[1]
+    gen = torch.Generator(device=dev).manual_seed(3000 + rank)
+    probs = torch.sigmoid(torch.randn(n, a, C, device=dev, generator=gen) * 2.0 - 4.0)
+    reg = torch.randn(n, a, 4, device=dev, generator=gen)
+    ann_np = synth_annotations(np.random.default_rng(3000 + rank), n, GMAX, H, W, C, empty=(0,))
+    ann = torch.from_numpy(ann_np).to(dev)
+    params = cld.HeadParams()
+    lp = to_loss_params(params, 0, C)
+
+    # ---- device-resident step through the C ABI, stage by stage so the loss kernel can be event-timed ----
+    n_global = n * world
+    weights = torch.full((4, n), 1.0 / n_global, device=dev)
+    weights[3] = 1.0
+    baked = weights.clone()
+    gcls = torch.empty_like(probs)
+    greg = torch.empty_like(reg)
+    losses = torch.empty((4, n), device=dev)
+    gathered = torch.empty((world, 4, n), device=dev) if world > 1 else None
+    meta = torch.empty((n, a), dtype=torch.int32, device=dev)
+    npos = torch.zeros(n, dtype=torch.int32, device=dev)
+    nvalid = torch.empty(n, dtype=torch.int32, device=dev)
+    ws_bytes = lib.cldet_focal_loss_workspace_bytes(n, a)
+    ws = torch.zeros(ws_bytes, dtype=torch.uint8, device=dev)
+    stream = torch.cuda.current_stream().cuda_stream
+    ev_a = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    ev_b = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    ev_c = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+
+    def step(i=None):
+        npos.zero_()
+        if i is not None:
+            ev_a[i].record()
+        _lib.check(lib.cldet_iou_assign(anchors.data_ptr(), a, ann.data_ptr(), n, GMAX, C, meta.data_ptr(), None, None,
+                                        npos.data_ptr(), nvalid.data_ptr(), stream))
+        if i is not None:
+            ev_b[i].record()
+        _lib.check(lib.cldet_focal_loss_from_assignment(
+            probs.data_ptr(), reg.data_ptr(), anchors.data_ptr(), ann.data_ptr(), n, a, C, GMAX, lp, weights.data_ptr(),
+            gcls.data_ptr(), greg.data_ptr(), losses.data_ptr(), meta.data_ptr(), None, npos.data_ptr(), None, None,
+            ws.data_ptr(), ws_bytes, stream))
+        if i is not None:
+            ev_c[i].record()
+        if world > 1:   # every rank gets every image's (bg, fg, reg) terms: what IL_Loss's mean / clip_loss needs
+            dist.all_gather_into_tensor(gathered, losses)
+        # backward: upstream weights are verified on the device; unchanged -> nothing is recomputed
+        _lib.check(lib.cldet_focal_loss_reweight(probs.data_ptr(), reg.data_ptr(), anchors.data_ptr(), ann.data_ptr(), n, a, C,
+                                                 GMAX, lp, weights.data_ptr(), baked.data_ptr(), gcls.data_ptr(),
+                                                 greg.data_ptr(), meta.data_ptr(), None, npos.data_ptr(), stream))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    sampler = ClockSampler(local_rank)
+    barrier()
+    sampler.start()
+    t_start = torch.cuda.Event(enable_timing=True)
+    t_end = torch.cuda.Event(enable_timing=True)
+    t_start.record()
+    for i in range(args.steps):
+        step(i)
+    t_end.record()
+    barrier()
+    sampler.stop()
+    total_ms = t_start.elapsed_time(t_end)
+    assign_ms = sum(x.elapsed_time(y) for x, y in zip(ev_a, ev_b)) / args.steps
+    loss_ms = sum(x.elapsed_time(y) for x, y in zip(ev_b, ev_c)) / args.steps
+    if len(sampler.samples) < 3:      # timed region shorter than the sampling period: keep sampling the same step under load
+        sampler.start()
+        t0 = time.perf_counter()
+        while time.perf_counter() - t0 < 0.3:
+            step()
+        torch.cuda.synchronize()
+        sampler.stop()
+    clocks = sampler.summary()
+
+    # ---- end to end through the public drop-in, host buffers in, losses out ----
+    e2e_steps = max(3, min(args.steps, 10))
+    h_probs = probs.cpu().pin_memory()
+    h_reg = reg.cpu().pin_memory()
+    h_ann = torch.from_numpy(ann_np).pin_memory()
+    h_out = torch.empty(3, dtype=torch.float32).pin_memory()
+    fl = cld.FocalLoss(upstream_hint=weights)
+    d_probs = torch.empty_like(probs)
+    d_reg = torch.empty_like(reg)
+    d_ann = torch.empty_like(ann)
+
+    def e2e_step():
+        d_probs.copy_(h_probs, non_blocking=True)
+        d_reg.copy_(h_reg, non_blocking=True)
+        d_ann.copy_(h_ann, non_blocking=True)
+        p = d_probs.detach().requires_grad_(True)
+        r = d_reg.detach().requires_grad_(True)
+        out = fl(p, r, anchors, d_ann, 0, params)
+        bg, fg = out['cls_loss']
+        if world > 1:
+            parts = torch.stack([bg.detach(), fg.detach()])
+            allp = torch.empty((world,) + tuple(parts.shape), device=dev)
+            dist.all_gather_into_tensor(allp, parts)
+        terms = torch.stack([bg.sum(), fg.sum(), out['reg_loss'].sum() * n]) / n_global
+        g = torch.autograd.grad(terms.sum(), [p, r])
+        h_out.copy_(terms.detach(), non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return g
+
+    for _ in range(2):
+        e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        e2e_step()
+    barrier()
+    e2e_s = (time.perf_counter() - t0) / e2e_steps
+    h2d = h_probs.numel() * 4 + h_reg.numel() * 4 + h_ann.numel() * 4
+    d2h = h_out.numel() * 4
+
+    # ---- max over ranks ----
+    stats = torch.tensor([total_ms, e2e_s, loss_ms, assign_ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(stats, op=dist.ReduceOp.MAX)
+    total_ms, e2e_s, loss_ms, assign_ms = [float(x) for x in stats.tolist()]
+    ms_per_step = total_ms / args.steps
+    value = n_global / (ms_per_step * 1e-3)
+
+    peak, peak_src = peak_hbm()
+    kernel_bytes = n * (8 * a * C + 20 * a)                    # loss kernel: p read + dL/dp write + assignment word + dL/dreg
+    path_bytes = n * (8 * a * C + 48 * a + 20 * GMAX)          # SURVEY 8(d) figure for the whole loss path
+    achieved = kernel_bytes / (loss_ms * 1e-3) / 1e9
+    traffic = ncu_traffic('focal_loss_kernel')
+    roofline = {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
+                'traffic': traffic, 'kernel': 'focal_loss_kernel<4,true,false,true>', 'kernel_ms': loss_ms,
+                'assign_kernel_ms': assign_ms, 'algorithmic_bytes_per_launch': kernel_bytes, 'peak_source': peak_src,
+                'path_frac': path_bytes / ((loss_ms + assign_ms) * 1e-3) / 1e9 / peak,
+                'step_frac': path_bytes / (ms_per_step * 1e-3) / 1e9 / peak}
+
+    if rank == 0:
+        cores = os.cpu_count() or 1
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            thr = max(1, min(cores, 8))
+            v, per, _ = time_cpu_reference(steps=2, warmup=0, images_per_step=thr, threads=thr)
+            cpu = {'value': v, 'unit': 'images/s', 'cores': thr, 'kind': 'port', 'host_cores': cores,
+                   'sample': '2 steps x %d COCO-shaped images (800x1333, C=80, A=200700), numpy port of FocalLoss fwd+bwd, '
+                             '%d threads' % (thr, thr)}
+        line = {'metric': METRIC, 'value': value, 'unit': 'images/s', 'n_gpus': world, 'steps': args.steps,
+                'warmup': max(args.warmup, 3), 'ms_per_step': ms_per_step, 'higher_is_better': True, 'scaling': 'weak',
+                'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+                'config': {'workload': 'coco_loss_fwd_bwd: %d x 800x1333 per GPU, C=80, A=%d, G<=%d (BASELINE config 3)' % (n, a, GMAX),
+                           'images_per_gpu': n, 'global_batch': n_global, 'parallelism': 'image-sharded dp%d' % world,
+                           'l2': 'inputs (%.2f GB per GPU) are larger than the 126 MB L2; no flush needed' % (probs.numel() * 4 / 1e9)},
+                'clocks': clocks,
+                'e2e': {'value': n_global / e2e_s, 'unit': 'images/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
+                        'ms_per_step': e2e_s * 1e3, 'steps': e2e_steps},
+                'gpu_launches': 4 * args.steps,
+                'roofline': roofline}
+        if cpu is not None:
+            line['cpu_baseline'] = cpu
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=100)
+    ap.add_argument('--warmup', type=int, default=10)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    args = ap.parse_args()
+    if args.impl == 'reference':
+        return run_reference(args)
+    return run_ours(args)
+
+
+if __name__ == '__main__':
+    sys.exit(main())

@@ -1,0 +1,113 @@
+"""Image-sharded data parallelism for the loss path (the reference itself is single-GPU).
+
+Every quantity of FocalLoss is per image (per-image GT, per-image npos normaliser), so the batch is split into
+contiguous image shards, one process per GPU, and the ONLY exchange is an all-gather of the per-image terms
+(bg_j, fg_j, reg_j, enhance_j: <= 4*N floats) so that every rank can form exactly the reductions the caller
+applies (IL_Loss: .mean() over the batch, or the clip_loss mask on per-image fg, losses.py:575-588).
+Gradients of the head outputs never leave the rank that owns the images.
+"""
+import torch
+import torch.distributed as dist
+import torch.nn as nn
+
+
+def shard_sizes(n_global, world):
+    """Contiguous shards, remainder spread over the first ranks (same rule on every rank)."""
+    base, rem = divmod(int(n_global), int(world))
+    return [base + (1 if r < rem else 0) for r in range(world)]
+
+
+def shard_slice(n_global, world, rank):
+    sizes = shard_sizes(n_global, world)
+    start = sum(sizes[:rank])
+    return slice(start, start + sizes[rank])
+
+
+class _GatherTerms(torch.autograd.Function):
+    """local [K, n_r] -> global [K, N] in rank order.  Backward hands each rank the slice of the incoming gradient
+    that belongs to its own images: the loss every rank forms from the gathered terms is the same function, so
+    d(loss)/d(local terms) is that slice and no reduction is needed."""
+
+    @staticmethod
+    def forward(ctx, local, sizes, rank, group):
+        k = local.shape[0]
+        nmax = max(sizes)
+        world = len(sizes)
+        padded = local.new_zeros((k, nmax))
+        padded[:, :local.shape[1]] = local
+        if world > 1:
+            flat = local.new_empty((world * k, nmax))
+            dist.all_gather_into_tensor(flat, padded.contiguous(), group=group)
+            out = flat.view(world, k, nmax)
+        else:
+            out = padded.unsqueeze(0)
+        ctx.sizes, ctx.rank = sizes, rank
+        return torch.cat([out[r, :, :sizes[r]] for r in range(world)], dim=1)
+
+    @staticmethod
+    def backward(ctx, grad):
+        start = sum(ctx.sizes[:ctx.rank])
+        return grad[:, start:start + ctx.sizes[ctx.rank]].contiguous(), None, None, None
+
+
+def gather_terms(local, sizes, rank, group=None):
+    return _GatherTerms.apply(local, sizes, rank, group)
+
+
+class ShardedFocalLoss(nn.Module):
+    """FocalLoss over an image-sharded batch.  Each rank passes ITS shard (classifications[n_r,A,C], ...); the result
+    dict has the reference's layout for the GLOBAL batch: 'cls_loss' = (bg[N], fg[N]) in global image order,
+    'reg_loss' = [1] mean over all N images, 'enhance_on_new_loss' = global sum.  'bg_masks' stays local (it is
+    consumed against local tensors by the distillation terms).
+
+    The gradients that flow back are d(global loss)/d(local head outputs); SUM parameter gradients over ranks to get
+    the single-process gradient (with DDP's averaging, scale the loss by world_size).
+    """
+
+    def __init__(self, local_loss=None, group=None):
+        super().__init__()
+        if local_loss is None:
+            from .losses import FocalLoss
+            local_loss = FocalLoss(upstream_hint='mean')
+        self.local_loss = local_loss
+        self.group = group
+
+    def forward(self, classifications, regressions, anchors, annotations, cur_state, params, progress=-1):
+        world = dist.get_world_size(self.group) if dist.is_initialized() else 1
+        rank = dist.get_rank(self.group) if dist.is_initialized() else 0
+        n_local = classifications.shape[0]
+        if world > 1:
+            t = torch.tensor([n_local], dtype=torch.int64, device=classifications.device)
+            all_n = [torch.zeros_like(t) for _ in range(world)]
+            dist.all_gather(all_n, t, group=self.group)
+            sizes = [int(x.item()) for x in all_n]
+        else:
+            sizes = [n_local]
+        n_global = sum(sizes)
+        if hasattr(self.local_loss, 'upstream_hint') and isinstance(self.local_loss.upstream_hint, str):
+            # the caller's mean runs over the GLOBAL batch: bake 1/N_global into the fused gradients
+            w = torch.full((4, n_local), 1.0 / n_global, dtype=torch.float32, device=classifications.device)
+            w[3] = 1.0
+            self.local_loss.upstream_hint = w
+            try:
+                out = self.local_loss(classifications, regressions, anchors, annotations, cur_state, params, progress)
+            finally:
+                self.local_loss.upstream_hint = 'mean'
+        else:
+            out = self.local_loss(classifications, regressions, anchors, annotations, cur_state, params, progress)
+        bg, fg = out['cls_loss']
+        # per-image regression terms: the reference returns only their mean; recover reg_j * 1 from the local mean
+        reg_local = getattr(self.local_loss, 'last_reg_per_image', None)
+        if reg_local is None:
+            reg_local = out['reg_loss'].expand(n_local)          # generic local loss: treat the mean as every image's term
+        terms = [bg, fg, reg_local]
+        has_enh = 'enhance_on_new_loss' in out
+        if has_enh:
+            terms.append(out['enhance_on_new_loss'].reshape(1).expand(n_local) / max(n_local, 1))
+        g = gather_terms(torch.stack(terms), sizes, rank, self.group)
+        result = {'cls_loss': (g[0], g[1]), 'reg_loss': g[2].mean(dim=0, keepdim=True)}
+        if has_enh:
+            result['enhance_on_new_loss'] = g[3].sum()
+        if 'bg_masks' in out:
+            result['bg_masks'] = out['bg_masks']
+        return result

@@ -204,5 +204,5 @@ class FocalLoss(nn.Module):
                 result['bg_masks'] = outs[6].bool()[nvalid > 0]
             if params['enhance_on_new']:
                 result['enhance_on_new_loss'] = enh_j.sum()
-        self.last_npos, self.last_nvalid = npos, nvalid
+        self.last_npos, self.last_nvalid, self.last_reg_per_image = npos, nvalid, reg_j
         return result
