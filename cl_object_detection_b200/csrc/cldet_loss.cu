@@ -53,7 +53,7 @@ __device__ __forceinline__ float log_fast(float q) {
     const int i = __float_as_int(q);
     const int e = (i - 0x3f2aaaab) & 0xff800000;
     const float m = __int_as_float(i - e);
-    const float fe = (float)(e >> 23);
+    const float fe = (float)e;                      // exponent * 2^23, exact
     const float f = m - 1.0f;
     const float s = f * f;
     float r = -1.492298990e-01f;
@@ -64,7 +64,13 @@ __device__ __forceinline__ float log_fast(float q) {
     r = fmaf(r, f, 3.333675861e-01f);
     r = fmaf(r, f, -0.5f);
     r = fmaf(r, s, f);
-    return fmaf(fe, 0.693147182f, r);
+    return fmaf(fe, 0.693147182f * 1.1920928955078125e-7f, r);   // ln2 * 2^-23
+}
+
+__device__ __forceinline__ float __frcp_rn_fast(float x) {
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
 }
 
 template <bool GAMMA2>
@@ -92,6 +98,21 @@ __device__ __forceinline__ void neg_element(float p_raw, float alpha, float gamm
         const float g = alpha * fmaf(dpw, nl, __fdividef(pw, q)) * scale;
         grad = (p == p_raw) ? g : 0.0f;
     }
+}
+
+// Hot-path form of the same element for gamma == 2: the per-image constant alpha is factored out of the loss
+// (raw += p^2 * (-ln(1-p)), multiplied by alpha once per block) and folded into `as` = alpha * upstream / npos for
+// the gradient: g = as * p * (2*(-ln(1-p)) + p/(1-p)).  ~26 instructions per element.
+template <bool GRAD>
+__device__ __forceinline__ float neg_element_raw(float p_raw, float as, float& raw) {
+    const float p = fminf(fmaxf(p_raw, 1e-4f), 0.9999f);
+    const float q = 1.0f - p;
+    const float L = log_fast(q);                     // ln(1-p) <= 0
+    raw = fmaf(-(p * p), L, raw);
+    if (!GRAD) return 0.0f;
+    const float t = fmaf(L, -2.0f, p * __frcp_rn_fast(q));
+    const float g = (as * p) * t;
+    return (p == p_raw) ? g : 0.0f;
 }
 
 // Element with target 1.  f is the focal-weight base of the three reference branches (losses.py:352-366).
@@ -142,6 +163,7 @@ struct ImageScales {
 
 struct Acc {
     float bg, fg, reg, enh;
+    float raw[4];     // hot path: sum of p^2 * (-ln(1-p)) without alpha, four independent chains
 };
 
 // One element of the classification map.  `c` is the class column, `m` the anchor's assignment word.
@@ -291,6 +313,9 @@ __device__ __forceinline__ void process_chunk(const LossArgs& a, int j, int64_t 
     const int64_t base = ((int64_t)j * a.A + a0) * a.C;
     const uint32_t count = (uint32_t)((a1 - a0) * a.C);
     const uint32_t C = (uint32_t)a.C;
+    // an image without GT has every anchor in state EMPTY: alpha becomes (1 - alpha) for the whole image (losses.py:293-296)
+    const float alpha_img = (meta_state(meta_j[0]) == CLDET_STATE_EMPTY) ? 1.0f - a.p.alpha : a.p.alpha;
+    const float as_bg = alpha_img * sc.s_bg;
     if (VEC == 4) {
         const float4* src = reinterpret_cast<const float4*>(a.cls + base);
         float4* dst = GRAD ? reinterpret_cast<float4*>(a.gcls + base) : nullptr;
@@ -317,13 +342,25 @@ __device__ __forceinline__ void process_chunk(const LossArgs& a, int j, int64_t 
             for (int u = 0; u < kUnroll; ++u) {
                 const uint32_t v = v0 + u * kLossThreads;
                 if (v < nvec) {
-                    float iou = 1.0f;
-                    if (need_iou && meta_state(mm[u]) == CLDET_STATE_POS) iou = a.iou_max[(int64_t)j * a.A + a0 + row[u]];
-                    float4 g;
-                    g.x = cls_element<GAMMA2, VARIANTS, GRAD>(x[u].x, (int)col[u] + 0, mm[u], a, sc, iou, acc);
-                    g.y = cls_element<GAMMA2, VARIANTS, GRAD>(x[u].y, (int)col[u] + 1, mm[u], a, sc, iou, acc);
-                    g.z = cls_element<GAMMA2, VARIANTS, GRAD>(x[u].z, (int)col[u] + 2, mm[u], a, sc, iou, acc);
-                    g.w = cls_element<GAMMA2, VARIANTS, GRAD>(x[u].w, (int)col[u] + 3, mm[u], a, sc, iou, acc);
+                    const uint32_t st = meta_state(mm[u]);
+                    float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+                    // the vector holds the target-1 element of a positive anchor?
+                    const bool special = (st == CLDET_STATE_POS) && (meta_label(mm[u]) - col[u] < 4u);
+                    if (GAMMA2 && !VARIANTS && !special) {
+                        if (st != CLDET_STATE_IGNORE) {      // bg anchor, empty image, or the target-0 part of a positive row
+                            g.x = neg_element_raw<GRAD>(x[u].x, as_bg, acc.raw[0]);
+                            g.y = neg_element_raw<GRAD>(x[u].y, as_bg, acc.raw[1]);
+                            g.z = neg_element_raw<GRAD>(x[u].z, as_bg, acc.raw[2]);
+                            g.w = neg_element_raw<GRAD>(x[u].w, as_bg, acc.raw[3]);
+                        }
+                    } else {
+                        float iou = 1.0f;
+                        if (need_iou && st == CLDET_STATE_POS) iou = a.iou_max[(int64_t)j * a.A + a0 + row[u]];
+                        g.x = cls_element<GAMMA2, VARIANTS, GRAD>(x[u].x, (int)col[u] + 0, mm[u], a, sc, iou, acc);
+                        g.y = cls_element<GAMMA2, VARIANTS, GRAD>(x[u].y, (int)col[u] + 1, mm[u], a, sc, iou, acc);
+                        g.z = cls_element<GAMMA2, VARIANTS, GRAD>(x[u].z, (int)col[u] + 2, mm[u], a, sc, iou, acc);
+                        g.w = cls_element<GAMMA2, VARIANTS, GRAD>(x[u].w, (int)col[u] + 3, mm[u], a, sc, iou, acc);
+                    }
                     if (GRAD) st_stream_f4(dst + v, g);
                 }
             }
@@ -355,8 +392,12 @@ __global__ void __launch_bounds__(kLossThreads) focal_loss_kernel(const LossArgs
     const int npos = a.npos[j];
     const ImageScales sc = image_scales(a.weights, a.N, j, npos);
 
-    Acc acc = {0.f, 0.f, 0.f, 0.f};
+    Acc acc = {0.f, 0.f, 0.f, 0.f, {0.f, 0.f, 0.f, 0.f}};
     process_chunk<VEC, GAMMA2, VARIANTS, GRAD>(a, j, a0, a1, sc, 0, acc);
+    {
+        const float alpha_img = (meta_state(a.meta[(int64_t)j * a.A]) == CLDET_STATE_EMPTY) ? 1.0f - a.p.alpha : a.p.alpha;
+        acc.bg += alpha_img * ((acc.raw[0] + acc.raw[1]) + (acc.raw[2] + acc.raw[3]));
+    }
 
     // block reduction of the four sums
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -424,7 +465,7 @@ __global__ void __launch_bounds__(kLossThreads) focal_reweight_kernel(const Loss
     const int64_t a0 = (int64_t)blockIdx.x * a.anchors_per_block;
     const int64_t a1 = min(a.A, a0 + a.anchors_per_block);
     const ImageScales sc = image_scales(a.weights, a.N, j, a.npos[j]);
-    Acc acc = {0.f, 0.f, 0.f, 0.f};
+    Acc acc = {0.f, 0.f, 0.f, 0.f, {0.f, 0.f, 0.f, 0.f}};
     process_chunk<VEC, GAMMA2, VARIANTS, true>(a, j, a0, a1, sc, bg_changed ? 1 : 2, acc);
 }
 
