@@ -274,19 +274,49 @@ __device__ __forceinline__ ImageScales image_scales(const float* w, int N, int j
     return sc;
 }
 
+constexpr int kMaxAnchorsPerBlock = 4096;     // assignment words of one chunk staged in shared memory (16 KB)
+constexpr uint32_t kTile = kLossThreads * kUnroll;   // float4 vectors per fully unrolled tile
+
+// One 128-bit vector (4 consecutive classes of one anchor; C % 4 == 0 so it never straddles anchors).
+template <bool GAMMA2, bool VARIANTS, bool GRAD>
+__device__ __forceinline__ float4 cls_vec4(const float4 x, uint32_t m, uint32_t col, int64_t anchor_abs, const LossArgs& a,
+                                           const ImageScales& sc, float as_bg, bool need_iou, Acc& acc) {
+    const uint32_t st = meta_state(m);
+    float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+    // does the vector hold the target-1 element of a positive anchor?
+    const bool special = (st == CLDET_STATE_POS) && (meta_label(m) - col < 4u);
+    if (GAMMA2 && !VARIANTS && !special) {
+        if (st != CLDET_STATE_IGNORE) {      // bg anchor, empty image, or the target-0 part of a positive row
+            g.x = neg_element_raw<GRAD>(x.x, as_bg, acc.raw[0]);
+            g.y = neg_element_raw<GRAD>(x.y, as_bg, acc.raw[1]);
+            g.z = neg_element_raw<GRAD>(x.z, as_bg, acc.raw[2]);
+            g.w = neg_element_raw<GRAD>(x.w, as_bg, acc.raw[3]);
+        }
+    } else {
+        float iou = 1.0f;
+        if (need_iou && st == CLDET_STATE_POS) iou = a.iou_max[anchor_abs];
+        g.x = cls_element<GAMMA2, VARIANTS, GRAD>(x.x, (int)col + 0, m, a, sc, iou, acc);
+        g.y = cls_element<GAMMA2, VARIANTS, GRAD>(x.y, (int)col + 1, m, a, sc, iou, acc);
+        g.z = cls_element<GAMMA2, VARIANTS, GRAD>(x.z, (int)col + 2, m, a, sc, iou, acc);
+        g.w = cls_element<GAMMA2, VARIANTS, GRAD>(x.w, (int)col + 3, m, a, sc, iou, acc);
+    }
+    return g;
+}
+
 // mode 0: everything (regression + classification, losses + grads)
 // mode 1: gradients only, classification + regression   (reweight: bg weight changed)
 // mode 2: gradients only, positive anchors only          (reweight: only fg / reg weight changed)
 template <int VEC, bool GAMMA2, bool VARIANTS, bool GRAD>
 __device__ __forceinline__ void process_chunk(const LossArgs& a, int j, int64_t a0, int64_t a1, const ImageScales& sc,
-                                              int mode, Acc& acc) {
+                                              int mode, Acc& acc, uint32_t* smeta) {
     const int tid = threadIdx.x;
     const uint32_t* meta_j = a.meta + (int64_t)j * a.A;
     const bool need_iou = VARIANTS && a.p.incremental && a.p.decrease_positive_by_iou;
 
-    // ---- regression rows + bg mask: one thread per anchor ----
+    // ---- regression rows + bg mask: one thread per anchor; the assignment words are staged for the sweep below ----
     for (int64_t an = a0 + tid; an < a1; an += kLossThreads) {
         const uint32_t m = meta_j[an];
+        smeta[an - a0] = m;
         const uint32_t st = meta_state(m);
         if (mode == 0 && a.bg_mask) a.bg_mask[(int64_t)j * a.A + an] = (st != CLDET_STATE_POS) ? 1 : 0;
         float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -308,61 +338,62 @@ __device__ __forceinline__ void process_chunk(const LossArgs& a, int j, int64_t 
             *reinterpret_cast<float4*>(a.greg + ((int64_t)j * a.A + an) * 4) = g;
     }
     if (mode == 2) return;
+    __syncthreads();
 
     // ---- classification map: flat vectorised sweep over this chunk's (a1-a0)*C elements ----
     const int64_t base = ((int64_t)j * a.A + a0) * a.C;
     const uint32_t count = (uint32_t)((a1 - a0) * a.C);
     const uint32_t C = (uint32_t)a.C;
+    const int64_t abs0 = (int64_t)j * a.A + a0;
     // an image without GT has every anchor in state EMPTY: alpha becomes (1 - alpha) for the whole image (losses.py:293-296)
-    const float alpha_img = (meta_state(meta_j[0]) == CLDET_STATE_EMPTY) ? 1.0f - a.p.alpha : a.p.alpha;
+    const float alpha_img = (meta_state(smeta[0]) == CLDET_STATE_EMPTY) ? 1.0f - a.p.alpha : a.p.alpha;
     const float as_bg = alpha_img * sc.s_bg;
     if (VEC == 4) {
         const float4* src = reinterpret_cast<const float4*>(a.cls + base);
         float4* dst = GRAD ? reinterpret_cast<float4*>(a.gcls + base) : nullptr;
         const uint32_t nvec = count >> 2;
-        for (uint32_t v0 = tid; v0 < nvec; v0 += kLossThreads * kUnroll) {
+        // (row, col) of this thread's vector advance by a constant per step of kLossThreads vectors: no division in the loop
+        const uint32_t step_elems = kLossThreads * 4u;
+        const uint32_t drow = step_elems / C, dcol = step_elems - drow * C;
+        uint32_t row = (uint32_t)(4 * tid) / C;
+        uint32_t col = (uint32_t)(4 * tid) - row * C;
+        uint32_t v0 = tid;
+        const uint32_t full_end = nvec - nvec % kTile;     // vectors covered by complete tiles (no bounds checks)
+        for (; v0 < full_end; v0 += kTile) {
             float4 x[kUnroll];
-            uint32_t mm[kUnroll];
-            uint32_t col[kUnroll];
-            uint32_t row[kUnroll];
+            uint32_t mm[kUnroll], cc[kUnroll], rr[kUnroll];
 #pragma unroll
             for (int u = 0; u < kUnroll; ++u) {
-                const uint32_t v = v0 + u * kLossThreads;
-                if (v < nvec) {
-                    const uint32_t e0 = v << 2;
-                    row[u] = fast_div(e0, C, a.div_magic);
-                    col[u] = e0 - row[u] * C;
-                    mm[u] = meta_j[a0 + row[u]];
-                    // ignored anchors contribute nothing: do not even read their probabilities
-                    if (meta_state(mm[u]) != CLDET_STATE_IGNORE) x[u] = ld_stream_f4(src + v);
-                    else x[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                rr[u] = row;
+                cc[u] = col;
+                mm[u] = smeta[row];
+                col += dcol;
+                row += drow;
+                if (col >= C) {
+                    col -= C;
+                    row += 1;
                 }
+                // ignored anchors contribute nothing: do not even read their probabilities
+                if (meta_state(mm[u]) != CLDET_STATE_IGNORE) x[u] = ld_stream_f4(src + v0 + u * kLossThreads);
+                else x[u] = make_float4(0.f, 0.f, 0.f, 0.f);
             }
 #pragma unroll
             for (int u = 0; u < kUnroll; ++u) {
-                const uint32_t v = v0 + u * kLossThreads;
-                if (v < nvec) {
-                    const uint32_t st = meta_state(mm[u]);
-                    float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
-                    // the vector holds the target-1 element of a positive anchor?
-                    const bool special = (st == CLDET_STATE_POS) && (meta_label(mm[u]) - col[u] < 4u);
-                    if (GAMMA2 && !VARIANTS && !special) {
-                        if (st != CLDET_STATE_IGNORE) {      // bg anchor, empty image, or the target-0 part of a positive row
-                            g.x = neg_element_raw<GRAD>(x[u].x, as_bg, acc.raw[0]);
-                            g.y = neg_element_raw<GRAD>(x[u].y, as_bg, acc.raw[1]);
-                            g.z = neg_element_raw<GRAD>(x[u].z, as_bg, acc.raw[2]);
-                            g.w = neg_element_raw<GRAD>(x[u].w, as_bg, acc.raw[3]);
-                        }
-                    } else {
-                        float iou = 1.0f;
-                        if (need_iou && st == CLDET_STATE_POS) iou = a.iou_max[(int64_t)j * a.A + a0 + row[u]];
-                        g.x = cls_element<GAMMA2, VARIANTS, GRAD>(x[u].x, (int)col[u] + 0, mm[u], a, sc, iou, acc);
-                        g.y = cls_element<GAMMA2, VARIANTS, GRAD>(x[u].y, (int)col[u] + 1, mm[u], a, sc, iou, acc);
-                        g.z = cls_element<GAMMA2, VARIANTS, GRAD>(x[u].z, (int)col[u] + 2, mm[u], a, sc, iou, acc);
-                        g.w = cls_element<GAMMA2, VARIANTS, GRAD>(x[u].w, (int)col[u] + 3, mm[u], a, sc, iou, acc);
-                    }
-                    if (GRAD) st_stream_f4(dst + v, g);
-                }
+                const float4 g = cls_vec4<GAMMA2, VARIANTS, GRAD>(x[u], mm[u], cc[u], abs0 + rr[u], a, sc, as_bg, need_iou, acc);
+                if (GRAD) st_stream_f4(dst + v0 + u * kLossThreads, g);
+            }
+        }
+        for (; v0 < nvec; v0 += kLossThreads) {              // ragged tail of the chunk
+            const uint32_t m = smeta[row];
+            float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (meta_state(m) != CLDET_STATE_IGNORE) x = ld_stream_f4(src + v0);
+            const float4 g = cls_vec4<GAMMA2, VARIANTS, GRAD>(x, m, col, abs0 + row, a, sc, as_bg, need_iou, acc);
+            if (GRAD) st_stream_f4(dst + v0, g);
+            col += dcol;
+            row += drow;
+            if (col >= C) {
+                col -= C;
+                row += 1;
             }
         }
     } else {
@@ -371,9 +402,9 @@ __device__ __forceinline__ void process_chunk(const LossArgs& a, int j, int64_t 
         for (uint32_t e = tid; e < count; e += kLossThreads) {
             const uint32_t row = fast_div(e, C, a.div_magic);
             const uint32_t col = e - row * C;
-            const uint32_t m = meta_j[a0 + row];
+            const uint32_t m = smeta[row];
             float iou = 1.0f;
-            if (need_iou && meta_state(m) == CLDET_STATE_POS) iou = a.iou_max[(int64_t)j * a.A + a0 + row];
+            if (need_iou && meta_state(m) == CLDET_STATE_POS) iou = a.iou_max[abs0 + row];
             const float g = cls_element<GAMMA2, VARIANTS, GRAD>(src[e], (int)col, m, a, sc, iou, acc);
             if (GRAD) dst[e] = g;
         }
@@ -385,6 +416,7 @@ __global__ void __launch_bounds__(kLossThreads) focal_loss_kernel(const LossArgs
     __shared__ float red[4][kLossThreads / 32];
     __shared__ double fin[4][kLossThreads / 32];
     __shared__ bool is_last;
+    __shared__ uint32_t smeta[kMaxAnchorsPerBlock];
 
     const int j = blockIdx.y;
     const int64_t a0 = (int64_t)blockIdx.x * a.anchors_per_block;
@@ -393,7 +425,7 @@ __global__ void __launch_bounds__(kLossThreads) focal_loss_kernel(const LossArgs
     const ImageScales sc = image_scales(a.weights, a.N, j, npos);
 
     Acc acc = {0.f, 0.f, 0.f, 0.f, {0.f, 0.f, 0.f, 0.f}};
-    process_chunk<VEC, GAMMA2, VARIANTS, GRAD>(a, j, a0, a1, sc, 0, acc);
+    process_chunk<VEC, GAMMA2, VARIANTS, GRAD>(a, j, a0, a1, sc, 0, acc, smeta);
     {
         const float alpha_img = (meta_state(a.meta[(int64_t)j * a.A]) == CLDET_STATE_EMPTY) ? 1.0f - a.p.alpha : a.p.alpha;
         acc.bg += alpha_img * ((acc.raw[0] + acc.raw[1]) + (acc.raw[2] + acc.raw[3]));
@@ -455,18 +487,21 @@ __global__ void __launch_bounds__(kLossThreads) focal_loss_kernel(const LossArgs
 // Backward with weights that differ from the ones baked in by the forward pass (see cldet.h).
 template <int VEC, bool GAMMA2, bool VARIANTS>
 __global__ void __launch_bounds__(kLossThreads) focal_reweight_kernel(const LossArgs a) {
+    __shared__ uint32_t smeta[kMaxAnchorsPerBlock];
     const int j = blockIdx.y;
     const float* wn = a.weights + j;
     const float* wo = a.baked_weights + j;
     const int N = a.N;
-    const bool bg_changed = (wn[0] != wo[0]) || (wn[3 * N] != wo[3 * N]);
+    // the enhance term only exists in incremental states with enhance_on_new (losses.py:380-384)
+    const bool enh_on = a.p.incremental && a.p.enhance_on_new;
+    const bool bg_changed = (wn[0] != wo[0]) || (enh_on && wn[3 * N] != wo[3 * N]);
     const bool pos_changed = (wn[N] != wo[N]) || (wn[2 * N] != wo[2 * N]);
     if (!bg_changed && !pos_changed) return;
     const int64_t a0 = (int64_t)blockIdx.x * a.anchors_per_block;
     const int64_t a1 = min(a.A, a0 + a.anchors_per_block);
     const ImageScales sc = image_scales(a.weights, a.N, j, a.npos[j]);
     Acc acc = {0.f, 0.f, 0.f, 0.f, {0.f, 0.f, 0.f, 0.f}};
-    process_chunk<VEC, GAMMA2, VARIANTS, true>(a, j, a0, a1, sc, bg_changed ? 1 : 2, acc);
+    process_chunk<VEC, GAMMA2, VARIANTS, true>(a, j, a0, a1, sc, bg_changed ? 1 : 2, acc, smeta);
 }
 
 __global__ void copy_weights_kernel(const float* __restrict__ src, float* __restrict__ dst, int n) {
@@ -497,16 +532,23 @@ struct LossPlan {
     uint32_t div_magic;
 };
 
+static int64_t gcd64(int64_t x, int64_t y) { return y == 0 ? x : gcd64(y, x % y); }
+
 static LossPlan make_plan(int N, int64_t A, int C) {
     LossPlan pl;
-    int64_t apb = (32768 / C + 31) / 32 * 32;            // ~8k float4 per block
-    if (apb < 32) apb = 32;
-    if (apb > 4096) apb = 4096;
-    // small problems: keep at least ~4 blocks per SM in flight
+    // ~5-8k float4 per block; when C % 4 == 0 the chunk is made a whole number of fully unrolled tiles
+    // (anchors_per_block * C/4 divisible by kTile) so the hot loop runs without bounds checks.
+    int64_t quantum = 32;
+    if (C % 4 == 0) quantum = kTile / gcd64(C / 4, kTile);
+    int64_t apb = (24576 / C + quantum - 1) / quantum * quantum;
+    if (apb > kMaxAnchorsPerBlock) apb = kMaxAnchorsPerBlock / quantum * quantum;
+    if (apb < 32) apb = (quantum <= kMaxAnchorsPerBlock) ? quantum : 32;
+    // small problems: keep at least ~4 blocks per SM in flight (ragged tiles are fine there)
     const int64_t want_blocks = (int64_t)sm_count() * 4;
     int64_t cap = ((int64_t)N * A / want_blocks + 31) / 32 * 32;
     if (cap < 32) cap = 32;
     if (apb > cap) apb = cap;
+    if (apb > kMaxAnchorsPerBlock) apb = kMaxAnchorsPerBlock;
     pl.anchors_per_block = (int)apb;
     pl.bpi = (int)((A + apb - 1) / apb);
     const uint64_t span = (uint64_t)apb * C;              // largest dividend + 1
