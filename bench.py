@@ -245,26 +245,26 @@ def run_ours(args):
     ev_b = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
     ev_c = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
 
+    for e in ev_a + ev_b + ev_c:
+        e.record()          # materialise the CUDA event handles
+    torch.cuda.synchronize()
+
     def step(i=None):
-        npos.zero_()
+        # the fused entry point (assign + loss in one call) -- what FocalLoss.forward issues; the profiling hook makes
+        # this call record events around its two kernels so the loss kernel is timed inside the real step
         if i is not None:
-            ev_a[i].record()
-        _lib.check(lib.cldet_iou_assign(anchors.data_ptr(), a, ann.data_ptr(), n, GMAX, C, meta.data_ptr(), None, None,
-                                        npos.data_ptr(), nvalid.data_ptr(), stream))
-        if i is not None:
-            ev_b[i].record()
-        _lib.check(lib.cldet_focal_loss_from_assignment(
+            lib.cldet_focal_loss_profile_events(ev_a[i].cuda_event, ev_b[i].cuda_event, ev_c[i].cuda_event)
+        _lib.check(lib.cldet_focal_loss(
             probs.data_ptr(), reg.data_ptr(), anchors.data_ptr(), ann.data_ptr(), n, a, C, GMAX, lp, weights.data_ptr(),
-            gcls.data_ptr(), greg.data_ptr(), losses.data_ptr(), meta.data_ptr(), None, npos.data_ptr(), None, None,
-            ws.data_ptr(), ws_bytes, stream))
-        if i is not None:
-            ev_c[i].record()
+            gcls.data_ptr(), greg.data_ptr(), losses.data_ptr(), meta.data_ptr(), None, npos.data_ptr(), nvalid.data_ptr(),
+            None, None, ws.data_ptr(), ws_bytes, stream))
         if world > 1:   # every rank gets every image's (bg, fg, reg) terms: what IL_Loss's mean / clip_loss needs
             dist.all_gather_into_tensor(gathered, losses)
         # backward: upstream weights are verified on the device; unchanged -> nothing is recomputed
         _lib.check(lib.cldet_focal_loss_reweight(probs.data_ptr(), reg.data_ptr(), anchors.data_ptr(), ann.data_ptr(), n, a, C,
                                                  GMAX, lp, weights.data_ptr(), baked.data_ptr(), gcls.data_ptr(),
-                                                 greg.data_ptr(), meta.data_ptr(), None, npos.data_ptr(), stream))
+                                                 greg.data_ptr(), meta.data_ptr(), None, npos.data_ptr(), ws.data_ptr(),
+                                                 ws_bytes, stream))
 
     def barrier():
         if world > 1:
@@ -373,7 +373,7 @@ def run_ours(args):
                 'clocks': clocks,
                 'e2e': {'value': n_global / e2e_s, 'unit': 'images/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
                         'ms_per_step': e2e_s * 1e3, 'steps': e2e_steps},
-                'gpu_launches': 4 * args.steps,
+                'gpu_launches': 3 * args.steps,
                 'roofline': roofline}
         if cpu is not None:
             line['cpu_baseline'] = cpu

@@ -92,105 +92,147 @@ __global__ void __launch_bounds__(256) anchors_kernel(const AnchorPlan plan, flo
 // ------------------------------------------------------------------------------------------------
 constexpr int kGtTile = 256;
 constexpr int kAssignThreads = 256;
-
-struct GtRow {
-    float x1, y1, x2, y2, area;
-    int label;  // -1 (as int) marks a padding row
-    int valid;
-};
-
-__device__ __forceinline__ float iou_exact(float ax1, float ay1, float ax2, float ay2, float area_a, float bx1, float by1,
-                                           float bx2, float by2, float area_b) {
-    float iw = fminf(ax2, bx2) - fmaxf(ax1, bx1);
-    float ih = fminf(ay2, by2) - fmaxf(ay1, by1);
-    iw = fmaxf(iw, 0.0f);
-    ih = fmaxf(ih, 0.0f);
-    const float inter = iw * ih;
-    float ua = (area_a + area_b) - inter;
-    ua = fmaxf(ua, 1e-8f);
-    // inter == 0 -> the quotient is +0 for every finite ua >= 1e-8; skip the IEEE divide (most pairs).
-    return (inter > 0.0f) ? __fdiv_rn(inter, ua) : 0.0f;
-}
+constexpr int kAnchorsPerThread = 4;
 
 __global__ void __launch_bounds__(kAssignThreads)
 iou_assign_kernel(const float4* __restrict__ anchors, int64_t A, const float* __restrict__ annotations, int G,
                   int num_classes, uint32_t* __restrict__ meta, int32_t* __restrict__ argmax_out,
                   float* __restrict__ iou_max_out, int32_t* __restrict__ npos, int32_t* __restrict__ nvalid) {
-    __shared__ GtRow tile[kGtTile];
-    __shared__ int warp_counts[kAssignThreads / 32];
+    // valid rows of the current tile, compacted in order: box, area, (label, raw row)
+    __shared__ float4 s_box[kGtTile];
+    __shared__ float s_area[kGtTile];
+    __shared__ int2 s_lab_row[kGtTile];
+    __shared__ int s_warp[kAssignThreads / 32];
+    __shared__ int s_tile_valid;
+    __shared__ int2 s_first[kGtTile];     // (label, raw row) of the image's first kGtTile valid rows
 
     const int j = blockIdx.y;
-    const int64_t a = (int64_t)blockIdx.x * kAssignThreads + threadIdx.x;
-    const bool active = a < A;
+    const int64_t a_base = (int64_t)blockIdx.x * (kAssignThreads * kAnchorsPerThread) + threadIdx.x;
     const float* ann = annotations + (int64_t)j * G * 5;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 
-    float4 box = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (active) box = anchors[a];
-    const float area_a = (box.z - box.x) * (box.w - box.y);
-
-    float best = -1.0f;   // IoU >= 0 always, so the first valid row always wins the first compare
-    int best_k = -1;      // compacted index
-    int best_row = 0;     // raw row
-    int best_label = 0;
-    int k = 0;            // valid rows seen so far (block-uniform)
+    // kAnchorsPerThread anchors per thread (strided by the block size: coalesced), so one broadcast read of a GT row
+    // feeds several independent IoU chains and the per-block tile set-up is amortised.
+    float4 box[kAnchorsPerThread];
+    float area_a[kAnchorsPerThread];
+    float best[kAnchorsPerThread];
+    int best_t[kAnchorsPerThread];     // compacted index of the winner
+#pragma unroll
+    for (int u = 0; u < kAnchorsPerThread; ++u) {
+        const int64_t a = a_base + u * kAssignThreads;
+        box[u] = (a < A) ? anchors[a] : make_float4(0.f, 0.f, 0.f, 0.f);
+        area_a[u] = (box[u].z - box[u].x) * (box[u].w - box[u].y);
+        // torch.max returns the FIRST maximal index and every IoU is >= 0, so the first valid row is the answer unless
+        // a later row has a strictly larger (hence strictly positive) IoU: start from (IoU 0, compacted index 0).
+        best[u] = 0.0f;
+        best_t[u] = 0;
+    }
+    int k = 0;            // valid rows seen so far (block-uniform) = compacted index of the next valid row
 
     for (int g0 = 0; g0 < G; g0 += kGtTile) {
         const int n = min(kGtTile, G - g0);
         __syncthreads();
-        for (int t = threadIdx.x; t < n; t += kAssignThreads) {
-            const float* r = ann + (int64_t)(g0 + t) * 5;
-            GtRow row;
-            row.x1 = r[0];
-            row.y1 = r[1];
-            row.x2 = r[2];
-            row.y2 = r[3];
-            const float lab = r[4];
-            row.area = (row.x2 - row.x1) * (row.y2 - row.y1);
-            row.valid = (lab != -1.0f) ? 1 : 0;          // losses.py:288  annotation[:, 4] != -1
-            row.label = (int)(long long)lab;             // .long() truncation, losses.py:341
-            tile[t] = row;
+        // ordered compaction of this tile's valid rows (label != -1, losses.py:288); tile size == block size
+        float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+        float lab = -1.0f;
+        if (threadIdx.x < n) {
+            const float* r = ann + (int64_t)(g0 + threadIdx.x) * 5;
+            b = make_float4(r[0], r[1], r[2], r[3]);
+            lab = r[4];
         }
+        const bool valid = (threadIdx.x < n) && (lab != -1.0f);
+        const unsigned ballot = __ballot_sync(0xffffffffu, valid);
+        if (lane == 0) s_warp[warp] = __popc(ballot);
         __syncthreads();
-        for (int t = 0; t < n; ++t) {
-            const GtRow row = tile[t];                   // broadcast read
-            if (!row.valid) continue;                    // block-uniform
-            const float v = iou_exact(box.x, box.y, box.z, box.w, area_a, row.x1, row.y1, row.x2, row.y2, row.area);
-            if (v > best) {                              // strict: first maximal index (torch.max)
-                best = v;
-                best_k = k;
-                best_row = g0 + t;
-                best_label = row.label;
-            }
-            ++k;
+        int before = 0;
+#pragma unroll
+        for (int w = 0; w < kAssignThreads / 32; ++w) before += (w < warp) ? s_warp[w] : 0;
+        if (valid) {
+            const int slot = before + __popc(ballot & ((1u << lane) - 1u));
+            s_box[slot] = b;
+            s_area[slot] = (b.z - b.x) * (b.w - b.y);
+            s_lab_row[slot] = make_int2((int)(long long)lab, g0 + threadIdx.x);    // .long() truncation, losses.py:341
+            // (label, raw row) of every valid row of the IMAGE, by compacted index, for the epilogue
+            if (k + slot < kGtTile) s_first[k + slot] = s_lab_row[slot];
         }
+        if (threadIdx.x == kAssignThreads - 1) s_tile_valid = before + __popc(ballot);
+        __syncthreads();
+        const int nv = s_tile_valid;
+        for (int t = 0; t < nv; ++t) {
+            const float4 gb = s_box[t];                        // warp-wide broadcast
+            const float ga = s_area[t];
+#pragma unroll
+            for (int u = 0; u < kAnchorsPerThread; ++u) {
+                // calc_iou (losses.py:4-21) with the clamps resolved by early exits: an empty intersection gives IoU
+                // +0, which can never beat `best` under the strict compare.
+                const float iw = fminf(box[u].z, gb.z) - fmaxf(box[u].x, gb.x);
+                const float ih = fminf(box[u].w, gb.w) - fmaxf(box[u].y, gb.y);
+                if (iw > 0.0f && ih > 0.0f) {
+                    const float inter = iw * ih;
+                    float ua = (area_a[u] + ga) - inter;
+                    ua = fmaxf(ua, 1e-8f);
+                    const float v = __fdiv_rn(inter, ua);
+                    if (v > best[u]) {                         // strict: first maximal index (torch.max)
+                        best[u] = v;
+                        best_t[u] = k + t;
+                    }
+                }
+            }
+        }
+        k += nv;
     }
+    __syncthreads();
 
-    uint32_t state;
-    int is_pos = 0;
-    if (k == 0) {
-        state = CLDET_STATE_EMPTY;
-    } else if (best >= 0.5f) {       // torch.ge(IoU_max, 0.5)   losses.py:330
-        state = CLDET_STATE_POS;
-        is_pos = 1;
-    } else if (best < 0.4f) {        // torch.lt(IoU_max, 0.4)   losses.py:316
-        state = CLDET_STATE_BG;
-    } else {
-        state = CLDET_STATE_IGNORE;
-    }
-    if (active) {
-        uint32_t lab = (best_label >= 0 && best_label < num_classes) ? (uint32_t)best_label : CLDET_BAD_LABEL;
-        meta[(int64_t)j * A + a] = meta_pack(state, lab, (uint32_t)best_row);
-        if (argmax_out) argmax_out[(int64_t)j * A + a] = best_k;
-        if (iou_max_out) iou_max_out[(int64_t)j * A + a] = (k == 0) ? 0.0f : best;
+    int npos_local = 0;
+#pragma unroll
+    for (int u = 0; u < kAnchorsPerThread; ++u) {
+        const int64_t a = a_base + u * kAssignThreads;
+        uint32_t state;
+        if (k == 0) {
+            state = CLDET_STATE_EMPTY;
+        } else if (best[u] >= 0.5f) {       // torch.ge(IoU_max, 0.5)   losses.py:330
+            state = CLDET_STATE_POS;
+        } else if (best[u] < 0.4f) {        // torch.lt(IoU_max, 0.4)   losses.py:316
+            state = CLDET_STATE_BG;
+        } else {
+            state = CLDET_STATE_IGNORE;
+        }
+        if (a < A) {
+            // winner's (label, raw row): from the staged table, or (images with > kGtTile valid rows) re-derived from
+            // the annotations by walking to the best_t-th valid row
+            int2 lr = make_int2(0, 0);
+            if (k > 0) {
+                if (best_t[u] < kGtTile) {
+                    lr = s_first[best_t[u]];
+                } else {
+                    int seen = 0;
+                    for (int g = 0; g < G; ++g) {
+                        const float lab = ann[(int64_t)g * 5 + 4];
+                        if (lab != -1.0f) {
+                            if (seen == best_t[u]) {
+                                lr = make_int2((int)(long long)lab, g);
+                                break;
+                            }
+                            ++seen;
+                        }
+                    }
+                }
+            }
+            const uint32_t lab = (lr.x >= 0 && lr.x < num_classes) ? (uint32_t)lr.x : CLDET_BAD_LABEL;
+            meta[(int64_t)j * A + a] = meta_pack(state, lab, (uint32_t)lr.y);
+            if (argmax_out) argmax_out[(int64_t)j * A + a] = (k == 0) ? -1 : best_t[u];
+            if (iou_max_out) iou_max_out[(int64_t)j * A + a] = best[u];
+            npos_local += (state == CLDET_STATE_POS) ? 1 : 0;
+        }
     }
     // positives per image: warp -> block -> one integer atomic (deterministic)
-    int c = warp_sum_int((active && is_pos) ? 1 : 0);
-    if ((threadIdx.x & 31) == 0) warp_counts[threadIdx.x >> 5] = c;
+    const int c = warp_sum_int(npos_local);
+    if (lane == 0) s_warp[warp] = c;
     __syncthreads();
     if (threadIdx.x == 0) {
         int tot = 0;
 #pragma unroll
-        for (int w = 0; w < kAssignThreads / 32; ++w) tot += warp_counts[w];
+        for (int w = 0; w < kAssignThreads / 32; ++w) tot += s_warp[w];
         if (tot) atomicAdd(&npos[j], tot);
         if (blockIdx.x == 0) nvalid[j] = k;
     }
@@ -259,7 +301,8 @@ int cldet_iou_assign(const float* d_anchors, int64_t num_anchors, const float* d
     if (!d_anchors || !d_annotations || !d_meta || !d_npos || !d_nvalid) return CLDET_ERR_INVALID_ARGUMENT;
     if (num_anchors <= 0 || num_images <= 0 || gt_rows <= 0 || gt_rows > CLDET_MAX_GT_ROWS) return CLDET_ERR_INVALID_ARGUMENT;
     if (num_classes <= 0 || num_classes > CLDET_MAX_CLASSES || num_images > 65535) return CLDET_ERR_INVALID_ARGUMENT;
-    dim3 grid((unsigned)((num_anchors + kAssignThreads - 1) / kAssignThreads), (unsigned)num_images);
+    const int64_t per_block = (int64_t)kAssignThreads * kAnchorsPerThread;
+    dim3 grid((unsigned)((num_anchors + per_block - 1) / per_block), (unsigned)num_images);
     iou_assign_kernel<<<grid, kAssignThreads, 0, (cudaStream_t)stream>>>(
         reinterpret_cast<const float4*>(d_anchors), num_anchors, d_annotations, gt_rows, num_classes, d_meta, d_argmax,
         d_iou_max, d_npos, d_nvalid);

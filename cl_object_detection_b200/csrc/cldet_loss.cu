@@ -36,7 +36,10 @@ struct LossArgs {
     float* losses;               // [4][N]
     const uint32_t* meta;
     const float* iou_max;
-    const int32_t* npos;
+    const int32_t* npos;         // positives per image (input of the loss stage)
+    int32_t* npos_out;           // fused call: where the last block of an image publishes npos (else null)
+    int32_t* npos_reset;         // fused call: the workspace accumulator to clear for the next call (else null)
+    unsigned int* rw_counters;   // reweight pass: per-image block counters (workspace)
     uint8_t* bg_mask;
     int32_t* status;
     float* partials;             // [N][bpi][4]
@@ -480,7 +483,9 @@ __global__ void __launch_bounds__(kLossThreads) focal_loss_kernel(const LossArgs
         out[a.N] = (float)t[1] / sc.n;                                // :396
         out[2 * a.N] = npos > 0 ? (float)(t[2] / (4.0 * (double)npos)) : 0.0f;   // :437 mean over npos*4
         out[3 * a.N] = (float)t[3];
-        a.counters[j] = 0;                                            // ready for the next call
+        a.counters[j] = 0;                                            // leave the workspace zeroed for the next call
+        if (a.npos_out) a.npos_out[j] = npos;
+        if (a.npos_reset) a.npos_reset[j] = 0;
     }
 }
 
@@ -502,11 +507,19 @@ __global__ void __launch_bounds__(kLossThreads) focal_reweight_kernel(const Loss
     const ImageScales sc = image_scales(a.weights, a.N, j, a.npos[j]);
     Acc acc = {0.f, 0.f, 0.f, 0.f, {0.f, 0.f, 0.f, 0.f}};
     process_chunk<VEC, GAMMA2, VARIANTS, true>(a, j, a0, a1, sc, bg_changed ? 1 : 2, acc, smeta);
-}
-
-__global__ void copy_weights_kernel(const float* __restrict__ src, float* __restrict__ dst, int n) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) dst[i] = src[i];
+    // the last block of the image records the weights now baked into the gradient buffers; every other block of the
+    // image has finished (and so has read the old record) by then
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        const unsigned int done = atomicAdd(&a.rw_counters[j], 1u);
+        if (done == (unsigned int)a.bpi - 1u) {
+            float* wb = const_cast<float*>(a.baked_weights) + j;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) wb[k * N] = wn[k * N];
+            a.rw_counters[j] = 0;
+        }
+    }
 }
 
 // new_ignore_past_class pre-pass (losses.py:326-327): flag background anchors whose clamped old-class
@@ -563,10 +576,14 @@ struct Workspace {
     unsigned int* counters;
 };
 
+// workspace: [counters N | npos accumulator N | reweight counters N | pad to 256 B | partials]; the three header arrays
+// must be zero before the first call and are left zero by every call.
+static size_t workspace_header_bytes(int N) { return ((size_t)N * 3 * sizeof(unsigned int) + 255) / 256 * 256; }
+
 static size_t workspace_bytes(int N, int64_t A) {
     // worst case bpi: 32 anchors per block
     const int64_t max_bpi = (A + 31) / 32;
-    return (size_t)N * max_bpi * 4 * sizeof(float) + (size_t)N * sizeof(unsigned int) + 256;
+    return workspace_header_bytes(N) + (size_t)N * max_bpi * 4 * sizeof(float) + 256;
 }
 
 template <int VEC, bool GAMMA2, bool VARIANTS>
@@ -612,23 +629,32 @@ static int check_common(const float* d_cls, const float* d_anchors, const float*
     return CLDET_OK;
 }
 
+// optional per-thread profiling hook: events recorded around the two stages of the NEXT fused call of this thread
+static thread_local cudaEvent_t g_prof_events[3] = {nullptr, nullptr, nullptr};
+
 }  // namespace cldet
 
 using namespace cldet;
 
 extern "C" {
 
+int cldet_focal_loss_profile_events(void* ev_begin, void* ev_between, void* ev_end) {
+    g_prof_events[0] = (cudaEvent_t)ev_begin;
+    g_prof_events[1] = (cudaEvent_t)ev_between;
+    g_prof_events[2] = (cudaEvent_t)ev_end;
+    return CLDET_OK;
+}
+
 size_t cldet_focal_loss_workspace_bytes(int num_images, int64_t num_anchors) {
     if (num_images <= 0 || num_anchors <= 0) return 0;
     return workspace_bytes(num_images, num_anchors);
 }
 
-int cldet_focal_loss_from_assignment(const float* d_cls, const float* d_reg, const float* d_anchors,
-                                     const float* d_annotations, int num_images, int64_t num_anchors, int num_classes,
-                                     int gt_rows, const cldet_loss_params* params, const float* d_weights,
-                                     float* d_grad_cls, float* d_grad_reg, float* d_losses, uint32_t* d_meta,
-                                     const float* d_iou_max, const int32_t* d_npos, uint8_t* d_bg_mask, int32_t* d_status,
-                                     void* d_workspace, size_t ws_bytes, void* stream) {
+static int loss_stage(const float* d_cls, const float* d_reg, const float* d_anchors, const float* d_annotations,
+                      int num_images, int64_t num_anchors, int num_classes, int gt_rows, const cldet_loss_params* params,
+                      const float* d_weights, float* d_grad_cls, float* d_grad_reg, float* d_losses, uint32_t* d_meta,
+                      const float* d_iou_max, const int32_t* d_npos, int32_t* d_npos_out, int32_t* d_npos_reset,
+                      uint8_t* d_bg_mask, int32_t* d_status, void* d_workspace, size_t ws_bytes, void* stream) {
     int rc = check_common(d_cls, d_anchors, d_annotations, num_images, num_anchors, num_classes, gt_rows, params);
     if (rc) return rc;
     if (!d_reg || !d_losses || !d_meta || !d_npos || !d_workspace) return CLDET_ERR_INVALID_ARGUMENT;
@@ -646,10 +672,9 @@ int cldet_focal_loss_from_assignment(const float* d_cls, const float* d_reg, con
     a.N = num_images; a.A = num_anchors; a.C = num_classes; a.G = gt_rows; a.p = *params;
     a.weights = d_weights; a.baked_weights = nullptr; a.gcls = d_grad_cls; a.greg = d_grad_reg; a.losses = d_losses;
     a.meta = d_meta; a.iou_max = d_iou_max; a.npos = d_npos; a.bg_mask = d_bg_mask; a.status = d_status;
-    // workspace layout: [counters N | pad to 256 B | partials]
+    a.npos_out = d_npos_out; a.npos_reset = d_npos_reset; a.rw_counters = nullptr;
     a.counters = reinterpret_cast<unsigned int*>(d_workspace);
-    const size_t off = ((size_t)num_images * sizeof(unsigned int) + 255) / 256 * 256;
-    a.partials = reinterpret_cast<float*>(reinterpret_cast<char*>(d_workspace) + off);
+    a.partials = reinterpret_cast<float*>(reinterpret_cast<char*>(d_workspace) + workspace_header_bytes(num_images));
     a.anchors_per_block = pl.anchors_per_block; a.bpi = pl.bpi; a.div_magic = pl.div_magic;
 
     const bool variants = has_variants(*params);
@@ -666,6 +691,17 @@ int cldet_focal_loss_from_assignment(const float* d_cls, const float* d_reg, con
     return CLDET_OK;
 }
 
+int cldet_focal_loss_from_assignment(const float* d_cls, const float* d_reg, const float* d_anchors,
+                                     const float* d_annotations, int num_images, int64_t num_anchors, int num_classes,
+                                     int gt_rows, const cldet_loss_params* params, const float* d_weights,
+                                     float* d_grad_cls, float* d_grad_reg, float* d_losses, uint32_t* d_meta,
+                                     const float* d_iou_max, const int32_t* d_npos, uint8_t* d_bg_mask, int32_t* d_status,
+                                     void* d_workspace, size_t ws_bytes, void* stream) {
+    return loss_stage(d_cls, d_reg, d_anchors, d_annotations, num_images, num_anchors, num_classes, gt_rows, params, d_weights,
+                      d_grad_cls, d_grad_reg, d_losses, d_meta, d_iou_max, d_npos, nullptr, nullptr, d_bg_mask, d_status,
+                      d_workspace, ws_bytes, stream);
+}
+
 int cldet_focal_loss(const float* d_cls, const float* d_reg, const float* d_anchors, const float* d_annotations,
                      int num_images, int64_t num_anchors, int num_classes, int gt_rows,
                      const cldet_loss_params* params, const float* d_weights,
@@ -678,26 +714,35 @@ int cldet_focal_loss(const float* d_cls, const float* d_reg, const float* d_anch
     if (!d_npos || !d_nvalid || !d_meta || !d_workspace) return CLDET_ERR_INVALID_ARGUMENT;
     if (ws_bytes < workspace_bytes(num_images, num_anchors)) return CLDET_ERR_WORKSPACE_TOO_SMALL;
     cudaStream_t s = (cudaStream_t)stream;
-    CLDET_CUDA_TRY(cudaMemsetAsync(d_npos, 0, sizeof(int32_t) * num_images, s));
-    CLDET_CUDA_TRY(cudaMemsetAsync(d_workspace, 0, sizeof(unsigned int) * num_images, s));
     if (d_status) CLDET_CUDA_TRY(cudaMemsetAsync(d_status, 0, sizeof(int32_t), s));
+    // positives are accumulated in the (zeroed) workspace; the loss kernel's last block per image publishes the count to
+    // d_npos and clears the accumulator again, so no memset is needed between calls
+    int32_t* npos_acc = reinterpret_cast<int32_t*>(d_workspace) + num_images;
+    cudaEvent_t ev[3] = {g_prof_events[0], g_prof_events[1], g_prof_events[2]};
+    g_prof_events[0] = g_prof_events[1] = g_prof_events[2] = nullptr;      // one-shot
+    if (ev[0]) CLDET_CUDA_TRY(cudaEventRecord(ev[0], s));
     rc = cldet_iou_assign(d_anchors, num_anchors, d_annotations, num_images, gt_rows, num_classes, d_meta, nullptr,
-                          d_iou_max, d_npos, d_nvalid, stream);
+                          d_iou_max, npos_acc, d_nvalid, stream);
     if (rc) return rc;
-    return cldet_focal_loss_from_assignment(d_cls, d_reg, d_anchors, d_annotations, num_images, num_anchors, num_classes,
-                                            gt_rows, params, d_weights, d_grad_cls, d_grad_reg, d_losses, d_meta,
-                                            d_iou_max, d_npos, d_bg_mask, d_status, d_workspace, ws_bytes, stream);
+    if (ev[1]) CLDET_CUDA_TRY(cudaEventRecord(ev[1], s));
+    rc = loss_stage(d_cls, d_reg, d_anchors, d_annotations, num_images, num_anchors, num_classes, gt_rows, params, d_weights,
+                      d_grad_cls, d_grad_reg, d_losses, d_meta, d_iou_max, npos_acc, d_npos, npos_acc, d_bg_mask, d_status,
+                      d_workspace, ws_bytes, stream);
+    if (rc) return rc;
+    if (ev[2]) CLDET_CUDA_TRY(cudaEventRecord(ev[2], s));
+    return CLDET_OK;
 }
 
 int cldet_focal_loss_reweight(const float* d_cls, const float* d_reg, const float* d_anchors, const float* d_annotations,
                               int num_images, int64_t num_anchors, int num_classes, int gt_rows,
                               const cldet_loss_params* params, const float* d_new_weights, float* d_baked_weights,
                               float* d_grad_cls, float* d_grad_reg, const uint32_t* d_meta, const float* d_iou_max,
-                              const int32_t* d_npos, void* stream) {
+                              const int32_t* d_npos, void* d_workspace, size_t ws_bytes, void* stream) {
     int rc = check_common(d_cls, d_anchors, d_annotations, num_images, num_anchors, num_classes, gt_rows, params);
     if (rc) return rc;
-    if (!d_reg || !d_new_weights || !d_baked_weights || !d_grad_cls || !d_grad_reg || !d_meta || !d_npos)
+    if (!d_reg || !d_new_weights || !d_baked_weights || !d_grad_cls || !d_grad_reg || !d_meta || !d_npos || !d_workspace)
         return CLDET_ERR_INVALID_ARGUMENT;
+    if (ws_bytes < workspace_bytes(num_images, num_anchors)) return CLDET_ERR_WORKSPACE_TOO_SMALL;
     if (params->incremental && params->decrease_positive_by_iou && !d_iou_max) return CLDET_ERR_INVALID_ARGUMENT;
     cudaStream_t s = (cudaStream_t)stream;
     const LossPlan pl = make_plan(num_images, num_anchors, num_classes);
@@ -706,15 +751,15 @@ int cldet_focal_loss_reweight(const float* d_cls, const float* d_reg, const floa
     a.N = num_images; a.A = num_anchors; a.C = num_classes; a.G = gt_rows; a.p = *params;
     a.weights = d_new_weights; a.baked_weights = d_baked_weights; a.gcls = d_grad_cls; a.greg = d_grad_reg;
     a.losses = nullptr; a.meta = d_meta; a.iou_max = d_iou_max; a.npos = d_npos; a.bg_mask = nullptr; a.status = nullptr;
+    a.npos_out = nullptr; a.npos_reset = nullptr;
     a.counters = nullptr; a.partials = nullptr;
+    a.rw_counters = reinterpret_cast<unsigned int*>(d_workspace) + 2 * (size_t)num_images;
     a.anchors_per_block = pl.anchors_per_block; a.bpi = pl.bpi; a.div_magic = pl.div_magic;
     dim3 grid((unsigned)pl.bpi, (unsigned)num_images);
     const bool gamma2 = params->gamma == 2.0f;
     const bool variants = has_variants(*params);
     if (num_classes % 4 == 0) dispatch_reweight<4>(a, gamma2, variants, grid, s);
     else dispatch_reweight<1>(a, gamma2, variants, grid, s);
-    CLDET_LAUNCH_CHECK();
-    copy_weights_kernel<<<(num_images * 4 + 255) / 256, 256, 0, s>>>(d_new_weights, d_baked_weights, num_images * 4);
     CLDET_LAUNCH_CHECK();
     return CLDET_OK;
 }

@@ -8,6 +8,8 @@ weights the caller is expected to apply (IL_Loss takes .mean() of each term, los
 autograd's backward only verifies those weights on the device and patches the (rare) images where they
 differ (clip_loss masking, losses.py:575-581).
 """
+import threading
+
 import torch
 import torch.nn as nn
 
@@ -66,6 +68,29 @@ def iou_assign(anchors, annotations, num_classes, want_argmax=True, want_iou_max
                 iou_max=iou_max, npos=npos, nvalid=nvalid)
 
 
+_tls = threading.local()
+
+
+def _workspace(dev, stream, n, a):
+    """Zero-initialised scratch for (device, stream, N, A), cached per host thread.  libcldet leaves the header of a
+    workspace zeroed after every call, so it is cleared exactly once; calls that share it are ordered by the stream."""
+    cache = getattr(_tls, 'ws', None)
+    if cache is None:
+        cache = _tls.ws = {}
+    key = (dev.index, stream, n, a)
+    ws = cache.get(key)
+    if ws is None:
+        if len(cache) > 8:
+            cache.clear()
+        nbytes = _lib.load().cldet_focal_loss_workspace_bytes(n, a)
+        ws = cache[key] = torch.zeros(nbytes, dtype=torch.uint8, device=dev)
+    return ws
+
+
+def _drop_workspaces():
+    _tls.ws = {}
+
+
 class _FocalLossFn(torch.autograd.Function):
     """outputs: bg[N], fg[N], reg_per_image[N], enhance_per_image[N] (rows of the kernel's [4,N] result)."""
 
@@ -84,18 +109,23 @@ class _FocalLossFn(torch.autograd.Function):
             nvalid = torch.empty(n, dtype=torch.int32, device=dev)
             bg_mask = torch.empty((n, a), dtype=torch.uint8, device=dev) if want_bg_mask else None
             status = torch.empty(1, dtype=torch.int32, device=dev) if check_labels else None
-            ws_bytes = lib.cldet_focal_loss_workspace_bytes(n, a)
-            ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+            ws = _workspace(dev, _stream(), n, a)
+            ws_bytes = ws.numel()
             if need_grad:
                 weights = hint.to(device=dev, dtype=torch.float32).clone()   # private: the reweight pass updates it
                 gcls = torch.empty_like(cls)
                 greg = torch.empty_like(reg)
             else:
                 weights = gcls = greg = None
-            _lib.check(lib.cldet_focal_loss(
-                cls.data_ptr(), reg.data_ptr(), anchors.data_ptr(), annotations.data_ptr(), n, a, c, g, lp,
-                _lib.ptr(weights), _lib.ptr(gcls), _lib.ptr(greg), losses.data_ptr(), meta.data_ptr(), _lib.ptr(iou_max),
-                npos.data_ptr(), nvalid.data_ptr(), _lib.ptr(bg_mask), _lib.ptr(status), ws.data_ptr(), ws_bytes, _stream()))
+            try:
+                _lib.check(lib.cldet_focal_loss(
+                    cls.data_ptr(), reg.data_ptr(), anchors.data_ptr(), annotations.data_ptr(), n, a, c, g, lp,
+                    _lib.ptr(weights), _lib.ptr(gcls), _lib.ptr(greg), losses.data_ptr(), meta.data_ptr(),
+                    _lib.ptr(iou_max), npos.data_ptr(), nvalid.data_ptr(), _lib.ptr(bg_mask), _lib.ptr(status),
+                    ws.data_ptr(), ws_bytes, _stream()))
+            except Exception:
+                _drop_workspaces()      # a failed call may leave the scratch header dirty
+                raise
         if check_labels and int(status.item()) != 0:
             raise IndexError('a GT label is outside [0, %d): the reference indexes the class dimension with it '
                              '(losses.py:341)' % c)
@@ -105,6 +135,7 @@ class _FocalLossFn(torch.autograd.Function):
         if need_grad:
             ctx.save_for_backward(cls, reg, anchors, annotations, weights, gcls, greg, meta, npos)
             ctx.iou_max = iou_max
+            ctx.ws = ws
         ctx.mark_non_differentiable(npos, nvalid)
         outs = (losses[0], losses[1], losses[2], losses[3], npos, nvalid)
         if want_bg_mask:
@@ -133,7 +164,7 @@ class _FocalLossFn(torch.autograd.Function):
             _lib.check(_lib.load().cldet_focal_loss_reweight(
                 cls.data_ptr(), reg.data_ptr(), anchors.data_ptr(), annotations.data_ptr(), n, a, c, g, ctx.lp,
                 new_w.data_ptr(), baked.data_ptr(), gcls.data_ptr(), greg.data_ptr(), meta.data_ptr(), _lib.ptr(iou_max),
-                npos.data_ptr(), _stream()))
+                npos.data_ptr(), ctx.ws.data_ptr(), ctx.ws.numel(), _stream()))
         ctx.backward_calls += 1
         if ctx.backward_calls > 1:   # the buffers may already be someone's .grad: hand out copies from now on
             return gcls.clone(), greg.clone(), None, None, None, None, None, None

@@ -92,10 +92,11 @@ typedef struct cldet_loss_params {
     float decrease_positive;           /* :364-366, default 1.0 */
 } cldet_loss_params;
 
-/* Bytes of scratch cldet_focal_loss needs for (N, A). */
+/* Bytes of scratch cldet_focal_loss needs for (N, A).  The first 3*N uint32 of a workspace must be ZERO before its first
+ * use; every call leaves them zero again, so one memset at allocation time is enough (no per-call memset nodes). */
 size_t cldet_focal_loss_workspace_bytes(int num_images, int64_t num_anchors);
 
-/* One call = memset of the counters + IoU/assign kernel + fused loss/gradient kernel.
+/* One call = IoU/assign kernel + fused loss/gradient kernel (two launches).
  *   d_cls  [N,A,C] probabilities (post-sigmoid, as the reference passes them)   d_reg [N,A,4]
  *   d_anchors [A,4]      d_annotations [N,G,5]
  *   d_weights [4,N] (row-major, one row per term) upstream gradients per image: row 0 dL/d(bg_j), row 1 dL/d(fg_j),
@@ -117,9 +118,14 @@ int cldet_focal_loss(const float* d_cls, const float* d_reg, const float* d_anch
                      uint8_t* d_bg_mask, int32_t* d_status,
                      void* d_workspace, size_t workspace_bytes, void* stream);
 
+/* Profiling hook (per host thread, one-shot): the next cldet_focal_loss call of THIS thread records the given
+ * cudaEvent_t handles before the assign kernel, between the two kernels and after the loss kernel, on its stream.
+ * NULL = do not record.  Lets a benchmark time each kernel inside the real fused call. */
+int cldet_focal_loss_profile_events(void* ev_begin, void* ev_between, void* ev_end);
+
 /* Loss/gradient stage alone, on an assignment produced earlier by cldet_iou_assign (same argument meaning).
  * d_meta is read; with params->new_ignore_past_class its bit 2 is (re)written by a pre-pass over the old-class columns.
- * The first num_images uint32 of the workspace must be zero on entry (they are left zero on return). */
+ * Workspace contract as cldet_focal_loss. */
 int cldet_focal_loss_from_assignment(const float* d_cls, const float* d_reg, const float* d_anchors,
                                      const float* d_annotations, int num_images, int64_t num_anchors, int num_classes,
                                      int gt_rows, const cldet_loss_params* params, const float* d_weights,
@@ -131,12 +137,13 @@ int cldet_focal_loss_from_assignment(const float* d_cls, const float* d_reg, con
  * (IL_Loss's clip_loss masking, losses.py:575-581, is only known after the forward).  Per image and per term the
  * kernel compares d_new_weights with d_baked_weights ON THE DEVICE (no host sync): images whose weights are unchanged
  * are skipped; a changed fg/reg weight touches only that image's positive anchors; a changed bg weight recomputes the
- * image.  d_baked_weights is updated to d_new_weights at the end. */
+ * image.  d_baked_weights is updated to d_new_weights for the images that were patched.  d_workspace: the same (zeroed)
+ * workspace contract as cldet_focal_loss. */
 int cldet_focal_loss_reweight(const float* d_cls, const float* d_reg, const float* d_anchors, const float* d_annotations,
                               int num_images, int64_t num_anchors, int num_classes, int gt_rows,
                               const cldet_loss_params* params, const float* d_new_weights, float* d_baked_weights,
                               float* d_grad_cls, float* d_grad_reg, const uint32_t* d_meta, const float* d_iou_max,
-                              const int32_t* d_npos, void* stream);
+                              const int32_t* d_npos, void* d_workspace, size_t workspace_bytes, void* stream);
 
 /* ---- a10-a13: eval-mode detection output (retinanet/utils.py:102-144 BBoxTransform/ClipBoxes;
  *      retinanet/model.py:507-550 ResNet.predict; IL_method/persuado_label.py:99-127 Labeler.predict;
