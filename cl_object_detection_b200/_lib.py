@@ -8,7 +8,7 @@ import os
 import threading
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG, 'libcldet.so')
+LIB_PATH = os.environ.get('CLDET_LIBRARY', os.path.join(_PKG, 'libcldet.so'))   # override: A/B builds only
 
 _lock = threading.Lock()
 _lib = None

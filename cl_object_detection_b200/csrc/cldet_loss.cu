@@ -16,8 +16,14 @@
 
 namespace cldet {
 
+#ifndef CLDET_LOSS_UNROLL
+#define CLDET_LOSS_UNROLL 2
+#endif
+#ifndef CLDET_LOSS_MINBLOCKS
+#define CLDET_LOSS_MINBLOCKS 6
+#endif
 constexpr int kLossThreads = 256;
-constexpr int kUnroll = 4;
+constexpr int kUnroll = CLDET_LOSS_UNROLL;
 
 struct LossArgs {
     const float* cls;
@@ -108,6 +114,10 @@ __device__ __forceinline__ void neg_element(float p_raw, float alpha, float gamm
 // the gradient: g = as * p * (2*(-ln(1-p)) + p/(1-p)).  ~26 instructions per element.
 template <bool GRAD>
 __device__ __forceinline__ float neg_element_raw(float p_raw, float as, float& raw) {
+#ifdef CLDET_LOSS_NOMATH      // experiment only: memory-side ceiling of this access pattern
+    raw += p_raw;
+    return p_raw * as;
+#endif
     const float p = fminf(fmaxf(p_raw, 1e-4f), 0.9999f);
     const float q = 1.0f - p;
     const float L = log_fast(q);                     // ln(1-p) <= 0
@@ -415,7 +425,7 @@ __device__ __forceinline__ void process_chunk(const LossArgs& a, int j, int64_t 
 }
 
 template <int VEC, bool GAMMA2, bool VARIANTS, bool GRAD>
-__global__ void __launch_bounds__(kLossThreads) focal_loss_kernel(const LossArgs a) {
+__global__ void __launch_bounds__(kLossThreads, CLDET_LOSS_MINBLOCKS) focal_loss_kernel(const LossArgs a) {
     __shared__ float red[4][kLossThreads / 32];
     __shared__ double fin[4][kLossThreads / 32];
     __shared__ bool is_last;
