@@ -88,15 +88,15 @@ __device__ __forceinline__ uint64_t make_key(float score, int anchor) {
 // Only survivors are decoded; the [N,A,C] sigmoid map and the [N,A,4] box tensor are never materialised.
 // ------------------------------------------------------------------------------------------------
 constexpr int kFilterThreads = 256;
-constexpr int kFilterMaxPartials = 8192;   // 32 KB of shared memory
+constexpr int kFilterMaxPartials = 8192;   // 32 KB of shared memory per block
 
 template <int VEC>
 __global__ void __launch_bounds__(kFilterThreads)
 decode_filter_kernel(const float* __restrict__ cls, int is_logits, const float4* __restrict__ reg,
-                     const float4* __restrict__ anchors, int64_t A, int C, int rows_per_block, float img_w, float img_h,
-                     float score_thresh, float prefilter, cldet_candidate* __restrict__ cand, uint64_t* __restrict__ keys,
-                     int64_t capacity, int32_t* __restrict__ counts) {
-    extern __shared__ float part[];
+                     const float4* __restrict__ anchors, int64_t A, int C, int rows_per_block, int stride, float img_w,
+                     float img_h, float score_thresh, float prefilter, cldet_candidate* __restrict__ cand,
+                     uint64_t* __restrict__ keys, int64_t capacity, int32_t* __restrict__ counts) {
+    extern __shared__ float part[];          // [rows_per_block][stride] per-vector maxima; stride is odd: conflict-free
     __shared__ int warp_tot[kFilterThreads / 32];
     __shared__ int block_base;
 
@@ -107,36 +107,67 @@ decode_filter_kernel(const float* __restrict__ cls, int is_logits, const float4*
     const int nvec = nrows * ppr;
     const float* base = cls + ((int64_t)j * A + a0) * C;
 
-    // ---- phase 1 ----
-    if (VEC == 4) {
-        const float4* src = reinterpret_cast<const float4*>(base);
-        for (int v0 = threadIdx.x; v0 < nvec; v0 += kFilterThreads * 4) {
-            float4 x[4];
+    // ---- phase 1: stream the [nrows, C] tile, keep each vector's maximum ----
+    {
+        // (row, k) of this thread's vector advance by constants per step of kFilterThreads vectors
+        const int drow = kFilterThreads / ppr, dk = kFilterThreads - drow * ppr;
+        int row = threadIdx.x / ppr, k = threadIdx.x - row * ppr;
+        if (VEC == 4) {
+            const float4* src = reinterpret_cast<const float4*>(base);
+            for (int v0 = threadIdx.x; v0 < nvec; v0 += kFilterThreads * 4) {
+                float4 x[4];
+                int idx[4];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const int v = v0 + u * kFilterThreads;
-                if (v < nvec) x[u] = ld_stream_f4(src + v);
+                for (int u = 0; u < 4; ++u) {
+                    const int v = v0 + u * kFilterThreads;
+                    idx[u] = row * stride + k;
+                    k += dk;
+                    row += drow;
+                    if (k >= ppr) {
+                        k -= ppr;
+                        row += 1;
+                    }
+                    if (v < nvec) x[u] = ld_stream_f4(src + v);
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int v = v0 + u * kFilterThreads;
+                    if (v < nvec) part[idx[u]] = fmaxf(fmaxf(x[u].x, x[u].y), fmaxf(x[u].z, x[u].w));
+                }
             }
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const int v = v0 + u * kFilterThreads;
-                if (v < nvec) part[v] = fmaxf(fmaxf(x[u].x, x[u].y), fmaxf(x[u].z, x[u].w));
+        } else {
+            for (int v = threadIdx.x; v < nvec; v += kFilterThreads) {
+                part[row * stride + k] = base[v];
+                k += dk;
+                row += drow;
+                if (k >= ppr) {
+                    k -= ppr;
+                    row += 1;
+                }
             }
         }
-    } else {
-        for (int v = threadIdx.x; v < nvec; v += kFilterThreads) part[v] = base[v];
     }
     __syncthreads();
 
-    // ---- phase 2 ----
+    // ---- phase 2: one thread per anchor row ----
     bool is_cand = false;
     float best = 0.0f;
     int best_c = 0;
     const int r = threadIdx.x;
     if (r < nrows) {
-        const float* p = part + r * ppr;
-        float m = p[0];
-        for (int k = 1; k < ppr; ++k) m = fmaxf(m, p[k]);
+        const float* p = part + r * stride;
+        float m = p[0], m2 = -INFINITY;      // largest and second largest per-vector maximum
+        int kmax = 0;
+        for (int k = 1; k < ppr; ++k) {
+            const float v = p[k];
+            if (v > m) {
+                m2 = m;
+                m = v;
+                kmax = k;
+            } else {
+                m2 = fmaxf(m2, v);
+            }
+        }
         if (m > prefilter) {
             // Which raw values can attain the row's maximum PROBABILITY?  For probabilities: only values == m.
             // For logits: sigmoid is evaluated in fp32 and saturates, so every logit within 0.05 of the max (or above 10
@@ -144,7 +175,10 @@ decode_filter_kernel(const float* __restrict__ cls, int is_logits, const float4*
             const float t = is_logits ? ((m > 10.05f) ? 10.0f : m - 0.05f) : m;
             const float* row = base + (int64_t)r * C;
             best = -1.0f;
-            for (int k = 0; k < ppr; ++k) {
+            // usually only the vector holding the maximum qualifies; otherwise walk every vector in class order
+            const int k_lo = (m2 >= t) ? 0 : kmax;
+            const int k_hi = (m2 >= t) ? ppr : kmax + 1;
+            for (int k = k_lo; k < k_hi; ++k) {
                 if (p[k] >= t) {
 #pragma unroll
                     for (int e = 0; e < VEC; ++e) {
@@ -165,7 +199,7 @@ decode_filter_kernel(const float* __restrict__ cls, int is_logits, const float4*
             is_cand = best > score_thresh;                // model.py:536  scores > 0.05
         }
     }
-    // block-aggregated append
+    // block-aggregated append: one atomic per block
     const unsigned ballot = __ballot_sync(0xffffffffu, is_cand);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     if (lane == 0) warp_tot[warp] = __popc(ballot);
@@ -186,10 +220,10 @@ decode_filter_kernel(const float* __restrict__ cls, int is_logits, const float4*
         if (slot < capacity) {
             const int64_t an = a0 + r;
             const float4 b = decode_clip(anchors[an], reg[(int64_t)j * A + an], img_w, img_h);
-            cldet_candidate c;
-            c.x1 = b.x; c.y1 = b.y; c.x2 = b.z; c.y2 = b.w;
-            c.score = best; c.label = best_c; c.anchor = (int32_t)an; c.pad = 0;
-            cand[(int64_t)j * capacity + slot] = c;
+            // 32-byte record as two 128-bit stores
+            float4* dst = reinterpret_cast<float4*>(cand + (int64_t)j * capacity + slot);
+            dst[0] = b;
+            dst[1] = make_float4(best, __int_as_float(best_c), __int_as_float((int)an), 0.0f);
             keys[(int64_t)j * capacity + slot] = make_key(best, (int)an);
         }
     }
@@ -601,11 +635,12 @@ int cldet_decode_filter(const float* d_cls, int is_logits, const float* d_reg, c
     if (!d_cls || !d_reg || !d_anchors || !d_candidates || !d_keys || !d_counts) return CLDET_ERR_INVALID_ARGUMENT;
     if (num_images <= 0 || num_images > 65535 || num_anchors <= 0 || num_classes <= 0 || capacity <= 0)
         return CLDET_ERR_INVALID_ARGUMENT;
-    if (num_classes > kFilterMaxPartials) return CLDET_ERR_UNSUPPORTED;
+    if (num_classes >= kFilterMaxPartials) return CLDET_ERR_UNSUPPORTED;
     const int vec = (num_classes % 4 == 0 && (((uintptr_t)d_cls) & 15) == 0) ? 4 : 1;
     const int ppr = (num_classes + vec - 1) / vec;
-    int rows = std::min(kFilterThreads, std::max(1, kFilterMaxPartials / ppr));
-    if (rows > 64 && ppr >= 8) rows = 64;        // keep ~5 vectors per thread in flight for wide rows
+    const int stride = ppr | 1;                  // odd row stride: phase 2 reads are bank-conflict free
+    // one anchor row per thread in phase 2; fewer rows only when a row's partials would not fit in shared memory
+    const int rows = std::min(kFilterThreads, std::max(1, kFilterMaxPartials / stride));
     // a pre-filter on the RAW maximum: a row can only pass if its best class probability exceeds the threshold
     float prefilter;
     if (is_logits) {
@@ -616,16 +651,18 @@ int cldet_decode_filter(const float* d_cls, int is_logits, const float* d_reg, c
         prefilter = score_thresh;                // exact: the score IS the raw maximum
     }
     dim3 grid((unsigned)((num_anchors + rows - 1) / rows), (unsigned)num_images);
-    const size_t smem = (size_t)rows * ppr * sizeof(float);
+    const size_t smem = (size_t)rows * stride * sizeof(float);
     cudaStream_t s = (cudaStream_t)stream;
     if (vec == 4)
         decode_filter_kernel<4><<<grid, kFilterThreads, smem, s>>>(
             d_cls, is_logits, reinterpret_cast<const float4*>(d_reg), reinterpret_cast<const float4*>(d_anchors), num_anchors,
-            num_classes, rows, (float)width, (float)height, score_thresh, prefilter, d_candidates, d_keys, capacity, d_counts);
+            num_classes, rows, stride, (float)width, (float)height, score_thresh, prefilter, d_candidates, d_keys, capacity,
+            d_counts);
     else
         decode_filter_kernel<1><<<grid, kFilterThreads, smem, s>>>(
             d_cls, is_logits, reinterpret_cast<const float4*>(d_reg), reinterpret_cast<const float4*>(d_anchors), num_anchors,
-            num_classes, rows, (float)width, (float)height, score_thresh, prefilter, d_candidates, d_keys, capacity, d_counts);
+            num_classes, rows, stride, (float)width, (float)height, score_thresh, prefilter, d_candidates, d_keys, capacity,
+            d_counts);
     CLDET_LAUNCH_CHECK();
     return CLDET_OK;
 }

@@ -1,0 +1,105 @@
+#!/usr/bin/env python
+"""Eval-mode detection output benchmark (BASELINE config 4): decode + score threshold + top-1000 + per-class NMS on a
+COCO-shaped batch (32 x 800x1333, C=80, A=200700).  Prints one JSON line; per-stage times come from CUDA events around
+the C-ABI calls.  Not the default bench line (bench.py measures the loss path the metric's target is quoted on)."""
+import argparse
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+import cl_object_detection_b200 as cld  # noqa: E402
+from cl_object_detection_b200 import _lib  # noqa: E402
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--steps', type=int, default=30)
+    ap.add_argument('--warmup', type=int, default=5)
+    ap.add_argument('--images', type=int, default=32)
+    ap.add_argument('--mu', type=float, default=-4.0)
+    ap.add_argument('--topk', type=int, default=1000)
+    ap.add_argument('--classes', type=int, default=80)
+    args = ap.parse_args()
+    dev = torch.device('cuda', 0)
+    torch.cuda.set_device(dev)
+    lib = _lib.load()
+    h, w, c, n, topk = 800, 1333, args.classes, args.images, args.topk
+    anchors = cld.generate_anchors(h, w, dev)
+    a = anchors.shape[1]
+    gen = torch.Generator(device=dev).manual_seed(4000)
+    logits = torch.randn(n, a, c, device=dev, generator=gen) * 2.0 + args.mu
+    reg = torch.randn(n, a, 4, device=dev, generator=gen) * 0.5
+    st = torch.cuda.current_stream().cuda_stream
+    cap = min(topk, a)
+    counts = torch.zeros(n, dtype=torch.int32, device=dev)
+    cand = torch.empty((n, a, 32), dtype=torch.uint8, device=dev)
+    keys = torch.empty((n, a), dtype=torch.int64, device=dev)
+    sorted_c = torch.empty((n, cap, 32), dtype=torch.uint8, device=dev)
+    sorted_counts = torch.empty(n, dtype=torch.int32, device=dev)
+    sws = torch.empty(lib.cldet_sort_workspace_bytes(n, a, topk), dtype=torch.uint8, device=dev)
+    nws = torch.empty(lib.cldet_nms_workspace_bytes(n, cap), dtype=torch.uint8, device=dev)
+    keep = torch.empty((n, cap), dtype=torch.int32, device=dev)
+    keep_counts = torch.empty(n, dtype=torch.int32, device=dev)
+    scores = torch.empty((n, cap), device=dev)
+    labels = torch.empty((n, cap), dtype=torch.int64, device=dev)
+    boxes = torch.empty((n, cap, 4), device=dev)
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(5)] for _ in range(args.steps)]
+
+    def step(i=None):
+        counts.zero_()
+        if i is not None:
+            ev[i][0].record()
+        _lib.check(lib.cldet_decode_filter(logits.data_ptr(), 1, reg.data_ptr(), anchors.data_ptr(), n, a, c, h, w, 0.05,
+                                           cand.data_ptr(), keys.data_ptr(), a, counts.data_ptr(), st))
+        if i is not None:
+            ev[i][1].record()
+        _lib.check(lib.cldet_sort_candidates(cand.data_ptr(), keys.data_ptr(), counts.data_ptr(), n, a, a, topk,
+                                             sorted_c.data_ptr(), cap, sorted_counts.data_ptr(), sws.data_ptr(), sws.numel(), st))
+        if i is not None:
+            ev[i][2].record()
+        _lib.check(lib.cldet_nms_sorted(sorted_c.data_ptr(), sorted_counts.data_ptr(), n, cap, cap, 0.5, 0, 100000,
+                                        keep.data_ptr(), keep_counts.data_ptr(), nws.data_ptr(), nws.numel(), st))
+        if i is not None:
+            ev[i][3].record()
+        _lib.check(lib.cldet_gather_detections(sorted_c.data_ptr(), keep.data_ptr(), keep_counts.data_ptr(), n, cap, cap,
+                                               scores.data_ptr(), labels.data_ptr(), boxes.data_ptr(), st))
+        if i is not None:
+            ev[i][4].record()
+
+    for _ in range(max(3, args.warmup)):
+        step()
+    torch.cuda.synchronize()
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0.record()
+    for i in range(args.steps):
+        step(i)
+    t1.record()
+    torch.cuda.synchronize()
+    ms = t0.elapsed_time(t1) / args.steps
+    stage = [sum(e[k].elapsed_time(e[k + 1]) for e in ev) / args.steps for k in range(4)]
+    kept = keep_counts.float().mean().item()
+    ncand = counts.float().mean().item()
+    peak = 6544.7
+    try:
+        peak = float(json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))['hbm_gbs'])
+    except Exception:
+        pass
+    filt_bytes = n * (4 * a * c) + counts.sum().item() * (32 + 40)
+    line = {'metric': 'detection-head images/sec (decode + threshold + top-k + per-class NMS)', 'value': n / (ms * 1e-3),
+            'unit': 'images/s', 'n_gpus': 1, 'steps': args.steps, 'ms_per_step': ms, 'dtype': 'f32', 'data': 'synthetic',
+            'config': {'workload': 'eval decode: %d x 800x1333, C=%d, A=%d, thr 0.05, top-%d, NMS 0.5 (BASELINE config 4)' % (n, c, a, topk),
+                       'logit_mean': args.mu, 'candidates_per_image': ncand, 'kept_per_image': kept},
+            'stage_ms': {'decode_filter': stage[0], 'select_sort': stage[1], 'nms': stage[2], 'gather': stage[3]},
+            'roofline': {'bound': 'hbm', 'kernel': 'decode_filter_kernel<4>', 'achieved': filt_bytes / (stage[0] * 1e-3) / 1e9,
+                         'peak': peak, 'unit': 'GB/s', 'frac': filt_bytes / (stage[0] * 1e-3) / 1e9 / peak,
+                         'algorithmic_bytes_per_launch': filt_bytes}}
+    print(json.dumps(line))
+
+
+if __name__ == '__main__':
+    main()
