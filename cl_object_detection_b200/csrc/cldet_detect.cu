@@ -285,31 +285,59 @@ select_hist_kernel(const uint64_t* __restrict__ keys, const int32_t* __restrict_
         if (sh[b]) atomicAdd(&hist[(int64_t)j * kSelBins + b], sh[b]);
 }
 
-// one block per image: find the digit where the descending cumulative count crosses the remaining k
+// one block per image: find the digit where the descending cumulative count crosses the remaining k.
+// 256 threads own 8 consecutive bins each (high bins first); a shared-memory suffix scan over the 256 partial sums
+// locates the owning thread, which then walks its 8 bins.
 __global__ void __launch_bounds__(256) select_pick_kernel(SelPass ps, uint32_t* __restrict__ state, uint32_t* __restrict__ hist) {
     __shared__ uint32_t sh[kSelBins];
+    __shared__ uint32_t part[256];
     const int j = blockIdx.x;
     uint32_t* st = state + 4 * j;
     const int nb = 1 << ps.bits;
     uint32_t* h = hist + (int64_t)j * kSelBins;
-    for (int b = threadIdx.x; b < nb; b += blockDim.x) {
-        sh[b] = h[b];
+    for (int b = threadIdx.x; b < kSelBins; b += blockDim.x) {
+        sh[b] = (b < nb) ? h[b] : 0u;
         h[b] = 0;                       // ready for the next pass
     }
     __syncthreads();
-    if (threadIdx.x == 0 && !st[3]) {
-        uint32_t need = st[1];
-        int b = nb - 1;
-        for (; b > 0; --b) {
-            if (sh[b] >= need) break;
+    if (st[3]) return;                  // block-uniform
+    // thread t owns bins [hi-7, hi] with hi = kSelBins-1-8t (descending order)
+    const int hi = kSelBins - 1 - 8 * (int)threadIdx.x;
+    uint32_t mine = 0;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) mine += sh[hi - q];
+    part[threadIdx.x] = mine;
+    __syncthreads();
+    // inclusive prefix over threads (= suffix over bins), Hillis-Steele in shared memory
+    for (int off = 1; off < 256; off <<= 1) {
+        const uint32_t add = (threadIdx.x >= (unsigned)off) ? part[threadIdx.x - off] : 0u;
+        __syncthreads();
+        part[threadIdx.x] += add;
+        __syncthreads();
+    }
+    const uint32_t need0 = st[1];
+    const uint32_t incl = part[threadIdx.x];
+    const uint32_t excl = incl - mine;
+    __syncthreads();
+    // the owner is the first thread whose inclusive count reaches `need`; if none does (cannot happen when the image has
+    // more candidates than k) the last bin wins
+    const bool owner = (excl < need0 && incl >= need0) || (threadIdx.x == 255 && incl < need0);
+    if (owner) {
+        uint32_t need = need0 - excl;
+        int b = hi;
+        for (int q = 0; q < 8; ++q, --b) {
+            if (sh[b] >= need || b == 0) break;
             need -= sh[b];
         }
+        if (b < 0) b = 0;
         st[0] |= (uint32_t)b << ps.shift;
         st[1] = need;                   // how many to take from inside this bucket
     }
 }
 
-// survivors: score bits > threshold always; == threshold: all of them (exact ties are cut after the ordering pass)
+// survivors: score bits > threshold always; == threshold: all of them (exact ties are cut after the ordering pass).
+// 4 candidates per thread, one atomic per block.
+constexpr int kCompactPerThread = 4;
 __global__ void __launch_bounds__(256)
 select_compact_kernel(const cldet_candidate* __restrict__ cand, const uint64_t* __restrict__ keys,
                       const int32_t* __restrict__ counts, int64_t capacity, uint32_t* __restrict__ state,
@@ -319,19 +347,29 @@ select_compact_kernel(const cldet_candidate* __restrict__ cand, const uint64_t* 
     const int j = blockIdx.y;
     uint32_t* st = state + 4 * j;
     const int64_t cnt = min64(counts[j], capacity);
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if ((int64_t)blockIdx.x * blockDim.x >= cnt) return;
+    const int64_t i0 = (int64_t)blockIdx.x * (256 * kCompactPerThread);
+    if (i0 >= cnt) return;
     const bool all = st[3] != 0;
     const uint32_t thr = st[0];
-    bool take = false;
-    uint64_t key = 0;
-    if (i < cnt) {
-        key = keys[(int64_t)j * capacity + i];
-        take = all || (uint32_t)(key >> 32) >= thr;
+    uint64_t key[kCompactPerThread];
+    bool take[kCompactPerThread];
+    int mine = 0;
+#pragma unroll
+    for (int u = 0; u < kCompactPerThread; ++u) {
+        const int64_t i = i0 + u * 256 + threadIdx.x;
+        key[u] = (i < cnt) ? keys[(int64_t)j * capacity + i] : 0ull;
+        take[u] = (i < cnt) && (all || (uint32_t)(key[u] >> 32) >= thr);
+        mine += take[u] ? 1 : 0;
     }
-    const unsigned ballot = __ballot_sync(0xffffffffu, take);
+    // exclusive prefix of `mine` over the block
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    if (lane == 0) warp_tot[warp] = __popc(ballot);
+    int incl = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += v;
+    }
+    if (lane == 31) warp_tot[warp] = incl;
     __syncthreads();
     if (threadIdx.x == 0) {
         int tot = 0;
@@ -343,17 +381,26 @@ select_compact_kernel(const cldet_candidate* __restrict__ cand, const uint64_t* 
         block_base = tot ? (int)atomicAdd(&st[2], (uint32_t)tot) : 0;
     }
     __syncthreads();
-    if (take) {
-        const int64_t slot = (int64_t)block_base + warp_tot[warp] + __popc(ballot & ((1u << lane) - 1u));
-        if (slot < out_capacity) {
-            out_cand[(int64_t)j * out_capacity + slot] = cand[(int64_t)j * capacity + i];
-            out_keys[(int64_t)j * out_capacity + slot] = key;
+    int64_t slot = (int64_t)block_base + warp_tot[warp] + (incl - mine);
+#pragma unroll
+    for (int u = 0; u < kCompactPerThread; ++u) {
+        if (take[u]) {
+            const int64_t i = i0 + u * 256 + threadIdx.x;
+            if (slot < out_capacity) {
+                const float4* src = reinterpret_cast<const float4*>(cand + (int64_t)j * capacity + i);
+                float4* dst = reinterpret_cast<float4*>(out_cand + (int64_t)j * out_capacity + slot);
+                dst[0] = src[0];
+                dst[1] = src[1];
+                out_keys[(int64_t)j * out_capacity + slot] = key[u];
+            }
+            ++slot;
         }
     }
 }
 
 // Tiled rank sort: rank_i = #{ l : key_l > key_i } (keys are distinct).  Writes candidate i to position rank_i when
-// rank_i < limit (top-k cut), and the final count min(n, limit).
+// rank_i < limit (top-k cut), and the final count min(n, limit).  Blocks stride over the candidates, so the grid can be
+// sized for the expected count and still be correct for any count.
 __global__ void __launch_bounds__(256)
 rank_sort_kernel(const cldet_candidate* __restrict__ cand, const uint64_t* __restrict__ keys, const uint32_t* __restrict__ state,
                  const int32_t* __restrict__ counts_in, int64_t in_capacity, int topk, cldet_candidate* __restrict__ sorted,
@@ -364,22 +411,28 @@ rank_sort_kernel(const cldet_candidate* __restrict__ cand, const uint64_t* __res
     n = min64(n, in_capacity);
     const int64_t limit = (topk > 0) ? min64(n, topk) : n;
     if (blockIdx.x == 0 && threadIdx.x == 0) sorted_counts[j] = (int32_t)min64(limit, out_capacity);
-    if ((int64_t)blockIdx.x * blockDim.x >= n) return;
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const uint64_t* k = keys + (int64_t)j * in_capacity;
-    const uint64_t mine = (i < n) ? k[i] : ~0ull;
-    int64_t rank = 0;
-    for (int64_t t0 = 0; t0 < n; t0 += 1024) {
-        const int m = (int)min64(1024, n - t0);
-        __syncthreads();
-        for (int t = threadIdx.x; t < m; t += blockDim.x) tile[t] = k[t0 + t];
-        __syncthreads();
-        int r = 0;
+    for (int64_t i0 = (int64_t)blockIdx.x * blockDim.x; i0 < n; i0 += (int64_t)gridDim.x * blockDim.x) {   // block-uniform
+        const int64_t i = i0 + threadIdx.x;
+        const uint64_t mine = (i < n) ? k[i] : ~0ull;
+        int64_t rank = 0;
+        for (int64_t t0 = 0; t0 < n; t0 += 1024) {
+            const int m = (int)min64(1024, n - t0);
+            __syncthreads();
+            for (int t = threadIdx.x; t < m; t += blockDim.x) tile[t] = k[t0 + t];
+            __syncthreads();
+            int r = 0;
 #pragma unroll 8
-        for (int t = 0; t < m; ++t) r += (tile[t] > mine) ? 1 : 0;
-        rank += r;
+            for (int t = 0; t < m; ++t) r += (tile[t] > mine) ? 1 : 0;
+            rank += r;
+        }
+        if (i < n && rank < limit && rank < out_capacity) {
+            const float4* src = reinterpret_cast<const float4*>(cand + (int64_t)j * in_capacity + i);
+            float4* dst = reinterpret_cast<float4*>(sorted + (int64_t)j * out_capacity + rank);
+            dst[0] = src[0];
+            dst[1] = src[1];
+        }
     }
-    if (i < n && rank < limit && rank < out_capacity) sorted[(int64_t)j * out_capacity + rank] = cand[(int64_t)j * in_capacity + i];
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -412,14 +465,17 @@ nms_prepare_kernel(const cldet_candidate* __restrict__ sorted, const int32_t* __
     }
 }
 
-__device__ __forceinline__ bool suppresses(const float4 a, const float4 b, float thr) {
-    // torchvision nms: inter / ((area_a + area_b) - inter) > thr, all fp32, one rounding per op
-    const float area_a = (a.z - a.x) * (a.w - a.y);
-    const float area_b = (b.z - b.x) * (b.w - b.y);
-    const float w = fmaxf(fminf(a.z, b.z) - fmaxf(a.x, b.x), 0.0f);
-    const float h = fmaxf(fminf(a.w, b.w) - fmaxf(a.y, b.y), 0.0f);
+__device__ __forceinline__ bool suppresses(const float4 a, float area_a, const float4 b, float area_b, float thr) {
+    // torchvision nms: inter / ((area_a + area_b) - inter) > thr, all fp32, one rounding per op.
+    // Empty intersections (the vast majority of pairs) give IoU +0 (or NaN), never > thr for thr >= 0: exit before the divide.
+    const float w = fminf(a.z, b.z) - fmaxf(a.x, b.x);
+    const float h = fminf(a.w, b.w) - fmaxf(a.y, b.y);
+    if (!(w > 0.0f) || !(h > 0.0f)) {
+        if (thr >= 0.0f) return false;
+        const float inter0 = fmaxf(w, 0.0f) * fmaxf(h, 0.0f);
+        return (inter0 / ((area_a + area_b) - inter0)) > thr;
+    }
     const float inter = w * h;
-    if (!(inter > 0.0f)) return (inter / ((area_a + area_b) - inter)) > thr;   // 0/x or NaN: keep IEEE semantics
     return __fdiv_rn(inter, (area_a + area_b) - inter) > thr;
 }
 
@@ -437,43 +493,56 @@ nms_mask_kernel(const cldet_candidate* __restrict__ sorted, const int32_t* __res
     const cldet_candidate* c = sorted + (int64_t)j * capacity;
 
     __shared__ float4 cbox[64];
+    __shared__ float carea[64];
     __shared__ int clab[64];
     const int ci = col_blk * 64 + threadIdx.x;
     if (ci < n) {
-        const cldet_candidate b = c[ci];
-        float4 v = make_float4(b.x1, b.y1, b.x2, b.y2);
+        const float4* rec = reinterpret_cast<const float4*>(c + ci);
+        float4 v = rec[0];
+        const int lab = __float_as_int(rec[1].y);
         if (mode == 1) {                                              // boxes + (label * (max + 1))[:, None]
-            const float off = (float)b.label * off_unit;
+            const float off = (float)lab * off_unit;
             v.x += off; v.y += off; v.z += off; v.w += off;
         }
         cbox[threadIdx.x] = v;
-        clab[threadIdx.x] = b.label;
+        carea[threadIdx.x] = (v.z - v.x) * (v.w - v.y);
+        clab[threadIdx.x] = lab;
     }
     __syncthreads();
     const int ri = row_blk * 64 + threadIdx.x;
     if (ri >= n) return;
-    const cldet_candidate rb = c[ri];
-    float4 me = make_float4(rb.x1, rb.y1, rb.x2, rb.y2);
+    const float4* rrec = reinterpret_cast<const float4*>(c + ri);
+    float4 me = rrec[0];
+    const int my_lab = __float_as_int(rrec[1].y);
     if (mode == 1) {
-        const float off = (float)rb.label * off_unit;
+        const float off = (float)my_lab * off_unit;
         me.x += off; me.y += off; me.z += off; me.w += off;
     }
+    const float my_area = (me.z - me.x) * (me.w - me.y);
     const int ncol = min(64, n - col_blk * 64);
     uint64_t bits = 0;
     const int start = (row_blk == col_blk) ? threadIdx.x + 1 : 0;
     for (int t = start; t < ncol; ++t) {
-        if (mode == 2 && clab[t] != rb.label) continue;
-        if (suppresses(me, cbox[t], thr)) bits |= 1ull << t;
+        if (mode == 2 && clab[t] != my_lab) continue;
+        if (suppresses(me, my_area, cbox[t], carea[t], thr)) bits |= 1ull << t;
     }
     mask[(int64_t)j * mask_stride_img + (int64_t)ri * col_blocks_alloc + col_blk] = bits;
 }
 
+// Sequential part of greedy NMS, one block per image, 64 sorted boxes per step:
+//   (1) 64 threads fetch the chunk's diagonal mask words into shared memory,
+//   (2) one warp resolves the chunk serially in registers (who survives inside the chunk),
+//   (3) all 256 threads OR the surviving rows' mask words into the running "removed" bitmap of the later chunks:
+//       thread = (column word, row group), 16 x 16, so every thread issues its <= 4 loads at once (the first version
+//       walked 64 dependent L2 loads per thread and took 13 us per chunk).
 __global__ void __launch_bounds__(256)
 nms_resolve_kernel(const int32_t* __restrict__ counts, int64_t capacity, const uint64_t* __restrict__ mask,
                    int64_t mask_stride_img, int col_blocks_alloc, uint64_t* __restrict__ remv_ws, int32_t* __restrict__ keep,
                    int32_t* __restrict__ keep_counts) {
+    __shared__ uint64_t diag[64];
     __shared__ uint64_t kept_bits;
     __shared__ int kept_total;
+    __shared__ unsigned long long acc[16];
     const int j = blockIdx.x;
     const int n = (int)min64(counts[j], capacity);
     const int col_blocks = (n + 63) / 64;
@@ -484,27 +553,28 @@ nms_resolve_kernel(const int32_t* __restrict__ counts, int64_t capacity, const u
     __syncthreads();
     for (int c = 0; c < col_blocks; ++c) {
         const int rows = min(64, n - c * 64);
-        const int base = kept_total;     // written by lane 0 below, published by the barriers that end the iteration
+        if (threadIdx.x < 64)
+            diag[threadIdx.x] = (threadIdx.x < rows) ? m[(int64_t)(c * 64 + threadIdx.x) * col_blocks_alloc + c] : 0ull;
         __syncthreads();
         if (threadIdx.x < 32) {
             const int lane = threadIdx.x;
-            // diagonal block words of rows lane and lane+32
-            const uint64_t d0 = (lane < rows) ? m[(int64_t)(c * 64 + lane) * col_blocks_alloc + c] : 0ull;
-            const uint64_t d1 = (lane + 32 < rows) ? m[(int64_t)(c * 64 + lane + 32) * col_blocks_alloc + c] : 0ull;
             uint64_t cur = remv[c];
             uint64_t kept = 0;
-            for (int b = 0; b < rows; ++b) {
-                const uint64_t w = __shfl_sync(0xffffffffu, (b < 32) ? d0 : d1, b & 31);
-                if (!((cur >> b) & 1ull)) {
+#pragma unroll 16
+            for (int b = 0; b < 64; ++b) {
+                const uint64_t w = diag[b];                       // broadcast read, independent of the chain
+                if (b < rows && !((cur >> b) & 1ull)) {
                     kept |= 1ull << b;
                     cur |= w;
                 }
             }
             // ordered output of this chunk's survivors
-            const uint64_t lo_mask0 = (1ull << lane) - 1ull;
-            if ((kept >> lane) & 1ull) keep[(int64_t)j * capacity + base + __popcll(kept & lo_mask0)] = c * 64 + lane;
-            const uint64_t lo_mask1 = (1ull << (lane + 32)) - 1ull;
-            if ((kept >> (lane + 32)) & 1ull) keep[(int64_t)j * capacity + base + __popcll(kept & lo_mask1)] = c * 64 + lane + 32;
+            const int base = kept_total;
+            const uint64_t lo0 = (1ull << lane) - 1ull;
+            if ((kept >> lane) & 1ull) keep[(int64_t)j * capacity + base + __popcll(kept & lo0)] = c * 64 + lane;
+            const uint64_t lo1 = (1ull << (lane + 32)) - 1ull;
+            if ((kept >> (lane + 32)) & 1ull) keep[(int64_t)j * capacity + base + __popcll(kept & lo1)] = c * 64 + lane + 32;
+            __syncwarp();
             if (lane == 0) {
                 kept_bits = kept;
                 kept_total = base + __popcll(kept);
@@ -512,16 +582,23 @@ nms_resolve_kernel(const int32_t* __restrict__ counts, int64_t capacity, const u
         }
         __syncthreads();
         const uint64_t kept = kept_bits;
-        // every later column block absorbs the masks of the rows kept in this chunk
-        for (int t = c + 1 + threadIdx.x; t < col_blocks; t += blockDim.x) {
-            uint64_t acc = remv[t];
-            uint64_t k = kept;
-            while (k) {
-                const int b = __ffsll((long long)k) - 1;
-                k &= k - 1;
-                acc |= m[(int64_t)(c * 64 + b) * col_blocks_alloc + t];
+        // absorb: later column words, 16 at a time; thread (tc, tg) handles word t0+tc and rows tg, tg+16, tg+32, tg+48
+        const int tc = threadIdx.x & 15, tg = threadIdx.x >> 4;
+        for (int t0 = c + 1; t0 < col_blocks; t0 += 16) {
+            if (threadIdx.x < 16) acc[threadIdx.x] = 0ull;
+            __syncthreads();
+            const int t = t0 + tc;
+            if (t < col_blocks) {
+                uint64_t v = 0;
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int b = tg + 16 * q;
+                    if ((kept >> b) & 1ull) v |= m[(int64_t)(c * 64 + b) * col_blocks_alloc + t];
+                }
+                if (v) atomicOr(&acc[tc], (unsigned long long)v);
             }
-            remv[t] = acc;
+            __syncthreads();
+            if (threadIdx.x < 16 && t0 + (int)threadIdx.x < col_blocks) remv[t0 + threadIdx.x] |= acc[threadIdx.x];
         }
         __syncthreads();
     }
@@ -706,16 +783,20 @@ int cldet_sort_candidates(const cldet_candidate* d_candidates, const uint64_t* d
         CLDET_LAUNCH_CHECK();
         const SelPass passes[3] = {{21, 11, 0}, {10, 11, 11}, {0, 10, 22}};
         for (int ps = 0; ps < 3; ++ps) {
-            dim3 g((unsigned)std::min(blocks_x, 64), (unsigned)num_images);
+            dim3 g((unsigned)std::max(1, std::min(blocks_x / 8, 16)), (unsigned)num_images);
             select_hist_kernel<<<g, 256, 0, s>>>(d_keys, d_counts, capacity, passes[ps], state, hist);
             CLDET_LAUNCH_CHECK();
             select_pick_kernel<<<num_images, 256, 0, s>>>(passes[ps], state, hist);
             CLDET_LAUNCH_CHECK();
         }
-        dim3 gc((unsigned)((max_count + 255) / 256), (unsigned)num_images);
+        const int64_t per_block = 256 * kCompactPerThread;
+        dim3 gc((unsigned)((max_count + per_block - 1) / per_block), (unsigned)num_images);
         select_compact_kernel<<<gc, 256, 0, s>>>(d_candidates, d_keys, d_counts, capacity, state, sel_cand, sel_keys, max_count);
         CLDET_LAUNCH_CHECK();
-        rank_sort_kernel<<<gc, 256, 0, s>>>(sel_cand, sel_keys, state, nullptr, max_count, topk, d_sorted, sorted_capacity,
+        // survivors are ~topk (plus exact score ties): size the grid for 2*topk, the kernel strides if there are more
+        dim3 gr((unsigned)std::max<int64_t>(1, std::min<int64_t>((max_count + 255) / 256, (2 * (int64_t)topk + 255) / 256)),
+                (unsigned)num_images);
+        rank_sort_kernel<<<gr, 256, 0, s>>>(sel_cand, sel_keys, state, nullptr, max_count, topk, d_sorted, sorted_capacity,
                                              d_sorted_counts);
         CLDET_LAUNCH_CHECK();
     } else {
