@@ -22,8 +22,17 @@ namespace cldet {
 #ifndef CLDET_LOSS_MINBLOCKS
 #define CLDET_LOSS_MINBLOCKS 6
 #endif
+#ifndef CLDET_LOSS_UNROLL8
+#define CLDET_LOSS_UNROLL8 2
+#endif
+#ifndef CLDET_LOSS_MINBLOCKS8
+#define CLDET_LOSS_MINBLOCKS8 4
+#endif
 constexpr int kLossThreads = 256;
-constexpr int kUnroll = CLDET_LOSS_UNROLL;
+// vectors in flight per thread and resident CTAs per SM, per vector width (tuned on B200, see profiles/)
+__host__ __device__ constexpr int unroll_for(int vec) { return vec == 8 ? CLDET_LOSS_UNROLL8 : CLDET_LOSS_UNROLL; }
+__host__ __device__ constexpr int minblocks_for(int vec) { return vec == 8 ? CLDET_LOSS_MINBLOCKS8 : CLDET_LOSS_MINBLOCKS; }
+__host__ __device__ constexpr uint32_t tile_for(int vec) { return (uint32_t)kLossThreads * unroll_for(vec); }
 
 struct LossArgs {
     const float* cls;
@@ -287,31 +296,68 @@ __device__ __forceinline__ ImageScales image_scales(const float* w, int N, int j
     return sc;
 }
 
-constexpr int kMaxAnchorsPerBlock = 4096;     // assignment words of one chunk staged in shared memory (16 KB)
-constexpr uint32_t kTile = kLossThreads * kUnroll;   // float4 vectors per fully unrolled tile
+// VEC consecutive classes of one anchor.  VEC = 8 uses the 256-bit global load/store of sm_100 (LDG.E.256 / STG.E.256):
+// one instruction moves 32 B per thread, 1 KB per warp.
+template <int VEC>
+struct VecT {
+    float v[VEC];
+};
 
-// One 128-bit vector (4 consecutive classes of one anchor; C % 4 == 0 so it never straddles anchors).
-template <bool GAMMA2, bool VARIANTS, bool GRAD>
-__device__ __forceinline__ float4 cls_vec4(const float4 x, uint32_t m, uint32_t col, int64_t anchor_abs, const LossArgs& a,
-                                           const ImageScales& sc, float as_bg, bool need_iou, Acc& acc) {
+template <int VEC>
+__device__ __forceinline__ VecT<VEC> ld_stream_vec(const float* p);
+template <>
+__device__ __forceinline__ VecT<4> ld_stream_vec<4>(const float* p) {
+    VecT<4> r;
+    asm volatile("ld.global.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(r.v[0]), "=f"(r.v[1]), "=f"(r.v[2]), "=f"(r.v[3])
+                 : "l"(p));
+    return r;
+}
+template <>
+__device__ __forceinline__ VecT<8> ld_stream_vec<8>(const float* p) {
+    VecT<8> r;
+    asm volatile("ld.global.L1::no_allocate.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(r.v[0]), "=f"(r.v[1]), "=f"(r.v[2]), "=f"(r.v[3]), "=f"(r.v[4]), "=f"(r.v[5]), "=f"(r.v[6]), "=f"(r.v[7])
+                 : "l"(p));
+    return r;
+}
+template <int VEC>
+__device__ __forceinline__ void st_stream_vec(float* p, const VecT<VEC>& x);
+template <>
+__device__ __forceinline__ void st_stream_vec<4>(float* p, const VecT<4>& x) {
+    asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(x.v[0]), "f"(x.v[1]), "f"(x.v[2]),
+                 "f"(x.v[3])
+                 : "memory");
+}
+template <>
+__device__ __forceinline__ void st_stream_vec<8>(float* p, const VecT<8>& x) {
+    asm volatile("st.global.L1::no_allocate.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "f"(x.v[0]), "f"(x.v[1]),
+                 "f"(x.v[2]), "f"(x.v[3]), "f"(x.v[4]), "f"(x.v[5]), "f"(x.v[6]), "f"(x.v[7])
+                 : "memory");
+}
+
+constexpr int kMaxAnchorsPerBlock = 4096;     // assignment words of one chunk staged in shared memory (16 KB)
+
+// One vector (VEC consecutive classes of one anchor; C % VEC == 0 so it never straddles anchors).
+template <int VEC, bool GAMMA2, bool VARIANTS, bool GRAD>
+__device__ __forceinline__ VecT<VEC> cls_vec(const VecT<VEC>& x, uint32_t m, uint32_t col, int64_t anchor_abs, const LossArgs& a,
+                                             const ImageScales& sc, float as_bg, bool need_iou, Acc& acc) {
     const uint32_t st = meta_state(m);
-    float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+    VecT<VEC> g;
+#pragma unroll
+    for (int e = 0; e < VEC; ++e) g.v[e] = 0.0f;
     // does the vector hold the target-1 element of a positive anchor?
-    const bool special = (st == CLDET_STATE_POS) && (meta_label(m) - col < 4u);
+    const bool special = (st == CLDET_STATE_POS) && (meta_label(m) - col < (uint32_t)VEC);
     if (GAMMA2 && !VARIANTS && !special) {
         if (st != CLDET_STATE_IGNORE) {      // bg anchor, empty image, or the target-0 part of a positive row
-            g.x = neg_element_raw<GRAD>(x.x, as_bg, acc.raw[0]);
-            g.y = neg_element_raw<GRAD>(x.y, as_bg, acc.raw[1]);
-            g.z = neg_element_raw<GRAD>(x.z, as_bg, acc.raw[2]);
-            g.w = neg_element_raw<GRAD>(x.w, as_bg, acc.raw[3]);
+#pragma unroll
+            for (int e = 0; e < VEC; ++e) g.v[e] = neg_element_raw<GRAD>(x.v[e], as_bg, acc.raw[e & 3]);
         }
     } else {
         float iou = 1.0f;
         if (need_iou && st == CLDET_STATE_POS) iou = a.iou_max[anchor_abs];
-        g.x = cls_element<GAMMA2, VARIANTS, GRAD>(x.x, (int)col + 0, m, a, sc, iou, acc);
-        g.y = cls_element<GAMMA2, VARIANTS, GRAD>(x.y, (int)col + 1, m, a, sc, iou, acc);
-        g.z = cls_element<GAMMA2, VARIANTS, GRAD>(x.z, (int)col + 2, m, a, sc, iou, acc);
-        g.w = cls_element<GAMMA2, VARIANTS, GRAD>(x.w, (int)col + 3, m, a, sc, iou, acc);
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) g.v[e] = cls_element<GAMMA2, VARIANTS, GRAD>(x.v[e], (int)col + e, m, a, sc, iou, acc);
     }
     return g;
 }
@@ -361,19 +407,21 @@ __device__ __forceinline__ void process_chunk(const LossArgs& a, int j, int64_t 
     // an image without GT has every anchor in state EMPTY: alpha becomes (1 - alpha) for the whole image (losses.py:293-296)
     const float alpha_img = (meta_state(smeta[0]) == CLDET_STATE_EMPTY) ? 1.0f - a.p.alpha : a.p.alpha;
     const float as_bg = alpha_img * sc.s_bg;
-    if (VEC == 4) {
-        const float4* src = reinterpret_cast<const float4*>(a.cls + base);
-        float4* dst = GRAD ? reinterpret_cast<float4*>(a.gcls + base) : nullptr;
-        const uint32_t nvec = count >> 2;
+    if constexpr (VEC >= 4) {
+        constexpr int kUnroll = unroll_for(VEC);
+        constexpr uint32_t kTile = tile_for(VEC);
+        const float* src = a.cls + base;
+        float* dst = GRAD ? a.gcls + base : nullptr;
+        const uint32_t nvec = count / VEC;
         // (row, col) of this thread's vector advance by a constant per step of kLossThreads vectors: no division in the loop
-        const uint32_t step_elems = kLossThreads * 4u;
+        const uint32_t step_elems = kLossThreads * (uint32_t)VEC;
         const uint32_t drow = step_elems / C, dcol = step_elems - drow * C;
-        uint32_t row = (uint32_t)(4 * tid) / C;
-        uint32_t col = (uint32_t)(4 * tid) - row * C;
+        uint32_t row = (uint32_t)(VEC * tid) / C;
+        uint32_t col = (uint32_t)(VEC * tid) - row * C;
         uint32_t v0 = tid;
         const uint32_t full_end = nvec - nvec % kTile;     // vectors covered by complete tiles (no bounds checks)
         for (; v0 < full_end; v0 += kTile) {
-            float4 x[kUnroll];
+            VecT<VEC> x[kUnroll];
             uint32_t mm[kUnroll], cc[kUnroll], rr[kUnroll];
 #pragma unroll
             for (int u = 0; u < kUnroll; ++u) {
@@ -387,21 +435,27 @@ __device__ __forceinline__ void process_chunk(const LossArgs& a, int j, int64_t 
                     row += 1;
                 }
                 // ignored anchors contribute nothing: do not even read their probabilities
-                if (meta_state(mm[u]) != CLDET_STATE_IGNORE) x[u] = ld_stream_f4(src + v0 + u * kLossThreads);
-                else x[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (meta_state(mm[u]) != CLDET_STATE_IGNORE) {
+                    x[u] = ld_stream_vec<VEC>(src + (size_t)(v0 + u * kLossThreads) * VEC);
+                } else {
+#pragma unroll
+                    for (int e = 0; e < VEC; ++e) x[u].v[e] = 0.0f;
+                }
             }
 #pragma unroll
             for (int u = 0; u < kUnroll; ++u) {
-                const float4 g = cls_vec4<GAMMA2, VARIANTS, GRAD>(x[u], mm[u], cc[u], abs0 + rr[u], a, sc, as_bg, need_iou, acc);
-                if (GRAD) st_stream_f4(dst + v0 + u * kLossThreads, g);
+                const VecT<VEC> g = cls_vec<VEC, GAMMA2, VARIANTS, GRAD>(x[u], mm[u], cc[u], abs0 + rr[u], a, sc, as_bg, need_iou, acc);
+                if (GRAD) st_stream_vec<VEC>(dst + (size_t)(v0 + u * kLossThreads) * VEC, g);
             }
         }
         for (; v0 < nvec; v0 += kLossThreads) {              // ragged tail of the chunk
             const uint32_t m = smeta[row];
-            float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (meta_state(m) != CLDET_STATE_IGNORE) x = ld_stream_f4(src + v0);
-            const float4 g = cls_vec4<GAMMA2, VARIANTS, GRAD>(x, m, col, abs0 + row, a, sc, as_bg, need_iou, acc);
-            if (GRAD) st_stream_f4(dst + v0, g);
+            VecT<VEC> x;
+#pragma unroll
+            for (int e = 0; e < VEC; ++e) x.v[e] = 0.0f;
+            if (meta_state(m) != CLDET_STATE_IGNORE) x = ld_stream_vec<VEC>(src + (size_t)v0 * VEC);
+            const VecT<VEC> g = cls_vec<VEC, GAMMA2, VARIANTS, GRAD>(x, m, col, abs0 + row, a, sc, as_bg, need_iou, acc);
+            if (GRAD) st_stream_vec<VEC>(dst + (size_t)v0 * VEC, g);
             col += dcol;
             row += drow;
             if (col >= C) {
@@ -425,7 +479,7 @@ __device__ __forceinline__ void process_chunk(const LossArgs& a, int j, int64_t 
 }
 
 template <int VEC, bool GAMMA2, bool VARIANTS, bool GRAD>
-__global__ void __launch_bounds__(kLossThreads, CLDET_LOSS_MINBLOCKS) focal_loss_kernel(const LossArgs a) {
+__global__ void __launch_bounds__(kLossThreads, minblocks_for(VEC)) focal_loss_kernel(const LossArgs a) {
     __shared__ float red[4][kLossThreads / 32];
     __shared__ double fin[4][kLossThreads / 32];
     __shared__ bool is_last;
@@ -557,12 +611,13 @@ struct LossPlan {
 
 static int64_t gcd64(int64_t x, int64_t y) { return y == 0 ? x : gcd64(y, x % y); }
 
-static LossPlan make_plan(int N, int64_t A, int C) {
+static LossPlan make_plan(int N, int64_t A, int C, int vec) {
     LossPlan pl;
-    // ~5-8k float4 per block; when C % 4 == 0 the chunk is made a whole number of fully unrolled tiles
-    // (anchors_per_block * C/4 divisible by kTile) so the hot loop runs without bounds checks.
+    // ~24k elements per block; with a vector path the chunk is made a whole number of fully unrolled tiles
+    // (anchors_per_block * C/vec divisible by kTile) so the hot loop runs without bounds checks.
     int64_t quantum = 32;
-    if (C % 4 == 0) quantum = kTile / gcd64(C / 4, kTile);
+    const int64_t kTile = tile_for(vec);
+    if (vec > 1) quantum = kTile / gcd64(C / vec, kTile);
     int64_t apb = (24576 / C + quantum - 1) / quantum * quantum;
     if (apb > kMaxAnchorsPerBlock) apb = kMaxAnchorsPerBlock / quantum * quantum;
     if (apb < 32) apb = (quantum <= kMaxAnchorsPerBlock) ? quantum : 32;
@@ -624,6 +679,14 @@ static void dispatch_reweight(const LossArgs& a, bool gamma2, bool variants, dim
     }
 }
 
+// widest vector the class map allows: rows must be a whole number of vectors and the buffers aligned to the vector
+static int pick_vec(int C, const void* cls, const void* gcls) {
+    const uintptr_t bits = (uintptr_t)cls | (uintptr_t)gcls;
+    if (C % 8 == 0 && (bits & 31) == 0) return 8;
+    if (C % 4 == 0 && (bits & 15) == 0) return 4;
+    return 1;
+}
+
 static bool has_variants(const cldet_loss_params& p) {
     return p.incremental && (p.ignore_past_class || p.decrease_positive_by_iou || p.enhance_on_new ||
                              p.decrease_positive != 1.0f);
@@ -676,7 +739,8 @@ static int loss_stage(const float* d_cls, const float* d_reg, const float* d_anc
         return CLDET_ERR_INVALID_ARGUMENT;
     cudaStream_t s = (cudaStream_t)stream;
 
-    const LossPlan pl = make_plan(num_images, num_anchors, num_classes);
+    const int vec = pick_vec(num_classes, d_cls, d_grad_cls);
+    const LossPlan pl = make_plan(num_images, num_anchors, num_classes, vec);
     LossArgs a;
     a.cls = d_cls; a.reg = d_reg; a.anchors = reinterpret_cast<const float4*>(d_anchors); a.ann = d_annotations;
     a.N = num_images; a.A = num_anchors; a.C = num_classes; a.G = gt_rows; a.p = *params;
@@ -695,7 +759,8 @@ static int loss_stage(const float* d_cls, const float* d_reg, const float* d_anc
     }
     dim3 grid((unsigned)pl.bpi, (unsigned)num_images);
     const bool gamma2 = params->gamma == 2.0f;
-    if (num_classes % 4 == 0) dispatch_loss<4>(a, grad, gamma2, variants, grid, s);
+    if (vec == 8) dispatch_loss<8>(a, grad, gamma2, variants, grid, s);
+    else if (vec == 4) dispatch_loss<4>(a, grad, gamma2, variants, grid, s);
     else dispatch_loss<1>(a, grad, gamma2, variants, grid, s);
     CLDET_LAUNCH_CHECK();
     return CLDET_OK;
@@ -755,7 +820,8 @@ int cldet_focal_loss_reweight(const float* d_cls, const float* d_reg, const floa
     if (ws_bytes < workspace_bytes(num_images, num_anchors)) return CLDET_ERR_WORKSPACE_TOO_SMALL;
     if (params->incremental && params->decrease_positive_by_iou && !d_iou_max) return CLDET_ERR_INVALID_ARGUMENT;
     cudaStream_t s = (cudaStream_t)stream;
-    const LossPlan pl = make_plan(num_images, num_anchors, num_classes);
+    const int vec = pick_vec(num_classes, d_cls, d_grad_cls);
+    const LossPlan pl = make_plan(num_images, num_anchors, num_classes, vec);
     LossArgs a;
     a.cls = d_cls; a.reg = d_reg; a.anchors = reinterpret_cast<const float4*>(d_anchors); a.ann = d_annotations;
     a.N = num_images; a.A = num_anchors; a.C = num_classes; a.G = gt_rows; a.p = *params;
@@ -768,7 +834,8 @@ int cldet_focal_loss_reweight(const float* d_cls, const float* d_reg, const floa
     dim3 grid((unsigned)pl.bpi, (unsigned)num_images);
     const bool gamma2 = params->gamma == 2.0f;
     const bool variants = has_variants(*params);
-    if (num_classes % 4 == 0) dispatch_reweight<4>(a, gamma2, variants, grid, s);
+    if (vec == 8) dispatch_reweight<8>(a, gamma2, variants, grid, s);
+    else if (vec == 4) dispatch_reweight<4>(a, gamma2, variants, grid, s);
     else dispatch_reweight<1>(a, gamma2, variants, grid, s);
     CLDET_LAUNCH_CHECK();
     return CLDET_OK;
