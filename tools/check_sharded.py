@@ -1,0 +1,68 @@
+#!/usr/bin/env python
+"""Multi-GPU check of the image-sharded loss (run under torchrun, one rank per GPU, NCCL):
+every rank computes its shard with ShardedFocalLoss; rank 0 also computes the whole batch on one GPU; the caller-side
+reductions (mean and the clip_loss mask) and the gradients of each shard must agree.
+
+    python -m torch.distributed.run --nproc-per-node 2 --master-addr 127.0.0.1 tools/check_sharded.py
+"""
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+import torch.distributed as dist  # noqa: E402
+
+import cl_object_detection_b200 as cld  # noqa: E402
+from bench import synth_annotations  # noqa: E402
+
+
+def caller_reduction(out, clip):
+    bg, fg = out['cls_loss']
+    mask = fg >= clip
+    fg_term = fg[mask].mean() if mask.sum() > 0 else fg.sum() * 0
+    return bg.mean() + fg_term + out['reg_loss'].mean()
+
+
+def main():
+    rank, world, local = int(os.environ['RANK']), int(os.environ['WORLD_SIZE']), int(os.environ['LOCAL_RANK'])
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    dist.init_process_group('nccl', device_id=dev)
+    h, w, c, n_global, g = 512, 512, 20, 5 * world + 1, 12         # uneven shards on purpose
+    anchors = cld.generate_anchors(h, w, dev)
+    a = anchors.shape[1]
+    gen = torch.Generator(device='cpu').manual_seed(77)
+    probs = torch.sigmoid(torch.randn(n_global, a, c, generator=gen) * 2 - 4)
+    reg = torch.randn(n_global, a, 4, generator=gen)
+    ann = torch.from_numpy(synth_annotations(np.random.default_rng(77), n_global, g, h, w, c, empty=(1,)))
+    params = cld.HeadParams()
+    sl = cld.shard_slice(n_global, world, rank)
+    p = probs[sl].to(dev).requires_grad_(True)
+    r = reg[sl].to(dev).requires_grad_(True)
+    out = cld.ShardedFocalLoss()(p, r, anchors, ann[sl].to(dev), 0, params)
+    clip = 0.5 * float(out['cls_loss'][1].detach().median())
+    loss = caller_reduction(out, clip)
+    loss.backward()
+    # single-GPU truth on every rank (cheap at this size)
+    p0 = probs.to(dev).requires_grad_(True)
+    r0 = reg.to(dev).requires_grad_(True)
+    ref_out = cld.FocalLoss()(p0, r0, anchors, ann.to(dev), 0, params)
+    ref = caller_reduction(ref_out, clip)
+    ref.backward()
+    # per-image terms: same kernels, but the block partition (hence the fp32 summation order) depends on the local batch size
+    assert torch.allclose(out['cls_loss'][0], ref_out['cls_loss'][0], rtol=2e-6, atol=0), 'bg terms differ'
+    assert torch.allclose(out['cls_loss'][1], ref_out['cls_loss'][1], rtol=2e-6, atol=0), 'fg terms differ'
+    assert torch.allclose(loss, ref, rtol=1e-6), (loss, ref)
+    assert torch.allclose(p.grad, p0.grad[sl], rtol=1e-6, atol=1e-12), 'cls gradient differs'
+    assert torch.allclose(r.grad, r0.grad[sl], rtol=1e-6, atol=1e-12), 'reg gradient differs'
+    dist.barrier()
+    if rank == 0:
+        print('sharded loss ok: world=%d n_global=%d loss=%.6f' % (world, n_global, float(loss)))
+    dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()
