@@ -23,6 +23,7 @@ SOURCES = {
     'cldet_assign.cu': ['-fmad=false'],
     'cldet_detect.cu': ['-fmad=false'],
     'cldet_loss.cu': [],
+    'cldet_loss_logits.cu': [],
 }
 
 

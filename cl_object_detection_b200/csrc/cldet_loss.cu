@@ -1,595 +1,16 @@
-// K3: fused focal-loss + smooth-L1 forward AND backward in one pass over the [N,A,C] probabilities.
-// Reference: FocalLoss.forward, retinanet/losses.py:252-452, and the autograd graph it records.
-//
-// HBM traffic per image: read p (4 B/elt) + write dL/dp (4 B/elt) + 4 B/anchor assignment word
-// + 16 B/anchor dL/dreg write; regression inputs are touched for positive anchors only.
-// The dense [A,C] target matrix, the [A,G] IoU matrix and the ~25 elementwise temporaries of the
-// reference never exist.
-//
-// Parallel layout: grid = (blocks_per_image, N).  A block owns a contiguous chunk of anchors of ONE
-// image, so every reduction it produces belongs to one image: warp shuffle -> shared -> one partial
-// per block -> the last block of the image (threadfence + counter) adds the partials in a fixed order
-// in fp64.  Results are bit-reproducible run to run; there are no floating-point atomics.
-#include <math.h>
-
-#include "cldet_common.cuh"
+// K3 host side: C-ABI entry points of the fused focal-loss + smooth-L1 forward/backward (kernels: cldet_loss_kernels.cuh).
+// This translation unit instantiates the probabilities-in kernels; cldet_loss_logits.cu the logits-in (sigmoid-fused) ones.
+#include "cldet_loss_kernels.cuh"
 
 namespace cldet {
 
-#ifndef CLDET_LOSS_UNROLL
-#define CLDET_LOSS_UNROLL 2
-#endif
-#ifndef CLDET_LOSS_MINBLOCKS
-#define CLDET_LOSS_MINBLOCKS 6
-#endif
-#ifndef CLDET_LOSS_UNROLL8
-#define CLDET_LOSS_UNROLL8 2
-#endif
-#ifndef CLDET_LOSS_MINBLOCKS8
-#define CLDET_LOSS_MINBLOCKS8 4
-#endif
-constexpr int kLossThreads = 256;
-// vectors in flight per thread and resident CTAs per SM, per vector width (tuned on B200, see profiles/)
-__host__ __device__ constexpr int unroll_for(int vec) { return vec == 8 ? CLDET_LOSS_UNROLL8 : CLDET_LOSS_UNROLL; }
-__host__ __device__ constexpr int minblocks_for(int vec) { return vec == 8 ? CLDET_LOSS_MINBLOCKS8 : CLDET_LOSS_MINBLOCKS; }
-__host__ __device__ constexpr uint32_t tile_for(int vec) { return (uint32_t)kLossThreads * unroll_for(vec); }
-
-struct LossArgs {
-    const float* cls;
-    const float* reg;
-    const float4* anchors;
-    const float* ann;
-    int N;
-    int64_t A;
-    int C;
-    int G;
-    cldet_loss_params p;
-    const float* weights;        // [4][N] or null
-    const float* baked_weights;  // reweight mode only
-    float* gcls;
-    float* greg;
-    float* losses;               // [4][N]
-    const uint32_t* meta;
-    const float* iou_max;
-    const int32_t* npos;         // positives per image (input of the loss stage)
-    int32_t* npos_out;           // fused call: where the last block of an image publishes npos (else null)
-    int32_t* npos_reset;         // fused call: the workspace accumulator to clear for the next call (else null)
-    unsigned int* rw_counters;   // reweight pass: per-image block counters (workspace)
-    uint8_t* bg_mask;
-    int32_t* status;
-    float* partials;             // [N][bpi][4]
-    unsigned int* counters;      // [N]
-    int anchors_per_block;
-    int bpi;
-    uint32_t div_magic;          // floor(2^32 / C) + 1, or 0 -> use a real division
-};
-
-// ln(q) for normal positive q (here q in [1e-4, 1]).  Range reduction to m in [2/3, 4/3), then
-// log1p(m-1) = f - f^2/2 + f^3 * P(f), P of degree 5 (least-squares minimax fit, 2.7e-7 max relative
-// error of the whole function in fp32 -- well inside the 1e-5 contract; libdevice logf costs ~2x).
-__device__ __forceinline__ float log_fast(float q) {
-    const int i = __float_as_int(q);
-    const int e = (i - 0x3f2aaaab) & 0xff800000;
-    const float m = __int_as_float(i - e);
-    const float fe = (float)e;                      // exponent * 2^23, exact
-    const float f = m - 1.0f;
-    const float s = f * f;
-    float r = -1.492298990e-01f;
-    r = fmaf(r, f, 1.699251682e-01f);
-    r = fmaf(r, f, -1.650529057e-01f);
-    r = fmaf(r, f, 1.981773674e-01f);
-    r = fmaf(r, f, -2.500296831e-01f);
-    r = fmaf(r, f, 3.333675861e-01f);
-    r = fmaf(r, f, -0.5f);
-    r = fmaf(r, s, f);
-    return fmaf(fe, 0.693147182f * 1.1920928955078125e-7f, r);   // ln2 * 2^-23
-}
-
-__device__ __forceinline__ float __frcp_rn_fast(float x) {
-    float r;
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
-    return r;
-}
-
-template <bool GAMMA2>
-__device__ __forceinline__ void pow_and_dpow(float x, float gamma, float& pw, float& dpw) {
-    if (GAMMA2) {
-        pw = x * x;          // ATen evaluates pow(x, 2.0) as x*x
-        dpw = 2.0f * x;
-    } else {
-        pw = powf(x, gamma);
-        dpw = gamma * powf(x, gamma - 1.0f);
-    }
-}
-
-// Element with target 0 (losses.py:344-377 with t == 0):  l = a * p^g * (-ln(1-p)),
-// dl/dp = a * (g p^(g-1) * (-ln(1-p)) + p^g / (1-p)), zero outside the clamp pass-band [1e-4, 1-1e-4].
-template <bool GAMMA2, bool GRAD>
-__device__ __forceinline__ void neg_element(float p_raw, float alpha, float gamma, float scale, float& loss, float& grad) {
-    const float p = fminf(fmaxf(p_raw, 1e-4f), 0.9999f);
-    const float q = 1.0f - p;
-    const float nl = -log_fast(q);
-    float pw, dpw;
-    pow_and_dpow<GAMMA2>(p, gamma, pw, dpw);
-    loss = (alpha * pw) * nl;
-    if (GRAD) {
-        const float g = alpha * fmaf(dpw, nl, __fdividef(pw, q)) * scale;
-        grad = (p == p_raw) ? g : 0.0f;
-    }
-}
-
-// Hot-path form of the same element for gamma == 2: the per-image constant alpha is factored out of the loss
-// (raw += p^2 * (-ln(1-p)), multiplied by alpha once per block) and folded into `as` = alpha * upstream / npos for
-// the gradient: g = as * p * (2*(-ln(1-p)) + p/(1-p)).  ~26 instructions per element.
-template <bool GRAD>
-__device__ __forceinline__ float neg_element_raw(float p_raw, float as, float& raw) {
-#ifdef CLDET_LOSS_NOMATH      // experiment only: memory-side ceiling of this access pattern
-    raw += p_raw;
-    return p_raw * as;
-#endif
-    const float p = fminf(fmaxf(p_raw, 1e-4f), 0.9999f);
-    const float q = 1.0f - p;
-    const float L = log_fast(q);                     // ln(1-p) <= 0
-    raw = fmaf(-(p * p), L, raw);
-    if (!GRAD) return 0.0f;
-    const float t = fmaf(L, -2.0f, p * __frcp_rn_fast(q));
-    const float g = (as * p) * t;
-    return (p == p_raw) ? g : 0.0f;
-}
-
-// Element with target 1.  f is the focal-weight base of the three reference branches (losses.py:352-366).
-template <bool GAMMA2, bool GRAD>
-__device__ __forceinline__ void pos_element(float p_raw, const cldet_loss_params& lp, float iou_max, float scale,
-                                            float& loss, float& grad) {
-    const float p = fminf(fmaxf(p_raw, 1e-4f), 0.9999f);
-    float f, df;
-    if (!lp.incremental) {
-        f = 1.0f - p;
-        df = -1.0f;
-    } else if (lp.decrease_positive_by_iou) {
-        f = 1.0f - p;
-        df = -1.0f;
-        if (iou_max <= 0.7f) {                                           // mid_indices, losses.py:354
-            const float upper = fminf(fmaxf(iou_max + 0.2f, 1e-4f), 0.9999f);   // :361
-            if (p >= upper) {
-                f = 1e-4f;
-                df = 0.0f;
-            } else {
-                f = fabsf(p - upper);
-                df = -1.0f;                                              // sign(p - upper), p < upper
-            }
-        }
-    } else {
-        const float s = lp.decrease_positive;                            // :365-366
-        f = s - fminf(fmaxf(p, 0.0f), s);
-        df = (p >= 0.0f && p <= s) ? -1.0f : 0.0f;
-    }
-    const float nl = -logf(p);
-    float pw, dpw;
-    pow_and_dpow<GAMMA2>(f, lp.gamma, pw, dpw);
-    loss = (lp.alpha * pw) * nl;
-    if (GRAD) {
-        const float g = lp.alpha * (dpw * df * nl - pw / p) * scale;
-        grad = (p == p_raw) ? g : 0.0f;
-    }
-}
-
-struct ImageScales {
-    float s_bg;     // dL/dbg_j / max(npos,1)
-    float s_fg;
-    float s_reg;    // dL/dreg_j / (4 npos)
-    float s_enh;
-    float n;        // max(npos, 1)
-    int npos;
-};
-
-struct Acc {
-    float bg, fg, reg, enh;
-    float raw[4];     // hot path: sum of p^2 * (-ln(1-p)) without alpha, four independent chains
-};
-
-// One element of the classification map.  `c` is the class column, `m` the anchor's assignment word.
-template <bool GAMMA2, bool VARIANTS, bool GRAD>
-__device__ __forceinline__ float cls_element(float p_raw, int c, uint32_t m, const LossArgs& a, const ImageScales& sc,
-                                             float iou_max, Acc& acc) {
-    const uint32_t st = meta_state(m);
-    float loss = 0.0f, grad = 0.0f;
-    if (st == CLDET_STATE_IGNORE) return 0.0f;
-    if (st == CLDET_STATE_EMPTY) {                       // losses.py:292-303: (1 - alpha), not normalised (n == 1)
-        neg_element<GAMMA2, GRAD>(p_raw, 1.0f - a.p.alpha, a.p.gamma, sc.s_bg, loss, grad);
-        acc.bg += loss;
-        return grad;
-    }
-    if (st == CLDET_STATE_POS) {
-        if ((uint32_t)c == meta_label(m)) {
-            pos_element<GAMMA2, GRAD>(p_raw, a.p, iou_max, sc.s_fg, loss, grad);
-            acc.fg += loss;
-            return grad;
-        }
-        neg_element<GAMMA2, GRAD>(p_raw, a.p.alpha, a.p.gamma, sc.s_bg, loss, grad);
-        acc.bg += loss;
-        return grad;
-    }
-    // background anchor
-    if (VARIANTS) {
-        const int past = a.p.past_class_num;
-        const bool old_col = c < past;
-        bool counted = true;
-        if (a.p.incremental && a.p.ignore_past_class && old_col)          // losses.py:319-327
-            counted = a.p.new_ignore_past_class && (m & CLDET_META_OLD_ACTIVE);
-        if (counted) {
-            neg_element<GAMMA2, GRAD>(p_raw, a.p.alpha, a.p.gamma, sc.s_bg, loss, grad);
-            acc.bg += loss;
-        }
-        if (a.p.incremental && a.p.enhance_on_new && !old_col) {          // losses.py:380-384
-            const float p = fminf(fmaxf(p_raw, 1e-4f), 0.9999f);
-            if (p > 0.05f) {
-                acc.enh += p * p;
-                if (GRAD && p == p_raw) grad += 2.0f * p * sc.s_enh;
-            }
-        }
-        return grad;
-    }
-    neg_element<GAMMA2, GRAD>(p_raw, a.p.alpha, a.p.gamma, sc.s_bg, loss, grad);
-    acc.bg += loss;
-    return grad;
-}
-
-__device__ __forceinline__ uint32_t fast_div(uint32_t x, uint32_t c, uint32_t magic) {
-    return magic ? __umulhi(x, magic) : x / c;
-}
-
-// Smooth-L1 on one positive anchor (losses.py:276-280, 398-437).  Returns the 4 losses summed; writes d/dreg.
-template <bool GRAD>
-__device__ __forceinline__ float reg_anchor(const LossArgs& a, int j, int64_t anchor, uint32_t m, float s_reg, float4& g) {
-    const float4 an = a.anchors[anchor];
-    const float* gt = a.ann + ((int64_t)j * a.G + meta_row(m)) * 5;
-    const float4 r = *reinterpret_cast<const float4*>(a.reg + ((int64_t)j * a.A + anchor) * 4);
-    // anchor geometry, reference op order, no contraction
-    const float aw = __fsub_rn(an.z, an.x);
-    const float ah = __fsub_rn(an.w, an.y);
-    const float acx = __fadd_rn(an.x, __fmul_rn(0.5f, aw));
-    const float acy = __fadd_rn(an.y, __fmul_rn(0.5f, ah));
-    float gw = __fsub_rn(gt[2], gt[0]);
-    float gh = __fsub_rn(gt[3], gt[1]);
-    const float gcx = __fadd_rn(gt[0], __fmul_rn(0.5f, gw));   // centre from the UN-clamped size (quirk Q4)
-    const float gcy = __fadd_rn(gt[1], __fmul_rn(0.5f, gh));
-    gw = fmaxf(gw, 1.0f);
-    gh = fmaxf(gh, 1.0f);
-    float t[4];
-    t[0] = __fdiv_rn(__fdiv_rn(__fsub_rn(gcx, acx), aw), 0.1f);
-    t[1] = __fdiv_rn(__fdiv_rn(__fsub_rn(gcy, acy), ah), 0.1f);
-    t[2] = __fdiv_rn(logf(__fdiv_rn(gw, aw)), 0.2f);
-    t[3] = __fdiv_rn(logf(__fdiv_rn(gh, ah)), 0.2f);
-    const float rr[4] = {r.x, r.y, r.z, r.w};
-    float gg[4];
-    float sum = 0.0f;
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const float e = __fsub_rn(t[i], rr[i]);
-        const float d = fabsf(e);
-        const bool small = d <= (1.0f / 9.0f);
-        sum += small ? 4.5f * (d * d) : d - (0.5f / 9.0f);
-        if (GRAD) {
-            const float mag = small ? 9.0f * d : 1.0f;
-            const float sgn = (e > 0.0f) ? -1.0f : ((e < 0.0f) ? 1.0f : 0.0f);   // d|e|/dr = -sign(e)
-            gg[i] = sgn * mag * s_reg;
-        }
-    }
-    if (GRAD) g = make_float4(gg[0], gg[1], gg[2], gg[3]);
-    return sum;
-}
-
-// weights are stored [4][N]: row 0 dL/dbg_j, 1 dL/dfg_j, 2 dL/dreg_j, 3 dL/d(enhance term)
-__device__ __forceinline__ ImageScales image_scales(const float* w, int N, int j, int npos) {
-    ImageScales sc;
-    sc.npos = npos;
-    sc.n = fmaxf((float)npos, 1.0f);
-    if (w) {
-        sc.s_bg = w[j] / sc.n;
-        sc.s_fg = w[N + j] / sc.n;
-        sc.s_reg = npos > 0 ? w[2 * N + j] / (4.0f * (float)npos) : 0.0f;
-        sc.s_enh = w[3 * N + j];
-    } else {
-        sc.s_bg = sc.s_fg = sc.s_reg = sc.s_enh = 0.0f;
-    }
-    return sc;
-}
-
-// VEC consecutive classes of one anchor.  VEC = 8 uses the 256-bit global load/store of sm_100 (LDG.E.256 / STG.E.256):
-// one instruction moves 32 B per thread, 1 KB per warp.
-template <int VEC>
-struct VecT {
-    float v[VEC];
-};
-
-template <int VEC>
-__device__ __forceinline__ VecT<VEC> ld_stream_vec(const float* p);
-template <>
-__device__ __forceinline__ VecT<4> ld_stream_vec<4>(const float* p) {
-    VecT<4> r;
-    asm volatile("ld.global.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
-                 : "=f"(r.v[0]), "=f"(r.v[1]), "=f"(r.v[2]), "=f"(r.v[3])
-                 : "l"(p));
-    return r;
-}
-template <>
-__device__ __forceinline__ VecT<8> ld_stream_vec<8>(const float* p) {
-    VecT<8> r;
-    asm volatile("ld.global.L1::no_allocate.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-                 : "=f"(r.v[0]), "=f"(r.v[1]), "=f"(r.v[2]), "=f"(r.v[3]), "=f"(r.v[4]), "=f"(r.v[5]), "=f"(r.v[6]), "=f"(r.v[7])
-                 : "l"(p));
-    return r;
-}
-template <int VEC>
-__device__ __forceinline__ void st_stream_vec(float* p, const VecT<VEC>& x);
-template <>
-__device__ __forceinline__ void st_stream_vec<4>(float* p, const VecT<4>& x) {
-    asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(x.v[0]), "f"(x.v[1]), "f"(x.v[2]),
-                 "f"(x.v[3])
-                 : "memory");
-}
-template <>
-__device__ __forceinline__ void st_stream_vec<8>(float* p, const VecT<8>& x) {
-    asm volatile("st.global.L1::no_allocate.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "f"(x.v[0]), "f"(x.v[1]),
-                 "f"(x.v[2]), "f"(x.v[3]), "f"(x.v[4]), "f"(x.v[5]), "f"(x.v[6]), "f"(x.v[7])
-                 : "memory");
-}
-
-constexpr int kMaxAnchorsPerBlock = 4096;     // assignment words of one chunk staged in shared memory (16 KB)
-
-// One vector (VEC consecutive classes of one anchor; C % VEC == 0 so it never straddles anchors).
-template <int VEC, bool GAMMA2, bool VARIANTS, bool GRAD>
-__device__ __forceinline__ VecT<VEC> cls_vec(const VecT<VEC>& x, uint32_t m, uint32_t col, int64_t anchor_abs, const LossArgs& a,
-                                             const ImageScales& sc, float as_bg, bool need_iou, Acc& acc) {
-    const uint32_t st = meta_state(m);
-    VecT<VEC> g;
-#pragma unroll
-    for (int e = 0; e < VEC; ++e) g.v[e] = 0.0f;
-    // does the vector hold the target-1 element of a positive anchor?
-    const bool special = (st == CLDET_STATE_POS) && (meta_label(m) - col < (uint32_t)VEC);
-    if (GAMMA2 && !VARIANTS && !special) {
-        if (st != CLDET_STATE_IGNORE) {      // bg anchor, empty image, or the target-0 part of a positive row
-#pragma unroll
-            for (int e = 0; e < VEC; ++e) g.v[e] = neg_element_raw<GRAD>(x.v[e], as_bg, acc.raw[e & 3]);
-        }
-    } else {
-        float iou = 1.0f;
-        if (need_iou && st == CLDET_STATE_POS) iou = a.iou_max[anchor_abs];
-#pragma unroll
-        for (int e = 0; e < VEC; ++e) g.v[e] = cls_element<GAMMA2, VARIANTS, GRAD>(x.v[e], (int)col + e, m, a, sc, iou, acc);
-    }
-    return g;
-}
-
-// mode 0: everything (regression + classification, losses + grads)
-// mode 1: gradients only, classification + regression   (reweight: bg weight changed)
-// mode 2: gradients only, positive anchors only          (reweight: only fg / reg weight changed)
-template <int VEC, bool GAMMA2, bool VARIANTS, bool GRAD>
-__device__ __forceinline__ void process_chunk(const LossArgs& a, int j, int64_t a0, int64_t a1, const ImageScales& sc,
-                                              int mode, Acc& acc, uint32_t* smeta) {
-    const int tid = threadIdx.x;
-    const uint32_t* meta_j = a.meta + (int64_t)j * a.A;
-    const bool need_iou = VARIANTS && a.p.incremental && a.p.decrease_positive_by_iou;
-
-    // ---- regression rows + bg mask: one thread per anchor; the assignment words are staged for the sweep below ----
-    for (int64_t an = a0 + tid; an < a1; an += kLossThreads) {
-        const uint32_t m = meta_j[an];
-        smeta[an - a0] = m;
-        const uint32_t st = meta_state(m);
-        if (mode == 0 && a.bg_mask) a.bg_mask[(int64_t)j * a.A + an] = (st != CLDET_STATE_POS) ? 1 : 0;
-        float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (st == CLDET_STATE_POS) {
-            acc.reg += reg_anchor<GRAD>(a, j, an, m, sc.s_reg, g);
-            if (mode == 0 && a.status && meta_label(m) == CLDET_BAD_LABEL) *a.status = 1;
-            if (mode == 2 && GRAD) {
-                // only the target-1 element of this row depends on the fg weight
-                const uint32_t c = meta_label(m);
-                if (c < (uint32_t)a.C) {
-                    const int64_t idx = ((int64_t)j * a.A + an) * a.C + c;
-                    float l, gr;
-                    pos_element<GAMMA2, true>(a.cls[idx], a.p, need_iou ? a.iou_max[(int64_t)j * a.A + an] : 1.0f, sc.s_fg, l, gr);
-                    a.gcls[idx] = gr;
-                }
-            }
-        }
-        if (GRAD && (mode != 2 || st == CLDET_STATE_POS))
-            *reinterpret_cast<float4*>(a.greg + ((int64_t)j * a.A + an) * 4) = g;
-    }
-    if (mode == 2) return;
-    __syncthreads();
-
-    // ---- classification map: flat vectorised sweep over this chunk's (a1-a0)*C elements ----
-    const int64_t base = ((int64_t)j * a.A + a0) * a.C;
-    const uint32_t count = (uint32_t)((a1 - a0) * a.C);
-    const uint32_t C = (uint32_t)a.C;
-    const int64_t abs0 = (int64_t)j * a.A + a0;
-    // an image without GT has every anchor in state EMPTY: alpha becomes (1 - alpha) for the whole image (losses.py:293-296)
-    const float alpha_img = (meta_state(smeta[0]) == CLDET_STATE_EMPTY) ? 1.0f - a.p.alpha : a.p.alpha;
-    const float as_bg = alpha_img * sc.s_bg;
-    if constexpr (VEC >= 4) {
-        constexpr int kUnroll = unroll_for(VEC);
-        constexpr uint32_t kTile = tile_for(VEC);
-        const float* src = a.cls + base;
-        float* dst = GRAD ? a.gcls + base : nullptr;
-        const uint32_t nvec = count / VEC;
-        // (row, col) of this thread's vector advance by a constant per step of kLossThreads vectors: no division in the loop
-        const uint32_t step_elems = kLossThreads * (uint32_t)VEC;
-        const uint32_t drow = step_elems / C, dcol = step_elems - drow * C;
-        uint32_t row = (uint32_t)(VEC * tid) / C;
-        uint32_t col = (uint32_t)(VEC * tid) - row * C;
-        uint32_t v0 = tid;
-        const uint32_t full_end = nvec - nvec % kTile;     // vectors covered by complete tiles (no bounds checks)
-        for (; v0 < full_end; v0 += kTile) {
-            VecT<VEC> x[kUnroll];
-            uint32_t mm[kUnroll], cc[kUnroll], rr[kUnroll];
-#pragma unroll
-            for (int u = 0; u < kUnroll; ++u) {
-                rr[u] = row;
-                cc[u] = col;
-                mm[u] = smeta[row];
-                col += dcol;
-                row += drow;
-                if (col >= C) {
-                    col -= C;
-                    row += 1;
-                }
-                // ignored anchors contribute nothing: do not even read their probabilities
-                if (meta_state(mm[u]) != CLDET_STATE_IGNORE) {
-                    x[u] = ld_stream_vec<VEC>(src + (size_t)(v0 + u * kLossThreads) * VEC);
-                } else {
-#pragma unroll
-                    for (int e = 0; e < VEC; ++e) x[u].v[e] = 0.0f;
-                }
-            }
-#pragma unroll
-            for (int u = 0; u < kUnroll; ++u) {
-                const VecT<VEC> g = cls_vec<VEC, GAMMA2, VARIANTS, GRAD>(x[u], mm[u], cc[u], abs0 + rr[u], a, sc, as_bg, need_iou, acc);
-                if (GRAD) st_stream_vec<VEC>(dst + (size_t)(v0 + u * kLossThreads) * VEC, g);
-            }
-        }
-        for (; v0 < nvec; v0 += kLossThreads) {              // ragged tail of the chunk
-            const uint32_t m = smeta[row];
-            VecT<VEC> x;
-#pragma unroll
-            for (int e = 0; e < VEC; ++e) x.v[e] = 0.0f;
-            if (meta_state(m) != CLDET_STATE_IGNORE) x = ld_stream_vec<VEC>(src + (size_t)v0 * VEC);
-            const VecT<VEC> g = cls_vec<VEC, GAMMA2, VARIANTS, GRAD>(x, m, col, abs0 + row, a, sc, as_bg, need_iou, acc);
-            if (GRAD) st_stream_vec<VEC>(dst + (size_t)v0 * VEC, g);
-            col += dcol;
-            row += drow;
-            if (col >= C) {
-                col -= C;
-                row += 1;
-            }
-        }
-    } else {
-        const float* src = a.cls + base;
-        float* dst = GRAD ? a.gcls + base : nullptr;
-        for (uint32_t e = tid; e < count; e += kLossThreads) {
-            const uint32_t row = fast_div(e, C, a.div_magic);
-            const uint32_t col = e - row * C;
-            const uint32_t m = smeta[row];
-            float iou = 1.0f;
-            if (need_iou && meta_state(m) == CLDET_STATE_POS) iou = a.iou_max[abs0 + row];
-            const float g = cls_element<GAMMA2, VARIANTS, GRAD>(src[e], (int)col, m, a, sc, iou, acc);
-            if (GRAD) dst[e] = g;
-        }
-    }
-}
-
-template <int VEC, bool GAMMA2, bool VARIANTS, bool GRAD>
-__global__ void __launch_bounds__(kLossThreads, minblocks_for(VEC)) focal_loss_kernel(const LossArgs a) {
-    __shared__ float red[4][kLossThreads / 32];
-    __shared__ double fin[4][kLossThreads / 32];
-    __shared__ bool is_last;
-    __shared__ uint32_t smeta[kMaxAnchorsPerBlock];
-
-    const int j = blockIdx.y;
-    const int64_t a0 = (int64_t)blockIdx.x * a.anchors_per_block;
-    const int64_t a1 = min(a.A, a0 + a.anchors_per_block);
-    const int npos = a.npos[j];
-    const ImageScales sc = image_scales(a.weights, a.N, j, npos);
-
-    Acc acc = {0.f, 0.f, 0.f, 0.f, {0.f, 0.f, 0.f, 0.f}};
-    process_chunk<VEC, GAMMA2, VARIANTS, GRAD>(a, j, a0, a1, sc, 0, acc, smeta);
-    {
-        const float alpha_img = (meta_state(a.meta[(int64_t)j * a.A]) == CLDET_STATE_EMPTY) ? 1.0f - a.p.alpha : a.p.alpha;
-        acc.bg += alpha_img * ((acc.raw[0] + acc.raw[1]) + (acc.raw[2] + acc.raw[3]));
-    }
-
-    // block reduction of the four sums
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    float v[4] = {warp_sum(acc.bg), warp_sum(acc.fg), warp_sum(acc.reg), warp_sum(acc.enh)};
-    if (lane == 0) {
-#pragma unroll
-        for (int k = 0; k < 4; ++k) red[k][warp] = v[k];
-    }
-    __syncthreads();
-    if (threadIdx.x < 4) {
-        float s = 0.f;
-#pragma unroll
-        for (int w = 0; w < kLossThreads / 32; ++w) s += red[threadIdx.x][w];
-        a.partials[((int64_t)j * a.bpi + blockIdx.x) * 4 + threadIdx.x] = s;
-        __threadfence();
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        const unsigned int done = atomicAdd(&a.counters[j], 1u);
-        is_last = (done == (unsigned int)a.bpi - 1u);
-    }
-    __syncthreads();
-    if (!is_last) return;
-
-    // last block of image j: fixed-order fp64 sum of the per-block partials
-    __threadfence();
-    double s[4] = {0.0, 0.0, 0.0, 0.0};
-    const volatile float* part = a.partials + (int64_t)j * a.bpi * 4;
-    for (int b = threadIdx.x; b < a.bpi; b += kLossThreads) {
-#pragma unroll
-        for (int k = 0; k < 4; ++k) s[k] += (double)part[b * 4 + k];
-    }
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) s[k] += __shfl_xor_sync(0xffffffffu, s[k], o);
-        if (lane == 0) fin[k][warp] = s[k];
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        double t[4] = {0.0, 0.0, 0.0, 0.0};
-        for (int w = 0; w < kLossThreads / 32; ++w) {
-#pragma unroll
-            for (int k = 0; k < 4; ++k) t[k] += fin[k][w];
-        }
-        float* out = a.losses + j;                                     // [4][N]
-        out[0] = (float)t[0] / sc.n;                                  // losses.py:395
-        out[a.N] = (float)t[1] / sc.n;                                // :396
-        out[2 * a.N] = npos > 0 ? (float)(t[2] / (4.0 * (double)npos)) : 0.0f;   // :437 mean over npos*4
-        out[3 * a.N] = (float)t[3];
-        a.counters[j] = 0;                                            // leave the workspace zeroed for the next call
-        if (a.npos_out) a.npos_out[j] = npos;
-        if (a.npos_reset) a.npos_reset[j] = 0;
-    }
-}
-
-// Backward with weights that differ from the ones baked in by the forward pass (see cldet.h).
-template <int VEC, bool GAMMA2, bool VARIANTS>
-__global__ void __launch_bounds__(kLossThreads) focal_reweight_kernel(const LossArgs a) {
-    __shared__ uint32_t smeta[kMaxAnchorsPerBlock];
-    const int j = blockIdx.y;
-    const float* wn = a.weights + j;
-    const float* wo = a.baked_weights + j;
-    const int N = a.N;
-    // the enhance term only exists in incremental states with enhance_on_new (losses.py:380-384)
-    const bool enh_on = a.p.incremental && a.p.enhance_on_new;
-    const bool bg_changed = (wn[0] != wo[0]) || (enh_on && wn[3 * N] != wo[3 * N]);
-    const bool pos_changed = (wn[N] != wo[N]) || (wn[2 * N] != wo[2 * N]);
-    if (!bg_changed && !pos_changed) return;
-    const int64_t a0 = (int64_t)blockIdx.x * a.anchors_per_block;
-    const int64_t a1 = min(a.A, a0 + a.anchors_per_block);
-    const ImageScales sc = image_scales(a.weights, a.N, j, a.npos[j]);
-    Acc acc = {0.f, 0.f, 0.f, 0.f, {0.f, 0.f, 0.f, 0.f}};
-    process_chunk<VEC, GAMMA2, VARIANTS, true>(a, j, a0, a1, sc, bg_changed ? 1 : 2, acc, smeta);
-    // the last block of the image records the weights now baked into the gradient buffers; every other block of the
-    // image has finished (and so has read the old record) by then
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        __threadfence();
-        const unsigned int done = atomicAdd(&a.rw_counters[j], 1u);
-        if (done == (unsigned int)a.bpi - 1u) {
-            float* wb = const_cast<float*>(a.baked_weights) + j;
-#pragma unroll
-            for (int k = 0; k < 4; ++k) wb[k * N] = wn[k * N];
-            a.rw_counters[j] = 0;
-        }
-    }
-}
+template void run_loss_kernels<false>(const LossArgs&, int, bool, bool, bool, dim3, cudaStream_t);
+template void run_reweight_kernels<false>(const LossArgs&, int, bool, bool, dim3, cudaStream_t);
 
 // new_ignore_past_class pre-pass (losses.py:326-327): flag background anchors whose clamped old-class
 // probabilities sum to < 0.5.  fp32 sequential sum in column order.
 __global__ void __launch_bounds__(256) old_class_flag_kernel(const float* __restrict__ cls, int64_t A, int C, int past,
-                                                             uint32_t* __restrict__ meta) {
+                                                             int is_logits, uint32_t* __restrict__ meta) {
     const int j = blockIdx.y;
     const int64_t an = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (an >= A) return;
@@ -597,7 +18,7 @@ __global__ void __launch_bounds__(256) old_class_flag_kernel(const float* __rest
     if (meta_state(m) == CLDET_STATE_BG) {
         const float* row = cls + ((int64_t)j * A + an) * C;
         float s = 0.0f;
-        for (int c = 0; c < past; ++c) s = __fadd_rn(s, fminf(fmaxf(row[c], 1e-4f), 0.9999f));
+        for (int c = 0; c < past; ++c) s = __fadd_rn(s, fminf(fmaxf(is_logits ? sigmoid_exact(row[c]) : row[c], 1e-4f), 0.9999f));
         if (s < 0.5f) m |= CLDET_META_OLD_ACTIVE;
     }
     meta[(int64_t)j * A + an] = m;
@@ -649,34 +70,6 @@ static size_t workspace_bytes(int N, int64_t A) {
     // worst case bpi: 32 anchors per block
     const int64_t max_bpi = (A + 31) / 32;
     return workspace_header_bytes(N) + (size_t)N * max_bpi * 4 * sizeof(float) + 256;
-}
-
-template <int VEC, bool GAMMA2, bool VARIANTS>
-static void launch_loss(const LossArgs& a, bool grad, dim3 grid, cudaStream_t s) {
-    if (grad) focal_loss_kernel<VEC, GAMMA2, VARIANTS, true><<<grid, kLossThreads, 0, s>>>(a);
-    else focal_loss_kernel<VEC, GAMMA2, VARIANTS, false><<<grid, kLossThreads, 0, s>>>(a);
-}
-
-template <int VEC>
-static void dispatch_loss(const LossArgs& a, bool grad, bool gamma2, bool variants, dim3 grid, cudaStream_t s) {
-    if (gamma2) {
-        if (variants) launch_loss<VEC, true, true>(a, grad, grid, s);
-        else launch_loss<VEC, true, false>(a, grad, grid, s);
-    } else {
-        if (variants) launch_loss<VEC, false, true>(a, grad, grid, s);
-        else launch_loss<VEC, false, false>(a, grad, grid, s);
-    }
-}
-
-template <int VEC>
-static void dispatch_reweight(const LossArgs& a, bool gamma2, bool variants, dim3 grid, cudaStream_t s) {
-    if (gamma2) {
-        if (variants) focal_reweight_kernel<VEC, true, true><<<grid, kLossThreads, 0, s>>>(a);
-        else focal_reweight_kernel<VEC, true, false><<<grid, kLossThreads, 0, s>>>(a);
-    } else {
-        if (variants) focal_reweight_kernel<VEC, false, true><<<grid, kLossThreads, 0, s>>>(a);
-        else focal_reweight_kernel<VEC, false, false><<<grid, kLossThreads, 0, s>>>(a);
-    }
 }
 
 // widest vector the class map allows: rows must be a whole number of vectors and the buffers aligned to the vector
@@ -754,14 +147,13 @@ static int loss_stage(const float* d_cls, const float* d_reg, const float* d_anc
     const bool variants = has_variants(*params);
     if (params->incremental && params->ignore_past_class && params->new_ignore_past_class && params->past_class_num > 0) {
         dim3 g((unsigned)((num_anchors + 255) / 256), (unsigned)num_images);
-        old_class_flag_kernel<<<g, 256, 0, s>>>(d_cls, num_anchors, num_classes, params->past_class_num, d_meta);
+        old_class_flag_kernel<<<g, 256, 0, s>>>(d_cls, num_anchors, num_classes, params->past_class_num, params->cls_is_logits, d_meta);
         CLDET_LAUNCH_CHECK();
     }
     dim3 grid((unsigned)pl.bpi, (unsigned)num_images);
     const bool gamma2 = params->gamma == 2.0f;
-    if (vec == 8) dispatch_loss<8>(a, grad, gamma2, variants, grid, s);
-    else if (vec == 4) dispatch_loss<4>(a, grad, gamma2, variants, grid, s);
-    else dispatch_loss<1>(a, grad, gamma2, variants, grid, s);
+    if (params->cls_is_logits) run_loss_kernels<true>(a, vec, grad, gamma2, variants, grid, s);
+    else run_loss_kernels<false>(a, vec, grad, gamma2, variants, grid, s);
     CLDET_LAUNCH_CHECK();
     return CLDET_OK;
 }
@@ -834,9 +226,8 @@ int cldet_focal_loss_reweight(const float* d_cls, const float* d_reg, const floa
     dim3 grid((unsigned)pl.bpi, (unsigned)num_images);
     const bool gamma2 = params->gamma == 2.0f;
     const bool variants = has_variants(*params);
-    if (vec == 8) dispatch_reweight<8>(a, gamma2, variants, grid, s);
-    else if (vec == 4) dispatch_reweight<4>(a, gamma2, variants, grid, s);
-    else dispatch_reweight<1>(a, gamma2, variants, grid, s);
+    if (params->cls_is_logits) run_reweight_kernels<true>(a, vec, gamma2, variants, grid, s);
+    else run_reweight_kernels<false>(a, vec, gamma2, variants, grid, s);
     CLDET_LAUNCH_CHECK();
     return CLDET_OK;
 }

@@ -1,0 +1,10 @@
+// Logits-in instantiation of the fused loss kernels: the kernel applies ATen's sigmoid itself and
+// returns dL/dlogits.  Separate translation unit so the two halves of the template space compile in parallel.
+#include "cldet_loss_kernels.cuh"
+
+namespace cldet {
+
+template void run_loss_kernels<true>(const LossArgs&, int, bool, bool, bool, dim3, cudaStream_t);
+template void run_reweight_kernels<true>(const LossArgs&, int, bool, bool, dim3, cudaStream_t);
+
+}  // namespace cldet

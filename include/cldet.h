@@ -90,6 +90,10 @@ typedef struct cldet_loss_params {
     int32_t decrease_positive_by_iou;  /* :353-362 */
     int32_t enhance_on_new;            /* :380-384 */
     float decrease_positive;           /* :364-366, default 1.0 */
+    int32_t cls_is_logits;             /* 0: d_cls holds probabilities (the reference's FocalLoss input).
+                                          1: d_cls holds LOGITS -- the kernel applies ATen's sigmoid 1/(1+exp(-x)) itself and
+                                          writes dL/dlogits = dL/dp * (1-p) * p (replaces the separate
+                                          Sigmoid at losses.py:566/633 and its backward; d_grad_cls may alias d_cls) */
 } cldet_loss_params;
 
 /* Bytes of scratch cldet_focal_loss needs for (N, A).  The first 3*N uint32 of a workspace must be ZERO before its first

@@ -158,7 +158,7 @@ def _dpow(x, gamma):
 
 
 def focal_loss(classifications, regressions, anchors, annotations, cur_state, params, progress=-1,
-               w_bg=None, w_fg=None, w_reg=1.0, w_enh=1.0, want_grads=True):
+               w_bg=None, w_fg=None, w_reg=1.0, w_enh=1.0, want_grads=True, from_logits=False):
     """Restatement of FocalLoss.forward (losses.py:252-452) plus its autograd backward.
 
     Inputs as the reference: classifications [N,A,C] fp32 PROBABILITIES, regressions [N,A,4],
@@ -173,6 +173,15 @@ def focal_loss(classifications, regressions, anchors, annotations, cur_state, pa
     grad_cls[N,A,C], grad_reg[N,A,4], and per-image assignment dicts under 'assign'.
     """
     cls = np.asarray(classifications, dtype=F32)
+    if from_logits:
+        # caller pattern of IL_Loss: focal_loss(self.classifier_act(classification), ...) with classifier_act = Sigmoid
+        # (losses.py:566, 633-647); grad_cls is then dL/dlogits = dL/dp * (1 - p) * p (SigmoidBackward)
+        out = focal_loss(sigmoid(cls), regressions, anchors, annotations, cur_state, params, progress, w_bg, w_fg, w_reg,
+                         w_enh, want_grads, from_logits=False)
+        if want_grads:
+            p = sigmoid(cls)
+            out['grad_cls'] = (out['grad_cls'] * (F32(1.0) - p)) * p
+        return out
     reg = np.asarray(regressions, dtype=F32)
     anc = np.asarray(anchors, dtype=F32)[0]
     ann = np.asarray(annotations, dtype=F32)
