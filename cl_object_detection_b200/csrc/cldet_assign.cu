@@ -94,14 +94,16 @@ constexpr int kGtTile = 256;
 constexpr int kAssignThreads = 256;
 constexpr int kAnchorsPerThread = 4;
 
-__global__ void __launch_bounds__(kAssignThreads)
+__global__ void __launch_bounds__(kAssignThreads, 5)
 iou_assign_kernel(const float4* __restrict__ anchors, int64_t A, const float* __restrict__ annotations, int G,
                   int num_classes, uint32_t* __restrict__ meta, int32_t* __restrict__ argmax_out,
                   float* __restrict__ iou_max_out, int32_t* __restrict__ npos, int32_t* __restrict__ nvalid) {
     // valid rows of the current tile, compacted in order: box, area, (label, raw row)
     __shared__ float4 s_box[kGtTile];
     __shared__ float s_area[kGtTile];
-    __shared__ int2 s_lab_row[kGtTile];
+    __shared__ int s_idx[kGtTile];        // compacted GT index of each staged (live) row
+    __shared__ float4 s_bbox[kAssignThreads / 32];
+    __shared__ int s_tile_live;
     __shared__ int s_warp[kAssignThreads / 32];
     __shared__ int s_tile_valid;
     __shared__ int2 s_first[kGtTile];     // (label, raw row) of the image's first kGtTile valid rows
@@ -113,6 +115,15 @@ iou_assign_kernel(const float4* __restrict__ anchors, int64_t A, const float* __
 
     // kAnchorsPerThread anchors per thread (strided by the block size: coalesced), so one broadcast read of a GT row
     // feeds several independent IoU chains and the per-block tile set-up is amortised.
+    // first GT tile: issue this thread's row load before anything depends on the anchors (both latencies overlap)
+    float4 pre_b = make_float4(0.f, 0.f, 0.f, 0.f);
+    float pre_lab = -1.0f;
+    if (threadIdx.x < min(kGtTile, G)) {
+        const float* r = ann + (int64_t)threadIdx.x * 5;
+        pre_b = make_float4(r[0], r[1], r[2], r[3]);
+        pre_lab = r[4];
+    }
+
     float4 box[kAnchorsPerThread];
     float area_a[kAnchorsPerThread];
     float best[kAnchorsPerThread];
@@ -129,38 +140,90 @@ iou_assign_kernel(const float4* __restrict__ anchors, int64_t A, const float* __
     }
     int k = 0;            // valid rows seen so far (block-uniform) = compacted index of the next valid row
 
+    // Bounding box of this block's anchors: a GT row that does not overlap it has IoU 0 with every anchor here and can
+    // never beat the default winner, so it is culled for the WHOLE block when the tile is staged (it still counts in k).
+    {
+        float x1 = INFINITY, y1 = INFINITY, x2 = -INFINITY, y2 = -INFINITY;
+#pragma unroll
+        for (int u = 0; u < kAnchorsPerThread; ++u) {
+            if (a_base + u * kAssignThreads < A) {
+                x1 = fminf(x1, box[u].x);
+                y1 = fminf(y1, box[u].y);
+                x2 = fmaxf(x2, box[u].z);
+                y2 = fmaxf(y2, box[u].w);
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            x1 = fminf(x1, __shfl_xor_sync(0xffffffffu, x1, o));
+            y1 = fminf(y1, __shfl_xor_sync(0xffffffffu, y1, o));
+            x2 = fmaxf(x2, __shfl_xor_sync(0xffffffffu, x2, o));
+            y2 = fmaxf(y2, __shfl_xor_sync(0xffffffffu, y2, o));
+        }
+        if (lane == 0) s_bbox[warp] = make_float4(x1, y1, x2, y2);
+    }
+    __syncthreads();
+    float4 bb = s_bbox[0];
+#pragma unroll
+    for (int w = 1; w < kAssignThreads / 32; ++w) {
+        const float4 o = s_bbox[w];
+        bb.x = fminf(bb.x, o.x);
+        bb.y = fminf(bb.y, o.y);
+        bb.z = fmaxf(bb.z, o.z);
+        bb.w = fmaxf(bb.w, o.w);
+    }
+
     for (int g0 = 0; g0 < G; g0 += kGtTile) {
         const int n = min(kGtTile, G - g0);
         __syncthreads();
         // ordered compaction of this tile's valid rows (label != -1, losses.py:288); tile size == block size
-        float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
-        float lab = -1.0f;
-        if (threadIdx.x < n) {
-            const float* r = ann + (int64_t)(g0 + threadIdx.x) * 5;
-            b = make_float4(r[0], r[1], r[2], r[3]);
-            lab = r[4];
+        float4 b = pre_b;
+        float lab = pre_lab;
+        if (g0 > 0) {
+            b = make_float4(0.f, 0.f, 0.f, 0.f);
+            lab = -1.0f;
+            if (threadIdx.x < n) {
+                const float* r = ann + (int64_t)(g0 + threadIdx.x) * 5;
+                b = make_float4(r[0], r[1], r[2], r[3]);
+                lab = r[4];
+            }
         }
         const bool valid = (threadIdx.x < n) && (lab != -1.0f);
+        // live = valid and with a non-empty intersection with the block's bounding box (same strict tests as the IoU)
+        const bool live = valid && (fminf(bb.z, b.z) - fmaxf(bb.x, b.x) > 0.0f) && (fminf(bb.w, b.w) - fmaxf(bb.y, b.y) > 0.0f);
         const unsigned ballot = __ballot_sync(0xffffffffu, valid);
-        if (lane == 0) s_warp[warp] = __popc(ballot);
+        const unsigned ballot_live = __ballot_sync(0xffffffffu, live);
+        if (lane == 0) s_warp[warp] = __popc(ballot) | (__popc(ballot_live) << 16);
         __syncthreads();
-        int before = 0;
+        int before = 0, before_live = 0;
 #pragma unroll
-        for (int w = 0; w < kAssignThreads / 32; ++w) before += (w < warp) ? s_warp[w] : 0;
-        if (valid) {
-            const int slot = before + __popc(ballot & ((1u << lane) - 1u));
-            s_box[slot] = b;
-            s_area[slot] = (b.z - b.x) * (b.w - b.y);
-            s_lab_row[slot] = make_int2((int)(long long)lab, g0 + threadIdx.x);    // .long() truncation, losses.py:341
-            // (label, raw row) of every valid row of the IMAGE, by compacted index, for the epilogue
-            if (k + slot < kGtTile) s_first[k + slot] = s_lab_row[slot];
+        for (int w = 0; w < kAssignThreads / 32; ++w) {
+            const int v = (w < warp) ? s_warp[w] : 0;
+            before += v & 0xffff;
+            before_live += v >> 16;
         }
-        if (threadIdx.x == kAssignThreads - 1) s_tile_valid = before + __popc(ballot);
+        if (valid) {
+            const int slot = before + __popc(ballot & ((1u << lane) - 1u));       // compacted index inside this tile
+            // (label, raw row) of every valid row of the IMAGE, by compacted index, for the epilogue
+            if (k + slot < kGtTile) s_first[k + slot] = make_int2((int)(long long)lab, g0 + threadIdx.x);   // .long(), losses.py:341
+            if (live) {
+                const int ls = before_live + __popc(ballot_live & ((1u << lane) - 1u));
+                s_box[ls] = b;
+                s_area[ls] = (b.z - b.x) * (b.w - b.y);
+                s_idx[ls] = k + slot;
+            }
+        }
+        if (threadIdx.x == kAssignThreads - 1) {
+            s_tile_valid = before + __popc(ballot);
+            s_tile_live = before_live + __popc(ballot_live);
+        }
         __syncthreads();
         const int nv = s_tile_valid;
-        for (int t = 0; t < nv; ++t) {
+        const int nl = s_tile_live;
+        for (int t = 0; t < nl; ++t) {
             const float4 gb = s_box[t];                        // warp-wide broadcast
             const float ga = s_area[t];
+            const int gi = s_idx[t];
 #pragma unroll
             for (int u = 0; u < kAnchorsPerThread; ++u) {
                 // calc_iou (losses.py:4-21) with the clamps resolved by early exits: an empty intersection gives IoU
@@ -174,7 +237,7 @@ iou_assign_kernel(const float4* __restrict__ anchors, int64_t A, const float* __
                     const float v = __fdiv_rn(inter, ua);
                     if (v > best[u]) {                         // strict: first maximal index (torch.max)
                         best[u] = v;
-                        best_t[u] = k + t;
+                        best_t[u] = gi;
                     }
                 }
             }
