@@ -518,3 +518,35 @@ def filter_pseudo_labels(scores, boxes, labels, real_gt_xyxy, scale, score_thres
         ok = (iw * ih / ua).max(axis=1) < iou_thresh
         s, b, l = s[ok], b[ok], l[ok]
     return s, b, l
+
+
+# --------------------------------------------------------------------------------------
+# 8(f) row f3  other calc_iou + max users  (IL_method/mas.py:35-67, IL_method/prototype.py:24-47)
+# --------------------------------------------------------------------------------------
+def output_norm(classifications, regressions, anchors, annotations):
+    """MAS Output_norm.forward: mean over images of mean|regression[positive]| (images without positives add 0) and
+    sum(cls^2) / (N * C).  Returns (regression_term, classification_term, grad_cls, grad_reg) for unit upstream weights."""
+    cls = np.asarray(classifications, dtype=F32)
+    reg = np.asarray(regressions, dtype=F32)
+    n, a, c = cls.shape
+    rterm = 0.0
+    greg = np.zeros_like(reg)
+    for j in range(n):
+        asg = assign(np.asarray(anchors, dtype=F32)[0], annotations[j])
+        pos = asg['iou_max'] >= F32(0.5)
+        k = int(pos.sum())
+        if k > 0:
+            rterm += float(np.mean(np.abs(reg[j][pos]).astype(np.float64)))
+            greg[j][pos] = np.sign(reg[j][pos]) / F32(4 * k * n)
+    cterm = float(np.sum((cls * cls).astype(np.float64)) / (n * c))
+    return F32(rterm / n), F32(cterm), (F32(2.0) * cls / F32(n * c)), greg
+
+
+def get_positive(anchors, annotations, threshold, num_anchors):
+    """ProtoTyper._get_positive: positive mask at a custom threshold and the assigned GT class, viewed [N, cells, 9]."""
+    pos, tgt = [], []
+    for j in range(annotations.shape[0]):
+        asg = assign(np.asarray(anchors, dtype=F32)[0], annotations[j])
+        pos.append((asg['iou_max'] >= F32(threshold)).reshape(-1, num_anchors))
+        tgt.append(asg['label'].astype(np.int64).reshape(-1, num_anchors))
+    return np.stack(pos), np.stack(tgt)

@@ -382,3 +382,22 @@ def test_focal_logits_in_place_c_abi():
     a = run(False)
     b = run(True)
     assert all(torch.equal(x, y) for x, y in zip(a, b))
+
+
+def test_f3_other_iou_users_golden():
+    """MAS Output_norm and ProtoTyper._get_positive on the K2 kernel vs the reference's own outputs."""
+    g = load('f3_iou_users')
+    h, w = int(g['h']), int(g['w'])
+    anchors = cld.generate_anchors(h, w, DEV)
+    pos, tgt = cld.get_positive(anchors, cu(g['ann']), float(g['proto_threshold']), 9)
+    assert np.array_equal(pos.cpu().numpy(), g['proto_positive'])                       # bit exact
+    assert np.array_equal(tgt.cpu().numpy()[g['proto_positive']], g['proto_targets'][g['proto_positive']])
+    assert np.array_equal(tgt.cpu().numpy(), g['proto_targets'])
+    c = cu(g['cls']).requires_grad_(True)
+    r = cu(g['reg']).requires_grad_(True)
+    out = cld.OutputNorm()(c, r, anchors, cu(g['ann']))
+    (out['regression'] * 0.7 + out['classification'] * 0.3).backward()
+    check_rel(out['regression'].detach().cpu().numpy(), g['norm_regression'], 1e-6)
+    check_rel(out['classification'].detach().cpu().numpy(), g['norm_classification'], 1e-6)
+    assert np.allclose(c.grad.cpu().numpy(), g['grad_cls'], rtol=1e-6, atol=0)
+    assert np.allclose(r.grad.cpu().numpy(), g['grad_reg'], rtol=1e-6, atol=0)

@@ -122,3 +122,15 @@ def test_collate_and_merge_format():
     out = O.collate_annotations([m, np.zeros((0, 5))])
     assert out.shape == (2, 3, 5) and out.dtype == np.float32 and np.all(out[1] == -1)
     assert O.collate_annotations([np.zeros((0, 5))]).shape == (1, 1, 5)
+
+
+def test_f3_iou_users_match_reference():
+    g = load('f3_iou_users')
+    anchors = O.anchors_for_image(int(g['h']), int(g['w']))
+    r, c, gc, gr = O.output_norm(g['cls'], g['reg'], anchors, g['ann'])
+    assert abs(float(r) - float(g['norm_regression'])) <= 1e-6 * abs(float(g['norm_regression']))
+    assert abs(float(c) - float(g['norm_classification'])) <= 1e-6 * abs(float(g['norm_classification']))
+    assert np.allclose(0.3 * gc, g['grad_cls'], rtol=1e-6, atol=0)
+    assert np.allclose(0.7 * gr, g['grad_reg'], rtol=1e-6, atol=0)
+    pos, tgt = O.get_positive(anchors, g['ann'], float(g['proto_threshold']), 9)
+    assert np.array_equal(pos, g['proto_positive']) and np.array_equal(tgt, g['proto_targets'])
