@@ -256,8 +256,8 @@ def run_ours(args):
             lib.cldet_focal_loss_profile_events(ev_a[i].cuda_event, ev_b[i].cuda_event, ev_c[i].cuda_event)
         _lib.check(lib.cldet_focal_loss(
             probs.data_ptr(), reg.data_ptr(), anchors.data_ptr(), ann.data_ptr(), n, a, C, GMAX, lp, weights.data_ptr(),
-            gcls.data_ptr(), greg.data_ptr(), losses.data_ptr(), meta.data_ptr(), None, npos.data_ptr(), nvalid.data_ptr(),
-            None, None, ws.data_ptr(), ws_bytes, stream))
+            baked.data_ptr(), gcls.data_ptr(), greg.data_ptr(), losses.data_ptr(), meta.data_ptr(), None, npos.data_ptr(),
+            nvalid.data_ptr(), None, None, ws.data_ptr(), ws_bytes, stream))
         if world > 1:   # every rank gets every image's (bg, fg, reg) terms: what IL_Loss's mean / clip_loss needs
             dist.all_gather_into_tensor(gathered, losses)
         # backward: upstream weights are verified on the device; unchanged -> nothing is recomputed

@@ -42,11 +42,13 @@ SIGNATURES = {
     'cldet_iou_assign': (_I, [_P, _L, _P, _I, _I, _I, _P, _P, _P, _P, _P, _P]),
     'cldet_calc_iou': (_I, [_P, _L, _P, _I, _P, _P]),
     'cldet_focal_loss_workspace_bytes': (_Z, [_I, _L]),
-    'cldet_focal_loss': (_I, [_P, _P, _P, _P, _I, _L, _I, _I, ctypes.POINTER(LossParams), _P, _P, _P, _P, _P, _P, _P,
+    'cldet_focal_loss': (_I, [_P, _P, _P, _P, _I, _L, _I, _I, ctypes.POINTER(LossParams), _P, _P, _P, _P, _P, _P, _P, _P,
                               _P, _P, _P, _P, _Z, _P]),
     'cldet_focal_loss_profile_events': (_I, [_P, _P, _P]),
-    'cldet_focal_loss_from_assignment': (_I, [_P, _P, _P, _P, _I, _L, _I, _I, ctypes.POINTER(LossParams), _P, _P, _P,
+    'cldet_focal_loss_from_assignment': (_I, [_P, _P, _P, _P, _I, _L, _I, _I, ctypes.POINTER(LossParams), _P, _P, _P, _P,
                                               _P, _P, _P, _P, _P, _P, _P, _Z, _P]),
+    'cldet_focal_loss_reweight_rows': (_I, [_P, _P, _P, _P, _I, _L, _I, _I, ctypes.POINTER(LossParams), _P, _L, _P, _L, _P,
+                                            _L, _P, _L, _P, _P, _P, _P, _P, _P, _P, _Z, _P]),
     'cldet_focal_loss_reweight': (_I, [_P, _P, _P, _P, _I, _L, _I, _I, ctypes.POINTER(LossParams), _P, _P, _P, _P, _P,
                                        _P, _P, _P, _Z, _P]),
     'cldet_decode_boxes': (_I, [_P, _P, _I, _L, _I, _I, _I, _P, _P]),

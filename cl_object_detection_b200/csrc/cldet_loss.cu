@@ -118,8 +118,8 @@ size_t cldet_focal_loss_workspace_bytes(int num_images, int64_t num_anchors) {
 
 static int loss_stage(const float* d_cls, const float* d_reg, const float* d_anchors, const float* d_annotations,
                       int num_images, int64_t num_anchors, int num_classes, int gt_rows, const cldet_loss_params* params,
-                      const float* d_weights, float* d_grad_cls, float* d_grad_reg, float* d_losses, uint32_t* d_meta,
-                      const float* d_iou_max, const int32_t* d_npos, int32_t* d_npos_out, int32_t* d_npos_reset,
+                      const float* d_weights, float* d_baked_weights, float* d_grad_cls, float* d_grad_reg, float* d_losses,
+                      uint32_t* d_meta, const float* d_iou_max, const int32_t* d_npos, int32_t* d_npos_out, int32_t* d_npos_reset,
                       uint8_t* d_bg_mask, int32_t* d_status, void* d_workspace, size_t ws_bytes, void* stream) {
     int rc = check_common(d_cls, d_anchors, d_annotations, num_images, num_anchors, num_classes, gt_rows, params);
     if (rc) return rc;
@@ -137,7 +137,12 @@ static int loss_stage(const float* d_cls, const float* d_reg, const float* d_anc
     LossArgs a;
     a.cls = d_cls; a.reg = d_reg; a.anchors = reinterpret_cast<const float4*>(d_anchors); a.ann = d_annotations;
     a.N = num_images; a.A = num_anchors; a.C = num_classes; a.G = gt_rows; a.p = *params;
-    a.weights = d_weights; a.baked_weights = nullptr; a.gcls = d_grad_cls; a.greg = d_grad_reg; a.losses = d_losses;
+    for (int k = 0; k < 4; ++k) {
+        a.w_ptr[k] = d_weights ? d_weights + (size_t)k * num_images : nullptr;
+        a.w_stride[k] = 1;
+    }
+    a.has_w = d_weights ? 1 : 0;
+    a.baked_weights = d_baked_weights; a.gcls = d_grad_cls; a.greg = d_grad_reg; a.losses = d_losses;
     a.meta = d_meta; a.iou_max = d_iou_max; a.npos = d_npos; a.bg_mask = d_bg_mask; a.status = d_status;
     a.npos_out = d_npos_out; a.npos_reset = d_npos_reset; a.rw_counters = nullptr;
     a.counters = reinterpret_cast<unsigned int*>(d_workspace);
@@ -161,17 +166,17 @@ static int loss_stage(const float* d_cls, const float* d_reg, const float* d_anc
 int cldet_focal_loss_from_assignment(const float* d_cls, const float* d_reg, const float* d_anchors,
                                      const float* d_annotations, int num_images, int64_t num_anchors, int num_classes,
                                      int gt_rows, const cldet_loss_params* params, const float* d_weights,
-                                     float* d_grad_cls, float* d_grad_reg, float* d_losses, uint32_t* d_meta,
-                                     const float* d_iou_max, const int32_t* d_npos, uint8_t* d_bg_mask, int32_t* d_status,
-                                     void* d_workspace, size_t ws_bytes, void* stream) {
+                                     float* d_baked_weights, float* d_grad_cls, float* d_grad_reg, float* d_losses,
+                                     uint32_t* d_meta, const float* d_iou_max, const int32_t* d_npos, uint8_t* d_bg_mask,
+                                     int32_t* d_status, void* d_workspace, size_t ws_bytes, void* stream) {
     return loss_stage(d_cls, d_reg, d_anchors, d_annotations, num_images, num_anchors, num_classes, gt_rows, params, d_weights,
-                      d_grad_cls, d_grad_reg, d_losses, d_meta, d_iou_max, d_npos, nullptr, nullptr, d_bg_mask, d_status,
+                      d_baked_weights, d_grad_cls, d_grad_reg, d_losses, d_meta, d_iou_max, d_npos, nullptr, nullptr, d_bg_mask, d_status,
                       d_workspace, ws_bytes, stream);
 }
 
 int cldet_focal_loss(const float* d_cls, const float* d_reg, const float* d_anchors, const float* d_annotations,
                      int num_images, int64_t num_anchors, int num_classes, int gt_rows,
-                     const cldet_loss_params* params, const float* d_weights,
+                     const cldet_loss_params* params, const float* d_weights, float* d_baked_weights,
                      float* d_grad_cls, float* d_grad_reg, float* d_losses,
                      uint32_t* d_meta, float* d_iou_max, int32_t* d_npos, int32_t* d_nvalid,
                      uint8_t* d_bg_mask, int32_t* d_status,
@@ -193,21 +198,21 @@ int cldet_focal_loss(const float* d_cls, const float* d_reg, const float* d_anch
     if (rc) return rc;
     if (ev[1]) CLDET_CUDA_TRY(cudaEventRecord(ev[1], s));
     rc = loss_stage(d_cls, d_reg, d_anchors, d_annotations, num_images, num_anchors, num_classes, gt_rows, params, d_weights,
-                      d_grad_cls, d_grad_reg, d_losses, d_meta, d_iou_max, npos_acc, d_npos, npos_acc, d_bg_mask, d_status,
+                      d_baked_weights, d_grad_cls, d_grad_reg, d_losses, d_meta, d_iou_max, npos_acc, d_npos, npos_acc, d_bg_mask, d_status,
                       d_workspace, ws_bytes, stream);
     if (rc) return rc;
     if (ev[2]) CLDET_CUDA_TRY(cudaEventRecord(ev[2], s));
     return CLDET_OK;
 }
 
-int cldet_focal_loss_reweight(const float* d_cls, const float* d_reg, const float* d_anchors, const float* d_annotations,
-                              int num_images, int64_t num_anchors, int num_classes, int gt_rows,
-                              const cldet_loss_params* params, const float* d_new_weights, float* d_baked_weights,
-                              float* d_grad_cls, float* d_grad_reg, const uint32_t* d_meta, const float* d_iou_max,
-                              const int32_t* d_npos, void* d_workspace, size_t ws_bytes, void* stream) {
+static int reweight_impl(const float* d_cls, const float* d_reg, const float* d_anchors, const float* d_annotations,
+                         int num_images, int64_t num_anchors, int num_classes, int gt_rows, const cldet_loss_params* params,
+                         const float* const w_ptr[4], const int64_t w_stride[4], float* d_baked_weights, float* d_grad_cls,
+                         float* d_grad_reg, const uint32_t* d_meta, const float* d_iou_max, const int32_t* d_npos,
+                         void* d_workspace, size_t ws_bytes, void* stream) {
     int rc = check_common(d_cls, d_anchors, d_annotations, num_images, num_anchors, num_classes, gt_rows, params);
     if (rc) return rc;
-    if (!d_reg || !d_new_weights || !d_baked_weights || !d_grad_cls || !d_grad_reg || !d_meta || !d_npos || !d_workspace)
+    if (!d_reg || !d_baked_weights || !d_grad_cls || !d_grad_reg || !d_meta || !d_npos || !d_workspace)
         return CLDET_ERR_INVALID_ARGUMENT;
     if (ws_bytes < workspace_bytes(num_images, num_anchors)) return CLDET_ERR_WORKSPACE_TOO_SMALL;
     if (params->incremental && params->decrease_positive_by_iou && !d_iou_max) return CLDET_ERR_INVALID_ARGUMENT;
@@ -217,7 +222,12 @@ int cldet_focal_loss_reweight(const float* d_cls, const float* d_reg, const floa
     LossArgs a;
     a.cls = d_cls; a.reg = d_reg; a.anchors = reinterpret_cast<const float4*>(d_anchors); a.ann = d_annotations;
     a.N = num_images; a.A = num_anchors; a.C = num_classes; a.G = gt_rows; a.p = *params;
-    a.weights = d_new_weights; a.baked_weights = d_baked_weights; a.gcls = d_grad_cls; a.greg = d_grad_reg;
+    for (int k = 0; k < 4; ++k) {
+        a.w_ptr[k] = w_ptr[k];
+        a.w_stride[k] = (int)w_stride[k];
+    }
+    a.has_w = 1;
+    a.baked_weights = d_baked_weights; a.gcls = d_grad_cls; a.greg = d_grad_reg;
     a.losses = nullptr; a.meta = d_meta; a.iou_max = d_iou_max; a.npos = d_npos; a.bg_mask = nullptr; a.status = nullptr;
     a.npos_out = nullptr; a.npos_reset = nullptr;
     a.counters = nullptr; a.partials = nullptr;
@@ -230,6 +240,36 @@ int cldet_focal_loss_reweight(const float* d_cls, const float* d_reg, const floa
     else run_reweight_kernels<false>(a, vec, gamma2, variants, grid, s);
     CLDET_LAUNCH_CHECK();
     return CLDET_OK;
+}
+
+int cldet_focal_loss_reweight(const float* d_cls, const float* d_reg, const float* d_anchors, const float* d_annotations,
+                              int num_images, int64_t num_anchors, int num_classes, int gt_rows,
+                              const cldet_loss_params* params, const float* d_new_weights, float* d_baked_weights,
+                              float* d_grad_cls, float* d_grad_reg, const uint32_t* d_meta, const float* d_iou_max,
+                              const int32_t* d_npos, void* d_workspace, size_t ws_bytes, void* stream) {
+    if (!d_new_weights || num_images <= 0) return CLDET_ERR_INVALID_ARGUMENT;
+    const float* rows[4] = {d_new_weights, d_new_weights + num_images, d_new_weights + 2 * (size_t)num_images,
+                            d_new_weights + 3 * (size_t)num_images};
+    const int64_t strides[4] = {1, 1, 1, 1};
+    return reweight_impl(d_cls, d_reg, d_anchors, d_annotations, num_images, num_anchors, num_classes, gt_rows, params, rows,
+                         strides, d_baked_weights, d_grad_cls, d_grad_reg, d_meta, d_iou_max, d_npos, d_workspace, ws_bytes,
+                         stream);
+}
+
+int cldet_focal_loss_reweight_rows(const float* d_cls, const float* d_reg, const float* d_anchors, const float* d_annotations,
+                                   int num_images, int64_t num_anchors, int num_classes, int gt_rows,
+                                   const cldet_loss_params* params, const float* d_w_bg, int64_t stride_bg,
+                                   const float* d_w_fg, int64_t stride_fg, const float* d_w_reg, int64_t stride_reg,
+                                   const float* d_w_enh, int64_t stride_enh, float* d_baked_weights, float* d_grad_cls,
+                                   float* d_grad_reg, const uint32_t* d_meta, const float* d_iou_max, const int32_t* d_npos,
+                                   void* d_workspace, size_t ws_bytes, void* stream) {
+    const float* rows[4] = {d_w_bg, d_w_fg, d_w_reg, d_w_enh};
+    const int64_t strides[4] = {stride_bg, stride_fg, stride_reg, stride_enh};
+    for (int k = 0; k < 4; ++k)
+        if (strides[k] < 0 || strides[k] > 0x7fffffff) return CLDET_ERR_INVALID_ARGUMENT;
+    return reweight_impl(d_cls, d_reg, d_anchors, d_annotations, num_images, num_anchors, num_classes, gt_rows, params, rows,
+                         strides, d_baked_weights, d_grad_cls, d_grad_reg, d_meta, d_iou_max, d_npos, d_workspace, ws_bytes,
+                         stream);
 }
 
 }  // extern "C"

@@ -35,7 +35,7 @@ def calc_iou(a, b):
     b = _check_cuda_f32('b', b)
     if a.dim() != 2 or a.shape[1] != 4 or b.dim() != 2 or b.shape[1] != 4:
         raise ValueError('calc_iou expects [A,4] and [G,4] boxes')
-    with torch.cuda.device(a.device):
+    with _DeviceGuard(a.device):
         out = torch.empty((a.shape[0], b.shape[0]), dtype=torch.float32, device=a.device)
         _lib.check(_lib.load().cldet_calc_iou(a.data_ptr(), a.shape[0], b.data_ptr(), b.shape[0], out.data_ptr(), _stream()))
     return out
@@ -55,7 +55,7 @@ def iou_assign(anchors, annotations, num_classes, want_argmax=True, want_iou_max
     n, g = annotations.shape[0], annotations.shape[1]
     a = anchors.shape[0]
     dev = anchors.device
-    with torch.cuda.device(dev):
+    with _DeviceGuard(dev):
         meta = torch.empty((n, a), dtype=torch.int32, device=dev)
         argmax = torch.empty((n, a), dtype=torch.int32, device=dev) if want_argmax else None
         iou_max = torch.empty((n, a), dtype=torch.float32, device=dev) if want_iou_max else None
@@ -91,6 +91,30 @@ def _drop_workspaces():
     _tls.ws = {}
 
 
+class _DeviceGuard:
+    """`with torch.cuda.device(dev)` only when dev is not already current (the context manager costs ~10 us of host time)."""
+
+    def __init__(self, dev):
+        self.ctx = None if torch.cuda.current_device() == dev.index else torch.cuda.device(dev)
+
+    def __enter__(self):
+        if self.ctx is not None:
+            self.ctx.__enter__()
+
+    def __exit__(self, *exc):
+        if self.ctx is not None:
+            self.ctx.__exit__(*exc)
+
+
+def _row(t):
+    """(device pointer, element stride) of an upstream-gradient row; None -> (NULL, 0) = zeros."""
+    if t is None:
+        return None, 0
+    if t.dtype != torch.float32:
+        t = t.to(torch.float32)
+    return t, (t.stride(0) if t.dim() else 0)
+
+
 class _FocalLossFn(torch.autograd.Function):
     """outputs: bg[N], fg[N], reg_per_image[N], enhance_per_image[N] (rows of the kernel's [4,N] result)."""
 
@@ -101,28 +125,30 @@ class _FocalLossFn(torch.autograd.Function):
         g = annotations.shape[1]
         dev = cls.device
         need_grad = ctx.needs_input_grad[0] or ctx.needs_input_grad[1]
-        with torch.cuda.device(dev):
+        with _DeviceGuard(dev):
+            stream = _stream()
             losses = torch.empty((4, n), dtype=torch.float32, device=dev)
             meta = torch.empty((n, a), dtype=torch.int32, device=dev)
             iou_max = torch.empty((n, a), dtype=torch.float32, device=dev) if lp.decrease_positive_by_iou else None
-            npos = torch.empty(n, dtype=torch.int32, device=dev)
-            nvalid = torch.empty(n, dtype=torch.int32, device=dev)
+            counts = torch.empty((2, n), dtype=torch.int32, device=dev)      # rows: npos, nvalid
+            npos, nvalid = counts[0], counts[1]
             bg_mask = torch.empty((n, a), dtype=torch.uint8, device=dev) if want_bg_mask else None
             status = torch.empty(1, dtype=torch.int32, device=dev) if check_labels else None
-            ws = _workspace(dev, _stream(), n, a)
+            ws = _workspace(dev, stream, n, a)
             ws_bytes = ws.numel()
             if need_grad:
-                weights = hint.to(device=dev, dtype=torch.float32).clone()   # private: the reweight pass updates it
+                weights = hint                        # shared, read-only; the kernel records what it baked into `baked`
+                baked = torch.empty((4, n), dtype=torch.float32, device=dev)
                 gcls = torch.empty_like(cls)
                 greg = torch.empty_like(reg)
             else:
-                weights = gcls = greg = None
+                weights = baked = gcls = greg = None
             try:
                 _lib.check(lib.cldet_focal_loss(
                     cls.data_ptr(), reg.data_ptr(), anchors.data_ptr(), annotations.data_ptr(), n, a, c, g, lp,
-                    _lib.ptr(weights), _lib.ptr(gcls), _lib.ptr(greg), losses.data_ptr(), meta.data_ptr(),
+                    _lib.ptr(weights), _lib.ptr(baked), _lib.ptr(gcls), _lib.ptr(greg), losses.data_ptr(), meta.data_ptr(),
                     _lib.ptr(iou_max), npos.data_ptr(), nvalid.data_ptr(), _lib.ptr(bg_mask), _lib.ptr(status),
-                    ws.data_ptr(), ws_bytes, _stream()))
+                    ws.data_ptr(), ws_bytes, stream))
             except Exception:
                 _drop_workspaces()      # a failed call may leave the scratch header dirty
                 raise
@@ -133,7 +159,7 @@ class _FocalLossFn(torch.autograd.Function):
         ctx.shape = (n, a, c, g)
         ctx.backward_calls = 0
         if need_grad:
-            ctx.save_for_backward(cls, reg, anchors, annotations, weights, gcls, greg, meta, npos)
+            ctx.save_for_backward(cls, reg, anchors, annotations, baked, gcls, greg, meta, npos)
             ctx.iou_max = iou_max
             ctx.ws = ws
         ctx.mark_non_differentiable(npos, nvalid)
@@ -148,23 +174,13 @@ class _FocalLossFn(torch.autograd.Function):
         cls, reg, anchors, annotations, baked, gcls, greg, meta, npos = ctx.saved_tensors
         n, a, c, g = ctx.shape
         dev = cls.device
-        zero = None
-
-        def row(t):
-            nonlocal zero
-            if t is None:
-                if zero is None:
-                    zero = torch.zeros(n, dtype=torch.float32, device=dev)
-                return zero
-            return t.to(torch.float32)
-
-        with torch.cuda.device(dev):
-            new_w = torch.stack([row(g_bg), row(g_fg), row(g_reg), row(g_enh)]).contiguous()
-            iou_max = ctx.iou_max
-            _lib.check(_lib.load().cldet_focal_loss_reweight(
+        rows = [_row(t) for t in (g_bg, g_fg, g_reg, g_enh)]      # keeps converted tensors alive until the call returns
+        with _DeviceGuard(dev):
+            _lib.check(_lib.load().cldet_focal_loss_reweight_rows(
                 cls.data_ptr(), reg.data_ptr(), anchors.data_ptr(), annotations.data_ptr(), n, a, c, g, ctx.lp,
-                new_w.data_ptr(), baked.data_ptr(), gcls.data_ptr(), greg.data_ptr(), meta.data_ptr(), _lib.ptr(iou_max),
-                npos.data_ptr(), ctx.ws.data_ptr(), ctx.ws.numel(), _stream()))
+                _lib.ptr(rows[0][0]), rows[0][1], _lib.ptr(rows[1][0]), rows[1][1], _lib.ptr(rows[2][0]), rows[2][1],
+                _lib.ptr(rows[3][0]), rows[3][1], baked.data_ptr(), gcls.data_ptr(), greg.data_ptr(), meta.data_ptr(),
+                _lib.ptr(ctx.iou_max), npos.data_ptr(), ctx.ws.data_ptr(), ctx.ws.numel(), _stream()))
         ctx.backward_calls += 1
         if ctx.backward_calls > 1:   # the buffers may already be someone's .grad: hand out copies from now on
             return gcls.clone(), greg.clone(), None, None, None, None, None, None
@@ -202,7 +218,7 @@ class FocalLoss(nn.Module):
         if isinstance(self.upstream_hint, torch.Tensor):
             if tuple(self.upstream_hint.shape) != (4, n):
                 raise ValueError('upstream_hint must be [4, N]')
-            return self.upstream_hint
+            return self.upstream_hint.to(device=device, dtype=torch.float32).contiguous()
         if self.upstream_hint != 'mean':
             raise ValueError("upstream_hint must be 'mean' or a [4,N] tensor")
         key = (n, device.index)

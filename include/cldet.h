@@ -107,6 +107,8 @@ size_t cldet_focal_loss_workspace_bytes(int num_images, int64_t num_anchors);
  *            row 2 dL/d(reg_j), row 3 dL/d(enhance term); reg_j is the per-image regression term, so a caller holding
  *            dL/d(reg_loss[0]) passes that / N.
  *            NULL = no gradients wanted (d_grad_* must then be NULL too).
+ *   d_baked_weights [4,N] out, may be NULL: receives a copy of the weights baked into the gradients (the record that
+ *            cldet_focal_loss_reweight compares against), so d_weights itself can be a shared read-only tensor.
  *   d_grad_cls [N,A,C], d_grad_reg [N,A,4]: written completely (zeros where the reference's gradient is zero).
  *            d_grad_cls may alias d_cls (in-place variant for a caller that no longer needs the probabilities).
  *   d_losses [4,N]: rows bg_j, fg_j (each already divided by max(npos_j,1)), reg_j, enhance_on_new partial of image j.
@@ -116,7 +118,7 @@ size_t cldet_focal_loss_workspace_bytes(int num_images, int64_t num_anchors);
  *   d_status: int32[1] out, may be NULL; set non-zero when a positive anchor's label is outside [0,C) (reference raises, Q8). */
 int cldet_focal_loss(const float* d_cls, const float* d_reg, const float* d_anchors, const float* d_annotations,
                      int num_images, int64_t num_anchors, int num_classes, int gt_rows,
-                     const cldet_loss_params* params, const float* d_weights,
+                     const cldet_loss_params* params, const float* d_weights, float* d_baked_weights,
                      float* d_grad_cls, float* d_grad_reg, float* d_losses,
                      uint32_t* d_meta, float* d_iou_max, int32_t* d_npos, int32_t* d_nvalid,
                      uint8_t* d_bg_mask, int32_t* d_status,
@@ -133,9 +135,9 @@ int cldet_focal_loss_profile_events(void* ev_begin, void* ev_between, void* ev_e
 int cldet_focal_loss_from_assignment(const float* d_cls, const float* d_reg, const float* d_anchors,
                                      const float* d_annotations, int num_images, int64_t num_anchors, int num_classes,
                                      int gt_rows, const cldet_loss_params* params, const float* d_weights,
-                                     float* d_grad_cls, float* d_grad_reg, float* d_losses, uint32_t* d_meta,
-                                     const float* d_iou_max, const int32_t* d_npos, uint8_t* d_bg_mask, int32_t* d_status,
-                                     void* d_workspace, size_t workspace_bytes, void* stream);
+                                     float* d_baked_weights, float* d_grad_cls, float* d_grad_reg, float* d_losses,
+                                     uint32_t* d_meta, const float* d_iou_max, const int32_t* d_npos, uint8_t* d_bg_mask,
+                                     int32_t* d_status, void* d_workspace, size_t workspace_bytes, void* stream);
 
 /* Backward with upstream weights that differ from the ones baked into d_grad_* by the forward call
  * (IL_Loss's clip_loss masking, losses.py:575-581, is only known after the forward).  Per image and per term the
@@ -148,6 +150,17 @@ int cldet_focal_loss_reweight(const float* d_cls, const float* d_reg, const floa
                               const cldet_loss_params* params, const float* d_new_weights, float* d_baked_weights,
                               float* d_grad_cls, float* d_grad_reg, const uint32_t* d_meta, const float* d_iou_max,
                               const int32_t* d_npos, void* d_workspace, size_t workspace_bytes, void* stream);
+
+/* Same, with the four upstream-weight rows given separately as (pointer, element stride): exactly what autograd hands to
+ * backward (dL/dbg[N], dL/dfg[N], dL/dreg_j[N], dL/d enhance) without packing them first.  stride 0 broadcasts one value,
+ * a NULL row means zeros. */
+int cldet_focal_loss_reweight_rows(const float* d_cls, const float* d_reg, const float* d_anchors, const float* d_annotations,
+                                   int num_images, int64_t num_anchors, int num_classes, int gt_rows,
+                                   const cldet_loss_params* params, const float* d_w_bg, int64_t stride_bg,
+                                   const float* d_w_fg, int64_t stride_fg, const float* d_w_reg, int64_t stride_reg,
+                                   const float* d_w_enh, int64_t stride_enh, float* d_baked_weights, float* d_grad_cls,
+                                   float* d_grad_reg, const uint32_t* d_meta, const float* d_iou_max, const int32_t* d_npos,
+                                   void* d_workspace, size_t workspace_bytes, void* stream);
 
 /* ---- a10-a13: eval-mode detection output (retinanet/utils.py:102-144 BBoxTransform/ClipBoxes;
  *      retinanet/model.py:507-550 ResNet.predict; IL_method/persuado_label.py:99-127 Labeler.predict;

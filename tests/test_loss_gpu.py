@@ -375,7 +375,7 @@ def test_focal_logits_in_place_c_abi():
         nvalid = torch.empty(N, dtype=torch.int32, device=DEV)
         ws = torch.zeros(lib.cldet_focal_loss_workspace_bytes(N, A), dtype=torch.uint8, device=DEV)
         _lib.check(lib.cldet_focal_loss(buf.data_ptr(), reg.data_ptr(), anchors.data_ptr(), ann.data_ptr(), N, A, C, G, lp,
-                                        weights.data_ptr(), gcls.data_ptr(), greg.data_ptr(), losses.data_ptr(), meta.data_ptr(),
+                                        weights.data_ptr(), None, gcls.data_ptr(), greg.data_ptr(), losses.data_ptr(), meta.data_ptr(),
                                         None, npos.data_ptr(), nvalid.data_ptr(), None, None, ws.data_ptr(), ws.numel(),
                                         torch.cuda.current_stream().cuda_stream))
         return gcls, greg, losses

@@ -80,7 +80,7 @@ def test_loss_path_is_cuda_graph_capturable_and_repeatable():
 
     def call():
         _lib.check(lib.cldet_focal_loss(p.data_ptr(), r.data_ptr(), anchors.data_ptr(), an.data_ptr(), N, A, C, G, lp,
-                                        weights.data_ptr(), gcls.data_ptr(), greg.data_ptr(), losses.data_ptr(), meta.data_ptr(),
+                                        weights.data_ptr(), None, gcls.data_ptr(), greg.data_ptr(), losses.data_ptr(), meta.data_ptr(),
                                         None, npos.data_ptr(), nvalid.data_ptr(), None, None, ws.data_ptr(), ws.numel(),
                                         torch.cuda.current_stream().cuda_stream))
     s = torch.cuda.Stream()

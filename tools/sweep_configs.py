@@ -58,7 +58,7 @@ def main():
 
         def step():
             _lib.check(lib.cldet_focal_loss(probs.data_ptr(), reg.data_ptr(), anchors.data_ptr(), ann.data_ptr(), n, a, c, g, lp,
-                                            weights.data_ptr(), gcls.data_ptr(), greg.data_ptr(), losses.data_ptr(),
+                                            weights.data_ptr(), baked.data_ptr(), gcls.data_ptr(), greg.data_ptr(), losses.data_ptr(),
                                             meta.data_ptr(), None, npos.data_ptr(), nvalid.data_ptr(), None, None,
                                             ws.data_ptr(), ws.numel(), st))
             _lib.check(lib.cldet_focal_loss_reweight(probs.data_ptr(), reg.data_ptr(), anchors.data_ptr(), ann.data_ptr(), n, a,
