@@ -9,9 +9,10 @@ from .anchors import Anchors, generate_anchors, num_anchors  # noqa: F401
 from .losses import FocalLoss, calc_iou, iou_assign  # noqa: F401
 from .dist import ShardedFocalLoss, gather_terms, shard_sizes, shard_slice  # noqa: F401
 from . import detect  # noqa: F401
+from .distill import head_distillation  # noqa: F401
 from .matching import OutputNorm, get_positive, match_anchors  # noqa: F401
 from .detect import BBoxTransform, ClipBoxes, batched_nms, nms, detect_batch, predict, labeler_predict  # noqa: F401
 
-__all__ = ['OutputNorm', 'get_positive', 'match_anchors', 'ShardedFocalLoss', 'gather_terms', 'shard_sizes', 'shard_slice', 'BBoxTransform', 'ClipBoxes', 'batched_nms', 'nms',
+__all__ = ['head_distillation', 'OutputNorm', 'get_positive', 'match_anchors', 'ShardedFocalLoss', 'gather_terms', 'shard_sizes', 'shard_slice', 'BBoxTransform', 'ClipBoxes', 'batched_nms', 'nms',
            'detect_batch', 'predict', 'labeler_predict', 'detect', 'Anchors', 'generate_anchors', 'num_anchors', 'FocalLoss', 'calc_iou', 'iou_assign', 'HeadParams',
            'CldetError', 'load_library', 'LIB_PATH']

@@ -51,6 +51,9 @@ SIGNATURES = {
                                             _L, _P, _L, _P, _P, _P, _P, _P, _P, _P, _Z, _P]),
     'cldet_focal_loss_reweight': (_I, [_P, _P, _P, _P, _I, _L, _I, _I, ctypes.POINTER(LossParams), _P, _P, _P, _P, _P,
                                        _P, _P, _P, _Z, _P]),
+    'cldet_distill_workspace_bytes': (_Z, [_I, _L]),
+    'cldet_distill_forward': (_I, [_P, _P, _P, _P, _P, _I, _L, _I, _I, _I, _I, _P, _P, _P, _Z, _P]),
+    'cldet_distill_backward': (_I, [_P, _P, _P, _P, _P, _I, _L, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P]),
     'cldet_decode_boxes': (_I, [_P, _P, _I, _L, _I, _I, _I, _P, _P]),
     'cldet_clip_boxes': (_I, [_P, _L, _I, _I, _P]),
     'cldet_decode_filter': (_I, [_P, _I, _P, _P, _I, _L, _I, _I, _I, _F, _P, _P, _L, _P, _P]),

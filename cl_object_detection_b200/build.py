@@ -24,6 +24,7 @@ SOURCES = {
     'cldet_detect.cu': ['-fmad=false'],
     'cldet_loss.cu': [],
     'cldet_loss_logits.cu': [],
+    'cldet_distill.cu': [],
 }
 
 

@@ -162,6 +162,24 @@ int cldet_focal_loss_reweight_rows(const float* d_cls, const float* d_reg, const
                                    float* d_grad_reg, const uint32_t* d_meta, const float* d_iou_max, const int32_t* d_npos,
                                    void* d_workspace, size_t workspace_bytes, void* stream);
 
+/* ---- head-distillation terms of IL_Loss (retinanet/losses.py:705-737) ----
+ * d_cls [N,A,C] current logits, d_prev_cls [N,A,P] previous-model logits (P = past_class_num), d_reg / d_prev_reg [N,A,4],
+ * d_bg_mask [N,A] uint8 (FocalLoss 'bg_masks').  prev_fg_mask = sigmoid(prev_cls) > 0.05; reg_mask = bg_mask & any(prev_fg_mask);
+ * d_losses[0] = MSE over prev_fg_mask elements (ignore_gd: over reg_mask rows) of logits (distill_logits) or probabilities,
+ * d_losses[1] = SmoothL1 (beta 1) over reg_mask rows; d_counts[0..1] = the two element counts (float) for the backward.
+ * An empty selection yields NaN like the reference's mean over an empty tensor. */
+size_t cldet_distill_workspace_bytes(int num_images, int64_t num_anchors);
+int cldet_distill_forward(const float* d_cls, const float* d_prev_cls, const float* d_reg, const float* d_prev_reg,
+                          const uint8_t* d_bg_mask, int num_images, int64_t num_anchors, int num_classes, int past_class_num,
+                          int distill_logits, int ignore_gd, float* d_losses, float* d_counts, void* d_workspace,
+                          size_t workspace_bytes, void* stream);
+/* d_grad_cls_loss / d_grad_reg_loss: device scalars dL/d(dist_cls_loss), dL/d(dist_reg_loss) (NULL = 0).
+ * Writes d_grad_cls [N,A,C] completely (zeros for columns >= P) and d_grad_reg [N,A,4]. */
+int cldet_distill_backward(const float* d_cls, const float* d_prev_cls, const float* d_reg, const float* d_prev_reg,
+                           const uint8_t* d_bg_mask, int num_images, int64_t num_anchors, int num_classes, int past_class_num,
+                           int distill_logits, int ignore_gd, const float* d_counts, const float* d_grad_cls_loss,
+                           const float* d_grad_reg_loss, float* d_grad_cls, float* d_grad_reg, void* stream);
+
 /* ---- a10-a13: eval-mode detection output (retinanet/utils.py:102-144 BBoxTransform/ClipBoxes;
  *      retinanet/model.py:507-550 ResNet.predict; IL_method/persuado_label.py:99-127 Labeler.predict;
  *      torchvision.ops.batched_nms at model.py:540) ---- */

@@ -550,3 +550,46 @@ def get_positive(anchors, annotations, threshold, num_anchors):
         pos.append((asg['iou_max'] >= F32(threshold)).reshape(-1, num_anchors))
         tgt.append(asg['label'].astype(np.int64).reshape(-1, num_anchors))
     return np.stack(pos), np.stack(tgt)
+
+
+# --------------------------------------------------------------------------------------
+# 8(f) row f2  head-distillation terms of IL_Loss  (retinanet/losses.py:705-737)
+# --------------------------------------------------------------------------------------
+def head_distillation(classification, regression, prev_classification, prev_regression, bg_masks, distill_logits=False,
+                      ignore_gd=False, g_cls=1.0, g_reg=1.0):
+    """Returns (dist_cls_loss, dist_reg_loss, grad_classification[N,A,C], grad_regression[N,A,4])."""
+    cls = np.asarray(classification, dtype=F32)
+    prev = np.asarray(prev_classification, dtype=F32)
+    reg = np.asarray(regression, dtype=F32)
+    preg = np.asarray(prev_regression, dtype=F32)
+    bgm = np.asarray(bg_masks).astype(bool)
+    P = prev.shape[2]
+    cur_l = cls[:, :, :P]                                          # :705
+    prev_p = sigmoid(prev)
+    fg = prev_p > F32(0.05)                                        # :712 / :717
+    if distill_logits:
+        a, b = prev, cur_l
+    else:
+        a, b = prev_p, sigmoid(cur_l)                              # :714-715
+    reg_mask = bgm & fg.any(axis=2)                                # :720
+    d = (preg[reg_mask] - reg[reg_mask]).astype(np.float64)
+    z = np.abs(d)
+    k_reg = d.size
+    reg_loss = np.sum(np.where(z < 1.0, 0.5 * z * z, z - 0.5)) / k_reg if k_reg else np.nan      # SmoothL1Loss, beta 1
+    greg = np.zeros_like(reg)
+    if k_reg:
+        greg[reg_mask] = (-np.clip(d, -1.0, 1.0) * (g_reg / k_reg)).astype(F32)
+    sel = np.broadcast_to(reg_mask[:, :, None], fg.shape) if ignore_gd else fg               # :724-727
+    e = (a[sel] - b[sel]).astype(np.float64)
+    k_cls = e.size
+    cls_loss = np.sum(e * e) / k_cls if k_cls else np.nan
+    gcls = np.zeros_like(cls)
+    if k_cls:
+        gsel = -2.0 * e * (g_cls / k_cls)
+        if not distill_logits:
+            bp = b[sel].astype(np.float64)
+            gsel = gsel * (1.0 - bp) * bp
+        tmp = np.zeros(fg.shape, dtype=F32)
+        tmp[sel] = gsel.astype(F32)
+        gcls[:, :, :P] = tmp
+    return F32(cls_loss), F32(reg_loss), gcls, greg

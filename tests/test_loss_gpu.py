@@ -401,3 +401,23 @@ def test_f3_other_iou_users_golden():
     check_rel(out['classification'].detach().cpu().numpy(), g['norm_classification'], 1e-6)
     assert np.allclose(c.grad.cpu().numpy(), g['grad_cls'], rtol=1e-6, atol=0)
     assert np.allclose(r.grad.cpu().numpy(), g['grad_reg'], rtol=1e-6, atol=0)
+
+
+@pytest.mark.parametrize('name,dl,ig', [('probs', False, False), ('logits', True, False), ('probs_ignoregd', False, True),
+                                        ('logits_ignoregd', True, True)])
+def test_f2_head_distillation(name, dl, ig):
+    """fused distillation terms vs the torch restatement of losses.py:705-737 (golden) and the oracle.
+    Small gradients of (prev - cur) differences cancel, hence the scale-relative floor."""
+    g = load('f2_distill')
+    c = cu(g['cls']).requires_grad_(True)
+    r = cu(g['reg']).requires_grad_(True)
+    out = cld.head_distillation(c, r, cu(g['prev']), cu(g['preg']), cu(g['bg']), distill_logits=dl, ignore_GD=ig)
+    (0.6 * out['dist_cls_loss'] + 1.7 * out['dist_reg_loss']).backward()
+    check_rel(out['dist_cls_loss'].detach().cpu().numpy(), g[name + '_cls_loss'])
+    check_rel(out['dist_reg_loss'].detach().cpu().numpy(), g[name + '_reg_loss'])
+    for got, ref in ((c.grad.cpu().numpy(), g[name + '_grad_cls']), (r.grad.cpu().numpy(), g[name + '_grad_reg'])):
+        assert np.array_equal(got == 0, ref == 0)
+        assert float(np.max(np.abs(got - ref) - 1e-5 * np.abs(ref))) <= 1e-5 * float(np.abs(ref).max())
+    lc, lr, gc, gr = O.head_distillation(g['cls'], g['reg'], g['prev'], g['preg'], g['bg'], dl, ig, g_cls=0.6, g_reg=1.7)
+    check_rel(out['dist_cls_loss'].detach().cpu().numpy(), lc)
+    check_rel(out['dist_reg_loss'].detach().cpu().numpy(), lr)

@@ -134,3 +134,15 @@ def test_f3_iou_users_match_reference():
     assert np.allclose(0.7 * gr, g['grad_reg'], rtol=1e-6, atol=0)
     pos, tgt = O.get_positive(anchors, g['ann'], float(g['proto_threshold']), 9)
     assert np.array_equal(pos, g['proto_positive']) and np.array_equal(tgt, g['proto_targets'])
+
+
+@pytest.mark.parametrize('name,dl,ig', [('probs', False, False), ('logits', True, False), ('probs_ignoregd', False, True),
+                                        ('logits_ignoregd', True, True)])
+def test_f2_head_distillation_matches_torch_restatement(name, dl, ig):
+    g = load('f2_distill')
+    lc, lr, gc, gr = O.head_distillation(g['cls'], g['reg'], g['prev'], g['preg'], g['bg'], dl, ig, g_cls=0.6, g_reg=1.7)
+    assert rel_err(lc, g[name + '_cls_loss'], 1e-30) < 1e-5 and rel_err(lr, g[name + '_reg_loss'], 1e-30) < 1e-5
+    ref_c, ref_r = g[name + '_grad_cls'], g[name + '_grad_reg']
+    assert np.array_equal(gc == 0, ref_c == 0) and np.array_equal(gr == 0, ref_r == 0)
+    assert float(np.max(np.abs(gc - ref_c) - 1e-5 * np.abs(ref_c))) <= 1e-5 * float(np.abs(ref_c).max())
+    assert float(np.max(np.abs(gr - ref_r) - 1e-5 * np.abs(ref_r))) <= 1e-6 * float(np.abs(ref_r).max())
