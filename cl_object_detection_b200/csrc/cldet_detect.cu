@@ -644,6 +644,72 @@ keep_to_original_kernel(const cldet_candidate* __restrict__ sorted, const int32_
     if (i < *keep_count) out[i] = (int64_t)sorted[keep[i]].anchor;
 }
 
+// ------------------------------------------------------------------------------------------------
+// evaluator post-processing (evaluator.py:329-361): boxes /= scale (true fp32 division, CPU ATen
+// semantics), xyxy -> xywh, keep score >= threshold; records ordered by image, then by rank.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+coco_offsets_kernel(const float* __restrict__ scores, const int32_t* __restrict__ counts, int N, int64_t capacity, float thr,
+                    int32_t* __restrict__ offsets /* [N+1] */) {
+    // one block: per-image number of detections with score >= thr, then an exclusive scan in image order
+    __shared__ int total;
+    if (threadIdx.x == 0) total = 0;
+    __syncthreads();
+    for (int j0 = 0; j0 < N; j0 += blockDim.x) {
+        const int j = j0 + threadIdx.x;
+        int pass = 0;
+        if (j < N) {
+            const int n = (int)min64(counts[j], capacity);
+            const float* s = scores + (int64_t)j * capacity;
+            for (int i = 0; i < n; ++i) pass += (s[i] >= thr) ? 1 : 0;     // `if score < threshold: continue`
+        }
+        // block-wide exclusive scan of `pass` (Hillis-Steele over a shared array)
+        __shared__ int sh[256];
+        sh[threadIdx.x] = pass;
+        __syncthreads();
+        for (int off = 1; off < (int)blockDim.x; off <<= 1) {
+            const int add = (threadIdx.x >= (unsigned)off) ? sh[threadIdx.x - off] : 0;
+            __syncthreads();
+            sh[threadIdx.x] += add;
+            __syncthreads();
+        }
+        if (j < N) offsets[j] = total + sh[threadIdx.x] - pass;
+        __syncthreads();
+        if (threadIdx.x == blockDim.x - 1) total += sh[threadIdx.x];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) offsets[N] = total;
+}
+
+__global__ void __launch_bounds__(256)
+coco_records_kernel(const float* __restrict__ scores, const int64_t* __restrict__ labels, const float4* __restrict__ boxes,
+                    const int32_t* __restrict__ counts, const float* __restrict__ scales, int64_t capacity, float thr,
+                    const int32_t* __restrict__ offsets, cldet_coco_record* __restrict__ out) {
+    const int j = blockIdx.y;
+    const int n = (int)min64(counts[j], capacity);
+    const float* s = scores + (int64_t)j * capacity;
+    // scores are in NMS (descending) order, but ties and the >= test are handled generally: rank among the passing ones
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const float sc = s[i];
+        if (!(sc >= thr)) continue;
+        int rank = 0;
+        for (int t = 0; t < i; ++t) rank += (s[t] >= thr) ? 1 : 0;
+        const float4 b = boxes[(int64_t)j * capacity + i];
+        const float scale = scales[j];
+        cldet_coco_record r;
+        const float x1 = __fdiv_rn(b.x, scale), y1 = __fdiv_rn(b.y, scale), x2 = __fdiv_rn(b.z, scale), y2 = __fdiv_rn(b.w, scale);
+        r.image = j;
+        r.label = (int32_t)labels[(int64_t)j * capacity + i];
+        r.score = sc;
+        r.x = x1;
+        r.y = y1;
+        r.w = __fsub_rn(x2, x1);
+        r.h = __fsub_rn(y2, y1);
+        r.pad = 0;
+        out[offsets[j] + rank] = r;
+    }
+}
+
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 struct NmsWs {
@@ -849,6 +915,21 @@ int cldet_gather_detections(const cldet_candidate* d_sorted, const int32_t* d_ke
     dim3 grid((unsigned)((max_keep + 255) / 256), (unsigned)num_images);
     gather_detections_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(d_sorted, d_keep, d_keep_counts, capacity, d_scores,
                                                                     d_labels, reinterpret_cast<float4*>(d_boxes));
+    CLDET_LAUNCH_CHECK();
+    return CLDET_OK;
+}
+
+int cldet_coco_results(const float* d_scores, const int64_t* d_labels, const float* d_boxes, const int32_t* d_counts,
+                       const float* d_scales, int num_images, int64_t capacity, float score_threshold,
+                       cldet_coco_record* d_records, int32_t* d_offsets, void* stream) {
+    if (!d_scores || !d_labels || !d_boxes || !d_counts || !d_scales || !d_records || !d_offsets) return CLDET_ERR_INVALID_ARGUMENT;
+    if (num_images <= 0 || num_images > 65535 || capacity <= 0) return CLDET_ERR_INVALID_ARGUMENT;
+    cudaStream_t s = (cudaStream_t)stream;
+    coco_offsets_kernel<<<1, 256, 0, s>>>(d_scores, d_counts, num_images, capacity, score_threshold, d_offsets);
+    CLDET_LAUNCH_CHECK();
+    dim3 grid((unsigned)std::min<int64_t>((capacity + 255) / 256, 64), (unsigned)num_images);
+    coco_records_kernel<<<grid, 256, 0, s>>>(d_scores, d_labels, reinterpret_cast<const float4*>(d_boxes), d_counts, d_scales,
+                                             capacity, score_threshold, d_offsets, d_records);
     CLDET_LAUNCH_CHECK();
     return CLDET_OK;
 }

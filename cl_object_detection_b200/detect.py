@@ -183,3 +183,40 @@ def labeler_predict(img_batch, classifications, regressions, anchors, **kw):
     if s.shape[0] == 0:
         return torch.tensor([]), torch.tensor([]), torch.tensor([])
     return s, b, l
+
+
+def coco_results(padded, scales, image_ids=None, label_to_coco_label=None, score_threshold=0.05):
+    """SURVEY 8(f) row f4 -- the evaluator's per-detection Python loop (evaluator.py:329-361) for a whole batch:
+    boxes / scale, xyxy -> xywh, keep score >= threshold, on the device; ONE device->host copy of the compact records.
+
+    padded: (scores[N,cap], labels[N,cap], boxes[N,cap,4], counts[N]) from detect_batch(..., return_padded=True);
+    scales: per-image resize scale (sequence or tensor).  Returns the reference's list of dicts
+    {'image_id', 'category_id', 'score', 'bbox'} (image_ids / label_to_coco_label default to identity).
+    """
+    scores, labels, boxes, counts = padded
+    n, cap = scores.shape
+    dev = scores.device
+    if cap == 0:
+        return []
+    lib = _lib.load()
+    with torch.cuda.device(dev):
+        sc = torch.as_tensor(scales, dtype=torch.float32).to(dev).contiguous()
+        if sc.numel() != n:
+            raise ValueError('one scale per image expected')
+        rec = torch.empty((n * cap, 8), dtype=torch.int32, device=dev)
+        offsets = torch.empty(n + 1, dtype=torch.int32, device=dev)
+        _lib.check(lib.cldet_coco_results(scores.contiguous().data_ptr(), labels.contiguous().data_ptr(),
+                                          boxes.contiguous().data_ptr(), counts.contiguous().data_ptr(), sc.data_ptr(), n, cap,
+                                          float(score_threshold), rec.data_ptr(), offsets.data_ptr(), _stream()))
+        total = int(offsets[n].item())
+        host = rec[:total].cpu()
+    ints = host.numpy()
+    floats = host.view(torch.float32).numpy()
+    out = []
+    for k in range(total):
+        j, lab = int(ints[k, 0]), int(ints[k, 1])
+        out.append({'image_id': j if image_ids is None else image_ids[j],
+                    'category_id': lab if label_to_coco_label is None else label_to_coco_label(lab),
+                    'score': float(floats[k, 2]),
+                    'bbox': [float(floats[k, 3]), float(floats[k, 4]), float(floats[k, 5]), float(floats[k, 6])]})
+    return out

@@ -247,6 +247,22 @@ int cldet_gather_detections(const cldet_candidate* d_sorted, const int32_t* d_ke
                             int num_images, int64_t capacity, int64_t max_keep, float* d_scores, int64_t* d_labels,
                             float* d_boxes, void* stream);
 
+/* ---- evaluator post-processing (evaluator.py:329-361) ----
+ * From the padded detections of cldet_gather_detections: divide boxes by the image's resize scale (true fp32 division),
+ * convert xyxy -> xywh (COCO), drop score < score_threshold, and write compact records ordered by image then rank.
+ * d_offsets [N+1] int32 out: exclusive scan of the per-image record counts (d_offsets[N] = total).
+ * d_records must hold num_images * capacity records. */
+typedef struct cldet_coco_record {   /* 32 bytes */
+    int32_t image;                  /* index into the batch */
+    int32_t label;
+    float score;
+    float x, y, w, h;               /* COCO bbox */
+    int32_t pad;
+} cldet_coco_record;
+int cldet_coco_results(const float* d_scores, const int64_t* d_labels, const float* d_boxes, const int32_t* d_counts,
+                       const float* d_scales, int num_images, int64_t capacity, float score_threshold,
+                       cldet_coco_record* d_records, int32_t* d_offsets, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -593,3 +593,22 @@ def head_distillation(classification, regression, prev_classification, prev_regr
         tmp[sel] = gsel.astype(F32)
         gcls[:, :, :P] = tmp
     return F32(cls_loss), F32(reg_loss), gcls, greg
+
+
+# --------------------------------------------------------------------------------------
+# 8(f) row f4  evaluator post-processing  (evaluator.py:329-361)
+# --------------------------------------------------------------------------------------
+def coco_results(detections, scales, score_threshold=0.05):
+    """detections: list over images of (scores, labels, boxes xyxy).  boxes /= scale (fp32 true division -- CPU ATen),
+    boxes[:,2:] -= boxes[:,:2], skip score < threshold.  Returns a list of (image, label, score, [x,y,w,h])."""
+    out = []
+    for j, (s, l, b) in enumerate(detections):
+        b = np.asarray(b, dtype=F32).reshape(-1, 4) / F32(scales[j])
+        b = b.copy()
+        b[:, 2] -= b[:, 0]
+        b[:, 3] -= b[:, 1]
+        for i in range(b.shape[0]):
+            if F32(s[i]) < F32(score_threshold):
+                continue
+            out.append((j, int(l[i]), float(s[i]), [float(v) for v in b[i]]))
+    return out

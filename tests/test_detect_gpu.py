@@ -182,3 +182,37 @@ def test_full_size_coco_shape_topk1000():
         # idempotence: NMS of the output keeps everything
         again = D.batched_nms(b, s, l, 0.5)
         assert again.shape[0] == s.shape[0]
+
+
+def test_f4_coco_results_vs_oracle_and_torch_cpu():
+    """evaluator post-processing (evaluator.py:329-361) on the device, bit-exact with the CPU statements."""
+    h, w, C, N = 256, 320, 7, 3
+    anchors = cld.generate_anchors(h, w, DEV)
+    A = anchors.shape[1]
+    gen = torch.Generator(device=DEV).manual_seed(21)
+    logits = torch.randn(N, A, C, device=DEV, generator=gen) * 2 - 5
+    logits[2] = -20.0                                           # an image without detections
+    reg = torch.randn(N, A, 4, device=DEV, generator=gen) * 0.4
+    scales = [1.3371234567, 0.731, 2.0]
+    padded = D.detect_batch(logits, reg, anchors, h, w, pre_nms_topk=200, return_padded=True)
+    got = D.coco_results(padded, scales, image_ids=[101, 102, 103], label_to_coco_label=lambda x: x + 1, score_threshold=0.3)
+    dets = D.detect_batch(logits, reg, anchors, h, w, pre_nms_topk=200)
+    ref = O.coco_results([(s.cpu().numpy(), l.cpu().numpy(), b.cpu().numpy()) for s, l, b in dets], scales, 0.3)
+    assert len(got) == len(ref) and len(got) > 0
+    for g_, r_ in zip(got, ref):
+        assert g_['image_id'] == 101 + r_[0] and g_['category_id'] == r_[1] + 1
+        assert g_['score'] == r_[2] and g_['bbox'] == r_[3]
+    # and against the evaluator's own torch-CPU statements
+    k = 0
+    for j, (s, l, b) in enumerate(dets):
+        b = b.cpu().clone()
+        b /= scales[j]
+        if b.shape[0] > 0:
+            b[:, 2] -= b[:, 0]
+            b[:, 3] -= b[:, 1]
+        for i in range(b.shape[0]):
+            if float(s[i]) < 0.3:
+                continue
+            assert got[k]['bbox'] == b[i].tolist() and got[k]['score'] == float(s[i])
+            k += 1
+    assert k == len(got)
