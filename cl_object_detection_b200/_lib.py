@@ -40,6 +40,7 @@ SIGNATURES = {
     'cldet_num_anchors': (_I, [_I, _I, ctypes.POINTER(_L)]),
     'cldet_anchors': (_I, [_I, _I, _P, _P]),
     'cldet_iou_assign': (_I, [_P, _L, _P, _I, _I, _I, _P, _P, _P, _P, _P, _P]),
+    'cldet_iou_max_f64': (_I, [_P, _L, _P, _I, _P, _P, _P]),
     'cldet_calc_iou': (_I, [_P, _L, _P, _I, _P, _P]),
     'cldet_focal_loss_workspace_bytes': (_Z, [_I, _L]),
     'cldet_focal_loss': (_I, [_P, _P, _P, _P, _I, _L, _I, _I, ctypes.POINTER(LossParams), _P, _P, _P, _P, _P, _P, _P, _P,

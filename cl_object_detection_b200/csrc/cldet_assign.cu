@@ -318,6 +318,32 @@ calc_iou_kernel(const float4* __restrict__ a, int64_t na, const float4* __restri
     }
 }
 
+// fp64 IoU + max over the second set (IL_method/persuado_label.py:68-72: calc_iou on float64 annotations, .max(dim=1))
+__global__ void __launch_bounds__(128)
+iou_max_f64_kernel(const double* __restrict__ a, int64_t na, const double* __restrict__ b, int nb, double* __restrict__ out_max,
+                   int32_t* __restrict__ out_arg) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= na) return;
+    const double ax1 = a[4 * i], ay1 = a[4 * i + 1], ax2 = a[4 * i + 2], ay2 = a[4 * i + 3];
+    const double area_a = (ax2 - ax1) * (ay2 - ay1);
+    double best = -1.0;
+    int arg = -1;
+    for (int g = 0; g < nb; ++g) {
+        const double bx1 = b[4 * g], by1 = b[4 * g + 1], bx2 = b[4 * g + 2], by2 = b[4 * g + 3];
+        const double area_b = (bx2 - bx1) * (by2 - by1);
+        double iw = fmax(fmin(ax2, bx2) - fmax(ax1, bx1), 0.0);
+        double ih = fmax(fmin(ay2, by2) - fmax(ay1, by1), 0.0);
+        const double ua = fmax((area_a + area_b) - iw * ih, 1e-8);
+        const double v = __ddiv_rn(iw * ih, ua);
+        if (v > best) {
+            best = v;
+            arg = g;
+        }
+    }
+    out_max[i] = best;
+    if (out_arg) out_arg[i] = arg;
+}
+
 }  // namespace cldet
 
 using namespace cldet;
@@ -369,6 +395,15 @@ int cldet_iou_assign(const float* d_anchors, int64_t num_anchors, const float* d
     iou_assign_kernel<<<grid, kAssignThreads, 0, (cudaStream_t)stream>>>(
         reinterpret_cast<const float4*>(d_anchors), num_anchors, d_annotations, gt_rows, num_classes, d_meta, d_argmax,
         d_iou_max, d_npos, d_nvalid);
+    CLDET_LAUNCH_CHECK();
+    return CLDET_OK;
+}
+
+int cldet_iou_max_f64(const double* d_a, int64_t num_a, const double* d_b, int num_b, double* d_max, int32_t* d_argmax,
+                      void* stream) {
+    if (!d_a || !d_b || !d_max || num_a < 0 || num_b <= 0) return CLDET_ERR_INVALID_ARGUMENT;
+    if (num_a == 0) return CLDET_OK;
+    iou_max_f64_kernel<<<(unsigned)((num_a + 127) / 128), 128, 0, (cudaStream_t)stream>>>(d_a, num_a, d_b, num_b, d_max, d_argmax);
     CLDET_LAUNCH_CHECK();
     return CLDET_OK;
 }

@@ -79,6 +79,12 @@ int cldet_iou_assign(const float* d_anchors, int64_t num_anchors, const float* d
  * weight_init.py:7-24).  For tests and the "next" callers; the loss path never materialises this matrix. */
 int cldet_calc_iou(const float* d_a, int64_t num_a, const float* d_b, int num_b, float* d_iou, void* stream);
 
+/* Row-wise max of the fp64 IoU matrix (calc_iou on float64 inputs followed by .max(dim=1)): the pseudo-label generator's
+ * overlap test against the real GT (IL_method/persuado_label.py:59-75).  d_a [num_a,4], d_b [num_b,4] doubles;
+ * d_max [num_a]; d_argmax [num_a] int32 (first maximal index) may be NULL. */
+int cldet_iou_max_f64(const double* d_a, int64_t num_a, const double* d_b, int num_b, double* d_max, int32_t* d_argmax,
+                      void* stream);
+
 /* ---- a5-a8: FocalLoss.forward + its autograd backward (retinanet/losses.py:252-452) ---- */
 typedef struct cldet_loss_params {
     float alpha;                       /* params['alpha'], default 0.25 */

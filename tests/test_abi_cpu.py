@@ -75,3 +75,16 @@ def test_params_translation_matches_reference_error_behaviour():
         to_loss_params(p, 1, 16)
     p['decrease_positive_by_IOU'] = True
     assert to_loss_params(p, 1, 16).decrease_positive_by_iou == 1
+
+
+def test_a9_pseudo_label_format_mirrors_reference_collater():
+    """Host-side format helpers (CPU): merged pseudo rows + -1 padding exactly as the reference's collater emits them."""
+    from tests.helpers import load
+    g = load('a9_pseudo_labels')
+    annots = [g['annot0'], g['annot1'], g['annot2']]
+    out = cld.collate_annotations(annots)
+    assert out.dtype == torch.float32 and np.array_equal(out.numpy(), g['collated'])
+    assert np.array_equal(cld.collate_annotations([np.zeros((0, 5))]).numpy(), g['collated_empty'])
+    real = np.array([[10, 20, 30, 40, 15]], dtype=np.float64)
+    pseudo = np.array([[5, 6, 7, 8, 1], [1, 2, 3, 4, 0]], dtype=np.float64)
+    assert np.array_equal(cld.merge_pseudo_labels(real, pseudo), O.merge_pseudo_labels(real, pseudo))

@@ -216,3 +216,16 @@ def test_f4_coco_results_vs_oracle_and_torch_cpu():
             assert got[k]['bbox'] == b[i].tolist() and got[k]['score'] == float(s[i])
             k += 1
     assert k == len(got)
+
+
+def test_a9_pseudo_label_filter_golden():
+    """Tail of Labeler.get_persuado_label (persuado_label.py:52-81) vs the reference's own torch statements (golden)."""
+    g = load('a9_pseudo_labels')
+    s, b, l = cld.filter_pseudo_labels(cu(g['pl_scores']), cu(g['pl_boxes']), cu(g['pl_labels']), cu(g['pl_gt']), float(g['pl_scale']))
+    assert np.array_equal(s.cpu().numpy(), g['out_scores']) and np.array_equal(l.cpu().numpy(), g['out_labels'])
+    # `boxes / scale` runs on the device like in the reference (persuado_label.py:55 divides CUDA tensors): ATen's CUDA kernel
+    # multiplies by the reciprocal of a scalar divisor, the CPU kernel that produced the golden vectors divides: <= 1 ulp.
+    assert np.allclose(b.cpu().numpy(), g['out_boxes'], rtol=2.4e-7, atol=6.2e-5)   # w = x2 - x1: 2 ulp of the coordinate (<= 512)
+    e = cld.filter_pseudo_labels(torch.empty(0, device=DEV), torch.empty((0, 4), device=DEV), torch.empty(0, dtype=torch.int64, device=DEV),
+                                 cu(g['pl_gt']), 1.0)
+    assert e[0].numel() == 0 and e[1].shape == (0, 4)

@@ -146,3 +146,16 @@ def test_f2_head_distillation_matches_torch_restatement(name, dl, ig):
     assert np.array_equal(gc == 0, ref_c == 0) and np.array_equal(gr == 0, ref_r == 0)
     assert float(np.max(np.abs(gc - ref_c) - 1e-5 * np.abs(ref_c))) <= 1e-5 * float(np.abs(ref_c).max())
     assert float(np.max(np.abs(gr - ref_r) - 1e-5 * np.abs(ref_r))) <= 1e-6 * float(np.abs(ref_r).max())
+
+
+def test_a9_collate_and_pseudo_filter_match_reference():
+    g = load('a9_pseudo_labels')
+    annots = [g['annot0'], g['annot1'], g['annot2']]
+    assert np.array_equal(O.collate_annotations(annots), g['collated'])
+    assert np.array_equal(O.collate_annotations([np.zeros((0, 5))]), g['collated_empty'])
+    s, b, l = O.filter_pseudo_labels(g['pl_scores'], g['pl_boxes'], g['pl_labels'], g['pl_gt'][g['pl_gt'][:, 4] != -1][:, :4] / float(g['pl_scale']),
+                                     float(g['pl_scale']))
+    b = b.copy()
+    b[:, 2] -= b[:, 0]
+    b[:, 3] -= b[:, 1]
+    assert np.array_equal(s, g['out_scores']) and np.array_equal(l, g['out_labels']) and np.array_equal(b, g['out_boxes'])
