@@ -249,17 +249,44 @@ def run_ours(args):
         e.record()          # materialise the CUDA event handles
     torch.cuda.synchronize()
 
+    # N > 1: every rank needs every image's (bg, fg, reg) terms (IL_Loss's mean / clip_loss mask).  Default: the loss kernel
+    # itself pushes them into all ranks' gather buffers over NVLink peer stores (cldet_focal_loss_sharded) and a one-block
+    # kernel waits for the arrivals; `--collective nccl` uses an NCCL all-gather after the kernel instead.
+    peer = None
+    collective = 'none'
+    if world > 1:
+        collective = args.collective
+        if collective == 'peer':
+            from cl_object_detection_b200.dist import PeerGather
+            try:
+                peer = PeerGather(n, dev)
+            except Exception as e:  # noqa: BLE001
+                print('peer exchange unavailable (%r): falling back to the NCCL all-gather' % (e,), file=sys.stderr)
+                peer = None
+            ok = torch.tensor([1 if peer is not None else 0], device=dev)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+            if int(ok.item()) == 0:
+                peer, collective = None, 'nccl'
+
     def step(i=None):
+        nonlocal peer
         # the fused entry point (assign + loss in one call) -- what FocalLoss.forward issues; the profiling hook makes
         # this call record events around its two kernels so the loss kernel is timed inside the real step
         if i is not None:
             lib.cldet_focal_loss_profile_events(ev_a[i].cuda_event, ev_b[i].cuda_event, ev_c[i].cuda_event)
-        _lib.check(lib.cldet_focal_loss(
-            probs.data_ptr(), reg.data_ptr(), anchors.data_ptr(), ann.data_ptr(), n, a, C, GMAX, lp, weights.data_ptr(),
-            baked.data_ptr(), gcls.data_ptr(), greg.data_ptr(), losses.data_ptr(), meta.data_ptr(), None, npos.data_ptr(),
-            nvalid.data_ptr(), None, None, ws.data_ptr(), ws_bytes, stream))
-        if world > 1:   # every rank gets every image's (bg, fg, reg) terms: what IL_Loss's mean / clip_loss needs
-            dist.all_gather_into_tensor(gathered, losses)
+        if peer is not None:
+            _lib.check(lib.cldet_focal_loss_sharded(
+                probs.data_ptr(), reg.data_ptr(), anchors.data_ptr(), ann.data_ptr(), n, a, C, GMAX, lp, weights.data_ptr(),
+                baked.data_ptr(), gcls.data_ptr(), greg.data_ptr(), losses.data_ptr(), meta.data_ptr(), None, npos.data_ptr(),
+                nvalid.data_ptr(), None, None, ws.data_ptr(), ws_bytes, peer.exchange(), stream))
+            peer.wait(stream)
+        else:
+            _lib.check(lib.cldet_focal_loss(
+                probs.data_ptr(), reg.data_ptr(), anchors.data_ptr(), ann.data_ptr(), n, a, C, GMAX, lp, weights.data_ptr(),
+                baked.data_ptr(), gcls.data_ptr(), greg.data_ptr(), losses.data_ptr(), meta.data_ptr(), None, npos.data_ptr(),
+                nvalid.data_ptr(), None, None, ws.data_ptr(), ws_bytes, stream))
+            if world > 1:
+                dist.all_gather_into_tensor(gathered, losses)
         # backward: upstream weights are verified on the device; unchanged -> nothing is recomputed
         _lib.check(lib.cldet_focal_loss_reweight(probs.data_ptr(), reg.data_ptr(), anchors.data_ptr(), ann.data_ptr(), n, a, C,
                                                  GMAX, lp, weights.data_ptr(), baked.data_ptr(), gcls.data_ptr(),
@@ -273,6 +300,16 @@ def run_ours(args):
 
     for _ in range(max(args.warmup, 3)):
         step()
+    if peer is not None:
+        # the warm-up doubles as a health check of the peer exchange: any rank that saw a missing arrival sends everyone
+        # back to the NCCL all-gather before the timed region
+        bad = torch.tensor([int(peer.status.item())], device=dev)
+        dist.all_reduce(bad, op=dist.ReduceOp.MAX)
+        if int(bad.item()) != 0:
+            print('peer exchange reported a missing arrival: using the NCCL all-gather', file=sys.stderr)
+            peer, collective = None, 'nccl'
+            for _ in range(3):
+                step()
     sampler = ClockSampler(local_rank)
     barrier()
     sampler.start()
@@ -369,16 +406,21 @@ def run_ours(args):
                 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
                 'config': {'workload': 'coco_loss_fwd_bwd: %d x 800x1333 per GPU, C=80, A=%d, G<=%d (BASELINE config 3)' % (n, a, GMAX),
                            'images_per_gpu': n, 'global_batch': n_global, 'parallelism': 'image-sharded dp%d' % world,
+                           'collective': {'none': 'none (1 GPU)', 'peer': 'fused into the loss kernel: NVLink peer stores + arrival counters',
+                                          'nccl': 'NCCL all-gather of the [4,N] terms'}[collective],
                            'l2': 'inputs (%.2f GB per GPU) are larger than the 126 MB L2; no flush needed' % (probs.numel() * 4 / 1e9)},
                 'clocks': clocks,
                 'e2e': {'value': n_global / e2e_s, 'unit': 'images/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
                         'ms_per_step': e2e_s * 1e3, 'steps': e2e_steps},
-                'gpu_launches': 3 * args.steps,
+                'gpu_launches': (4 if peer is not None else 3) * args.steps,
                 'roofline': roofline}
         if cpu is not None:
             line['cpu_baseline'] = cpu
         print(json.dumps(line))
     if world > 1:
+        if peer is not None:
+            dist.barrier()
+            peer.close()
         dist.destroy_process_group()
     return 0
 
@@ -390,6 +432,7 @@ def main():
     ap.add_argument('--warmup', type=int, default=10)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--collective', default='peer', choices=['peer', 'nccl'])
     args = ap.parse_args()
     if args.impl == 'reference':
         return run_reference(args)

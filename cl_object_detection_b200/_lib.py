@@ -18,6 +18,12 @@ class CldetError(RuntimeError):
     pass
 
 
+class PeerExchange(ctypes.Structure):
+    """struct cldet_peer_exchange (include/cldet.h)."""
+    _fields_ = [('d_peer_terms', ctypes.c_void_p), ('d_peer_flags', ctypes.c_void_p), ('rank', ctypes.c_int32),
+                ('world', ctypes.c_int32), ('parity', ctypes.c_int32)]
+
+
 class LossParams(ctypes.Structure):
     """struct cldet_loss_params (include/cldet.h)."""
     _fields_ = [('alpha', ctypes.c_float), ('gamma', ctypes.c_float), ('incremental', ctypes.c_int32),
@@ -45,6 +51,14 @@ SIGNATURES = {
     'cldet_focal_loss_workspace_bytes': (_Z, [_I, _L]),
     'cldet_focal_loss': (_I, [_P, _P, _P, _P, _I, _L, _I, _I, ctypes.POINTER(LossParams), _P, _P, _P, _P, _P, _P, _P, _P,
                               _P, _P, _P, _P, _Z, _P]),
+    'cldet_focal_loss_sharded': (_I, [_P, _P, _P, _P, _I, _L, _I, _I, ctypes.POINTER(LossParams), _P, _P, _P, _P, _P, _P, _P,
+                                      _P, _P, _P, _P, _P, _Z, ctypes.POINTER(PeerExchange), _P]),
+    'cldet_peer_alloc': (_I, [_Z, ctypes.POINTER(ctypes.c_void_p), ctypes.c_char_p]),
+    'cldet_peer_open': (_I, [ctypes.c_char_p, ctypes.POINTER(ctypes.c_void_p)]),
+    'cldet_peer_close': (_I, [_P]),
+    'cldet_peer_free': (_I, [_P]),
+    'cldet_enable_peer_access': (_I, [_I]),
+    'cldet_peer_wait': (_I, [_P, _I, _I, _I, _P, _P]),
     'cldet_focal_loss_profile_events': (_I, [_P, _P, _P]),
     'cldet_focal_loss_from_assignment': (_I, [_P, _P, _P, _P, _I, _L, _I, _I, ctypes.POINTER(LossParams), _P, _P, _P, _P,
                                               _P, _P, _P, _P, _P, _P, _P, _Z, _P]),

@@ -1,5 +1,7 @@
 // K3 host side: C-ABI entry points of the fused focal-loss + smooth-L1 forward/backward (kernels: cldet_loss_kernels.cuh).
 // This translation unit instantiates the probabilities-in kernels; cldet_loss_logits.cu the logits-in (sigmoid-fused) ones.
+#include <string.h>
+
 #include "cldet_loss_kernels.cuh"
 
 namespace cldet {
@@ -120,7 +122,8 @@ static int loss_stage(const float* d_cls, const float* d_reg, const float* d_anc
                       int num_images, int64_t num_anchors, int num_classes, int gt_rows, const cldet_loss_params* params,
                       const float* d_weights, float* d_baked_weights, float* d_grad_cls, float* d_grad_reg, float* d_losses,
                       uint32_t* d_meta, const float* d_iou_max, const int32_t* d_npos, int32_t* d_npos_out, int32_t* d_npos_reset,
-                      uint8_t* d_bg_mask, int32_t* d_status, void* d_workspace, size_t ws_bytes, void* stream) {
+                      uint8_t* d_bg_mask, int32_t* d_status, void* d_workspace, size_t ws_bytes, void* stream,
+                      const cldet_peer_exchange* peer = nullptr) {
     int rc = check_common(d_cls, d_anchors, d_annotations, num_images, num_anchors, num_classes, gt_rows, params);
     if (rc) return rc;
     if (!d_reg || !d_losses || !d_meta || !d_npos || !d_workspace) return CLDET_ERR_INVALID_ARGUMENT;
@@ -145,6 +148,15 @@ static int loss_stage(const float* d_cls, const float* d_reg, const float* d_anc
     a.baked_weights = d_baked_weights; a.gcls = d_grad_cls; a.greg = d_grad_reg; a.losses = d_losses;
     a.meta = d_meta; a.iou_max = d_iou_max; a.npos = d_npos; a.bg_mask = d_bg_mask; a.status = d_status;
     a.npos_out = d_npos_out; a.npos_reset = d_npos_reset; a.rw_counters = nullptr;
+    a.peer_terms = nullptr; a.peer_flags = nullptr; a.rank = 0; a.world = 1; a.parity = 0;
+    if (peer && peer->world > 1) {
+        if (!peer->d_peer_terms || !peer->d_peer_flags || peer->rank < 0 || peer->rank >= peer->world || peer->world > 64 ||
+            (peer->parity != 0 && peer->parity != 1))
+            return CLDET_ERR_INVALID_ARGUMENT;
+        a.peer_terms = reinterpret_cast<float* const*>(peer->d_peer_terms);
+        a.peer_flags = reinterpret_cast<unsigned int* const*>(peer->d_peer_flags);
+        a.rank = peer->rank; a.world = peer->world; a.parity = peer->parity;
+    }
     a.counters = reinterpret_cast<unsigned int*>(d_workspace);
     a.partials = reinterpret_cast<float*>(reinterpret_cast<char*>(d_workspace) + workspace_header_bytes(num_images));
     a.anchors_per_block = pl.anchors_per_block; a.bpi = pl.bpi; a.div_magic = pl.div_magic;
@@ -174,13 +186,13 @@ int cldet_focal_loss_from_assignment(const float* d_cls, const float* d_reg, con
                       d_workspace, ws_bytes, stream);
 }
 
-int cldet_focal_loss(const float* d_cls, const float* d_reg, const float* d_anchors, const float* d_annotations,
-                     int num_images, int64_t num_anchors, int num_classes, int gt_rows,
-                     const cldet_loss_params* params, const float* d_weights, float* d_baked_weights,
-                     float* d_grad_cls, float* d_grad_reg, float* d_losses,
-                     uint32_t* d_meta, float* d_iou_max, int32_t* d_npos, int32_t* d_nvalid,
-                     uint8_t* d_bg_mask, int32_t* d_status,
-                     void* d_workspace, size_t ws_bytes, void* stream) {
+int cldet_focal_loss_sharded(const float* d_cls, const float* d_reg, const float* d_anchors, const float* d_annotations,
+                             int num_images, int64_t num_anchors, int num_classes, int gt_rows,
+                             const cldet_loss_params* params, const float* d_weights, float* d_baked_weights,
+                             float* d_grad_cls, float* d_grad_reg, float* d_losses,
+                             uint32_t* d_meta, float* d_iou_max, int32_t* d_npos, int32_t* d_nvalid,
+                             uint8_t* d_bg_mask, int32_t* d_status,
+                             void* d_workspace, size_t ws_bytes, const cldet_peer_exchange* peer, void* stream) {
     int rc = check_common(d_cls, d_anchors, d_annotations, num_images, num_anchors, num_classes, gt_rows, params);
     if (rc) return rc;
     if (!d_npos || !d_nvalid || !d_meta || !d_workspace) return CLDET_ERR_INVALID_ARGUMENT;
@@ -199,9 +211,111 @@ int cldet_focal_loss(const float* d_cls, const float* d_reg, const float* d_anch
     if (ev[1]) CLDET_CUDA_TRY(cudaEventRecord(ev[1], s));
     rc = loss_stage(d_cls, d_reg, d_anchors, d_annotations, num_images, num_anchors, num_classes, gt_rows, params, d_weights,
                       d_baked_weights, d_grad_cls, d_grad_reg, d_losses, d_meta, d_iou_max, npos_acc, d_npos, npos_acc, d_bg_mask, d_status,
-                      d_workspace, ws_bytes, stream);
+                      d_workspace, ws_bytes, stream, peer);
     if (rc) return rc;
     if (ev[2]) CLDET_CUDA_TRY(cudaEventRecord(ev[2], s));
+    return CLDET_OK;
+}
+
+int cldet_focal_loss(const float* d_cls, const float* d_reg, const float* d_anchors, const float* d_annotations,
+                     int num_images, int64_t num_anchors, int num_classes, int gt_rows,
+                     const cldet_loss_params* params, const float* d_weights, float* d_baked_weights,
+                     float* d_grad_cls, float* d_grad_reg, float* d_losses,
+                     uint32_t* d_meta, float* d_iou_max, int32_t* d_npos, int32_t* d_nvalid,
+                     uint8_t* d_bg_mask, int32_t* d_status,
+                     void* d_workspace, size_t ws_bytes, void* stream) {
+    return cldet_focal_loss_sharded(d_cls, d_reg, d_anchors, d_annotations, num_images, num_anchors, num_classes, gt_rows, params,
+                                    d_weights, d_baked_weights, d_grad_cls, d_grad_reg, d_losses, d_meta, d_iou_max, d_npos,
+                                    d_nvalid, d_bg_mask, d_status, d_workspace, ws_bytes, nullptr, stream);
+}
+
+// Consumer side of the fused all-gather: spin (bounded) until every source rank has signalled `expected` arrivals in this
+// parity's counters, then clear them for the next use of the parity.  One tiny block; later kernels on the stream see the
+// complete gather buffer.
+__global__ void peer_wait_kernel(unsigned int* flags, int world, int parity, unsigned int expected, int32_t* status) {
+    const int r = threadIdx.x;
+    bool ok = true;
+    if (r < world) {
+        volatile unsigned int* f = flags + parity * world + r;
+        long long spins = 0;
+        while (*f < expected) {
+            __nanosleep(64);
+            if (++spins > 40000000ll) {       // ~ a few seconds: a peer died or the call sequence is wrong -- do not hang the GPU
+                ok = false;
+                break;
+            }
+        }
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (r < world) {
+        if (ok) flags[parity * world + r] = 0;
+        else if (status) *status = 2;
+    }
+}
+
+// Buffers every rank of a node can map: allocated with cudaMalloc (whole allocation = one IPC handle, offset 0), exported
+// with cudaIpcGetMemHandle and opened by the peers WITH THEIR OWN DEVICE CURRENT (cudaIpcMemLazyEnablePeerAccess), which is
+// what makes the mapping dereferenceable from kernels of the opening device.
+int cldet_peer_alloc(size_t bytes, void** d_ptr, unsigned char* h_handle64) {
+    if (!d_ptr || !h_handle64 || bytes == 0) return CLDET_ERR_INVALID_ARGUMENT;
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+    void* p = nullptr;
+    CLDET_CUDA_TRY(cudaMalloc(&p, bytes));
+    cudaError_t e = cudaMemset(p, 0, bytes);
+    cudaIpcMemHandle_t h;
+    if (e == cudaSuccess) e = cudaIpcGetMemHandle(&h, p);
+    if (e != cudaSuccess) {
+        cudaFree(p);
+        CLDET_CUDA_TRY(e);
+    }
+    memcpy(h_handle64, &h, 64);
+    *d_ptr = p;
+    return CLDET_OK;
+}
+
+int cldet_peer_open(const unsigned char* h_handle64, void** d_ptr) {
+    if (!h_handle64 || !d_ptr) return CLDET_ERR_INVALID_ARGUMENT;
+    cudaIpcMemHandle_t h;
+    memcpy(&h, h_handle64, 64);
+    CLDET_CUDA_TRY(cudaIpcOpenMemHandle(d_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return CLDET_OK;
+}
+
+int cldet_peer_close(void* d_ptr) {
+    if (!d_ptr) return CLDET_OK;
+    CLDET_CUDA_TRY(cudaIpcCloseMemHandle(d_ptr));
+    return CLDET_OK;
+}
+
+int cldet_peer_free(void* d_ptr) {
+    if (!d_ptr) return CLDET_OK;
+    CLDET_CUDA_TRY(cudaFree(d_ptr));
+    return CLDET_OK;
+}
+
+int cldet_enable_peer_access(int peer_device) {
+    int cur = 0;
+    CLDET_CUDA_TRY(cudaGetDevice(&cur));
+    if (peer_device == cur) return CLDET_OK;
+    int can = 0;
+    CLDET_CUDA_TRY(cudaDeviceCanAccessPeer(&can, cur, peer_device));
+    if (!can) return CLDET_ERR_UNSUPPORTED;
+    const cudaError_t e = cudaDeviceEnablePeerAccess(peer_device, 0);
+    if (e == cudaErrorPeerAccessAlreadyEnabled) {
+        (void)cudaGetLastError();
+        return CLDET_OK;
+    }
+    CLDET_CUDA_TRY(e);
+    return CLDET_OK;
+}
+
+int cldet_peer_wait(void* d_flags_local, int world, int parity, int expected_arrivals, int32_t* d_status, void* stream) {
+    if (!d_flags_local || world < 1 || world > 64 || (parity != 0 && parity != 1) || expected_arrivals < 0)
+        return CLDET_ERR_INVALID_ARGUMENT;
+    peer_wait_kernel<<<1, 64, 0, (cudaStream_t)stream>>>(reinterpret_cast<unsigned int*>(d_flags_local), world, parity,
+                                                        (unsigned int)expected_arrivals, d_status);
+    CLDET_LAUNCH_CHECK();
     return CLDET_OK;
 }
 
@@ -230,6 +344,7 @@ static int reweight_impl(const float* d_cls, const float* d_reg, const float* d_
     a.baked_weights = d_baked_weights; a.gcls = d_grad_cls; a.greg = d_grad_reg;
     a.losses = nullptr; a.meta = d_meta; a.iou_max = d_iou_max; a.npos = d_npos; a.bg_mask = nullptr; a.status = nullptr;
     a.npos_out = nullptr; a.npos_reset = nullptr;
+    a.peer_terms = nullptr; a.peer_flags = nullptr; a.rank = 0; a.world = 1; a.parity = 0;
     a.counters = nullptr; a.partials = nullptr;
     a.rw_counters = reinterpret_cast<unsigned int*>(d_workspace) + 2 * (size_t)num_images;
     a.anchors_per_block = pl.anchors_per_block; a.bpi = pl.bpi; a.div_magic = pl.div_magic;

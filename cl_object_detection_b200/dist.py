@@ -23,6 +23,84 @@ def shard_slice(n_global, world, rank):
     return slice(start, start + sizes[rank])
 
 
+class _DevicePointer:
+    """Lets torch alias raw device memory owned by libcldet (CUDA array interface)."""
+
+    def __init__(self, ptr, numel):
+        self.__cuda_array_interface__ = {'shape': (numel,), 'typestr': '<f4', 'data': (ptr, False), 'version': 2}
+
+
+class PeerGather:
+    """Per-process state of the FUSED all-gather (include/cldet.h, cldet_focal_loss_sharded): a gather buffer
+    float[2][world][4][N] plus arrival counters uint32[2][world], allocated by libcldet (cudaMalloc), exported with CUDA IPC
+    and opened by every other rank of the group with ITS device current, so that kernels there can store into it over NVLink.
+    The loss kernel's last block per image writes the image's four terms straight into every rank's buffer; `wait()` enqueues
+    the tiny kernel that blocks the stream until all ranks have delivered."""
+
+    def __init__(self, n_local, device, group=None):
+        import ctypes
+
+        from . import _lib
+        lib = _lib.load()
+        self._lib = _lib
+        self.group = group
+        self.world = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+        self.n = int(n_local)
+        self.device = device
+        n_terms = 2 * self.world * 4 * self.n
+        self._flag_off = n_terms + ((-n_terms) % 64)
+        numel = self._flag_off + 2 * self.world + 64
+        with torch.cuda.device(device):
+            ptr = ctypes.c_void_p()
+            hbuf = ctypes.create_string_buffer(64)
+            _lib.check(lib.cldet_peer_alloc(4 * numel, ctypes.byref(ptr), hbuf))
+            self._own = ptr.value
+            handles = [None] * self.world
+            dist.all_gather_object(handles, hbuf.raw, group=group)
+            self._opened = []
+            base_ptrs = []
+            for r in range(self.world):
+                if r == self.rank:
+                    base_ptrs.append(self._own)
+                    continue
+                q = ctypes.c_void_p()
+                _lib.check(lib.cldet_peer_open(handles[r], ctypes.byref(q)))
+                self._opened.append(q.value)
+                base_ptrs.append(q.value)
+            self.buf = torch.as_tensor(_DevicePointer(self._own, numel), device=device)      # aliases libcldet's memory
+            self.term_ptrs = torch.tensor(base_ptrs, dtype=torch.int64, device=device)
+            self.flag_ptrs = torch.tensor([p + 4 * self._flag_off for p in base_ptrs], dtype=torch.int64, device=device)
+            self.status = torch.zeros(1, dtype=torch.int32, device=device)
+        self.parity = 0
+        torch.cuda.synchronize(device)
+        dist.barrier(group=group)                       # every rank has zeroed, exported and mapped its buffers
+
+    def exchange(self):
+        return self._lib.PeerExchange(self.term_ptrs.data_ptr(), self.flag_ptrs.data_ptr(), self.rank, self.world, self.parity)
+
+    def wait(self, stream):
+        """Block `stream` until this parity's gather is complete, then advance the parity.  Returns the [world,4,N] view."""
+        flags_ptr = self._own + 4 * self._flag_off
+        self._lib.check(self._lib.load().cldet_peer_wait(flags_ptr, self.world, self.parity, self.n, self.status.data_ptr(), stream))
+        block = self.world * 4 * self.n
+        view = self.buf[self.parity * block:(self.parity + 1) * block].view(self.world, 4, self.n)
+        self.parity ^= 1
+        return view
+
+    def close(self):
+        """Unmap the peers' buffers and free this rank's (call on every rank, after a barrier)."""
+        lib = self._lib.load()
+        with torch.cuda.device(self.device):
+            torch.cuda.synchronize(self.device)
+            for p in self._opened:
+                lib.cldet_peer_close(p)
+            self._opened = []
+            if self._own:
+                lib.cldet_peer_free(self._own)
+                self._own = 0
+
+
 class _GatherTerms(torch.autograd.Function):
     """local [K, n_r] -> global [K, N] in rank order.  Backward hands each rank the slice of the incoming gradient
     that belongs to its own images: the loss every rank forms from the gathered terms is the same function, so
@@ -64,13 +142,33 @@ class ShardedFocalLoss(nn.Module):
     the single-process gradient (with DDP's averaging, scale the loss by world_size).
     """
 
-    def __init__(self, local_loss=None, group=None):
+    def __init__(self, local_loss=None, group=None, use_peer_memory=True):
         super().__init__()
         if local_loss is None:
             from .losses import FocalLoss
             local_loss = FocalLoss(upstream_hint='mean')
         self.local_loss = local_loss
         self.group = group
+        self.use_peer_memory = use_peer_memory
+        self._peer = {}          # n_local -> PeerGather, or False when the mapping could not be set up
+
+    def _peer_for(self, n_local, sizes, device):
+        """Fused all-gather over peer memory needs equal shards, CUDA tensors and the built-in FocalLoss."""
+        from .losses import FocalLoss
+        if not self.use_peer_memory or device.type != 'cuda' or not isinstance(self.local_loss, FocalLoss):
+            return None
+        if len(set(sizes)) != 1:
+            return None
+        if n_local not in self._peer:
+            try:
+                self._peer[n_local] = PeerGather(n_local, device, self.group)
+            except Exception:     # no IPC between the ranks (different nodes / containers): use the NCCL all-gather
+                self._peer[n_local] = False
+            ok = torch.tensor([1 if self._peer[n_local] else 0], device=device)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=self.group)
+            if int(ok.item()) == 0:
+                self._peer[n_local] = False
+        return self._peer[n_local] or None
 
     def forward(self, classifications, regressions, anchors, annotations, cur_state, params, progress=-1):
         world = dist.get_world_size(self.group) if dist.is_initialized() else 1
@@ -84,6 +182,18 @@ class ShardedFocalLoss(nn.Module):
         else:
             sizes = [n_local]
         n_global = sum(sizes)
+        peer = self._peer_for(n_local, sizes, classifications.device) if world > 1 else None
+        if peer is not None:
+            # fused path: the loss kernel scatters the per-image terms to every rank; the result already holds GLOBAL rows
+            w = torch.full((4, n_local), 1.0 / n_global, dtype=torch.float32, device=classifications.device)
+            w[3] = 1.0
+            old = self.local_loss.upstream_hint
+            self.local_loss.upstream_hint = w
+            try:
+                out = self.local_loss(classifications, regressions, anchors, annotations, cur_state, params, progress, peer=peer)
+            finally:
+                self.local_loss.upstream_hint = old
+            return out       # rows are already global: FocalLoss formed reg_loss / enhance over all N images
         if hasattr(self.local_loss, 'upstream_hint') and isinstance(self.local_loss.upstream_hint, str):
             # the caller's mean runs over the GLOBAL batch: bake 1/N_global into the fused gradients
             w = torch.full((4, n_local), 1.0 / n_global, dtype=torch.float32, device=classifications.device)

@@ -119,7 +119,7 @@ class _FocalLossFn(torch.autograd.Function):
     """outputs: bg[N], fg[N], reg_per_image[N], enhance_per_image[N] (rows of the kernel's [4,N] result)."""
 
     @staticmethod
-    def forward(ctx, cls, reg, anchors, annotations, lp, hint, want_bg_mask, check_labels):
+    def forward(ctx, cls, reg, anchors, annotations, lp, hint, want_bg_mask, check_labels, peer=None):
         lib = _lib.load()
         n, a, c = cls.shape
         g = annotations.shape[1]
@@ -144,11 +144,22 @@ class _FocalLossFn(torch.autograd.Function):
             else:
                 weights = baked = gcls = greg = None
             try:
-                _lib.check(lib.cldet_focal_loss(
-                    cls.data_ptr(), reg.data_ptr(), anchors.data_ptr(), annotations.data_ptr(), n, a, c, g, lp,
-                    _lib.ptr(weights), _lib.ptr(baked), _lib.ptr(gcls), _lib.ptr(greg), losses.data_ptr(), meta.data_ptr(),
-                    _lib.ptr(iou_max), npos.data_ptr(), nvalid.data_ptr(), _lib.ptr(bg_mask), _lib.ptr(status),
-                    ws.data_ptr(), ws_bytes, stream))
+                if peer is None:
+                    _lib.check(lib.cldet_focal_loss(
+                        cls.data_ptr(), reg.data_ptr(), anchors.data_ptr(), annotations.data_ptr(), n, a, c, g, lp,
+                        _lib.ptr(weights), _lib.ptr(baked), _lib.ptr(gcls), _lib.ptr(greg), losses.data_ptr(), meta.data_ptr(),
+                        _lib.ptr(iou_max), npos.data_ptr(), nvalid.data_ptr(), _lib.ptr(bg_mask), _lib.ptr(status),
+                        ws.data_ptr(), ws_bytes, stream))
+                else:
+                    # image-sharded: the kernel's epilogue pushes every image's terms into all ranks' gather buffers
+                    ex = peer.exchange()
+                    _lib.check(lib.cldet_focal_loss_sharded(
+                        cls.data_ptr(), reg.data_ptr(), anchors.data_ptr(), annotations.data_ptr(), n, a, c, g, lp,
+                        _lib.ptr(weights), _lib.ptr(baked), _lib.ptr(gcls), _lib.ptr(greg), losses.data_ptr(), meta.data_ptr(),
+                        _lib.ptr(iou_max), npos.data_ptr(), nvalid.data_ptr(), _lib.ptr(bg_mask), _lib.ptr(status),
+                        ws.data_ptr(), ws_bytes, ex, stream))
+                    gathered = peer.wait(stream)                                   # [world, 4, n]
+                    losses = gathered.permute(1, 0, 2).reshape(4, peer.world * n)   # global image order, private copy
             except Exception:
                 _drop_workspaces()      # a failed call may leave the scratch header dirty
                 raise
@@ -157,6 +168,7 @@ class _FocalLossFn(torch.autograd.Function):
                              '(losses.py:341)' % c)
         ctx.lp = lp
         ctx.shape = (n, a, c, g)
+        ctx.local = None if peer is None else slice(peer.rank * n, (peer.rank + 1) * n)   # my images inside the global rows
         ctx.backward_calls = 0
         if need_grad:
             ctx.save_for_backward(cls, reg, anchors, annotations, baked, gcls, greg, meta, npos)
@@ -174,6 +186,8 @@ class _FocalLossFn(torch.autograd.Function):
         cls, reg, anchors, annotations, baked, gcls, greg, meta, npos = ctx.saved_tensors
         n, a, c, g = ctx.shape
         dev = cls.device
+        if ctx.local is not None:        # global rows came back: only the slice of this rank's images feeds its gradients
+            g_bg, g_fg, g_reg, g_enh = (None if t is None else t[ctx.local] for t in (g_bg, g_fg, g_reg, g_enh))
         rows = [_row(t) for t in (g_bg, g_fg, g_reg, g_enh)]      # keeps converted tensors alive until the call returns
         with _DeviceGuard(dev):
             _lib.check(_lib.load().cldet_focal_loss_reweight_rows(
@@ -183,8 +197,8 @@ class _FocalLossFn(torch.autograd.Function):
                 _lib.ptr(ctx.iou_max), npos.data_ptr(), ctx.ws.data_ptr(), ctx.ws.numel(), _stream()))
         ctx.backward_calls += 1
         if ctx.backward_calls > 1:   # the buffers may already be someone's .grad: hand out copies from now on
-            return gcls.clone(), greg.clone(), None, None, None, None, None, None
-        return gcls, greg, None, None, None, None, None, None
+            return gcls.clone(), greg.clone(), None, None, None, None, None, None, None
+        return gcls, greg, None, None, None, None, None, None, None
 
 
 class FocalLoss(nn.Module):
@@ -230,7 +244,7 @@ class FocalLoss(nn.Module):
             self._hint_cache[key] = w
         return w
 
-    def forward(self, classifications, regressions, anchors, annotations, cur_state: int, params, progress=-1):
+    def forward(self, classifications, regressions, anchors, annotations, cur_state: int, params, progress=-1, peer=None):
         cls = _check_cuda_f32('classifications', classifications)
         reg = _check_cuda_f32('regressions', regressions)
         anc = _check_cuda_f32('anchors', anchors)
@@ -248,7 +262,7 @@ class FocalLoss(nn.Module):
         lp.cls_is_logits = int(self.from_logits)
         incremental = cur_state > 0
         want_mask = bool(incremental and params['distill'])
-        outs = _FocalLossFn.apply(cls, reg, anc, ann, lp, self._hint(n, cls.device), want_mask, self.check_labels)
+        outs = _FocalLossFn.apply(cls, reg, anc, ann, lp, self._hint(n, cls.device), want_mask, self.check_labels, peer)
         bg, fg, reg_j, enh_j, npos, nvalid = outs[:6]
         result = {'cls_loss': (bg, fg), 'reg_loss': reg_j.mean(dim=0, keepdim=True)}   # losses.py:444-445
         if incremental:

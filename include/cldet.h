@@ -130,6 +130,37 @@ int cldet_focal_loss(const float* d_cls, const float* d_reg, const float* d_anch
                      uint8_t* d_bg_mask, int32_t* d_status,
                      void* d_workspace, size_t workspace_bytes, void* stream);
 
+/* ---- image-sharded runs: fused loss + all-gather over NVLink peer memory ----
+ * Every rank owns a gather buffer float[2][world][4][N] and arrival counters uint32[2][world] (both zero-initialised) that
+ * all ranks have mapped (CUDA IPC / symmetric memory).  With a peer exchange, the loss kernel's last block per image stores
+ * that image's four terms into slot [parity][rank] of EVERY rank's buffer (peer stores) and signals one arrival per
+ * destination -- there is no separate collective launch.  cldet_peer_wait then blocks the stream until all `world` source
+ * ranks have delivered `expected_arrivals` (= N) terms for this parity and clears the counters; alternate parity 0/1 between
+ * consecutive steps.  All ranks must use the same N. */
+typedef struct cldet_peer_exchange {
+    void* d_peer_terms;   /* device array of `world` float*  : rank p's gather buffer, as mapped in THIS process */
+    void* d_peer_flags;   /* device array of `world` uint32* : rank p's arrival counters */
+    int32_t rank, world, parity;
+} cldet_peer_exchange;
+int cldet_focal_loss_sharded(const float* d_cls, const float* d_reg, const float* d_anchors, const float* d_annotations,
+                             int num_images, int64_t num_anchors, int num_classes, int gt_rows,
+                             const cldet_loss_params* params, const float* d_weights, float* d_baked_weights,
+                             float* d_grad_cls, float* d_grad_reg, float* d_losses,
+                             uint32_t* d_meta, float* d_iou_max, int32_t* d_npos, int32_t* d_nvalid,
+                             uint8_t* d_bg_mask, int32_t* d_status,
+                             void* d_workspace, size_t workspace_bytes, const cldet_peer_exchange* peer, void* stream);
+/* Node-shared buffers for the peer exchange.  cldet_peer_alloc: cudaMalloc + zero + export (64-byte cudaIpcMemHandle_t copied
+ * to h_handle64); cldet_peer_open: map a peer rank's buffer into this process WITH THE CALLER'S DEVICE CURRENT (lazy peer
+ * access), returning a pointer kernels of that device can dereference; cldet_peer_close / cldet_peer_free undo them. */
+int cldet_peer_alloc(size_t bytes, void** d_ptr, unsigned char* h_handle64);
+int cldet_peer_open(const unsigned char* h_handle64, void** d_ptr);
+int cldet_peer_close(void* d_ptr);
+int cldet_peer_free(void* d_ptr);
+/* Let kernels of the CURRENT device dereference memory of `peer_device` (cudaDeviceEnablePeerAccess; already-enabled is ok). */
+int cldet_enable_peer_access(int peer_device);
+/* d_status (may be NULL) is set to 2 if a peer never arrives (bounded spin, the GPU is not left hanging). */
+int cldet_peer_wait(void* d_flags_local, int world, int parity, int expected_arrivals, int32_t* d_status, void* stream);
+
 /* Profiling hook (per host thread, one-shot): the next cldet_focal_loss call of THIS thread records the given
  * cudaEvent_t handles before the assign kernel, between the two kernels and after the loss kernel, on its stream.
  * NULL = do not record.  Lets a benchmark time each kernel inside the real fused call. */

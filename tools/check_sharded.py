@@ -31,7 +31,9 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device('cuda', local)
     dist.init_process_group('nccl', device_id=dev)
-    h, w, c, n_global, g = 512, 512, 20, 5 * world + 1, 12         # uneven shards on purpose
+    equal = os.environ.get('CLDET_EQUAL_SHARDS', '0') == '1'        # equal shards take the fused peer-memory all-gather
+    h, w, c, g = 512, 512, 20, 12
+    n_global = 4 * world if equal else 5 * world + 1               # uneven shards on purpose (NCCL all-gather path)
     anchors = cld.generate_anchors(h, w, dev)
     a = anchors.shape[1]
     gen = torch.Generator(device='cpu').manual_seed(77)
@@ -42,7 +44,14 @@ def main():
     sl = cld.shard_slice(n_global, world, rank)
     p = probs[sl].to(dev).requires_grad_(True)
     r = reg[sl].to(dev).requires_grad_(True)
-    out = cld.ShardedFocalLoss()(p, r, anchors, ann[sl].to(dev), 0, params)
+    sharded = cld.ShardedFocalLoss()
+    out = sharded(p, r, anchors, ann[sl].to(dev), 0, params)
+    used_peer = bool(sharded._peer and any(v for v in sharded._peer.values()))
+    if equal:      # run twice more: exercises both parities of the gather buffer and the counter reset
+        for _ in range(2):
+            p.grad = None
+            r.grad = None
+            out = sharded(p, r, anchors, ann[sl].to(dev), 0, params)
     clip = 0.5 * float(out['cls_loss'][1].detach().median())
     loss = caller_reduction(out, clip)
     loss.backward()
@@ -60,7 +69,7 @@ def main():
     assert torch.allclose(r.grad, r0.grad[sl], rtol=1e-6, atol=1e-12), 'reg gradient differs'
     dist.barrier()
     if rank == 0:
-        print('sharded loss ok: world=%d n_global=%d loss=%.6f' % (world, n_global, float(loss)))
+        print('sharded loss ok: world=%d n_global=%d loss=%.6f fused_peer_allgather=%s' % (world, n_global, float(loss), used_peer))
     dist.destroy_process_group()
 
 
