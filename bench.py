@@ -387,7 +387,7 @@ def run_ours(args):
     achieved = kernel_bytes / (loss_ms * 1e-3) / 1e9
     traffic = ncu_traffic('focal_loss_kernel')
     roofline = {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
-                'traffic': traffic, 'kernel': 'focal_loss_kernel<4,true,false,true>', 'kernel_ms': loss_ms,
+                'traffic': traffic, 'kernel': 'focal_loss_kernel<VEC=8,GAMMA2,no IL variants,GRAD,probabilities> (256-bit LDG/STG)', 'kernel_ms': loss_ms,
                 'assign_kernel_ms': assign_ms, 'algorithmic_bytes_per_launch': kernel_bytes, 'peak_source': peak_src,
                 'path_frac': path_bytes / ((loss_ms + assign_ms) * 1e-3) / 1e9 / peak,
                 'step_frac': path_bytes / (ms_per_step * 1e-3) / 1e9 / peak}
