@@ -225,6 +225,7 @@ def run_ours(args):
     ann = torch.from_numpy(ann_np).to(dev)
     params = cld.HeadParams()
     lp = to_loss_params(params, 0, C)
+    lp.image_height, lp.image_width = H, W          # the anchors are the standard grid: GT-centric assignment
 
     # ---- device-resident step through the C ABI, stage by stage so the loss kernel can be event-timed ----
     n_global = n * world

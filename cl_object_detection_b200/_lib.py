@@ -29,7 +29,8 @@ class LossParams(ctypes.Structure):
     _fields_ = [('alpha', ctypes.c_float), ('gamma', ctypes.c_float), ('incremental', ctypes.c_int32),
                 ('past_class_num', ctypes.c_int32), ('ignore_past_class', ctypes.c_int32),
                 ('new_ignore_past_class', ctypes.c_int32), ('decrease_positive_by_iou', ctypes.c_int32),
-                ('enhance_on_new', ctypes.c_int32), ('decrease_positive', ctypes.c_float), ('cls_is_logits', ctypes.c_int32)]
+                ('enhance_on_new', ctypes.c_int32), ('decrease_positive', ctypes.c_float), ('image_height', ctypes.c_int32),
+                ('image_width', ctypes.c_int32), ('cls_is_logits', ctypes.c_int32)]
 
 
 _P = ctypes.c_void_p

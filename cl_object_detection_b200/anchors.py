@@ -4,11 +4,38 @@ per (H, W, device) -- the reference recomputes it with numpy on the host and upl
 """
 import ctypes
 import threading
+import weakref
 
 import torch
 import torch.nn as nn
 
 from . import _lib
+
+
+# anchors tensors produced here, by storage address: lets FocalLoss know that an `anchors` argument is the standard grid of
+# an (H, W) image, which unlocks the GT-centric assignment kernel (include/cldet.h, cldet_loss_params.image_height)
+_GRIDS = {}
+_GRIDS_LOCK = threading.Lock()
+
+
+def _register_grid(t, height, width):
+    with _GRIDS_LOCK:
+        if len(_GRIDS) > 64:
+            for k in [k for k, (ref, _, _) in _GRIDS.items() if ref() is None]:
+                del _GRIDS[k]
+        _GRIDS[t.data_ptr()] = (weakref.ref(t), int(height), int(width))
+
+
+def grid_of(anchors):
+    """(height, width) if `anchors` is (a view of) a live tensor made by generate_anchors / Anchors, else None."""
+    hit = _GRIDS.get(anchors.data_ptr())
+    if hit is None:
+        return None
+    ref, h, w = hit
+    t = ref()
+    if t is None or t.numel() != anchors.numel() or t.device != anchors.device:
+        return None
+    return h, w
 
 
 def num_anchors(height, width):
@@ -27,6 +54,7 @@ def generate_anchors(height, width, device=None):
     with torch.cuda.device(device):
         out = torch.empty((1, a, 4), dtype=torch.float32, device=device)
         _lib.check(lib.cldet_anchors(int(height), int(width), out.data_ptr(), torch.cuda.current_stream().cuda_stream))
+    _register_grid(out, height, width)
     return out
 
 

@@ -318,6 +318,118 @@ calc_iou_kernel(const float4* __restrict__ a, int64_t na, const float4* __restri
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// K2' GT-centric assignment (used by the fused loss call when the anchors are the standard grid of a known image size).
+//
+// IoU >= 0.4 forces  iw >= 0.4*max(w_a, w_g)  and  ih >= 0.4*max(h_a, h_g)  (I >= 0.4*U >= 0.4*max(area), and the
+// intersection is no wider/taller than either box), while  iw <= (w_a + w_g)/2 - |cx_a - cx_g|.  So for a GT box only the
+// anchor types (level, ratio, scale) with min(w)/max(w) >= 0.4 and min(h)/max(h) >= 0.4 matter, and of those only the cells
+// whose centre is within  (w_a + w_g)/2 - 0.4*max(w_a, w_g)  of the GT centre (same in y).  That is a few hundred anchors
+// per GT instead of all 200 k.  Everything visited gets the EXACT reference IoU (same fp32 op order) folded into
+// best[anchor] with a 64-bit integer atomicMax on the key (IoU bits << 32 | ~GT row): IoU >= 0, so float bits order like
+// unsigned integers, and among equal IoUs the SMALLEST row wins -- torch.max's first maximal index.  For every anchor whose
+// true maximum is >= 0.4 the stored key is exactly (maximum, argmax); all others stay below 0.4 = background.  The bounds use 0.39
+// plus slack and one extra cell on each side, so rounding can only ADD candidates.
+// ------------------------------------------------------------------------------------------------
+struct ScatterPlan {
+    float type_w[kNumLevels][kAnchorsPerCell];
+    float type_h[kNumLevels][kAnchorsPerCell];
+    int64_t level_offset[kNumLevels + 1];
+    int level_w[kNumLevels];
+    int level_h[kNumLevels];
+    int stride[kNumLevels];
+};
+
+__global__ void __launch_bounds__(128)
+gt_scatter_kernel(const ScatterPlan plan, const float4* __restrict__ anchors, int64_t A, const float* __restrict__ annotations,
+                  int G, unsigned long long* __restrict__ best, int32_t* __restrict__ npos_acc, int32_t* __restrict__ nvalid) {
+    // grid = (GT row, image, pyramid level): one block visits the candidate anchors of one GT box on one level
+    const int j = blockIdx.y;
+    const int l = blockIdx.z;
+    const float* ann = annotations + (int64_t)j * G * 5;
+    if (blockIdx.x == 0 && l == 0) {                         // valid rows of the image (label != -1, losses.py:288)
+        __shared__ int s_cnt[4];
+        int c = 0;
+        for (int g = threadIdx.x; g < G; g += blockDim.x) c += (ann[(int64_t)g * 5 + 4] != -1.0f) ? 1 : 0;
+        c = warp_sum_int(c);
+        if ((threadIdx.x & 31) == 0) s_cnt[threadIdx.x >> 5] = c;
+        __syncthreads();
+        if (threadIdx.x == 0) nvalid[j] = s_cnt[0] + s_cnt[1] + s_cnt[2] + s_cnt[3];
+    }
+    const int g = blockIdx.x;
+    const float* r = ann + (int64_t)g * 5;
+    if (r[4] == -1.0f) return;                               // padding row
+    const float gx1 = r[0], gy1 = r[1], gx2 = r[2], gy2 = r[3];
+    const float gw = gx2 - gx1, gh = gy2 - gy1;
+    if (!(gw > 0.0f) || !(gh > 0.0f)) return;                // degenerate box: IoU is 0 (or NaN) with every anchor
+    const float area_g = gw * gh;
+    const float gcx = 0.5f * (gx1 + gx2), gcy = 0.5f * (gy1 + gy2);
+    const float s = (float)plan.stride[l];
+    const int wl = plan.level_w[l], hl = plan.level_h[l];
+
+    // candidate cell window of each of the 9 anchor types of this level (block-uniform), flattened into one index space
+    __shared__ int s_x0[kAnchorsPerCell], s_y0[kAnchorsPerCell], s_nx[kAnchorsPerCell], s_first[kAnchorsPerCell + 1];
+    if (threadIdx.x < kAnchorsPerCell) {
+        const int k = threadIdx.x;
+        const float wa = plan.type_w[l][k], ha = plan.type_h[l][k];
+        int cells = 0, x0 = 0, y0 = 0, nx = 0;
+        // type filter (0.39 < 0.4: conservative)
+        if (!(fminf(wa, gw) < 0.39f * fmaxf(wa, gw) || fminf(ha, gh) < 0.39f * fmaxf(ha, gh))) {
+            const float dx = 0.5f * (wa + gw) - 0.39f * fmaxf(wa, gw) + 1e-3f * (wa + gw) + 0.05f;
+            const float dy = 0.5f * (ha + gh) - 0.39f * fmaxf(ha, gh) + 1e-3f * (ha + gh) + 0.05f;
+            // cell centres (x + 0.5) * s within [gc - d, gc + d], one extra cell on each side
+            x0 = max((int)floorf((gcx - dx) / s - 0.5f) - 1, 0);
+            y0 = max((int)floorf((gcy - dy) / s - 0.5f) - 1, 0);
+            const int x1 = min((int)ceilf((gcx + dx) / s - 0.5f) + 1, wl - 1);
+            const int y1 = min((int)ceilf((gcy + dy) / s - 0.5f) + 1, hl - 1);
+            if (x1 >= x0 && y1 >= y0) {
+                nx = x1 - x0 + 1;
+                cells = nx * (y1 - y0 + 1);
+            }
+        }
+        s_x0[k] = x0; s_y0[k] = y0; s_nx[k] = nx;
+        s_first[k + 1] = cells;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        s_first[0] = 0;
+        for (int k = 0; k < kAnchorsPerCell; ++k) s_first[k + 1] += s_first[k];
+    }
+    __syncthreads();
+    const int total = s_first[kAnchorsPerCell];
+    unsigned long long* best_j = best + (int64_t)j * A;
+    const unsigned long long low = 0xFFFFFFFFull - (unsigned long long)g;      // ties -> smallest row wins the max
+    int crossings = 0;
+    for (int c = threadIdx.x; c < total; c += blockDim.x) {
+        int k = 0;
+#pragma unroll
+        for (int t = 1; t < kAnchorsPerCell; ++t) k += (c >= s_first[t]) ? 1 : 0;
+        const int rel = c - s_first[k];
+        const int nx = s_nx[k];
+        const int yy = s_y0[k] + rel / nx, xx = s_x0[k] + (rel - (rel / nx) * nx);
+        const int64_t idx = plan.level_offset[l] + ((int64_t)yy * wl + xx) * kAnchorsPerCell + k;
+        const float4 an = anchors[idx];
+        // exact calc_iou (losses.py:4-21), this translation unit is built with -fmad=false
+        const float iw = fminf(an.z, gx2) - fmaxf(an.x, gx1);
+        const float ih = fminf(an.w, gy2) - fmaxf(an.y, gy1);
+        if (iw > 0.0f && ih > 0.0f) {
+            const float area_a = (an.z - an.x) * (an.w - an.y);
+            const float inter = iw * ih;
+            float ua = (area_a + area_g) - inter;
+            ua = fmaxf(ua, 1e-8f);
+            const float v = __fdiv_rn(inter, ua);
+            if (v >= 0.39f) {                                   // lower values cannot change any anchor's state
+                const unsigned long long key = ((unsigned long long)__float_as_uint(v) << 32) | low;
+                const unsigned long long old = atomicMax(best_j + idx, key);
+                // the anchor becomes positive exactly once: when its maximum first reaches 0.5 (losses.py:330)
+                if ((uint32_t)(old >> 32) < 0x3f000000u && v >= 0.5f) ++crossings;
+            }
+        }
+    }
+    crossings = warp_sum_int(crossings);
+    if ((threadIdx.x & 31) == 0 && crossings) atomicAdd(&npos_acc[j], crossings);
+}
+
 // fp64 IoU + max over the second set (IL_method/persuado_label.py:68-72: calc_iou on float64 annotations, .max(dim=1))
 __global__ void __launch_bounds__(128)
 iou_max_f64_kernel(const double* __restrict__ a, int64_t na, const double* __restrict__ b, int nb, double* __restrict__ out_max,
@@ -342,6 +454,38 @@ iou_max_f64_kernel(const double* __restrict__ a, int64_t na, const double* __res
     }
     out_max[i] = best;
     if (out_arg) out_arg[i] = arg;
+}
+
+}  // namespace cldet
+
+namespace cldet {
+
+int launch_gt_scatter(int height, int width, const float* d_anchors, int64_t num_anchors, const float* d_annotations,
+                      int num_images, int gt_rows, unsigned long long* d_best, int32_t* d_npos_acc, int32_t* d_nvalid,
+                      cudaStream_t s) {
+    AnchorPlan ap;
+    build_anchor_plan(height, width, &ap);
+    if (ap.level_offset[kNumLevels] != num_anchors) return CLDET_ERR_UNSUPPORTED;
+    ScatterPlan sp;
+    for (int l = 0; l < kNumLevels; ++l) {
+        for (int k = 0; k < kAnchorsPerCell; ++k) {
+            sp.type_w[l][k] = (float)(ap.base[l][k][2] - ap.base[l][k][0]);
+            sp.type_h[l][k] = (float)(ap.base[l][k][3] - ap.base[l][k][1]);
+        }
+        sp.level_offset[l] = ap.level_offset[l];
+        sp.level_w[l] = ap.level_w[l];
+        sp.stride[l] = ap.stride[l];
+        sp.level_h[l] = (height + ap.stride[l] - 1) / ap.stride[l];
+    }
+    sp.level_offset[kNumLevels] = ap.level_offset[kNumLevels];
+    dim3 grid((unsigned)gt_rows, (unsigned)num_images, (unsigned)kNumLevels);
+    gt_scatter_kernel<<<grid, 128, 0, s>>>(sp, reinterpret_cast<const float4*>(d_anchors), num_anchors, d_annotations, gt_rows,
+                                           d_best, d_npos_acc, d_nvalid);
+    if (cudaPeekAtLastError() != cudaSuccess) {
+        set_last_cuda_error(cudaGetLastError());
+        return CLDET_ERR_CUDA;
+    }
+    return CLDET_OK;
 }
 
 }  // namespace cldet

@@ -56,6 +56,15 @@ __device__ __forceinline__ void st_stream_f4(float4* p, const float4& v) {
                  : "memory");
 }
 
+// GT-centric assignment for the standard anchor grid of an (height, width) image (cldet_assign.cu): for every valid GT row,
+// visit only the anchors that can reach IoU >= 0.4 with it and atomicMax the key (exact IoU bits << 32 | ~row) into best[N,A]
+// (zero on entry);
+// counts anchors crossing 0.5 into npos_acc and valid rows into nvalid.  Returns CLDET_ERR_UNSUPPORTED when A does not match
+// the grid of (height, width).
+int launch_gt_scatter(int height, int width, const float* d_anchors, int64_t num_anchors, const float* d_annotations,
+                      int num_images, int gt_rows, unsigned long long* d_best, int32_t* d_npos_acc, int32_t* d_nvalid,
+                      cudaStream_t s);
+
 inline int sm_count() {
     int dev = 0, n = 148;
     if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);

@@ -68,10 +68,15 @@ struct Workspace {
 // must be zero before the first call and are left zero by every call.
 static size_t workspace_header_bytes(int N) { return ((size_t)N * 3 * sizeof(unsigned int) + 255) / 256 * 256; }
 
-static size_t workspace_bytes(int N, int64_t A) {
+static size_t workspace_partials_bytes(int N, int64_t A) {
     // worst case bpi: 32 anchors per block
     const int64_t max_bpi = (A + 31) / 32;
-    return workspace_header_bytes(N) + (size_t)N * max_bpi * 4 * sizeof(float) + 256;
+    return ((size_t)N * max_bpi * 4 * sizeof(float) + 255) / 256 * 256;
+}
+
+// [header | partials | best: N*A uint64 (IoU_max bits, ~row) keys of the GT-centric assignment (zero between calls)]
+static size_t workspace_bytes(int N, int64_t A) {
+    return workspace_header_bytes(N) + workspace_partials_bytes(N, A) + (size_t)N * A * sizeof(unsigned long long) + 256;
 }
 
 // widest vector the class map allows: rows must be a whole number of vectors and the buffers aligned to the vector
@@ -123,7 +128,8 @@ static int loss_stage(const float* d_cls, const float* d_reg, const float* d_anc
                       const float* d_weights, float* d_baked_weights, float* d_grad_cls, float* d_grad_reg, float* d_losses,
                       uint32_t* d_meta, const float* d_iou_max, const int32_t* d_npos, int32_t* d_npos_out, int32_t* d_npos_reset,
                       uint8_t* d_bg_mask, int32_t* d_status, void* d_workspace, size_t ws_bytes, void* stream,
-                      const cldet_peer_exchange* peer = nullptr) {
+                      const cldet_peer_exchange* peer = nullptr, unsigned long long* d_best = nullptr, const int32_t* d_nvalid = nullptr,
+                      float* d_iou_out = nullptr) {
     int rc = check_common(d_cls, d_anchors, d_annotations, num_images, num_anchors, num_classes, gt_rows, params);
     if (rc) return rc;
     if (!d_reg || !d_losses || !d_meta || !d_npos || !d_workspace) return CLDET_ERR_INVALID_ARGUMENT;
@@ -148,6 +154,7 @@ static int loss_stage(const float* d_cls, const float* d_reg, const float* d_anc
     a.baked_weights = d_baked_weights; a.gcls = d_grad_cls; a.greg = d_grad_reg; a.losses = d_losses;
     a.meta = d_meta; a.iou_max = d_iou_max; a.npos = d_npos; a.bg_mask = d_bg_mask; a.status = d_status;
     a.npos_out = d_npos_out; a.npos_reset = d_npos_reset; a.rw_counters = nullptr;
+    a.best = d_best; a.meta_out = d_meta; a.iou_out = d_iou_out; a.nvalid = d_nvalid;
     a.peer_terms = nullptr; a.peer_flags = nullptr; a.rank = 0; a.world = 1; a.parity = 0;
     if (peer && peer->world > 1) {
         if (!peer->d_peer_terms || !peer->d_peer_flags || peer->rank < 0 || peer->rank >= peer->world || peer->world > 64 ||
@@ -205,13 +212,29 @@ int cldet_focal_loss_sharded(const float* d_cls, const float* d_reg, const float
     cudaEvent_t ev[3] = {g_prof_events[0], g_prof_events[1], g_prof_events[2]};
     g_prof_events[0] = g_prof_events[1] = g_prof_events[2] = nullptr;      // one-shot
     if (ev[0]) CLDET_CUDA_TRY(cudaEventRecord(ev[0], s));
-    rc = cldet_iou_assign(d_anchors, num_anchors, d_annotations, num_images, gt_rows, num_classes, d_meta, nullptr,
-                          d_iou_max, npos_acc, d_nvalid, stream);
-    if (rc) return rc;
+    // Standard anchor grid of a known image size: GT-centric assignment (a few hundred anchors per GT box instead of A x G
+    // pairs); the loss kernel turns the IoU_max bits into assignment words itself.  The new_ignore_past_class pre-pass needs
+    // ready-made words, and arbitrary anchor sets have no grid: both use the anchor-centric kernel.
+    unsigned long long* best = nullptr;
+    const bool needs_words = params->incremental && params->ignore_past_class && params->new_ignore_past_class &&
+                             params->past_class_num > 0;
+    if (params->image_height > 0 && params->image_width > 0 && !needs_words) {
+        best = reinterpret_cast<unsigned long long*>(reinterpret_cast<char*>(d_workspace) + workspace_header_bytes(num_images) +
+                                           workspace_partials_bytes(num_images, num_anchors));
+        rc = launch_gt_scatter(params->image_height, params->image_width, d_anchors, num_anchors, d_annotations, num_images,
+                               gt_rows, best, npos_acc, d_nvalid, s);
+        if (rc == CLDET_ERR_UNSUPPORTED) best = nullptr;      // anchors are not this image size's grid
+        else if (rc) return rc;
+    }
+    if (!best) {
+        rc = cldet_iou_assign(d_anchors, num_anchors, d_annotations, num_images, gt_rows, num_classes, d_meta, nullptr,
+                              d_iou_max, npos_acc, d_nvalid, stream);
+        if (rc) return rc;
+    }
     if (ev[1]) CLDET_CUDA_TRY(cudaEventRecord(ev[1], s));
     rc = loss_stage(d_cls, d_reg, d_anchors, d_annotations, num_images, num_anchors, num_classes, gt_rows, params, d_weights,
                       d_baked_weights, d_grad_cls, d_grad_reg, d_losses, d_meta, d_iou_max, npos_acc, d_npos, npos_acc, d_bg_mask, d_status,
-                      d_workspace, ws_bytes, stream, peer);
+                      d_workspace, ws_bytes, stream, peer, best, d_nvalid, best ? d_iou_max : nullptr);
     if (rc) return rc;
     if (ev[2]) CLDET_CUDA_TRY(cudaEventRecord(ev[2], s));
     return CLDET_OK;
@@ -344,6 +367,7 @@ static int reweight_impl(const float* d_cls, const float* d_reg, const float* d_
     a.baked_weights = d_baked_weights; a.gcls = d_grad_cls; a.greg = d_grad_reg;
     a.losses = nullptr; a.meta = d_meta; a.iou_max = d_iou_max; a.npos = d_npos; a.bg_mask = nullptr; a.status = nullptr;
     a.npos_out = nullptr; a.npos_reset = nullptr;
+    a.best = nullptr; a.meta_out = nullptr; a.iou_out = nullptr; a.nvalid = nullptr;
     a.peer_terms = nullptr; a.peer_flags = nullptr; a.rank = 0; a.world = 1; a.parity = 0;
     a.counters = nullptr; a.partials = nullptr;
     a.rw_counters = reinterpret_cast<unsigned int*>(d_workspace) + 2 * (size_t)num_images;

@@ -14,6 +14,7 @@ import torch
 import torch.nn as nn
 
 from . import _lib
+from .anchors import grid_of
 from .params import to_loss_params
 
 
@@ -260,6 +261,9 @@ class FocalLoss(nn.Module):
         n, _, c = cls.shape
         lp = to_loss_params(params, int(cur_state), c)
         lp.cls_is_logits = int(self.from_logits)
+        grid = grid_of(anc)            # anchors made by our Anchors module: GT-centric assignment
+        if grid is not None:
+            lp.image_height, lp.image_width = grid
         incremental = cur_state > 0
         want_mask = bool(incremental and params['distill'])
         outs = _FocalLossFn.apply(cls, reg, anc, ann, lp, self._hint(n, cls.device), want_mask, self.check_labels, peer)

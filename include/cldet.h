@@ -96,14 +96,19 @@ typedef struct cldet_loss_params {
     int32_t decrease_positive_by_iou;  /* :353-362 */
     int32_t enhance_on_new;            /* :380-384 */
     float decrease_positive;           /* :364-366, default 1.0 */
+    int32_t image_height, image_width; /* > 0: d_anchors is the standard anchor grid of an image of this size (what
+                                          cldet_anchors(height, width) produces): cldet_focal_loss then uses the GT-centric
+                                          assignment (a few hundred anchors per GT box instead of every anchor x GT pair).
+                                          0: arbitrary anchors, anchor-centric kernel.  Results are identical. */
     int32_t cls_is_logits;             /* 0: d_cls holds probabilities (the reference's FocalLoss input).
                                           1: d_cls holds LOGITS -- the kernel applies ATen's sigmoid 1/(1+exp(-x)) itself and
                                           writes dL/dlogits = dL/dp * (1-p) * p (replaces the separate
                                           Sigmoid at losses.py:566/633 and its backward; d_grad_cls may alias d_cls) */
 } cldet_loss_params;
 
-/* Bytes of scratch cldet_focal_loss needs for (N, A).  The first 3*N uint32 of a workspace must be ZERO before its first
- * use; every call leaves them zero again, so one memset at allocation time is enough (no per-call memset nodes). */
+/* Bytes of scratch cldet_focal_loss needs for (N, A).  A workspace must be ZERO before its first use; every call leaves it
+ * zero-clean again (counters, npos accumulator, IoU_max scratch), so one memset at allocation time is enough and the steady
+ * state has no memset nodes. */
 size_t cldet_focal_loss_workspace_bytes(int num_images, int64_t num_anchors);
 
 /* One call = IoU/assign kernel + fused loss/gradient kernel (two launches).
@@ -119,7 +124,8 @@ size_t cldet_focal_loss_workspace_bytes(int num_images, int64_t num_anchors);
  *            d_grad_cls may alias d_cls (in-place variant for a caller that no longer needs the probabilities).
  *   d_losses [4,N]: rows bg_j, fg_j (each already divided by max(npos_j,1)), reg_j, enhance_on_new partial of image j.
  *   d_meta [N,A] uint32 out (kept by the caller for the re-weighting pass); d_iou_max [N,A] out, may be NULL unless
- *            params->decrease_positive_by_iou; d_npos / d_nvalid [N] out.
+ *            params->decrease_positive_by_iou (on the GT-centric path it is exact wherever IoU_max >= 0.39 -- all the loss
+ *            reads -- and 0 elsewhere; background anchors' words carry label/row 0); d_npos / d_nvalid [N] out.
  *   d_bg_mask [N,A] uint8 out, may be NULL: 1 where the anchor is NOT positive (reference 'bg_masks', losses.py:334-335).
  *   d_status: int32[1] out, may be NULL; set non-zero when a positive anchor's label is outside [0,C) (reference raises, Q8). */
 int cldet_focal_loss(const float* d_cls, const float* d_reg, const float* d_anchors, const float* d_annotations,

