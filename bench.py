@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Benchmark of the detection-head hot path (BASELINE.json metric: detection-head images/sec + % HBM roofline).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload loss|decode]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--no-cpu-baseline] [--no-decode]
 
 Default workload = BASELINE config 3: COCO-shaped focal loss fwd+bwd, 16 x 800x1333, C=80, A=200700 per GPU
 (weak scaling: every rank processes its own 16 images; one NCCL all-gather of the per-image loss terms per step).
@@ -12,6 +12,9 @@ e2e   : the same metric through the public Python drop-in (FocalLoss.forward + a
         copies cls/reg/annotations from pinned host memory and reads the loss back.
 roofline: the fused loss kernel's algorithmic bytes / its own CUDA-event time inside the timed loop.
 cpu_baseline: the numpy oracle port of the reference timed on this box's host cores (bounded sample), rank 0 only.
+gpu_eager_baseline (N=1, baseline leg): the reference's own execution model (eager torch ops + autograd, oracle/torch_eager.py)
+        on the same GPU and batch -- informative, like cpu_baseline.
+decode (N=1): BASELINE config 4, the other half of the metric: decode + threshold + top-1000 + per-class NMS over 32 images.
 --impl reference: times that CPU port only (the reference is pure Python/torch and /root/reference is not on the box).
 """
 import argparse
@@ -163,6 +166,80 @@ def time_cpu_reference(steps, warmup, images_per_step, threads, frac=1.0):
         cpu_reference_step(imgs, anchors, threads)
     dt = time.perf_counter() - t0
     return images_per_step * f * steps / dt, dt / steps, f
+
+
+def time_gpu_eager(probs, reg, anchors, ann, n, steps=3):
+    """Informative second baseline (part of the baseline leg, rank 0, N=1): the reference's own execution model -- one
+    eager ATen op at a time, a dense [A,C] target matrix, boolean-mask gathers, autograd backward -- restated with
+    plain torch calls (oracle/torch_eager.py, bit-identical to the reference on the CPU fixtures) and run on the same
+    B200 over the same device-resident batch.  Not our product path; reported beside cpu_baseline."""
+    import torch
+    from oracle import torch_eager as E
+
+    def step():
+        p = probs.detach().requires_grad_(True)
+        r = reg.detach().requires_grad_(True)
+        bg, fg, rl = E.focal_loss(p, r, anchors, ann)
+        (bg.mean() + fg.mean() + rl.mean()).backward()
+        return p.grad, r.grad
+
+    try:
+        step()
+        torch.cuda.synchronize()
+        t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0.record()
+        for _ in range(steps):
+            step()
+        t1.record()
+        torch.cuda.synchronize()
+        ms = t0.elapsed_time(t1) / steps
+    except Exception as e:  # noqa: BLE001  (e.g. out of memory on a shared box): the line is informative only
+        return {'unavailable': repr(e)[:200]}
+    finally:
+        torch.cuda.empty_cache()
+    return {'value': n / (ms * 1e-3), 'unit': 'images/s', 'ms_per_step': ms, 'steps': steps, 'kind': 'port',
+            'sample': '%d steps x %d COCO-shaped images (the bench batch itself), torch-eager restatement of FocalLoss '
+                      'fwd + autograd bwd on the same GPU, inputs resident' % (steps, n)}
+
+
+def decode_section(dev, with_eager):
+    """BASELINE config 4 (the second half of the metric): eval-mode decode + threshold + top-1000 + per-class NMS over
+    32 x 800x1333, C=80, device-resident logits, through the C ABI (tools/bench_detect.py).  Two synthetic logit
+    distributions: SURVEY 8(d)'s N(-4, 2) (every anchor passes the 0.05 threshold: 200 700 candidates per image, the
+    worst case) and a trained-like N(-10.5, 2) (~1.3 k candidates per image).  With `with_eager` the torch-eager
+    restatement of ResNet.predict + torchvision.ops.batched_nms (the reference's mode: one image per call, no top-k)
+    is timed on the same GPU over the same logits as part of the baseline leg."""
+    import argparse as _ap
+
+    import torch
+    from tools.bench_detect import measure
+    out = {}
+    for name, mu, eager_images in (('all_anchors_candidates', -4.0, 2), ('trained_like', -10.5, 8)):
+        a = _ap.Namespace(steps=10, warmup=3, images=32, mu=mu, topk=1000, classes=C)
+        line, (logits, reg, anchors, h, w) = measure(a, dev, return_inputs=True)
+        entry = {'value': line['value'], 'unit': 'images/s', 'ms_per_step': line['ms_per_step'], 'steps': a.steps,
+                 'workload': line['config']['workload'], 'candidates_per_image': line['config']['candidates_per_image'],
+                 'kept_per_image': line['config']['kept_per_image'], 'stage_ms': line['stage_ms'], 'roofline': line['roofline']}
+        if with_eager:
+            try:
+                from oracle import torch_eager as E
+                E.predict(logits[:1], reg[:1], anchors, h, w)
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                for j in range(eager_images):
+                    s_, l_, b_ = E.predict(logits[j:j + 1], reg[j:j + 1], anchors, h, w)
+                torch.cuda.synchronize()
+                dt = time.perf_counter() - t0
+                entry['gpu_eager_baseline'] = {
+                    'value': eager_images / dt, 'unit': 'images/s', 'kind': 'port',
+                    'sample': '%d images, one predict() call each (torch-eager sigmoid/decode/clip/max/threshold + '
+                              'torchvision batched_nms 0.5, no top-k: the reference has none), same GPU, same logits' % eager_images}
+            except Exception as e:  # noqa: BLE001
+                entry['gpu_eager_baseline'] = {'unavailable': repr(e)[:200]}
+        out[name] = entry
+        del logits, reg
+        torch.cuda.empty_cache()
+    return out
 
 
 def run_reference(args):
@@ -402,6 +479,9 @@ def run_ours(args):
             cpu = {'value': v, 'unit': 'images/s', 'cores': thr, 'kind': 'port', 'host_cores': cores,
                    'sample': '2 steps x %d COCO-shaped images (800x1333, C=80, A=200700), numpy port of FocalLoss fwd+bwd, '
                              '%d threads' % (thr, thr)}
+        eager = None
+        if world == 1 and not args.no_cpu_baseline:
+            eager = time_gpu_eager(probs, reg, anchors, ann, n)
         line = {'metric': METRIC, 'value': value, 'unit': 'images/s', 'n_gpus': world, 'steps': args.steps,
                 'warmup': max(args.warmup, 3), 'ms_per_step': ms_per_step, 'higher_is_better': True, 'scaling': 'weak',
                 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
@@ -417,6 +497,12 @@ def run_ours(args):
                 'roofline': roofline}
         if cpu is not None:
             line['cpu_baseline'] = cpu
+        if eager is not None:
+            line['gpu_eager_baseline'] = eager
+        if world == 1 and not args.no_decode:
+            del probs, reg, gcls, greg, d_probs, d_reg, h_probs, h_reg
+            torch.cuda.empty_cache()
+            line['decode'] = decode_section(dev, with_eager=not args.no_cpu_baseline)
         print(json.dumps(line))
     if world > 1:
         if peer is not None:
@@ -432,7 +518,8 @@ def main():
     ap.add_argument('--steps', type=int, default=100)
     ap.add_argument('--warmup', type=int, default=10)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
-    ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-cpu-baseline', action='store_true', help='skip the CPU port and the GPU-eager baseline legs')
+    ap.add_argument('--no-decode', action='store_true', help='skip the BASELINE config 4 (decode + NMS) section')
     ap.add_argument('--collective', default='peer', choices=['peer', 'nccl'])
     args = ap.parse_args()
     if args.impl == 'reference':

@@ -605,6 +605,63 @@ nms_resolve_kernel(const int32_t* __restrict__ counts, int64_t capacity, const u
     if (threadIdx.x == 0) keep_counts[j] = kept_total;
 }
 
+// Small-K resolve (K <= kSmemResolveMax, e.g. after the top-1000 stage): the whole block pulls the image's upper-triangular
+// mask (<= 185 KB) into shared memory with independent coalesced loads, then ONE warp runs the sequential part with the
+// "removed" bitmap in registers (lane t owns column word t).  The dependent chain sees no global load and no block barrier:
+// ~1 us per 64 boxes instead of ~4 us in nms_resolve_kernel.
+constexpr int kSmemResolveMax = 1216;      // 1216 rows x 19 words x 8 B = 184.8 KB of the 227 KB a CTA may use
+
+__global__ void __launch_bounds__(256)
+nms_resolve_smem_kernel(const int32_t* __restrict__ counts, int64_t capacity, const uint64_t* __restrict__ mask,
+                        int64_t mask_stride_img, int col_blocks_alloc, int32_t* __restrict__ keep,
+                        int32_t* __restrict__ keep_counts) {
+    extern __shared__ uint64_t sm_mask[];                                // [n][cb]
+    const int j = blockIdx.x;
+    const int n = (int)min64(counts[j], capacity);
+    const int cb = (n + 63) / 64;
+    const uint64_t* m = mask + (int64_t)j * mask_stride_img;
+    const int total = n * cb;
+    for (int idx = threadIdx.x; idx < total; idx += blockDim.x) {
+        const int row = idx / cb, t = idx - row * cb;
+        if (t >= (row >> 6)) sm_mask[idx] = m[(int64_t)row * col_blocks_alloc + t];   // the lower triangle is never written
+    }
+    __syncthreads();
+    if (threadIdx.x >= 32) return;
+    const int lane = threadIdx.x;
+    uint64_t remv = 0;                                                    // lane t: removed bits of boxes 64t .. 64t+63
+    int kept_total = 0;
+    for (int c = 0; c < cb; ++c) {
+        const int rows = min(64, n - c * 64);
+        uint64_t cur = __shfl_sync(0xffffffffu, remv, c);
+        uint64_t kept = 0;
+        const uint64_t* diag = sm_mask + (int64_t)(c * 64) * cb + c;
+#pragma unroll 16
+        for (int b = 0; b < rows; ++b) {
+            const uint64_t w = diag[b * cb];                              // broadcast read, independent of the chain
+            if (!((cur >> b) & 1ull)) {
+                kept |= 1ull << b;
+                cur |= w;
+            }
+        }
+        const uint64_t lo0 = (1ull << lane) - 1ull;
+        if ((kept >> lane) & 1ull) keep[(int64_t)j * capacity + kept_total + __popcll(kept & lo0)] = c * 64 + lane;
+        const uint64_t lo1 = (1ull << (lane + 32)) - 1ull;
+        if ((kept >> (lane + 32)) & 1ull) keep[(int64_t)j * capacity + kept_total + __popcll(kept & lo1)] = c * 64 + lane + 32;
+        kept_total += __popcll(kept);
+        if (lane > c && lane < cb) {                                      // absorb the survivors' rows into the later words
+            uint64_t v = 0, k = kept;
+            const uint64_t* rowp = sm_mask + (int64_t)(c * 64) * cb + lane;
+            while (k) {
+                const int b = __ffsll((long long)k) - 1;
+                k &= k - 1;
+                v |= rowp[b * cb];
+            }
+            remv |= v;
+        }
+    }
+    if (lane == 0) keep_counts[j] = kept_total;
+}
+
 __global__ void __launch_bounds__(256)
 gather_detections_kernel(const cldet_candidate* __restrict__ sorted, const int32_t* __restrict__ keep,
                          const int32_t* __restrict__ keep_counts, int64_t capacity, float* __restrict__ scores,
@@ -899,8 +956,16 @@ int cldet_nms_sorted(const cldet_candidate* d_sorted, const int32_t* d_sorted_co
     nms_mask_kernel<<<grid, 64, 0, s>>>(d_sorted, d_sorted_counts, capacity, w.info, iou_thresh, w.mask, w.mask_stride_img,
                                         w.col_blocks);
     CLDET_LAUNCH_CHECK();
-    nms_resolve_kernel<<<num_images, 256, 0, s>>>(d_sorted_counts, capacity, w.mask, w.mask_stride_img, w.col_blocks, w.remv,
-                                                  d_keep, d_keep_counts);
+    if (max_count <= kSmemResolveMax) {
+        const size_t smem = (size_t)max_count * (size_t)((max_count + 63) / 64) * sizeof(uint64_t);
+        if (smem > 48 * 1024)
+            CLDET_CUDA_TRY(cudaFuncSetAttribute(nms_resolve_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        nms_resolve_smem_kernel<<<num_images, 256, smem, s>>>(d_sorted_counts, capacity, w.mask, w.mask_stride_img, w.col_blocks,
+                                                              d_keep, d_keep_counts);
+    } else {
+        nms_resolve_kernel<<<num_images, 256, 0, s>>>(d_sorted_counts, capacity, w.mask, w.mask_stride_img, w.col_blocks, w.remv,
+                                                      d_keep, d_keep_counts);
+    }
     CLDET_LAUNCH_CHECK();
     return CLDET_OK;
 }

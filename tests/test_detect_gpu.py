@@ -184,6 +184,27 @@ def test_full_size_coco_shape_topk1000():
         assert again.shape[0] == s.shape[0]
 
 
+@pytest.mark.parametrize('mu,reg_sigma', [(-10.5, 0.5), (-9.5, 0.3), (-8.5, 0.3)])
+def test_full_size_vs_torch_eager_and_torchvision_on_the_same_device(mu, reg_sigma):
+    """BASELINE config 4 shape in the reference's own mode (no top-k) against the torch-eager restatement of
+    ResNet.predict + torchvision.ops.batched_nms run on the SAME GPU: ~1.3 k, ~8 k and ~40 k candidates per image (the
+    last one crosses torchvision's 100 000-element switch to per-class NMS).  Same-device sigmoid and exp: everything
+    bit-exact, including the order."""
+    from oracle import torch_eager as E
+    h, w, C, N = 800, 1333, 80, 3
+    anchors = cld.generate_anchors(h, w, DEV)
+    A = anchors.shape[1]
+    gen = torch.Generator(device=DEV).manual_seed(int(-mu * 10))
+    logits = torch.randn(N, A, C, device=DEV, generator=gen) * 2 + mu
+    reg = torch.randn(N, A, 4, device=DEV, generator=gen) * reg_sigma
+    got = D.detect_batch(logits, reg, anchors, h, w)
+    for j in range(N):
+        s, l, b = E.predict(logits[j:j + 1], reg[j:j + 1], anchors, h, w)
+        assert s.shape[0] > 100
+        assert torch.equal(got[j][0], s) and torch.equal(got[j][1], l)
+        assert torch.equal(got[j][2], b)
+
+
 def test_f4_coco_results_vs_oracle_and_torch_cpu():
     """evaluator post-processing (evaluator.py:329-361) on the device, bit-exact with the CPU statements."""
     h, w, C, N = 256, 320, 7, 3

@@ -486,3 +486,45 @@ def test_gt_centric_assignment_equals_anchor_centric(h, w, C, N, G):
         ref = O.assign(O.anchors_for_image(h, w)[0], ann[j])
         if ref['valid']:
             assert np.array_equal(sb[j].cpu().numpy(), ref['state'])
+
+
+@pytest.mark.parametrize('h,w,C,N,G,exact,empty', [(800, 1333, 80, 4, 20, False, (1,)), (1333, 1333, 80, 2, 100, True, ()),
+                                                   (512, 512, 16, 16, 20, False, (0,))])
+def test_full_size_vs_torch_eager_on_the_same_device(h, w, C, N, G, exact, empty):
+    """BASELINE configs 3, 5 and 2 at their full per-image size against the torch-eager restatement of the reference
+    (oracle/torch_eager.py, bit-identical to the reference on CPU fixtures) evaluated on the SAME GPU, gradients from
+    torch autograd: every image, every element.  Losses and gradients 1e-5 relative (north_star)."""
+    from oracle import torch_eager as E
+    rng = np.random.default_rng(h + C + N)
+    A = O.num_anchors(h, w)
+    anchors = cld.generate_anchors(h, w, DEV)
+    gen = torch.Generator(device=DEV).manual_seed(h * 7 + C)
+    probs = torch.sigmoid(torch.randn(N, A, C, device=DEV, generator=gen) * 2 - 4)
+    reg = torch.randn(N, A, 4, device=DEV, generator=gen)
+    ann = cu(synth_gt(rng, N, G, h, w, C, empty=empty, exact=exact))
+    wb = torch.rand(N, device=DEV, generator=gen) + 0.5
+    wf = torch.rand(N, device=DEV, generator=gen) + 0.5
+
+    def run(fn):
+        c = probs.clone().requires_grad_(True)
+        r = reg.clone().requires_grad_(True)
+        bg, fg, rl = fn(c, r)
+        ((bg * wb).sum() + (fg * wf).sum() + 0.7 * rl.sum()).backward()
+        return bg.detach(), fg.detach(), rl.detach(), c.grad, r.grad
+
+    def ours(c, r):
+        out = cld.FocalLoss()(c, r, anchors, ann, 0, cld.HeadParams())
+        return out['cls_loss'][0], out['cls_loss'][1], out['reg_loss']
+
+    got = run(ours)
+    ref = run(lambda c, r: E.focal_loss(c, r, anchors, ann))
+    for k in range(3):
+        check_rel(got[k].cpu().numpy(), ref[k].cpu().numpy())
+    # gradients compared on the device (2 x 1 GB at config 3), same bars as check_grad_cls / check_grad_reg
+    gc, rc = got[3], ref[3]
+    assert torch.equal(gc == 0, rc == 0), 'zero-gradient pattern (ignore / out-of-band) differs'
+    err = ((gc - rc).abs() / (rc.abs() + 1e-12 * rc.abs().max() + 1e-45)).max().item()
+    assert err < 1e-5, err
+    gr, rr = got[4], ref[4]
+    assert torch.equal(gr == 0, rr == 0)
+    assert ((gr - rr).abs() - 1e-5 * rr.abs()).max().item() <= 1e-5 * rr.abs().max().item()

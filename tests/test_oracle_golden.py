@@ -159,3 +159,44 @@ def test_a9_collate_and_pseudo_filter_match_reference():
     b[:, 2] -= b[:, 0]
     b[:, 3] -= b[:, 1]
     assert np.array_equal(s, g['out_scores']) and np.array_equal(l, g['out_labels']) and np.array_equal(b, g['out_boxes'])
+
+
+# ---- the torch-eager restatement (oracle/torch_eager.py): same fixtures, gradients through autograd ----
+@pytest.mark.parametrize('case', ['state0_voc', 'state0_allvalid', 'state0_allempty', 'state0_gamma15', 'il_default_pseudo'])
+def test_torch_eager_focal_matches_reference(case):
+    import torch
+    from oracle import torch_eager as E
+    g = load('focal_' + case)
+    params = golden_params(g)
+    anchors = torch.from_numpy(O.anchors_for_image(int(g['h']), int(g['w'])))
+    cls = torch.from_numpy(g['cls']).requires_grad_(True)
+    reg = torch.from_numpy(g['reg']).requires_grad_(True)
+    bg, fg, rl = E.focal_loss(cls, reg, anchors, torch.from_numpy(g['ann']), params['alpha'], params['gamma'])
+    # the fixture's upstream weights: dL/dbg_j = wb_j, dL/dfg_j = wf_j, dL/dreg_loss = wr
+    ((bg * torch.from_numpy(g['wb'])).sum() + (fg * torch.from_numpy(g['wf'])).sum() + rl.sum() * float(g['wr'])).backward()
+    # the same torch ops in the same order as the reference on the same CPU: identical bits
+    assert np.array_equal(bg.detach().numpy(), g['bg'])
+    assert np.array_equal(fg.detach().numpy(), g['fg'])
+    assert np.array_equal(rl.detach().numpy(), g['reg_loss'])
+    assert rel_err(cls.grad.numpy(), g['grad_cls'], 1e-30) < 1e-6
+    assert np.array_equal(cls.grad.numpy() == 0, g['grad_cls'] == 0)
+    reg_grad = np.zeros_like(g['grad_reg']) if reg.grad is None else reg.grad.numpy()     # no positives anywhere: no graph
+    assert float(np.abs(reg_grad - g['grad_reg']).max()) <= 1e-6 * float(np.abs(g['grad_reg']).max())
+
+
+def test_torch_eager_decode_and_predict_match_reference():
+    import torch
+    from oracle import torch_eager as E
+    g = load('decode')
+    h, w = int(g['h']), int(g['w'])
+    anchors = torch.from_numpy(O.anchors_for_image(h, w))
+    dec = E.decode_boxes(anchors, torch.from_numpy(g['reg']))
+    assert np.array_equal(dec.numpy(), g['decoded'])
+    assert np.array_equal(E.clip_boxes(dec.clone(), h, w).numpy(), g['clipped'])
+    for name in ('trick', 'none'):
+        p = load('predict_' + name)
+        h, w = int(p['h']), int(p['w'])
+        anchors = torch.from_numpy(O.anchors_for_image(h, w))
+        s, l, b = E.predict(torch.from_numpy(p['logits']), torch.from_numpy(p['reg']), anchors, h, w)
+        assert np.array_equal(s.numpy(), p['scores']) and np.array_equal(l.numpy(), p['labels'])
+        assert np.array_equal(b.numpy(), p['boxes'])

@@ -16,17 +16,11 @@ import cl_object_detection_b200 as cld  # noqa: E402
 from cl_object_detection_b200 import _lib  # noqa: E402
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument('--steps', type=int, default=30)
-    ap.add_argument('--warmup', type=int, default=5)
-    ap.add_argument('--images', type=int, default=32)
-    ap.add_argument('--mu', type=float, default=-4.0)
-    ap.add_argument('--topk', type=int, default=1000)
-    ap.add_argument('--classes', type=int, default=80)
-    args = ap.parse_args()
-    dev = torch.device('cuda', 0)
-    torch.cuda.set_device(dev)
+def measure(args, dev=None, return_inputs=False):
+    """One JSON-able dict for the configuration in `args` (steps, warmup, images, mu, topk, classes)."""
+    if dev is None:
+        dev = torch.device('cuda', 0)
+        torch.cuda.set_device(dev)
     lib = _lib.load()
     h, w, c, n, topk = 800, 1333, args.classes, args.images, args.topk
     anchors = cld.generate_anchors(h, w, dev)
@@ -98,7 +92,20 @@ def main():
             'roofline': {'bound': 'hbm', 'kernel': 'decode_filter_kernel<4>', 'achieved': filt_bytes / (stage[0] * 1e-3) / 1e9,
                          'peak': peak, 'unit': 'GB/s', 'frac': filt_bytes / (stage[0] * 1e-3) / 1e9 / peak,
                          'algorithmic_bytes_per_launch': filt_bytes}}
-    print(json.dumps(line))
+    if return_inputs:
+        return line, (logits, reg, anchors, h, w)
+    return line
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--steps', type=int, default=30)
+    ap.add_argument('--warmup', type=int, default=5)
+    ap.add_argument('--images', type=int, default=32)
+    ap.add_argument('--mu', type=float, default=-4.0)
+    ap.add_argument('--topk', type=int, default=1000)
+    ap.add_argument('--classes', type=int, default=80)
+    print(json.dumps(measure(ap.parse_args())))
 
 
 if __name__ == '__main__':
