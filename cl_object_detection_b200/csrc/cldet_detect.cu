@@ -611,19 +611,33 @@ nms_resolve_kernel(const int32_t* __restrict__ counts, int64_t capacity, const u
 // ~1 us per 64 boxes instead of ~4 us in nms_resolve_kernel.
 constexpr int kSmemResolveMax = 1216;      // 1216 rows x 19 words x 8 B = 184.8 KB of the 227 KB a CTA may use
 
-__global__ void __launch_bounds__(256)
+constexpr int kSmemResolveThreads = 1024;
+
+__global__ void __launch_bounds__(kSmemResolveThreads)
 nms_resolve_smem_kernel(const int32_t* __restrict__ counts, int64_t capacity, const uint64_t* __restrict__ mask,
                         int64_t mask_stride_img, int col_blocks_alloc, int32_t* __restrict__ keep,
                         int32_t* __restrict__ keep_counts) {
-    extern __shared__ uint64_t sm_mask[];                                // [n][cb]
+    extern __shared__ uint64_t sm_mask[];                                // [64*cb][cb], rows >= n zero
     const int j = blockIdx.x;
     const int n = (int)min64(counts[j], capacity);
     const int cb = (n + 63) / 64;
     const uint64_t* m = mask + (int64_t)j * mask_stride_img;
-    const int total = n * cb;
-    for (int idx = threadIdx.x; idx < total; idx += blockDim.x) {
-        const int row = idx / cb, t = idx - row * cb;
-        if (t >= (row >> 6)) sm_mask[idx] = m[(int64_t)row * col_blocks_alloc + t];   // the lower triangle is never written
+    const int total = 64 * cb * cb;
+    // four independent loads in flight per thread (the copy is latency-bound: one CTA per image)
+    for (int i0 = threadIdx.x; i0 < total; i0 += 4 * kSmemResolveThreads) {
+        uint64_t v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int idx = i0 + u * kSmemResolveThreads;
+            const int row = idx / cb, t = idx - row * cb;
+            // the lower triangle is never written by nms_mask_kernel and never read below; rows past n read as zero
+            v[u] = (idx < total && row < n && t >= (row >> 6)) ? m[(int64_t)row * col_blocks_alloc + t] : 0ull;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int idx = i0 + u * kSmemResolveThreads;
+            if (idx < total) sm_mask[idx] = v[u];
+        }
     }
     __syncthreads();
     if (threadIdx.x >= 32) return;
@@ -633,14 +647,21 @@ nms_resolve_smem_kernel(const int32_t* __restrict__ counts, int64_t capacity, co
     for (int c = 0; c < cb; ++c) {
         const int rows = min(64, n - c * 64);
         uint64_t cur = __shfl_sync(0xffffffffu, remv, c);
+        if (rows < 64) cur |= ~0ull << rows;                              // slots past the end can never be kept
         uint64_t kept = 0;
         const uint64_t* diag = sm_mask + (int64_t)(c * 64) * cb + c;
-#pragma unroll 16
-        for (int b = 0; b < rows; ++b) {
-            const uint64_t w = diag[b * cb];                              // broadcast read, independent of the chain
-            if (!((cur >> b) & 1ull)) {
-                kept |= 1ull << b;
-                cur |= w;
+        // 16 rows at a time: the (broadcast) loads first, then a branch-free chain of constant-position bit tests
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+            uint64_t w[16];
+#pragma unroll
+            for (int q = 0; q < 16; ++q) w[q] = diag[(g * 16 + q) * cb];
+#pragma unroll
+            for (int q = 0; q < 16; ++q) {
+                const int b = g * 16 + q;
+                const bool take = !((cur >> b) & 1ull);
+                kept |= take ? (1ull << b) : 0ull;
+                cur |= take ? w[q] : 0ull;
             }
         }
         const uint64_t lo0 = (1ull << lane) - 1ull;
@@ -649,14 +670,14 @@ nms_resolve_smem_kernel(const int32_t* __restrict__ counts, int64_t capacity, co
         if ((kept >> (lane + 32)) & 1ull) keep[(int64_t)j * capacity + kept_total + __popcll(kept & lo1)] = c * 64 + lane + 32;
         kept_total += __popcll(kept);
         if (lane > c && lane < cb) {                                      // absorb the survivors' rows into the later words
-            uint64_t v = 0, k = kept;
             const uint64_t* rowp = sm_mask + (int64_t)(c * 64) * cb + lane;
-            while (k) {
-                const int b = __ffsll((long long)k) - 1;
-                k &= k - 1;
-                v |= rowp[b * cb];
+            uint64_t v0 = 0, v1 = 0;
+#pragma unroll
+            for (int b = 0; b < 64; b += 2) {                             // unconditional, independent loads, masked by the bit
+                v0 |= rowp[b * cb] & (0ull - ((kept >> b) & 1ull));
+                v1 |= rowp[(b + 1) * cb] & (0ull - ((kept >> (b + 1)) & 1ull));
             }
-            remv |= v;
+            remv |= v0 | v1;
         }
     }
     if (lane == 0) keep_counts[j] = kept_total;
@@ -957,10 +978,11 @@ int cldet_nms_sorted(const cldet_candidate* d_sorted, const int32_t* d_sorted_co
                                         w.col_blocks);
     CLDET_LAUNCH_CHECK();
     if (max_count <= kSmemResolveMax) {
-        const size_t smem = (size_t)max_count * (size_t)((max_count + 63) / 64) * sizeof(uint64_t);
+        const size_t cbm = (size_t)((max_count + 63) / 64);
+        const size_t smem = 64 * cbm * cbm * sizeof(uint64_t);
         if (smem > 48 * 1024)
             CLDET_CUDA_TRY(cudaFuncSetAttribute(nms_resolve_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        nms_resolve_smem_kernel<<<num_images, 256, smem, s>>>(d_sorted_counts, capacity, w.mask, w.mask_stride_img, w.col_blocks,
+        nms_resolve_smem_kernel<<<num_images, kSmemResolveThreads, smem, s>>>(d_sorted_counts, capacity, w.mask, w.mask_stride_img, w.col_blocks,
                                                               d_keep, d_keep_counts);
     } else {
         nms_resolve_kernel<<<num_images, 256, 0, s>>>(d_sorted_counts, capacity, w.mask, w.mask_stride_img, w.col_blocks, w.remv,
