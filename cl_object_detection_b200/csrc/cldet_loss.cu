@@ -1,6 +1,9 @@
 // K3 host side: C-ABI entry points of the fused focal-loss + smooth-L1 forward/backward (kernels: cldet_loss_kernels.cuh).
 // This translation unit instantiates the probabilities-in kernels; cldet_loss_logits.cu the logits-in (sigmoid-fused) ones.
+#include <stdlib.h>
 #include <string.h>
+
+#include <algorithm>
 
 #include "cldet_loss_kernels.cuh"
 
@@ -41,7 +44,9 @@ static LossPlan make_plan(int N, int64_t A, int C, int vec) {
     int64_t quantum = 32;
     const int64_t kTile = tile_for(vec);
     if (vec > 1) quantum = kTile / gcd64(C / vec, kTile);
-    int64_t apb = (24576 / C + quantum - 1) / quantum * quantum;
+    int64_t target = 24576;                                  // elements per block
+    if (const char* e = getenv("CLDET_LOSS_BLOCK_ELEMS")) target = std::max<int64_t>(1024, atoll(e));    // A/B experiments only
+    int64_t apb = (target / C + quantum - 1) / quantum * quantum;
     if (apb > kMaxAnchorsPerBlock) apb = kMaxAnchorsPerBlock / quantum * quantum;
     if (apb < 32) apb = (quantum <= kMaxAnchorsPerBlock) ? quantum : 32;
     // small problems: keep at least ~4 blocks per SM in flight (ragged tiles are fine there)
@@ -372,7 +377,9 @@ static int reweight_impl(const float* d_cls, const float* d_reg, const float* d_
     a.counters = nullptr; a.partials = nullptr;
     a.rw_counters = reinterpret_cast<unsigned int*>(d_workspace) + 2 * (size_t)num_images;
     a.anchors_per_block = pl.anchors_per_block; a.bpi = pl.bpi; a.div_magic = pl.div_magic;
-    dim3 grid((unsigned)pl.bpi, (unsigned)num_images);
+    // ~4 CTAs per SM over the whole batch; blocks loop over their image's chunks
+    const int per_image = std::max(1, (sm_count() * 4 + num_images - 1) / num_images);
+    dim3 grid((unsigned)std::min(pl.bpi, per_image), (unsigned)num_images);
     const bool gamma2 = params->gamma == 2.0f;
     const bool variants = has_variants(*params);
     if (params->cls_is_logits) run_reweight_kernels<true>(a, vec, gamma2, variants, grid, s);
