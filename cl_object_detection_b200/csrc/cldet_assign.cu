@@ -342,7 +342,8 @@ struct ScatterPlan {
 
 __global__ void __launch_bounds__(128)
 gt_scatter_kernel(const ScatterPlan plan, const float4* __restrict__ anchors, int64_t A, const float* __restrict__ annotations,
-                  int G, unsigned long long* __restrict__ best, int32_t* __restrict__ npos_acc, int32_t* __restrict__ nvalid) {
+                  int G, unsigned long long* __restrict__ best, uint32_t* __restrict__ touched, int32_t* __restrict__ npos_acc,
+                  int32_t* __restrict__ nvalid) {
     // grid = (GT row, image, pyramid level): one block visits the candidate anchors of one GT box on one level
     const int j = blockIdx.y;
     const int l = blockIdx.z;
@@ -398,6 +399,8 @@ gt_scatter_kernel(const ScatterPlan plan, const float4* __restrict__ anchors, in
     __syncthreads();
     const int total = s_first[kAnchorsPerCell];
     unsigned long long* best_j = best + (int64_t)j * A;
+    // one bit per anchor that received a key: the loss kernel reads 1 bit instead of 8 bytes for the ~98 % that did not
+    uint32_t* touched_j = touched ? touched + (int64_t)j * ((A + 31) / 32) : nullptr;
     const unsigned long long low = 0xFFFFFFFFull - (unsigned long long)g;      // ties -> smallest row wins the max
     int crossings = 0;
     for (int c = threadIdx.x; c < total; c += blockDim.x) {
@@ -421,6 +424,7 @@ gt_scatter_kernel(const ScatterPlan plan, const float4* __restrict__ anchors, in
             if (v >= 0.39f) {                                   // lower values cannot change any anchor's state
                 const unsigned long long key = ((unsigned long long)__float_as_uint(v) << 32) | low;
                 const unsigned long long old = atomicMax(best_j + idx, key);
+                if (touched_j && old == 0ull) atomicOr(touched_j + (idx >> 5), 1u << (idx & 31));
                 // the anchor becomes positive exactly once: when its maximum first reaches 0.5 (losses.py:330)
                 if ((uint32_t)(old >> 32) < 0x3f000000u && v >= 0.5f) ++crossings;
             }
@@ -461,8 +465,8 @@ iou_max_f64_kernel(const double* __restrict__ a, int64_t na, const double* __res
 namespace cldet {
 
 int launch_gt_scatter(int height, int width, const float* d_anchors, int64_t num_anchors, const float* d_annotations,
-                      int num_images, int gt_rows, unsigned long long* d_best, int32_t* d_npos_acc, int32_t* d_nvalid,
-                      cudaStream_t s) {
+                      int num_images, int gt_rows, unsigned long long* d_best, uint32_t* d_touched, int32_t* d_npos_acc,
+                      int32_t* d_nvalid, cudaStream_t s) {
     AnchorPlan ap;
     build_anchor_plan(height, width, &ap);
     if (ap.level_offset[kNumLevels] != num_anchors) return CLDET_ERR_UNSUPPORTED;
@@ -480,7 +484,7 @@ int launch_gt_scatter(int height, int width, const float* d_anchors, int64_t num
     sp.level_offset[kNumLevels] = ap.level_offset[kNumLevels];
     dim3 grid((unsigned)gt_rows, (unsigned)num_images, (unsigned)kNumLevels);
     gt_scatter_kernel<<<grid, 128, 0, s>>>(sp, reinterpret_cast<const float4*>(d_anchors), num_anchors, d_annotations, gt_rows,
-                                           d_best, d_npos_acc, d_nvalid);
+                                           d_best, d_touched, d_npos_acc, d_nvalid);
     if (cudaPeekAtLastError() != cudaSuccess) {
         set_last_cuda_error(cudaGetLastError());
         return CLDET_ERR_CUDA;

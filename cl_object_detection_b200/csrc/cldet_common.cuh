@@ -62,8 +62,8 @@ __device__ __forceinline__ void st_stream_f4(float4* p, const float4& v) {
 // counts anchors crossing 0.5 into npos_acc and valid rows into nvalid.  Returns CLDET_ERR_UNSUPPORTED when A does not match
 // the grid of (height, width).
 int launch_gt_scatter(int height, int width, const float* d_anchors, int64_t num_anchors, const float* d_annotations,
-                      int num_images, int gt_rows, unsigned long long* d_best, int32_t* d_npos_acc, int32_t* d_nvalid,
-                      cudaStream_t s);
+                      int num_images, int gt_rows, unsigned long long* d_best, uint32_t* d_touched, int32_t* d_npos_acc,
+                      int32_t* d_nvalid, cudaStream_t s);
 
 inline int sm_count() {
     int dev = 0, n = 148;

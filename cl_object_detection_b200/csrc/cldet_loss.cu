@@ -80,8 +80,12 @@ static size_t workspace_partials_bytes(int N, int64_t A) {
 }
 
 // [header | partials | best: N*A uint64 (IoU_max bits, ~row) keys of the GT-centric assignment (zero between calls)]
+static size_t workspace_best_bytes(int N, int64_t A) { return ((size_t)N * A * sizeof(unsigned long long) + 255) / 256 * 256; }
+static size_t workspace_touched_bytes(int N, int64_t A) { return ((size_t)N * ((A + 31) / 32) * sizeof(uint32_t) + 255) / 256 * 256; }
+
+// ... | touched: N * ceil(A/32) words, one bit per anchor that holds a key (zero between calls)]
 static size_t workspace_bytes(int N, int64_t A) {
-    return workspace_header_bytes(N) + workspace_partials_bytes(N, A) + (size_t)N * A * sizeof(unsigned long long) + 256;
+    return workspace_header_bytes(N) + workspace_partials_bytes(N, A) + workspace_best_bytes(N, A) + workspace_touched_bytes(N, A) + 256;
 }
 
 // widest vector the class map allows: rows must be a whole number of vectors and the buffers aligned to the vector
@@ -134,7 +138,7 @@ static int loss_stage(const float* d_cls, const float* d_reg, const float* d_anc
                       uint32_t* d_meta, const float* d_iou_max, const int32_t* d_npos, int32_t* d_npos_out, int32_t* d_npos_reset,
                       uint8_t* d_bg_mask, int32_t* d_status, void* d_workspace, size_t ws_bytes, void* stream,
                       const cldet_peer_exchange* peer = nullptr, unsigned long long* d_best = nullptr, const int32_t* d_nvalid = nullptr,
-                      float* d_iou_out = nullptr) {
+                      float* d_iou_out = nullptr, uint32_t* d_touched = nullptr) {
     int rc = check_common(d_cls, d_anchors, d_annotations, num_images, num_anchors, num_classes, gt_rows, params);
     if (rc) return rc;
     if (!d_reg || !d_losses || !d_meta || !d_npos || !d_workspace) return CLDET_ERR_INVALID_ARGUMENT;
@@ -159,7 +163,7 @@ static int loss_stage(const float* d_cls, const float* d_reg, const float* d_anc
     a.baked_weights = d_baked_weights; a.gcls = d_grad_cls; a.greg = d_grad_reg; a.losses = d_losses;
     a.meta = d_meta; a.iou_max = d_iou_max; a.npos = d_npos; a.bg_mask = d_bg_mask; a.status = d_status;
     a.npos_out = d_npos_out; a.npos_reset = d_npos_reset; a.rw_counters = nullptr;
-    a.best = d_best; a.meta_out = d_meta; a.iou_out = d_iou_out; a.nvalid = d_nvalid;
+    a.best = d_best; a.touched = d_touched; a.meta_out = d_meta; a.iou_out = d_iou_out; a.nvalid = d_nvalid;
     a.peer_terms = nullptr; a.peer_flags = nullptr; a.rank = 0; a.world = 1; a.parity = 0;
     if (peer && peer->world > 1) {
         if (!peer->d_peer_terms || !peer->d_peer_flags || peer->rank < 0 || peer->rank >= peer->world || peer->world > 64 ||
@@ -221,14 +225,19 @@ int cldet_focal_loss_sharded(const float* d_cls, const float* d_reg, const float
     // pairs); the loss kernel turns the IoU_max bits into assignment words itself.  The new_ignore_past_class pre-pass needs
     // ready-made words, and arbitrary anchor sets have no grid: both use the anchor-centric kernel.
     unsigned long long* best = nullptr;
+    uint32_t* touched = nullptr;
     const bool needs_words = params->incremental && params->ignore_past_class && params->new_ignore_past_class &&
                              params->past_class_num > 0;
     if (params->image_height > 0 && params->image_width > 0 && !needs_words) {
         best = reinterpret_cast<unsigned long long*>(reinterpret_cast<char*>(d_workspace) + workspace_header_bytes(num_images) +
                                            workspace_partials_bytes(num_images, num_anchors));
+        // the key bitmap needs chunks that own whole bitmap words (always true except for C >= 1024, where chunks are tiny)
+        const LossPlan pl = make_plan(num_images, num_anchors, num_classes, pick_vec(num_classes, d_cls, d_grad_cls));
+        if (pl.anchors_per_block % 32 == 0)
+            touched = reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(best) + workspace_best_bytes(num_images, num_anchors));
         rc = launch_gt_scatter(params->image_height, params->image_width, d_anchors, num_anchors, d_annotations, num_images,
-                               gt_rows, best, npos_acc, d_nvalid, s);
-        if (rc == CLDET_ERR_UNSUPPORTED) best = nullptr;      // anchors are not this image size's grid
+                               gt_rows, best, touched, npos_acc, d_nvalid, s);
+        if (rc == CLDET_ERR_UNSUPPORTED) best = nullptr, touched = nullptr;      // anchors are not this image size's grid
         else if (rc) return rc;
     }
     if (!best) {
@@ -239,7 +248,7 @@ int cldet_focal_loss_sharded(const float* d_cls, const float* d_reg, const float
     if (ev[1]) CLDET_CUDA_TRY(cudaEventRecord(ev[1], s));
     rc = loss_stage(d_cls, d_reg, d_anchors, d_annotations, num_images, num_anchors, num_classes, gt_rows, params, d_weights,
                       d_baked_weights, d_grad_cls, d_grad_reg, d_losses, d_meta, d_iou_max, npos_acc, d_npos, npos_acc, d_bg_mask, d_status,
-                      d_workspace, ws_bytes, stream, peer, best, d_nvalid, best ? d_iou_max : nullptr);
+                      d_workspace, ws_bytes, stream, peer, best, d_nvalid, best ? d_iou_max : nullptr, touched);
     if (rc) return rc;
     if (ev[2]) CLDET_CUDA_TRY(cudaEventRecord(ev[2], s));
     return CLDET_OK;
@@ -372,7 +381,7 @@ static int reweight_impl(const float* d_cls, const float* d_reg, const float* d_
     a.baked_weights = d_baked_weights; a.gcls = d_grad_cls; a.greg = d_grad_reg;
     a.losses = nullptr; a.meta = d_meta; a.iou_max = d_iou_max; a.npos = d_npos; a.bg_mask = nullptr; a.status = nullptr;
     a.npos_out = nullptr; a.npos_reset = nullptr;
-    a.best = nullptr; a.meta_out = nullptr; a.iou_out = nullptr; a.nvalid = nullptr;
+    a.best = nullptr; a.touched = nullptr; a.meta_out = nullptr; a.iou_out = nullptr; a.nvalid = nullptr;
     a.peer_terms = nullptr; a.peer_flags = nullptr; a.rank = 0; a.world = 1; a.parity = 0;
     a.counters = nullptr; a.partials = nullptr;
     a.rw_counters = reinterpret_cast<unsigned int*>(d_workspace) + 2 * (size_t)num_images;
