@@ -67,6 +67,10 @@ SIGNATURES = {
                                             _L, _P, _L, _P, _P, _P, _P, _P, _P, _P, _Z, _P]),
     'cldet_focal_loss_reweight': (_I, [_P, _P, _P, _P, _I, _L, _I, _I, ctypes.POINTER(LossParams), _P, _P, _P, _P, _P,
                                        _P, _P, _P, _Z, _P]),
+    'cldet_focal_loss_head': (_I, [_P, _P, _I, _I, _I, _P, _P, _I, _I, _I, ctypes.POINTER(LossParams), _P, _P, _P, _P, _P, _P,
+                                   _P, _P, _P, _P, _P, _P, _Z, _P]),
+    'cldet_focal_loss_head_reweight': (_I, [_P, _P, _I, _I, _I, _P, _P, _I, _I, _I, ctypes.POINTER(LossParams), _P, _L, _P, _L,
+                                            _P, _L, _P, _L, _P, _P, _P, _P, _P, _P, _P, _Z, _P]),
     'cldet_distill_workspace_bytes': (_Z, [_I, _L]),
     'cldet_distill_forward': (_I, [_P, _P, _P, _P, _P, _I, _L, _I, _I, _I, _I, _P, _P, _P, _Z, _P]),
     'cldet_distill_backward': (_I, [_P, _P, _P, _P, _P, _I, _L, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P]),
@@ -128,3 +132,10 @@ def check(status):
 def ptr(t):
     """Device pointer of a tensor (None -> NULL)."""
     return None if t is None else t.data_ptr()
+
+
+def ptr_array(tensors):
+    """Host array of device pointers (`const float* const*` in the C ABI) for a list of tensors; None -> NULL."""
+    if tensors is None:
+        return None
+    return (ctypes.c_void_p * len(tensors))(*[t.data_ptr() for t in tensors])

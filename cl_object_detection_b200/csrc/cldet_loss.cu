@@ -5,12 +5,15 @@
 
 #include <algorithm>
 
-#include "cldet_loss_kernels.cuh"
+#include "cldet_loss_head_kernels.cuh"
 
 namespace cldet {
 
 template void run_loss_kernels<false>(const LossArgs&, int, bool, bool, bool, dim3, cudaStream_t);
 template void run_reweight_kernels<false>(const LossArgs&, int, bool, bool, dim3, cudaStream_t);
+template void run_head_loss_kernels<false>(const LossArgs&, const HeadLevels&, bool, bool, bool, dim3, cudaStream_t);
+template void run_head_reweight_kernels<false>(const LossArgs&, const HeadLevels&, bool, bool, dim3, cudaStream_t);
+template void run_head_flag_kernels<false>(const HeadLevels&, int, int64_t, int, int, uint32_t*, cudaStream_t);
 
 // new_ignore_past_class pre-pass (losses.py:326-327): flag background anchors whose clamped old-class
 // probabilities sum to < 0.5.  fp32 sequential sum in column order.
@@ -356,6 +359,60 @@ int cldet_peer_wait(void* d_flags_local, int world, int parity, int expected_arr
     return CLDET_OK;
 }
 
+// ---- head layout: per-level NCHW conv outputs in, gradients of the same layout out ----
+// Fills the level table for an (image_height, image_width) input: level l = 3..7 has ceil(H/2^l) x ceil(W/2^l) positions
+// (retinanet/anchors.py:25) with 9 anchors each; channels are k*C + c (classification) and k*4 + i (regression).
+static int head_levels(const float* const* h_cls, const float* const* h_reg, float* const* h_gcls, float* const* h_greg,
+                       int num_levels, int image_height, int image_width, bool grad, HeadLevels* lv, int64_t* num_anchors,
+                       int* chunks_per_image) {
+    if (!h_cls || !h_reg || num_levels != kNumLevels || image_height <= 0 || image_width <= 0) return CLDET_ERR_INVALID_ARGUMENT;
+    if (grad && (!h_gcls || !h_greg)) return CLDET_ERR_INVALID_ARGUMENT;
+    lv->n = num_levels;
+    int64_t aoff = 0;
+    int coff = 0;
+    for (int l = 0; l < kHeadMaxLevels; ++l) {
+        lv->cls[l] = lv->reg[l] = nullptr;
+        lv->gcls[l] = lv->greg[l] = nullptr;
+        lv->hw[l] = 0;
+    }
+    for (int l = 0; l < num_levels; ++l) {
+        const int sh = 3 + l;
+        const int64_t hw = (int64_t)((image_height + (1 << sh) - 1) >> sh) * ((image_width + (1 << sh) - 1) >> sh);
+        if (hw <= 0 || hw > (1 << 26)) return CLDET_ERR_INVALID_ARGUMENT;
+        if (!h_cls[l] || !h_reg[l] || (grad && (!h_gcls[l] || !h_greg[l]))) return CLDET_ERR_INVALID_ARGUMENT;
+        lv->cls[l] = h_cls[l]; lv->reg[l] = h_reg[l];
+        lv->gcls[l] = grad ? h_gcls[l] : nullptr; lv->greg[l] = grad ? h_greg[l] : nullptr;
+        lv->hw[l] = (int)hw;
+        lv->anchor_off[l] = aoff;
+        lv->chunk_off[l] = coff;
+        aoff += hw * kHeadTypes;
+        coff += (int)((hw + kHeadPos - 1) / kHeadPos);
+    }
+    for (int l = num_levels; l <= kHeadMaxLevels; ++l) {
+        lv->anchor_off[l] = aoff;
+        lv->chunk_off[l] = coff;
+    }
+    *num_anchors = aoff;
+    *chunks_per_image = coff;
+    return CLDET_OK;
+}
+
+static void head_args(LossArgs* a, const float* d_anchors, const float* d_annotations, int N, int64_t A, int C, int G,
+                      const cldet_loss_params* params, int chunks_per_image, void* d_workspace) {
+    memset(a, 0, sizeof(*a));
+    a->anchors = reinterpret_cast<const float4*>(d_anchors); a->ann = d_annotations;
+    a->N = N; a->A = A; a->C = C; a->G = G; a->p = *params;
+    a->world = 1;
+    a->counters = reinterpret_cast<unsigned int*>(d_workspace);
+    a->partials = reinterpret_cast<float*>(reinterpret_cast<char*>(d_workspace) + workspace_header_bytes(N));
+    a->rw_counters = reinterpret_cast<unsigned int*>(d_workspace) + 2 * (size_t)N;
+    a->bpi = chunks_per_image;
+    a->anchors_per_block = kHeadPos * kHeadTypes;
+    const uint64_t span = (uint64_t)kHeadTypes * C;              // dividends are channel indices < 9*C
+    const uint64_t magic = (1ull << 32) / (uint64_t)C + 1;
+    a->div_magic = (span * (magic * (uint64_t)C - (1ull << 32)) < (1ull << 32) && magic < (1ull << 32)) ? (uint32_t)magic : 0u;
+}
+
 static int reweight_impl(const float* d_cls, const float* d_reg, const float* d_anchors, const float* d_annotations,
                          int num_images, int64_t num_anchors, int num_classes, int gt_rows, const cldet_loss_params* params,
                          const float* const w_ptr[4], const int64_t w_stride[4], float* d_baked_weights, float* d_grad_cls,
@@ -425,6 +482,106 @@ int cldet_focal_loss_reweight_rows(const float* d_cls, const float* d_reg, const
     return reweight_impl(d_cls, d_reg, d_anchors, d_annotations, num_images, num_anchors, num_classes, gt_rows, params, rows,
                          strides, d_baked_weights, d_grad_cls, d_grad_reg, d_meta, d_iou_max, d_npos, d_workspace, ws_bytes,
                          stream);
+}
+
+int cldet_focal_loss_head(const float* const* h_cls_levels, const float* const* h_reg_levels, int num_levels, int image_height,
+                          int image_width, const float* d_anchors, const float* d_annotations, int num_images, int num_classes,
+                          int gt_rows, const cldet_loss_params* params, const float* d_weights, float* d_baked_weights,
+                          float* const* h_grad_cls_levels, float* const* h_grad_reg_levels, float* d_losses, uint32_t* d_meta,
+                          float* d_iou_max, int32_t* d_npos, int32_t* d_nvalid, uint8_t* d_bg_mask, int32_t* d_status,
+                          void* d_workspace, size_t ws_bytes, void* stream) {
+    const bool grad = d_weights != nullptr;
+    HeadLevels lv;
+    int64_t A = 0;
+    int cpi = 0;
+    int rc = head_levels(h_cls_levels, h_reg_levels, h_grad_cls_levels, h_grad_reg_levels, num_levels, image_height, image_width,
+                         grad, &lv, &A, &cpi);
+    if (rc) return rc;
+    rc = check_common(lv.cls[0], d_anchors, d_annotations, num_images, A, num_classes, gt_rows, params);
+    if (rc) return rc;
+    if (!d_losses || !d_meta || !d_npos || !d_nvalid || !d_workspace) return CLDET_ERR_INVALID_ARGUMENT;
+    if (params->incremental && params->decrease_positive_by_iou && !d_iou_max) return CLDET_ERR_INVALID_ARGUMENT;
+    if (ws_bytes < workspace_bytes(num_images, A)) return CLDET_ERR_WORKSPACE_TOO_SMALL;
+    if ((uintptr_t)d_anchors & 15) return CLDET_ERR_INVALID_ARGUMENT;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (d_status) CLDET_CUDA_TRY(cudaMemsetAsync(d_status, 0, sizeof(int32_t), s));
+    int32_t* npos_acc = reinterpret_cast<int32_t*>(d_workspace) + num_images;
+    // assignment: GT-centric keys (the anchors must be the standard grid of this image size), except when the
+    // new_ignore_past_class pre-pass needs ready-made words
+    const bool needs_words = params->incremental && params->ignore_past_class && params->new_ignore_past_class &&
+                             params->past_class_num > 0;
+    unsigned long long* best = nullptr;
+    if (!needs_words) {
+        best = reinterpret_cast<unsigned long long*>(reinterpret_cast<char*>(d_workspace) + workspace_header_bytes(num_images) +
+                                                      workspace_partials_bytes(num_images, A));
+        rc = launch_gt_scatter(image_height, image_width, d_anchors, A, d_annotations, num_images, gt_rows, best, nullptr, npos_acc,
+                               d_nvalid, s);
+        if (rc) return rc;
+    } else {
+        rc = cldet_iou_assign(d_anchors, A, d_annotations, num_images, gt_rows, num_classes, d_meta, nullptr, d_iou_max, npos_acc,
+                              d_nvalid, stream);
+        if (rc) return rc;
+        if (params->cls_is_logits) run_head_flag_kernels<true>(lv, num_images, A, num_classes, params->past_class_num, d_meta, s);
+        else run_head_flag_kernels<false>(lv, num_images, A, num_classes, params->past_class_num, d_meta, s);
+        CLDET_LAUNCH_CHECK();
+    }
+    LossArgs a;
+    head_args(&a, d_anchors, d_annotations, num_images, A, num_classes, gt_rows, params, cpi, d_workspace);
+    for (int k = 0; k < 4; ++k) {
+        a.w_ptr[k] = d_weights ? d_weights + (size_t)k * num_images : nullptr;
+        a.w_stride[k] = 1;
+    }
+    a.has_w = grad ? 1 : 0;
+    a.baked_weights = d_baked_weights; a.losses = d_losses; a.meta = d_meta; a.iou_max = d_iou_max;
+    a.npos = npos_acc; a.npos_out = d_npos; a.npos_reset = npos_acc; a.bg_mask = d_bg_mask; a.status = d_status;
+    a.best = best; a.touched = nullptr; a.meta_out = d_meta; a.iou_out = best ? d_iou_max : nullptr; a.nvalid = d_nvalid;
+    dim3 grid((unsigned)cpi, (unsigned)num_images);
+    const bool gamma2 = params->gamma == 2.0f;
+    const bool variants = has_variants(*params);
+    if (params->cls_is_logits) run_head_loss_kernels<true>(a, lv, grad, gamma2, variants, grid, s);
+    else run_head_loss_kernels<false>(a, lv, grad, gamma2, variants, grid, s);
+    CLDET_LAUNCH_CHECK();
+    return CLDET_OK;
+}
+
+int cldet_focal_loss_head_reweight(const float* const* h_cls_levels, const float* const* h_reg_levels, int num_levels,
+                                   int image_height, int image_width, const float* d_anchors, const float* d_annotations,
+                                   int num_images, int num_classes, int gt_rows, const cldet_loss_params* params,
+                                   const float* d_w_bg, int64_t stride_bg, const float* d_w_fg, int64_t stride_fg,
+                                   const float* d_w_reg, int64_t stride_reg, const float* d_w_enh, int64_t stride_enh,
+                                   float* d_baked_weights, float* const* h_grad_cls_levels, float* const* h_grad_reg_levels,
+                                   const uint32_t* d_meta, const float* d_iou_max, const int32_t* d_npos, void* d_workspace,
+                                   size_t ws_bytes, void* stream) {
+    HeadLevels lv;
+    int64_t A = 0;
+    int cpi = 0;
+    int rc = head_levels(h_cls_levels, h_reg_levels, h_grad_cls_levels, h_grad_reg_levels, num_levels, image_height, image_width,
+                         true, &lv, &A, &cpi);
+    if (rc) return rc;
+    rc = check_common(lv.cls[0], d_anchors, d_annotations, num_images, A, num_classes, gt_rows, params);
+    if (rc) return rc;
+    if (!d_baked_weights || !d_meta || !d_npos || !d_workspace) return CLDET_ERR_INVALID_ARGUMENT;
+    if (params->incremental && params->decrease_positive_by_iou && !d_iou_max) return CLDET_ERR_INVALID_ARGUMENT;
+    if (ws_bytes < workspace_bytes(num_images, A)) return CLDET_ERR_WORKSPACE_TOO_SMALL;
+    cudaStream_t s = (cudaStream_t)stream;
+    LossArgs a;
+    head_args(&a, d_anchors, d_annotations, num_images, A, num_classes, gt_rows, params, cpi, d_workspace);
+    const float* w[4] = {d_w_bg, d_w_fg, d_w_reg, d_w_enh};
+    const int64_t st[4] = {stride_bg, stride_fg, stride_reg, stride_enh};
+    for (int k = 0; k < 4; ++k) {
+        a.w_ptr[k] = w[k];
+        a.w_stride[k] = (int)st[k];
+    }
+    a.has_w = 1;
+    a.baked_weights = d_baked_weights; a.meta = d_meta; a.iou_max = d_iou_max; a.npos = d_npos;
+    const int per_image = std::max(1, (sm_count() * 4 + num_images - 1) / num_images);
+    dim3 grid((unsigned)std::min(cpi, per_image), (unsigned)num_images);
+    const bool gamma2 = params->gamma == 2.0f;
+    const bool variants = has_variants(*params);
+    if (params->cls_is_logits) run_head_reweight_kernels<true>(a, lv, gamma2, variants, grid, s);
+    else run_head_reweight_kernels<false>(a, lv, gamma2, variants, grid, s);
+    CLDET_LAUNCH_CHECK();
+    return CLDET_OK;
 }
 
 }  // extern "C"

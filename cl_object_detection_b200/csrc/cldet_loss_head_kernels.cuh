@@ -1,0 +1,321 @@
+// K3h: the fused focal + smooth-L1 forward/backward reading the detection head's RAW conv outputs, one tensor per pyramid
+// level in the layout the convolutions produce: classification [N, 9*C, H_l, W_l] and regression [N, 9*4, H_l, W_l] (NCHW).
+//
+// Reference: ClassificationModel.forward / RegressionModel.forward (retinanet/model.py:133-214) turn every level's output into
+// [N, H_l*W_l*9, C] with permute(0,2,3,1) + contiguous() + view, ResNet.forward concatenates the five levels
+// (model.py:472-474), and autograd mirrors all of it in backward: 8 B/element for the permute copy, 8 for the cat, and the
+// same again for their gradients -- more traffic than the loss itself (8 B/element).  SURVEY 8(f) row f1 names this as the
+// step immediately before the path.  Here the layout change is index arithmetic: the element of anchor (y, x, k) and class c
+// lives at channel k*C + c, position y*W_l + x of its level's plane, and its gradient is written to the same place of a
+// gradient tensor of the same layout, which is exactly what the output convolution's backward wants.
+//
+// Work decomposition: a block owns kHeadPos consecutive positions of ONE level of ONE image with all 9*C channels, i.e.
+// 9*kHeadPos anchors.  For a fixed channel the positions are contiguous in memory, so the sweep is made of 256-byte rows read
+// with 128-bit loads (planes whose size is not a multiple of 4 floats -- the tiny top levels -- use 32-bit loads).  The
+// assignment words of the block's anchors sit in shared memory at [position][type]; a 64-bit mask per anchor type marks the
+// positions whose anchor is plain background, so the hot path (four background elements) costs one mask test per vector.
+#pragma once
+#include "cldet_loss_kernels.cuh"
+
+namespace cldet {
+
+#ifndef CLDET_HEAD_POS
+#define CLDET_HEAD_POS 64
+#endif
+constexpr int kHeadPos = CLDET_HEAD_POS;  // positions per block (a multiple of 64)
+constexpr int kHeadMaskWords = kHeadPos / 64;
+constexpr int kHeadMaxLevels = 8;
+constexpr int kHeadTypes = 9;           // anchors per position (3 ratios x 3 scales, retinanet/anchors.py:10-19)
+
+struct HeadLevels {
+    int n;                                       // pyramid levels
+    const float* cls[kHeadMaxLevels];            // [N, 9*C, hw]
+    const float* reg[kHeadMaxLevels];            // [N, 36, hw]
+    float* gcls[kHeadMaxLevels];
+    float* greg[kHeadMaxLevels];
+    int hw[kHeadMaxLevels];                      // H_l * W_l
+    int64_t anchor_off[kHeadMaxLevels + 1];      // level offsets inside the concatenated anchor index space
+    int chunk_off[kHeadMaxLevels + 1];           // level offsets inside the per-image chunk index space
+};
+
+// One element with target 0 in the general (gamma != 2 or IL variants) configuration, or target 1: defer to cls_element.
+// mode 0: losses + gradients; mode 1: gradients only (backward with different upstream weights).
+template <bool GAMMA2, bool VARIANTS, bool GRAD, bool LOGITS>
+__device__ __forceinline__ float head_element(float x, int c, uint32_t m, int64_t anchor_abs, const LossArgs& a,
+                                              const ImageScales& sc, float as_bg, bool need_iou, Acc& acc, int lane4) {
+    const uint32_t st = meta_state(m);
+    if (st == CLDET_STATE_IGNORE) return 0.0f;
+    const float p = LOGITS ? sigmoid_exact(x) : x;
+    float g;
+    const bool target1 = (st == CLDET_STATE_POS) && ((uint32_t)c == meta_label(m));
+    if (GAMMA2 && !VARIANTS && !target1) {
+        g = neg_element_raw<GRAD>(p, as_bg, acc.raw[lane4]);
+    } else {
+        float iou = 1.0f;
+        if (need_iou && st == CLDET_STATE_POS) iou = a.iou_max[anchor_abs];
+        g = cls_element<GAMMA2, VARIANTS, GRAD>(p, c, m, a, sc, iou, acc);
+    }
+    if (GRAD && LOGITS) g = sigmoid_bwd(g, p);
+    return g;
+}
+
+template <bool GAMMA2, bool VARIANTS, bool GRAD, bool LOGITS>
+__device__ __forceinline__ void head_chunk(const LossArgs& a, const HeadLevels& lv, int j, int chunk, int mode,
+                                           const ImageScales& sc, Acc& acc, uint32_t* smeta, unsigned long long* plain) {
+    const int tid = threadIdx.x;
+    int l = 0;
+    while (l + 1 < lv.n && chunk >= lv.chunk_off[l + 1]) ++l;
+    const int hw = lv.hw[l];
+    const int p0 = (chunk - lv.chunk_off[l]) * kHeadPos;
+    const int np = min(kHeadPos, hw - p0);
+    const int na = np * kHeadTypes;
+    const int64_t an0 = lv.anchor_off[l] + (int64_t)p0 * kHeadTypes;       // first anchor of the chunk, concatenated index
+    const int C = a.C;
+    const bool need_iou = VARIANTS && a.p.incremental && a.p.decrease_positive_by_iou;
+
+    // ---- regression gradient rows: zero everywhere, positives overwrite their four entries after the barrier ----
+    float* greg_img = GRAD ? lv.greg[l] + (int64_t)j * (kHeadTypes * 4) * hw + p0 : nullptr;
+    if (GRAD) {
+        for (int v = tid; v < kHeadTypes * 4 * np; v += kLossThreads) {
+            const int chr = v / np, pp = v - chr * np;
+            greg_img[(int64_t)chr * hw + pp] = 0.0f;
+        }
+    }
+    if (tid < kHeadTypes * kHeadMaskWords) plain[tid] = 0ull;
+    __syncthreads();
+
+    // ---- per-anchor prologue: assignment word, outputs keyed by anchor, smooth-L1 for the positives ----
+    const int nvalid_j = (mode == 0 && a.best) ? a.nvalid[j] : 1;
+    const float* reg_img = lv.reg[l] + (int64_t)j * (kHeadTypes * 4) * hw + p0;
+    for (int i = tid; i < na; i += kLossThreads) {
+        const int64_t an = an0 + i;
+        const int64_t gi = (int64_t)j * a.A + an;
+        uint32_t m;
+        if (mode == 0 && a.best) {
+            const unsigned long long key = a.best[gi];
+            if (key) a.best[gi] = 0ull;                       // leave the scratch zeroed for the next call
+            m = word_from_best(a, j, key, nvalid_j);
+            a.meta_out[gi] = m;
+            if (a.iou_out) a.iou_out[gi] = __uint_as_float((uint32_t)(key >> 32));
+        } else {
+            m = a.meta[gi];
+        }
+        smeta[i] = m;
+        const uint32_t st = meta_state(m);
+        const int pp = i / kHeadTypes, k = i - pp * kHeadTypes;
+        if (st == CLDET_STATE_BG || st == CLDET_STATE_EMPTY) atomicOr(&plain[k * kHeadMaskWords + (pp >> 6)], 1ull << (pp & 63));
+        if (mode == 0 && a.bg_mask) a.bg_mask[gi] = (st != CLDET_STATE_POS) ? 1 : 0;
+        if (st == CLDET_STATE_POS) {
+            const float* rp = reg_img + (int64_t)(k * 4) * hw + pp;
+            const float4 r = make_float4(rp[0], rp[hw], rp[2 * (int64_t)hw], rp[3 * (int64_t)hw]);
+            float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+            acc.reg += reg_anchor<GRAD>(a, j, an, m, r, sc.s_reg, g);
+            if (mode == 0 && a.status && meta_label(m) == CLDET_BAD_LABEL) *a.status = 1;
+            if (GRAD) {
+                float* gp = greg_img + (int64_t)(k * 4) * hw + pp;
+                gp[0] = g.x;
+                gp[hw] = g.y;
+                gp[2 * (int64_t)hw] = g.z;
+                gp[3 * (int64_t)hw] = g.w;
+            }
+        }
+    }
+    __syncthreads();
+
+    // ---- classification planes: rows of `np` contiguous positions, one row per channel ----
+    const float alpha_img = (meta_state(smeta[0]) == CLDET_STATE_EMPTY) ? 1.0f - a.p.alpha : a.p.alpha;
+    const float as_bg = alpha_img * sc.s_bg;
+    const float* src = lv.cls[l] + (int64_t)j * (kHeadTypes * C) * hw + p0;
+    float* dst = GRAD ? lv.gcls[l] + (int64_t)j * (kHeadTypes * C) * hw + p0 : nullptr;
+    const int nch = kHeadTypes * C;
+    const bool vec_ok = (np == kHeadPos) && ((hw & 3) == 0) &&
+                        ((((uintptr_t)lv.cls[l] | (uintptr_t)lv.gcls[l]) & 15) == 0);
+    if (vec_ok) {
+        constexpr int kVecPerRow = kHeadPos / 4;                         // 16
+        constexpr int kU = 4;                                            // vectors in flight per thread
+        const int nvec = nch * kVecPerRow;
+        const int q = tid & (kVecPerRow - 1);                            // this thread's vector inside a row: fixed
+        for (int v0 = tid; v0 < nvec; v0 += kLossThreads * kU) {
+            float4 x[kU];
+            int chv[kU];
+#pragma unroll
+            for (int u = 0; u < kU; ++u) {
+                const int v = v0 + u * kLossThreads;
+                chv[u] = v / kVecPerRow;
+                if (v < nvec) {
+                    const float* sp = src + (int64_t)chv[u] * hw + 4 * q;
+                    asm volatile(CLDET_LD_QUAL ".v4.f32 {%0,%1,%2,%3}, [%4];"
+                                 : "=f"(x[u].x), "=f"(x[u].y), "=f"(x[u].z), "=f"(x[u].w)
+                                 : "l"(sp));
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < kU; ++u) {
+                if (v0 + u * kLossThreads >= nvec) break;
+                const int ch = chv[u];
+                const int k = (int)fast_div((uint32_t)ch, (uint32_t)C, a.div_magic);
+                const int c = ch - k * C;
+                const uint32_t plain4 = (uint32_t)(plain[k * kHeadMaskWords + ((4 * q) >> 6)] >> ((4 * q) & 63)) & 0xFu;
+                float4 g;
+                if (GAMMA2 && !VARIANTS && plain4 == 0xFu) {
+                    // four plain background anchors (or an image without GT): the hot path
+                    const float p0v = LOGITS ? sigmoid_exact(x[u].x) : x[u].x;
+                    const float p1v = LOGITS ? sigmoid_exact(x[u].y) : x[u].y;
+                    const float p2v = LOGITS ? sigmoid_exact(x[u].z) : x[u].z;
+                    const float p3v = LOGITS ? sigmoid_exact(x[u].w) : x[u].w;
+                    g.x = neg_element_raw<GRAD>(p0v, as_bg, acc.raw[0]);
+                    g.y = neg_element_raw<GRAD>(p1v, as_bg, acc.raw[1]);
+                    g.z = neg_element_raw<GRAD>(p2v, as_bg, acc.raw[2]);
+                    g.w = neg_element_raw<GRAD>(p3v, as_bg, acc.raw[3]);
+                    if (GRAD && LOGITS) {
+                        g.x = sigmoid_bwd(g.x, p0v);
+                        g.y = sigmoid_bwd(g.y, p1v);
+                        g.z = sigmoid_bwd(g.z, p2v);
+                        g.w = sigmoid_bwd(g.w, p3v);
+                    }
+                } else {
+                    const uint32_t* mp = smeta + (4 * q) * kHeadTypes + k;
+                    const int64_t ab = (int64_t)j * a.A + an0 + (4 * q) * kHeadTypes + k;
+                    g.x = head_element<GAMMA2, VARIANTS, GRAD, LOGITS>(x[u].x, c, mp[0], ab, a, sc, as_bg, need_iou, acc, 0);
+                    g.y = head_element<GAMMA2, VARIANTS, GRAD, LOGITS>(x[u].y, c, mp[kHeadTypes], ab + kHeadTypes, a, sc, as_bg, need_iou, acc, 1);
+                    g.z = head_element<GAMMA2, VARIANTS, GRAD, LOGITS>(x[u].z, c, mp[2 * kHeadTypes], ab + 2 * kHeadTypes, a, sc, as_bg, need_iou, acc, 2);
+                    g.w = head_element<GAMMA2, VARIANTS, GRAD, LOGITS>(x[u].w, c, mp[3 * kHeadTypes], ab + 3 * kHeadTypes, a, sc, as_bg, need_iou, acc, 3);
+                }
+                if (GRAD) {
+                    float* dp = dst + (int64_t)ch * hw + 4 * q;
+                    asm volatile(CLDET_ST_QUAL ".v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(dp), "f"(g.x), "f"(g.y), "f"(g.z), "f"(g.w)
+                                 : "memory");
+                }
+            }
+        }
+    } else {
+        // ragged chunk or a plane that is not a multiple of four floats: 32-bit accesses, positions fastest
+        const int total = nch * np;
+        for (int e = tid; e < total; e += kLossThreads) {
+            const int ch = e / np, pp = e - ch * np;
+            const int k = ch / C, c = ch - k * C;
+            const float x = src[(int64_t)ch * hw + pp];
+            const float g = head_element<GAMMA2, VARIANTS, GRAD, LOGITS>(x, c, smeta[pp * kHeadTypes + k],
+                                                                         (int64_t)j * a.A + an0 + pp * kHeadTypes + k, a, sc, as_bg,
+                                                                         need_iou, acc, e & 3);
+            if (GRAD) dst[(int64_t)ch * hw + pp] = g;
+        }
+    }
+}
+
+template <bool GAMMA2, bool VARIANTS, bool GRAD, bool LOGITS>
+__global__ void __launch_bounds__(kLossThreads, 4) focal_loss_head_kernel(const LossArgs a, const HeadLevels lv) {
+    __shared__ float red[4][kLossThreads / 32];
+    __shared__ double fin[4][kLossThreads / 32];
+    __shared__ bool is_last;
+    __shared__ uint32_t smeta[kHeadPos * kHeadTypes];
+    __shared__ unsigned long long plain[kHeadTypes * kHeadMaskWords];
+
+    const int j = blockIdx.y;
+    const int npos = a.npos[j];
+    const ImageScales sc = image_scales(a, j, npos);
+    Acc acc = {0.f, 0.f, 0.f, 0.f, {0.f, 0.f, 0.f, 0.f}};
+    head_chunk<GAMMA2, VARIANTS, GRAD, LOGITS>(a, lv, j, (int)blockIdx.x, 0, sc, acc, smeta, plain);
+    finish_block(a, j, (int)blockIdx.x, acc, npos, sc, red, fin, &is_last);
+}
+
+// Backward with upstream weights that differ from the baked ones: the image's gradients are recomputed (one mode only; the
+// positives-only patch of the concatenated layout is not worth a second code path here).
+template <bool GAMMA2, bool VARIANTS, bool LOGITS>
+__global__ void __launch_bounds__(kLossThreads, 4) focal_head_reweight_kernel(const LossArgs a, const HeadLevels lv) {
+    __shared__ uint32_t smeta[kHeadPos * kHeadTypes];
+    __shared__ unsigned long long plain[kHeadTypes * kHeadMaskWords];
+    const int j = blockIdx.y;
+    const float* wo = a.baked_weights + j;
+    const int N = a.N;
+    const float wn[4] = {weight_of(a, 0, j), weight_of(a, 1, j), weight_of(a, 2, j), weight_of(a, 3, j)};
+    const bool enh_on = a.p.incremental && a.p.enhance_on_new;
+    const bool changed = (wn[0] != wo[0]) || (wn[1] != wo[N]) || (wn[2] != wo[2 * N]) || (enh_on && wn[3] != wo[3 * N]);
+    if (!changed) return;
+    const ImageScales sc = image_scales(a, j, a.npos[j]);
+    for (int chunk = blockIdx.x; chunk < a.bpi; chunk += gridDim.x) {
+        Acc acc = {0.f, 0.f, 0.f, 0.f, {0.f, 0.f, 0.f, 0.f}};
+        head_chunk<GAMMA2, VARIANTS, true, LOGITS>(a, lv, j, chunk, 1, sc, acc, smeta, plain);
+        __syncthreads();
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        const unsigned int done = atomicAdd(&a.rw_counters[j], 1u);
+        if (done == gridDim.x - 1u) {
+            float* wb = a.baked_weights + j;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) wb[k * N] = wn[k];
+            a.rw_counters[j] = 0;
+        }
+    }
+}
+
+// new_ignore_past_class pre-pass (losses.py:326-327) on the head layout: one thread per anchor, positions fastest so that the
+// loads of one class column are coalesced.
+template <bool LOGITS>
+__global__ void __launch_bounds__(256) old_class_flag_head_kernel(const HeadLevels lv, int level, int64_t A, int C, int past,
+                                                                  uint32_t* __restrict__ meta) {
+    const int j = blockIdx.y;
+    const int hw = lv.hw[level];
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= hw * kHeadTypes) return;
+    const int k = t / hw, pp = t - k * hw;
+    const int64_t an = lv.anchor_off[level] + (int64_t)pp * kHeadTypes + k;
+    uint32_t m = meta[(int64_t)j * A + an] & ~CLDET_META_OLD_ACTIVE;
+    if (meta_state(m) == CLDET_STATE_BG) {
+        const float* base = lv.cls[level] + ((int64_t)j * (kHeadTypes * C) + (int64_t)k * C) * hw + pp;
+        float s = 0.0f;
+        for (int c = 0; c < past; ++c) {
+            const float x = base[(int64_t)c * hw];
+            s = __fadd_rn(s, fminf(fmaxf(LOGITS ? sigmoid_exact(x) : x, 1e-4f), 0.9999f));
+        }
+        if (s < 0.5f) m |= CLDET_META_OLD_ACTIVE;
+    }
+    meta[(int64_t)j * A + an] = m;
+}
+
+template <bool LOGITS>
+void run_head_loss_kernels(const LossArgs& a, const HeadLevels& lv, bool grad, bool gamma2, bool variants, dim3 grid, cudaStream_t s) {
+#define CLDET_HEAD_LAUNCH(G2, VAR)                                                                              \
+    do {                                                                                                        \
+        if (grad) focal_loss_head_kernel<G2, VAR, true, LOGITS><<<grid, kLossThreads, 0, s>>>(a, lv);           \
+        else focal_loss_head_kernel<G2, VAR, false, LOGITS><<<grid, kLossThreads, 0, s>>>(a, lv);               \
+    } while (0)
+    if (gamma2) {
+        if (variants) CLDET_HEAD_LAUNCH(true, true);
+        else CLDET_HEAD_LAUNCH(true, false);
+    } else {
+        if (variants) CLDET_HEAD_LAUNCH(false, true);
+        else CLDET_HEAD_LAUNCH(false, false);
+    }
+#undef CLDET_HEAD_LAUNCH
+}
+
+template <bool LOGITS>
+void run_head_reweight_kernels(const LossArgs& a, const HeadLevels& lv, bool gamma2, bool variants, dim3 grid, cudaStream_t s) {
+    if (gamma2) {
+        if (variants) focal_head_reweight_kernel<true, true, LOGITS><<<grid, kLossThreads, 0, s>>>(a, lv);
+        else focal_head_reweight_kernel<true, false, LOGITS><<<grid, kLossThreads, 0, s>>>(a, lv);
+    } else {
+        if (variants) focal_head_reweight_kernel<false, true, LOGITS><<<grid, kLossThreads, 0, s>>>(a, lv);
+        else focal_head_reweight_kernel<false, false, LOGITS><<<grid, kLossThreads, 0, s>>>(a, lv);
+    }
+}
+
+template <bool LOGITS>
+void run_head_flag_kernels(const HeadLevels& lv, int N, int64_t A, int C, int past, uint32_t* meta, cudaStream_t s) {
+    for (int l = 0; l < lv.n; ++l) {
+        dim3 g((unsigned)((lv.hw[l] * kHeadTypes + 255) / 256), (unsigned)N);
+        old_class_flag_head_kernel<LOGITS><<<g, 256, 0, s>>>(lv, l, A, C, past, meta);
+    }
+}
+
+extern template void run_head_loss_kernels<true>(const LossArgs&, const HeadLevels&, bool, bool, bool, dim3, cudaStream_t);
+extern template void run_head_loss_kernels<false>(const LossArgs&, const HeadLevels&, bool, bool, bool, dim3, cudaStream_t);
+extern template void run_head_reweight_kernels<true>(const LossArgs&, const HeadLevels&, bool, bool, dim3, cudaStream_t);
+extern template void run_head_reweight_kernels<false>(const LossArgs&, const HeadLevels&, bool, bool, dim3, cudaStream_t);
+extern template void run_head_flag_kernels<true>(const HeadLevels&, int, int64_t, int, int, uint32_t*, cudaStream_t);
+extern template void run_head_flag_kernels<false>(const HeadLevels&, int, int64_t, int, int, uint32_t*, cudaStream_t);
+
+}  // namespace cldet

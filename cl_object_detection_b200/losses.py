@@ -202,6 +202,85 @@ class _FocalLossFn(torch.autograd.Function):
         return gcls, greg, None, None, None, None, None, None, None
 
 
+class _FocalLossHeadFn(torch.autograd.Function):
+    """The fused loss on the head's raw conv outputs (cldet_focal_loss_head).  Tensor inputs: 5 classification levels
+    [N, 9*C, H_l, W_l] followed by 5 regression levels [N, 36, H_l, W_l]; outputs as _FocalLossFn."""
+
+    @staticmethod
+    def forward(ctx, anchors, annotations, lp, hint, want_bg_mask, check_labels, hw, *levels):
+        lib = _lib.load()
+        nl = len(levels) // 2
+        cls_lv, reg_lv = levels[:nl], levels[nl:]
+        n = cls_lv[0].shape[0]
+        c = cls_lv[0].shape[1] // 9
+        a = anchors.shape[1]
+        g = annotations.shape[1]
+        dev = cls_lv[0].device
+        need_grad = any(ctx.needs_input_grad[7:])
+        with _DeviceGuard(dev):
+            stream = _stream()
+            losses = torch.empty((4, n), dtype=torch.float32, device=dev)
+            meta = torch.empty((n, a), dtype=torch.int32, device=dev)
+            iou_max = torch.empty((n, a), dtype=torch.float32, device=dev) if lp.decrease_positive_by_iou else None
+            counts = torch.empty((2, n), dtype=torch.int32, device=dev)
+            npos, nvalid = counts[0], counts[1]
+            bg_mask = torch.empty((n, a), dtype=torch.uint8, device=dev) if want_bg_mask else None
+            status = torch.empty(1, dtype=torch.int32, device=dev) if check_labels else None
+            ws = _workspace(dev, stream, n, a)
+            if need_grad:
+                baked = torch.empty((4, n), dtype=torch.float32, device=dev)
+                gcls = [torch.empty_like(t) for t in cls_lv]
+                greg = [torch.empty_like(t) for t in reg_lv]
+            else:
+                hint = baked = gcls = greg = None
+            try:
+                _lib.check(lib.cldet_focal_loss_head(
+                    _lib.ptr_array(cls_lv), _lib.ptr_array(reg_lv), nl, hw[0], hw[1], anchors.data_ptr(), annotations.data_ptr(),
+                    n, c, g, lp, _lib.ptr(hint), _lib.ptr(baked), _lib.ptr_array(gcls), _lib.ptr_array(greg), losses.data_ptr(),
+                    meta.data_ptr(), _lib.ptr(iou_max), npos.data_ptr(), nvalid.data_ptr(), _lib.ptr(bg_mask), _lib.ptr(status),
+                    ws.data_ptr(), ws.numel(), stream))
+            except Exception:
+                _drop_workspaces()
+                raise
+        if check_labels and int(status.item()) != 0:
+            raise IndexError('a GT label is outside [0, %d): the reference indexes the class dimension with it '
+                             '(losses.py:341)' % c)
+        ctx.lp, ctx.hw, ctx.nl, ctx.shape = lp, hw, nl, (n, a, c, g)
+        ctx.backward_calls = 0
+        if need_grad:
+            ctx.save_for_backward(anchors, annotations, baked, meta, npos, *cls_lv, *reg_lv, *gcls, *greg)
+            ctx.iou_max = iou_max
+            ctx.ws = ws
+        ctx.mark_non_differentiable(npos, nvalid)
+        outs = (losses[0], losses[1], losses[2], losses[3], npos, nvalid)
+        if want_bg_mask:
+            ctx.mark_non_differentiable(bg_mask)
+            outs = outs + (bg_mask,)
+        return outs
+
+    @staticmethod
+    def backward(ctx, g_bg, g_fg, g_reg, g_enh, *unused):
+        saved = ctx.saved_tensors
+        anchors, annotations, baked, meta, npos = saved[:5]
+        nl = ctx.nl
+        cls_lv, reg_lv = saved[5:5 + nl], saved[5 + nl:5 + 2 * nl]
+        gcls, greg = saved[5 + 2 * nl:5 + 3 * nl], saved[5 + 3 * nl:5 + 4 * nl]
+        n, a, c, g = ctx.shape
+        rows = [_row(t) for t in (g_bg, g_fg, g_reg, g_enh)]
+        with _DeviceGuard(anchors.device):
+            _lib.check(_lib.load().cldet_focal_loss_head_reweight(
+                _lib.ptr_array(cls_lv), _lib.ptr_array(reg_lv), nl, ctx.hw[0], ctx.hw[1], anchors.data_ptr(),
+                annotations.data_ptr(), n, c, g, ctx.lp, _lib.ptr(rows[0][0]), rows[0][1], _lib.ptr(rows[1][0]), rows[1][1],
+                _lib.ptr(rows[2][0]), rows[2][1], _lib.ptr(rows[3][0]), rows[3][1], baked.data_ptr(), _lib.ptr_array(gcls),
+                _lib.ptr_array(greg), meta.data_ptr(), _lib.ptr(ctx.iou_max), npos.data_ptr(), ctx.ws.data_ptr(),
+                ctx.ws.numel(), _stream()))
+        ctx.backward_calls += 1
+        grads = list(gcls) + list(greg)
+        if ctx.backward_calls > 1:
+            grads = [t.clone() for t in grads]
+        return (None,) * 7 + tuple(grads)
+
+
 class FocalLoss(nn.Module):
     """Same call signature and result dict as the reference module (losses.py:252-253, 444-452).
 
@@ -272,6 +351,56 @@ class FocalLoss(nn.Module):
         if incremental:
             if params['distill']:
                 # the reference appends a mask only for images that have GT (quirk Q6): M <= N rows
+                result['bg_masks'] = outs[6].bool()[nvalid > 0]
+            if params['enhance_on_new']:
+                result['enhance_on_new_loss'] = enh_j.sum()
+        self.last_npos, self.last_nvalid, self.last_reg_per_image = npos, nvalid, reg_j
+        return result
+
+    def forward_head(self, cls_levels, reg_levels, anchors, annotations, cur_state: int, params, image_size, progress=-1):
+        """SURVEY 8(f) row f1, second half: FocalLoss on the head's RAW conv outputs (beyond the reference's signature).
+
+        cls_levels / reg_levels: the five per-level results of the classification / regression output convolutions as they
+        come out of the conv, [N, 9*C, H_l, W_l] and [N, 36, H_l, W_l] (contiguous NCHW) -- i.e. `self.output(out)` (after
+        `self.output_act` unless from_logits=True) of ClassificationModel / RegressionModel BEFORE their
+        permute + contiguous + view (retinanet/model.py:125-130, 170-184) and before ResNet.forward's torch.cat
+        (model.py:472-474).  image_size = (H, W) of the input batch; anchors = Anchors()(img) for it.  Returns the same
+        dict as forward(); gradients flow to the level tensors in their own layout."""
+        cls_lv = [_check_cuda_f32('cls_levels[%d]' % i, t) for i, t in enumerate(cls_levels)]
+        reg_lv = [_check_cuda_f32('reg_levels[%d]' % i, t) for i, t in enumerate(reg_levels)]
+        anc = _check_cuda_f32('anchors', anchors)
+        ann = _check_cuda_f32('annotations', annotations)
+        h, w = int(image_size[0]), int(image_size[1])
+        if len(cls_lv) != 5 or len(reg_lv) != 5:
+            raise ValueError('expected the 5 pyramid levels (3..7) of both heads')
+        n = cls_lv[0].shape[0]
+        if cls_lv[0].dim() != 4 or cls_lv[0].shape[1] % 9 != 0:
+            raise ValueError('classification levels must be [N, 9*C, H_l, W_l]')
+        c = cls_lv[0].shape[1] // 9
+        total = 0
+        for l in range(5):
+            hl, wl = (h + 2 ** (l + 3) - 1) // 2 ** (l + 3), (w + 2 ** (l + 3) - 1) // 2 ** (l + 3)
+            if tuple(cls_lv[l].shape) != (n, 9 * c, hl, wl) or tuple(reg_lv[l].shape) != (n, 36, hl, wl):
+                raise ValueError('level %d: expected cls [%d,%d,%d,%d] and reg [%d,36,%d,%d] for a %dx%d input'
+                                 % (l + 3, n, 9 * c, hl, wl, n, hl, wl, h, w))
+            total += 9 * hl * wl
+        if anc.dim() != 3 or anc.shape[0] != 1 or anc.shape[1] != total or anc.shape[2] != 4:
+            raise ValueError('anchors must be [1,%d,4] for a %dx%d input' % (total, h, w))
+        if grid_of(anc) != (h, w):
+            raise ValueError('forward_head needs the anchors made by cl_object_detection_b200.Anchors for this image size')
+        if ann.dim() != 3 or ann.shape[0] != n or ann.shape[2] != 5 or ann.shape[1] == 0:
+            raise ValueError('annotations must be [N,G>=1,5]')
+        lp = to_loss_params(params, int(cur_state), c)
+        lp.cls_is_logits = int(self.from_logits)
+        lp.image_height, lp.image_width = h, w
+        incremental = cur_state > 0
+        want_mask = bool(incremental and params['distill'])
+        outs = _FocalLossHeadFn.apply(anc, ann, lp, self._hint(n, anc.device), want_mask, self.check_labels, (h, w),
+                                      *cls_lv, *reg_lv)
+        bg, fg, reg_j, enh_j, npos, nvalid = outs[:6]
+        result = {'cls_loss': (bg, fg), 'reg_loss': reg_j.mean(dim=0, keepdim=True)}
+        if incremental:
+            if params['distill']:
                 result['bg_masks'] = outs[6].bool()[nvalid > 0]
             if params['enhance_on_new']:
                 result['enhance_on_new_loss'] = enh_j.sum()

@@ -205,6 +205,39 @@ int cldet_focal_loss_reweight_rows(const float* d_cls, const float* d_reg, const
                                    float* d_grad_reg, const uint32_t* d_meta, const float* d_iou_max, const int32_t* d_npos,
                                    void* d_workspace, size_t workspace_bytes, void* stream);
 
+/* ---- SURVEY 8(f) row f1, second half: the head's RAW conv outputs in, gradients of the same layout out ----
+ * Replaces, for training, the layout work between the output convolutions and FocalLoss: ClassificationModel.forward /
+ * RegressionModel.forward (retinanet/model.py:125-130, 170-184: permute(0,2,3,1) + contiguous() + view per level),
+ * torch.cat over the five levels in ResNet.forward (model.py:472-474), optionally classifier_act = Sigmoid
+ * (params->cls_is_logits), and the mirror image of all of it in autograd's backward.
+ *   h_cls_levels / h_reg_levels: HOST arrays of num_levels (= 5, pyramid levels 3..7) DEVICE pointers; level l holds the
+ *            output convolution's result as is: classification [N, 9*C, H_l, W_l] (channel = k*C + c for anchor type k and
+ *            class c), regression [N, 36, H_l, W_l] (channel = k*4 + i), contiguous NCHW, fp32, with
+ *            H_l = ceil(image_height / 2^l), W_l = ceil(image_width / 2^l) (retinanet/anchors.py:25).
+ *   h_grad_cls_levels / h_grad_reg_levels: host arrays of device pointers to gradient tensors of the same shapes, written
+ *            completely; both NULL (together with d_weights) when no gradients are wanted.
+ *   d_anchors [A,4]: the standard grid of (image_height, image_width) (cldet_anchors), A = 9 * sum_l H_l*W_l.
+ *   Everything else (annotations, params, weights/baked weights, d_losses [4,N], d_meta / d_iou_max / d_bg_mask [N,A] in the
+ *   reference's concatenated anchor order, d_npos, d_nvalid, d_status, workspace of cldet_focal_loss_workspace_bytes(N, A))
+ *   means what it means for cldet_focal_loss.  Results: per-image terms equal to cldet_focal_loss on the permuted +
+ *   concatenated tensors up to summation order; gradients equal element for element. */
+int cldet_focal_loss_head(const float* const* h_cls_levels, const float* const* h_reg_levels, int num_levels, int image_height,
+                          int image_width, const float* d_anchors, const float* d_annotations, int num_images, int num_classes,
+                          int gt_rows, const cldet_loss_params* params, const float* d_weights, float* d_baked_weights,
+                          float* const* h_grad_cls_levels, float* const* h_grad_reg_levels, float* d_losses, uint32_t* d_meta,
+                          float* d_iou_max, int32_t* d_npos, int32_t* d_nvalid, uint8_t* d_bg_mask, int32_t* d_status,
+                          void* d_workspace, size_t workspace_bytes, void* stream);
+/* Backward of cldet_focal_loss_head with upstream weights that differ from the baked ones (rows as in
+ * cldet_focal_loss_reweight_rows): images whose weights changed are recomputed, the others are skipped. */
+int cldet_focal_loss_head_reweight(const float* const* h_cls_levels, const float* const* h_reg_levels, int num_levels,
+                                   int image_height, int image_width, const float* d_anchors, const float* d_annotations,
+                                   int num_images, int num_classes, int gt_rows, const cldet_loss_params* params,
+                                   const float* d_w_bg, int64_t stride_bg, const float* d_w_fg, int64_t stride_fg,
+                                   const float* d_w_reg, int64_t stride_reg, const float* d_w_enh, int64_t stride_enh,
+                                   float* d_baked_weights, float* const* h_grad_cls_levels, float* const* h_grad_reg_levels,
+                                   const uint32_t* d_meta, const float* d_iou_max, const int32_t* d_npos, void* d_workspace,
+                                   size_t workspace_bytes, void* stream);
+
 /* ---- head-distillation terms of IL_Loss (retinanet/losses.py:705-737) ----
  * d_cls [N,A,C] current logits, d_prev_cls [N,A,P] previous-model logits (P = past_class_num), d_reg / d_prev_reg [N,A,4],
  * d_bg_mask [N,A] uint8 (FocalLoss 'bg_masks').  prev_fg_mask = sigmoid(prev_cls) > 0.05; reg_mask = bg_mask & any(prev_fg_mask);

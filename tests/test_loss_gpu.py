@@ -528,3 +528,96 @@ def test_full_size_vs_torch_eager_on_the_same_device(h, w, C, N, G, exact, empty
     gr, rr = got[4], ref[4]
     assert torch.equal(gr == 0, rr == 0)
     assert ((gr - rr).abs() - 1e-5 * rr.abs()).max().item() <= 1e-5 * rr.abs().max().item()
+
+
+# ---- SURVEY 8(f) row f1, second half: the loss on the head's raw conv outputs (per-level NCHW) ----
+def _level_shapes(h, w):
+    return [((h + 2 ** l - 1) // 2 ** l, (w + 2 ** l - 1) // 2 ** l) for l in range(3, 8)]
+
+
+def _to_levels(x, h, w, per_anchor):
+    """[N, A, per_anchor] in the reference's concatenated order -> five [N, 9*per_anchor, H_l, W_l] conv-layout tensors."""
+    out, off = [], 0
+    n = x.shape[0]
+    for hl, wl in _level_shapes(h, w):
+        cnt = hl * wl * 9
+        lvl = x[:, off:off + cnt].reshape(n, hl, wl, 9 * per_anchor).permute(0, 3, 1, 2).contiguous()
+        out.append(lvl)
+        off += cnt
+    assert off == x.shape[1]
+    return out
+
+
+def _from_levels(levels, per_anchor):
+    """What the reference does to the conv outputs: permute(0,2,3,1) + contiguous + view per level (model.py:125-130,
+    170-184), then torch.cat over the levels (model.py:472-474)."""
+    return torch.cat([t.permute(0, 2, 3, 1).contiguous().view(t.shape[0], -1, per_anchor) for t in levels], dim=1)
+
+
+@pytest.mark.parametrize('case', ['state0_voc', 'state0_allempty', 'state0_gamma15', 'il_default_pseudo', 'il_ignore_past',
+                                  'il_new_ignore_past', 'il_distill_enhance', 'il_decrease_by_iou', 'il_all_flags'])
+def test_head_layout_golden_reference(case):
+    """The golden fixtures of the unmodified reference, fed in conv layout: losses 1e-5, gradients (mapped back) 1e-5."""
+    g = load('focal_' + case)
+    h, w = int(g['h']), int(g['w'])
+    params = head_params(g)
+    anchors = cld.generate_anchors(h, w, DEV)
+    cls_lv = [t.requires_grad_(True) for t in _to_levels(cu(g['cls']), h, w, g['cls'].shape[2])]
+    reg_lv = [t.requires_grad_(True) for t in _to_levels(cu(g['reg']), h, w, 4)]
+    out = cld.FocalLoss().forward_head(cls_lv, reg_lv, anchors, cu(g['ann']), int(g['cur_state']), params, (h, w),
+                                       progress=float(g['progress']))
+    bg, fg = out['cls_loss']
+    check_rel(bg.detach().cpu().numpy(), g['bg'])
+    check_rel(fg.detach().cpu().numpy(), g['fg'])
+    check_rel(out['reg_loss'].detach().cpu().numpy(), g['reg_loss'])
+    loss = (bg * cu(g['wb'])).sum() + (fg * cu(g['wf'])).sum() + out['reg_loss'].sum() * float(g['wr'])
+    if 'enhance_on_new_loss' in g:
+        check_rel(out['enhance_on_new_loss'].detach().cpu().numpy(), g['enhance_on_new_loss'])
+        loss = loss + out['enhance_on_new_loss'] * float(g['we'])
+    if 'bg_masks' in g:
+        assert np.array_equal(out['bg_masks'].cpu().numpy(), g['bg_masks'])
+    loss.backward()
+    check_grad_cls(_from_levels([t.grad for t in cls_lv], g['cls'].shape[2]).cpu().numpy(), g['grad_cls'])
+    check_grad_reg(_from_levels([t.grad for t in reg_lv], 4).cpu().numpy(), g['grad_reg'])
+
+
+@pytest.mark.parametrize('h,w,C,N,G,logits,empty', [(512, 512, 20, 3, 10, False, (1,)), (800, 1333, 80, 2, 20, False, ()),
+                                                    (800, 1333, 80, 2, 20, True, (0,)), (33, 70, 4, 2, 6, False, ()),
+                                                    (608, 1024, 16, 2, 20, True, ())])
+def test_head_layout_equals_concatenated_path(h, w, C, N, G, logits, empty):
+    """Conv-layout entry vs the reference's own permute + contiguous + view + cat followed by the concatenated-layout kernel,
+    gradients flowing back through those layout ops by autograd: every level, every element."""
+    rng = np.random.default_rng(h + w + C)
+    anchors = cld.generate_anchors(h, w, DEV)
+    gen = torch.Generator(device=DEV).manual_seed(h + C)
+    shapes = _level_shapes(h, w)
+    raw = [torch.randn(N, 9 * C, hl, wl, device=DEV, generator=gen) * 2 - 4 for hl, wl in shapes]
+    if not logits:
+        raw = [torch.sigmoid(t) for t in raw]
+    regs = [torch.randn(N, 36, hl, wl, device=DEV, generator=gen) for hl, wl in shapes]
+    ann = cu(synth_gt(rng, N, G, h, w, C, empty=empty))
+    wb = torch.rand(N, device=DEV, generator=gen) + 0.5
+    wf = torch.rand(N, device=DEV, generator=gen) + 0.5
+    fl = cld.FocalLoss(from_logits=logits)
+
+    def run(head):
+        cl = [t.clone().requires_grad_(True) for t in raw]
+        rl = [t.clone().requires_grad_(True) for t in regs]
+        if head:
+            out = fl.forward_head(cl, rl, anchors, ann, 0, cld.HeadParams(), (h, w))
+        else:
+            out = fl(_from_levels(cl, C), _from_levels(rl, 4), anchors, ann, 0, cld.HeadParams())
+        bg, fg = out['cls_loss']
+        ((bg * wb).sum() + (fg * wf).sum() + 0.7 * out['reg_loss'].sum()).backward()
+        return bg.detach(), fg.detach(), out['reg_loss'].detach(), [t.grad for t in cl], [t.grad for t in rl]
+
+    got, ref = run(True), run(False)
+    for k in range(3):
+        check_rel(got[k].cpu().numpy(), ref[k].cpu().numpy(), 2e-6)
+    for a_, b_ in zip(got[3], ref[3]):
+        assert torch.equal(a_ == 0, b_ == 0)
+        # target-0 elements sharing a vector with a positive's label take the general formula in one layout and the
+        # factored hot-path formula in the other: same value, different rounding (~1e-7)
+        assert ((a_ - b_).abs() <= 2e-6 * b_.abs()).all()
+    for a_, b_ in zip(got[4], ref[4]):
+        assert torch.equal(a_, b_)
