@@ -77,8 +77,9 @@ struct Workspace {
 static size_t workspace_header_bytes(int N) { return ((size_t)N * 3 * sizeof(unsigned int) + 255) / 256 * 256; }
 
 static size_t workspace_partials_bytes(int N, int64_t A) {
-    // worst case bpi: 32 anchors per block
-    const int64_t max_bpi = (A + 31) / 32;
+    // worst case bpi: 32 anchors per block (concatenated layout); the head layout has 9 * ceil(hw_l / kHeadPos) blocks per
+    // level, i.e. at most A / kHeadPos + 9 per level
+    const int64_t max_bpi = (A + 31) / 32 + kHeadTypes * kHeadMaxLevels;
     return ((size_t)N * max_bpi * 4 * sizeof(float) + 255) / 256 * 256;
 }
 
@@ -374,6 +375,7 @@ static int head_levels(const float* const* h_cls, const float* const* h_reg, flo
         lv->cls[l] = lv->reg[l] = nullptr;
         lv->gcls[l] = lv->greg[l] = nullptr;
         lv->hw[l] = 0;
+        lv->pos_chunks[l] = 1;
     }
     for (int l = 0; l < num_levels; ++l) {
         const int sh = 3 + l;
@@ -385,8 +387,9 @@ static int head_levels(const float* const* h_cls, const float* const* h_reg, flo
         lv->hw[l] = (int)hw;
         lv->anchor_off[l] = aoff;
         lv->chunk_off[l] = coff;
+        lv->pos_chunks[l] = (int)((hw + kHeadPos - 1) / kHeadPos);
         aoff += hw * kHeadTypes;
-        coff += (int)((hw + kHeadPos - 1) / kHeadPos);
+        coff += kHeadTypes * lv->pos_chunks[l];
     }
     for (int l = num_levels; l <= kHeadMaxLevels; ++l) {
         lv->anchor_off[l] = aoff;
@@ -407,7 +410,7 @@ static void head_args(LossArgs* a, const float* d_anchors, const float* d_annota
     a->partials = reinterpret_cast<float*>(reinterpret_cast<char*>(d_workspace) + workspace_header_bytes(N));
     a->rw_counters = reinterpret_cast<unsigned int*>(d_workspace) + 2 * (size_t)N;
     a->bpi = chunks_per_image;
-    a->anchors_per_block = kHeadPos * kHeadTypes;
+    a->anchors_per_block = kHeadPos;
     const uint64_t span = (uint64_t)kHeadTypes * C;              // dividends are channel indices < 9*C
     const uint64_t magic = (1ull << 32) / (uint64_t)C + 1;
     a->div_magic = (span * (magic * (uint64_t)C - (1ull << 32)) < (1ull << 32) && magic < (1ull << 32)) ? (uint32_t)magic : 0u;

@@ -9,21 +9,24 @@
 // lives at channel k*C + c, position y*W_l + x of its level's plane, and its gradient is written to the same place of a
 // gradient tensor of the same layout, which is exactly what the output convolution's backward wants.
 //
-// Work decomposition: a block owns kHeadPos consecutive positions of ONE level of ONE image with all 9*C channels, i.e.
-// 9*kHeadPos anchors.  For a fixed channel the positions are contiguous in memory, so the sweep is made of 256-byte rows read
-// with 128-bit loads (planes whose size is not a multiple of 4 floats -- the tiny top levels -- use 32-bit loads).  The
-// assignment words of the block's anchors sit in shared memory at [position][type]; a 64-bit mask per anchor type marks the
-// positions whose anchor is plain background, so the hot path (four background elements) costs one mask test per vector.
+// Work decomposition: a block owns kHeadPos consecutive positions of ONE anchor type k of ONE level of ONE image: C channel
+// rows (k*C .. k*C+C-1) of kHeadPos contiguous floats (2 KB) each.  Consecutive blocks walk the channel planes in address
+// order, so the blocks in flight touch ~100 MB of contiguous memory like the concatenated-layout kernel does (a first version
+// gave each block all 9*C channels of 64 positions: 720 rows 67 KB apart per block, twice as slow -- TLB reach).  One warp
+// sweeps one row at a time with 128-bit accesses, four in flight per lane (planes whose size is not a multiple of 4 floats --
+// the tiny top levels -- use 32-bit accesses).  The assignment words of the block's anchors sit in shared memory by position; a
+// bitmask marks the positions whose anchor is plain background, so the hot path (four background elements) costs one mask
+// test per vector.  The 9 type-blocks of a position range read the same key / word sectors; L2 serves the repeats.
 #pragma once
 #include "cldet_loss_kernels.cuh"
 
 namespace cldet {
 
 #ifndef CLDET_HEAD_POS
-#define CLDET_HEAD_POS 64
+#define CLDET_HEAD_POS 512
 #endif
-constexpr int kHeadPos = CLDET_HEAD_POS;  // positions per block (a multiple of 64)
-constexpr int kHeadMaskWords = kHeadPos / 64;
+constexpr int kHeadPos = CLDET_HEAD_POS;  // positions per block (a multiple of 128)
+constexpr int kHeadMaskWords = kHeadPos / 32;
 constexpr int kHeadMaxLevels = 8;
 constexpr int kHeadTypes = 9;           // anchors per position (3 ratios x 3 scales, retinanet/anchors.py:10-19)
 
@@ -36,6 +39,7 @@ struct HeadLevels {
     int hw[kHeadMaxLevels];                      // H_l * W_l
     int64_t anchor_off[kHeadMaxLevels + 1];      // level offsets inside the concatenated anchor index space
     int chunk_off[kHeadMaxLevels + 1];           // level offsets inside the per-image chunk index space
+    int pos_chunks[kHeadMaxLevels];              // ceil(hw / kHeadPos); a level has 9 * pos_chunks chunks, type-major
 };
 
 // One element with target 0 in the general (gamma != 2 or IL variants) configuration, or target 1: defer to cls_element.
@@ -59,146 +63,169 @@ __device__ __forceinline__ float head_element(float x, int c, uint32_t m, int64_
     return g;
 }
 
+// Four consecutive positions of one class row.
+template <bool GAMMA2, bool VARIANTS, bool GRAD, bool LOGITS>
+__device__ __forceinline__ float4 head_vec(const float4 x, int c, uint32_t plain4, const uint32_t* mp, int64_t anchor_abs,
+                                           const LossArgs& a, const ImageScales& sc, float as_bg, bool need_iou, Acc& acc) {
+    float4 g;
+    if (GAMMA2 && !VARIANTS && plain4 == 0xFu) {
+        // four plain background anchors (or an image without GT): the hot path
+        const float p0 = LOGITS ? sigmoid_exact(x.x) : x.x;
+        const float p1 = LOGITS ? sigmoid_exact(x.y) : x.y;
+        const float p2 = LOGITS ? sigmoid_exact(x.z) : x.z;
+        const float p3 = LOGITS ? sigmoid_exact(x.w) : x.w;
+        g.x = neg_element_raw<GRAD>(p0, as_bg, acc.raw[0]);
+        g.y = neg_element_raw<GRAD>(p1, as_bg, acc.raw[1]);
+        g.z = neg_element_raw<GRAD>(p2, as_bg, acc.raw[2]);
+        g.w = neg_element_raw<GRAD>(p3, as_bg, acc.raw[3]);
+        if (GRAD && LOGITS) {
+            g.x = sigmoid_bwd(g.x, p0);
+            g.y = sigmoid_bwd(g.y, p1);
+            g.z = sigmoid_bwd(g.z, p2);
+            g.w = sigmoid_bwd(g.w, p3);
+        }
+    } else {
+        g.x = head_element<GAMMA2, VARIANTS, GRAD, LOGITS>(x.x, c, mp[0], anchor_abs, a, sc, as_bg, need_iou, acc, 0);
+        g.y = head_element<GAMMA2, VARIANTS, GRAD, LOGITS>(x.y, c, mp[1], anchor_abs + kHeadTypes, a, sc, as_bg, need_iou, acc, 1);
+        g.z = head_element<GAMMA2, VARIANTS, GRAD, LOGITS>(x.z, c, mp[2], anchor_abs + 2 * kHeadTypes, a, sc, as_bg, need_iou, acc, 2);
+        g.w = head_element<GAMMA2, VARIANTS, GRAD, LOGITS>(x.w, c, mp[3], anchor_abs + 3 * kHeadTypes, a, sc, as_bg, need_iou, acc, 3);
+    }
+    return g;
+}
+
 template <bool GAMMA2, bool VARIANTS, bool GRAD, bool LOGITS>
 __device__ __forceinline__ void head_chunk(const LossArgs& a, const HeadLevels& lv, int j, int chunk, int mode,
-                                           const ImageScales& sc, Acc& acc, uint32_t* smeta, unsigned long long* plain) {
+                                           const ImageScales& sc, Acc& acc, uint32_t* smeta, uint32_t* plain) {
     const int tid = threadIdx.x;
+    const int lane = tid & 31, warp = tid >> 5;
+    constexpr int kWarps = kLossThreads / 32;
     int l = 0;
     while (l + 1 < lv.n && chunk >= lv.chunk_off[l + 1]) ++l;
     const int hw = lv.hw[l];
-    const int p0 = (chunk - lv.chunk_off[l]) * kHeadPos;
+    const int local = chunk - lv.chunk_off[l];
+    const int k = local / lv.pos_chunks[l];                                 // anchor type of this block
+    const int p0 = (local - k * lv.pos_chunks[l]) * kHeadPos;
     const int np = min(kHeadPos, hw - p0);
-    const int na = np * kHeadTypes;
-    const int64_t an0 = lv.anchor_off[l] + (int64_t)p0 * kHeadTypes;       // first anchor of the chunk, concatenated index
+    const int64_t an0 = lv.anchor_off[l] + (int64_t)p0 * kHeadTypes + k;    // anchor of position p0; stride kHeadTypes
     const int C = a.C;
     const bool need_iou = VARIANTS && a.p.incremental && a.p.decrease_positive_by_iou;
 
-    // ---- regression gradient rows: zero everywhere, positives overwrite their four entries after the barrier ----
-    float* greg_img = GRAD ? lv.greg[l] + (int64_t)j * (kHeadTypes * 4) * hw + p0 : nullptr;
+    // ---- regression gradient rows of this type (4 rows of np floats): zero, positives overwrite theirs after the barrier ----
+    float* greg_rows = GRAD ? lv.greg[l] + ((int64_t)j * (kHeadTypes * 4) + k * 4) * hw + p0 : nullptr;
     if (GRAD) {
-        for (int v = tid; v < kHeadTypes * 4 * np; v += kLossThreads) {
-            const int chr = v / np, pp = v - chr * np;
-            greg_img[(int64_t)chr * hw + pp] = 0.0f;
-        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+            for (int pp = tid; pp < np; pp += kLossThreads) greg_rows[(int64_t)i * hw + pp] = 0.0f;
     }
-    if (tid < kHeadTypes * kHeadMaskWords) plain[tid] = 0ull;
     __syncthreads();
 
     // ---- per-anchor prologue: assignment word, outputs keyed by anchor, smooth-L1 for the positives ----
     const int nvalid_j = (mode == 0 && a.best) ? a.nvalid[j] : 1;
-    const float* reg_img = lv.reg[l] + (int64_t)j * (kHeadTypes * 4) * hw + p0;
-    for (int i = tid; i < na; i += kLossThreads) {
-        const int64_t an = an0 + i;
-        const int64_t gi = (int64_t)j * a.A + an;
-        uint32_t m;
-        if (mode == 0 && a.best) {
-            const unsigned long long key = a.best[gi];
-            if (key) a.best[gi] = 0ull;                       // leave the scratch zeroed for the next call
-            m = word_from_best(a, j, key, nvalid_j);
-            a.meta_out[gi] = m;
-            if (a.iou_out) a.iou_out[gi] = __uint_as_float((uint32_t)(key >> 32));
-        } else {
-            m = a.meta[gi];
-        }
-        smeta[i] = m;
-        const uint32_t st = meta_state(m);
-        const int pp = i / kHeadTypes, k = i - pp * kHeadTypes;
-        if (st == CLDET_STATE_BG || st == CLDET_STATE_EMPTY) atomicOr(&plain[k * kHeadMaskWords + (pp >> 6)], 1ull << (pp & 63));
-        if (mode == 0 && a.bg_mask) a.bg_mask[gi] = (st != CLDET_STATE_POS) ? 1 : 0;
-        if (st == CLDET_STATE_POS) {
-            const float* rp = reg_img + (int64_t)(k * 4) * hw + pp;
-            const float4 r = make_float4(rp[0], rp[hw], rp[2 * (int64_t)hw], rp[3 * (int64_t)hw]);
-            float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
-            acc.reg += reg_anchor<GRAD>(a, j, an, m, r, sc.s_reg, g);
-            if (mode == 0 && a.status && meta_label(m) == CLDET_BAD_LABEL) *a.status = 1;
-            if (GRAD) {
-                float* gp = greg_img + (int64_t)(k * 4) * hw + pp;
-                gp[0] = g.x;
-                gp[hw] = g.y;
-                gp[2 * (int64_t)hw] = g.z;
-                gp[3 * (int64_t)hw] = g.w;
+    const float* reg_rows = lv.reg[l] + ((int64_t)j * (kHeadTypes * 4) + k * 4) * hw + p0;
+    for (int pp0 = 0; pp0 < kHeadPos; pp0 += kLossThreads) {                // uniform trip count: the ballot needs whole warps
+        const int pp = pp0 + tid;
+        bool is_plain = false;
+        if (pp < np) {
+            const int64_t an = an0 + (int64_t)pp * kHeadTypes;
+            const int64_t gi = (int64_t)j * a.A + an;
+            uint32_t m;
+            if (mode == 0 && a.best) {
+                const unsigned long long key = a.best[gi];
+                if (key) a.best[gi] = 0ull;                   // leave the scratch zeroed for the next call
+                m = word_from_best(a, j, key, nvalid_j);
+                a.meta_out[gi] = m;
+                if (a.iou_out) a.iou_out[gi] = __uint_as_float((uint32_t)(key >> 32));
+            } else {
+                m = a.meta[gi];
+            }
+            smeta[pp] = m;
+            const uint32_t st = meta_state(m);
+            is_plain = (st == CLDET_STATE_BG || st == CLDET_STATE_EMPTY);
+            if (mode == 0 && a.bg_mask) a.bg_mask[gi] = (st != CLDET_STATE_POS) ? 1 : 0;
+            if (st == CLDET_STATE_POS) {
+                const float* rp = reg_rows + pp;
+                const float4 r = make_float4(rp[0], rp[hw], rp[2 * (int64_t)hw], rp[3 * (int64_t)hw]);
+                float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+                acc.reg += reg_anchor<GRAD>(a, j, an, m, r, sc.s_reg, g);
+                if (mode == 0 && a.status && meta_label(m) == CLDET_BAD_LABEL) *a.status = 1;
+                if (GRAD) {
+                    float* gp = greg_rows + pp;
+                    gp[0] = g.x;
+                    gp[hw] = g.y;
+                    gp[2 * (int64_t)hw] = g.z;
+                    gp[3 * (int64_t)hw] = g.w;
+                }
             }
         }
+        const uint32_t bits = __ballot_sync(0xffffffffu, is_plain);
+        if (lane == 0) plain[pp >> 5] = bits;
     }
     __syncthreads();
 
-    // ---- classification planes: rows of `np` contiguous positions, one row per channel ----
+    // ---- classification rows: C rows of np contiguous positions, one warp per row ----
     const float alpha_img = (meta_state(smeta[0]) == CLDET_STATE_EMPTY) ? 1.0f - a.p.alpha : a.p.alpha;
     const float as_bg = alpha_img * sc.s_bg;
-    const float* src = lv.cls[l] + (int64_t)j * (kHeadTypes * C) * hw + p0;
-    float* dst = GRAD ? lv.gcls[l] + (int64_t)j * (kHeadTypes * C) * hw + p0 : nullptr;
-    const int nch = kHeadTypes * C;
-    const bool vec_ok = (np == kHeadPos) && ((hw & 3) == 0) &&
-                        ((((uintptr_t)lv.cls[l] | (uintptr_t)lv.gcls[l]) & 15) == 0);
+    const float* src = lv.cls[l] + ((int64_t)j * (kHeadTypes * C) + (int64_t)k * C) * hw + p0;
+    float* dst = GRAD ? lv.gcls[l] + ((int64_t)j * (kHeadTypes * C) + (int64_t)k * C) * hw + p0 : nullptr;
+    const int64_t abs0 = (int64_t)j * a.A + an0;
+    const bool vec_ok = ((np & 3) == 0) && ((hw & 3) == 0) && ((((uintptr_t)lv.cls[l] | (uintptr_t)lv.gcls[l]) & 15) == 0);
     if (vec_ok) {
-        constexpr int kVecPerRow = kHeadPos / 4;                         // 16
-        constexpr int kU = 4;                                            // vectors in flight per thread
-        const int nvec = nch * kVecPerRow;
-        const int q = tid & (kVecPerRow - 1);                            // this thread's vector inside a row: fixed
-        for (int v0 = tid; v0 < nvec; v0 += kLossThreads * kU) {
-            float4 x[kU];
-            int chv[kU];
+        constexpr int kU = 4;                                            // 4 x 32 lanes x 16 B = one 2 KB row per round
+        const int nv = np >> 2;
+        for (int c = warp; c < C; c += kWarps) {
+            const float* sp = src + (int64_t)c * hw;
+            float* dp = GRAD ? dst + (int64_t)c * hw : nullptr;
+            for (int q0 = lane; q0 < nv; q0 += 32 * kU) {
+                float4 x[kU];
 #pragma unroll
-            for (int u = 0; u < kU; ++u) {
-                const int v = v0 + u * kLossThreads;
-                chv[u] = v / kVecPerRow;
-                if (v < nvec) {
-                    const float* sp = src + (int64_t)chv[u] * hw + 4 * q;
-                    asm volatile(CLDET_LD_QUAL ".v4.f32 {%0,%1,%2,%3}, [%4];"
-                                 : "=f"(x[u].x), "=f"(x[u].y), "=f"(x[u].z), "=f"(x[u].w)
-                                 : "l"(sp));
-                }
-            }
-#pragma unroll
-            for (int u = 0; u < kU; ++u) {
-                if (v0 + u * kLossThreads >= nvec) break;
-                const int ch = chv[u];
-                const int k = (int)fast_div((uint32_t)ch, (uint32_t)C, a.div_magic);
-                const int c = ch - k * C;
-                const uint32_t plain4 = (uint32_t)(plain[k * kHeadMaskWords + ((4 * q) >> 6)] >> ((4 * q) & 63)) & 0xFu;
-                float4 g;
-                if (GAMMA2 && !VARIANTS && plain4 == 0xFu) {
-                    // four plain background anchors (or an image without GT): the hot path
-                    const float p0v = LOGITS ? sigmoid_exact(x[u].x) : x[u].x;
-                    const float p1v = LOGITS ? sigmoid_exact(x[u].y) : x[u].y;
-                    const float p2v = LOGITS ? sigmoid_exact(x[u].z) : x[u].z;
-                    const float p3v = LOGITS ? sigmoid_exact(x[u].w) : x[u].w;
-                    g.x = neg_element_raw<GRAD>(p0v, as_bg, acc.raw[0]);
-                    g.y = neg_element_raw<GRAD>(p1v, as_bg, acc.raw[1]);
-                    g.z = neg_element_raw<GRAD>(p2v, as_bg, acc.raw[2]);
-                    g.w = neg_element_raw<GRAD>(p3v, as_bg, acc.raw[3]);
-                    if (GRAD && LOGITS) {
-                        g.x = sigmoid_bwd(g.x, p0v);
-                        g.y = sigmoid_bwd(g.y, p1v);
-                        g.z = sigmoid_bwd(g.z, p2v);
-                        g.w = sigmoid_bwd(g.w, p3v);
+                for (int u = 0; u < kU; ++u) {
+                    const int q = q0 + 32 * u;
+                    if (q < nv) {
+                        asm volatile(CLDET_LD_QUAL ".v4.f32 {%0,%1,%2,%3}, [%4];"
+                                     : "=f"(x[u].x), "=f"(x[u].y), "=f"(x[u].z), "=f"(x[u].w)
+                                     : "l"(sp + 4 * q));
                     }
-                } else {
-                    const uint32_t* mp = smeta + (4 * q) * kHeadTypes + k;
-                    const int64_t ab = (int64_t)j * a.A + an0 + (4 * q) * kHeadTypes + k;
-                    g.x = head_element<GAMMA2, VARIANTS, GRAD, LOGITS>(x[u].x, c, mp[0], ab, a, sc, as_bg, need_iou, acc, 0);
-                    g.y = head_element<GAMMA2, VARIANTS, GRAD, LOGITS>(x[u].y, c, mp[kHeadTypes], ab + kHeadTypes, a, sc, as_bg, need_iou, acc, 1);
-                    g.z = head_element<GAMMA2, VARIANTS, GRAD, LOGITS>(x[u].z, c, mp[2 * kHeadTypes], ab + 2 * kHeadTypes, a, sc, as_bg, need_iou, acc, 2);
-                    g.w = head_element<GAMMA2, VARIANTS, GRAD, LOGITS>(x[u].w, c, mp[3 * kHeadTypes], ab + 3 * kHeadTypes, a, sc, as_bg, need_iou, acc, 3);
                 }
-                if (GRAD) {
-                    float* dp = dst + (int64_t)ch * hw + 4 * q;
-                    asm volatile(CLDET_ST_QUAL ".v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(dp), "f"(g.x), "f"(g.y), "f"(g.z), "f"(g.w)
-                                 : "memory");
+#pragma unroll
+                for (int u = 0; u < kU; ++u) {
+                    const int q = q0 + 32 * u;
+                    if (q < nv) {
+                        const uint32_t plain4 = (plain[q >> 3] >> ((q & 7) * 4)) & 0xFu;
+                        const float4 g = head_vec<GAMMA2, VARIANTS, GRAD, LOGITS>(x[u], c, plain4, smeta + 4 * q,
+                                                                                 abs0 + (int64_t)(4 * q) * kHeadTypes, a, sc, as_bg,
+                                                                                 need_iou, acc);
+                        if (GRAD) {
+                            asm volatile(CLDET_ST_QUAL ".v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(dp + 4 * q), "f"(g.x), "f"(g.y), "f"(g.z),
+                                         "f"(g.w)
+                                         : "memory");
+                        }
+                    }
                 }
             }
         }
     } else {
-        // ragged chunk or a plane that is not a multiple of four floats: 32-bit accesses, positions fastest
-        const int total = nch * np;
-        for (int e = tid; e < total; e += kLossThreads) {
-            const int ch = e / np, pp = e - ch * np;
-            const int k = ch / C, c = ch - k * C;
-            const float x = src[(int64_t)ch * hw + pp];
-            const float g = head_element<GAMMA2, VARIANTS, GRAD, LOGITS>(x, c, smeta[pp * kHeadTypes + k],
-                                                                         (int64_t)j * a.A + an0 + pp * kHeadTypes + k, a, sc, as_bg,
-                                                                         need_iou, acc, e & 3);
-            if (GRAD) dst[(int64_t)ch * hw + pp] = g;
+        // a plane that is not a multiple of four floats, or a ragged end: 32-bit accesses, lanes along the positions
+        constexpr int kU = 4;
+        for (int c = warp; c < C; c += kWarps) {
+            const float* sp = src + (int64_t)c * hw;
+            float* dp = GRAD ? dst + (int64_t)c * hw : nullptr;
+            for (int pp0 = lane; pp0 < np; pp0 += 32 * kU) {
+                float x[kU];
+#pragma unroll
+                for (int u = 0; u < kU; ++u) {
+                    const int pp = pp0 + 32 * u;
+                    if (pp < np) x[u] = sp[pp];
+                }
+#pragma unroll
+                for (int u = 0; u < kU; ++u) {
+                    const int pp = pp0 + 32 * u;
+                    if (pp < np) {
+                        const float g = head_element<GAMMA2, VARIANTS, GRAD, LOGITS>(x[u], c, smeta[pp], abs0 + (int64_t)pp * kHeadTypes,
+                                                                                     a, sc, as_bg, need_iou, acc, 0);
+                        if (GRAD) dp[pp] = g;
+                    }
+                }
+            }
         }
     }
 }
@@ -208,8 +235,8 @@ __global__ void __launch_bounds__(kLossThreads, 4) focal_loss_head_kernel(const 
     __shared__ float red[4][kLossThreads / 32];
     __shared__ double fin[4][kLossThreads / 32];
     __shared__ bool is_last;
-    __shared__ uint32_t smeta[kHeadPos * kHeadTypes];
-    __shared__ unsigned long long plain[kHeadTypes * kHeadMaskWords];
+    __shared__ uint32_t smeta[kHeadPos];
+    __shared__ uint32_t plain[kHeadMaskWords];
 
     const int j = blockIdx.y;
     const int npos = a.npos[j];
@@ -223,8 +250,8 @@ __global__ void __launch_bounds__(kLossThreads, 4) focal_loss_head_kernel(const 
 // positives-only patch of the concatenated layout is not worth a second code path here).
 template <bool GAMMA2, bool VARIANTS, bool LOGITS>
 __global__ void __launch_bounds__(kLossThreads, 4) focal_head_reweight_kernel(const LossArgs a, const HeadLevels lv) {
-    __shared__ uint32_t smeta[kHeadPos * kHeadTypes];
-    __shared__ unsigned long long plain[kHeadTypes * kHeadMaskWords];
+    __shared__ uint32_t smeta[kHeadPos];
+    __shared__ uint32_t plain[kHeadMaskWords];
     const int j = blockIdx.y;
     const float* wo = a.baked_weights + j;
     const int N = a.N;

@@ -79,15 +79,40 @@ def main():
         torch.cuda.synchronize()
         return t0.elapsed_time(t1) / args.steps
 
+    # the C ABI alone (scatter + fused kernel, preallocated outputs): the device time without autograd / allocator work
+    from cl_object_detection_b200 import _lib
+    from cl_object_detection_b200.params import to_loss_params
+    lib = _lib.load()
+    a = anchors.shape[1]
+    lp = to_loss_params(params, 0, c)
+    lp.cls_is_logits = int(args.logits)
+    lp.image_height, lp.image_width = h, w
+    weights = torch.full((4, n), 1.0 / n, device=dev)
+    baked = torch.empty_like(weights)
+    gcls = [torch.empty_like(t) for t in cls_lv]
+    greg = [torch.empty_like(t) for t in reg_lv]
+    losses = torch.empty((4, n), device=dev)
+    meta = torch.empty((n, a), dtype=torch.int32, device=dev)
+    npos = torch.zeros(n, dtype=torch.int32, device=dev)
+    nvalid = torch.zeros(n, dtype=torch.int32, device=dev)
+    ws = torch.zeros(lib.cldet_focal_loss_workspace_bytes(n, a), dtype=torch.uint8, device=dev)
+    pc, pr, pgc, pgr = (_lib.ptr_array(x) for x in (cls_lv, reg_lv, gcls, greg))
+    st = torch.cuda.current_stream().cuda_stream
+
+    def raw_step():
+        _lib.check(lib.cldet_focal_loss_head(pc, pr, 5, h, w, anchors.data_ptr(), ann.data_ptr(), n, c, ann.shape[1], lp,
+                                             weights.data_ptr(), baked.data_ptr(), pgc, pgr, losses.data_ptr(), meta.data_ptr(),
+                                             None, npos.data_ptr(), nvalid.data_ptr(), None, None, ws.data_ptr(), ws.numel(), st))
+
     g_ref, g_head = ref_step(), head_step()
     diff = ((g_ref - g_head).abs() / (g_ref.abs() + 1e-30)).max().item()
-    ms_ref, ms_head = timeit(ref_step), timeit(head_step)
+    ms_ref, ms_head, ms_raw = timeit(ref_step), timeit(head_step), timeit(raw_step)
     elems = sum(t.numel() for t in cls_lv)
     print(json.dumps({'workload': '%d x %dx%d, C=%d, %s in: head outputs -> losses -> gradients of the head outputs'
                                   % (n, h, w, c, 'logits' if args.logits else 'probabilities'),
                       'ref_layout_ms': ms_ref, 'head_layout_ms': ms_head, 'speedup': ms_ref / ms_head,
                       'images_per_s_head_layout': n / (ms_head * 1e-3),
-                      'head_layout_GBps_algorithmic': 8.0 * elems / (ms_head * 1e-3) / 1e9,
+                      'head_layout_c_abi_ms': ms_raw, 'head_layout_c_abi_GBps_algorithmic': 8.0 * elems / (ms_raw * 1e-3) / 1e9,
                       'max_rel_grad_diff_level3': diff}))
 
 
