@@ -26,7 +26,11 @@ namespace cldet {
 #define CLDET_HEAD_POS 512
 #endif
 constexpr int kHeadPos = CLDET_HEAD_POS;  // positions per block (a multiple of 128)
+static_assert(kHeadPos % 128 == 0 && kHeadPos <= 1024, "kHeadPos: whole 128-position groups, at most 8 vectors per lane");
 constexpr int kHeadMaskWords = kHeadPos / 32;
+#ifndef CLDET_HEAD_MINBLOCKS
+#define CLDET_HEAD_MINBLOCKS 5
+#endif
 constexpr int kHeadMaxLevels = 8;
 constexpr int kHeadTypes = 9;           // anchors per position (3 ratios x 3 scales, retinanet/anchors.py:10-19)
 
@@ -63,21 +67,82 @@ __device__ __forceinline__ float head_element(float x, int c, uint32_t m, int64_
     return g;
 }
 
-// Four consecutive positions of one class row.
+// Target-0 element with a 0/1 weight (0: the element is ignored or is a positive anchor's own class, handled separately):
+// neg_element_raw with the weight folded into the loss term and the gradient scale -- no branch.
+template <bool GRAD>
+__device__ __forceinline__ float neg_element_raw_w(float p_raw, float as, float w, float& raw) {
+    const float p = fminf(fmaxf(p_raw, 1e-4f), 0.9999f);
+    const float q = 1.0f - p;
+    const float L = log_fast(q);
+    raw = fmaf(-(p * p) * w, L, raw);
+    if (!GRAD) return 0.0f;
+    const float t = fmaf(L, -2.0f, p * __frcp_rn_fast(q));
+    const float g = ((as * w) * p) * t;
+    return (p == p_raw) ? g : 0.0f;
+}
+
+// A positive anchor's own class (target 1) when no IL variant is active: f = 1 - p in all three reference branches
+// (losses.py:352-366 with decrease_positive == 1).  Rare (one element per positive anchor) and fat (logf): kept out of line,
+// arguments by value, so the hot loop's instruction footprint stays small.
+static __device__ __noinline__ float2 own_class_element(float p_raw, float alpha, float scale) {
+    const float p = fminf(fmaxf(p_raw, 1e-4f), 0.9999f);
+    const float f = 1.0f - p;
+    const float nl = -logf(p);
+    const float pw = f * f;                                   // ATen evaluates pow(x, 2.0) as x*x
+    const float loss = (alpha * pw) * nl;
+    const float g = alpha * ((2.0f * f) * -1.0f * nl - pw / p) * scale;
+    return make_float2(loss, (p == p_raw) ? g : 0.0f);
+}
+
+// Four consecutive positions of one class row.  gamma == 2 without IL variants: every element runs the weighted target-0
+// form (weight 0 for ignored anchors and for a positive anchor's own class, looked up only for non-plain positions), then the
+// rare own-class elements are recomputed out of line.  One code path for all lanes: non-background anchors cluster around
+// the GT boxes, so a per-vector branch between a bare and a general path would make most warps execute both, and two inlined
+// copies of the math per unrolled vector overflow the instruction cache (measured: 2.4 warps per issue stalled on fetch).
 template <bool GAMMA2, bool VARIANTS, bool GRAD, bool LOGITS>
 __device__ __forceinline__ float4 head_vec(const float4 x, int c, uint32_t plain4, const uint32_t* mp, int64_t anchor_abs,
                                            const LossArgs& a, const ImageScales& sc, float as_bg, bool need_iou, Acc& acc) {
     float4 g;
-    if (GAMMA2 && !VARIANTS && plain4 == 0xFu) {
-        // four plain background anchors (or an image without GT): the hot path
+    if (GAMMA2 && !VARIANTS) {
         const float p0 = LOGITS ? sigmoid_exact(x.x) : x.x;
         const float p1 = LOGITS ? sigmoid_exact(x.y) : x.y;
         const float p2 = LOGITS ? sigmoid_exact(x.z) : x.z;
         const float p3 = LOGITS ? sigmoid_exact(x.w) : x.w;
-        g.x = neg_element_raw<GRAD>(p0, as_bg, acc.raw[0]);
-        g.y = neg_element_raw<GRAD>(p1, as_bg, acc.raw[1]);
-        g.z = neg_element_raw<GRAD>(p2, as_bg, acc.raw[2]);
-        g.w = neg_element_raw<GRAD>(p3, as_bg, acc.raw[3]);
+        float w0 = 1.0f, w1 = 1.0f, w2 = 1.0f, w3 = 1.0f;
+        uint32_t own = 0;                                               // elements that are a positive anchor's own class
+        if (plain4 != 0xFu) {
+            float wgt[4] = {1.0f, 1.0f, 1.0f, 1.0f};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                if (!((plain4 >> e) & 1u)) {
+                    const uint32_t m = mp[e];                           // not plain background: ignored or positive
+                    if (meta_state(m) == CLDET_STATE_IGNORE) {
+                        wgt[e] = 0.0f;
+                    } else if (meta_state(m) == CLDET_STATE_POS && (uint32_t)c == meta_label(m)) {
+                        wgt[e] = 0.0f;
+                        own |= 1u << e;
+                    }
+                }
+            }
+            w0 = wgt[0]; w1 = wgt[1]; w2 = wgt[2]; w3 = wgt[3];
+        }
+        g.x = neg_element_raw_w<GRAD>(p0, as_bg, w0, acc.raw[0]);
+        g.y = neg_element_raw_w<GRAD>(p1, as_bg, w1, acc.raw[1]);
+        g.z = neg_element_raw_w<GRAD>(p2, as_bg, w2, acc.raw[2]);
+        g.w = neg_element_raw_w<GRAD>(p3, as_bg, w3, acc.raw[3]);
+        if (own) {
+            const float pv[4] = {p0, p1, p2, p3};
+            float gv[4] = {g.x, g.y, g.z, g.w};
+#pragma unroll 1
+            for (int e = 0; e < 4; ++e) {
+                if ((own >> e) & 1u) {
+                    const float2 lg = own_class_element(pv[e], a.p.alpha, sc.s_fg);
+                    acc.fg += lg.x;
+                    gv[e] = GRAD ? lg.y : 0.0f;
+                }
+            }
+            g = make_float4(gv[0], gv[1], gv[2], gv[3]);
+        }
         if (GRAD && LOGITS) {
             g.x = sigmoid_bwd(g.x, p0);
             g.y = sigmoid_bwd(g.y, p1);
@@ -160,6 +225,7 @@ __device__ __forceinline__ void head_chunk(const LossArgs& a, const HeadLevels& 
         const uint32_t bits = __ballot_sync(0xffffffffu, is_plain);
         if (lane == 0) plain[pp >> 5] = bits;
     }
+    if (tid == 0) plain[kHeadMaskWords] = 0u;
     __syncthreads();
 
     // ---- classification rows: C rows of np contiguous positions, one warp per row ----
@@ -168,61 +234,85 @@ __device__ __forceinline__ void head_chunk(const LossArgs& a, const HeadLevels& 
     const float* src = lv.cls[l] + ((int64_t)j * (kHeadTypes * C) + (int64_t)k * C) * hw + p0;
     float* dst = GRAD ? lv.gcls[l] + ((int64_t)j * (kHeadTypes * C) + (int64_t)k * C) * hw + p0 : nullptr;
     const int64_t abs0 = (int64_t)j * a.A + an0;
-    const bool vec_ok = ((np & 3) == 0) && ((hw & 3) == 0) && ((((uintptr_t)lv.cls[l] | (uintptr_t)lv.gcls[l]) & 15) == 0);
-    if (vec_ok) {
-        constexpr int kU = 4;                                            // 4 x 32 lanes x 16 B = one 2 KB row per round
-        const int nv = np >> 2;
+    // 128-bit accesses need 16-byte aligned addresses; a row starts at float offset row_off = (channel * hw + p0) from the
+    // (16-byte aligned) tensor base, so up to 3 leading and 3 trailing positions of a row are handled with 32-bit accesses.
+    const bool base_ok = (((uintptr_t)lv.cls[l] | (uintptr_t)lv.gcls[l]) & 15) == 0;
+    constexpr int kU = kHeadPos / 128;                                   // kU x 32 lanes x 16 B = one full row per round
+    if (base_ok && (hw & 3) == 0 && np == kHeadPos) {
+        // Full rows of an aligned plane (94 % of a COCO-shaped batch): no bounds checks, and the plain-background bits of this
+        // lane's kU vectors do not depend on the class row, so they are looked up once per chunk.
+        uint32_t pm = 0;
+#pragma unroll
+        for (int u = 0; u < kU; ++u) {
+            const int q = lane + 32 * u;
+            pm |= ((plain[q >> 3] >> ((q & 7) * 4)) & 0xFu) << (4 * u);
+        }
+        const uint32_t* mp = smeta + 4 * lane;
+        const int64_t ab = abs0 + (int64_t)(4 * lane) * kHeadTypes;
         for (int c = warp; c < C; c += kWarps) {
-            const float* sp = src + (int64_t)c * hw;
-            float* dp = GRAD ? dst + (int64_t)c * hw : nullptr;
-            for (int q0 = lane; q0 < nv; q0 += 32 * kU) {
-                float4 x[kU];
+            const float* sp = src + (int64_t)c * hw + 4 * lane;
+            float* dp = GRAD ? dst + (int64_t)c * hw + 4 * lane : nullptr;
+            float4 x[kU];
 #pragma unroll
-                for (int u = 0; u < kU; ++u) {
-                    const int q = q0 + 32 * u;
-                    if (q < nv) {
-                        asm volatile(CLDET_LD_QUAL ".v4.f32 {%0,%1,%2,%3}, [%4];"
-                                     : "=f"(x[u].x), "=f"(x[u].y), "=f"(x[u].z), "=f"(x[u].w)
-                                     : "l"(sp + 4 * q));
-                    }
-                }
+            for (int u = 0; u < kU; ++u) {
+                asm volatile(CLDET_LD_QUAL ".v4.f32 {%0,%1,%2,%3}, [%4];"
+                             : "=f"(x[u].x), "=f"(x[u].y), "=f"(x[u].z), "=f"(x[u].w)
+                             : "l"(sp + 128 * u));
+            }
 #pragma unroll
-                for (int u = 0; u < kU; ++u) {
-                    const int q = q0 + 32 * u;
-                    if (q < nv) {
-                        const uint32_t plain4 = (plain[q >> 3] >> ((q & 7) * 4)) & 0xFu;
-                        const float4 g = head_vec<GAMMA2, VARIANTS, GRAD, LOGITS>(x[u], c, plain4, smeta + 4 * q,
-                                                                                 abs0 + (int64_t)(4 * q) * kHeadTypes, a, sc, as_bg,
-                                                                                 need_iou, acc);
-                        if (GRAD) {
-                            asm volatile(CLDET_ST_QUAL ".v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(dp + 4 * q), "f"(g.x), "f"(g.y), "f"(g.z),
-                                         "f"(g.w)
-                                         : "memory");
-                        }
-                    }
+            for (int u = 0; u < kU; ++u) {
+                const float4 g = head_vec<GAMMA2, VARIANTS, GRAD, LOGITS>(x[u], c, (pm >> (4 * u)) & 0xFu, mp + 128 * u,
+                                                                         ab + (int64_t)(128 * u) * kHeadTypes, a, sc, as_bg, need_iou, acc);
+                if (GRAD) {
+                    asm volatile(CLDET_ST_QUAL ".v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(dp + 128 * u), "f"(g.x), "f"(g.y), "f"(g.z), "f"(g.w)
+                                 : "memory");
                 }
             }
         }
-    } else {
-        // a plane that is not a multiple of four floats, or a ragged end: 32-bit accesses, lanes along the positions
-        constexpr int kU = 4;
-        for (int c = warp; c < C; c += kWarps) {
-            const float* sp = src + (int64_t)c * hw;
-            float* dp = GRAD ? dst + (int64_t)c * hw : nullptr;
-            for (int pp0 = lane; pp0 < np; pp0 += 32 * kU) {
-                float x[kU];
+        return;
+    }
+    // Ragged ends and planes that are not a multiple of four floats (the small top levels, ~6 % of a COCO-shaped batch):
+    // compact code, two vectors in flight.
+    constexpr int kUg = 2;
+#pragma unroll 1
+    for (int c = warp; c < C; c += kWarps) {
+        const int64_t row_off = ((int64_t)j * (kHeadTypes * C) + (int64_t)k * C + c) * hw + p0;
+        const float* sp = src + (int64_t)c * hw;
+        float* dp = GRAD ? dst + (int64_t)c * hw : nullptr;
+        const int peel = base_ok ? min(np, (int)((4 - (row_off & 3)) & 3)) : np;
+        const int nv = (np - peel) >> 2;
+        const int tail0 = peel + 4 * nv;
+        // leading / trailing scalars (at most 3 + 3 when the base is aligned)
+#pragma unroll 1
+        for (int pp = lane; pp < peel + (np - tail0); pp += 32) {
+            const int pos = pp < peel ? pp : tail0 + (pp - peel);
+            const float g = head_element<GAMMA2, VARIANTS, GRAD, LOGITS>(sp[pos], c, smeta[pos], abs0 + (int64_t)pos * kHeadTypes, a, sc,
+                                                                         as_bg, need_iou, acc, 0);
+            if (GRAD) dp[pos] = g;
+        }
+#pragma unroll 1
+        for (int q0 = lane; q0 < nv; q0 += 32 * kUg) {
+            float4 x[kUg];
 #pragma unroll
-                for (int u = 0; u < kU; ++u) {
-                    const int pp = pp0 + 32 * u;
-                    if (pp < np) x[u] = sp[pp];
+            for (int u = 0; u < kUg; ++u) {
+                const int q = q0 + 32 * u;
+                if (q < nv) {
+                    asm volatile(CLDET_LD_QUAL ".v4.f32 {%0,%1,%2,%3}, [%4];"
+                                 : "=f"(x[u].x), "=f"(x[u].y), "=f"(x[u].z), "=f"(x[u].w)
+                                 : "l"(sp + peel + 4 * q));
                 }
+            }
 #pragma unroll
-                for (int u = 0; u < kU; ++u) {
-                    const int pp = pp0 + 32 * u;
-                    if (pp < np) {
-                        const float g = head_element<GAMMA2, VARIANTS, GRAD, LOGITS>(x[u], c, smeta[pp], abs0 + (int64_t)pp * kHeadTypes,
-                                                                                     a, sc, as_bg, need_iou, acc, 0);
-                        if (GRAD) dp[pp] = g;
+            for (int u = 0; u < kUg; ++u) {
+                const int q = q0 + 32 * u;
+                if (q < nv) {
+                    const int pos = peel + 4 * q;                        // first of the vector's four positions
+                    const uint32_t plain4 = __funnelshift_r(plain[pos >> 5], plain[(pos >> 5) + 1], pos & 31) & 0xFu;
+                    const float4 g = head_vec<GAMMA2, VARIANTS, GRAD, LOGITS>(x[u], c, plain4, smeta + pos,
+                                                                             abs0 + (int64_t)pos * kHeadTypes, a, sc, as_bg, need_iou, acc);
+                    if (GRAD) {
+                        asm volatile(CLDET_ST_QUAL ".v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(dp + pos), "f"(g.x), "f"(g.y), "f"(g.z), "f"(g.w)
+                                     : "memory");
                     }
                 }
             }
@@ -231,12 +321,12 @@ __device__ __forceinline__ void head_chunk(const LossArgs& a, const HeadLevels& 
 }
 
 template <bool GAMMA2, bool VARIANTS, bool GRAD, bool LOGITS>
-__global__ void __launch_bounds__(kLossThreads, 4) focal_loss_head_kernel(const LossArgs a, const HeadLevels lv) {
+__global__ void __launch_bounds__(kLossThreads, CLDET_HEAD_MINBLOCKS) focal_loss_head_kernel(const LossArgs a, const HeadLevels lv) {
     __shared__ float red[4][kLossThreads / 32];
     __shared__ double fin[4][kLossThreads / 32];
     __shared__ bool is_last;
     __shared__ uint32_t smeta[kHeadPos];
-    __shared__ uint32_t plain[kHeadMaskWords];
+    __shared__ uint32_t plain[kHeadMaskWords + 1];      // + 1: the funnel shift reads one word past the last
 
     const int j = blockIdx.y;
     const int npos = a.npos[j];
@@ -251,7 +341,7 @@ __global__ void __launch_bounds__(kLossThreads, 4) focal_loss_head_kernel(const 
 template <bool GAMMA2, bool VARIANTS, bool LOGITS>
 __global__ void __launch_bounds__(kLossThreads, 4) focal_head_reweight_kernel(const LossArgs a, const HeadLevels lv) {
     __shared__ uint32_t smeta[kHeadPos];
-    __shared__ uint32_t plain[kHeadMaskWords];
+    __shared__ uint32_t plain[kHeadMaskWords + 1];      // + 1: the funnel shift reads one word past the last
     const int j = blockIdx.y;
     const float* wo = a.baked_weights + j;
     const int N = a.N;
