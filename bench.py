@@ -252,7 +252,7 @@ def run_reference(args):
     # keep the whole run to a few minutes: probe a quarter-size step, then pick the anchor fraction of the per-step sample
     _, probe_step, f0 = time_cpu_reference(1, 0, images_per_step, threads, 0.25)
     full_step = probe_step / f0
-    budget = 150.0
+    budget = float(os.environ.get('CLDET_BENCH_BUDGET_S', '150'))      # seconds of CPU work for the whole run (tests shrink it)
     frac = max(0.02, min(1.0, budget / (full_step * (args.steps + args.warmup))))
     val, per_step, f = time_cpu_reference(args.steps, args.warmup, images_per_step, threads, frac)
     sample = ('%d images x %.0f%% of the anchors per step (800x1333, C=80, A=200700 full), numpy port of FocalLoss fwd+bwd, '
@@ -266,7 +266,7 @@ def run_reference(args):
                              'host_cores': cores},
             'e2e': {'value': val, 'unit': 'images/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
             'gpu_launches': 0}
-    print(json.dumps(line))
+    emit(line)
     return 0
 
 
@@ -505,7 +505,7 @@ def run_ours(args):
             del probs, reg, gcls, greg, d_probs, d_reg, h_probs, h_reg
             torch.cuda.empty_cache()
             line['decode'] = decode_section(dev, with_eager=not args.no_cpu_baseline)
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         if peer is not None:
             dist.barrier()
@@ -514,7 +514,30 @@ def run_ours(args):
     return 0
 
 
+_JSON_FD = None
+
+
+def _claim_stdout():
+    """stdout must carry exactly ONE JSON line, but libraries under us print there too (NCCL's version banner, warnings):
+    point fd 1 at stderr for the whole run and keep the real stdout for emit()."""
+    global _JSON_FD
+    if _JSON_FD is None:
+        sys.stdout.flush()
+        _JSON_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line):
+    data = (json.dumps(line) + '\n').encode()
+    if _JSON_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, data)
+
+
 def main():
+    _claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
     ap.add_argument('--steps', type=int, default=100)
