@@ -80,6 +80,65 @@ def test_loss_path_writes_stay_in_bounds(h, w, C, N, G):
                                 iou.data_ptr(), npos.data_ptr(), nvalid.data_ptr(), None, None, ws.data_ptr(), ws_bytes, st) == 1
 
 
+@pytest.mark.parametrize('h,w,C,N,G', [(200, 264, 80, 3, 9), (136, 200, 20, 2, 5), (96, 104, 7, 2, 3), (33, 70, 4, 2, 6), (1, 1, 3, 2, 2)])
+def test_head_layout_writes_stay_in_bounds(h, w, C, N, G):
+    """cldet_focal_loss_head / _reweight: ten per-level gradient tensors + the anchor-keyed outputs, all guard-banded; level
+    planes here are ragged (not multiples of 4 floats, shorter than a block's 512 positions, down to 1 x 1)."""
+    lib = _lib.load()
+    rng = np.random.default_rng(C + h)
+    anchors = cld.generate_anchors(h, w, DEV)
+    A = anchors.shape[1]
+    shapes = [((h + 2 ** l - 1) // 2 ** l, (w + 2 ** l - 1) // 2 ** l) for l in range(3, 8)]
+    cls_lv = [torch.rand(N, 9 * C, hl, wl, device=DEV) * 0.2 for hl, wl in shapes]
+    reg_lv = [torch.randn(N, 36, hl, wl, device=DEV) for hl, wl in shapes]
+    ann = torch.from_numpy(synth_gt(rng, N, G, max(h, 32), max(w, 32), C, empty=(1,))).to(DEV)
+    g = Guarded()
+    gcls = [g.alloc(tuple(t.shape), torch.float32) for t in cls_lv]
+    greg = [g.alloc(tuple(t.shape), torch.float32) for t in reg_lv]
+    losses, baked = g.alloc((4, N), torch.float32), g.alloc((4, N), torch.float32)
+    meta, iou = g.alloc((N, A), torch.int32), g.alloc((N, A), torch.float32)
+    npos, nvalid = g.alloc((N,), torch.int32), g.alloc((N,), torch.int32)
+    mask, status = g.alloc((N, A), torch.uint8), g.alloc((1,), torch.int32)
+    ws_bytes = lib.cldet_focal_loss_workspace_bytes(N, A)
+    ws = g.alloc((ws_bytes,), torch.uint8)
+    ws.zero_()
+    weights = torch.full((4, N), 0.5, device=DEV)
+    st = torch.cuda.current_stream().cuda_stream
+    pc, pr, pgc, pgr = (_lib.ptr_array(x) for x in (cls_lv, reg_lv, gcls, greg))
+    for variant in range(2):
+        params = cld.HeadParams([0, max(1, C // 2)], ignore_past_class=True, new_ignore_past_class=True, enhance_on_new=True,
+                                decrease_positive_by_IOU=True, distill=True) if variant else cld.HeadParams()
+        lp = to_loss_params(params, variant, C)
+        _lib.check(lib.cldet_focal_loss_head(pc, pr, 5, h, w, anchors.data_ptr(), ann.data_ptr(), N, C, G, lp, weights.data_ptr(),
+                                             baked.data_ptr(), pgc, pgr, losses.data_ptr(), meta.data_ptr(), iou.data_ptr(),
+                                             npos.data_ptr(), nvalid.data_ptr(), mask.data_ptr(), status.data_ptr(), ws.data_ptr(),
+                                             ws_bytes, st))
+        w2 = weights * 2
+        _lib.check(lib.cldet_focal_loss_head_reweight(pc, pr, 5, h, w, anchors.data_ptr(), ann.data_ptr(), N, C, G, lp,
+                                                      w2[0].data_ptr(), 1, w2[1].data_ptr(), 1, w2[2].data_ptr(), 1, w2[3].data_ptr(), 1,
+                                                      baked.data_ptr(), pgc, pgr, meta.data_ptr(), iou.data_ptr(), npos.data_ptr(),
+                                                      ws.data_ptr(), ws_bytes, st))
+        torch.cuda.synchronize()
+        g.check()
+        assert torch.isfinite(losses).all() and all(torch.isfinite(t).all() for t in gcls + greg)
+        assert torch.equal(baked, w2)
+    # the scratch (keys, counters) is left zeroed: a second pair of calls gives the same losses
+    first = losses.clone()
+    _lib.check(lib.cldet_focal_loss_head(pc, pr, 5, h, w, anchors.data_ptr(), ann.data_ptr(), N, C, G, lp, weights.data_ptr(),
+                                         baked.data_ptr(), pgc, pgr, losses.data_ptr(), meta.data_ptr(), iou.data_ptr(),
+                                         npos.data_ptr(), nvalid.data_ptr(), mask.data_ptr(), status.data_ptr(), ws.data_ptr(),
+                                         ws_bytes, st))
+    torch.cuda.synchronize()
+    assert torch.equal(first, losses)
+    # status codes instead of faults for bad arguments
+    assert lib.cldet_focal_loss_head(pc, pr, 4, h, w, anchors.data_ptr(), ann.data_ptr(), N, C, G, lp, weights.data_ptr(),
+                                     baked.data_ptr(), pgc, pgr, losses.data_ptr(), meta.data_ptr(), iou.data_ptr(), npos.data_ptr(),
+                                     nvalid.data_ptr(), None, None, ws.data_ptr(), ws_bytes, st) == 1
+    assert lib.cldet_focal_loss_head(pc, pr, 5, h, w, anchors.data_ptr(), ann.data_ptr(), N, C, G, lp, weights.data_ptr(),
+                                     baked.data_ptr(), pgc, pgr, losses.data_ptr(), meta.data_ptr(), iou.data_ptr(), npos.data_ptr(),
+                                     nvalid.data_ptr(), None, None, ws.data_ptr(), 16, st) == 2
+
+
 @pytest.mark.parametrize('C,topk', [(80, 100), (20, 0), (7, 33)])
 def test_detection_pipeline_writes_stay_in_bounds(C, topk):
     lib = _lib.load()
