@@ -77,6 +77,7 @@ SIGNATURES = {
     'cldet_decode_boxes': (_I, [_P, _P, _I, _L, _I, _I, _I, _P, _P]),
     'cldet_clip_boxes': (_I, [_P, _L, _I, _I, _P]),
     'cldet_decode_filter': (_I, [_P, _I, _P, _P, _I, _L, _I, _I, _I, _F, _P, _P, _L, _P, _P]),
+    'cldet_decode_filter_head': (_I, [_P, _P, _I, _I, _I, _I, _P, _I, _I, _F, _P, _P, _L, _P, _P]),
     'cldet_sort_workspace_bytes': (_Z, [_I, _L, _I]),
     'cldet_sort_candidates': (_I, [_P, _P, _P, _I, _L, _L, _I, _P, _L, _P, _P, _Z, _P]),
     'cldet_nms_workspace_bytes': (_Z, [_I, _L]),

@@ -230,6 +230,130 @@ decode_filter_kernel(const float* __restrict__ cls, int is_logits, const float4*
 }
 
 // ------------------------------------------------------------------------------------------------
+// K4h: the same filter on the head's RAW conv outputs (eval side): per pyramid level, classification
+// [N, 9*C, H_l, W_l] and regression [N, 36, H_l, W_l] as the output convolutions produce them, i.e. before
+// ClassificationModel / RegressionModel's permute + contiguous + view (retinanet/model.py:125-130, 170-184) and
+// ResNet.forward's torch.cat (model.py:472-474) -- 16 B/element of layout copies in front of a 4 B/element read.
+// Block = one level, one anchor type k, kHeadFilterPos consecutive positions; thread = one position.  The C class rows of
+// type k are C contiguous runs of positions, so a warp reads 128 contiguous bytes per class and every thread keeps its own
+// running (max, first argmax, second max) -- no shared-memory staging.  Rows whose runner-up is within reach of the maximum
+// (see decode_filter_kernel) walk their classes once more to apply torch.max's first-index rule on the exact probabilities.
+// Candidates carry the anchor index of the reference's concatenated order, so K5/K6 are unchanged.
+// ------------------------------------------------------------------------------------------------
+constexpr int kHeadFilterPos = 256;
+constexpr int kHeadFilterMaxLevels = 8;
+
+struct HeadFilterLevels {
+    int n;
+    const float* cls[kHeadFilterMaxLevels];
+    const float* reg[kHeadFilterMaxLevels];
+    int hw[kHeadFilterMaxLevels];
+    int64_t anchor_off[kHeadFilterMaxLevels + 1];
+    int chunk_off[kHeadFilterMaxLevels + 1];
+    int pos_chunks[kHeadFilterMaxLevels];
+};
+
+__global__ void __launch_bounds__(kHeadFilterPos)
+decode_filter_head_kernel(const HeadFilterLevels lv, int is_logits, const float4* __restrict__ anchors, int64_t A, int C,
+                          float img_w, float img_h, float score_thresh, float prefilter, cldet_candidate* __restrict__ cand,
+                          uint64_t* __restrict__ keys, int64_t capacity, int32_t* __restrict__ counts) {
+    __shared__ int warp_tot[kHeadFilterPos / 32];
+    __shared__ int block_base;
+    const int j = blockIdx.y;
+    int l = 0;
+    while (l + 1 < lv.n && (int)blockIdx.x >= lv.chunk_off[l + 1]) ++l;
+    const int hw = lv.hw[l];
+    const int local = (int)blockIdx.x - lv.chunk_off[l];
+    const int k = local / lv.pos_chunks[l];
+    const int pp = (local - k * lv.pos_chunks[l]) * kHeadFilterPos + (int)threadIdx.x;     // position inside the level's plane
+    const bool live = pp < hw;
+
+    bool is_cand = false;
+    float best = 0.0f;
+    int best_c = 0;
+    if (live) {
+        const float* col = lv.cls[l] + ((int64_t)j * (kAnchorsPerCell * C) + (int64_t)k * C) * hw + pp;    // + c * hw
+        float m = -INFINITY, m2 = -INFINITY;
+        int cmax = 0;
+        int c = 0;
+        for (; c + 8 <= C; c += 8) {                       // eight independent loads in flight per thread
+            float x[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) x[u] = __ldg(col + (int64_t)(c + u) * hw);
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                if (x[u] > m) {                            // strict: the first maximal class stays
+                    m2 = m;
+                    m = x[u];
+                    cmax = c + u;
+                } else {
+                    m2 = fmaxf(m2, x[u]);
+                }
+            }
+        }
+        for (; c < C; ++c) {
+            const float x = __ldg(col + (int64_t)c * hw);
+            if (x > m) {
+                m2 = m;
+                m = x;
+                cmax = c;
+            } else {
+                m2 = fmaxf(m2, x);
+            }
+        }
+        if (m > prefilter) {
+            const float t = is_logits ? ((m > 10.05f) ? 10.0f : m - 0.05f) : m;
+            if (!is_logits || m2 < t) {
+                // only the maximal raw value can attain the maximal probability (ties in the raw value: first index)
+                best = is_logits ? sigmoid_exact(m) : m;
+                best_c = cmax;
+            } else {
+                best = -1.0f;
+                for (int c2 = 0; c2 < C; ++c2) {
+                    const float x = __ldg(col + (int64_t)c2 * hw);
+                    if (x >= t) {
+                        const float pr = sigmoid_exact(x);
+                        if (pr > best) {                   // strict: first maximal index, like torch.max(dim=1)
+                            best = pr;
+                            best_c = c2;
+                        }
+                    }
+                }
+            }
+            is_cand = best > score_thresh;                 // model.py:536  scores > 0.05
+        }
+    }
+    const unsigned ballot = __ballot_sync(0xffffffffu, is_cand);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) warp_tot[warp] = __popc(ballot);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int tot = 0;
+#pragma unroll
+        for (int w = 0; w < kHeadFilterPos / 32; ++w) {
+            const int cnt = warp_tot[w];
+            warp_tot[w] = tot;
+            tot += cnt;
+        }
+        block_base = tot ? atomicAdd(&counts[j], tot) : 0;
+    }
+    __syncthreads();
+    if (is_cand) {
+        const int64_t slot = (int64_t)block_base + warp_tot[warp] + __popc(ballot & ((1u << lane) - 1u));
+        if (slot < capacity) {
+            const int64_t an = lv.anchor_off[l] + (int64_t)pp * kAnchorsPerCell + k;
+            const float* rp = lv.reg[l] + ((int64_t)j * (kAnchorsPerCell * 4) + k * 4) * hw + pp;
+            const float4 d = make_float4(rp[0], rp[hw], rp[2 * (int64_t)hw], rp[3 * (int64_t)hw]);
+            const float4 b = decode_clip(anchors[an], d, img_w, img_h);
+            float4* dst = reinterpret_cast<float4*>(cand + (int64_t)j * capacity + slot);
+            dst[0] = b;
+            dst[1] = make_float4(best, __int_as_float(best_c), __int_as_float((int)an), 0.0f);
+            keys[(int64_t)j * capacity + slot] = make_key(best, (int)an);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // K5: top-k by radix select on the 32 score bits (3 passes of 11/11/10 bits), then exact ordering of the
 // survivors by the full 64-bit key with a tiled rank sort.  Everything is per image; no host sync.
 // select state per image: [0] prefix (score bits decided so far), [1] remaining k, [2] survivors written, [3] done flag
@@ -884,6 +1008,55 @@ int cldet_decode_filter(const float* d_cls, int is_logits, const float* d_reg, c
             d_cls, is_logits, reinterpret_cast<const float4*>(d_reg), reinterpret_cast<const float4*>(d_anchors), num_anchors,
             num_classes, rows, stride, (float)width, (float)height, score_thresh, prefilter, d_candidates, d_keys, capacity,
             d_counts);
+    CLDET_LAUNCH_CHECK();
+    return CLDET_OK;
+}
+
+int cldet_decode_filter_head(const float* const* h_cls_levels, const float* const* h_reg_levels, int num_levels,
+                             int image_height, int image_width, int is_logits, const float* d_anchors, int num_images,
+                             int num_classes, float score_thresh, cldet_candidate* d_candidates, uint64_t* d_keys,
+                             int64_t capacity, int32_t* d_counts, void* stream) {
+    if (!h_cls_levels || !h_reg_levels || !d_anchors || !d_candidates || !d_keys || !d_counts) return CLDET_ERR_INVALID_ARGUMENT;
+    if (num_levels != kNumLevels || image_height <= 0 || image_width <= 0) return CLDET_ERR_INVALID_ARGUMENT;
+    if (num_images <= 0 || num_images > 65535 || num_classes <= 0 || capacity <= 0) return CLDET_ERR_INVALID_ARGUMENT;
+    HeadFilterLevels lv;
+    lv.n = num_levels;
+    int64_t aoff = 0;
+    int coff = 0;
+    for (int l = 0; l < kHeadFilterMaxLevels; ++l) {
+        lv.cls[l] = lv.reg[l] = nullptr;
+        lv.hw[l] = 0;
+        lv.pos_chunks[l] = 1;
+    }
+    for (int l = 0; l < num_levels; ++l) {
+        const int sh = 3 + l;
+        const int64_t hw = (int64_t)((image_height + (1 << sh) - 1) >> sh) * ((image_width + (1 << sh) - 1) >> sh);
+        if (hw <= 0 || hw > (1 << 26) || !h_cls_levels[l] || !h_reg_levels[l]) return CLDET_ERR_INVALID_ARGUMENT;
+        lv.cls[l] = h_cls_levels[l];
+        lv.reg[l] = h_reg_levels[l];
+        lv.hw[l] = (int)hw;
+        lv.anchor_off[l] = aoff;
+        lv.chunk_off[l] = coff;
+        lv.pos_chunks[l] = (int)((hw + kHeadFilterPos - 1) / kHeadFilterPos);
+        aoff += hw * kAnchorsPerCell;
+        coff += kAnchorsPerCell * lv.pos_chunks[l];
+    }
+    for (int l = num_levels; l <= kHeadFilterMaxLevels; ++l) {
+        lv.anchor_off[l] = aoff;
+        lv.chunk_off[l] = coff;
+    }
+    float prefilter;
+    if (is_logits) {
+        if (score_thresh <= 0.0f) prefilter = -INFINITY;
+        else if (score_thresh >= 1.0f) prefilter = INFINITY;
+        else prefilter = (float)(log((double)score_thresh / (1.0 - (double)score_thresh)) - 0.01);
+    } else {
+        prefilter = score_thresh;
+    }
+    dim3 grid((unsigned)coff, (unsigned)num_images);
+    decode_filter_head_kernel<<<grid, kHeadFilterPos, 0, (cudaStream_t)stream>>>(
+        lv, is_logits, reinterpret_cast<const float4*>(d_anchors), aoff, num_classes, (float)image_width, (float)image_height,
+        score_thresh, prefilter, d_candidates, d_keys, capacity, d_counts);
     CLDET_LAUNCH_CHECK();
     return CLDET_OK;
 }

@@ -112,15 +112,62 @@ def detect_batch(cls, regressions, anchors, height, width, is_logits=True, score
     n, a, nc = c.shape
     dev = c.device
     lib = _lib.load()
+
+    def run_filter(cand, keys, counts, st):
+        _lib.check(lib.cldet_decode_filter(c.data_ptr(), int(bool(is_logits)), r.data_ptr(), anc.data_ptr(), n, a, nc,
+                                           int(height), int(width), float(score_thresh), cand.data_ptr(), keys.data_ptr(),
+                                           a, counts.data_ptr(), st))
+
+    return _detect_pipeline(run_filter, n, a, dev, iou_threshold, pre_nms_topk, nms_mode, vanilla_numel_limit, return_padded)
+
+
+def detect_batch_head(cls_levels, reg_levels, anchors, height, width, is_logits=True, score_thresh=0.05, iou_threshold=0.5,
+                      pre_nms_topk=0, nms_mode=NMS_MODE_TORCHVISION, vanilla_numel_limit=CUDA_VANILLA_NUMEL_LIMIT,
+                      return_padded=False):
+    """detect_batch on the head's RAW conv outputs (eval side; beyond the reference's signature).
+
+    cls_levels / reg_levels: the five per-level results of the classification / regression output convolutions,
+    [N, 9*C, H_l, W_l] logits (or probabilities with is_logits=False) and [N, 36, H_l, W_l], contiguous NCHW -- what
+    ClassificationModel / RegressionModel hold BEFORE their permute + contiguous + view (retinanet/model.py:125-130, 170-184)
+    and before ResNet.forward's torch.cat (model.py:472-474).  anchors = Anchors()(img) for the (height, width) input.
+    Same results as detect_batch on the reshaped + concatenated tensors, bit for bit."""
+    cl = [_check_cuda_f32('cls_levels[%d]' % i, t) for i, t in enumerate(cls_levels)]
+    rl = [_check_cuda_f32('reg_levels[%d]' % i, t) for i, t in enumerate(reg_levels)]
+    anc = _aligned(_check_cuda_f32('anchors', anchors).reshape(-1, 4))
+    h, w = int(height), int(width)
+    if len(cl) != 5 or len(rl) != 5 or cl[0].dim() != 4 or cl[0].shape[1] % 9 != 0:
+        raise ValueError('expected the 5 pyramid levels (3..7) of both heads, classification [N, 9*C, H_l, W_l]')
+    n, nc = cl[0].shape[0], cl[0].shape[1] // 9
+    a = 0
+    for l in range(5):
+        hl, wl = (h + 2 ** (l + 3) - 1) // 2 ** (l + 3), (w + 2 ** (l + 3) - 1) // 2 ** (l + 3)
+        if tuple(cl[l].shape) != (n, 9 * nc, hl, wl) or tuple(rl[l].shape) != (n, 36, hl, wl):
+            raise ValueError('level %d: expected cls [%d,%d,%d,%d] and reg [%d,36,%d,%d] for a %dx%d input'
+                             % (l + 3, n, 9 * nc, hl, wl, n, hl, wl, h, w))
+        a += 9 * hl * wl
+    if anc.shape[0] != a:
+        raise ValueError('anchors must be [1,%d,4] for a %dx%d input' % (a, h, w))
+    dev = cl[0].device
+    lib = _lib.load()
+    pc, pr = _lib.ptr_array(cl), _lib.ptr_array(rl)
+
+    def run_filter(cand, keys, counts, st):
+        _lib.check(lib.cldet_decode_filter_head(pc, pr, 5, h, w, int(bool(is_logits)), anc.data_ptr(), n, nc, float(score_thresh),
+                                                cand.data_ptr(), keys.data_ptr(), a, counts.data_ptr(), st))
+
+    return _detect_pipeline(run_filter, n, a, dev, iou_threshold, pre_nms_topk, nms_mode, vanilla_numel_limit, return_padded)
+
+
+def _detect_pipeline(run_filter, n, a, dev, iou_threshold, pre_nms_topk, nms_mode, vanilla_numel_limit, return_padded):
+    """Candidate filter (K4 / K4h, supplied by the caller) -> K5 select + rank sort -> K6 NMS -> gather."""
+    lib = _lib.load()
     topk = int(pre_nms_topk) if pre_nms_topk and pre_nms_topk > 0 else 0
     with torch.cuda.device(dev):
         st = _stream()
         counts = torch.zeros(n, dtype=torch.int32, device=dev)
         cand = torch.empty((n, a, _CAND_BYTES), dtype=torch.uint8, device=dev)
         keys = torch.empty((n, a), dtype=torch.int64, device=dev)
-        _lib.check(lib.cldet_decode_filter(c.data_ptr(), int(bool(is_logits)), r.data_ptr(), anc.data_ptr(), n, a, nc,
-                                           int(height), int(width), float(score_thresh), cand.data_ptr(), keys.data_ptr(),
-                                           a, counts.data_ptr(), st))
+        run_filter(cand, keys, counts, st)
         if topk:
             max_count, cap = a, min(topk, a)
         else:

@@ -286,6 +286,18 @@ int cldet_decode_filter(const float* d_cls, int is_logits, const float* d_reg, c
                         int64_t num_anchors, int num_classes, int height, int width, float score_thresh,
                         cldet_candidate* d_candidates, uint64_t* d_keys, int64_t capacity, int32_t* d_counts, void* stream);
 
+/* The same filter on the head's RAW conv outputs (eval side): h_cls_levels / h_reg_levels are HOST arrays of
+ * num_levels (= 5) device pointers to classification [N, 9*C, H_l, W_l] and regression [N, 36, H_l, W_l] tensors exactly as
+ * the output convolutions produce them (layout as in cldet_focal_loss_head), replacing the per-level permute + contiguous +
+ * view (retinanet/model.py:125-130, 170-184) and the torch.cat over levels (model.py:472-474) in front of ResNet.predict
+ * (model.py:507-550).  d_anchors: the standard grid of (image_height, image_width).  Candidates, keys and counts are
+ * written exactly as by cldet_decode_filter (anchor indices in the reference's concatenated order), so
+ * cldet_sort_candidates / cldet_nms_sorted / cldet_gather_detections follow unchanged. */
+int cldet_decode_filter_head(const float* const* h_cls_levels, const float* const* h_reg_levels, int num_levels,
+                             int image_height, int image_width, int is_logits, const float* d_anchors, int num_images,
+                             int num_classes, float score_thresh, cldet_candidate* d_candidates, uint64_t* d_keys,
+                             int64_t capacity, int32_t* d_counts, void* stream);
+
 /* Order each image's candidates by (score descending, anchor ascending) -- the order torchvision's stable
  * descending sort gives the reference's anchor-ordered candidate list -- and optionally keep only the first
  * `topk` of them (topk <= 0: keep all; the reference has no top-k).  With topk > 0 a 3-pass radix

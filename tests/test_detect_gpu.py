@@ -205,6 +205,44 @@ def test_full_size_vs_torch_eager_and_torchvision_on_the_same_device(mu, reg_sig
         assert torch.equal(got[j][2], b)
 
 
+def _conv_levels(x, h, w, per_anchor):
+    """[N, A, per_anchor] in the reference's concatenated order -> five [N, 9*per_anchor, H_l, W_l] conv-layout tensors
+    (the inverse of ClassificationModel / RegressionModel's permute + view and ResNet.forward's cat)."""
+    out, off, n = [], 0, x.shape[0]
+    for l in range(3, 8):
+        hl, wl = (h + 2 ** l - 1) // 2 ** l, (w + 2 ** l - 1) // 2 ** l
+        cnt = hl * wl * 9
+        out.append(x[:, off:off + cnt].reshape(n, hl, wl, 9 * per_anchor).permute(0, 3, 1, 2).contiguous())
+        off += cnt
+    assert off == x.shape[1]
+    return out
+
+
+@pytest.mark.parametrize('h,w,C,N,mu,topk,logits', [(800, 1333, 80, 3, -10.5, 0, True), (800, 1333, 80, 2, -4.0, 1000, True),
+                                                    (512, 512, 20, 4, -6.0, 0, True), (33, 70, 7, 2, -3.0, 50, True),
+                                                    (608, 1024, 16, 2, -5.0, 300, False), (1, 1, 3, 2, 0.0, 0, True)])
+def test_conv_layout_filter_equals_concatenated_path(h, w, C, N, mu, topk, logits):
+    """SURVEY 8f row f1, eval side: detect_batch_head on the head's raw conv outputs vs detect_batch on the reference's
+    reshaped + concatenated tensors -- scores, labels, boxes and order bit for bit (quantised logits give exact ties in the
+    class maximum, saturated logits exercise the equal-probability rule)."""
+    anchors = cld.generate_anchors(h, w, DEV)
+    A = anchors.shape[1]
+    gen = torch.Generator(device=DEV).manual_seed(h + C)
+    x = torch.randn(N, A, C, device=DEV, generator=gen) * 2 + mu
+    x[0] = torch.round(x[0] * 4) / 4                              # exact ties between classes
+    if N > 1:
+        x[1, ::7] += 16.0                                         # saturated sigmoid: several classes with p == 1.0f
+    if not logits:
+        x = torch.sigmoid(x)
+    reg = torch.randn(N, A, 4, device=DEV, generator=gen) * 0.4
+    ref = D.detect_batch(x, reg, anchors, h, w, is_logits=logits, pre_nms_topk=topk)
+    got = D.detect_batch_head(_conv_levels(x, h, w, C), _conv_levels(reg, h, w, 4), anchors, h, w, is_logits=logits,
+                              pre_nms_topk=topk)
+    for (s0, l0, b0), (s1, l1, b1) in zip(ref, got):
+        assert torch.equal(s0, s1) and torch.equal(l0, l1) and torch.equal(b0, b1)
+    assert sum(int(s.shape[0]) for s, _, _ in ref) > 0 or A < 100
+
+
 def test_f4_coco_results_vs_oracle_and_torch_cpu():
     """evaluator post-processing (evaluator.py:329-361) on the device, bit-exact with the CPU statements."""
     h, w, C, N = 256, 320, 7, 3

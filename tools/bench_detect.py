@@ -92,9 +92,57 @@ def measure(args, dev=None, return_inputs=False):
             'roofline': {'bound': 'hbm', 'kernel': 'decode_filter_kernel<4>', 'achieved': filt_bytes / (stage[0] * 1e-3) / 1e9,
                          'peak': peak, 'unit': 'GB/s', 'frac': filt_bytes / (stage[0] * 1e-3) / 1e9 / peak,
                          'algorithmic_bytes_per_launch': filt_bytes}}
+    if getattr(args, 'head', False):
+        line['conv_layout'] = measure_head(args, dev, logits, reg, anchors, h, w)
     if return_inputs:
         return line, (logits, reg, anchors, h, w)
     return line
+
+
+def measure_head(args, dev, logits, reg, anchors, h, w):
+    """SURVEY 8f row f1, eval side: head outputs in conv layout -> detections.  ref-layout = the reference's per-level
+    permute + contiguous + view and torch.cat (model.py:125-130, 170-184, 472-474) followed by detect_batch; head-layout =
+    detect_batch_head on the conv outputs as they are."""
+    from cl_object_detection_b200 import detect as D
+    n, a, c = logits.shape
+    shapes = [((h + 2 ** l - 1) // 2 ** l, (w + 2 ** l - 1) // 2 ** l) for l in range(3, 8)]
+
+    def to_levels(x, per):
+        out, off = [], 0
+        for hl, wl in shapes:
+            cnt = hl * wl * 9
+            out.append(x[:, off:off + cnt].reshape(n, hl, wl, 9 * per).permute(0, 3, 1, 2).contiguous())
+            off += cnt
+        return out
+
+    cls_lv, reg_lv = to_levels(logits, c), to_levels(reg, 4)
+
+    def cat_layout(levels, per):
+        return torch.cat([t.permute(0, 2, 3, 1).contiguous().view(t.shape[0], -1, per) for t in levels], dim=1)
+
+    def ref_step():
+        return D.detect_batch(cat_layout(cls_lv, c), cat_layout(reg_lv, 4), anchors, h, w, pre_nms_topk=args.topk, return_padded=True)
+
+    def head_step():
+        return D.detect_batch_head(cls_lv, reg_lv, anchors, h, w, pre_nms_topk=args.topk, return_padded=True)
+
+    def timeit(fn):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0.record()
+        for _ in range(args.steps):
+            fn()
+        t1.record()
+        torch.cuda.synchronize()
+        return t0.elapsed_time(t1) / args.steps
+
+    r0, r1 = ref_step(), head_step()
+    same = all(torch.equal(x0, x1) for x0, x1 in zip(r0, r1))
+    ms_ref, ms_head = timeit(ref_step), timeit(head_step)
+    return {'ref_layout_ms': ms_ref, 'head_layout_ms': ms_head, 'speedup': ms_ref / ms_head,
+            'images_per_s_head_layout': n / (ms_head * 1e-3), 'identical_detections': bool(same)}
 
 
 def main():
@@ -105,6 +153,7 @@ def main():
     ap.add_argument('--mu', type=float, default=-4.0)
     ap.add_argument('--topk', type=int, default=1000)
     ap.add_argument('--classes', type=int, default=80)
+    ap.add_argument('--head', action='store_true', help='also time the conv-layout entry (detect_batch_head)')
     print(json.dumps(measure(ap.parse_args())))
 
 
