@@ -18,8 +18,8 @@ python tools/bench_head_layout.py --logits >> gpurun_out/bench_head_layout.json 
 python tools/bench_head_layout.py --steps 2 > gpurun_out/plain3.log 2>&1 && \
   ncu --set full --clock-control none --import-source on -k regex:focal_loss_head_kernel -c 1 -o gpurun_out/r01_head_final --force-overwrite \
       python tools/bench_head_layout.py --steps 2 > gpurun_out/ncu_h.log 2>&1
-python tools/bench_detect.py > gpurun_out/detect_dense.json 2>/dev/null
-python tools/bench_detect.py --mu -10.5 > gpurun_out/detect_sparse.json 2>/dev/null
+python tools/bench_detect.py --head > gpurun_out/detect_dense.json 2>/dev/null
+python tools/bench_detect.py --mu -10.5 --head > gpurun_out/detect_sparse.json 2>/dev/null
 python tools/bench_api.py > gpurun_out/bench_api.jsonl 2>/dev/null
 python tools/bench_logits.py > gpurun_out/bench_logits.json 2>/dev/null
 python tools/bench_distill.py > gpurun_out/bench_distill.json 2>/dev/null
