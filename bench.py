@@ -215,11 +215,13 @@ def decode_section(dev, with_eager):
     from tools.bench_detect import measure
     out = {}
     for name, mu, eager_images in (('all_anchors_candidates', -4.0, 2), ('trained_like', -10.5, 8)):
-        a = _ap.Namespace(steps=10, warmup=3, images=32, mu=mu, topk=1000, classes=C)
+        a = _ap.Namespace(steps=10, warmup=3, images=32, mu=mu, topk=1000, classes=C, head=True)
         line, (logits, reg, anchors, h, w) = measure(a, dev, return_inputs=True)
         entry = {'value': line['value'], 'unit': 'images/s', 'ms_per_step': line['ms_per_step'], 'steps': a.steps,
                  'workload': line['config']['workload'], 'candidates_per_image': line['config']['candidates_per_image'],
-                 'kept_per_image': line['config']['kept_per_image'], 'stage_ms': line['stage_ms'], 'roofline': line['roofline']}
+                 'kept_per_image': line['config']['kept_per_image'], 'stage_ms': line['stage_ms'], 'roofline': line['roofline'],
+                 # the same detections from the head's raw conv outputs (detect_batch_head) vs the reference's layout ops + detect_batch
+                 'conv_layout': line.get('conv_layout')}
         if with_eager:
             try:
                 from oracle import torch_eager as E

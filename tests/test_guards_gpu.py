@@ -177,3 +177,29 @@ def test_detection_pipeline_writes_stay_in_bounds(C, topk):
     torch.cuda.synchronize()
     g.check()
     assert int(keep_counts.min()) > 0 and int(offs[N]) <= int(keep_counts.sum())
+
+
+@pytest.mark.parametrize('h,w,C', [(200, 264, 80), (96, 104, 7), (33, 70, 4)])
+def test_conv_layout_filter_writes_stay_in_bounds(h, w, C):
+    """cldet_decode_filter_head with a candidate capacity SMALLER than the number of candidates: counts may exceed the
+    capacity, records and keys must not be written past it."""
+    lib = _lib.load()
+    N = 2
+    anchors = cld.generate_anchors(h, w, DEV)
+    A = anchors.shape[1]
+    shapes = [((h + 2 ** l - 1) // 2 ** l, (w + 2 ** l - 1) // 2 ** l) for l in range(3, 8)]
+    cls_lv = [torch.randn(N, 9 * C, hl, wl, device=DEV) for hl, wl in shapes]          # ~every anchor is a candidate
+    reg_lv = [torch.randn(N, 36, hl, wl, device=DEV) * 0.3 for hl, wl in shapes]
+    cap = max(1, A // 3)
+    g = Guarded()
+    cand, keys = g.alloc((N, cap, 32), torch.uint8), g.alloc((N, cap), torch.int64)
+    counts = g.alloc((N,), torch.int32)
+    counts.zero_()
+    st = torch.cuda.current_stream().cuda_stream
+    _lib.check(lib.cldet_decode_filter_head(_lib.ptr_array(cls_lv), _lib.ptr_array(reg_lv), 5, h, w, 1, anchors.data_ptr(), N, C,
+                                            0.05, cand.data_ptr(), keys.data_ptr(), cap, counts.data_ptr(), st))
+    torch.cuda.synchronize()
+    g.check()
+    assert int(counts.min()) > cap
+    assert lib.cldet_decode_filter_head(_lib.ptr_array(cls_lv), _lib.ptr_array(reg_lv), 4, h, w, 1, anchors.data_ptr(), N, C, 0.05,
+                                        cand.data_ptr(), keys.data_ptr(), cap, counts.data_ptr(), st) == 1
