@@ -621,3 +621,8 @@ def test_head_layout_equals_concatenated_path(h, w, C, N, G, logits, empty):
         assert ((a_ - b_).abs() <= 2e-6 * b_.abs()).all()
     for a_, b_ in zip(got[4], ref[4]):
         assert torch.equal(a_, b_)
+    # forward only (torch.no_grad(): the GRAD = false kernels): same per-image terms, bit for bit
+    with torch.no_grad():
+        out = fl.forward_head(raw, regs, anchors, ann, 0, cld.HeadParams(), (h, w))
+    assert torch.equal(out['cls_loss'][0], got[0]) and torch.equal(out['cls_loss'][1], got[1])
+    assert torch.equal(out['reg_loss'], got[2])
