@@ -272,6 +272,37 @@ def run_reference(args):
     return 0
 
 
+def bind_near_gpu(index):
+    """Best effort, for the e2e leg on multi-socket boxes: run this rank on the CPUs NVML reports as local to its GPU and
+    prefer that NUMA node for the pinned staging buffers, so that eight ranks do not pull their host->device copies across
+    the socket interconnect.  Returns a short description for the JSON line; never raises."""
+    note = []
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, 16)                 # 1024 CPUs
+        cpus = {64 * i + b for i, wd in enumerate(words) for b in range(64) if (int(wd) >> b) & 1}
+        usable = cpus & os.sched_getaffinity(0)
+        if usable:
+            os.sched_setaffinity(0, usable)
+            note.append('cpus=%d' % len(usable))
+        bus = pynvml.nvmlDeviceGetPciInfo(h).busId
+        bus = bus.decode() if isinstance(bus, bytes) else bus
+        node_file = '/sys/bus/pci/devices/%s/numa_node' % bus.lower()[-12:]
+        node = int(open(node_file).read().strip()) if os.path.exists(node_file) else -1
+        if node >= 0:
+            libc = ctypes.CDLL(None, use_errno=True)
+            mask = (ctypes.c_ulong * 16)()
+            mask[node // 64] = 1 << (node % 64)
+            # set_mempolicy(MPOL_PREFERRED = 1, nodemask, maxnode): syscall 238 on x86_64
+            rc = libc.syscall(238, 1, mask, 1024)
+            note.append('numa_node=%d%s' % (node, '' if rc == 0 else ' (mempolicy refused)'))
+    except Exception as e:  # noqa: BLE001
+        note.append('unavailable: %s' % type(e).__name__)
+    return ', '.join(note) if note else 'none'
+
+
 # --------------------------------------------------------------------------------------------------------------
 # our arm
 # --------------------------------------------------------------------------------------------------------------
@@ -290,6 +321,7 @@ def run_ours(args):
         raise SystemExit('bench.py needs a CUDA device (there is no CPU fallback for the product path)')
     torch.cuda.set_device(local_rank)
     dev = torch.device('cuda', local_rank)
+    numa = bind_near_gpu(local_rank) if world > 1 else 'not applied (1 GPU)'
     if world > 1:
         # NCCL writes its banner / debug lines to stdout unless told otherwise: keep stdout for the one JSON line
         os.environ.setdefault('NCCL_DEBUG_FILE', '/dev/stderr')
@@ -493,7 +525,8 @@ def run_ours(args):
                            'images_per_gpu': n, 'global_batch': n_global, 'parallelism': 'image-sharded dp%d' % world,
                            'collective': {'none': 'none (1 GPU)', 'peer': 'fused into the loss kernel: NVLink peer stores + arrival counters',
                                           'nccl': 'NCCL all-gather of the [4,N] terms'}[collective],
-                           'l2': 'inputs (%.2f GB per GPU) are larger than the 126 MB L2; no flush needed' % (probs.numel() * 4 / 1e9)},
+                           'l2': 'inputs (%.2f GB per GPU) are larger than the 126 MB L2; no flush needed' % (probs.numel() * 4 / 1e9),
+                           'host_binding_rank0': numa},
                 'clocks': clocks,
                 'e2e': {'value': n_global / e2e_s, 'unit': 'images/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
                         'ms_per_step': e2e_s * 1e3, 'steps': e2e_steps},
