@@ -162,3 +162,77 @@ def test_large_candidate_count_reference_mode():
     ref = O.detect(probs, reg.cpu().numpy(), O.anchors_for_image(h, w), h, w, is_logits=False, device_rule='cuda')
     assert ref['cand_scores'].shape[0] > 8000
     assert np.array_equal(s.cpu().numpy(), ref['scores']) and np.array_equal(l.cpu().numpy(), ref['labels'])
+
+
+def test_conv_layout_entries_from_threads_and_in_a_cuda_graph():
+    """The conv-layout entry points: six host threads on their own streams, then the fused call captured in
+    a CUDA graph and replayed (no host sync, no per-call memset, scratch left clean)."""
+    h, w, C, N, G = 160, 192, 8, 2, 5
+    rng = np.random.default_rng(21)
+    anchors = cld.generate_anchors(h, w, DEV)
+    shapes = [((h + 2 ** l - 1) // 2 ** l, (w + 2 ** l - 1) // 2 ** l) for l in range(3, 8)]
+    gen = torch.Generator(device=DEV).manual_seed(21)
+    cls_lv = [torch.sigmoid(torch.randn(N, 9 * C, hl, wl, device=DEV, generator=gen) * 2 - 3) for hl, wl in shapes]
+    reg_lv = [torch.randn(N, 36, hl, wl, device=DEV, generator=gen) * 0.4 for hl, wl in shapes]
+    ann = cu(synth_gt(rng, N, G, h, w, C))
+    fl = cld.FocalLoss()
+    with torch.no_grad():
+        want = fl.forward_head(cls_lv, reg_lv, anchors, ann, 0, cld.HeadParams(), (h, w))
+        want_det = D.detect_batch_head(cls_lv, reg_lv, anchors, h, w, is_logits=False)
+    torch.cuda.synchronize()
+    errors = []
+
+    def worker(t):
+        try:
+            with torch.cuda.stream(torch.cuda.Stream(device=DEV)):
+                for _ in range(5):
+                    with torch.no_grad():
+                        out = cld.FocalLoss().forward_head(cls_lv, reg_lv, anchors, ann, 0, cld.HeadParams(), (h, w))
+                    det = D.detect_batch_head(cls_lv, reg_lv, anchors, h, w, is_logits=False)
+                    assert torch.equal(out['cls_loss'][0], want['cls_loss'][0]) and torch.equal(out['cls_loss'][1], want['cls_loss'][1])
+                    for (s0, l0, b0), (s1, l1, b1) in zip(want_det, det):
+                        assert torch.equal(s0, s1) and torch.equal(l0, l1) and torch.equal(b0, b1)
+        except Exception as e:  # noqa: BLE001
+            errors.append((t, repr(e)))
+    threads = [threading.Thread(target=worker, args=(t,)) for t in range(6)]
+    for th in threads:
+        th.start()
+    for th in threads:
+        th.join()
+    assert not errors, errors
+
+    lib = _lib.load()
+    A = anchors.shape[1]
+    lp = to_loss_params(cld.HeadParams(), 0, C)
+    lp.image_height, lp.image_width = h, w
+    weights = torch.full((4, N), 1.0 / N, device=DEV)
+    gcls, greg = [torch.empty_like(t) for t in cls_lv], [torch.empty_like(t) for t in reg_lv]
+    losses = torch.empty((4, N), device=DEV)
+    meta = torch.empty((N, A), dtype=torch.int32, device=DEV)
+    npos = torch.empty(N, dtype=torch.int32, device=DEV)
+    nvalid = torch.empty(N, dtype=torch.int32, device=DEV)
+    ws = torch.zeros(lib.cldet_focal_loss_workspace_bytes(N, A), dtype=torch.uint8, device=DEV)
+    pc, pr, pgc, pgr = (_lib.ptr_array(x) for x in (cls_lv, reg_lv, gcls, greg))
+
+    def call():
+        _lib.check(lib.cldet_focal_loss_head(pc, pr, 5, h, w, anchors.data_ptr(), ann.data_ptr(), N, C, G, lp, weights.data_ptr(), None,
+                                             pgc, pgr, losses.data_ptr(), meta.data_ptr(), None, npos.data_ptr(), nvalid.data_ptr(),
+                                             None, None, ws.data_ptr(), ws.numel(), torch.cuda.current_stream().cuda_stream))
+    s = torch.cuda.Stream()
+    with torch.cuda.stream(s):
+        call()
+        torch.cuda.current_stream().synchronize()
+        first = (losses.clone(), gcls[0].clone(), greg[0].clone())
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=s):
+            call()
+        for _ in range(3):
+            losses.zero_(); gcls[0].zero_(); greg[0].zero_()
+            g.replay()
+        torch.cuda.current_stream().synchronize()
+    assert torch.equal(losses, first[0]) and torch.equal(gcls[0], first[1]) and torch.equal(greg[0], first[2])
+    assert torch.equal(losses[0], want['cls_loss'][0]) and torch.equal(losses[1], want['cls_loss'][1])
+    # counters / accumulators (header) and the assignment keys + bitmap (after the per-block partials) are left zeroed
+    header = (12 * N + 255) // 256 * 256
+    partials = (N * ((A + 31) // 32 + 72) * 16 + 255) // 256 * 256
+    assert int(ws[:12 * N].sum()) == 0 and int(ws[header + partials:].sum()) == 0
