@@ -359,6 +359,7 @@ decode_filter_head_kernel(const HeadFilterLevels lv, int is_logits, const float4
 // select state per image: [0] prefix (score bits decided so far), [1] remaining k, [2] survivors written, [3] done flag
 // ------------------------------------------------------------------------------------------------
 constexpr int kSelBins = 2048;
+constexpr int kRankDirect = 2048;      // up to this many candidates per image the O(n^2) rank sort beats radix select + compaction
 
 struct SelPass {
     int shift;     // bit position of this digit inside the 32 score bits
@@ -375,7 +376,9 @@ __global__ void select_init_kernel(const int32_t* __restrict__ counts, int64_t c
         uint32_t* st = state + 4 * j;
         st[0] = 0;
         st[2] = 0;
-        if (topk <= 0 || cnt <= topk) {   // keep everything
+        // keep everything: no top-k, fewer candidates than k, or few enough (kRankDirect) that the rank sort can order ALL
+        // of them and cut at k itself -- the three histogram/pick passes and the compaction then exit immediately
+        if (topk <= 0 || cnt <= topk || cnt <= kRankDirect) {
             st[1] = 0;
             st[3] = 1;
         } else {
@@ -473,7 +476,8 @@ select_compact_kernel(const cldet_candidate* __restrict__ cand, const uint64_t* 
     const int64_t cnt = min64(counts[j], capacity);
     const int64_t i0 = (int64_t)blockIdx.x * (256 * kCompactPerThread);
     if (i0 >= cnt) return;
-    const bool all = st[3] != 0;
+    if (st[3] != 0) return;              // everything is kept: the rank sort reads the original arrays
+    const bool all = false;
     const uint32_t thr = st[0];
     uint64_t key[kCompactPerThread];
     bool take[kCompactPerThread];
@@ -528,10 +532,18 @@ select_compact_kernel(const cldet_candidate* __restrict__ cand, const uint64_t* 
 __global__ void __launch_bounds__(256)
 rank_sort_kernel(const cldet_candidate* __restrict__ cand, const uint64_t* __restrict__ keys, const uint32_t* __restrict__ state,
                  const int32_t* __restrict__ counts_in, int64_t in_capacity, int topk, cldet_candidate* __restrict__ sorted,
-                 int64_t out_capacity, int32_t* __restrict__ sorted_counts) {
+                 int64_t out_capacity, int32_t* __restrict__ sorted_counts, const cldet_candidate* __restrict__ orig_cand = nullptr,
+                 const uint64_t* __restrict__ orig_keys = nullptr, int64_t orig_capacity = 0) {
     __shared__ uint64_t tile[1024];
     const int j = blockIdx.y;
     int64_t n = state ? (int64_t)state[4 * j + 2] : (int64_t)counts_in[j];
+    if (state && state[4 * j + 3] && orig_cand) {
+        // this image kept every candidate (select_init_kernel): nothing was compacted, order the original arrays
+        cand = orig_cand;
+        keys = orig_keys;
+        in_capacity = orig_capacity;
+        n = (int64_t)counts_in[j];
+    }
     n = min64(n, in_capacity);
     const int64_t limit = (topk > 0) ? min64(n, topk) : n;
     if (blockIdx.x == 0 && threadIdx.x == 0) sorted_counts[j] = (int32_t)min64(limit, out_capacity);
@@ -1113,8 +1125,8 @@ int cldet_sort_candidates(const cldet_candidate* d_candidates, const uint64_t* d
         // survivors are ~topk (plus exact score ties): size the grid for 2*topk, the kernel strides if there are more
         dim3 gr((unsigned)std::max<int64_t>(1, std::min<int64_t>((max_count + 255) / 256, (2 * (int64_t)topk + 255) / 256)),
                 (unsigned)num_images);
-        rank_sort_kernel<<<gr, 256, 0, s>>>(sel_cand, sel_keys, state, nullptr, max_count, topk, d_sorted, sorted_capacity,
-                                             d_sorted_counts);
+        rank_sort_kernel<<<gr, 256, 0, s>>>(sel_cand, sel_keys, state, d_counts, max_count, topk, d_sorted, sorted_capacity,
+                                             d_sorted_counts, d_candidates, d_keys, capacity);
         CLDET_LAUNCH_CHECK();
     } else {
         dim3 gc((unsigned)((max_count + 255) / 256), (unsigned)num_images);
