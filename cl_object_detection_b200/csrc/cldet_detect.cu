@@ -368,10 +368,11 @@ struct SelPass {
 };
 
 __global__ void select_init_kernel(const int32_t* __restrict__ counts, int64_t capacity, int topk, uint32_t* __restrict__ state,
-                                   uint32_t* __restrict__ hist, int N) {
+                                   uint32_t* __restrict__ hist, uint32_t* __restrict__ done, int N) {
     const int j = blockIdx.x;
     for (int b = threadIdx.x; b < kSelBins; b += blockDim.x) hist[(int64_t)j * kSelBins + b] = 0;
     if (threadIdx.x == 0) {
+        done[j] = 0;
         const int64_t cnt = min64(counts[j], capacity);
         uint32_t* st = state + 4 * j;
         st[0] = 0;
@@ -388,15 +389,24 @@ __global__ void select_init_kernel(const int32_t* __restrict__ counts, int64_t c
     }
 }
 
+// One radix pass: per-image histogram of the current digit among the keys that match the prefix decided so far, then the
+// image's LAST block to finish (threadfence + counter, as in the loss kernel) picks the digit where the descending cumulative
+// count crosses the remaining k, clears the histogram for the next pass and re-arms the counter.  (The pick used to be a
+// second launch per pass; in the trained-like regime the stage is a chain of short dependent launches, so each one removed
+// is ~5 us.)  In the pick, 256 threads own 8 consecutive bins each (high bins first); a shared-memory suffix scan over the
+// 256 partial sums locates the owning thread, which then walks its 8 bins.
 __global__ void __launch_bounds__(256)
-select_hist_kernel(const uint64_t* __restrict__ keys, const int32_t* __restrict__ counts, int64_t capacity, SelPass ps,
-                   const uint32_t* __restrict__ state, uint32_t* __restrict__ hist) {
+select_hist_pick_kernel(const uint64_t* __restrict__ keys, const int32_t* __restrict__ counts, int64_t capacity, SelPass ps,
+                        uint32_t* __restrict__ state, uint32_t* __restrict__ hist, uint32_t* __restrict__ done) {
     __shared__ uint32_t sh[kSelBins];
+    __shared__ uint32_t part[256];
+    __shared__ bool is_last;
     const int j = blockIdx.y;
-    const uint32_t* st = state + 4 * j;
-    if (st[3]) return;
+    uint32_t* st = state + 4 * j;
+    if (st[3]) return;                                   // everything is kept (block-uniform)
     const int64_t cnt = min64(counts[j], capacity);
-    if ((int64_t)blockIdx.x * blockDim.x >= cnt) return;
+    const unsigned int nblk = (unsigned int)min64((int64_t)gridDim.x, (cnt + blockDim.x - 1) / blockDim.x);   // blocks with work
+    if (blockIdx.x >= nblk) return;
     const int nb = 1 << ps.bits;
     for (int b = threadIdx.x; b < nb; b += blockDim.x) sh[b] = 0;
     __syncthreads();
@@ -408,26 +418,23 @@ select_hist_kernel(const uint64_t* __restrict__ keys, const int32_t* __restrict_
         if (match) atomicAdd(&sh[(s >> ps.shift) & (nb - 1)], 1u);
     }
     __syncthreads();
-    for (int b = threadIdx.x; b < nb; b += blockDim.x)
-        if (sh[b]) atomicAdd(&hist[(int64_t)j * kSelBins + b], sh[b]);
-}
-
-// one block per image: find the digit where the descending cumulative count crosses the remaining k.
-// 256 threads own 8 consecutive bins each (high bins first); a shared-memory suffix scan over the 256 partial sums
-// locates the owning thread, which then walks its 8 bins.
-__global__ void __launch_bounds__(256) select_pick_kernel(SelPass ps, uint32_t* __restrict__ state, uint32_t* __restrict__ hist) {
-    __shared__ uint32_t sh[kSelBins];
-    __shared__ uint32_t part[256];
-    const int j = blockIdx.x;
-    uint32_t* st = state + 4 * j;
-    const int nb = 1 << ps.bits;
     uint32_t* h = hist + (int64_t)j * kSelBins;
-    for (int b = threadIdx.x; b < kSelBins; b += blockDim.x) {
-        sh[b] = (b < nb) ? h[b] : 0u;
-        h[b] = 0;                       // ready for the next pass
-    }
+    for (int b = threadIdx.x; b < nb; b += blockDim.x)
+        if (sh[b]) atomicAdd(&h[b], sh[b]);
+    __threadfence();
     __syncthreads();
-    if (st[3]) return;                  // block-uniform
+    if (threadIdx.x == 0) is_last = (atomicAdd(&done[j], 1u) == nblk - 1u);
+    __syncthreads();
+    if (!is_last) return;
+
+    // ---- the image's last block: pick the digit ----
+    __threadfence();
+    for (int b = threadIdx.x; b < kSelBins; b += blockDim.x) {
+        sh[b] = (b < nb) ? __ldcg(h + b) : 0u;           // written by other blocks' atomics: read through L2
+        h[b] = 0;                                        // ready for the next pass
+    }
+    if (threadIdx.x == 0) done[j] = 0;
+    __syncthreads();
     // thread t owns bins [hi-7, hi] with hi = kSelBins-1-8t (descending order)
     const int hi = kSelBins - 1 - 8 * (int)threadIdx.x;
     uint32_t mine = 0;
@@ -1077,6 +1084,7 @@ size_t cldet_sort_workspace_bytes(int num_images, int64_t max_count, int topk) {
     if (num_images <= 0 || max_count < 0) return 0;
     size_t off = align_up((size_t)num_images * 4 * sizeof(uint32_t), 256);            // select state
     off = align_up(off + (size_t)num_images * kSelBins * sizeof(uint32_t), 256);      // histograms
+    off = align_up(off + (size_t)num_images * sizeof(uint32_t), 256);                 // per-image "blocks done" counters
     if (topk > 0) {                                                                  // compacted survivors (with ties)
         off = align_up(off + (size_t)num_images * max_count * sizeof(cldet_candidate), 256);
         off = align_up(off + (size_t)num_images * max_count * sizeof(uint64_t), 256);
@@ -1102,20 +1110,20 @@ int cldet_sort_candidates(const cldet_candidate* d_candidates, const uint64_t* d
     size_t off = align_up((size_t)num_images * 4 * sizeof(uint32_t), 256);
     uint32_t* hist = reinterpret_cast<uint32_t*>(p + off);
     off = align_up(off + (size_t)num_images * kSelBins * sizeof(uint32_t), 256);
+    uint32_t* done = reinterpret_cast<uint32_t*>(p + off);
+    off = align_up(off + (size_t)num_images * sizeof(uint32_t), 256);
     const int blocks_x = (int)std::min<int64_t>((max_count + 255) / 256, 4096);
 
     if (topk > 0) {
         cldet_candidate* sel_cand = reinterpret_cast<cldet_candidate*>(p + off);
         off = align_up(off + (size_t)num_images * max_count * sizeof(cldet_candidate), 256);
         uint64_t* sel_keys = reinterpret_cast<uint64_t*>(p + off);
-        select_init_kernel<<<num_images, 256, 0, s>>>(d_counts, capacity, topk, state, hist, num_images);
+        select_init_kernel<<<num_images, 256, 0, s>>>(d_counts, capacity, topk, state, hist, done, num_images);
         CLDET_LAUNCH_CHECK();
         const SelPass passes[3] = {{21, 11, 0}, {10, 11, 11}, {0, 10, 22}};
         for (int ps = 0; ps < 3; ++ps) {
             dim3 g((unsigned)std::max(1, std::min(blocks_x / 8, 16)), (unsigned)num_images);
-            select_hist_kernel<<<g, 256, 0, s>>>(d_keys, d_counts, capacity, passes[ps], state, hist);
-            CLDET_LAUNCH_CHECK();
-            select_pick_kernel<<<num_images, 256, 0, s>>>(passes[ps], state, hist);
+            select_hist_pick_kernel<<<g, 256, 0, s>>>(d_keys, d_counts, capacity, passes[ps], state, hist, done);
             CLDET_LAUNCH_CHECK();
         }
         const int64_t per_block = 256 * kCompactPerThread;
