@@ -626,10 +626,17 @@ __global__ void __launch_bounds__(64)
 nms_mask_kernel(const cldet_candidate* __restrict__ sorted, const int32_t* __restrict__ counts, int64_t capacity,
                 const uint32_t* __restrict__ info, float thr, uint64_t* __restrict__ mask, int64_t mask_stride_img,
                 int col_blocks_alloc) {
-    const int j = blockIdx.z;
+    const int j = blockIdx.y;
     const int n = (int)min64(counts[j], capacity);
-    const int row_blk = blockIdx.y, col_blk = blockIdx.x;
-    if (col_blk < row_blk) return;
+    // blockIdx.x enumerates the UPPER-TRIANGULAR 64x64 tiles row by row: tile t of row r starts at r*cb - r(r-1)/2
+    // (a square grid launched twice as many blocks, half of which only returned: this kernel is block-scheduling bound)
+    const int cb = col_blocks_alloc;
+    const long long t = blockIdx.x;
+    int row_blk = (int)floor(((2.0 * cb + 1.0) - sqrt((2.0 * cb + 1.0) * (2.0 * cb + 1.0) - 8.0 * (double)t)) * 0.5);
+    row_blk = max(0, min(row_blk, cb - 1));
+    while (row_blk > 0 && (long long)row_blk * cb - (long long)row_blk * (row_blk - 1) / 2 > t) --row_blk;
+    while ((long long)(row_blk + 1) * cb - (long long)(row_blk + 1) * row_blk / 2 <= t) ++row_blk;
+    const int col_blk = row_blk + (int)(t - ((long long)row_blk * cb - (long long)row_blk * (row_blk - 1) / 2));
     if (row_blk * 64 >= n || col_blk * 64 >= n) return;
     const int mode = (int)info[2 * j + 1];
     const float off_unit = __uint_as_float(info[2 * j]) + 1.0f;       // max_coordinate + 1
@@ -1166,7 +1173,9 @@ int cldet_nms_sorted(const cldet_candidate* d_sorted, const int32_t* d_sorted_co
     if (w.col_blocks > 65535) return CLDET_ERR_UNSUPPORTED;
     nms_prepare_kernel<<<num_images, 256, 0, s>>>(d_sorted, d_sorted_counts, capacity, mode, vanilla_numel_limit, w.info);
     CLDET_LAUNCH_CHECK();
-    dim3 grid((unsigned)w.col_blocks, (unsigned)w.col_blocks, (unsigned)num_images);
+    const long long tiles = (long long)w.col_blocks * (w.col_blocks + 1) / 2;          // upper-triangular tiles per image
+    if (tiles > 2147483647ll) return CLDET_ERR_UNSUPPORTED;
+    dim3 grid((unsigned)tiles, (unsigned)num_images);
     nms_mask_kernel<<<grid, 64, 0, s>>>(d_sorted, d_sorted_counts, capacity, w.info, iou_thresh, w.mask, w.mask_stride_img,
                                         w.col_blocks);
     CLDET_LAUNCH_CHECK();
