@@ -359,6 +359,7 @@ decode_filter_head_kernel(const HeadFilterLevels lv, int is_logits, const float4
 // select state per image: [0] prefix (score bits decided so far), [1] remaining k, [2] survivors written, [3] done flag
 // ------------------------------------------------------------------------------------------------
 constexpr int kSelBins = 2048;
+constexpr int kRankPerBlock = 64;       // candidates ranked by one 256-thread block of rank_sort_kernel (4 threads each)
 constexpr int kRankDirect = 2048;      // up to this many candidates per image the O(n^2) rank sort beats radix select + compaction
 
 struct SelPass {
@@ -555,26 +556,34 @@ rank_sort_kernel(const cldet_candidate* __restrict__ cand, const uint64_t* __res
     const int64_t limit = (topk > 0) ? min64(n, topk) : n;
     if (blockIdx.x == 0 && threadIdx.x == 0) sorted_counts[j] = (int32_t)min64(limit, out_capacity);
     const uint64_t* k = keys + (int64_t)j * in_capacity;
-    for (int64_t i0 = (int64_t)blockIdx.x * blockDim.x; i0 < n; i0 += (int64_t)gridDim.x * blockDim.x) {   // block-uniform
-        const int64_t i = i0 + threadIdx.x;
+    // a block ranks kRankPerBlock candidates; the four threads of a candidate count a quarter of every tile each
+    __shared__ int rank_s[kRankPerBlock];
+    const int c = threadIdx.x & (kRankPerBlock - 1), q = threadIdx.x / kRankPerBlock;
+    for (int64_t i0 = (int64_t)blockIdx.x * kRankPerBlock; i0 < n; i0 += (int64_t)gridDim.x * kRankPerBlock) {   // block-uniform
+        const int64_t i = i0 + c;
         const uint64_t mine = (i < n) ? k[i] : ~0ull;
-        int64_t rank = 0;
+        if (q == 0) rank_s[c] = 0;
+        int r = 0;
         for (int64_t t0 = 0; t0 < n; t0 += 1024) {
             const int m = (int)min64(1024, n - t0);
             __syncthreads();
             for (int t = threadIdx.x; t < m; t += blockDim.x) tile[t] = k[t0 + t];
             __syncthreads();
-            int r = 0;
+            const int per = (m + 3) >> 2;
+            const int lo = q * per, hi = min(m, lo + per);
 #pragma unroll 8
-            for (int t = 0; t < m; ++t) r += (tile[t] > mine) ? 1 : 0;
-            rank += r;
+            for (int t = lo; t < hi; ++t) r += (tile[t] > mine) ? 1 : 0;
         }
-        if (i < n && rank < limit && rank < out_capacity) {
+        atomicAdd(&rank_s[c], r);
+        __syncthreads();
+        const int rank = rank_s[c];
+        if (q == 0 && i < n && rank < limit && rank < out_capacity) {
             const float4* src = reinterpret_cast<const float4*>(cand + (int64_t)j * in_capacity + i);
             float4* dst = reinterpret_cast<float4*>(sorted + (int64_t)j * out_capacity + rank);
             dst[0] = src[0];
             dst[1] = src[1];
         }
+        __syncthreads();
     }
 }
 
@@ -622,7 +631,7 @@ __device__ __forceinline__ bool suppresses(const float4 a, float area_a, const f
     return __fdiv_rn(inter, (area_a + area_b) - inter) > thr;
 }
 
-__global__ void __launch_bounds__(64)
+__global__ void __launch_bounds__(256)
 nms_mask_kernel(const cldet_candidate* __restrict__ sorted, const int32_t* __restrict__ counts, int64_t capacity,
                 const uint32_t* __restrict__ info, float thr, uint64_t* __restrict__ mask, int64_t mask_stride_img,
                 int col_blocks_alloc) {
@@ -645,8 +654,11 @@ nms_mask_kernel(const cldet_candidate* __restrict__ sorted, const int32_t* __res
     __shared__ float4 cbox[64];
     __shared__ float carea[64];
     __shared__ int clab[64];
+    // 256 threads = 64 rows x 4 column quarters (16 columns each); the first 64 threads stage the column boxes
+    const int rr = threadIdx.x & 63, qq = threadIdx.x >> 6;
+    __shared__ unsigned int part[4][64];
     const int ci = col_blk * 64 + threadIdx.x;
-    if (ci < n) {
+    if (threadIdx.x < 64 && ci < n) {
         const float4* rec = reinterpret_cast<const float4*>(c + ci);
         float4 v = rec[0];
         const int lab = __float_as_int(rec[1].y);
@@ -659,9 +671,9 @@ nms_mask_kernel(const cldet_candidate* __restrict__ sorted, const int32_t* __res
         clab[threadIdx.x] = lab;
     }
     __syncthreads();
-    const int ri = row_blk * 64 + threadIdx.x;
-    if (ri >= n) return;
-    const float4* rrec = reinterpret_cast<const float4*>(c + ri);
+    const int ri = row_blk * 64 + rr;
+    const bool live = ri < n;
+    const float4* rrec = reinterpret_cast<const float4*>(c + (live ? ri : 0));
     float4 me = rrec[0];
     const int my_lab = __float_as_int(rrec[1].y);
     if (mode == 1) {
@@ -670,13 +682,22 @@ nms_mask_kernel(const cldet_candidate* __restrict__ sorted, const int32_t* __res
     }
     const float my_area = (me.z - me.x) * (me.w - me.y);
     const int ncol = min(64, n - col_blk * 64);
-    uint64_t bits = 0;
-    const int start = (row_blk == col_blk) ? threadIdx.x + 1 : 0;
-    for (int t = start; t < ncol; ++t) {
-        if (mode == 2 && clab[t] != my_lab) continue;
-        if (suppresses(me, my_area, cbox[t], carea[t], thr)) bits |= 1ull << t;
+    unsigned int bits = 0;                                            // this quarter's 16 columns
+    const int start = (row_blk == col_blk) ? rr + 1 : 0;
+    const int t_lo = max(start, 16 * qq), t_hi = min(ncol, 16 * qq + 16);
+    if (live) {
+        for (int t = t_lo; t < t_hi; ++t) {
+            if (mode == 2 && clab[t] != my_lab) continue;
+            if (suppresses(me, my_area, cbox[t], carea[t], thr)) bits |= 1u << (t - 16 * qq);
+        }
     }
-    mask[(int64_t)j * mask_stride_img + (int64_t)ri * col_blocks_alloc + col_blk] = bits;
+    part[qq][rr] = bits;
+    __syncthreads();
+    if (qq == 0 && live) {
+        const uint64_t all = (uint64_t)part[0][rr] | ((uint64_t)part[1][rr] << 16) | ((uint64_t)part[2][rr] << 32) |
+                             ((uint64_t)part[3][rr] << 48);
+        mask[(int64_t)j * mask_stride_img + (int64_t)ri * col_blocks_alloc + col_blk] = all;
+    }
 }
 
 // Sequential part of greedy NMS, one block per image, 64 sorted boxes per step:
@@ -1138,13 +1159,14 @@ int cldet_sort_candidates(const cldet_candidate* d_candidates, const uint64_t* d
         select_compact_kernel<<<gc, 256, 0, s>>>(d_candidates, d_keys, d_counts, capacity, state, sel_cand, sel_keys, max_count);
         CLDET_LAUNCH_CHECK();
         // survivors are ~topk (plus exact score ties): size the grid for 2*topk, the kernel strides if there are more
-        dim3 gr((unsigned)std::max<int64_t>(1, std::min<int64_t>((max_count + 255) / 256, (2 * (int64_t)topk + 255) / 256)),
+        dim3 gr((unsigned)std::max<int64_t>(1, std::min<int64_t>((max_count + kRankPerBlock - 1) / kRankPerBlock,
+                                                                   (2 * (int64_t)topk + kRankPerBlock - 1) / kRankPerBlock)),
                 (unsigned)num_images);
         rank_sort_kernel<<<gr, 256, 0, s>>>(sel_cand, sel_keys, state, d_counts, max_count, topk, d_sorted, sorted_capacity,
                                              d_sorted_counts, d_candidates, d_keys, capacity);
         CLDET_LAUNCH_CHECK();
     } else {
-        dim3 gc((unsigned)((max_count + 255) / 256), (unsigned)num_images);
+        dim3 gc((unsigned)std::min<int64_t>((max_count + kRankPerBlock - 1) / kRankPerBlock, 65535 * 16), (unsigned)num_images);
         rank_sort_kernel<<<gc, 256, 0, s>>>(d_candidates, d_keys, nullptr, d_counts, capacity, 0, d_sorted, sorted_capacity,
                                              d_sorted_counts);
         CLDET_LAUNCH_CHECK();
@@ -1176,7 +1198,7 @@ int cldet_nms_sorted(const cldet_candidate* d_sorted, const int32_t* d_sorted_co
     const long long tiles = (long long)w.col_blocks * (w.col_blocks + 1) / 2;          // upper-triangular tiles per image
     if (tiles > 2147483647ll) return CLDET_ERR_UNSUPPORTED;
     dim3 grid((unsigned)tiles, (unsigned)num_images);
-    nms_mask_kernel<<<grid, 64, 0, s>>>(d_sorted, d_sorted_counts, capacity, w.info, iou_thresh, w.mask, w.mask_stride_img,
+    nms_mask_kernel<<<grid, 256, 0, s>>>(d_sorted, d_sorted_counts, capacity, w.info, iou_thresh, w.mask, w.mask_stride_img,
                                         w.col_blocks);
     CLDET_LAUNCH_CHECK();
     if (max_count <= kSmemResolveMax) {
@@ -1264,7 +1286,7 @@ int cldet_batched_nms(const float* d_boxes, const float* d_scores, const int64_t
     pack_boxes_kernel<<<blocks, 256, 0, s>>>(reinterpret_cast<const float4*>(d_boxes), d_scores, d_idxs, num_boxes, packed, keys,
                                              cnts);
     CLDET_LAUNCH_CHECK();
-    dim3 g(blocks, 1);
+    dim3 g((unsigned)((num_boxes + kRankPerBlock - 1) / kRankPerBlock), 1);
     rank_sort_kernel<<<g, 256, 0, s>>>(packed, keys, nullptr, cnts, num_boxes, 0, sorted, num_boxes, cnts + 1);
     CLDET_LAUNCH_CHECK();
     int rc = cldet_nms_sorted(sorted, cnts + 1, 1, num_boxes, num_boxes, iou_thresh, d_idxs ? mode : 1, vanilla_numel_limit,
