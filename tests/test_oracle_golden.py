@@ -200,3 +200,31 @@ def test_torch_eager_decode_and_predict_match_reference():
         s, l, b = E.predict(torch.from_numpy(p['logits']), torch.from_numpy(p['reg']), anchors, h, w)
         assert np.array_equal(s.numpy(), p['scores']) and np.array_equal(l.numpy(), p['labels'])
         assert np.array_equal(b.numpy(), p['boxes'])
+
+
+@pytest.mark.parametrize('seed,h,w,C,N,G', [(0, 128, 160, 8, 3, 6), (1, 96, 96, 20, 2, 12), (2, 33, 70, 3, 2, 4)])
+def test_two_oracles_agree_on_random_inputs(seed, h, w, C, N, G):
+    """The numpy oracle (analytic gradients) and the torch-eager restatement (autograd) are independent statements of the same
+    reference code: on seeded random inputs beyond the fixtures they must agree on assignments-derived losses and on every
+    gradient element within the north_star tolerance."""
+    import torch
+    from oracle import torch_eager as E
+    from tests.helpers import synth_gt, synth_head
+    rng = np.random.default_rng(seed)
+    anchors = O.anchors_for_image(h, w)
+    A = anchors.shape[1]
+    _, probs, reg = synth_head(rng, N, A, C, mu=-3.0)
+    ann = synth_gt(rng, N, G, h, w, C, empty=(N - 1,))
+    wb, wf = rng.uniform(0.5, 1.5, N), rng.uniform(0.5, 1.5, N)
+    ref = O.focal_loss(probs, reg, anchors, ann, 0, O.OracleParams(), w_bg=wb, w_fg=wf, w_reg=0.7)
+    cls_t = torch.from_numpy(probs).requires_grad_(True)
+    reg_t = torch.from_numpy(reg).requires_grad_(True)
+    bg, fg, rl = E.focal_loss(cls_t, reg_t, torch.from_numpy(anchors), torch.from_numpy(ann))
+    ((bg * torch.from_numpy(wb).float()).sum() + (fg * torch.from_numpy(wf).float()).sum() + 0.7 * rl.sum()).backward()
+    assert rel_err(bg.detach().numpy(), ref['bg'], 1e-30) < 1e-5 and rel_err(fg.detach().numpy(), ref['fg'], 1e-30) < 1e-5
+    assert rel_err(rl.detach().numpy(), ref['reg_loss'], 1e-30) < 1e-5
+    gc = cls_t.grad.numpy()
+    assert np.array_equal(gc == 0, ref['grad_cls'] == 0)
+    assert np.max(np.abs(gc - ref['grad_cls']) / (np.abs(ref['grad_cls']) + 1e-12 * np.abs(ref['grad_cls']).max())) < 1e-5
+    gr = np.zeros_like(ref['grad_reg']) if reg_t.grad is None else reg_t.grad.numpy()
+    assert float((np.abs(gr - ref['grad_reg']) - 1e-5 * np.abs(ref['grad_reg'])).max()) <= 1e-5 * float(np.abs(ref['grad_reg']).max())
