@@ -16,6 +16,14 @@ import cl_object_detection_b200 as cld  # noqa: E402
 from cl_object_detection_b200 import _lib  # noqa: E402
 
 
+def ncu_traffic(kernel):
+    """dram bytes per launch from the committed ncu --set full capture (profiles/traffic.json; trained-like logits), or None."""
+    try:
+        return json.load(open(os.path.join(ROOT, 'profiles', 'traffic.json'))).get(kernel)
+    except Exception:
+        return None
+
+
 def measure(args, dev=None, return_inputs=False):
     """One JSON-able dict for the configuration in `args` (steps, warmup, images, mu, topk, classes)."""
     if dev is None:
@@ -91,7 +99,7 @@ def measure(args, dev=None, return_inputs=False):
             'stage_ms': {'decode_filter': stage[0], 'select_sort': stage[1], 'nms': stage[2], 'gather': stage[3]},
             'roofline': {'bound': 'hbm', 'kernel': 'decode_filter_kernel<4>', 'achieved': filt_bytes / (stage[0] * 1e-3) / 1e9,
                          'peak': peak, 'unit': 'GB/s', 'frac': filt_bytes / (stage[0] * 1e-3) / 1e9 / peak,
-                         'algorithmic_bytes_per_launch': filt_bytes}}
+                         'algorithmic_bytes_per_launch': filt_bytes, 'traffic': ncu_traffic('decode_filter_kernel')}}
     if getattr(args, 'head', False):
         line['conv_layout'] = measure_head(args, dev, logits, reg, anchors, h, w)
     if return_inputs:
