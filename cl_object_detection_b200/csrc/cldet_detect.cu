@@ -636,7 +636,8 @@ nms_mask_kernel(const cldet_candidate* __restrict__ sorted, const int32_t* __res
                 const uint32_t* __restrict__ info, float thr, uint64_t* __restrict__ mask, int64_t mask_stride_img,
                 int col_blocks_alloc) {
     const int j = blockIdx.y;
-    const int n = (int)min64(counts[j], capacity);
+    // never past what the mask workspace was sized for (max_count), even if the caller's counts are larger
+    const int n = (int)min64(min64(counts[j], capacity), (int64_t)col_blocks_alloc * 64);
     // blockIdx.x enumerates the UPPER-TRIANGULAR 64x64 tiles row by row: tile t of row r starts at r*cb - r(r-1)/2
     // (a square grid launched twice as many blocks, half of which only returned: this kernel is block-scheduling bound)
     const int cb = col_blocks_alloc;
@@ -715,7 +716,8 @@ nms_resolve_kernel(const int32_t* __restrict__ counts, int64_t capacity, const u
     __shared__ int kept_total;
     __shared__ unsigned long long acc[16];
     const int j = blockIdx.x;
-    const int n = (int)min64(counts[j], capacity);
+    // never past what the mask workspace was sized for (max_count), even if the caller's counts are larger
+    const int n = (int)min64(min64(counts[j], capacity), (int64_t)col_blocks_alloc * 64);
     const int col_blocks = (n + 63) / 64;
     uint64_t* remv = remv_ws + (int64_t)j * col_blocks_alloc;
     const uint64_t* m = mask + (int64_t)j * mask_stride_img;
@@ -790,7 +792,8 @@ nms_resolve_smem_kernel(const int32_t* __restrict__ counts, int64_t capacity, co
                         int32_t* __restrict__ keep_counts) {
     extern __shared__ uint64_t sm_mask[];                                // [64*cb][cb], rows >= n zero
     const int j = blockIdx.x;
-    const int n = (int)min64(counts[j], capacity);
+    // never past what the mask workspace was sized for (max_count), even if the caller's counts are larger
+    const int n = (int)min64(min64(counts[j], capacity), (int64_t)col_blocks_alloc * 64);
     const int cb = (n + 63) / 64;
     const uint64_t* m = mask + (int64_t)j * mask_stride_img;
     const int total = 64 * cb * cb;
