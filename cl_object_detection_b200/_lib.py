@@ -59,7 +59,7 @@ SIGNATURES = {
     'cldet_peer_close': (_I, [_P]),
     'cldet_peer_free': (_I, [_P]),
     'cldet_enable_peer_access': (_I, [_I]),
-    'cldet_peer_wait': (_I, [_P, _I, _I, _I, _P, _P]),
+    'cldet_peer_wait': (_I, [_P, _P, _I, _I, _I, ctypes.c_uint32, _I, _P, _P, _P]),
     'cldet_focal_loss_profile_events': (_I, [_P, _P, _P]),
     'cldet_focal_loss_from_assignment': (_I, [_P, _P, _P, _P, _I, _L, _I, _I, ctypes.POINTER(LossParams), _P, _P, _P, _P,
                                               _P, _P, _P, _P, _P, _P, _P, _Z, _P]),

@@ -270,28 +270,51 @@ int cldet_focal_loss(const float* d_cls, const float* d_reg, const float* d_anch
                                     d_nvalid, d_bg_mask, d_status, d_workspace, ws_bytes, nullptr, stream);
 }
 
-// Consumer side of the fused all-gather: spin (bounded) until every source rank has signalled `expected` arrivals in this
-// parity's counters, then clear them for the next use of the parity.  One tiny block; later kernels on the stream see the
-// complete gather buffer.
-__global__ void peer_wait_kernel(unsigned int* flags, int world, int parity, unsigned int expected, int32_t* status) {
+// Consumer side of the fused all-gather.  Thread r < world waits (acquire, system scope) until source rank r's arrival
+// counter for this parity has reached `target` -- the counters only ever grow, `target` = N x (number of uses of the parity
+// so far), compared wrap-safely -- then the whole block copies this parity's [world][4][N] terms into the caller's PRIVATE
+// [4][world*N] tensor (global image order), so nothing the caller keeps aliases memory that peers overwrite two steps later.
+// The wait is bounded by `timeout_ns` of %globaltimer: a peer that never arrives poisons ITS rows of the output with NaN and
+// raises *status (which may live in mapped host memory, so the host sees it without a synchronisation) instead of hanging the
+// GPU; because nothing is ever reset, a late arrival cannot desynchronise the following steps.
+__global__ void __launch_bounds__(256)
+peer_wait_copy_kernel(const unsigned int* flags, int world, int parity, unsigned int target, unsigned long long timeout_ns,
+                      const float* terms, int n, float* out, int32_t* status) {
+    __shared__ int bad[64];
     const int r = threadIdx.x;
-    bool ok = true;
     if (r < world) {
-        volatile unsigned int* f = flags + parity * world + r;
-        long long spins = 0;
-        while (*f < expected) {
-            __nanosleep(64);
-            if (++spins > 40000000ll) {       // ~ a few seconds: a peer died or the call sequence is wrong -- do not hang the GPU
-                ok = false;
+        const unsigned int* f = flags + parity * world + r;
+        bool ok = false;
+        unsigned long long t0 = 0;
+        for (unsigned int spins = 0;; ++spins) {
+            unsigned int v;
+            asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
+            if ((int)(v - target) >= 0) {
+                ok = true;
                 break;
             }
+            __nanosleep(spins < 64 ? 32 : 256);
+            if ((spins & 255u) == 255u) {
+                unsigned long long now;
+                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+                if (t0 == 0) t0 = now;
+                else if (now - t0 > timeout_ns) break;
+            }
+        }
+        bad[r] = ok ? 0 : 1;
+        if (!ok && status) {
+            *status = 2;
+            __threadfence_system();
         }
     }
-    __threadfence_system();
     __syncthreads();
-    if (r < world) {
-        if (ok) flags[parity * world + r] = 0;
-        else if (status) *status = 2;
+    if (!out) return;
+    const int total = world * 4 * n;
+    for (int i = threadIdx.x; i < total; i += blockDim.x) {
+        const int src = i / (4 * n), rem = i - src * 4 * n;
+        const int k = rem / n, j = rem - k * n;
+        // written by peers into this GPU's L2: read past L1 (a line of the previous use of this parity may still sit there)
+        out[(size_t)k * world * n + (size_t)src * n + j] = bad[src] ? __int_as_float(0x7fc00000) : __ldcg(terms + i);
     }
 }
 
@@ -351,11 +374,15 @@ int cldet_enable_peer_access(int peer_device) {
     return CLDET_OK;
 }
 
-int cldet_peer_wait(void* d_flags_local, int world, int parity, int expected_arrivals, int32_t* d_status, void* stream) {
-    if (!d_flags_local || world < 1 || world > 64 || (parity != 0 && parity != 1) || expected_arrivals < 0)
+int cldet_peer_wait(const void* d_flags_local, const float* d_terms_local, int world, int num_images, int parity,
+                    uint32_t target_arrivals, int timeout_ms, float* d_out, int32_t* d_status, void* stream) {
+    if (!d_flags_local || world < 1 || world > 64 || (parity != 0 && parity != 1) || num_images <= 0 || timeout_ms <= 0)
         return CLDET_ERR_INVALID_ARGUMENT;
-    peer_wait_kernel<<<1, 64, 0, (cudaStream_t)stream>>>(reinterpret_cast<unsigned int*>(d_flags_local), world, parity,
-                                                        (unsigned int)expected_arrivals, d_status);
+    if (d_out && !d_terms_local) return CLDET_ERR_INVALID_ARGUMENT;
+    const float* terms = d_terms_local ? d_terms_local + (size_t)parity * world * 4 * num_images : nullptr;
+    peer_wait_copy_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const unsigned int*>(d_flags_local), world, parity,
+                                                              target_arrivals, (unsigned long long)timeout_ms * 1000000ull, terms,
+                                                              num_images, d_out, d_status);
     CLDET_LAUNCH_CHECK();
     return CLDET_OK;
 }

@@ -23,22 +23,22 @@ def shard_slice(n_global, world, rank):
     return slice(start, start + sizes[rank])
 
 
-class _DevicePointer:
-    """Lets torch alias raw device memory owned by libcldet (CUDA array interface)."""
-
-    def __init__(self, ptr, numel):
-        self.__cuda_array_interface__ = {'shape': (numel,), 'typestr': '<f4', 'data': (ptr, False), 'version': 2}
-
-
 class PeerGather:
     """Per-process state of the FUSED all-gather (include/cldet.h, cldet_focal_loss_sharded): a gather buffer
     float[2][world][4][N] plus arrival counters uint32[2][world], allocated by libcldet (cudaMalloc), exported with CUDA IPC
     and opened by every other rank of the group with ITS device current, so that kernels there can store into it over NVLink.
     The loss kernel's last block per image writes the image's four terms straight into every rank's buffer; `wait()` enqueues
-    the tiny kernel that blocks the stream until all ranks have delivered."""
+    the one-block kernel that blocks the stream until all ranks have delivered and copies the terms into a private tensor.
 
-    def __init__(self, n_local, device, group=None):
+    Protocol: the arrival counters only ever grow; the u-th use of a parity waits for u*N arrivals per source rank, so a late
+    arrival is never mistaken for the next step's.  The wait is bounded (`timeout_ms`, default $CLDET_PEER_TIMEOUT_MS or
+    20 000): on a timeout the kernel fills the missing rank's rows with NaN and raises a status word that lives in mapped
+    pinned HOST memory; the next `wait()`/`check()` on this rank reads it without a device synchronisation and raises
+    CldetError -- a straggler can make a step fail loudly, never silently wrong."""
+
+    def __init__(self, n_local, device, group=None, timeout_ms=None):
         import ctypes
+        import os
 
         from . import _lib
         lib = _lib.load()
@@ -48,45 +48,77 @@ class PeerGather:
         self.rank = dist.get_rank(group)
         self.n = int(n_local)
         self.device = device
+        self.timeout_ms = int(timeout_ms if timeout_ms is not None else os.environ.get('CLDET_PEER_TIMEOUT_MS', '20000'))
         n_terms = 2 * self.world * 4 * self.n
         self._flag_off = n_terms + ((-n_terms) % 64)
         numel = self._flag_off + 2 * self.world + 64
+        self._own = 0
+        self._opened = []
+        self.uses = [0, 0]          # how many times each parity has been used (the wait target is uses * N arrivals)
+        self.parity = 0
+        # ---- local, fallible part: no collective in here ----
+        err = None
+        hbuf = ctypes.create_string_buffer(64)
+        try:
+            with torch.cuda.device(device):
+                ptr = ctypes.c_void_p()
+                _lib.check(lib.cldet_peer_alloc(4 * numel, ctypes.byref(ptr), hbuf))
+                self._own = ptr.value
+        except Exception as e:  # noqa: BLE001
+            err = e
+        # ---- collectives: entered by EVERY rank exactly once each, whatever happened locally ----
+        handles = [None] * self.world
+        dist.all_gather_object(handles, hbuf.raw if err is None else None, group=group)
+        base_ptrs = []
+        if err is None and all(h is not None for h in handles):
+            try:
+                with torch.cuda.device(device):
+                    for r in range(self.world):
+                        if r == self.rank:
+                            base_ptrs.append(self._own)
+                            continue
+                        q = ctypes.c_void_p()
+                        _lib.check(lib.cldet_peer_open(handles[r], ctypes.byref(q)))
+                        self._opened.append(q.value)
+                        base_ptrs.append(q.value)
+            except Exception as e:  # noqa: BLE001
+                err = e
+        elif err is None:
+            err = RuntimeError('a peer rank could not allocate its exchange buffer')
+        ok = torch.tensor([1 if err is None else 0], device=device)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
+        torch.cuda.synchronize(device)
+        dist.barrier(group=group)                       # every rank has zeroed, exported and mapped its buffers (or given up)
+        if int(ok.item()) == 0:
+            self.close()
+            raise _lib.CldetError('peer exchange unavailable on at least one rank%s' % ('' if err is None else ': %r' % (err,)))
         with torch.cuda.device(device):
-            ptr = ctypes.c_void_p()
-            hbuf = ctypes.create_string_buffer(64)
-            _lib.check(lib.cldet_peer_alloc(4 * numel, ctypes.byref(ptr), hbuf))
-            self._own = ptr.value
-            handles = [None] * self.world
-            dist.all_gather_object(handles, hbuf.raw, group=group)
-            self._opened = []
-            base_ptrs = []
-            for r in range(self.world):
-                if r == self.rank:
-                    base_ptrs.append(self._own)
-                    continue
-                q = ctypes.c_void_p()
-                _lib.check(lib.cldet_peer_open(handles[r], ctypes.byref(q)))
-                self._opened.append(q.value)
-                base_ptrs.append(q.value)
-            self.buf = torch.as_tensor(_DevicePointer(self._own, numel), device=device)      # aliases libcldet's memory
             self.term_ptrs = torch.tensor(base_ptrs, dtype=torch.int64, device=device)
             self.flag_ptrs = torch.tensor([p + 4 * self._flag_off for p in base_ptrs], dtype=torch.int64, device=device)
-            self.status = torch.zeros(1, dtype=torch.int32, device=device)
-        self.parity = 0
-        torch.cuda.synchronize(device)
-        dist.barrier(group=group)                       # every rank has zeroed, exported and mapped its buffers
+        # status word in pinned host memory (UVA: the same address is valid on the device): readable without a sync
+        self.status = torch.zeros(1, dtype=torch.int32).pin_memory()
 
     def exchange(self):
         return self._lib.PeerExchange(self.term_ptrs.data_ptr(), self.flag_ptrs.data_ptr(), self.rank, self.world, self.parity)
 
-    def wait(self, stream):
-        """Block `stream` until this parity's gather is complete, then advance the parity.  Returns the [world,4,N] view."""
-        flags_ptr = self._own + 4 * self._flag_off
-        self._lib.check(self._lib.load().cldet_peer_wait(flags_ptr, self.world, self.parity, self.n, self.status.data_ptr(), stream))
-        block = self.world * 4 * self.n
-        view = self.buf[self.parity * block:(self.parity + 1) * block].view(self.world, 4, self.n)
+    def check(self):
+        """Raise if an earlier wait on this rank timed out (reads mapped host memory: no device synchronisation)."""
+        if int(self.status[0]) != 0:
+            raise self._lib.CldetError('peer exchange: a rank did not deliver its loss terms within %d ms (its rows of that step '
+                                       'were filled with NaN); the job is out of step or a peer died' % self.timeout_ms)
+
+    def wait(self, stream, out=None):
+        """Block `stream` until this parity's gather is complete, copy it into a PRIVATE [4, world*N] tensor (rows bg, fg, reg,
+        enhance in global image order) and advance the parity."""
+        self.check()
+        if out is None:
+            out = torch.empty((4, self.world * self.n), dtype=torch.float32, device=self.device)
+        self.uses[self.parity] += 1
+        target = (self.uses[self.parity] * self.n) & 0xFFFFFFFF
+        self._lib.check(self._lib.load().cldet_peer_wait(self._own + 4 * self._flag_off, self._own, self.world, self.n, self.parity,
+                                                        target, self.timeout_ms, out.data_ptr(), self.status.data_ptr(), stream))
         self.parity ^= 1
-        return view
+        return out
 
     def close(self):
         """Unmap the peers' buffers and free this rank's (call on every rank, after a barrier)."""
@@ -140,9 +172,14 @@ class ShardedFocalLoss(nn.Module):
 
     The gradients that flow back are d(global loss)/d(local head outputs); SUM parameter gradients over ranks to get
     the single-process gradient (with DDP's averaging, scale the loss by world_size).
+
+    shard_sizes: how a rank learns the other ranks' image counts WITHOUT a per-step collective and host sync:
+      'equal'  (default) every rank holds as many images as this one (DistributedSampler semantics) -- no communication;
+      a list   the per-rank image counts, fixed;
+      'gather' all-gather the counts on every call (one small collective + a host sync per step; ragged, changing shards).
     """
 
-    def __init__(self, local_loss=None, group=None, use_peer_memory=True):
+    def __init__(self, local_loss=None, group=None, use_peer_memory=True, shard_sizes='equal'):
         super().__init__()
         if local_loss is None:
             from .losses import FocalLoss
@@ -150,7 +187,32 @@ class ShardedFocalLoss(nn.Module):
         self.local_loss = local_loss
         self.group = group
         self.use_peer_memory = use_peer_memory
+        if not (shard_sizes in ('equal', 'gather') or isinstance(shard_sizes, (list, tuple))):
+            raise ValueError("shard_sizes must be 'equal', 'gather' or a list of per-rank image counts")
+        self.shard_sizes = shard_sizes
         self._peer = {}          # n_local -> PeerGather, or False when the mapping could not be set up
+        self._weights = {}       # (n_local, n_global, device index) -> [4, n_local] upstream weights baked by the kernel
+
+    def _sizes(self, n_local, world, device):
+        if isinstance(self.shard_sizes, (list, tuple)):
+            if len(self.shard_sizes) != world:
+                raise ValueError('shard_sizes has %d entries for %d ranks' % (len(self.shard_sizes), world))
+            return [int(x) for x in self.shard_sizes]
+        if self.shard_sizes == 'equal' or world == 1:
+            return [n_local] * world
+        t = torch.tensor([n_local], dtype=torch.int64, device=device)
+        all_n = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(all_n, t, group=self.group)
+        return [int(x.item()) for x in all_n]
+
+    def _hint(self, n_local, n_global, device):
+        key = (n_local, n_global, device.index)
+        w = self._weights.get(key)
+        if w is None:
+            w = torch.full((4, n_local), 1.0 / n_global, dtype=torch.float32)
+            w[3] = 1.0
+            w = self._weights[key] = w.to(device)
+        return w
 
     def _peer_for(self, n_local, sizes, device):
         """Fused all-gather over peer memory needs equal shards, CUDA tensors and the built-in FocalLoss."""
@@ -161,12 +223,8 @@ class ShardedFocalLoss(nn.Module):
             return None
         if n_local not in self._peer:
             try:
-                self._peer[n_local] = PeerGather(n_local, device, self.group)
+                self._peer[n_local] = PeerGather(n_local, device, self.group)     # collective; agrees on ok / not ok itself
             except Exception:     # no IPC between the ranks (different nodes / containers): use the NCCL all-gather
-                self._peer[n_local] = False
-            ok = torch.tensor([1 if self._peer[n_local] else 0], device=device)
-            dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=self.group)
-            if int(ok.item()) == 0:
                 self._peer[n_local] = False
         return self._peer[n_local] or None
 
@@ -174,21 +232,15 @@ class ShardedFocalLoss(nn.Module):
         world = dist.get_world_size(self.group) if dist.is_initialized() else 1
         rank = dist.get_rank(self.group) if dist.is_initialized() else 0
         n_local = classifications.shape[0]
-        if world > 1:
-            t = torch.tensor([n_local], dtype=torch.int64, device=classifications.device)
-            all_n = [torch.zeros_like(t) for _ in range(world)]
-            dist.all_gather(all_n, t, group=self.group)
-            sizes = [int(x.item()) for x in all_n]
-        else:
-            sizes = [n_local]
+        sizes = self._sizes(n_local, world, classifications.device)
+        if sizes[rank] != n_local:
+            raise ValueError('this rank holds %d images but shard_sizes says %d' % (n_local, sizes[rank]))
         n_global = sum(sizes)
         peer = self._peer_for(n_local, sizes, classifications.device) if world > 1 else None
         if peer is not None:
             # fused path: the loss kernel scatters the per-image terms to every rank; the result already holds GLOBAL rows
-            w = torch.full((4, n_local), 1.0 / n_global, dtype=torch.float32, device=classifications.device)
-            w[3] = 1.0
             old = self.local_loss.upstream_hint
-            self.local_loss.upstream_hint = w
+            self.local_loss.upstream_hint = self._hint(n_local, n_global, classifications.device)
             try:
                 out = self.local_loss(classifications, regressions, anchors, annotations, cur_state, params, progress, peer=peer)
             finally:
@@ -196,9 +248,7 @@ class ShardedFocalLoss(nn.Module):
             return out       # rows are already global: FocalLoss formed reg_loss / enhance over all N images
         if hasattr(self.local_loss, 'upstream_hint') and isinstance(self.local_loss.upstream_hint, str):
             # the caller's mean runs over the GLOBAL batch: bake 1/N_global into the fused gradients
-            w = torch.full((4, n_local), 1.0 / n_global, dtype=torch.float32, device=classifications.device)
-            w[3] = 1.0
-            self.local_loss.upstream_hint = w
+            self.local_loss.upstream_hint = self._hint(n_local, n_global, classifications.device)
             try:
                 out = self.local_loss(classifications, regressions, anchors, annotations, cur_state, params, progress)
             finally:
@@ -221,3 +271,10 @@ class ShardedFocalLoss(nn.Module):
         if 'bg_masks' in out:
             result['bg_masks'] = out['bg_masks']
         return result
+
+    def close(self):
+        """Release the peer-exchange buffers (collective-free; call on every rank after a barrier)."""
+        for p in self._peer.values():
+            if p:
+                p.close()
+        self._peer = {}

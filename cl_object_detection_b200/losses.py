@@ -159,8 +159,9 @@ class _FocalLossFn(torch.autograd.Function):
                         _lib.ptr(weights), _lib.ptr(baked), _lib.ptr(gcls), _lib.ptr(greg), losses.data_ptr(), meta.data_ptr(),
                         _lib.ptr(iou_max), npos.data_ptr(), nvalid.data_ptr(), _lib.ptr(bg_mask), _lib.ptr(status),
                         ws.data_ptr(), ws_bytes, ex, stream))
-                    gathered = peer.wait(stream)                                   # [world, 4, n]
-                    losses = gathered.permute(1, 0, 2).reshape(4, peer.world * n)   # global image order, private copy
+                    # [4, world*n], global image order: a PRIVATE tensor written by the wait kernel (never a view of the
+                    # exchange buffer, which peers overwrite two steps later)
+                    losses = peer.wait(stream)
             except Exception:
                 _drop_workspaces()      # a failed call may leave the scratch header dirty
                 raise

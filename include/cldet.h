@@ -139,10 +139,11 @@ int cldet_focal_loss(const float* d_cls, const float* d_reg, const float* d_anch
 /* ---- image-sharded runs: fused loss + all-gather over NVLink peer memory ----
  * Every rank owns a gather buffer float[2][world][4][N] and arrival counters uint32[2][world] (both zero-initialised) that
  * all ranks have mapped (CUDA IPC / symmetric memory).  With a peer exchange, the loss kernel's last block per image stores
- * that image's four terms into slot [parity][rank] of EVERY rank's buffer (peer stores) and signals one arrival per
- * destination -- there is no separate collective launch.  cldet_peer_wait then blocks the stream until all `world` source
- * ranks have delivered `expected_arrivals` (= N) terms for this parity and clears the counters; alternate parity 0/1 between
- * consecutive steps.  All ranks must use the same N. */
+ * that image's four terms into slot [parity][rank] of EVERY rank's buffer (one lane per destination: peer stores followed by
+ * a release-ordered system-scope arrival) -- there is no separate collective launch.  The arrival counters ONLY GROW: the
+ * u-th use of a parity (u = 1, 2, ...) is complete when every source rank's counter has reached u * N.  cldet_peer_wait
+ * blocks the stream until then and copies the gathered terms out; alternate parity 0/1 between consecutive steps.
+ * All ranks must use the same N. */
 typedef struct cldet_peer_exchange {
     void* d_peer_terms;   /* device array of `world` float*  : rank p's gather buffer, as mapped in THIS process */
     void* d_peer_flags;   /* device array of `world` uint32* : rank p's arrival counters */
@@ -164,8 +165,13 @@ int cldet_peer_close(void* d_ptr);
 int cldet_peer_free(void* d_ptr);
 /* Let kernels of the CURRENT device dereference memory of `peer_device` (cudaDeviceEnablePeerAccess; already-enabled is ok). */
 int cldet_enable_peer_access(int peer_device);
-/* d_status (may be NULL) is set to 2 if a peer never arrives (bounded spin, the GPU is not left hanging). */
-int cldet_peer_wait(void* d_flags_local, int world, int parity, int expected_arrivals, int32_t* d_status, void* stream);
+/* Wait (bounded by timeout_ms) until all `world` source ranks have signalled `target_arrivals` (wrap-safe compare) on
+ * this parity's counters of THIS rank (d_flags_local), then copy this parity's terms d_terms_local[parity][world][4][N] into
+ * d_out [4][world*N] (row k, image r*N + j: the caller's private copy in global image order; d_out may be NULL = wait only).
+ * A source rank that does not arrive in time gets its rows of d_out filled with NaN and *d_status (may be NULL; may point to
+ * mapped pinned host memory) is set to 2; the counters are never reset, so later steps stay in sequence regardless. */
+int cldet_peer_wait(const void* d_flags_local, const float* d_terms_local, int world, int num_images, int parity,
+                    uint32_t target_arrivals, int timeout_ms, float* d_out, int32_t* d_status, void* stream);
 
 /* Profiling hook (per host thread, one-shot): the next cldet_focal_loss call of THIS thread records the given
  * cudaEvent_t handles before the assign kernel, between the two kernels and after the loss kernel, on its stream.

@@ -31,3 +31,18 @@ def pytest_collection_modifyitems(config, items):
 @pytest.fixture(scope='session')
 def golden_dir():
     return GOLDEN
+
+
+def pytest_sessionfinish(session, exitstatus):
+    """Tolerance book-keeping: tests record the worst error they observed (tests.helpers.OBSERVED); on a GPU box the record is
+    written to gpurun_out/test_metrics.json so that relaxed bars can be tightened against measured numbers."""
+    try:
+        from tests.helpers import OBSERVED
+        if OBSERVED:
+            import json
+            out = os.path.join(ROOT, 'gpurun_out')
+            os.makedirs(out, exist_ok=True)
+            with open(os.path.join(out, 'test_metrics.json'), 'w') as f:
+                json.dump(OBSERVED, f, indent=1, sort_keys=True)
+    except Exception:
+        pass

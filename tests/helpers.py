@@ -59,3 +59,7 @@ def synth_head(rng, n_img, num_anchors, num_classes, mu=-4.0, sigma=2.0, reg_sig
     probs = (1.0 / (1.0 + np.exp(-logits.astype(np.float64)))).astype(np.float32)
     reg = rng.normal(0, reg_sigma, (n_img, num_anchors, 4)).astype(np.float32)
     return logits, probs, reg
+
+
+# worst errors observed by the tolerance helpers during a session (written out by conftest.pytest_sessionfinish)
+OBSERVED = {}

@@ -31,7 +31,7 @@ def caller_reduction(out, clip):
     return bg.mean() + fg_term + out['reg_loss'].mean()
 
 
-def _worker(rank, world, port, n_global, tmp):
+def _worker(rank, world, port, n_global, tmp, mode):
     os.environ['MASTER_ADDR'] = '127.0.0.1'
     os.environ['MASTER_PORT'] = str(port)
     dist.init_process_group('gloo', rank=rank, world_size=world)
@@ -49,7 +49,9 @@ def _worker(rank, world, port, n_global, tmp):
         sl = shard_slice(n_global, world, rank)
         c = cls[sl].clone().requires_grad_(True)
         r = reg[sl].clone().requires_grad_(True)
-        out = ShardedFocalLoss(StandInLoss())(c, r, None, None, 0, None)
+        sizes = {'equal': 'equal', 'gather': 'gather', 'list': shard_sizes(n_global, world)}[mode]
+        sharded = ShardedFocalLoss(StandInLoss(), shard_sizes=sizes)
+        out = sharded(c, r, None, None, 0, None)
         assert out['cls_loss'][0].shape[0] == n_global
         loss = caller_reduction(out, clip)
         loss.backward()
@@ -65,10 +67,12 @@ def _worker(rank, world, port, n_global, tmp):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize('n_global', [4, 5])
-def test_sharded_loss_world2_gloo(tmp_path, n_global):
-    port = 29500 + (os.getpid() % 2000) + n_global
-    mp.spawn(_worker, args=(2, port, n_global, str(tmp_path)), nprocs=2, join=True)
+@pytest.mark.parametrize('n_global,mode', [(4, 'equal'), (5, 'list'), (5, 'gather')])
+def test_sharded_loss_world2_gloo(tmp_path, n_global, mode):
+    # 'equal' (the default) assumes DistributedSampler-style equal shards and needs no per-step collective; ragged shards
+    # are given as a list or gathered on every call
+    port = 29500 + (os.getpid() % 2000) + n_global + (7 if mode == 'gather' else 0)
+    mp.spawn(_worker, args=(2, port, n_global, str(tmp_path), mode), nprocs=2, join=True)
     assert os.path.exists(tmp_path / 'ok0') and os.path.exists(tmp_path / 'ok1')
 
 
@@ -85,3 +89,12 @@ def test_single_process_passthrough():
     a = ShardedFocalLoss(StandInLoss())(cls, reg, None, None, 0, None)
     b = StandInLoss()(cls, reg, None, None, 0, None)
     assert torch.allclose(a['cls_loss'][0], b['cls_loss'][0]) and torch.allclose(a['reg_loss'], b['reg_loss'])
+
+
+def test_shard_sizes_argument_is_checked():
+    with pytest.raises(ValueError):
+        ShardedFocalLoss(StandInLoss(), shard_sizes='sometimes')
+    cls = torch.rand(3, 5, 2)
+    reg = torch.randn(3, 5, 4)
+    with pytest.raises(ValueError):          # this rank holds 3 images, the list says 2
+        ShardedFocalLoss(StandInLoss(), shard_sizes=[2])(cls, reg, None, None, 0, None)

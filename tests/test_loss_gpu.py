@@ -9,7 +9,7 @@ import torch
 
 import cl_object_detection_b200 as cld
 from oracle import head_oracle as O
-from tests.helpers import FOCAL_CASES, golden_params, load, synth_gt, synth_head
+from tests.helpers import FOCAL_CASES, OBSERVED, golden_params, load, synth_gt, synth_head
 
 pytestmark = pytest.mark.gpu
 DEV = 'cuda:0'
@@ -32,6 +32,9 @@ def check_grad_cls(got, ref):
     assert err < 1e-5, err
 
 
+GRAD_REG_ABS = 1e-5     # absolute allowance in units of max|grad| (see check_grad_reg)
+
+
 def check_grad_reg(got, ref):
     """Smooth-L1's quadratic zone has gradient 9*(t - r)*w: the subtraction cancels, so an ulp-level difference in the
     target t (log / divide chain, |t| up to ~8) appears as an ABSOLUTE error of ~9*ulp(t)*w ~ 5e-6*w on entries that can
@@ -40,7 +43,10 @@ def check_grad_reg(got, ref):
     same_zeros = bool(np.array_equal(got == 0, ref == 0))
     assert same_zeros
     excess = float((np.abs(got - ref) - 1e-5 * np.abs(ref)).max())
-    assert excess <= 1e-5 * float(np.abs(ref).max()), (excess, float(np.abs(ref).max()))
+    scale = float(np.abs(ref).max())
+    # the worst excess seen in a session, as a fraction of the allowance, is written to gpurun_out/test_metrics.json (conftest)
+    OBSERVED['grad_reg_worst_excess_over_scale'] = max(OBSERVED.get('grad_reg_worst_excess_over_scale', 0.0), excess / scale if scale else 0.0)
+    assert excess <= GRAD_REG_ABS * scale, (excess, scale)
 
 
 def check_rel(got, ref, tol=1e-5):
@@ -466,7 +472,12 @@ def test_gt_centric_assignment_equals_anchor_centric(h, w, C, N, G):
                                             out['npos'].data_ptr(), out['nvalid'].data_ptr(), None, None, ws.data_ptr(),
                                             ws.numel(), torch.cuda.current_stream().cuda_stream))
         torch.cuda.synchronize()
-        assert int(ws.sum()) == 0 or True
+        # every call leaves the workspace zero-clean EXCEPT the per-block partial sums (plain floats, overwritten by each call):
+        # header (counters / npos accumulator), GT-centric keys and the touched bitmap must all read zero again
+        hdr = (N * 3 * 4 + 255) // 256 * 256
+        part = (N * ((A + 31) // 32 + 9 * 8) * 16 + 255) // 256 * 256
+        assert int(ws[:hdr].sum()) == 0, 'workspace header not left zeroed'
+        assert int(ws[hdr + part:].to(torch.int64).sum()) == 0, 'assignment keys / touched bitmap not left zeroed'
         return out, ws
     a, ws_a = run(False)
     b, ws_b = run(True)
