@@ -33,20 +33,32 @@ if ROOT not in sys.path:
 import numpy as np  # noqa: E402
 
 H, W, C, N_PER_GPU, GMAX = 800, 1333, 80, 16, 20
+NOMINAL_HBM_GBS = 8000.0      # "also report against nominal 8 TB/s"
+CPU_THREADS_CAP = 16          # both arms time the CPU port with min(host cores, 16) threads
+# the SAME string in both arms (the driver compares the two lines' config.workload)
+WORKLOAD = 'coco_loss_fwd_bwd: 16 x 800x1333 per GPU, C=80, A=200700, G<=20 (BASELINE config 3)'
 METRIC = 'detection-head images/sec (loss fwd+bwd: IoU assign + focal + smooth-L1, grads for cls and reg)'
 
 
-def synth_annotations(rng, n, gmax, h, w, c, empty=(0,)):
+def synth_annotations(rng, n, gmax, h, w, c, empty=(0,), exact=False, pseudo_split=None):
+    """SURVEY 8(d) GT generator.  exact: every image has exactly gmax boxes (config 5).  pseudo_split = P: the first rows of
+    an image are new-class GT (label >= P), the remaining rows pseudo-labels of old classes (label < P) -- the layout the
+    dataset produces when it appends the Labeler's boxes (dataloader.py:129-136); padding rows are -1."""
     ann = np.full((n, gmax, 5), -1.0, np.float32)
     for j in range(n):
         if j in empty:
             continue
-        g = int(rng.integers(1, gmax + 1))
+        g = gmax if exact else int(rng.integers(1, gmax + 1))
         x1 = rng.uniform(0, 0.7 * w, g)
         y1 = rng.uniform(0, 0.7 * h, g)
         bw = rng.uniform(16, 0.3 * w + 16, g)
         bh = rng.uniform(16, 0.3 * h + 16, g)
-        ann[j, :g] = np.stack([x1, y1, x1 + bw, y1 + bh, rng.integers(0, c, g).astype(np.float64)], 1)
+        if pseudo_split:
+            k = max(1, g // 2)
+            lab = np.concatenate([rng.integers(pseudo_split, c, k), rng.integers(0, pseudo_split, g - k)])
+        else:
+            lab = rng.integers(0, c, g)
+        ann[j, :g] = np.stack([x1, y1, x1 + bw, y1 + bh, lab.astype(np.float64)], 1)
     return ann
 
 
@@ -249,7 +261,7 @@ def run_reference(args):
     if rank != 0:
         return 0
     cores = os.cpu_count() or 1
-    threads = max(1, min(cores, 16))
+    threads = max(1, min(cores, CPU_THREADS_CAP))
     images_per_step = threads
     # keep the whole run to a few minutes: probe a quarter-size step, then pick the anchor fraction of the per-step sample
     _, probe_step, f0 = time_cpu_reference(1, 0, images_per_step, threads, 0.25)
@@ -262,8 +274,7 @@ def run_reference(args):
     line = {'impl': 'reference', 'metric': METRIC, 'value': val, 'unit': 'images/s', 'n_gpus': args.gpus, 'steps': args.steps,
             'warmup': args.warmup, 'ms_per_step': per_step * 1e3, 'higher_is_better': True, 'scaling': 'weak',
             'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-            'config': {'workload': 'coco_loss_fwd_bwd 800x1333 C=80 A=200700 G<=20 (BASELINE config 3)',
-                       'images_per_step': images_per_step * f},
+            'config': {'workload': WORKLOAD, 'images_per_step': images_per_step * f},
             'cpu_baseline': {'value': val, 'unit': 'images/s', 'cores': threads, 'kind': 'port', 'sample': sample,
                              'host_cores': cores},
             'e2e': {'value': val, 'unit': 'images/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
@@ -306,13 +317,190 @@ def bind_near_gpu(index):
 # --------------------------------------------------------------------------------------------------------------
 # our arm
 # --------------------------------------------------------------------------------------------------------------
+def make_inputs(dev, cfg, seed):
+    """Seeded synthetic batch of one BASELINE config: probabilities sigmoid(N(-4,2)), reg N(0,1), random GT."""
+    import torch
+
+    import cl_object_detection_b200 as cld
+    anchors = cld.generate_anchors(cfg['h'], cfg['w'], dev)
+    a = anchors.shape[1]
+    gen = torch.Generator(device=dev).manual_seed(seed)
+    probs = torch.sigmoid(torch.randn(cfg['n'], a, cfg['c'], device=dev, generator=gen) * 2.0 - 4.0)
+    reg = torch.randn(cfg['n'], a, 4, device=dev, generator=gen)
+    ann_np = synth_annotations(np.random.default_rng(seed), cfg['n'], cfg['gmax'], cfg['h'], cfg['w'], cfg['c'],
+                               empty=cfg.get('empty', (0,)), exact=cfg.get('exact_g', False), pseudo_split=cfg.get('past') or None)
+    return probs, reg, ann_np, anchors
+
+
+class LossStep:
+    """One step of the loss path THROUGH THE PUBLIC DROP-IN: FocalLoss.forward (or ShardedFocalLoss.forward on N > 1 ranks) ->
+    torch.ops.cldet.focal_loss (C++ op layer -> C ABI -> kernels), then autograd backward of its outputs with the upstream
+    gradients the caller's reduction delivers (IL_Loss: .mean() of every term, losses.py:584-588 -> 1/N_global per image)."""
+
+    def __init__(self, probs, reg, ann, anchors, state, params, n_global, module):
+        import torch
+        self.torch = torch
+        self.p = probs.detach().requires_grad_(True)
+        self.r = reg.detach().requires_grad_(True)
+        self.ann, self.anchors, self.state, self.params, self.module = ann, anchors, state, params, module
+        dev = probs.device
+        self.g_rows = torch.full((n_global,), 1.0 / n_global, device=dev)      # dL/dbg_j = dL/dfg_j of the caller's mean
+        self.g_one = torch.ones(1, device=dev)                                 # dL/dreg_loss
+        self.out = None
+
+    def __call__(self):
+        out = self.module(self.p, self.r, self.anchors, self.ann, self.state, self.params)
+        bg, fg = out['cls_loss']
+        self.out = out
+        return self.torch.autograd.grad([bg, fg, out['reg_loss']], [self.p, self.r], [self.g_rows, self.g_rows, self.g_one])
+
+
+def time_loop(step, steps, warmup, barrier, hook=None, sampler=None):
+    """`steps` timed iterations after `warmup`, CUDA events on the current stream, barrier + synchronize on both sides; one
+    more untimed step directly before the timed region aligns the ranks (on N > 1 it ends in the peer exchange)."""
+    import torch
+    for _ in range(max(warmup, 3)):
+        step()
+    barrier()
+    step()
+    if sampler is not None:
+        sampler.start()          # SM clock + throttle reasons are sampled DURING the timed region
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0.record()
+    for i in range(steps):
+        if hook is not None:
+            hook(i)
+        step()
+    t1.record()
+    barrier()
+    if sampler is not None:
+        sampler.stop()
+    return t0.elapsed_time(t1)
+
+
+LOSS_CONFIGS = {
+    1: dict(name="1: VOC '20' state 0, 2 x 512x512, C=20", n=2, h=512, w=512, c=20, gmax=20, state=0, past=0),
+    2: dict(name="2: VOC '15_1' state 1 + pseudo-label GT rows, 16 x 512x512, C=16 (15 old + 1 new)", n=16, h=512, w=512, c=16,
+            gmax=20, state=1, past=15),
+    3: dict(name='3: COCO-shaped, 16 x 800x1333, C=80', n=N_PER_GPU, h=H, w=W, c=C, gmax=GMAX, state=0, past=0),
+    5: dict(name='5: dense-GT stress, 8 x 1333x1333 per GPU, C=80, exactly 100 GT boxes per image', n=8, h=1333, w=1333, c=80,
+            gmax=100, state=0, past=0, exact_g=True, empty=()),
+}
+
+
+def config_lines(dev, world, rank, steps, barrier, reduce_max, make_module):
+    """Device-resident lines for the other loss configs of BASELINE.json through the same public step: 1 and 2 (VOC shapes; one
+    GPU only -- they are L2-resident, launch-bound problems) and 5 (dense GT) on every N, image-sharded like config 3."""
+    import torch
+
+    import cl_object_detection_b200 as cld
+    peak, _ = peak_hbm()
+    out = {}
+    for cid in ((1, 2, 5) if world == 1 else (5,)):
+        cfg = LOSS_CONFIGS[cid]
+        probs, reg, ann_np, anchors = make_inputs(dev, cfg, 1000 * cid + rank)
+        ann = torch.from_numpy(ann_np).to(dev)
+        params = cld.HeadParams([0, cfg['past']]) if cfg['state'] else cld.HeadParams()
+        n_global = cfg['n'] * world
+        step = LossStep(probs, reg, ann, anchors, cfg['state'], params, n_global, make_module())
+        ms = reduce_max(time_loop(step, steps, 5, barrier)) / steps
+        a = anchors.shape[1]
+        path_bytes = cfg['n'] * (8 * a * cfg['c'] + 48 * a + 20 * cfg['gmax'])
+        gbs = path_bytes / (ms * 1e-3) / 1e9
+        out[str(cid)] = {'workload': cfg['name'], 'value': n_global / (ms * 1e-3), 'unit': 'images/s', 'ms_per_step': ms,
+                         'steps': steps, 'images_per_gpu': cfg['n'], 'anchors': a, 'n_gpus': world,
+                         'path_bytes_per_gpu_step': path_bytes, 'achieved_gbs_per_gpu': gbs, 'roofline_frac': gbs / peak,
+                         'note': 'working set %.0f MB per GPU%s' % (2 * probs.numel() * 4 / 1e6,
+                                                                    ' (fits the 126 MB L2: latency-bound, not a roofline case)'
+                                                                    if 2 * probs.numel() * 4 < 126e6 else '')}
+        mod = step.module
+        del step, probs, reg
+        if world > 1:
+            dist_barrier_close(mod, barrier)
+        torch.cuda.empty_cache()
+    return out
+
+
+def dist_barrier_close(module, barrier):
+    barrier()
+    if hasattr(module, 'close'):
+        module.close()
+
+
+def sharded_parity(dev, world, rank, sharded, cfg):
+    """Driver-visible correctness of the image-sharded path (N > 1), on config 3's own batch:
+    (a) for two consecutive steps (both parities of the exchange buffers) the [4, N_global] rows delivered by the FUSED peer
+        exchange must be bit-equal to an NCCL all-gather of every rank's locally computed [4, n] rows;
+    (b) rank 0 recomputes the GLOBAL batch on its one GPU; IL_Loss's clip_loss reduction (losses.py:572-588: bg.mean() +
+        fg[fg >= clip].mean() + reg.mean(), clip = the median fg so that half the images are masked) must give the same loss,
+        and the gradients of rank 0's own shard must match what the sharded run produced."""
+    import torch
+    import torch.distributed as dist
+
+    import cl_object_detection_b200 as cld
+    n = cfg['n']
+    params = cld.HeadParams()
+    probs, reg, ann_np, anchors = make_inputs(dev, cfg, 3000 + rank)
+    ann = torch.from_numpy(ann_np).to(dev)
+    local_fl = cld.FocalLoss()
+    bit_equal = True
+    with torch.no_grad():
+        for _ in range(2):
+            out = sharded(probs, reg, anchors, ann, 0, params)
+            peer_rows = torch.stack([out['cls_loss'][0], out['cls_loss'][1], sharded.local_loss.last_reg_per_image])
+            lo = local_fl(probs, reg, anchors, ann, 0, params)
+            mine = torch.stack([lo['cls_loss'][0], lo['cls_loss'][1], local_fl.last_reg_per_image]).contiguous()     # [3, n]
+            allr = torch.empty((world, 3, n), device=dev)
+            dist.all_gather_into_tensor(allr, mine)
+            nccl_rows = allr.permute(1, 0, 2).reshape(3, world * n)
+            bit_equal = bit_equal and bool(torch.equal(peer_rows, nccl_rows))
+
+    def reduction(o, clip):
+        bg, fg = o['cls_loss']
+        m = fg >= clip
+        return bg.mean() + (fg[m].mean() if bool(m.any()) else fg.sum() * 0) + o['reg_loss'].mean()
+
+    p = probs.detach().requires_grad_(True)
+    r = reg.detach().requires_grad_(True)
+    out = sharded(p, r, anchors, ann, 0, params)
+    clip = float(out['cls_loss'][1].detach().median())
+    loss = reduction(out, clip)
+    gp, gr = torch.autograd.grad(loss, [p, r])
+    flag = torch.tensor([1 if bit_equal else 0], device=dev)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    res = {'terms_bit_equal': bool(int(flag.item())), 'checked_parities': 2, 'world': world,
+           'reduction': 'IL_Loss clip_loss (losses.py:572-588), clip = median fg'}
+    if rank == 0:
+        parts = [make_inputs(dev, cfg, 3000 + q) for q in range(world)]
+        gp_all = torch.cat([x[0] for x in parts]).requires_grad_(True)
+        gr_all = torch.cat([x[1] for x in parts]).requires_grad_(True)
+        ann_all = torch.from_numpy(np.concatenate([x[2] for x in parts])).to(dev)
+        del parts
+        single = cld.FocalLoss()(gp_all, gr_all, anchors, ann_all, 0, params)
+        ref = reduction(single, clip)
+        rp, rr = torch.autograd.grad(ref, [gp_all, gr_all])
+
+        def max_rel(got, want):
+            d = (got - want).abs()
+            return float((d / want.abs().clamp_min(1e-30)).max()) if bool((d > 0).any()) else 0.0
+        res.update({'loss_rel': abs(float(loss) - float(ref)) / abs(float(ref)),
+                    'grad_cls_max_rel': max_rel(gp, rp[:n]), 'grad_reg_max_rel': max_rel(gr, rr[:n]),
+                    'grad_bit_equal': bool(torch.equal(gp, rp[:n]) and torch.equal(gr, rr[:n])),
+                    'global_rows_bit_equal_single_gpu': bool(torch.equal(out['cls_loss'][0], single['cls_loss'][0]) and
+                                                             torch.equal(out['cls_loss'][1], single['cls_loss'][1]))})
+        res['grad_max_rel'] = max(res['grad_cls_max_rel'], res['grad_reg_max_rel'])
+        del gp_all, gr_all, rp, rr, single
+    torch.cuda.empty_cache()
+    dist.barrier()
+    return res
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
 
     import cl_object_detection_b200 as cld
     from cl_object_detection_b200 import _lib
-    from cl_object_detection_b200.params import to_loss_params
 
     world = int(os.environ.get('WORLD_SIZE', '1'))
     rank = int(os.environ.get('RANK', '0'))
@@ -327,125 +515,75 @@ def run_ours(args):
         os.environ.setdefault('NCCL_DEBUG_FILE', '/dev/stderr')
         dist.init_process_group('nccl', device_id=dev)
     lib = _lib.load()
+    cld.load_ops()
 
-    n = N_PER_GPU
-    anchors = cld.generate_anchors(H, W, dev)
+    cfg = LOSS_CONFIGS[3]
+    n = cfg['n']
+    n_global = n * world
+    probs, reg, ann_np, anchors = make_inputs(dev, cfg, 3000 + rank)
     a = anchors.shape[1]
-    gen = torch.Generator(device=dev).manual_seed(3000 + rank)
-    probs = torch.sigmoid(torch.randn(n, a, C, device=dev, generator=gen) * 2.0 - 4.0)
-    reg = torch.randn(n, a, 4, device=dev, generator=gen)
-    ann_np = synth_annotations(np.random.default_rng(3000 + rank), n, GMAX, H, W, C, empty=(0,))
     ann = torch.from_numpy(ann_np).to(dev)
     params = cld.HeadParams()
-    lp = to_loss_params(params, 0, C)
-    lp.image_height, lp.image_width = H, W          # the anchors are the standard grid: GT-centric assignment
-
-    # ---- device-resident step through the C ABI, stage by stage so the loss kernel can be event-timed ----
-    n_global = n * world
-    weights = torch.full((4, n), 1.0 / n_global, device=dev)
-    weights[3] = 1.0
-    baked = weights.clone()
-    gcls = torch.empty_like(probs)
-    greg = torch.empty_like(reg)
-    losses = torch.empty((4, n), device=dev)
-    gathered = torch.empty((world, 4, n), device=dev) if world > 1 else None
-    meta = torch.empty((n, a), dtype=torch.int32, device=dev)
-    npos = torch.zeros(n, dtype=torch.int32, device=dev)
-    nvalid = torch.empty(n, dtype=torch.int32, device=dev)
-    ws_bytes = lib.cldet_focal_loss_workspace_bytes(n, a)
-    ws = torch.zeros(ws_bytes, dtype=torch.uint8, device=dev)
-    stream = torch.cuda.current_stream().cuda_stream
-    ev_a = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
-    ev_b = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
-    ev_c = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
-
-    for e in ev_a + ev_b + ev_c:
-        e.record()          # materialise the CUDA event handles
-    torch.cuda.synchronize()
-
-    # N > 1: every rank needs every image's (bg, fg, reg) terms (IL_Loss's mean / clip_loss mask).  Default: the loss kernel
-    # itself pushes them into all ranks' gather buffers over NVLink peer stores (cldet_focal_loss_sharded) and a one-block
-    # kernel waits for the arrivals; `--collective nccl` uses an NCCL all-gather after the kernel instead.
-    peer = None
-    collective = 'none'
-    if world > 1:
-        collective = args.collective
-        if collective == 'peer':
-            from cl_object_detection_b200.dist import PeerGather
-            try:
-                peer = PeerGather(n, dev)
-            except Exception as e:  # noqa: BLE001
-                print('peer exchange unavailable (%r): falling back to the NCCL all-gather' % (e,), file=sys.stderr)
-                peer = None
-            ok = torch.tensor([1 if peer is not None else 0], device=dev)
-            dist.all_reduce(ok, op=dist.ReduceOp.MIN)
-            if int(ok.item()) == 0:
-                peer, collective = None, 'nccl'
-
-    def step(i=None):
-        nonlocal peer
-        # the fused entry point (assign + loss in one call) -- what FocalLoss.forward issues; the profiling hook makes
-        # this call record events around its two kernels so the loss kernel is timed inside the real step
-        if i is not None:
-            lib.cldet_focal_loss_profile_events(ev_a[i].cuda_event, ev_b[i].cuda_event, ev_c[i].cuda_event)
-        if peer is not None:
-            _lib.check(lib.cldet_focal_loss_sharded(
-                probs.data_ptr(), reg.data_ptr(), anchors.data_ptr(), ann.data_ptr(), n, a, C, GMAX, lp, weights.data_ptr(),
-                baked.data_ptr(), gcls.data_ptr(), greg.data_ptr(), losses.data_ptr(), meta.data_ptr(), None, npos.data_ptr(),
-                nvalid.data_ptr(), None, None, ws.data_ptr(), ws_bytes, peer.exchange(), stream))
-            peer.wait(stream)
-        else:
-            _lib.check(lib.cldet_focal_loss(
-                probs.data_ptr(), reg.data_ptr(), anchors.data_ptr(), ann.data_ptr(), n, a, C, GMAX, lp, weights.data_ptr(),
-                baked.data_ptr(), gcls.data_ptr(), greg.data_ptr(), losses.data_ptr(), meta.data_ptr(), None, npos.data_ptr(),
-                nvalid.data_ptr(), None, None, ws.data_ptr(), ws_bytes, stream))
-            if world > 1:
-                dist.all_gather_into_tensor(gathered, losses)
-        # backward: upstream weights are verified on the device; unchanged -> nothing is recomputed
-        _lib.check(lib.cldet_focal_loss_reweight(probs.data_ptr(), reg.data_ptr(), anchors.data_ptr(), ann.data_ptr(), n, a, C,
-                                                 GMAX, lp, weights.data_ptr(), baked.data_ptr(), gcls.data_ptr(),
-                                                 greg.data_ptr(), meta.data_ptr(), None, npos.data_ptr(), ws.data_ptr(),
-                                                 ws_bytes, stream))
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(max(args.warmup, 3)):
-        step()
-    if peer is not None:
-        # the warm-up doubles as a health check of the peer exchange: any rank that saw a missing arrival sends everyone
-        # back to the NCCL all-gather before the timed region
-        bad = torch.tensor([int(peer.status.item())], device=dev)
-        dist.all_reduce(bad, op=dist.ReduceOp.MAX)
-        if int(bad.item()) != 0:
-            print('peer exchange reported a missing arrival: using the NCCL all-gather', file=sys.stderr)
-            peer, collective = None, 'nccl'
-            for _ in range(3):
-                step()
+    def reduce_max(x):
+        if world == 1:
+            return float(x)
+        t = torch.tensor([x], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # N > 1: every rank needs every image's (bg, fg, reg) terms (IL_Loss's mean / clip_loss mask).  ShardedFocalLoss: the loss
+    # kernel itself pushes them into all ranks' gather buffers over NVLink peer stores and a one-block kernel waits for the
+    # arrivals and copies them out (`--collective nccl`: an NCCL all-gather after the kernel instead).
+    def make_module():
+        if world == 1:
+            return cld.FocalLoss()
+        return cld.ShardedFocalLoss(use_peer_memory=(args.collective == 'peer'))
+
+    module = make_module()
+    step = LossStep(probs, reg, ann, anchors, 0, params, n_global, module)
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.steps)]
+    for tri in ev:
+        for e in tri:
+            e.record()          # materialise the CUDA event handles
+    torch.cuda.synchronize()
+
+    def hook(i):
+        # the next fused call of this thread records events around its two kernels: the loss kernel is timed inside the real step
+        lib.cldet_focal_loss_profile_events(ev[i][0].cuda_event, ev[i][1].cuda_event, ev[i][2].cuda_event)
+
     sampler = ClockSampler(local_rank)
-    barrier()
-    sampler.start()
-    t_start = torch.cuda.Event(enable_timing=True)
-    t_end = torch.cuda.Event(enable_timing=True)
-    t_start.record()
-    for i in range(args.steps):
-        step(i)
-    t_end.record()
-    barrier()
-    sampler.stop()
-    total_ms = t_start.elapsed_time(t_end)
-    assign_ms = sum(x.elapsed_time(y) for x, y in zip(ev_a, ev_b)) / args.steps
-    loss_ms = sum(x.elapsed_time(y) for x, y in zip(ev_b, ev_c)) / args.steps
-    if len(sampler.samples) < 3:      # timed region shorter than the sampling period: keep sampling the same step under load
+    total_ms = time_loop(step, args.steps, args.warmup, barrier, hook, sampler)
+    collective = 'none'
+    if world > 1:
+        used_peer = bool(module._peer and any(v for v in module._peer.values()))
+        collective = 'peer' if used_peer else 'nccl'
+        if used_peer:
+            for pg in module._peer.values():
+                pg.check()          # a timed-out exchange raises here (status word in mapped host memory)
+    assign_ms = sum(t[0].elapsed_time(t[1]) for t in ev) / args.steps
+    loss_ms = sum(t[1].elapsed_time(t[2]) for t in ev) / args.steps
+    if args.steps < 300:
+        # the timed region is a few milliseconds -- shorter than a handful of sampling periods: keep sampling the clocks under the
+        # very same load for a FIXED number of extra steps (the same on every rank: the ranks exchange terms every step)
         sampler.start()
-        t0 = time.perf_counter()
-        while time.perf_counter() - t0 < 0.3:
+        for _ in range(600):
             step()
         torch.cuda.synchronize()
         sampler.stop()
     clocks = sampler.summary()
+    # host time to ENQUEUE one step through the drop-in (how far the CPU is from being the limit)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(20):
+        step()
+    host_us = (time.perf_counter() - t0) / 20 * 1e6
+    barrier()
 
     # ---- end to end through the public drop-in, host buffers in, losses out ----
     e2e_steps = max(3, min(args.steps, 10))
@@ -453,7 +591,6 @@ def run_ours(args):
     h_reg = reg.cpu().pin_memory()
     h_ann = torch.from_numpy(ann_np).pin_memory()
     h_out = torch.empty(3, dtype=torch.float32).pin_memory()
-    fl = cld.FocalLoss(upstream_hint=weights)
     d_probs = torch.empty_like(probs)
     d_reg = torch.empty_like(reg)
     d_ann = torch.empty_like(ann)
@@ -464,13 +601,9 @@ def run_ours(args):
         d_ann.copy_(h_ann, non_blocking=True)
         p = d_probs.detach().requires_grad_(True)
         r = d_reg.detach().requires_grad_(True)
-        out = fl(p, r, anchors, d_ann, 0, params)
+        out = module(p, r, anchors, d_ann, 0, params)          # rows of the GLOBAL batch on N > 1
         bg, fg = out['cls_loss']
-        if world > 1:
-            parts = torch.stack([bg.detach(), fg.detach()])
-            allp = torch.empty((world,) + tuple(parts.shape), device=dev)
-            dist.all_gather_into_tensor(allp, parts)
-        terms = torch.stack([bg.sum(), fg.sum(), out['reg_loss'].sum() * n]) / n_global
+        terms = torch.stack([bg.mean(), fg.mean(), out['reg_loss'].mean()])      # the caller's reductions (losses.py:584-588)
         g = torch.autograd.grad(terms.sum(), [p, r])
         h_out.copy_(terms.detach(), non_blocking=True)
         torch.cuda.current_stream().synchronize()
@@ -483,15 +616,13 @@ def run_ours(args):
     for _ in range(e2e_steps):
         e2e_step()
     barrier()
-    e2e_s = (time.perf_counter() - t0) / e2e_steps
+    e2e_s = reduce_max((time.perf_counter() - t0) / e2e_steps)
     h2d = h_probs.numel() * 4 + h_reg.numel() * 4 + h_ann.numel() * 4
     d2h = h_out.numel() * 4
+    del h_probs, h_reg, d_probs, d_reg
 
     # ---- max over ranks ----
-    stats = torch.tensor([total_ms, e2e_s, loss_ms, assign_ms], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(stats, op=dist.ReduceOp.MAX)
-    total_ms, e2e_s, loss_ms, assign_ms = [float(x) for x in stats.tolist()]
+    total_ms, loss_ms, assign_ms = reduce_max(total_ms), reduce_max(loss_ms), reduce_max(assign_ms)
     ms_per_step = total_ms / args.steps
     value = n_global / (ms_per_step * 1e-3)
 
@@ -503,14 +634,19 @@ def run_ours(args):
     roofline = {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
                 'traffic': traffic, 'kernel': 'focal_loss_kernel<VEC=8,GAMMA2,no IL variants,GRAD,probabilities> (256-bit LDG/STG)', 'kernel_ms': loss_ms,
                 'assign_kernel_ms': assign_ms, 'algorithmic_bytes_per_launch': kernel_bytes, 'peak_source': peak_src,
+                'frac_nominal': achieved / NOMINAL_HBM_GBS, 'nominal_peak': NOMINAL_HBM_GBS,
                 'path_frac': path_bytes / ((loss_ms + assign_ms) * 1e-3) / 1e9 / peak,
-                'step_frac': path_bytes / (ms_per_step * 1e-3) / 1e9 / peak}
+                'step_frac': path_bytes / (ms_per_step * 1e-3) / 1e9 / peak,
+                'step_frac_nominal': path_bytes / (ms_per_step * 1e-3) / 1e9 / NOMINAL_HBM_GBS}
+
+    cfg_lines = config_lines(dev, world, rank, 50, barrier, reduce_max, make_module) if not args.no_configs else None
+    parity = sharded_parity(dev, world, rank, module, cfg) if (world > 1 and collective == 'peer') else None
 
     if rank == 0:
         cores = os.cpu_count() or 1
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
-            thr = max(1, min(cores, 8))
+            thr = max(1, min(cores, CPU_THREADS_CAP))
             v, per, _ = time_cpu_reference(steps=2, warmup=0, images_per_step=thr, threads=thr)
             cpu = {'value': v, 'unit': 'images/s', 'cores': thr, 'kind': 'port', 'host_cores': cores,
                    'sample': '2 steps x %d COCO-shaped images (800x1333, C=80, A=200700), numpy port of FocalLoss fwd+bwd, '
@@ -521,8 +657,10 @@ def run_ours(args):
         line = {'metric': METRIC, 'value': value, 'unit': 'images/s', 'n_gpus': world, 'steps': args.steps,
                 'warmup': max(args.warmup, 3), 'ms_per_step': ms_per_step, 'higher_is_better': True, 'scaling': 'weak',
                 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-                'config': {'workload': 'coco_loss_fwd_bwd: %d x 800x1333 per GPU, C=80, A=%d, G<=%d (BASELINE config 3)' % (n, a, GMAX),
-                           'images_per_gpu': n, 'global_batch': n_global, 'parallelism': 'image-sharded dp%d' % world,
+                'config': {'workload': WORKLOAD, 'images_per_gpu': n, 'global_batch': n_global,
+                           'parallelism': 'image-sharded dp%d' % world,
+                           'api': 'FocalLoss.forward -> torch.ops.cldet.focal_loss (C++ op layer over the C ABI) + autograd backward'
+                                  if world == 1 else 'ShardedFocalLoss.forward -> torch.ops.cldet.focal_loss + autograd backward',
                            'collective': {'none': 'none (1 GPU)', 'peer': 'fused into the loss kernel: NVLink peer stores + arrival counters',
                                           'nccl': 'NCCL all-gather of the [4,N] terms'}[collective],
                            'l2': 'inputs (%.2f GB per GPU) are larger than the 126 MB L2; no flush needed' % (probs.numel() * 4 / 1e9),
@@ -530,21 +668,25 @@ def run_ours(args):
                 'clocks': clocks,
                 'e2e': {'value': n_global / e2e_s, 'unit': 'images/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
                         'ms_per_step': e2e_s * 1e3, 'steps': e2e_steps},
-                'gpu_launches': (4 if peer is not None else 3) * args.steps,
+                'gpu_launches': (4 if collective == 'peer' else 3) * args.steps,
+                'host_enqueue_us_per_step': host_us,
                 'roofline': roofline}
+        if cfg_lines is not None:
+            line['configs'] = cfg_lines
+        if parity is not None:
+            line['sharded_parity'] = parity
         if cpu is not None:
             line['cpu_baseline'] = cpu
         if eager is not None:
             line['gpu_eager_baseline'] = eager
         if world == 1 and not args.no_decode:
-            del probs, reg, gcls, greg, d_probs, d_reg, h_probs, h_reg
+            del probs, reg, step
             torch.cuda.empty_cache()
             line['decode'] = decode_section(dev, with_eager=not args.no_cpu_baseline)
         emit(line)
     if world > 1:
-        if peer is not None:
-            dist.barrier()
-            peer.close()
+        dist.barrier()
+        module.close()
         dist.destroy_process_group()
     return 0
 
@@ -580,6 +722,7 @@ def main():
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--no-cpu-baseline', action='store_true', help='skip the CPU port and the GPU-eager baseline legs')
     ap.add_argument('--no-decode', action='store_true', help='skip the BASELINE config 4 (decode + NMS) section')
+    ap.add_argument('--no-configs', action='store_true', help='skip the lines for BASELINE configs 1, 2 and 5')
     ap.add_argument('--collective', default='peer', choices=['peer', 'nccl'])
     args = ap.parse_args()
     if args.impl == 'reference':

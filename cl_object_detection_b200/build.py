@@ -13,6 +13,8 @@ ROOT = os.path.dirname(PKG)
 CSRC = os.path.join(PKG, 'csrc')
 INCLUDE = os.path.join(ROOT, 'include')
 LIB = os.path.join(PKG, 'libcldet.so')
+OPS_LIB = os.path.join(PKG, '_cldet_torch.so')          # the torch custom-op layer (csrc/cldet_torch.cpp) over the C ABI
+OPS_SRC = os.path.join(CSRC, 'cldet_torch.cpp')
 OBJ_DIR = os.path.join(ROOT, 'build', 'cldet')
 
 ARCH = ['-gencode', 'arch=compute_100a,code=sm_100a']
@@ -78,5 +80,39 @@ def build_library(force=False, verbose=False):
     return LIB
 
 
+def ops_is_stale():
+    if not os.path.exists(OPS_LIB):
+        return True
+    t = os.path.getmtime(OPS_LIB)
+    return any(os.path.getmtime(d) > t for d in (OPS_SRC, os.path.join(INCLUDE, 'cldet.h')))
+
+
+def build_ops(force=False, verbose=False):
+    """Compile the torch custom-op layer (host C++ only: it holds no kernel) against this interpreter's torch and link it to
+    libcldet.so next to it ($ORIGIN rpath).  Loaded with torch.ops.load_library, so it needs no Python headers."""
+    build_library(force=False)
+    if not force and not ops_is_stale():
+        return OPS_LIB
+    import torch
+    from torch.utils import cpp_extension as ce
+    cxx = os.environ.get('CXX') or shutil.which('g++') or 'g++'
+    tlib = os.path.join(os.path.dirname(torch.__file__), 'lib')
+    cuda_home = ce.CUDA_HOME or '/usr/local/cuda'
+    inc = ['-I' + p for p in ce.include_paths()] + ['-I' + os.path.join(cuda_home, 'include'), '-I' + INCLUDE]
+    tmp = OPS_LIB + '.tmp.%d' % os.getpid()
+    cmd = [cxx, '-O2', '-std=c++17', '-fPIC', '-shared', '-D_GLIBCXX_USE_CXX11_ABI=%d' % int(torch._C._GLIBCXX_USE_CXX11_ABI),
+           '-DTORCH_API_INCLUDE_EXTENSION_H', '-Wno-deprecated-declarations'] + inc + [OPS_SRC, '-o', tmp,
+           '-L' + tlib, '-ltorch', '-ltorch_cpu', '-ltorch_cuda', '-lc10', '-lc10_cuda', '-L' + PKG, '-l:libcldet.so',
+           '-Wl,-rpath,$ORIGIN', '-Wl,--no-as-needed']
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if verbose and r.stdout:
+        print(r.stdout)
+    if r.returncode != 0:
+        raise RuntimeError('building the torch op layer failed: %s\n%s' % (' '.join(cmd), r.stdout))
+    os.replace(tmp, OPS_LIB)
+    return OPS_LIB
+
+
 if __name__ == '__main__':
     print(build_library(force='--force' in sys.argv, verbose='-v' in sys.argv))
+    print(build_ops(force='--force' in sys.argv, verbose='-v' in sys.argv))

@@ -9,7 +9,7 @@ image per call; `detect_batch` runs a whole batch through the same kernels at on
 import torch
 import torch.nn as nn
 
-from . import _lib
+from . import _lib, _ops
 from .losses import _check_cuda_f32, _stream
 
 NMS_MODE_TORCHVISION = 0   # coordinate trick unless 4*K > limit (torchvision.ops.boxes.batched_nms)
@@ -74,19 +74,10 @@ def batched_nms(boxes, scores, idxs, iou_threshold, mode=NMS_MODE_TORCHVISION,
     k = b.shape[0]
     if s.shape[0] != k:
         raise ValueError('boxes and scores disagree')
-    lib = _lib.load()
-    with torch.cuda.device(b.device):
-        if k == 0:
-            return torch.empty(0, dtype=torch.int64, device=b.device)
-        i = None if idxs is None else idxs.to(torch.int64).contiguous()
-        ws_bytes = lib.cldet_batched_nms_workspace_bytes(k)
-        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=b.device)
-        keep = torch.empty(k, dtype=torch.int64, device=b.device)
-        count = torch.empty(1, dtype=torch.int32, device=b.device)
-        _lib.check(lib.cldet_batched_nms(b.data_ptr(), s.data_ptr(), _lib.ptr(i), k, float(iou_threshold), int(mode),
-                                         int(vanilla_numel_limit), keep.data_ptr(), count.data_ptr(), ws.data_ptr(),
-                                         ws_bytes, _stream()))
-        return keep[:int(count.item())]
+    if k == 0:
+        return torch.empty(0, dtype=torch.int64, device=b.device)
+    keep, count = _ops.load().batched_nms(b, s, idxs, float(iou_threshold), int(mode), int(vanilla_numel_limit))
+    return keep[:int(count.item())]
 
 
 def nms(boxes, scores, iou_threshold):
@@ -109,16 +100,15 @@ def detect_batch(cls, regressions, anchors, height, width, is_logits=True, score
     anc = _aligned(_check_cuda_f32('anchors', anchors).reshape(-1, 4))
     if c.dim() != 3 or r.dim() != 3 or r.shape[2] != 4 or r.shape[:2] != c.shape[:2] or anc.shape[0] != c.shape[1]:
         raise ValueError('expected cls [N,A,C], regressions [N,A,4], anchors [1,A,4]')
-    n, a, nc = c.shape
-    dev = c.device
-    lib = _lib.load()
-
-    def run_filter(cand, keys, counts, st):
-        _lib.check(lib.cldet_decode_filter(c.data_ptr(), int(bool(is_logits)), r.data_ptr(), anc.data_ptr(), n, a, nc,
-                                           int(height), int(width), float(score_thresh), cand.data_ptr(), keys.data_ptr(),
-                                           a, counts.data_ptr(), st))
-
-    return _detect_pipeline(run_filter, n, a, dev, iou_threshold, pre_nms_topk, nms_mode, vanilla_numel_limit, return_padded)
+    n = c.shape[0]
+    # one call into the C++ op layer (csrc/cldet_torch.cpp `detect`): allocation + K4 -> K5 -> K6 -> gather launches
+    topk = int(pre_nms_topk) if pre_nms_topk and pre_nms_topk > 0 else 0
+    scores, labels, boxes, keep_counts = _ops.load().detect(c, r, anc, int(height), int(width), bool(is_logits), float(score_thresh),
+                                                            float(iou_threshold), topk, int(nms_mode), int(vanilla_numel_limit))
+    if return_padded:
+        return scores, labels, boxes, keep_counts
+    kc = keep_counts.cpu().tolist()
+    return [(scores[j, :kc[j]], labels[j, :kc[j]], boxes[j, :kc[j]]) for j in range(n)]
 
 
 def detect_batch_head(cls_levels, reg_levels, anchors, height, width, is_logits=True, score_thresh=0.05, iou_threshold=0.5,

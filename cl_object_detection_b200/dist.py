@@ -101,6 +101,17 @@ class PeerGather:
     def exchange(self):
         return self._lib.PeerExchange(self.term_ptrs.data_ptr(), self.flag_ptrs.data_ptr(), self.rank, self.world, self.parity)
 
+    def descriptor(self):
+        """The exchange as the ten integers `torch.ops.cldet.focal_loss` takes (csrc/cldet_torch.cpp, `peer`), for ONE step:
+        advances the parity and that parity's use count like exchange() + wait() do."""
+        self.check()
+        parity = self.parity
+        self.uses[parity] += 1
+        self.parity ^= 1
+        return [self.term_ptrs.data_ptr(), self.flag_ptrs.data_ptr(), self.rank, self.world, parity,
+                self._own + 4 * self._flag_off, self._own, (self.uses[parity] * self.n) & 0xFFFFFFFF, self.timeout_ms,
+                self.status.data_ptr()]
+
     def check(self):
         """Raise if an earlier wait on this rank timed out (reads mapped host memory: no device synchronisation)."""
         if int(self.status[0]) != 0:

@@ -13,7 +13,7 @@ import threading
 import torch
 import torch.nn as nn
 
-from . import _lib
+from . import _lib, _ops
 from .anchors import grid_of
 from .params import to_loss_params
 
@@ -114,93 +114,6 @@ def _row(t):
     if t.dtype != torch.float32:
         t = t.to(torch.float32)
     return t, (t.stride(0) if t.dim() else 0)
-
-
-class _FocalLossFn(torch.autograd.Function):
-    """outputs: bg[N], fg[N], reg_per_image[N], enhance_per_image[N] (rows of the kernel's [4,N] result)."""
-
-    @staticmethod
-    def forward(ctx, cls, reg, anchors, annotations, lp, hint, want_bg_mask, check_labels, peer=None):
-        lib = _lib.load()
-        n, a, c = cls.shape
-        g = annotations.shape[1]
-        dev = cls.device
-        need_grad = ctx.needs_input_grad[0] or ctx.needs_input_grad[1]
-        with _DeviceGuard(dev):
-            stream = _stream()
-            losses = torch.empty((4, n), dtype=torch.float32, device=dev)
-            meta = torch.empty((n, a), dtype=torch.int32, device=dev)
-            iou_max = torch.empty((n, a), dtype=torch.float32, device=dev) if lp.decrease_positive_by_iou else None
-            counts = torch.empty((2, n), dtype=torch.int32, device=dev)      # rows: npos, nvalid
-            npos, nvalid = counts[0], counts[1]
-            bg_mask = torch.empty((n, a), dtype=torch.uint8, device=dev) if want_bg_mask else None
-            status = torch.empty(1, dtype=torch.int32, device=dev) if check_labels else None
-            ws = _workspace(dev, stream, n, a)
-            ws_bytes = ws.numel()
-            if need_grad:
-                weights = hint                        # shared, read-only; the kernel records what it baked into `baked`
-                baked = torch.empty((4, n), dtype=torch.float32, device=dev)
-                gcls = torch.empty_like(cls)
-                greg = torch.empty_like(reg)
-            else:
-                weights = baked = gcls = greg = None
-            try:
-                if peer is None:
-                    _lib.check(lib.cldet_focal_loss(
-                        cls.data_ptr(), reg.data_ptr(), anchors.data_ptr(), annotations.data_ptr(), n, a, c, g, lp,
-                        _lib.ptr(weights), _lib.ptr(baked), _lib.ptr(gcls), _lib.ptr(greg), losses.data_ptr(), meta.data_ptr(),
-                        _lib.ptr(iou_max), npos.data_ptr(), nvalid.data_ptr(), _lib.ptr(bg_mask), _lib.ptr(status),
-                        ws.data_ptr(), ws_bytes, stream))
-                else:
-                    # image-sharded: the kernel's epilogue pushes every image's terms into all ranks' gather buffers
-                    ex = peer.exchange()
-                    _lib.check(lib.cldet_focal_loss_sharded(
-                        cls.data_ptr(), reg.data_ptr(), anchors.data_ptr(), annotations.data_ptr(), n, a, c, g, lp,
-                        _lib.ptr(weights), _lib.ptr(baked), _lib.ptr(gcls), _lib.ptr(greg), losses.data_ptr(), meta.data_ptr(),
-                        _lib.ptr(iou_max), npos.data_ptr(), nvalid.data_ptr(), _lib.ptr(bg_mask), _lib.ptr(status),
-                        ws.data_ptr(), ws_bytes, ex, stream))
-                    # [4, world*n], global image order: a PRIVATE tensor written by the wait kernel (never a view of the
-                    # exchange buffer, which peers overwrite two steps later)
-                    losses = peer.wait(stream)
-            except Exception:
-                _drop_workspaces()      # a failed call may leave the scratch header dirty
-                raise
-        if check_labels and int(status.item()) != 0:
-            raise IndexError('a GT label is outside [0, %d): the reference indexes the class dimension with it '
-                             '(losses.py:341)' % c)
-        ctx.lp = lp
-        ctx.shape = (n, a, c, g)
-        ctx.local = None if peer is None else slice(peer.rank * n, (peer.rank + 1) * n)   # my images inside the global rows
-        ctx.backward_calls = 0
-        if need_grad:
-            ctx.save_for_backward(cls, reg, anchors, annotations, baked, gcls, greg, meta, npos)
-            ctx.iou_max = iou_max
-            ctx.ws = ws
-        ctx.mark_non_differentiable(npos, nvalid)
-        outs = (losses[0], losses[1], losses[2], losses[3], npos, nvalid)
-        if want_bg_mask:
-            ctx.mark_non_differentiable(bg_mask)
-            outs = outs + (bg_mask,)
-        return outs
-
-    @staticmethod
-    def backward(ctx, g_bg, g_fg, g_reg, g_enh, *unused):
-        cls, reg, anchors, annotations, baked, gcls, greg, meta, npos = ctx.saved_tensors
-        n, a, c, g = ctx.shape
-        dev = cls.device
-        if ctx.local is not None:        # global rows came back: only the slice of this rank's images feeds its gradients
-            g_bg, g_fg, g_reg, g_enh = (None if t is None else t[ctx.local] for t in (g_bg, g_fg, g_reg, g_enh))
-        rows = [_row(t) for t in (g_bg, g_fg, g_reg, g_enh)]      # keeps converted tensors alive until the call returns
-        with _DeviceGuard(dev):
-            _lib.check(_lib.load().cldet_focal_loss_reweight_rows(
-                cls.data_ptr(), reg.data_ptr(), anchors.data_ptr(), annotations.data_ptr(), n, a, c, g, ctx.lp,
-                _lib.ptr(rows[0][0]), rows[0][1], _lib.ptr(rows[1][0]), rows[1][1], _lib.ptr(rows[2][0]), rows[2][1],
-                _lib.ptr(rows[3][0]), rows[3][1], baked.data_ptr(), gcls.data_ptr(), greg.data_ptr(), meta.data_ptr(),
-                _lib.ptr(ctx.iou_max), npos.data_ptr(), ctx.ws.data_ptr(), ctx.ws.numel(), _stream()))
-        ctx.backward_calls += 1
-        if ctx.backward_calls > 1:   # the buffers may already be someone's .grad: hand out copies from now on
-            return gcls.clone(), greg.clone(), None, None, None, None, None, None, None
-        return gcls, greg, None, None, None, None, None, None, None
 
 
 class _FocalLossHeadFn(torch.autograd.Function):
@@ -340,22 +253,27 @@ class FocalLoss(nn.Module):
             raise ValueError('annotations needs at least one (possibly padding) row; the collater emits [N,1,5] of -1')
         n, _, c = cls.shape
         lp = to_loss_params(params, int(cur_state), c)
-        lp.cls_is_logits = int(self.from_logits)
         grid = grid_of(anc)            # anchors made by our Anchors module: GT-centric assignment
-        if grid is not None:
-            lp.image_height, lp.image_width = grid
+        h, w = grid if grid is not None else (0, 0)
         incremental = cur_state > 0
         want_mask = bool(incremental and params['distill'])
-        outs = _FocalLossFn.apply(cls, reg, anc, ann, lp, self._hint(n, cls.device), want_mask, self.check_labels, peer)
-        bg, fg, reg_j, enh_j, npos, nvalid = outs[:6]
-        result = {'cls_loss': (bg, fg), 'reg_loss': reg_j.mean(dim=0, keepdim=True)}   # losses.py:444-445
+        # one call into the C++ op layer (csrc/cldet_torch.cpp): allocation, the two kernel launches and the autograd node
+        outs = _ops.load().focal_loss(cls, reg, anc, ann, self._hint(n, cls.device), lp.alpha, lp.gamma, lp.incremental,
+                                      lp.past_class_num, lp.ignore_past_class, lp.new_ignore_past_class,
+                                      lp.decrease_positive_by_iou, lp.enhance_on_new, lp.decrease_positive, h, w, self.from_logits,
+                                      want_mask, self.check_labels, [] if peer is None else peer.descriptor())
+        bg, fg, reg_j, enh_j, reg_loss, npos, nvalid, meta = outs[:8]
+        if self.check_labels and int(outs[-1].item()) != 0:
+            raise IndexError('a GT label is outside [0, %d): the reference indexes the class dimension with it '
+                             '(losses.py:341)' % c)
+        result = {'cls_loss': (bg, fg), 'reg_loss': reg_loss}          # losses.py:444-445
         if incremental:
-            if params['distill']:
+            if want_mask:
                 # the reference appends a mask only for images that have GT (quirk Q6): M <= N rows
-                result['bg_masks'] = outs[6].bool()[nvalid > 0]
+                result['bg_masks'] = outs[8].bool()[nvalid > 0]
             if params['enhance_on_new']:
                 result['enhance_on_new_loss'] = enh_j.sum()
-        self.last_npos, self.last_nvalid, self.last_reg_per_image = npos, nvalid, reg_j
+        self.last_npos, self.last_nvalid, self.last_reg_per_image, self.last_meta = npos, nvalid, reg_j, meta
         return result
 
     def forward_head(self, cls_levels, reg_levels, anchors, annotations, cur_state: int, params, image_size, progress=-1):

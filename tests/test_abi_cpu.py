@@ -115,3 +115,22 @@ def test_a9_pseudo_label_format_mirrors_reference_collater():
     real = np.array([[10, 20, 30, 40, 15]], dtype=np.float64)
     pseudo = np.array([[5, 6, 7, 8, 1], [1, 2, 3, 4, 0]], dtype=np.float64)
     assert np.array_equal(cld.merge_pseudo_labels(real, pseudo), O.merge_pseudo_labels(real, pseudo))
+
+
+def test_torch_op_layer_builds_loads_and_registers():
+    """The C++ custom-op layer (csrc/cldet_torch.cpp) builds against this torch, links to libcldet.so and registers its
+    schemas; without a GPU its ops refuse CPU tensors (no fallback)."""
+    from cl_object_detection_b200.build import build_ops
+    build_ops()
+    ops = cld.load_ops()
+    assert ops.abi_version() == 1
+    for name in ('focal_loss', 'detect', 'batched_nms'):
+        assert hasattr(ops, name)
+    schema = str(torch.ops.cldet.focal_loss.default._schema)
+    assert 'Tensor cls' in schema and 'int[] peer' in schema and schema.endswith('-> Tensor[]')
+    with pytest.raises(RuntimeError, match='CUDA'):
+        ops.batched_nms(torch.rand(3, 4), torch.rand(3), None, 0.5, 0, 100000)
+    with pytest.raises(RuntimeError, match='CUDA'):
+        ops.detect(torch.rand(1, 9, 2), torch.rand(1, 9, 4), torch.rand(1, 9, 4), 8, 8, True, 0.05, 0.5, 0, 0, 100000)
+    with pytest.raises(RuntimeError, match='CUDA'):
+        cld.detect.detect_batch(torch.rand(1, 9, 2), torch.rand(1, 9, 4), torch.rand(1, 9, 4), 8, 8)

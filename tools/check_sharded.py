@@ -26,6 +26,35 @@ def caller_reduction(out, clip):
     return bg.mean() + fg_term + out['reg_loss'].mean()
 
 
+def straggler(sharded, p, r, anchors, ann, params, rank, world):
+    """A rank that is late by more than the exchange's timeout: the waiting ranks must see NaN in the late rank's rows of THAT
+    step and an exception on their next call -- never stale numbers -- and the late rank itself completes normally."""
+    import time
+    pg = [v for v in sharded._peer.values() if v][0]
+    pg.timeout_ms = 300
+    dist.barrier()
+    torch.cuda.synchronize()
+    if rank == world - 1:
+        time.sleep(1.5)
+    with torch.no_grad():
+        out = sharded(p, r, anchors, ann, 0, params)
+    torch.cuda.synchronize()
+    bg = out['cls_loss'][0]
+    n = p.shape[0]
+    late = bg[(world - 1) * n:]
+    if rank != world - 1:
+        assert bool(torch.isnan(late).all()), 'a late rank\'s rows must be poisoned, got %r' % (late,)
+        assert not bool(torch.isnan(bg[:(world - 1) * n]).any())
+        try:
+            sharded(p, r, anchors, ann, 0, params)
+            raise AssertionError('the step after a timed-out exchange must raise')
+        except cld.CldetError as e:
+            print('rank %d: straggler detected as designed: %s' % (rank, str(e)[:90]))
+    else:
+        assert not bool(torch.isnan(bg).any()), 'the late rank itself received everything'
+        print('rank %d: late rank completed normally' % rank)
+
+
 def main():
     rank, world, local = int(os.environ['RANK']), int(os.environ['WORLD_SIZE']), int(os.environ['LOCAL_RANK'])
     torch.cuda.set_device(local)
@@ -44,14 +73,17 @@ def main():
     sl = cld.shard_slice(n_global, world, rank)
     p = probs[sl].to(dev).requires_grad_(True)
     r = reg[sl].to(dev).requires_grad_(True)
-    sharded = cld.ShardedFocalLoss()
+    sharded = cld.ShardedFocalLoss() if equal else cld.ShardedFocalLoss(shard_sizes=cld.shard_sizes(n_global, world))
     out = sharded(p, r, anchors, ann[sl].to(dev), 0, params)
     used_peer = bool(sharded._peer and any(v for v in sharded._peer.values()))
-    if equal:      # run twice more: exercises both parities of the gather buffer and the counter reset
-        for _ in range(2):
+    if equal:      # run three times more: both parities of the gather buffer, several uses of each (growing arrival targets)
+        first = [t.clone() for t in out['cls_loss']]
+        for _ in range(3):
             p.grad = None
             r.grad = None
             out = sharded(p, r, anchors, ann[sl].to(dev), 0, params)
+        # results of an earlier step stay what they were: they are private copies, not views of the exchange buffer
+        assert all(torch.equal(a, b) for a, b in zip(first, [t for t in out['cls_loss']])), 'step results are not reproducible'
     clip = 0.5 * float(out['cls_loss'][1].detach().median())
     loss = caller_reduction(out, clip)
     loss.backward()
@@ -67,6 +99,8 @@ def main():
     assert torch.allclose(loss, ref, rtol=1e-6), (loss, ref)
     assert torch.allclose(p.grad, p0.grad[sl], rtol=1e-6, atol=1e-12), 'cls gradient differs'
     assert torch.allclose(r.grad, r0.grad[sl], rtol=1e-6, atol=1e-12), 'reg gradient differs'
+    if equal and used_peer and os.environ.get('CLDET_STRAGGLER', '0') == '1':
+        straggler(sharded, p, r, anchors, ann[sl].to(dev), params, rank, world)
     dist.barrier()
     if rank == 0:
         print('sharded loss ok: world=%d n_global=%d loss=%.6f fused_peer_allgather=%s' % (world, n_global, float(loss), used_peer))
