@@ -53,18 +53,18 @@ SIGNATURES = {
     'cldet_focal_loss': (_I, [_P, _P, _P, _P, _I, _L, _I, _I, ctypes.POINTER(LossParams), _P, _P, _P, _P, _P, _P, _P, _P,
                               _P, _P, _P, _P, _Z, _P]),
     'cldet_focal_loss_sharded': (_I, [_P, _P, _P, _P, _I, _L, _I, _I, ctypes.POINTER(LossParams), _P, _P, _P, _P, _P, _P, _P,
-                                      _P, _P, _P, _P, _P, _Z, ctypes.POINTER(PeerExchange), _P]),
+                                      _P, _P, _P, _P, _P, _Z, ctypes.POINTER(PeerExchange), _P, _P]),
     'cldet_peer_alloc': (_I, [_Z, ctypes.POINTER(ctypes.c_void_p), ctypes.c_char_p]),
     'cldet_peer_open': (_I, [ctypes.c_char_p, ctypes.POINTER(ctypes.c_void_p)]),
     'cldet_peer_close': (_I, [_P]),
     'cldet_peer_free': (_I, [_P]),
     'cldet_enable_peer_access': (_I, [_I]),
-    'cldet_peer_wait': (_I, [_P, _P, _I, _I, _I, ctypes.c_uint32, _I, _P, _P, _P]),
+    'cldet_peer_wait': (_I, [_P, _P, _I, _I, _I, ctypes.c_uint32, _I, _P, _P, _P, _P]),
     'cldet_focal_loss_profile_events': (_I, [_P, _P, _P]),
     'cldet_focal_loss_from_assignment': (_I, [_P, _P, _P, _P, _I, _L, _I, _I, ctypes.POINTER(LossParams), _P, _P, _P, _P,
                                               _P, _P, _P, _P, _P, _P, _P, _Z, _P]),
     'cldet_focal_loss_reweight_rows': (_I, [_P, _P, _P, _P, _I, _L, _I, _I, ctypes.POINTER(LossParams), _P, _L, _P, _L, _P,
-                                            _L, _P, _L, _P, _P, _P, _P, _P, _P, _P, _Z, _P]),
+                                            _L, _P, _L, _P, _F, _P, _P, _P, _P, _P, _P, _P, _Z, _P]),
     'cldet_focal_loss_reweight': (_I, [_P, _P, _P, _P, _I, _L, _I, _I, ctypes.POINTER(LossParams), _P, _P, _P, _P, _P,
                                        _P, _P, _P, _Z, _P]),
     'cldet_focal_loss_head': (_I, [_P, _P, _I, _I, _I, _P, _P, _I, _I, _I, ctypes.POINTER(LossParams), _P, _P, _P, _P, _P, _P,

@@ -72,9 +72,9 @@ struct Workspace {
     unsigned int* counters;
 };
 
-// workspace: [counters N | npos accumulator N | reweight counters N | pad to 256 B | partials]; the three header arrays
-// must be zero before the first call and are left zero by every call.
-static size_t workspace_header_bytes(int N) { return ((size_t)N * 3 * sizeof(unsigned int) + 255) / 256 * 256; }
+// workspace: [counters N | npos accumulator N | reweight counters N | images-done counter 1 | pad to 256 B | partials]; the
+// header must be zero before the first call and is left zero by every call.
+static size_t workspace_header_bytes(int N) { return (((size_t)N * 3 + 1) * sizeof(unsigned int) + 255) / 256 * 256; }
 
 static size_t workspace_partials_bytes(int N, int64_t A) {
     // worst case bpi: 32 anchors per block (concatenated layout); the head layout has 9 * ceil(hw_l / kHeadPos) blocks per
@@ -142,7 +142,7 @@ static int loss_stage(const float* d_cls, const float* d_reg, const float* d_anc
                       uint32_t* d_meta, const float* d_iou_max, const int32_t* d_npos, int32_t* d_npos_out, int32_t* d_npos_reset,
                       uint8_t* d_bg_mask, int32_t* d_status, void* d_workspace, size_t ws_bytes, void* stream,
                       const cldet_peer_exchange* peer = nullptr, unsigned long long* d_best = nullptr, const int32_t* d_nvalid = nullptr,
-                      float* d_iou_out = nullptr, uint32_t* d_touched = nullptr) {
+                      float* d_iou_out = nullptr, uint32_t* d_touched = nullptr, float* d_reg_mean = nullptr) {
     int rc = check_common(d_cls, d_anchors, d_annotations, num_images, num_anchors, num_classes, gt_rows, params);
     if (rc) return rc;
     if (!d_reg || !d_losses || !d_meta || !d_npos || !d_workspace) return CLDET_ERR_INVALID_ARGUMENT;
@@ -164,7 +164,9 @@ static int loss_stage(const float* d_cls, const float* d_reg, const float* d_anc
         a.w_stride[k] = 1;
     }
     a.has_w = d_weights ? 1 : 0;
+    a.w_reg_mean = nullptr; a.reg_mean_scale = 0.0f;
     a.baked_weights = d_baked_weights; a.gcls = d_grad_cls; a.greg = d_grad_reg; a.losses = d_losses;
+    a.reg_mean = d_reg_mean; a.images_done = reinterpret_cast<unsigned int*>(d_workspace) + 3 * (size_t)num_images;
     a.meta = d_meta; a.iou_max = d_iou_max; a.npos = d_npos; a.bg_mask = d_bg_mask; a.status = d_status;
     a.npos_out = d_npos_out; a.npos_reset = d_npos_reset; a.rw_counters = nullptr;
     a.best = d_best; a.touched = d_touched; a.meta_out = d_meta; a.iou_out = d_iou_out; a.nvalid = d_nvalid;
@@ -212,7 +214,7 @@ int cldet_focal_loss_sharded(const float* d_cls, const float* d_reg, const float
                              float* d_grad_cls, float* d_grad_reg, float* d_losses,
                              uint32_t* d_meta, float* d_iou_max, int32_t* d_npos, int32_t* d_nvalid,
                              uint8_t* d_bg_mask, int32_t* d_status,
-                             void* d_workspace, size_t ws_bytes, const cldet_peer_exchange* peer, void* stream) {
+                             void* d_workspace, size_t ws_bytes, const cldet_peer_exchange* peer, float* d_reg_mean, void* stream) {
     int rc = check_common(d_cls, d_anchors, d_annotations, num_images, num_anchors, num_classes, gt_rows, params);
     if (rc) return rc;
     if (!d_npos || !d_nvalid || !d_meta || !d_workspace) return CLDET_ERR_INVALID_ARGUMENT;
@@ -252,7 +254,7 @@ int cldet_focal_loss_sharded(const float* d_cls, const float* d_reg, const float
     if (ev[1]) CLDET_CUDA_TRY(cudaEventRecord(ev[1], s));
     rc = loss_stage(d_cls, d_reg, d_anchors, d_annotations, num_images, num_anchors, num_classes, gt_rows, params, d_weights,
                       d_baked_weights, d_grad_cls, d_grad_reg, d_losses, d_meta, d_iou_max, npos_acc, d_npos, npos_acc, d_bg_mask, d_status,
-                      d_workspace, ws_bytes, stream, peer, best, d_nvalid, best ? d_iou_max : nullptr, touched);
+                      d_workspace, ws_bytes, stream, peer, best, d_nvalid, best ? d_iou_max : nullptr, touched, d_reg_mean);
     if (rc) return rc;
     if (ev[2]) CLDET_CUDA_TRY(cudaEventRecord(ev[2], s));
     return CLDET_OK;
@@ -267,7 +269,7 @@ int cldet_focal_loss(const float* d_cls, const float* d_reg, const float* d_anch
                      void* d_workspace, size_t ws_bytes, void* stream) {
     return cldet_focal_loss_sharded(d_cls, d_reg, d_anchors, d_annotations, num_images, num_anchors, num_classes, gt_rows, params,
                                     d_weights, d_baked_weights, d_grad_cls, d_grad_reg, d_losses, d_meta, d_iou_max, d_npos,
-                                    d_nvalid, d_bg_mask, d_status, d_workspace, ws_bytes, nullptr, stream);
+                                    d_nvalid, d_bg_mask, d_status, d_workspace, ws_bytes, nullptr, nullptr, stream);
 }
 
 // Consumer side of the fused all-gather.  Thread r < world waits (acquire, system scope) until source rank r's arrival
@@ -279,7 +281,7 @@ int cldet_focal_loss(const float* d_cls, const float* d_reg, const float* d_anch
 // GPU; because nothing is ever reset, a late arrival cannot desynchronise the following steps.
 __global__ void __launch_bounds__(256)
 peer_wait_copy_kernel(const unsigned int* flags, int world, int parity, unsigned int target, unsigned long long timeout_ns,
-                      const float* terms, int n, float* out, int32_t* status) {
+                      const float* terms, int n, float* out, float* reg_mean, int32_t* status) {
     __shared__ int bad[64];
     const int r = threadIdx.x;
     if (r < world) {
@@ -315,6 +317,13 @@ peer_wait_copy_kernel(const unsigned int* flags, int world, int parity, unsigned
         const int k = rem / n, j = rem - k * n;
         // written by peers into this GPU's L2: read past L1 (a line of the previous use of this parity may still sit there)
         out[(size_t)k * world * n + (size_t)src * n + j] = bad[src] ? __int_as_float(0x7fc00000) : __ldcg(terms + i);
+    }
+    if (reg_mean && threadIdx.x == 0) {
+        // reg_loss = mean over the GLOBAL batch of the per-image regression terms (losses.py:445), in global image order
+        float s = 0.0f;
+        for (int src = 0; src < world; ++src)
+            for (int j = 0; j < n; ++j) s += bad[src] ? __int_as_float(0x7fc00000) : __ldcg(terms + ((size_t)src * 4 + 2) * n + j);
+        *reg_mean = s / (float)(world * n);
     }
 }
 
@@ -375,14 +384,14 @@ int cldet_enable_peer_access(int peer_device) {
 }
 
 int cldet_peer_wait(const void* d_flags_local, const float* d_terms_local, int world, int num_images, int parity,
-                    uint32_t target_arrivals, int timeout_ms, float* d_out, int32_t* d_status, void* stream) {
+                    uint32_t target_arrivals, int timeout_ms, float* d_out, float* d_reg_mean, int32_t* d_status, void* stream) {
     if (!d_flags_local || world < 1 || world > 64 || (parity != 0 && parity != 1) || num_images <= 0 || timeout_ms <= 0)
         return CLDET_ERR_INVALID_ARGUMENT;
-    if (d_out && !d_terms_local) return CLDET_ERR_INVALID_ARGUMENT;
+    if ((d_out || d_reg_mean) && !d_terms_local) return CLDET_ERR_INVALID_ARGUMENT;
     const float* terms = d_terms_local ? d_terms_local + (size_t)parity * world * 4 * num_images : nullptr;
     peer_wait_copy_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const unsigned int*>(d_flags_local), world, parity,
                                                               target_arrivals, (unsigned long long)timeout_ms * 1000000ull, terms,
-                                                              num_images, d_out, d_status);
+                                                              num_images, d_out, d_reg_mean, d_status);
     CLDET_LAUNCH_CHECK();
     return CLDET_OK;
 }
@@ -447,7 +456,8 @@ static int reweight_impl(const float* d_cls, const float* d_reg, const float* d_
                          int num_images, int64_t num_anchors, int num_classes, int gt_rows, const cldet_loss_params* params,
                          const float* const w_ptr[4], const int64_t w_stride[4], float* d_baked_weights, float* d_grad_cls,
                          float* d_grad_reg, const uint32_t* d_meta, const float* d_iou_max, const int32_t* d_npos,
-                         void* d_workspace, size_t ws_bytes, void* stream) {
+                         void* d_workspace, size_t ws_bytes, void* stream, const float* w_reg_mean = nullptr,
+                         float reg_mean_scale = 0.0f) {
     int rc = check_common(d_cls, d_anchors, d_annotations, num_images, num_anchors, num_classes, gt_rows, params);
     if (rc) return rc;
     if (!d_reg || !d_baked_weights || !d_grad_cls || !d_grad_reg || !d_meta || !d_npos || !d_workspace)
@@ -465,6 +475,8 @@ static int reweight_impl(const float* d_cls, const float* d_reg, const float* d_
         a.w_stride[k] = (int)w_stride[k];
     }
     a.has_w = 1;
+    a.w_reg_mean = w_reg_mean; a.reg_mean_scale = reg_mean_scale;
+    a.reg_mean = nullptr; a.images_done = nullptr;
     a.baked_weights = d_baked_weights; a.gcls = d_grad_cls; a.greg = d_grad_reg;
     a.losses = nullptr; a.meta = d_meta; a.iou_max = d_iou_max; a.npos = d_npos; a.bg_mask = nullptr; a.status = nullptr;
     a.npos_out = nullptr; a.npos_reset = nullptr;
@@ -502,7 +514,8 @@ int cldet_focal_loss_reweight_rows(const float* d_cls, const float* d_reg, const
                                    int num_images, int64_t num_anchors, int num_classes, int gt_rows,
                                    const cldet_loss_params* params, const float* d_w_bg, int64_t stride_bg,
                                    const float* d_w_fg, int64_t stride_fg, const float* d_w_reg, int64_t stride_reg,
-                                   const float* d_w_enh, int64_t stride_enh, float* d_baked_weights, float* d_grad_cls,
+                                   const float* d_w_enh, int64_t stride_enh, const float* d_w_reg_mean, float reg_mean_scale,
+                                   float* d_baked_weights, float* d_grad_cls,
                                    float* d_grad_reg, const uint32_t* d_meta, const float* d_iou_max, const int32_t* d_npos,
                                    void* d_workspace, size_t ws_bytes, void* stream) {
     const float* rows[4] = {d_w_bg, d_w_fg, d_w_reg, d_w_enh};
@@ -511,7 +524,7 @@ int cldet_focal_loss_reweight_rows(const float* d_cls, const float* d_reg, const
         if (strides[k] < 0 || strides[k] > 0x7fffffff) return CLDET_ERR_INVALID_ARGUMENT;
     return reweight_impl(d_cls, d_reg, d_anchors, d_annotations, num_images, num_anchors, num_classes, gt_rows, params, rows,
                          strides, d_baked_weights, d_grad_cls, d_grad_reg, d_meta, d_iou_max, d_npos, d_workspace, ws_bytes,
-                         stream);
+                         stream, d_w_reg_mean, reg_mean_scale);
 }
 
 int cldet_focal_loss_head(const float* const* h_cls_levels, const float* const* h_reg_levels, int num_levels, int image_height,

@@ -124,8 +124,13 @@ Peer parse_peer(at::IntArrayRef v) {
     return p;
 }
 
+// What backward needs besides tensors, as ONE saved IValue (an int list): sizes, the peer slice and the params struct's words.
+enum { kN = 0, kA, kC, kG, kNg, kLocal0, kLp0 };
+constexpr size_t kLpWords = sizeof(cldet_loss_params) / sizeof(int32_t);
+static_assert(sizeof(cldet_loss_params) % sizeof(int32_t) == 0, "cldet_loss_params is a sequence of 32-bit fields");
+
 struct FocalLossFn : public torch::autograd::Function<FocalLossFn> {
-    // outputs: bg[Ng], fg[Ng], reg_j[Ng], enh_j[Ng], reg_loss[1], npos[N], nvalid[N], meta?, bg_mask?, status?
+    // outputs: bg[Ng], fg[Ng], reg_j[Ng], enh_j[Ng], reg_loss[1], npos[N], nvalid[N], meta, bg_mask?, status?
     // (Ng = N, or world*N rows in global image order on an image-sharded run)
     static variable_list forward(AutogradContext* ctx, const Tensor& cls, const Tensor& reg, const Tensor& anchors,
                                  const Tensor& ann, const Tensor& hint, cldet_loss_params lp, bool need_grad, bool want_bg_mask,
@@ -135,7 +140,9 @@ struct FocalLossFn : public torch::autograd::Function<FocalLossFn> {
         cudaStream_t stream = c10::cuda::getCurrentCUDAStream();
         const auto f32 = cls.options();
         const auto i32 = cls.options().dtype(at::kInt);
+        const int64_t ng = peer.on ? n * peer.ex.world : n;
         Tensor losses = at::empty({4, n}, f32);
+        Tensor reg_loss = at::empty({1}, f32);
         Tensor meta = at::empty({n, a}, i32);
         Tensor iou_max = lp.decrease_positive_by_iou ? at::empty({n, a}, f32) : Tensor();
         Tensor counts = at::empty({2, n}, i32);
@@ -155,41 +162,35 @@ struct FocalLossFn : public torch::autograd::Function<FocalLossFn> {
             cls.data_ptr<float>(), reg.data_ptr<float>(), anchors.data_ptr<float>(), ann.data_ptr<float>(), (int)n, a, (int)c,
             (int)g, &lp, need_grad ? hint.data_ptr<float>() : nullptr, (float*)opt(baked), (float*)opt(gcls), (float*)opt(greg),
             losses.data_ptr<float>(), (uint32_t*)meta.data_ptr(), (float*)opt(iou_max), npos, nvalid, (uint8_t*)opt(bg_mask),
-            (int32_t*)opt(status), ws.data_ptr(), (size_t)ws.numel(), peer.on ? &peer.ex : nullptr, stream);
+            (int32_t*)opt(status), ws.data_ptr(), (size_t)ws.numel(), peer.on ? &peer.ex : nullptr,
+            peer.on ? nullptr : reg_loss.data_ptr<float>(), stream);
         if (rc != CLDET_OK) {
             drop_workspaces();          // a failed call may leave the scratch header dirty
             check_status(rc, "cldet_focal_loss");
         }
-        int64_t ng = n;
         if (peer.on) {
             // fused all-gather: the kernel pushed every image's terms into all ranks' buffers; wait and copy the GLOBAL rows
             // into a private tensor (never a view of the exchange buffer)
-            ng = n * peer.ex.world;
             Tensor global = at::empty({4, ng}, f32);
             check_status(cldet_peer_wait(peer.flags_local, peer.terms_local, peer.ex.world, (int)n, peer.ex.parity, peer.target,
-                                         peer.timeout_ms, global.data_ptr<float>(), peer.status, stream),
+                                         peer.timeout_ms, global.data_ptr<float>(), reg_loss.data_ptr<float>(), peer.status, stream),
                          "cldet_peer_wait");
             losses = global;
         }
-        Tensor reg_loss = at::mean(losses[2], at::IntArrayRef{0}, /*keepdim=*/true);        // losses.py:445  stack(regression_losses).mean(dim=0, keepdim=True)
-        ctx->saved_data["n"] = n;
-        ctx->saved_data["a"] = a;
-        ctx->saved_data["c"] = c;
-        ctx->saved_data["g"] = g;
-        ctx->saved_data["ng"] = ng;
-        ctx->saved_data["local0"] = peer.on ? (int64_t)peer.ex.rank * n : (int64_t)0;
-        ctx->saved_data["calls"] = (int64_t)0;
+        ctx->set_materialize_grads(false);          // absent upstream gradients stay undefined (= zero rows), no fill kernels
         if (need_grad) {
-            std::vector<int64_t> raw(sizeof(lp) / sizeof(int32_t));
-            static_assert(sizeof(cldet_loss_params) % sizeof(int32_t) == 0, "cldet_loss_params is a sequence of 32-bit fields");
+            std::vector<int64_t> info(kLp0 + kLpWords);
+            info[kN] = n; info[kA] = a; info[kC] = c; info[kG] = g; info[kNg] = ng;
+            info[kLocal0] = peer.on ? (int64_t)peer.ex.rank * n : (int64_t)0;
             const int32_t* words = reinterpret_cast<const int32_t*>(&lp);
-            for (size_t i = 0; i < raw.size(); ++i) raw[i] = words[i];
-            ctx->saved_data["lp"] = raw;
-            ctx->save_for_backward({cls, reg, anchors, ann, baked, gcls, greg, meta, counts, iou_max.defined() ? iou_max : Tensor(), ws});
+            for (size_t i = 0; i < kLpWords; ++i) info[kLp0 + i] = words[i];
+            ctx->saved_data["info"] = std::move(info);
+            ctx->save_for_backward({cls, reg, anchors, ann, baked, gcls, greg, meta, counts, iou_max, ws});
         }
-        Tensor npos_t = counts[0], nvalid_t = counts[1];
-        variable_list outs = {losses[0], losses[1], losses[2], losses[3], reg_loss, npos_t, nvalid_t, meta};
-        std::vector<Tensor> nondiff = {npos_t, nvalid_t, meta};
+        std::vector<Tensor> rows = losses.unbind(0);
+        std::vector<Tensor> cnt = counts.unbind(0);
+        variable_list outs = {rows[0], rows[1], rows[2], rows[3], reg_loss, cnt[0], cnt[1], meta};
+        std::vector<Tensor> nondiff = {cnt[0], cnt[1], meta};
         if (want_bg_mask) {
             outs.push_back(bg_mask);
             nondiff.push_back(bg_mask);
@@ -207,46 +208,44 @@ struct FocalLossFn : public torch::autograd::Function<FocalLossFn> {
         const Tensor &cls = saved[0], &reg = saved[1], &anchors = saved[2], &ann = saved[3], &baked = saved[4];
         Tensor gcls = saved[5], greg = saved[6];
         const Tensor &meta = saved[7], &counts = saved[8], &iou_max = saved[9], &ws = saved[10];
-        const int64_t n = ctx->saved_data["n"].toInt(), a = ctx->saved_data["a"].toInt(), c = ctx->saved_data["c"].toInt(),
-                      g = ctx->saved_data["g"].toInt(), ng = ctx->saved_data["ng"].toInt(),
-                      local0 = ctx->saved_data["local0"].toInt();
+        const auto info = ctx->saved_data["info"].toIntVector();
+        const int64_t n = info[kN], a = info[kA], c = info[kC], g = info[kG], ng = info[kNg], local0 = info[kLocal0];
         cldet_loss_params lp;
         {
-            const auto raw = ctx->saved_data["lp"].toIntVector();
             int32_t* words = reinterpret_cast<int32_t*>(&lp);
-            for (size_t i = 0; i < raw.size(); ++i) words[i] = (int32_t)raw[i];
+            for (size_t i = 0; i < kLpWords; ++i) words[i] = (int32_t)info[kLp0 + i];
         }
         c10::cuda::CUDAGuard guard(cls.device());
         cudaStream_t stream = c10::cuda::getCurrentCUDAStream();
-        // rows: dL/dbg, dL/dfg, dL/dreg_j, dL/denh as (pointer, element stride); a row may arrive expanded (stride 0).
-        // The regression term reaches the caller twice -- per image (reg_j) and as the batch mean reg_loss = mean_j reg_j
-        // (what the reference returns): fold dL/dreg_loss / Ng into the per-image row.
-        Tensor rows[4] = {grads[0], grads[1], grads[2], grads[3]};
-        if (grads[4].defined()) {
-            Tensor spread = grads[4].to(at::kFloat).div((double)ng);          // [1]
-            rows[2] = rows[2].defined() ? rows[2].to(at::kFloat) + spread : spread;
-        }
+        // rows: dL/dbg, dL/dfg, dL/dreg_j, dL/denh as (pointer, element stride); a row may arrive expanded (stride 0) or not
+        // at all (undefined = zeros).  The regression term reaches the caller twice -- per image (reg_j) and as the batch mean
+        // reg_loss = mean_j reg_j (what the reference returns): the kernel adds dL/dreg_loss * (1/Ng) to the per-image row.
+        Tensor rows[5] = {grads[0], grads[1], grads[2], grads[3], grads[4]};
         const float* ptr[4];
         int64_t stride[4];
+        for (int k = 0; k < 5; ++k)
+            if (rows[k].defined() && (rows[k].scalar_type() != at::kFloat || !rows[k].is_cuda())) rows[k] = rows[k].to(cls.options());
         for (int k = 0; k < 4; ++k) {
             if (!rows[k].defined()) {
                 ptr[k] = nullptr;
                 stride[k] = 0;
                 continue;
             }
-            if (rows[k].scalar_type() != at::kFloat) rows[k] = rows[k].to(at::kFloat);
             const int64_t st = (rows[k].dim() == 0 || rows[k].numel() == 1) ? 0 : rows[k].stride(0);
             ptr[k] = rows[k].data_ptr<float>() + ((st != 0) ? local0 * st : 0);   // global rows: this rank's images start at local0
             stride[k] = st;
         }
+        const float* reg_mean_w = rows[4].defined() ? rows[4].data_ptr<float>() : nullptr;
         const int32_t* npos = counts.data_ptr<int32_t>();
         check_status(cldet_focal_loss_reweight_rows(
                          cls.data_ptr<float>(), reg.data_ptr<float>(), anchors.data_ptr<float>(), ann.data_ptr<float>(), (int)n, a,
-                         (int)c, (int)g, &lp, ptr[0], stride[0], ptr[1], stride[1], ptr[2], stride[2], ptr[3], stride[3],
-                         baked.data_ptr<float>(), gcls.data_ptr<float>(), greg.data_ptr<float>(), (const uint32_t*)meta.data_ptr(),
-                         iou_max.defined() ? iou_max.data_ptr<float>() : nullptr, npos, ws.data_ptr(), (size_t)ws.numel(), stream),
+                         (int)c, (int)g, &lp, ptr[0], stride[0], ptr[1], stride[1], ptr[2], stride[2], ptr[3], stride[3], reg_mean_w,
+                         (float)(1.0 / (double)ng), baked.data_ptr<float>(), gcls.data_ptr<float>(), greg.data_ptr<float>(),
+                         (const uint32_t*)meta.data_ptr(), iou_max.defined() ? iou_max.data_ptr<float>() : nullptr, npos,
+                         ws.data_ptr(), (size_t)ws.numel(), stream),
                      "cldet_focal_loss_reweight_rows");
-        const int64_t calls = ctx->saved_data["calls"].toInt() + 1;
+        auto it = ctx->saved_data.find("calls");
+        const int64_t calls = (it == ctx->saved_data.end() ? 0 : it->second.toInt()) + 1;
         ctx->saved_data["calls"] = calls;
         if (calls > 1) {       // the buffers may already be someone's .grad: hand out copies from now on
             gcls = gcls.clone();

@@ -127,7 +127,7 @@ class PeerGather:
         self.uses[self.parity] += 1
         target = (self.uses[self.parity] * self.n) & 0xFFFFFFFF
         self._lib.check(self._lib.load().cldet_peer_wait(self._own + 4 * self._flag_off, self._own, self.world, self.n, self.parity,
-                                                        target, self.timeout_ms, out.data_ptr(), self.status.data_ptr(), stream))
+                                                        target, self.timeout_ms, out.data_ptr(), None, self.status.data_ptr(), stream))
         self.parity ^= 1
         return out
 

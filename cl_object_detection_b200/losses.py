@@ -15,7 +15,7 @@ import torch.nn as nn
 
 from . import _lib, _ops
 from .anchors import grid_of
-from .params import to_loss_params
+from .params import loss_param_args, to_loss_params
 
 
 def _check_cuda_f32(name, t):
@@ -23,7 +23,18 @@ def _check_cuda_f32(name, t):
         raise RuntimeError('%s must be a CUDA tensor: this path has no CPU implementation' % name)
     if t.dtype != torch.float32:
         raise TypeError('%s must be float32 (got %s)' % (name, t.dtype))
-    return t.contiguous()
+    return t if t.is_contiguous() else t.contiguous()
+
+
+_FOCAL_OP = None
+
+
+def _focal_loss_op():
+    """torch.ops.cldet.focal_loss.default (the overload itself: skips the packet's overload resolution on every call)."""
+    global _FOCAL_OP
+    if _FOCAL_OP is None:
+        _FOCAL_OP = _ops.load().focal_loss.default
+    return _FOCAL_OP
 
 
 def _stream():
@@ -252,16 +263,14 @@ class FocalLoss(nn.Module):
         if ann.shape[1] == 0:
             raise ValueError('annotations needs at least one (possibly padding) row; the collater emits [N,1,5] of -1')
         n, _, c = cls.shape
-        lp = to_loss_params(params, int(cur_state), c)
+        lp = loss_param_args(params, int(cur_state), c)
         grid = grid_of(anc)            # anchors made by our Anchors module: GT-centric assignment
         h, w = grid if grid is not None else (0, 0)
         incremental = cur_state > 0
         want_mask = bool(incremental and params['distill'])
         # one call into the C++ op layer (csrc/cldet_torch.cpp): allocation, the two kernel launches and the autograd node
-        outs = _ops.load().focal_loss(cls, reg, anc, ann, self._hint(n, cls.device), lp.alpha, lp.gamma, lp.incremental,
-                                      lp.past_class_num, lp.ignore_past_class, lp.new_ignore_past_class,
-                                      lp.decrease_positive_by_iou, lp.enhance_on_new, lp.decrease_positive, h, w, self.from_logits,
-                                      want_mask, self.check_labels, [] if peer is None else peer.descriptor())
+        outs = _focal_loss_op()(cls, reg, anc, ann, self._hint(n, cls.device), *lp, h, w, self.from_logits, want_mask,
+                                self.check_labels, [] if peer is None else peer.descriptor())
         bg, fg, reg_j, enh_j, reg_loss, npos, nvalid, meta = outs[:8]
         if self.check_labels and int(outs[-1].item()) != 0:
             raise IndexError('a GT label is outside [0, %d): the reference indexes the class dimension with it '

@@ -155,7 +155,11 @@ int cldet_focal_loss_sharded(const float* d_cls, const float* d_reg, const float
                              float* d_grad_cls, float* d_grad_reg, float* d_losses,
                              uint32_t* d_meta, float* d_iou_max, int32_t* d_npos, int32_t* d_nvalid,
                              uint8_t* d_bg_mask, int32_t* d_status,
-                             void* d_workspace, size_t workspace_bytes, const cldet_peer_exchange* peer, void* stream);
+                             void* d_workspace, size_t workspace_bytes, const cldet_peer_exchange* peer, float* d_reg_mean,
+                             void* stream);
+/* d_reg_mean (device float[1], may be NULL; used when peer == NULL or peer->world <= 1): receives reg_loss = mean_j reg_j
+ * (losses.py:445), added in image order by the block that finishes the last image, so the caller needs no reduction launch.
+ * With a peer exchange the mean over the GLOBAL batch comes from cldet_peer_wait. */
 /* Node-shared buffers for the peer exchange.  cldet_peer_alloc: cudaMalloc + zero + export (64-byte cudaIpcMemHandle_t copied
  * to h_handle64); cldet_peer_open: map a peer rank's buffer into this process WITH THE CALLER'S DEVICE CURRENT (lazy peer
  * access), returning a pointer kernels of that device can dereference; cldet_peer_close / cldet_peer_free undo them. */
@@ -171,7 +175,8 @@ int cldet_enable_peer_access(int peer_device);
  * A source rank that does not arrive in time gets its rows of d_out filled with NaN and *d_status (may be NULL; may point to
  * mapped pinned host memory) is set to 2; the counters are never reset, so later steps stay in sequence regardless. */
 int cldet_peer_wait(const void* d_flags_local, const float* d_terms_local, int world, int num_images, int parity,
-                    uint32_t target_arrivals, int timeout_ms, float* d_out, int32_t* d_status, void* stream);
+                    uint32_t target_arrivals, int timeout_ms, float* d_out, float* d_reg_mean, int32_t* d_status, void* stream);
+/* d_reg_mean (may be NULL): receives the mean of row 2 (the per-image regression terms) over all world*N images. */
 
 /* Profiling hook (per host thread, one-shot): the next cldet_focal_loss call of THIS thread records the given
  * cudaEvent_t handles before the assign kernel, between the two kernels and after the loss kernel, on its stream.
@@ -207,9 +212,13 @@ int cldet_focal_loss_reweight_rows(const float* d_cls, const float* d_reg, const
                                    int num_images, int64_t num_anchors, int num_classes, int gt_rows,
                                    const cldet_loss_params* params, const float* d_w_bg, int64_t stride_bg,
                                    const float* d_w_fg, int64_t stride_fg, const float* d_w_reg, int64_t stride_reg,
-                                   const float* d_w_enh, int64_t stride_enh, float* d_baked_weights, float* d_grad_cls,
+                                   const float* d_w_enh, int64_t stride_enh, const float* d_w_reg_mean, float reg_mean_scale,
+                                   float* d_baked_weights, float* d_grad_cls,
                                    float* d_grad_reg, const uint32_t* d_meta, const float* d_iou_max, const int32_t* d_npos,
                                    void* d_workspace, size_t workspace_bytes, void* stream);
+/* d_w_reg_mean (device float[1], may be NULL) and reg_mean_scale: a second source of the regression weight for callers that
+ * hold dL/d(reg_loss) of reg_loss = mean_j reg_j (the tensor the reference returns): dL/dreg_j = d_w_reg[j*stride] +
+ * d_w_reg_mean[0] * reg_mean_scale with reg_mean_scale = 1/N (over the global batch on image-sharded runs). */
 
 /* ---- SURVEY 8(f) row f1, second half: the head's RAW conv outputs in, gradients of the same layout out ----
  * Replaces, for training, the layout work between the output convolutions and FocalLoss: ClassificationModel.forward /

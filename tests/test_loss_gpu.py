@@ -32,7 +32,7 @@ def check_grad_cls(got, ref):
     assert err < 1e-5, err
 
 
-GRAD_REG_ABS = 1e-5     # absolute allowance in units of max|grad| (see check_grad_reg)
+GRAD_REG_ABS = 3e-6     # absolute allowance in units of max|grad| (see check_grad_reg); worst observed on B200: 1.05e-6
 
 
 def check_grad_reg(got, ref):
@@ -474,7 +474,7 @@ def test_gt_centric_assignment_equals_anchor_centric(h, w, C, N, G):
         torch.cuda.synchronize()
         # every call leaves the workspace zero-clean EXCEPT the per-block partial sums (plain floats, overwritten by each call):
         # header (counters / npos accumulator), GT-centric keys and the touched bitmap must all read zero again
-        hdr = (N * 3 * 4 + 255) // 256 * 256
+        hdr = ((N * 3 + 1) * 4 + 255) // 256 * 256
         part = (N * ((A + 31) // 32 + 9 * 8) * 16 + 255) // 256 * 256
         assert int(ws[:hdr].sum()) == 0, 'workspace header not left zeroed'
         assert int(ws[hdr + part:].to(torch.int64).sum()) == 0, 'assignment keys / touched bitmap not left zeroed'
