@@ -253,6 +253,22 @@ def decode_section(dev, with_eager):
         out[name] = entry
         del logits, reg
         torch.cuda.empty_cache()
+    # the boundary as the reference calls it: predict, one image per call, no top-k, host head outputs in, detections out
+    from tools.bench_detect import measure_nms_h2h, measure_predict
+    out['predict_batch1_reference_mode'] = {}
+    for label, mu in (('~1.3k candidates', -10.5), ('~8k candidates', -9.5), ('~40k candidates', -8.5)):
+        try:
+            out['predict_batch1_reference_mode'][label] = measure_predict(dev, mu, cpu_images=2 if with_eager else 0)
+        except Exception as e:  # noqa: BLE001
+            out['predict_batch1_reference_mode'][label] = {'unavailable': repr(e)[:200]}
+        torch.cuda.empty_cache()
+    # K6 (+ its sort) against torchvision's own CUDA nms on identical inputs
+    out['nms_vs_torchvision'] = {}
+    for k in (1000, 8000, 40000):
+        try:
+            out['nms_vs_torchvision'][str(k)] = measure_nms_h2h(dev, k)
+        except Exception as e:  # noqa: BLE001
+            out['nms_vs_torchvision'][str(k)] = {'unavailable': repr(e)[:200]}
     return out
 
 

@@ -74,6 +74,11 @@ SIGNATURES = {
     'cldet_distill_workspace_bytes': (_Z, [_I, _L]),
     'cldet_distill_forward': (_I, [_P, _P, _P, _P, _P, _I, _L, _I, _I, _I, _I, _P, _P, _P, _Z, _P]),
     'cldet_distill_backward': (_I, [_P, _P, _P, _P, _P, _I, _L, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P]),
+    'cldet_enhance_error_workspace_bytes': (_Z, [_L]),
+    'cldet_enhance_error_forward': (_I, [_P, _I, _L, _I, _I, _I, _P, _P, _P, _Z, _P]),
+    'cldet_enhance_error_backward': (_I, [_P, _I, _L, _I, _I, _I, _P, _P, _P, _P]),
+    'cldet_masked_abs_mean_forward': (_I, [_P, _P, _I, _L, _P, _P, _P]),
+    'cldet_masked_abs_mean_backward': (_I, [_P, _P, _I, _L, _P, _P, _L, _P, _P]),
     'cldet_decode_boxes': (_I, [_P, _P, _I, _L, _I, _I, _I, _P, _P]),
     'cldet_clip_boxes': (_I, [_P, _L, _I, _I, _P]),
     'cldet_decode_filter': (_I, [_P, _I, _P, _P, _I, _L, _I, _I, _I, _F, _P, _P, _L, _P, _P]),

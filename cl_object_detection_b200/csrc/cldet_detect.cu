@@ -6,6 +6,7 @@
 // Compiled with -fmad=false: decoded boxes, scores and IoU compares must round exactly like the reference's
 // separate ATen ops, because keep indices / labels are integer outputs of those fp32 values.
 #include <math.h>
+#include <stdlib.h>
 
 #include <algorithm>
 
@@ -361,6 +362,7 @@ decode_filter_head_kernel(const HeadFilterLevels lv, int is_logits, const float4
 constexpr int kSelBins = 2048;
 constexpr int kRankPerBlock = 64;       // candidates ranked by one 256-thread block of rank_sort_kernel (4 threads each)
 constexpr int kRankDirect = 2048;      // up to this many candidates per image the O(n^2) rank sort beats radix select + compaction
+constexpr int kRadixMin = 4096;        // longer lists (no top-k) are ordered by the one-launch radix sort instead of the pairwise rank sort
 
 struct SelPass {
     int shift;     // bit position of this digit inside the 32 score bits
@@ -588,6 +590,139 @@ rank_sort_kernel(const cldet_candidate* __restrict__ cand, const uint64_t* __res
 }
 
 // ------------------------------------------------------------------------------------------------
+// K5 (large lists): segmented LSD radix sort of each image's candidates by the full 64-bit key, DESCENDING -- the order the
+// rank sort produces, without its O(n^2) pair count.  One CTA per image runs ALL passes in one launch: the image's keys live
+// in L2, 8-bit digits, stable by construction (tiles are processed in order; inside a tile the 32 warps own consecutive
+// 128-key runs, a warp ranks its keys with match.any and per-(warp, digit) counters, an exclusive scan over (digit, warp)
+// turns the counters into tile-local offsets).  The digit histograms of all 8 passes come from ONE sweep over the keys;
+// a pass whose digit is constant over the image (the high score bits, the unused anchor bits) is skipped -- typically 6-7 of
+// the 8 passes run.  The last pass's index permutation gathers the 32-byte records straight into the sorted list.
+// ------------------------------------------------------------------------------------------------
+constexpr int kRsThreads = 1024;
+constexpr int kRsWarps = kRsThreads / 32;
+constexpr int kRsItems = 4;
+constexpr int kRsTile = kRsThreads * kRsItems;
+constexpr int kRsBins = 256;
+
+__global__ void __launch_bounds__(kRsThreads)
+radix_sort_kernel(const cldet_candidate* __restrict__ cand, const uint64_t* __restrict__ keys, const int32_t* __restrict__ counts,
+                  int64_t in_capacity, int64_t max_count, cldet_candidate* __restrict__ sorted, int64_t out_capacity,
+                  int32_t* __restrict__ sorted_counts, uint64_t* __restrict__ kbuf, uint32_t* __restrict__ ibuf) {
+    __shared__ uint32_t hist[8][kRsBins];
+    __shared__ uint32_t cnt[kRsWarps][kRsBins];
+    __shared__ uint32_t base[kRsBins];
+    __shared__ uint32_t tile_tot[kRsBins];
+    __shared__ int skip[8];
+    const int j = blockIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int n = (int)min64(min64(counts[j], in_capacity), max_count);
+    const uint64_t* k_in = keys + (int64_t)j * in_capacity;
+    uint64_t* kb[2] = {kbuf + (int64_t)j * 2 * max_count, kbuf + (int64_t)j * 2 * max_count + max_count};
+    uint32_t* ib[2] = {ibuf + (int64_t)j * 2 * max_count, ibuf + (int64_t)j * 2 * max_count + max_count};
+    if (tid == 0) sorted_counts[j] = (int32_t)min64(n, out_capacity);
+    if (n == 0) return;
+
+    // ---- one sweep: the digit histograms of all 8 passes ----
+    for (int i = tid; i < 8 * kRsBins; i += kRsThreads) (&hist[0][0])[i] = 0u;
+    if (tid < 8) skip[tid] = 0;
+    __syncthreads();
+    for (int i = tid; i < n; i += kRsThreads) {
+        const uint64_t k = k_in[i];
+#pragma unroll
+        for (int p = 0; p < 8; ++p) atomicAdd(&hist[p][(uint32_t)(k >> (8 * p)) & 255u], 1u);
+    }
+    __syncthreads();
+    for (int i = tid; i < 8 * kRsBins; i += kRsThreads)
+        if ((&hist[0][0])[i] == (uint32_t)n) skip[i / kRsBins] = 1;       // the whole image shares this digit: identity pass
+    __syncthreads();
+
+    int cur = -1;                                  // -1: the data still sits in the input arrays (index = position)
+    for (int p = 0; p < 8; ++p) {
+        if (skip[p]) continue;                     // block-uniform
+        // descending order: bin d starts after all larger digits
+        if (tid < kRsBins) base[tid] = hist[p][tid];
+        __syncthreads();
+        for (int off = 1; off < kRsBins; off <<= 1) {          // inclusive suffix sum (Hillis-Steele)
+            uint32_t add = 0;
+            if (tid < kRsBins && tid + off < kRsBins) add = base[tid + off];
+            __syncthreads();
+            if (tid < kRsBins) base[tid] += add;
+            __syncthreads();
+        }
+        if (tid < kRsBins) base[tid] -= hist[p][tid];           // exclusive
+        __syncthreads();
+        const uint64_t* src_k = (cur < 0) ? k_in : kb[cur];
+        const uint32_t* src_i = (cur < 0) ? nullptr : ib[cur];
+        const int nxt = (cur < 0) ? 0 : (cur ^ 1);
+        uint64_t* dst_k = kb[nxt];
+        uint32_t* dst_i = ib[nxt];
+        const int shift = 8 * p;
+        for (int t0 = 0; t0 < n; t0 += kRsTile) {
+            for (int i = tid; i < kRsWarps * kRsBins; i += kRsThreads) (&cnt[0][0])[i] = 0u;
+            __syncthreads();
+            uint64_t key[kRsItems];
+            uint32_t idx[kRsItems], loc[kRsItems];
+            int dig[kRsItems];
+#pragma unroll
+            for (int r = 0; r < kRsItems; ++r) {
+                const int i = t0 + warp * (32 * kRsItems) + r * 32 + lane;
+                const bool valid = i < n;
+                key[r] = valid ? src_k[i] : 0ull;
+                idx[r] = valid ? (src_i ? src_i[i] : (uint32_t)i) : 0u;
+                dig[r] = valid ? (int)((uint32_t)(key[r] >> shift) & 255u) : -1;
+            }
+#pragma unroll
+            for (int r = 0; r < kRsItems; ++r) {
+                const unsigned m = __match_any_sync(0xffffffffu, dig[r]);
+                const int leader = __ffs(m) - 1;
+                uint32_t prev = 0;
+                if (lane == leader && dig[r] >= 0) {
+                    prev = cnt[warp][dig[r]];
+                    cnt[warp][dig[r]] = prev + (uint32_t)__popc(m);
+                }
+                prev = __shfl_sync(0xffffffffu, prev, leader);
+                loc[r] = prev + (uint32_t)__popc(m & ((1u << lane) - 1u));
+                __syncwarp();
+            }
+            __syncthreads();
+            if (tid < kRsBins) {
+                uint32_t run = 0;
+#pragma unroll 8
+                for (int w = 0; w < kRsWarps; ++w) {
+                    const uint32_t t = cnt[w][tid];
+                    cnt[w][tid] = run;
+                    run += t;
+                }
+                tile_tot[tid] = run;
+            }
+            __syncthreads();
+#pragma unroll
+            for (int r = 0; r < kRsItems; ++r) {
+                if (dig[r] >= 0) {
+                    const uint32_t pos = base[dig[r]] + cnt[warp][dig[r]] + loc[r];
+                    dst_k[pos] = key[r];
+                    dst_i[pos] = idx[r];
+                }
+            }
+            __syncthreads();
+            if (tid < kRsBins) base[tid] += tile_tot[tid];
+            // (the next tile's first barrier orders this update before any use)
+        }
+        __syncthreads();          // this pass's global writes are visible to the whole block before the next pass reads them
+        cur = nxt;
+    }
+    // ---- gather the records in sorted order ----
+    const int lim = (int)min64(n, out_capacity);
+    const float4* src = reinterpret_cast<const float4*>(cand + (int64_t)j * in_capacity);
+    float4* dst = reinterpret_cast<float4*>(sorted + (int64_t)j * out_capacity);
+    for (int i = tid; i < lim; i += kRsThreads) {
+        const uint32_t from = (cur < 0) ? (uint32_t)i : ib[cur][i];
+        dst[2 * (int64_t)i] = src[2 * (int64_t)from];
+        dst[2 * (int64_t)i + 1] = src[2 * (int64_t)from + 1];
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // K6: NMS.  (1) per-image max coordinate + mode (2) 64x64 suppression bitmask over the SORTED list
 // (3) sequential resolve, one block per image, 64 boxes per step.
 // nms_info per image: [0] max coordinate (float bits), [1] mode actually used (1 trick, 2 vanilla)
@@ -716,8 +851,11 @@ nms_resolve_kernel(const int32_t* __restrict__ counts, int64_t capacity, const u
     __shared__ int kept_total;
     __shared__ unsigned long long acc[16];
     const int j = blockIdx.x;
-    // never past what the mask workspace was sized for (max_count), even if the caller's counts are larger
-    const int n = (int)min64(min64(counts[j], capacity), (int64_t)col_blocks_alloc * 64);
+    if (min64(counts[j], capacity) > (int64_t)col_blocks_alloc * 64) {     // more boxes than the mask workspace was sized for
+        if (threadIdx.x == 0) keep_counts[j] = -1;                         // report, never truncate silently
+        return;
+    }
+    const int n = (int)min64(counts[j], capacity);
     const int col_blocks = (n + 63) / 64;
     uint64_t* remv = remv_ws + (int64_t)j * col_blocks_alloc;
     const uint64_t* m = mask + (int64_t)j * mask_stride_img;
@@ -792,8 +930,11 @@ nms_resolve_smem_kernel(const int32_t* __restrict__ counts, int64_t capacity, co
                         int32_t* __restrict__ keep_counts) {
     extern __shared__ uint64_t sm_mask[];                                // [64*cb][cb], rows >= n zero
     const int j = blockIdx.x;
-    // never past what the mask workspace was sized for (max_count), even if the caller's counts are larger
-    const int n = (int)min64(min64(counts[j], capacity), (int64_t)col_blocks_alloc * 64);
+    if (min64(counts[j], capacity) > (int64_t)col_blocks_alloc * 64) {     // more boxes than the mask workspace was sized for
+        if (threadIdx.x == 0) keep_counts[j] = -1;                         // report, never truncate silently
+        return;
+    }
+    const int n = (int)min64(counts[j], capacity);
     const int cb = (n + 63) / 64;
     const uint64_t* m = mask + (int64_t)j * mask_stride_img;
     const int total = 64 * cb * cb;
@@ -857,12 +998,133 @@ nms_resolve_smem_kernel(const int32_t* __restrict__ counts, int64_t capacity, co
     if (lane == 0) keep_counts[j] = kept_total;
 }
 
+// Any-K resolve: one CTA per image, the "removed" bitmap in shared memory, and a two-stage software pipeline over the 64-box
+// chunks so that no global-memory latency sits on the sequential chain:
+//   warp 0 (the chain)  chunk c: cur = removed[c]; 64-step greedy scan over the chunk's DIAGONAL mask block (prefetched into
+//                       shared memory one chunk ahead) -> kept bits; write the chunk's survivors; fold the kept rows' words of the
+//                       NEXT column block (c, c+1) (also prefetched) into removed[c+1] -- all the next chunk needs from this one;
+//   warps 1..31         meanwhile absorb chunk c-1's kept rows into removed[c+1 ..] with independent coalesced loads (every
+//                       thread owns column words), and prefetch the diagonal and next blocks of chunk c+1.
+// One block barrier per chunk.  removed[c] is complete when the chain reads it: chunk c-1 reached it through the folded next
+// block, chunks <= c-2 through absorb passes that ended at earlier barriers.  Replaces both the 64-dependent-loads-per-chunk
+// nms_resolve_kernel (K > 1216) and, when it wins, the whole-mask-in-shared-memory variant.
+constexpr int kStreamThreads = 1024;
+constexpr int kStreamAbsorbWarps = 24;     // warps 1..24 absorb, 25..28 prefetch, warp 0 runs the chain
+constexpr int kStreamUnroll = 8;            // independent loads in flight per absorber thread
+
+__global__ void __launch_bounds__(kStreamThreads)
+nms_resolve_stream_kernel(const int32_t* __restrict__ counts, int64_t capacity, const uint64_t* __restrict__ mask,
+                          int64_t mask_stride_img, int col_blocks_alloc, int32_t* __restrict__ keep,
+                          int32_t* __restrict__ keep_counts) {
+    extern __shared__ unsigned long long removed[];                      // [col_blocks]
+    __shared__ uint64_t diag[2][64];
+    __shared__ uint64_t nextb[2][64];
+    __shared__ uint64_t kept_s[2];
+    const int j = blockIdx.x;
+    const int64_t cnt_j = min64(counts[j], capacity);
+    if (cnt_j > (int64_t)col_blocks_alloc * 64) {                         // more boxes than the mask workspace was sized for:
+        if (threadIdx.x == 0) keep_counts[j] = -1;                        // report, never truncate silently
+        return;
+    }
+    const int n = (int)cnt_j;
+    const int cb = (n + 63) / 64;
+    const uint64_t* m = mask + (int64_t)j * mask_stride_img;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int t = tid; t < cb; t += kStreamThreads) removed[t] = 0ull;
+    if (tid < 2) kept_s[tid] = 0ull;
+    // prefetch for chunk 0
+    if (tid < 128) {
+        const int b = tid & 63, which = tid >> 6;                         // 0: block (0,0), 1: block (0,1)
+        const int row = b, word = which;
+        uint64_t v = 0ull;
+        if (row < n && word < cb) v = m[(int64_t)row * col_blocks_alloc + word];
+        if (which == 0) diag[0][b] = v; else nextb[0][b] = v;
+    }
+    __syncthreads();
+    int kept_total = 0;
+    for (int c = 0; c < cb; ++c) {
+        const int buf = c & 1;
+        if (warp == 0) {
+            const int rows = min(64, n - c * 64);
+            uint64_t cur = removed[c];
+            if (rows < 64) cur |= ~0ull << rows;                           // slots past the end can never be kept
+            uint64_t kept = 0;
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+                uint64_t w[16];
+#pragma unroll
+                for (int q = 0; q < 16; ++q) w[q] = diag[buf][g * 16 + q];
+#pragma unroll
+                for (int q = 0; q < 16; ++q) {
+                    const int b = g * 16 + q;
+                    const bool take = !((cur >> b) & 1ull);
+                    kept |= take ? (1ull << b) : 0ull;
+                    cur |= take ? w[q] : 0ull;
+                }
+            }
+            if (c + 1 < cb) {                                             // what chunk c+1 needs from this chunk
+                const uint64_t v = (((kept >> lane) & 1ull) ? nextb[buf][lane] : 0ull) |
+                                   (((kept >> (lane + 32)) & 1ull) ? nextb[buf][lane + 32] : 0ull);
+                const unsigned lo = __reduce_or_sync(0xffffffffu, (unsigned)v);
+                const unsigned hi = __reduce_or_sync(0xffffffffu, (unsigned)(v >> 32));
+                if (lane == 0) atomicOr(&removed[c + 1], ((unsigned long long)hi << 32) | lo);
+            }
+            if (lane == 0) kept_s[buf] = kept;
+            const uint64_t lo0 = (1ull << lane) - 1ull;
+            if ((kept >> lane) & 1ull) keep[(int64_t)j * capacity + kept_total + __popcll(kept & lo0)] = c * 64 + lane;
+            const uint64_t lo1 = (1ull << (lane + 32)) - 1ull;
+            if ((kept >> (lane + 32)) & 1ull) keep[(int64_t)j * capacity + kept_total + __popcll(kept & lo1)] = c * 64 + lane + 32;
+            kept_total += __popcll(kept);
+        } else if (warp >= 1 + kStreamAbsorbWarps) {
+            // four warps prefetch the diagonal and next blocks of chunk c+1 (three warps idle)
+            const int q = tid - 32 * (1 + kStreamAbsorbWarps);
+            if (q < 128) {
+                const int b = q & 63, which = q >> 6;
+                const int row = (c + 1) * 64 + b, word = c + 1 + which;
+                uint64_t v = 0ull;
+                if (row < n && word < cb) v = m[(int64_t)row * col_blocks_alloc + word];
+                if (which == 0) diag[buf ^ 1][b] = v; else nextb[buf ^ 1][b] = v;
+            }
+        } else if (c >= 1 && c + 1 < cb) {
+            // Absorb chunk c-1's kept rows into the column words c+1 ..  A warp = 8 rows x 4 consecutive words (one 32-byte
+            // sector per row); the 24 warps = 8 row groups x 3 sector slots.  Every thread issues kStreamUnroll INDEPENDENT
+            // loads per round (one L2 latency per round, not per row), the 8 rows of a warp are OR-reduced with shuffles and
+            // 4 lanes publish the words with shared-memory atomics.
+            const int aw = warp - 1;
+            const int b = (aw & 7) * 8 + (lane >> 2), wq = lane & 3, ss = aw >> 3;
+            const uint64_t kp = kept_s[buf ^ 1];
+            const bool on = (kp >> b) & 1ull;
+            const uint64_t* rowp = m + ((int64_t)(c - 1) * 64 + b) * col_blocks_alloc;
+            constexpr int kSlots = kStreamAbsorbWarps / 8;                // sector slots per round
+            for (int w0 = c + 1 + 4 * ss; w0 < cb; w0 += 4 * kSlots * kStreamUnroll) {
+                uint64_t v[kStreamUnroll];
+#pragma unroll
+                for (int u = 0; u < kStreamUnroll; ++u) {
+                    const int wd = w0 + 4 * kSlots * u + wq;
+                    v[u] = (on && wd < cb) ? rowp[wd] : 0ull;
+                }
+#pragma unroll
+                for (int u = 0; u < kStreamUnroll; ++u) {
+                    uint64_t x = v[u];
+                    x |= __shfl_xor_sync(0xffffffffu, x, 4);
+                    x |= __shfl_xor_sync(0xffffffffu, x, 8);
+                    x |= __shfl_xor_sync(0xffffffffu, x, 16);
+                    const int wd = w0 + 4 * kSlots * u + lane;
+                    if (lane < 4 && x && wd < cb) atomicOr(&removed[wd], (unsigned long long)x);
+                }
+            }
+        }
+        __syncthreads();
+    }
+    if (tid == 0) keep_counts[j] = kept_total;
+}
+
 __global__ void __launch_bounds__(256)
 gather_detections_kernel(const cldet_candidate* __restrict__ sorted, const int32_t* __restrict__ keep,
                          const int32_t* __restrict__ keep_counts, int64_t capacity, float* __restrict__ scores,
                          int64_t* __restrict__ labels, float4* __restrict__ boxes) {
     const int j = blockIdx.y;
-    const int n = (int)min64(keep_counts[j], capacity);
+    const int n = (int)min64(keep_counts[j], capacity);           // a negative count (error marker) gathers nothing
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const cldet_candidate c = sorted[(int64_t)j * capacity + keep[(int64_t)j * capacity + i]];
@@ -963,6 +1225,26 @@ coco_records_kernel(const float* __restrict__ scores, const int64_t* __restrict_
 }
 
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+// A/B switches for experiments only (read once): CLDET_NMS_RESOLVE = stream | smem | legacy, CLDET_FORCE_RANK_SORT = 1
+static int resolve_choice() {
+    static const int v = [] {
+        const char* e = getenv("CLDET_NMS_RESOLVE");
+        if (!e) return 0;
+        if (e[0] == 's' && e[1] == 't') return 1;
+        if (e[0] == 's' && e[1] == 'm') return 2;
+        if (e[0] == 'l') return 3;
+        return 0;
+    }();
+    return v;
+}
+static bool force_rank_sort() {
+    static const bool v = [] {
+        const char* e = getenv("CLDET_FORCE_RANK_SORT");
+        return e && e[0] == '1';
+    }();
+    return v;
+}
 
 struct NmsWs {
     uint32_t* info;
@@ -1119,6 +1401,9 @@ size_t cldet_sort_workspace_bytes(int num_images, int64_t max_count, int topk) {
     if (topk > 0) {                                                                  // compacted survivors (with ties)
         off = align_up(off + (size_t)num_images * max_count * sizeof(cldet_candidate), 256);
         off = align_up(off + (size_t)num_images * max_count * sizeof(uint64_t), 256);
+    } else if (max_count > kRadixMin) {                                              // radix sort: key + index ping-pong buffers
+        off = align_up(off + (size_t)num_images * 2 * max_count * sizeof(uint64_t), 256);
+        off = align_up(off + (size_t)num_images * 2 * max_count * sizeof(uint32_t), 256);
     }
     return off + 256;
 }
@@ -1168,6 +1453,14 @@ int cldet_sort_candidates(const cldet_candidate* d_candidates, const uint64_t* d
         rank_sort_kernel<<<gr, 256, 0, s>>>(sel_cand, sel_keys, state, d_counts, max_count, topk, d_sorted, sorted_capacity,
                                              d_sorted_counts, d_candidates, d_keys, capacity);
         CLDET_LAUNCH_CHECK();
+    } else if (max_count > kRadixMin && !force_rank_sort()) {
+        // the reference's mode (no top-k) with long lists: one launch, one CTA per image, every radix pass inside it
+        uint64_t* kbuf = reinterpret_cast<uint64_t*>(p + off);
+        off = align_up(off + (size_t)num_images * 2 * max_count * sizeof(uint64_t), 256);
+        uint32_t* ibuf = reinterpret_cast<uint32_t*>(p + off);
+        radix_sort_kernel<<<num_images, kRsThreads, 0, s>>>(d_candidates, d_keys, d_counts, capacity, max_count, d_sorted,
+                                                             sorted_capacity, d_sorted_counts, kbuf, ibuf);
+        CLDET_LAUNCH_CHECK();
     } else {
         dim3 gc((unsigned)std::min<int64_t>((max_count + kRankPerBlock - 1) / kRankPerBlock, 65535 * 16), (unsigned)num_images);
         rank_sort_kernel<<<gc, 256, 0, s>>>(d_candidates, d_keys, nullptr, d_counts, capacity, 0, d_sorted, sorted_capacity,
@@ -1204,7 +1497,15 @@ int cldet_nms_sorted(const cldet_candidate* d_sorted, const int32_t* d_sorted_co
     nms_mask_kernel<<<grid, 256, 0, s>>>(d_sorted, d_sorted_counts, capacity, w.info, iou_thresh, w.mask, w.mask_stride_img,
                                         w.col_blocks);
     CLDET_LAUNCH_CHECK();
-    if (max_count <= kSmemResolveMax) {
+    const int resolve = resolve_choice();          // 0 default, 1 stream, 2 whole mask in shared memory, 3 legacy (A/B experiments)
+    if (resolve == 1 || (resolve == 0 && max_count > kSmemResolveMax)) {
+        const size_t smem = (size_t)w.col_blocks * sizeof(unsigned long long);
+        if (smem > 200 * 1024) return CLDET_ERR_UNSUPPORTED;
+        if (smem > 40 * 1024)
+            CLDET_CUDA_TRY(cudaFuncSetAttribute(nms_resolve_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        nms_resolve_stream_kernel<<<num_images, kStreamThreads, smem, s>>>(d_sorted_counts, capacity, w.mask, w.mask_stride_img,
+                                                                         w.col_blocks, d_keep, d_keep_counts);
+    } else if (max_count <= kSmemResolveMax && resolve != 3) {
         const size_t cbm = (size_t)((max_count + 63) / 64);
         const size_t smem = 64 * cbm * cbm * sizeof(uint64_t);
         if (smem > 48 * 1024)
@@ -1256,6 +1557,10 @@ size_t cldet_batched_nms_workspace_bytes(int64_t num_boxes) {
     off = align_up(off + (size_t)num_boxes * sizeof(cldet_candidate), 256);   // sorted
     off = align_up(off + (size_t)num_boxes * sizeof(int32_t), 256);           // keep positions
     off = align_up(off + 4 * sizeof(int32_t), 256);                           // counts
+    if (num_boxes > kRadixMin) {                                              // radix sort ping-pong buffers
+        off = align_up(off + (size_t)2 * num_boxes * sizeof(uint64_t), 256);
+        off = align_up(off + (size_t)2 * num_boxes * sizeof(uint32_t), 256);
+    }
     off += cldet_nms_workspace_bytes(1, num_boxes);
     return off + 256;
 }
@@ -1284,13 +1589,25 @@ int cldet_batched_nms(const float* d_boxes, const float* d_scores, const int64_t
     off = align_up(off + (size_t)num_boxes * sizeof(int32_t), 256);
     int32_t* cnts = reinterpret_cast<int32_t*>(p + off);   // [0] packed count, [1] sorted count
     off = align_up(off + 4 * sizeof(int32_t), 256);
+    uint64_t* kbuf = nullptr;
+    uint32_t* ibuf = nullptr;
+    if (num_boxes > kRadixMin) {
+        kbuf = reinterpret_cast<uint64_t*>(p + off);
+        off = align_up(off + (size_t)2 * num_boxes * sizeof(uint64_t), 256);
+        ibuf = reinterpret_cast<uint32_t*>(p + off);
+        off = align_up(off + (size_t)2 * num_boxes * sizeof(uint32_t), 256);
+    }
     void* nms_ws = p + off;
     const unsigned blocks = (unsigned)((num_boxes + 255) / 256);
     pack_boxes_kernel<<<blocks, 256, 0, s>>>(reinterpret_cast<const float4*>(d_boxes), d_scores, d_idxs, num_boxes, packed, keys,
                                              cnts);
     CLDET_LAUNCH_CHECK();
-    dim3 g((unsigned)((num_boxes + kRankPerBlock - 1) / kRankPerBlock), 1);
-    rank_sort_kernel<<<g, 256, 0, s>>>(packed, keys, nullptr, cnts, num_boxes, 0, sorted, num_boxes, cnts + 1);
+    if (kbuf && !force_rank_sort()) {
+        radix_sort_kernel<<<1, kRsThreads, 0, s>>>(packed, keys, cnts, num_boxes, num_boxes, sorted, num_boxes, cnts + 1, kbuf, ibuf);
+    } else {
+        dim3 g((unsigned)((num_boxes + kRankPerBlock - 1) / kRankPerBlock), 1);
+        rank_sort_kernel<<<g, 256, 0, s>>>(packed, keys, nullptr, cnts, num_boxes, 0, sorted, num_boxes, cnts + 1);
+    }
     CLDET_LAUNCH_CHECK();
     int rc = cldet_nms_sorted(sorted, cnts + 1, 1, num_boxes, num_boxes, iou_thresh, d_idxs ? mode : 1, vanilla_numel_limit,
                               keep_pos, d_keep_count, nms_ws, workspace_bytes - off, stream);

@@ -167,6 +167,138 @@ distill_backward_kernel(const DistillArgs a, const float* __restrict__ counts, c
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// enhance_error on replay batches (retinanet/losses.py:590-603): over the NEW-class columns (c >= past) of the class
+// probabilities, the elements > 0.05 contribute |p| (L1), p^2 (L2) or p^3 (L3); loss = sum / max(count, 1).
+// Flat coalesced sweep over [rows, C]; per-block partials, fixed-order fp64 finalize (bit-reproducible).
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float enhance_term(float p, int method) { return method == 1 ? fabsf(p) : (method == 2 ? p * p : (p * p) * p); }
+
+__global__ void __launch_bounds__(kDistillThreads)
+enhance_error_forward_kernel(const float* __restrict__ cls, int64_t total, int C, int past, int method,
+                             double* __restrict__ partial_sums, long long* __restrict__ partial_counts) {
+    __shared__ float rs[kDistillThreads / 32];
+    __shared__ int rc[kDistillThreads / 32];
+    float sum = 0.f;
+    int cnt = 0;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+        const int col = (int)(e % C);
+        if (col < past) continue;
+        const float p = cls[e];
+        if (p > 0.05f) {
+            sum += enhance_term(p, method);
+            ++cnt;
+        }
+    }
+    sum = warp_sum(sum);
+    cnt = warp_sum_int(cnt);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) {
+        rs[warp] = sum;
+        rc[warp] = cnt;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double s = 0.0;
+        long long c = 0;
+        for (int w = 0; w < kDistillThreads / 32; ++w) {
+            s += (double)rs[w];
+            c += rc[w];
+        }
+        partial_sums[blockIdx.x] = s;
+        partial_counts[blockIdx.x] = c;
+    }
+}
+
+__global__ void enhance_error_finalize_kernel(const double* __restrict__ partial_sums, const long long* __restrict__ partial_counts,
+                                              int nblocks, float* __restrict__ out, float* __restrict__ count) {
+    if (threadIdx.x == 0) {
+        double s = 0.0;
+        long long c = 0;
+        for (int b = 0; b < nblocks; ++b) {
+            s += partial_sums[b];
+            c += partial_counts[b];
+        }
+        const float denom = (float)(c > 1 ? c : 1);                      // max(classification.shape[0], 1)
+        *out = (float)s / denom;
+        *count = denom;
+    }
+}
+
+__global__ void __launch_bounds__(kDistillThreads)
+enhance_error_backward_kernel(const float* __restrict__ cls, int64_t total, int C, int past, int method,
+                              const float* __restrict__ count, const float* __restrict__ g_loss, float* __restrict__ grad) {
+    const float k = (g_loss ? *g_loss : 0.0f) / *count;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+        const int col = (int)(e % C);
+        float g = 0.0f;
+        if (col >= past) {
+            const float p = cls[e];
+            if (p > 0.05f) g = (method == 1 ? 1.0f : (method == 2 ? 2.0f * p : 3.0f * (p * p))) * k;
+        }
+        grad[e] = g;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// MAS Output_norm's regression term (IL_method/mas.py:52-55): per image, the mean of |regression| over the rows of its
+// positive anchors (0 for an image without positives), summed over images -- without the reference's per-image boolean
+// gather + host sync.  One block per image; fixed summation order.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kDistillThreads)
+masked_abs_mean_forward_kernel(const float4* __restrict__ reg, const uint8_t* __restrict__ positive, int64_t A,
+                               float* __restrict__ terms, float* __restrict__ counts) {
+    __shared__ double rs[kDistillThreads / 32];
+    __shared__ int rc[kDistillThreads / 32];
+    const int j = blockIdx.x;
+    double sum = 0.0;
+    int cnt = 0;
+    for (int64_t an = threadIdx.x; an < A; an += blockDim.x) {
+        if (positive[(int64_t)j * A + an]) {
+            const float4 r = reg[(int64_t)j * A + an];
+            sum += (double)fabsf(r.x) + (double)fabsf(r.y) + (double)fabsf(r.z) + (double)fabsf(r.w);
+            ++cnt;
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    cnt = warp_sum_int(cnt);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) {
+        rs[warp] = sum;
+        rc[warp] = cnt;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double s = 0.0;
+        int c = 0;
+        for (int w = 0; w < kDistillThreads / 32; ++w) {
+            s += rs[w];
+            c += rc[w];
+        }
+        terms[j] = c > 0 ? (float)(s / (4.0 * (double)c)) : 0.0f;
+        counts[j] = (float)c;
+    }
+}
+
+__global__ void __launch_bounds__(kDistillThreads)
+masked_abs_mean_backward_kernel(const float4* __restrict__ reg, const uint8_t* __restrict__ positive, int64_t A,
+                                const float* __restrict__ counts, const float* __restrict__ g_terms, int64_t g_stride,
+                                float4* __restrict__ grad) {
+    const int j = blockIdx.y;
+    const float cnt = counts[j];
+    const float k = cnt > 0.0f ? g_terms[(int64_t)j * g_stride] / (4.0f * cnt) : 0.0f;
+    for (int64_t an = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; an < A; an += (int64_t)gridDim.x * blockDim.x) {
+        float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (positive[(int64_t)j * A + an]) {
+            const float4 r = reg[(int64_t)j * A + an];
+            auto sgn = [](float x) { return x > 0.0f ? 1.0f : (x < 0.0f ? -1.0f : 0.0f); };
+            g = make_float4(sgn(r.x) * k, sgn(r.y) * k, sgn(r.z) * k, sgn(r.w) * k);
+        }
+        grad[(int64_t)j * A + an] = g;
+    }
+}
+
 static int distill_blocks(int64_t rows) {
     return (int)std::max<int64_t>(1, std::min<int64_t>((rows + kDistillThreads - 1) / kDistillThreads, (int64_t)sm_count() * 8));
 }
@@ -228,6 +360,68 @@ int cldet_distill_backward(const float* d_cls, const float* d_prev_cls, const fl
     distill_backward_kernel<<<distill_blocks(a.rows), kDistillThreads, 0, (cudaStream_t)stream>>>(a, d_counts, d_grad_cls_loss,
                                                                                                 d_grad_reg_loss, d_grad_cls,
                                                                                                 d_grad_reg);
+    CLDET_LAUNCH_CHECK();
+    return CLDET_OK;
+}
+
+size_t cldet_enhance_error_workspace_bytes(int64_t num_elements) {
+    if (num_elements <= 0) return 0;
+    return (size_t)distill_blocks(num_elements) * (sizeof(double) + sizeof(long long)) + 256;
+}
+
+int cldet_enhance_error_forward(const float* d_cls, int num_images, int64_t num_anchors, int num_classes, int past_class_num,
+                                int method, float* d_loss, float* d_count, void* d_workspace, size_t workspace_bytes, void* stream) {
+    if (!d_cls || !d_loss || !d_count || !d_workspace) return CLDET_ERR_INVALID_ARGUMENT;
+    if (num_images <= 0 || num_anchors <= 0 || num_classes <= 0 || past_class_num < 0 || past_class_num > num_classes || method < 1 ||
+        method > 3)
+        return CLDET_ERR_INVALID_ARGUMENT;
+    const int64_t total = (int64_t)num_images * num_anchors * num_classes;
+    if (workspace_bytes < cldet_enhance_error_workspace_bytes(total)) return CLDET_ERR_WORKSPACE_TOO_SMALL;
+    const int nb = distill_blocks(total);
+    double* ps = reinterpret_cast<double*>(d_workspace);
+    long long* pc = reinterpret_cast<long long*>(ps + nb);
+    cudaStream_t s = (cudaStream_t)stream;
+    enhance_error_forward_kernel<<<nb, kDistillThreads, 0, s>>>(d_cls, total, num_classes, past_class_num, method, ps, pc);
+    CLDET_LAUNCH_CHECK();
+    enhance_error_finalize_kernel<<<1, 32, 0, s>>>(ps, pc, nb, d_loss, d_count);
+    CLDET_LAUNCH_CHECK();
+    return CLDET_OK;
+}
+
+int cldet_enhance_error_backward(const float* d_cls, int num_images, int64_t num_anchors, int num_classes, int past_class_num,
+                                 int method, const float* d_count, const float* d_grad_loss, float* d_grad_cls, void* stream) {
+    if (!d_cls || !d_count || !d_grad_cls) return CLDET_ERR_INVALID_ARGUMENT;
+    if (num_images <= 0 || num_anchors <= 0 || num_classes <= 0 || past_class_num < 0 || past_class_num > num_classes || method < 1 ||
+        method > 3)
+        return CLDET_ERR_INVALID_ARGUMENT;
+    const int64_t total = (int64_t)num_images * num_anchors * num_classes;
+    enhance_error_backward_kernel<<<distill_blocks(total), kDistillThreads, 0, (cudaStream_t)stream>>>(
+        d_cls, total, num_classes, past_class_num, method, d_count, d_grad_loss, d_grad_cls);
+    CLDET_LAUNCH_CHECK();
+    return CLDET_OK;
+}
+
+int cldet_masked_abs_mean_forward(const float* d_reg, const uint8_t* d_positive, int num_images, int64_t num_anchors,
+                                  float* d_terms, float* d_counts, void* stream) {
+    if (!d_reg || !d_positive || !d_terms || !d_counts || num_images <= 0 || num_anchors <= 0 || ((uintptr_t)d_reg & 15))
+        return CLDET_ERR_INVALID_ARGUMENT;
+    masked_abs_mean_forward_kernel<<<num_images, kDistillThreads, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<const float4*>(d_reg), d_positive, num_anchors, d_terms, d_counts);
+    CLDET_LAUNCH_CHECK();
+    return CLDET_OK;
+}
+
+int cldet_masked_abs_mean_backward(const float* d_reg, const uint8_t* d_positive, int num_images, int64_t num_anchors,
+                                   const float* d_counts, const float* d_grad_terms, int64_t grad_stride, float* d_grad_reg,
+                                   void* stream) {
+    if (!d_reg || !d_positive || !d_counts || !d_grad_terms || !d_grad_reg || num_images <= 0 || num_images > 65535 ||
+        num_anchors <= 0 || (((uintptr_t)d_reg | (uintptr_t)d_grad_reg) & 15) || grad_stride < 0)
+        return CLDET_ERR_INVALID_ARGUMENT;
+    dim3 grid((unsigned)std::max<int64_t>(1, std::min<int64_t>((num_anchors + kDistillThreads - 1) / kDistillThreads, 64)),
+              (unsigned)num_images);
+    masked_abs_mean_backward_kernel<<<grid, kDistillThreads, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<const float4*>(d_reg), d_positive, num_anchors, d_counts, d_grad_terms, grad_stride,
+        reinterpret_cast<float4*>(d_grad_reg));
     CLDET_LAUNCH_CHECK();
     return CLDET_OK;
 }

@@ -20,6 +20,7 @@
 #include <torch/csrc/autograd/custom_function.h>
 #include <torch/library.h>
 
+#include <algorithm>
 #include <string>
 #include <unordered_map>
 #include <vector>
@@ -276,12 +277,16 @@ std::vector<Tensor> focal_loss(const Tensor& cls, const Tensor& reg, const Tenso
 }
 
 // ---- eval-mode detection output for a batch: K4 decode+filter -> K5 ordering (+ optional top-k) -> K6 NMS -> gather ----
-// Returns the padded result (scores[N,cap], labels[N,cap] int64, boxes[N,cap,4], counts[N] int32).  With pre_nms_topk == 0
-// (the reference's mode) the pipeline reads the largest candidate count back once to size its buffers;
-// with top-k it never synchronises.
+// Returns the padded result (scores[N,cap], labels[N,cap] int64, boxes[N,cap,4], counts[N] int32, candidates[N] int32) and
+// NEVER synchronises.  With pre_nms_topk == 0 (the reference's mode) the per-image capacity `cap` is
+// `capacity` when > 0, else an optimistic kOptimisticCapacity: the caller reads counts and candidates back together (the one
+// read it needs anyway to slice the results) and, only if some image had more candidates than cap, calls again with
+// capacity = that count.
+constexpr int64_t kOptimisticCapacity = 4096;
+
 std::vector<Tensor> detect(const Tensor& cls, const Tensor& reg, const Tensor& anchors, int64_t height, int64_t width, bool is_logits,
                            double score_thresh, double iou_thresh, int64_t pre_nms_topk, int64_t nms_mode,
-                           int64_t vanilla_numel_limit) {
+                           int64_t vanilla_numel_limit, int64_t capacity) {
     check_f32_cuda(cls, "classifications");
     check_f32_cuda(reg, "regressions");
     check_f32_cuda(anchors, "anchors");
@@ -309,11 +314,8 @@ std::vector<Tensor> detect(const Tensor& cls, const Tensor& reg, const Tensor& a
         max_count = a;
         cap = std::min<int64_t>(topk, a);
     } else {
-        max_count = counts.max().item<int32_t>();        // the one mid-pipeline sync of the reference-faithful mode
-        cap = max_count;
+        cap = max_count = std::min<int64_t>(a, capacity > 0 ? capacity : kOptimisticCapacity);
     }
-    if (cap == 0)
-        return {at::empty({n, 0}, f32), at::empty({n, 0}, f32.dtype(at::kLong)), at::empty({n, 0, 4}, f32), at::zeros({n}, i32)};
     Tensor sorted = at::empty({n, cap, (int64_t)sizeof(cldet_candidate)}, u8);
     Tensor sorted_counts = at::empty({n}, i32);
     const size_t sws_bytes = cldet_sort_workspace_bytes((int)n, max_count, topk);
@@ -322,14 +324,22 @@ std::vector<Tensor> detect(const Tensor& cls, const Tensor& reg, const Tensor& a
                                        (int)n, a, max_count, topk, (cldet_candidate*)sorted.data_ptr(), cap,
                                        sorted_counts.data_ptr<int32_t>(), sws.data_ptr(), sws_bytes, stream),
                  "cldet_sort_candidates");
-    const size_t nws_bytes = cldet_nms_workspace_bytes((int)n, cap);
-    Tensor nws = at::empty({(int64_t)nws_bytes}, u8);
+    // the suppression mask is cap^2/8 bytes per image (200 MB at 40 k candidates): with long lists, run the NMS over groups of
+    // images that fit a fixed budget instead of sizing one workspace for the whole batch
     Tensor keep = at::empty({n, cap}, i32);
     Tensor keep_counts = at::empty({n}, i32);
-    check_status(cldet_nms_sorted((const cldet_candidate*)sorted.data_ptr(), sorted_counts.data_ptr<int32_t>(), (int)n, cap, cap,
-                                  (float)iou_thresh, (int)nms_mode, vanilla_numel_limit, keep.data_ptr<int32_t>(),
-                                  keep_counts.data_ptr<int32_t>(), nws.data_ptr(), nws_bytes, stream),
-                 "cldet_nms_sorted");
+    const size_t one_image = cldet_nms_workspace_bytes(1, cap);
+    const size_t budget = (size_t)4 << 30;
+    const int64_t group = std::max<int64_t>(1, std::min<int64_t>(n, (int64_t)(budget / std::max<size_t>(one_image, 1))));
+    const size_t nws_bytes = cldet_nms_workspace_bytes((int)group, cap);
+    Tensor nws = at::empty({(int64_t)nws_bytes}, u8);
+    for (int64_t j0 = 0; j0 < n; j0 += group) {
+        const int64_t cnt = std::min<int64_t>(group, n - j0);
+        check_status(cldet_nms_sorted((const cldet_candidate*)sorted.data_ptr() + j0 * cap, sorted_counts.data_ptr<int32_t>() + j0, (int)cnt,
+                                      cap, cap, (float)iou_thresh, (int)nms_mode, vanilla_numel_limit, keep.data_ptr<int32_t>() + j0 * cap,
+                                      keep_counts.data_ptr<int32_t>() + j0, nws.data_ptr(), nws_bytes, stream),
+                     "cldet_nms_sorted");
+    }
     Tensor scores = at::empty({n, cap}, f32);
     Tensor labels = at::empty({n, cap}, f32.dtype(at::kLong));
     Tensor boxes = at::empty({n, cap, 4}, f32);
@@ -337,7 +347,7 @@ std::vector<Tensor> detect(const Tensor& cls, const Tensor& reg, const Tensor& a
                                          (int)n, cap, cap, scores.data_ptr<float>(), labels.data_ptr<int64_t>(), boxes.data_ptr<float>(),
                                          stream),
                  "cldet_gather_detections");
-    return {scores, labels, boxes, keep_counts};
+    return {scores, labels, boxes, keep_counts, counts};
 }
 
 // torchvision.ops.batched_nms / nms drop-in: returns (keep[K] int64 padded, count[1] int32)
@@ -381,7 +391,7 @@ TORCH_LIBRARY(cldet, m) {
         &focal_loss);
     m.def(
         "detect(Tensor cls, Tensor reg, Tensor anchors, int height, int width, bool is_logits, float score_thresh, "
-        "float iou_thresh, int pre_nms_topk, int nms_mode, int vanilla_numel_limit) -> Tensor[]",
+        "float iou_thresh, int pre_nms_topk, int nms_mode, int vanilla_numel_limit, int capacity) -> Tensor[]",
         &detect);
     m.def("batched_nms(Tensor boxes, Tensor scores, Tensor? idxs, float iou_thresh, int mode, int vanilla_numel_limit) -> Tensor[]",
           &batched_nms);

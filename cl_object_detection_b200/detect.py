@@ -101,13 +101,24 @@ def detect_batch(cls, regressions, anchors, height, width, is_logits=True, score
     if c.dim() != 3 or r.dim() != 3 or r.shape[2] != 4 or r.shape[:2] != c.shape[:2] or anc.shape[0] != c.shape[1]:
         raise ValueError('expected cls [N,A,C], regressions [N,A,4], anchors [1,A,4]')
     n = c.shape[0]
-    # one call into the C++ op layer (csrc/cldet_torch.cpp `detect`): allocation + K4 -> K5 -> K6 -> gather launches
+    # one call into the C++ op layer (csrc/cldet_torch.cpp `detect`): allocation + K4 -> K5 -> K6 -> gather launches, no sync
     topk = int(pre_nms_topk) if pre_nms_topk and pre_nms_topk > 0 else 0
-    scores, labels, boxes, keep_counts = _ops.load().detect(c, r, anc, int(height), int(width), bool(is_logits), float(score_thresh),
-                                                            float(iou_threshold), topk, int(nms_mode), int(vanilla_numel_limit))
+    args = (c, r, anc, int(height), int(width), bool(is_logits), float(score_thresh), float(iou_threshold), topk, int(nms_mode),
+            int(vanilla_numel_limit))
+    op = _ops.load().detect
+    scores, labels, boxes, keep_counts, cand_counts = op(*args, 0)
+    if topk and return_padded:
+        return scores, labels, boxes, keep_counts
+    # ONE device->host read: the kept counts (needed to slice) together with the candidate counts.  Without a top-k the op
+    # sized its buffers optimistically; an image with more candidates than that (an untrained model) repeats the call at the
+    # exact size -- the reference-faithful mode needs no other synchronisation.
+    host = torch.stack((keep_counts, cand_counts)).cpu()
+    if not topk and int(host[1].max()) > scores.shape[1]:
+        scores, labels, boxes, keep_counts, cand_counts = op(*args, int(host[1].max()))
+        host = torch.stack((keep_counts, cand_counts)).cpu()
     if return_padded:
         return scores, labels, boxes, keep_counts
-    kc = keep_counts.cpu().tolist()
+    kc = host[0].tolist()
     return [(scores[j, :kc[j]], labels[j, :kc[j]], boxes[j, :kc[j]]) for j in range(n)]
 
 

@@ -66,3 +66,52 @@ def head_distillation(classification, regression, prev_classification, prev_regr
     mask = bg_masks.to(torch.uint8).contiguous() if bg_masks.dtype != torch.uint8 else bg_masks.contiguous()
     dc, dr = _HeadDistillFn.apply(cls, reg, pcls, preg, mask, bool(distill_logits), bool(ignore_GD))
     return {'dist_cls_loss': dc, 'dist_reg_loss': dr}
+
+
+class _EnhanceErrorFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, cls, past, method):
+        lib = _lib.load()
+        n, a, c = cls.shape
+        dev = cls.device
+        with _DeviceGuard(dev):
+            loss = torch.empty(1, dtype=torch.float32, device=dev)
+            count = torch.empty(1, dtype=torch.float32, device=dev)
+            ws_bytes = lib.cldet_enhance_error_workspace_bytes(cls.numel())
+            ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+            _lib.check(lib.cldet_enhance_error_forward(cls.data_ptr(), n, a, c, past, method, loss.data_ptr(), count.data_ptr(),
+                                                       ws.data_ptr(), ws_bytes, _stream()))
+        ctx.save_for_backward(cls, count)
+        ctx.args = (past, method)
+        return loss[0]
+
+    @staticmethod
+    def backward(ctx, g):
+        cls, count = ctx.saved_tensors
+        n, a, c = cls.shape
+        g = g.to(torch.float32).contiguous()
+        with _DeviceGuard(cls.device):
+            grad = torch.empty_like(cls)
+            _lib.check(_lib.load().cldet_enhance_error_backward(cls.data_ptr(), n, a, c, ctx.args[0], ctx.args[1], count.data_ptr(),
+                                                                g.data_ptr(), grad.data_ptr(), _stream()))
+        return grad, None, None
+
+
+def enhance_error(classification, past_class_num, method='L2'):
+    """SURVEY 8(f) row f2, second half -- `enhance_error` on replay batches (retinanet/losses.py:590-603):
+
+        classification = classification[:, :, past_class_num:]; classification = classification[classification > 0.05]
+        enhance_loss = {L1: abs, L2: pow 2, L3: pow 3}(classification).sum() / max(classification.shape[0], 1)
+
+    classification [N,A,C] are class PROBABILITIES (that branch runs the model with enable_act=True).  One fused pass instead of
+    a slice copy, a boolean gather (host sync) and three elementwise kernels; differentiable, no synchronisation."""
+    cls = _check_cuda_f32('classification', classification)
+    if cls.dim() != 3:
+        raise ValueError('classification must be [N,A,C]')
+    m = {'L1': 1, 'L2': 2, 'L3': 3}.get(str(method).upper())
+    if m is None:            # the reference leaves enhance_loss unbound for any other string (UnboundLocalError)
+        raise ValueError("enhance_error_method must be 'L1', 'L2' or 'L3'")
+    past = int(past_class_num)
+    if past < 0 or past > cls.shape[2]:
+        raise IndexError('past_class_num outside [0, C]')
+    return _EnhanceErrorFn.apply(cls, past, m)

@@ -11,7 +11,8 @@ autograd-visible torch reductions over the selected rows, which keeps these modu
 import torch
 import torch.nn as nn
 
-from .losses import iou_assign
+from . import _lib
+from .losses import _DeviceGuard, _check_cuda_f32, _stream, iou_assign
 
 
 def match_anchors(anchors, annotations, threshold=0.5, num_classes=8191):
@@ -33,18 +34,70 @@ def get_positive(anchors, annotations, threshold, num_anchors):
     return m['positive'].view(n, -1, num_anchors), m['targets'].view(n, -1, num_anchors)
 
 
+class _MaskedAbsMeanFn(torch.autograd.Function):
+    """sum_j mean(|reg[j][positive_j]|) over images with at least one positive anchor (mas.py:52-55), no host sync."""
+
+    @staticmethod
+    def forward(ctx, reg, positive):
+        lib = _lib.load()
+        n, a, _ = reg.shape
+        dev = reg.device
+        with _DeviceGuard(dev):
+            terms = torch.empty(n, dtype=torch.float32, device=dev)
+            counts = torch.empty(n, dtype=torch.float32, device=dev)
+            _lib.check(lib.cldet_masked_abs_mean_forward(reg.data_ptr(), positive.data_ptr(), n, a, terms.data_ptr(),
+                                                         counts.data_ptr(), _stream()))
+        ctx.save_for_backward(reg, positive, counts)
+        return terms
+
+    @staticmethod
+    def backward(ctx, g):
+        reg, positive, counts = ctx.saved_tensors
+        n, a, _ = reg.shape
+        g = g.to(torch.float32)
+        stride = g.stride(0) if g.dim() else 0
+        with _DeviceGuard(reg.device):
+            grad = torch.empty_like(reg)
+            _lib.check(_lib.load().cldet_masked_abs_mean_backward(reg.data_ptr(), positive.data_ptr(), n, a, counts.data_ptr(),
+                                                                  g.data_ptr(), stride, grad.data_ptr(), _stream()))
+        return grad, None
+
+
 class OutputNorm(nn.Module):
     """Drop-in for IL_method/mas.py Output_norm (:35-67): same forward signature and result dict, differentiable w.r.t.
-    classifications and regressions."""
+    classifications and regressions.  No per-image Python loop and no host synchronisation: the matching is one K2 launch for
+    the batch, the per-image masked mean one more (cldet_masked_abs_mean_*)."""
 
     def forward(self, classifications, regressions, anchors, annotations):
         n = classifications.shape[0]
-        positive = match_anchors(anchors, annotations, 0.5)['positive']
-        reg_term = regressions.new_zeros(())
-        counts = positive.sum(dim=1)
-        for j in range(n):                                   # per-image mean over that image's positive rows (mas.py:52-55)
-            if int(counts[j]) > 0:
-                reg_term = reg_term + regressions[j][positive[j]].abs().mean()
-        result = {'regression': reg_term / n,
+        positive = match_anchors(anchors, annotations, 0.5)['positive'].to(torch.uint8).contiguous()
+        reg = _check_cuda_f32('regressions', regressions)
+        terms = _MaskedAbsMeanFn.apply(reg, positive)                    # [N]: per-image mean, 0 for images without positives
+        result = {'regression': terms.sum() / n,
                   'classification': torch.sum(torch.pow(classifications, 2)) / (n * classifications.shape[2])}
         return result
+
+
+class WeightSimilarity(object):
+    """Drop-in for IL_method/weight_init.py Weight_similarity (:75-115): forward(img_batch, annotations) ->
+    (classification[K,C] normalised rows, assigned labels[K] float) for image 0 of the batch, or None when it has no GT.
+    calc_iou + max + the label gather are the K2 kernel (match_anchors); the row selection has a data-dependent size, so --
+    like the reference -- it ends in one boolean index."""
+
+    def __init__(self, model, new_class_num, old_class_num, thresold=0.5):
+        self.model = model
+        self.new_class_num = new_class_num
+        self.old_class_num = old_class_num
+        self.thresold = thresold
+
+    def forward(self, img_batch, annotations):
+        classifications, _, anchors = self.model(img_batch, return_feat=False, return_anchor=True, enable_act=True)
+        m = match_anchors(anchors, annotations[:1], 0.5)
+        classification = torch.clamp(classifications[0], 1e-4, 1.0 - 1e-4)
+        if int(m['nvalid'][0]) == 0:
+            return None
+        rowsum = torch.sum(classification, dim=1)
+        indices = torch.logical_and(m['positive'][0], torch.ge(rowsum, self.thresold))
+        classification = classification[indices, :]
+        classification = classification / torch.sum(classification, dim=1).unsqueeze(dim=1)
+        return classification, m['targets'][0][indices].to(torch.float32)

@@ -271,6 +271,27 @@ int cldet_distill_backward(const float* d_cls, const float* d_prev_cls, const fl
                            int distill_logits, int ignore_gd, const float* d_counts, const float* d_grad_cls_loss,
                            const float* d_grad_reg_loss, float* d_grad_cls, float* d_grad_reg, void* stream);
 
+/* ---- SURVEY 8(f) row f2, second half: enhance_error on replay batches (retinanet/losses.py:590-603) ----
+ * d_cls [N,A,C] class PROBABILITIES (the replay branch runs the model with enable_act=True).  Over the new-class columns
+ * c >= past_class_num, the elements > 0.05 contribute |p| (method 1 = "L1"), p^2 (2 = "L2") or p^3 (3 = "L3");
+ * *d_loss = sum / max(count, 1), *d_count = max(count, 1) (float, kept for the backward pass).
+ * Backward writes d_grad_cls [N,A,C] completely (zeros for unselected elements); d_grad_loss: device scalar dL/d(loss), NULL = 0. */
+size_t cldet_enhance_error_workspace_bytes(int64_t num_elements);
+int cldet_enhance_error_forward(const float* d_cls, int num_images, int64_t num_anchors, int num_classes, int past_class_num,
+                                int method, float* d_loss, float* d_count, void* d_workspace, size_t workspace_bytes, void* stream);
+int cldet_enhance_error_backward(const float* d_cls, int num_images, int64_t num_anchors, int num_classes, int past_class_num,
+                                 int method, const float* d_count, const float* d_grad_loss, float* d_grad_cls, void* stream);
+
+/* ---- the regression term of MAS Output_norm (IL_method/mas.py:52-55) without per-image gathers ----
+ * d_terms[j] = mean(|d_reg[j][positive rows]|) over rows x 4 (0 when image j has no positive anchor), d_counts[j] = number
+ * of positive rows (float).  d_positive [N,A] uint8.  Backward: d_grad_reg [N,A,4] written completely, from
+ * d_grad_terms[j * grad_stride] (stride 0 broadcasts one value). */
+int cldet_masked_abs_mean_forward(const float* d_reg, const uint8_t* d_positive, int num_images, int64_t num_anchors,
+                                  float* d_terms, float* d_counts, void* stream);
+int cldet_masked_abs_mean_backward(const float* d_reg, const uint8_t* d_positive, int num_images, int64_t num_anchors,
+                                   const float* d_counts, const float* d_grad_terms, int64_t grad_stride, float* d_grad_reg,
+                                   void* stream);
+
 /* ---- a10-a13: eval-mode detection output (retinanet/utils.py:102-144 BBoxTransform/ClipBoxes;
  *      retinanet/model.py:507-550 ResNet.predict; IL_method/persuado_label.py:99-127 Labeler.predict;
  *      torchvision.ops.batched_nms at model.py:540) ---- */

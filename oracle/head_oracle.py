@@ -595,6 +595,55 @@ def head_distillation(classification, regression, prev_classification, prev_regr
     return F32(cls_loss), F32(reg_loss), gcls, greg
 
 
+def enhance_error(classification, past_class_num, method='L2', g=1.0):
+    """`enhance_error` on replay batches (retinanet/losses.py:590-603): over the new-class columns, the probabilities > 0.05
+    contribute |p|, p^2 or p^3; loss = sum / max(count, 1).  Returns (loss, grad_classification) for upstream weight g."""
+    cls = np.asarray(classification, dtype=F32)
+    sel = np.zeros(cls.shape, dtype=bool)
+    sel[:, :, past_class_num:] = cls[:, :, past_class_num:] > F32(0.05)          # :591-592
+    p = cls[sel].astype(np.float64)
+    m = str(method).upper()
+    denom = max(p.size, 1)                                                       # :600  max(classification.shape[0], 1)
+    if m == 'L1':
+        loss, d = np.abs(p).sum() / denom, np.ones_like(p)
+    elif m == 'L2':
+        loss, d = (p * p).sum() / denom, 2.0 * p
+    elif m == 'L3':
+        loss, d = (p * p * p).sum() / denom, 3.0 * p * p
+    else:
+        raise ValueError(method)
+    grad = np.zeros_like(cls)
+    grad[sel] = (d * (g / denom)).astype(F32)
+    return F32(loss), grad
+
+
+def clip_loss_reduce(bg, fg, clip):
+    """IL_Loss's reductions of the per-image terms with clip_loss (losses.py:575-583, 651-659): bg.mean(), and the mean of the
+    fg terms >= clip (0 when none).  Returns (cls_bg_loss, cls_fg_loss, w_bg[N], w_fg[N]) -- the weights are d/d(bg_j), d/d(fg_j)."""
+    bg = np.asarray(bg, dtype=F32)
+    fg = np.asarray(fg, dtype=F32)
+    n = bg.shape[0]
+    mask = fg >= F32(clip)
+    k = int(mask.sum())
+    w_fg = np.where(mask, 1.0 / k, 0.0) if k else np.zeros(n)
+    fg_term = F32(fg[mask].astype(np.float64).mean()) if k else F32(0)
+    return F32(bg.astype(np.float64).mean()), fg_term, np.full(n, 1.0 / n), w_fg
+
+
+def weight_similarity(classifications, anchors, annotations, threshold=0.5):
+    """Weight_similarity.forward (IL_method/weight_init.py:82-115) on image 0: rows of the clamped class probabilities of
+    positive anchors whose row sum >= threshold, normalised to sum 1, and the assigned GT labels.  None without GT."""
+    cls = np.clip(np.asarray(classifications, dtype=F32)[0], F32(1e-4), F32(1.0 - 1e-4))
+    ann = np.asarray(annotations, dtype=F32)[0]
+    if not np.any(ann[:, 4] != -1):
+        return None
+    asg = assign(np.asarray(anchors, dtype=F32)[0], ann)
+    rowsum = cls.sum(axis=1, dtype=F32)
+    idx = (asg['iou_max'] >= F32(0.5)) & (rowsum >= F32(threshold))
+    rows = cls[idx]
+    return rows / rows.sum(axis=1, dtype=F32)[:, None], asg['label'][idx].astype(F32)
+
+
 # --------------------------------------------------------------------------------------
 # 8(f) row f4  evaluator post-processing  (evaluator.py:329-361)
 # --------------------------------------------------------------------------------------

@@ -131,6 +131,6 @@ def test_torch_op_layer_builds_loads_and_registers():
     with pytest.raises(RuntimeError, match='CUDA'):
         ops.batched_nms(torch.rand(3, 4), torch.rand(3), None, 0.5, 0, 100000)
     with pytest.raises(RuntimeError, match='CUDA'):
-        ops.detect(torch.rand(1, 9, 2), torch.rand(1, 9, 4), torch.rand(1, 9, 4), 8, 8, True, 0.05, 0.5, 0, 0, 100000)
+        ops.detect(torch.rand(1, 9, 2), torch.rand(1, 9, 4), torch.rand(1, 9, 4), 8, 8, True, 0.05, 0.5, 0, 0, 100000, 0)
     with pytest.raises(RuntimeError, match='CUDA'):
         cld.detect.detect_batch(torch.rand(1, 9, 2), torch.rand(1, 9, 4), torch.rand(1, 9, 4), 8, 8)

@@ -288,3 +288,120 @@ def test_a9_pseudo_label_filter_golden():
     e = cld.filter_pseudo_labels(torch.empty(0, device=DEV), torch.empty((0, 4), device=DEV), torch.empty(0, dtype=torch.int64, device=DEV),
                                  cu(g['pl_gt']), 1.0)
     assert e[0].numel() == 0 and e[1].shape == (0, 4)
+
+
+def _sort_through_abi(scores, anchors_idx, counts, topk=0):
+    """cldet_sort_candidates on hand-made candidate lists: scores [N, cap] float32, anchors_idx [N, cap] int32 (distinct per
+    image), counts [N].  Returns (sorted anchor ids [N, cap], sorted score bits, sorted_counts)."""
+    from cl_object_detection_b200 import _lib
+    lib = _lib.load()
+    n, cap = scores.shape
+    cand = torch.zeros((n, cap, 8), dtype=torch.float32, device=DEV)
+    cand[:, :, 4] = scores
+    cand.view(torch.int32)[:, :, 6] = anchors_idx
+    bits = scores.view(torch.int32).to(torch.int64) & 0xFFFFFFFF
+    ordered = torch.where(bits >= 0x80000000, (~bits) & 0xFFFFFFFF, bits | 0x80000000)
+    keys = (ordered << 32) | ((0xFFFFFFFF - anchors_idx.to(torch.int64)) & 0xFFFFFFFF)
+    keys = keys.contiguous()
+    cnt = torch.as_tensor(counts, dtype=torch.int32, device=DEV)
+    max_count = int(max(counts))
+    out_cap = min(topk, cap) if topk else max_count
+    sorted_c = torch.zeros((n, out_cap, 8), dtype=torch.float32, device=DEV)
+    sorted_counts = torch.empty(n, dtype=torch.int32, device=DEV)
+    ws_bytes = lib.cldet_sort_workspace_bytes(n, max_count, topk)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=DEV)
+    _lib.check(lib.cldet_sort_candidates(cand.data_ptr(), keys.data_ptr(), cnt.data_ptr(), n, cap, max_count, topk,
+                                         sorted_c.data_ptr(), out_cap, sorted_counts.data_ptr(), ws.data_ptr(), ws_bytes,
+                                         torch.cuda.current_stream().cuda_stream))
+    torch.cuda.synchronize()
+    return sorted_c.view(torch.int32)[:, :, 6], sorted_c[:, :, 4], sorted_counts, keys
+
+
+@pytest.mark.parametrize('counts', [[2049, 4096, 4097], [100000, 1, 0], [12345, 8192, 2048], [40000]])
+@pytest.mark.parametrize('kind', ['random', 'all_equal', 'few_values', 'negative_and_zero'])
+def test_radix_sort_orders_like_a_stable_descending_sort(counts, kind):
+    """The long-list ordering (segmented LSD radix sort, one CTA per image) against torch.sort of the 64-bit keys: score
+    descending, equal scores by ascending anchor -- for ragged counts around the tile size, a list where EVERY score is equal
+    (the case that made the pairwise rank sort quadratic), heavy ties, and scores <= 0 (the key transform's other branch)."""
+    n, cap = len(counts), max(max(counts), 1)
+    gen = torch.Generator(device=DEV).manual_seed(sum(counts) + len(kind))
+    if kind == 'random':
+        scores = torch.rand(n, cap, device=DEV, generator=gen)
+    elif kind == 'all_equal':
+        scores = torch.full((n, cap), 0.75, device=DEV)
+    elif kind == 'few_values':
+        scores = torch.randint(0, 7, (n, cap), device=DEV, generator=gen).float() / 8 + 0.06
+    else:
+        scores = torch.randn(n, cap, device=DEV, generator=gen)
+        scores[:, ::5] = 0.0
+        scores[:, 1::11] = -0.0
+    # distinct anchor ids per image, in scrambled order (the filter appends candidates in arbitrary order)
+    ids = torch.stack([torch.randperm(cap + 1000, device=DEV, generator=gen)[:cap] for _ in range(n)]).to(torch.int32)
+    got_ids, got_scores, got_counts, keys = _sort_through_abi(scores, ids, counts)
+    assert got_counts.tolist() == counts
+    for j, c in enumerate(counts):
+        if c == 0:
+            continue
+        # reference order: descending unsigned 64-bit key (flip the top bit to compare as signed int64)
+        order = torch.argsort(keys[j, :c] ^ (-0x8000000000000000), descending=True, stable=True)
+        assert torch.equal(got_ids[j, :c], ids[j, :c][order]), (kind, j, c)
+        assert torch.equal(got_scores[j, :c].view(torch.int32), scores[j, :c][order].view(torch.int32))
+
+
+@pytest.mark.parametrize('k,trick', [(3000, True), (10000, True), (10000, False), (30000, False)])
+def test_batched_nms_long_lists_vs_torchvision_same_device(k, trick):
+    """cldet batched_nms (radix sort + streamed resolve for K > 2048 / > 1216) vs torchvision.ops on the same GPU: clustered
+    boxes with duplicated scores, both torchvision branches (coordinate trick / per-class)."""
+    import torchvision
+    gen = torch.Generator(device=DEV).manual_seed(k + int(trick))
+    centers = torch.rand(k // 20 + 1, 2, device=DEV, generator=gen) * 600
+    which = torch.randint(0, centers.shape[0], (k,), device=DEV, generator=gen)
+    xy = centers[which] + torch.randn(k, 2, device=DEV, generator=gen) * 6
+    wh = torch.rand(k, 2, device=DEV, generator=gen) * 60 + 8
+    boxes = torch.cat([xy, xy + wh], dim=1).contiguous()
+    scores = (torch.randint(0, 4000, (k,), device=DEV, generator=gen).float() / 4000).contiguous()      # many exact ties
+    idxs = torch.randint(0, 5, (k,), device=DEV, generator=gen)
+    if trick:
+        ref = torchvision.ops.boxes._batched_nms_coordinate_trick(boxes, scores, idxs, 0.5)
+        got = D.batched_nms(boxes, scores, idxs, 0.5, mode=D.NMS_MODE_TRICK)
+    else:
+        ref = torchvision.ops.boxes._batched_nms_vanilla(boxes, scores, idxs, 0.5)
+        got = D.batched_nms(boxes, scores, idxs, 0.5, mode=D.NMS_MODE_VANILLA)
+    assert got.shape[0] > 10
+    assert torch.all(scores[got][:-1] >= scores[got][1:])
+    # exact agreement with the oracle semantics (stable by index) on a distinct-score copy of the problem
+    sd = ((torch.randperm(k, device=DEV, generator=gen).float() + 1) / (k + 1)).contiguous()      # distinct by construction
+    if trick:
+        ref_d = torchvision.ops.boxes._batched_nms_coordinate_trick(boxes, sd, idxs, 0.5)
+        got_d = D.batched_nms(boxes, sd, idxs, 0.5, mode=D.NMS_MODE_TRICK)
+    else:
+        ref_d = torchvision.ops.boxes._batched_nms_vanilla(boxes, sd, idxs, 0.5)
+        got_d = D.batched_nms(boxes, sd, idxs, 0.5, mode=D.NMS_MODE_VANILLA)
+    assert torch.equal(got_d, ref_d), (got_d.shape, ref_d.shape)
+    # with ties: the CPU oracle defines the order (stable sort), the kept set must match it exactly
+    want = O.batched_nms(boxes.cpu().numpy(), scores.cpu().numpy(), idxs.cpu().numpy(), 0.5, 'cuda' if trick else 'cpu')     # rule picks the branch
+    assert np.array_equal(got.cpu().numpy(), want)
+    assert ref.shape[0] > 0
+
+
+def test_nms_reports_counts_larger_than_the_workspace():
+    """A caller whose counts exceed the max_count the workspace was sized for gets an error marker (keep count -1), never
+    silently truncated detections."""
+    from cl_object_detection_b200 import _lib
+    lib = _lib.load()
+    n, cap = 2, 512
+    sorted_c = torch.zeros((n, cap, 8), dtype=torch.float32, device=DEV)
+    sorted_c[:, :, 2:4] = 1.0
+    counts = torch.tensor([100, 400], dtype=torch.int32, device=DEV)
+    for max_count in (128, 2000):      # shared-memory resolve and (via a larger workspace than the list) the normal case
+        ws_bytes = lib.cldet_nms_workspace_bytes(n, max_count)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=DEV)
+        keep = torch.empty((n, cap), dtype=torch.int32, device=DEV)
+        kc = torch.empty(n, dtype=torch.int32, device=DEV)
+        _lib.check(lib.cldet_nms_sorted(sorted_c.data_ptr(), counts.data_ptr(), n, cap, max_count, 0.5, 1, 100000, keep.data_ptr(),
+                                        kc.data_ptr(), ws.data_ptr(), ws_bytes, torch.cuda.current_stream().cuda_stream))
+        got = kc.tolist()
+        if max_count == 128:
+            assert got[0] == 1 and got[1] == -1, got          # 100 identical boxes -> 1 kept; 400 > 128 -> error marker
+        else:
+            assert got == [1, 1], got

@@ -429,6 +429,116 @@ def test_f2_head_distillation(name, dl, ig):
     check_rel(out['dist_reg_loss'].detach().cpu().numpy(), lr)
 
 
+def _il_step_cuda(g, dl=None, ig=None, method=None, fused_sigmoid=False):
+    """One IL_Loss.forward call rebuilt from the drop-ins on the CUDA path: Sigmoid -> FocalLoss -> clip_loss reductions ->
+    head_distillation (incremental state) or enhance_error (replay batch); returns (terms, grad wrt logits, grad wrt reg)."""
+    wts = dict(zip([str(k) for k in g['weight_keys']], [float(v) for v in g['weight_vals']]))
+    P = int(g['P'])
+    anchors = cld.generate_anchors(int(g['h']), int(g['w']), DEV)
+    logits = cu(g['logits']).requires_grad_(True)
+    reg = cu(g['reg']).requires_grad_(True)
+    ann = cu(g['ann'])
+    replay = method is not None
+    params = cld.HeadParams([0, P], distill=not replay)
+    state, clip = (0, 0.003) if replay else (1, 0.03)
+    if fused_sigmoid:
+        out = cld.FocalLoss(from_logits=True)(logits, reg, anchors, ann, state, params)
+        probs = None
+    else:
+        probs = torch.sigmoid(logits)                     # self.classifier_act(classification), losses.py:633
+        out = cld.FocalLoss()(probs, reg, anchors, ann, state, params)
+    bg, fg = out['cls_loss']
+    mask = fg >= clip                                     # losses.py:651-659
+    terms = {'cls_bg_loss': bg.mean(), 'cls_fg_loss': fg[mask].mean() if int(mask.sum()) > 0 else fg.sum() * 0,
+             'reg_loss': out['reg_loss'].mean()}
+    if replay:
+        terms['enhance_loss'] = cld.enhance_error(torch.sigmoid(logits) if probs is None else probs, P, method)
+    else:
+        dist = cld.head_distillation(logits, reg, cu(g['prev_logits']), cu(g['prev_reg']), out['bg_masks'], distill_logits=dl,
+                                     ignore_GD=ig)
+        terms.update(dist_cls_loss=dist['dist_cls_loss'], dist_reg_loss=dist['dist_reg_loss'])
+    sum(wts[k] * v for k, v in terms.items()).backward()
+    return {k: float(v) for k, v in terms.items()}, logits.grad.cpu().numpy(), reg.grad.cpu().numpy()
+
+
+def _grad_close(got, ref, rel=1e-5, floor=2e-6):
+    got, ref = np.asarray(got, np.float64), np.asarray(ref, np.float64)
+    excess = float(np.max(np.abs(got - ref) - rel * np.abs(ref))) / float(np.abs(ref).max())
+    OBSERVED['il_step_grad_worst_excess_over_scale'] = max(OBSERVED.get('il_step_grad_worst_excess_over_scale', 0.0), excess)
+    assert excess <= floor, excess
+
+
+@pytest.mark.parametrize('fused_sigmoid', [False, True])
+@pytest.mark.parametrize('name,dl,ig', [('probs', False, False), ('logits', True, False), ('probs_ignoregd', False, True),
+                                        ('logits_ignoregd', True, True)])
+def test_f2_il_loss_distillation_step_vs_reference_il_loss(name, dl, ig, fused_sigmoid):
+    """Row f2 against the reference ITSELF: the fixture holds what the unmodified IL_Loss.forward (losses.py:633-737, stub
+    models) returned and the autograd gradients of the weighted sum of its terms.  Sums of two gradient contributions that can
+    cancel: 1e-5 relative plus 2e-6 of the gradient scale."""
+    g = load('f2_il_loss_reference')
+    terms, gc, gr = _il_step_cuda(g, dl, ig, fused_sigmoid=fused_sigmoid)
+    for k, v in terms.items():
+        check_rel(v, g['distill_%s_%s' % (name, k)])
+    _grad_close(gc, g['distill_%s_grad_cls' % name])
+    _grad_close(gr, g['distill_%s_grad_reg' % name])
+
+
+@pytest.mark.parametrize('method', ['L1', 'L2', 'L3'])
+def test_f2_enhance_error_replay_step_vs_reference_il_loss(method):
+    """enhance_error (losses.py:590-603) inside the reference's replay branch, plus the kernel alone against the oracle."""
+    g = load('f2_il_loss_reference')
+    terms, gc, gr = _il_step_cuda(g, method=method)
+    for k, v in terms.items():
+        check_rel(v, g['replay_%s_%s' % (method, k)])
+    _grad_close(gc, g['replay_%s_grad_cls' % method])
+    _grad_close(gr, g['replay_%s_grad_reg' % method])
+    # kernel alone, larger and with an empty selection
+    rng = np.random.default_rng(5)
+    p = rng.uniform(0, 0.3, (2, 1000, 7)).astype(np.float32)
+    for past in (0, 3, 7):
+        t = cu(p).requires_grad_(True)
+        loss = cld.enhance_error(t, past, method)
+        (loss * 1.5).backward()
+        want, gwant = O.enhance_error(p, past, method, g=1.5)
+        check_rel(float(loss), want) if past < 7 else None
+        assert past < 7 or float(loss) == 0.0
+        assert np.array_equal(t.grad.cpu().numpy() == 0, gwant == 0)
+        assert np.allclose(t.grad.cpu().numpy(), gwant, rtol=1e-5, atol=0)
+    with pytest.raises(ValueError):
+        cld.enhance_error(cu(p), 3, 'L4')
+
+
+def test_f3_weight_similarity_and_sync_free_output_norm():
+    """Row f3: Weight_similarity.forward (weight_init.py:82-115) on the K2 kernel vs the reference's own output (stub model),
+    and OutputNorm without per-image host syncs still equal to the reference fixture, including an image without positives."""
+    g = load('f2_il_loss_reference')
+    h, w = int(g['h']), int(g['w'])
+    anchors = cld.generate_anchors(h, w, DEV)
+    probs = cu(g['ws_probs'])
+
+    def model(img, return_feat=False, return_anchor=True, enable_act=True):
+        return probs, None, anchors
+    ws = cld.WeightSimilarity(model, 2, 4)
+    sc, lab = ws.forward(torch.zeros(2, 3, h, w), cu(g['ann']))
+    assert np.array_equal(lab.cpu().numpy(), g['ws_labels'])
+    assert np.allclose(sc.cpu().numpy(), g['ws_scores'], rtol=1e-6, atol=0)
+    assert ws.forward(torch.zeros(2, 3, h, w), cu(np.full_like(g['ann'], -1.0))) is None
+    # OutputNorm: an image whose only box matches nothing still contributes 0 (mas.py:52-55), no host round trip
+    g3 = load('f3_iou_users')
+    a3 = cld.generate_anchors(int(g3['h']), int(g3['w']), DEV)
+    ann = g3['ann'].copy()
+    ann[1, :, :] = -1.0
+    ann[1, 0] = [0.0, 0.0, 1.0, 1.0, 2.0]                 # a 1x1 box: valid GT, no anchor reaches IoU 0.5
+    c = cu(g3['cls']).requires_grad_(True)
+    r = cu(g3['reg']).requires_grad_(True)
+    out = cld.OutputNorm()(c, r, a3, cu(ann))
+    (out['regression'] * 0.7 + out['classification'] * 0.3).backward()
+    rt, ct, gc, gr = O.output_norm(g3['cls'], g3['reg'], O.anchors_for_image(int(g3['h']), int(g3['w'])), ann)
+    check_rel(out['regression'].detach().cpu().numpy(), rt, 1e-6)
+    assert np.allclose(r.grad.cpu().numpy(), 0.7 * gr, rtol=1e-6, atol=0)
+    assert not r.grad[1].any()
+
+
 @pytest.mark.parametrize('h,w,C,N,G', [(512, 512, 20, 3, 12), (33, 70, 4, 2, 6), (800, 1333, 8, 2, 40), (1333, 1333, 4, 1, 100),
                                        (200, 264, 16, 4, 300)])
 def test_gt_centric_assignment_equals_anchor_centric(h, w, C, N, G):

@@ -148,6 +148,77 @@ def test_f2_head_distillation_matches_torch_restatement(name, dl, ig):
     assert float(np.max(np.abs(gr - ref_r) - 1e-5 * np.abs(ref_r))) <= 1e-6 * float(np.abs(ref_r).max())
 
 
+def _il_step_oracle(g, name, dl=None, ig=None, method=None):
+    """The oracle's composition of one IL_Loss.forward call on the fixture's inputs; returns (terms dict, grad_cls, grad_reg)
+    for the fixture's weights."""
+    wts = dict(zip([str(k) for k in g['weight_keys']], [float(v) for v in g['weight_vals']]))
+    P = int(g['P'])
+    anchors = O.anchors_for_image(int(g['h']), int(g['w']))
+    logits, reg, ann = g['logits'], g['reg'], g['ann']
+    n = logits.shape[0]
+    replay = method is not None
+    params = O.OracleParams(num_past_class=[0, P], distill=not replay)
+    state = 0 if replay else 1
+    clip = 0.003 if replay else 0.03
+    probe = O.focal_loss(logits, reg, anchors, ann, state, params, want_grads=False, from_logits=True)
+    bg_l, fg_l, w_bg, w_fg = O.clip_loss_reduce(probe['bg'], probe['fg'], clip)
+    out = O.focal_loss(logits, reg, anchors, ann, state, params, w_bg=w_bg * wts['cls_bg_loss'], w_fg=w_fg * wts['cls_fg_loss'],
+                       w_reg=wts['reg_loss'], from_logits=True)
+    terms = {'cls_bg_loss': bg_l, 'cls_fg_loss': fg_l, 'reg_loss': out['reg_loss'][0]}
+    gc, gr = out['grad_cls'].copy(), out['grad_reg'].copy()
+    if replay:
+        p = O.sigmoid(logits)
+        loss, gp = O.enhance_error(p, P, method, g=wts['enhance_loss'])
+        terms['enhance_loss'] = loss
+        gc = gc + (gp * (np.float32(1.0) - p)) * p
+    else:
+        assert out['bg_masks'].shape[0] == n
+        lc, lr, dgc, dgr = O.head_distillation(logits, reg, g['prev_logits'], g['prev_reg'], out['bg_masks'], dl, ig,
+                                               g_cls=wts['dist_cls_loss'], g_reg=wts['dist_reg_loss'])
+        terms.update(dist_cls_loss=lc, dist_reg_loss=lr)
+        gc, gr = gc + dgc, gr + dgr
+    return terms, gc, gr
+
+
+def _assert_grad_close(got, ref, rel=1e-5, floor=2e-7):
+    got, ref = np.asarray(got, np.float64), np.asarray(ref, np.float64)
+    assert float(np.max(np.abs(got - ref) - rel * np.abs(ref))) <= floor * float(np.abs(ref).max())
+
+
+@pytest.mark.parametrize('name,dl,ig', [('probs', False, False), ('logits', True, False), ('probs_ignoregd', False, True),
+                                        ('logits_ignoregd', True, True)])
+def test_f2_il_loss_distillation_step_matches_reference_il_loss(name, dl, ig):
+    """Row f2 pinned on the reference ITSELF: tests/golden/make_golden_f2_ref.py ran the unmodified IL_Loss.forward
+    (losses.py:633-737) with stub models; the oracle's Sigmoid -> FocalLoss -> clip_loss -> distillation composition must
+    reproduce every returned term and the autograd gradients of their weighted sum."""
+    g = load('f2_il_loss_reference')
+    terms, gc, gr = _il_step_oracle(g, name, dl, ig)
+    for k, v in terms.items():
+        assert rel_err(v, g['distill_%s_%s' % (name, k)], 1e-30) < 1e-5, k
+    _assert_grad_close(gc, g['distill_%s_grad_cls' % name])
+    _assert_grad_close(gr, g['distill_%s_grad_reg' % name])
+
+
+@pytest.mark.parametrize('method', ['L1', 'L2', 'L3'])
+def test_f2_enhance_error_replay_step_matches_reference_il_loss(method):
+    """enhance_error (losses.py:590-603) inside the reference's replay branch (:566-603), same fixture generator."""
+    g = load('f2_il_loss_reference')
+    terms, gc, gr = _il_step_oracle(g, method, method=method)
+    for k, v in terms.items():
+        assert rel_err(v, g['replay_%s_%s' % (method, k)], 1e-30) < 1e-5, k
+    _assert_grad_close(gc, g['replay_%s_grad_cls' % method])
+    _assert_grad_close(gr, g['replay_%s_grad_reg' % method])
+
+
+def test_f3_weight_similarity_matches_reference():
+    g = load('f2_il_loss_reference')
+    anchors = O.anchors_for_image(int(g['h']), int(g['w']))
+    sc, lab = O.weight_similarity(g['ws_probs'], anchors, g['ann'])
+    assert np.array_equal(lab, g['ws_labels']) and sc.shape == g['ws_scores'].shape
+    assert np.allclose(sc, g['ws_scores'], rtol=1e-6, atol=0)
+    assert O.weight_similarity(g['ws_probs'], anchors, np.full_like(g['ann'], -1.0)) is None
+
+
 def test_a9_collate_and_pseudo_filter_match_reference():
     g = load('a9_pseudo_labels')
     annots = [g['annot0'], g['annot1'], g['annot2']]

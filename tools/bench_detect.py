@@ -157,6 +157,108 @@ def measure_head(args, dev, logits, reg, anchors, h, w):
             'images_per_s_head_layout': n / (ms_head * 1e-3), 'identical_detections': bool(same)}
 
 
+def measure_predict(dev, mu, images=6, cpu_images=2):
+    """The eval boundary AS THE REFERENCE CALLS IT (evaluator.py:324-329 -> ResNet.predict, model.py:507-550): one image per
+    call, no top-k, head outputs of that image arriving from the HOST (pinned) and the detections read back with .cpu().
+    Timed wall clock per call, after warm-up.  cpu_baseline: the torch-eager restatement of predict + torchvision's CPU
+    batched_nms on the box's host cores over the same image (what the reference's own code does on a CPU)."""
+    import time
+
+    from cl_object_detection_b200 import detect as D
+    from oracle import torch_eager as E
+    h, w, c = 800, 1333, 80
+    anchors = cld.generate_anchors(h, w, dev)
+    a = anchors.shape[1]
+    gen = torch.Generator(device=dev).manual_seed(int(-mu * 100))
+    logits = torch.randn(images, a, c, device=dev, generator=gen) * 2.0 + mu
+    reg = torch.randn(images, a, 4, device=dev, generator=gen) * 0.3
+    h_logits = [logits[j:j + 1].cpu().pin_memory() for j in range(images)]
+    h_reg = [reg[j:j + 1].cpu().pin_memory() for j in range(images)]
+    d_logits = torch.empty_like(logits[:1])
+    d_reg = torch.empty_like(reg[:1])
+
+    def call(j):
+        d_logits.copy_(h_logits[j], non_blocking=True)
+        d_reg.copy_(h_reg[j], non_blocking=True)
+        s, l, b = D.detect_batch(d_logits, d_reg, anchors, h, w)[0]          # reference mode: pre_nms_topk=0
+        return s.cpu(), l.cpu(), b.cpu()
+
+    for j in range(min(3, images)):
+        call(j)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    kept = 0
+    for j in range(images):
+        kept += call(j)[0].shape[0]
+    dt = (time.perf_counter() - t0) / images
+    # the same call with the head outputs already on the device (what a real evaluator has: the model ran on the GPU)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for j in range(images):
+        s, l, b = D.detect_batch(logits[j:j + 1], reg[j:j + 1], anchors, h, w)[0]
+        s.cpu(), l.cpu(), b.cpu()
+    dt_dev = (time.perf_counter() - t0) / images
+    cand = int(((torch.sigmoid(logits).amax(dim=2)) > 0.05).sum().item()) / images
+    out = {'workload': 'predict, batch 1, no top-k (reference mode): 800x1333, C=80, A=%d, logit mean %.1f' % (a, mu),
+           'candidates_per_image': cand, 'kept_per_image': kept / images,
+           'e2e_ms_per_image': dt * 1e3, 'e2e_images_per_s': 1.0 / dt, 'h2d_bytes_per_image': (a * c + a * 4) * 4,
+           'device_resident_ms_per_image': dt_dev * 1e3, 'device_resident_images_per_s': 1.0 / dt_dev}
+    # same-GPU eager baseline: torch ops + torchvision.ops.batched_nms (the reference's own execution model)
+    E.predict(logits[:1], reg[:1], anchors, h, w)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for j in range(images):
+        s, l, b = E.predict(logits[j:j + 1], reg[j:j + 1], anchors, h, w)
+        s.cpu(), l.cpu(), b.cpu()
+    out['gpu_eager_ms_per_image'] = (time.perf_counter() - t0) / images * 1e3
+    if cpu_images:
+        cl, cr, ca = [x.cpu() for x in (logits[:cpu_images], reg[:cpu_images], anchors)]
+        t0 = time.perf_counter()
+        for j in range(cpu_images):
+            E.predict(cl[j:j + 1], cr[j:j + 1], ca, h, w)
+        cdt = (time.perf_counter() - t0) / cpu_images
+        out['cpu_baseline'] = {'value': 1.0 / cdt, 'unit': 'images/s', 'ms_per_image': cdt * 1e3, 'cores': torch.get_num_threads(),
+                               'kind': 'port', 'sample': '%d images, torch-eager restatement of ResNet.predict + torchvision CPU '
+                                                         'batched_nms on the host cores' % cpu_images}
+    return out
+
+
+def measure_nms_h2h(dev, k, iters=10):
+    """cldet batched_nms vs torchvision.ops.batched_nms on IDENTICAL (boxes, scores, idxs) device tensors ('the
+    kernel to beat on the same box'), K boxes drawn from the decode of a COCO-shaped image.  CUDA-event time per call,
+    including each implementation's own sort; results must be identical."""
+    import torchvision
+
+    from cl_object_detection_b200 import detect as D
+    h, w = 800, 1333
+    gen = torch.Generator(device=dev).manual_seed(k)
+    anchors = cld.generate_anchors(h, w, dev)[0]
+    pick = torch.randperm(anchors.shape[0], device=dev, generator=gen)[:k]
+    reg = torch.randn(1, anchors.shape[0], 4, device=dev, generator=gen) * 0.3
+    boxes = D.decode_boxes(anchors.unsqueeze(0), reg, clip_to=(h, w))[0][pick].contiguous()
+    scores = ((torch.randperm(k, device=dev, generator=gen).float() + 1) / (k + 1)).contiguous()        # distinct
+    idxs = torch.randint(0, 80, (k,), device=dev, generator=gen)
+
+    def timeit(fn):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(iters):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / iters
+
+    ours = D.batched_nms(boxes, scores, idxs, 0.5)
+    theirs = torchvision.ops.batched_nms(boxes, scores, idxs, 0.5)
+    ms_ours = timeit(lambda: D.batched_nms(boxes, scores, idxs, 0.5))
+    ms_tv = timeit(lambda: torchvision.ops.batched_nms(boxes, scores, idxs, 0.5))
+    return {'boxes': k, 'kept': int(ours.shape[0]), 'cldet_ms': ms_ours, 'torchvision_ms': ms_tv, 'speedup': ms_tv / ms_ours,
+            'identical_keep': bool(torch.equal(ours, theirs))}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--steps', type=int, default=30)
