@@ -87,6 +87,7 @@ SIGNATURES = {
     'cldet_sort_candidates': (_I, [_P, _P, _P, _I, _L, _L, _I, _P, _L, _P, _P, _Z, _P]),
     'cldet_nms_workspace_bytes': (_Z, [_I, _L]),
     'cldet_nms_sorted': (_I, [_P, _P, _I, _L, _L, _F, _I, _L, _P, _P, _P, _Z, _P]),
+    'cldet_nms_gather_sorted': (_I, [_P, _P, _I, _L, _L, _F, _I, _L, _P, _P, _P, _P, _P, _P, _Z, _P]),
     'cldet_batched_nms_workspace_bytes': (_Z, [_L]),
     'cldet_batched_nms': (_I, [_P, _P, _P, _L, _F, _I, _L, _P, _P, _P, _Z, _P]),
     'cldet_coco_results': (_I, [_P, _P, _P, _P, _P, _I, _L, _F, _P, _P, _P]),

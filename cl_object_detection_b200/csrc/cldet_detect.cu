@@ -472,6 +472,151 @@ select_hist_pick_kernel(const uint64_t* __restrict__ keys, const int32_t* __rest
     }
 }
 
+// The whole top-k SELECT of one image in ONE launch (one CTA per image): state init, the three radix passes on the score
+// bits and the compaction of the survivors.  An image that keeps everything (no top-k, fewer candidates than k, or few enough
+// for the rank sort to order them all) costs one block that returns at once -- the trained-model regime used to pay five
+// launches that did nothing (init + 3 passes + compaction, ~20 us of a 400 us pipeline).  Keys are streamed from L2 with
+// four independent loads per thread; the pick is the same descending cumulative-count walk as select_hist_pick_kernel.
+constexpr int kSelThreads = 1024;
+
+__global__ void __launch_bounds__(kSelThreads)
+select_fused_kernel(const cldet_candidate* __restrict__ cand, const uint64_t* __restrict__ keys, const int32_t* __restrict__ counts,
+                    int64_t capacity, int topk, uint32_t* __restrict__ state, cldet_candidate* __restrict__ out_cand,
+                    uint64_t* __restrict__ out_keys, int64_t out_capacity) {
+    __shared__ uint32_t sh[kSelBins];
+    __shared__ uint32_t part[256];
+    __shared__ uint32_t s_prefix, s_need;
+    __shared__ int warp_tot[kSelThreads / 32];
+    __shared__ int block_base;
+    const int j = blockIdx.x;
+    const int tid = threadIdx.x;
+    uint32_t* st = state + 4 * j;
+    const int64_t cnt = min64(counts[j], capacity);
+    if (topk <= 0 || cnt <= topk || cnt <= kRankDirect) {       // keep everything: the rank sort reads the original arrays
+        if (tid == 0) {
+            st[0] = 0; st[1] = 0; st[2] = 0; st[3] = 1;
+        }
+        return;
+    }
+    if (tid == 0) {
+        s_prefix = 0;
+        s_need = (uint32_t)topk;
+    }
+    const uint64_t* k = keys + (int64_t)j * capacity;
+    const SelPass passes[3] = {{21, 11, 0}, {10, 11, 11}, {0, 10, 22}};
+#pragma unroll 1
+    for (int ps = 0; ps < 3; ++ps) {
+        const SelPass P = passes[ps];
+        const int nb = 1 << P.bits;
+        for (int b = tid; b < kSelBins; b += kSelThreads) sh[b] = 0;
+        __syncthreads();
+        const uint32_t prefix = s_prefix;
+        for (int64_t i0 = 0; i0 < cnt; i0 += 4 * kSelThreads) {
+            uint32_t sc[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int64_t i = i0 + u * kSelThreads + tid;
+                sc[u] = (i < cnt) ? (uint32_t)(k[i] >> 32) : 0u;
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int64_t i = i0 + u * kSelThreads + tid;
+                const bool match = P.hi_bits == 0 || (sc[u] >> (32 - P.hi_bits)) == (prefix >> (32 - P.hi_bits));
+                if (i < cnt && match) atomicAdd(&sh[(sc[u] >> P.shift) & (nb - 1)], 1u);
+            }
+        }
+        __syncthreads();
+        // pick: thread t < 256 owns bins [hi-7, hi], hi = kSelBins-1-8t (descending); suffix scan over the 256 partial sums
+        uint32_t mine = 0;
+        const int hi = kSelBins - 1 - 8 * (tid & 255);
+        if (tid < 256) {
+#pragma unroll
+            for (int q = 0; q < 8; ++q) mine += sh[hi - q];
+            part[tid] = mine;
+        }
+        __syncthreads();
+        for (int off = 1; off < 256; off <<= 1) {
+            uint32_t add = 0;
+            if (tid < 256 && tid >= off) add = part[tid - off];
+            __syncthreads();
+            if (tid < 256) part[tid] += add;
+            __syncthreads();
+        }
+        const uint32_t need0 = s_need;
+        __syncthreads();
+        if (tid < 256) {
+            const uint32_t incl = part[tid], excl = incl - mine;
+            const bool owner = (excl < need0 && incl >= need0) || (tid == 255 && incl < need0);
+            if (owner) {
+                uint32_t need = need0 - excl;
+                int b = hi;
+                for (int q = 0; q < 8; ++q, --b) {
+                    if (sh[b] >= need || b == 0) break;
+                    need -= sh[b];
+                }
+                if (b < 0) b = 0;
+                s_prefix = prefix | ((uint32_t)b << P.shift);
+                s_need = need;
+            }
+        }
+        __syncthreads();
+    }
+    // compaction: every candidate whose score bits reach the k-th score (exact ties included; the ordering pass cuts at k)
+    const uint32_t thr = s_prefix;
+    const int lane = tid & 31, warp = tid >> 5;
+    int written = 0;                                   // block-uniform running total
+    for (int64_t i0 = 0; i0 < cnt; i0 += 4 * kSelThreads) {
+        uint64_t key[4];
+        bool take[4];
+        int mine = 0;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int64_t i = i0 + u * kSelThreads + tid;
+            key[u] = (i < cnt) ? k[i] : 0ull;
+            take[u] = (i < cnt) && (uint32_t)(key[u] >> 32) >= thr;
+            mine += take[u] ? 1 : 0;
+        }
+        int incl = mine;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int v = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += v;
+        }
+        if (lane == 31) warp_tot[warp] = incl;
+        __syncthreads();
+        if (tid == 0) {
+            int tot = 0;
+            for (int w = 0; w < kSelThreads / 32; ++w) {
+                const int c = warp_tot[w];
+                warp_tot[w] = tot;
+                tot += c;
+            }
+            block_base = tot;
+        }
+        __syncthreads();
+        int64_t slot = (int64_t)written + warp_tot[warp] + (incl - mine);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            if (take[u]) {
+                const int64_t i = i0 + u * kSelThreads + tid;
+                if (slot < out_capacity) {
+                    const float4* src = reinterpret_cast<const float4*>(cand + (int64_t)j * capacity + i);
+                    float4* dst = reinterpret_cast<float4*>(out_cand + (int64_t)j * out_capacity + slot);
+                    dst[0] = src[0];
+                    dst[1] = src[1];
+                    out_keys[(int64_t)j * out_capacity + slot] = key[u];
+                }
+                ++slot;
+            }
+        }
+        written += block_base;
+        __syncthreads();
+    }
+    if (tid == 0) {
+        st[0] = thr; st[1] = 0; st[2] = (uint32_t)written; st[3] = 0;
+    }
+}
+
 // survivors: score bits > threshold always; == threshold: all of them (exact ties are cut after the ordering pass).
 // 4 candidates per thread, one atomic per block.
 constexpr int kCompactPerThread = 4;
@@ -916,6 +1061,20 @@ nms_resolve_kernel(const int32_t* __restrict__ counts, int64_t capacity, const u
     if (threadIdx.x == 0) keep_counts[j] = kept_total;
 }
 
+// Tail of the resolve kernels: the block that resolved image j also gathers its kept candidates into the dense outputs
+// (scores / labels / boxes rows of `capacity` entries) -- one launch fewer on a chain that is bound by launch latency.
+__device__ __forceinline__ void gather_image(const cldet_candidate* __restrict__ sorted, const int32_t* __restrict__ keep, int j,
+                                             int64_t capacity, int kept, float* __restrict__ scores, int64_t* __restrict__ labels,
+                                             float4* __restrict__ boxes) {
+    for (int i = threadIdx.x; i < kept; i += blockDim.x) {
+        const float4* rec = reinterpret_cast<const float4*>(sorted + (int64_t)j * capacity + keep[(int64_t)j * capacity + i]);
+        const float4 b = rec[0], t = rec[1];
+        scores[(int64_t)j * capacity + i] = t.x;
+        labels[(int64_t)j * capacity + i] = (int64_t)__float_as_int(t.y);
+        boxes[(int64_t)j * capacity + i] = b;
+    }
+}
+
 // Small-K resolve (K <= kSmemResolveMax, e.g. after the top-1000 stage): the whole block pulls the image's upper-triangular
 // mask (<= 185 KB) into shared memory with independent coalesced loads, then ONE warp runs the sequential part with the
 // "removed" bitmap in registers (lane t owns column word t).  The dependent chain sees no global load and no block barrier:
@@ -927,8 +1086,11 @@ constexpr int kSmemResolveThreads = 1024;
 __global__ void __launch_bounds__(kSmemResolveThreads)
 nms_resolve_smem_kernel(const int32_t* __restrict__ counts, int64_t capacity, const uint64_t* __restrict__ mask,
                         int64_t mask_stride_img, int col_blocks_alloc, int32_t* __restrict__ keep,
-                        int32_t* __restrict__ keep_counts) {
+                        int32_t* __restrict__ keep_counts, const cldet_candidate* __restrict__ sorted = nullptr,
+                        float* __restrict__ out_scores = nullptr, int64_t* __restrict__ out_labels = nullptr,
+                        float4* __restrict__ out_boxes = nullptr) {
     extern __shared__ uint64_t sm_mask[];                                // [64*cb][cb], rows >= n zero
+    __shared__ int kept_total_s;
     const int j = blockIdx.x;
     if (min64(counts[j], capacity) > (int64_t)col_blocks_alloc * 64) {     // more boxes than the mask workspace was sized for
         if (threadIdx.x == 0) keep_counts[j] = -1;                         // report, never truncate silently
@@ -955,7 +1117,7 @@ nms_resolve_smem_kernel(const int32_t* __restrict__ counts, int64_t capacity, co
         }
     }
     __syncthreads();
-    if (threadIdx.x >= 32) return;
+    if (threadIdx.x < 32) {
     const int lane = threadIdx.x;
     uint64_t remv = 0;                                                    // lane t: removed bits of boxes 64t .. 64t+63
     int kept_total = 0;
@@ -995,7 +1157,14 @@ nms_resolve_smem_kernel(const int32_t* __restrict__ counts, int64_t capacity, co
             remv |= v0 | v1;
         }
     }
-    if (lane == 0) keep_counts[j] = kept_total;
+    if (lane == 0) {
+        keep_counts[j] = kept_total;
+        kept_total_s = kept_total;
+    }
+    }
+    if (!out_scores) return;
+    __syncthreads();
+    gather_image(sorted, keep, j, capacity, kept_total_s, out_scores, out_labels, out_boxes);
 }
 
 // Any-K resolve: one CTA per image, the "removed" bitmap in shared memory, and a two-stage software pipeline over the 64-box
@@ -1015,8 +1184,11 @@ constexpr int kStreamUnroll = 8;            // independent loads in flight per a
 __global__ void __launch_bounds__(kStreamThreads)
 nms_resolve_stream_kernel(const int32_t* __restrict__ counts, int64_t capacity, const uint64_t* __restrict__ mask,
                           int64_t mask_stride_img, int col_blocks_alloc, int32_t* __restrict__ keep,
-                          int32_t* __restrict__ keep_counts) {
+                          int32_t* __restrict__ keep_counts, const cldet_candidate* __restrict__ sorted = nullptr,
+                          float* __restrict__ out_scores = nullptr, int64_t* __restrict__ out_labels = nullptr,
+                          float4* __restrict__ out_boxes = nullptr) {
     extern __shared__ unsigned long long removed[];                      // [col_blocks]
+    __shared__ int kept_total_s;
     __shared__ uint64_t diag[2][64];
     __shared__ uint64_t nextb[2][64];
     __shared__ uint64_t kept_s[2];
@@ -1116,7 +1288,13 @@ nms_resolve_stream_kernel(const int32_t* __restrict__ counts, int64_t capacity, 
         }
         __syncthreads();
     }
-    if (tid == 0) keep_counts[j] = kept_total;
+    if (tid == 0) {
+        keep_counts[j] = kept_total;
+        kept_total_s = kept_total;
+    }
+    if (!out_scores) return;
+    __syncthreads();
+    gather_image(sorted, keep, j, capacity, kept_total_s, out_scores, out_labels, out_boxes);
 }
 
 __global__ void __launch_bounds__(256)
@@ -1235,6 +1413,13 @@ static int resolve_choice() {
         if (e[0] == 's' && e[1] == 'm') return 2;
         if (e[0] == 'l') return 3;
         return 0;
+    }();
+    return v;
+}
+static bool select_multi_launch() {          // CLDET_SELECT_MULTI=1: the round-1 chain of five select launches (A/B only)
+    static const bool v = [] {
+        const char* e = getenv("CLDET_SELECT_MULTI");
+        return e && e[0] == '1';
     }();
     return v;
 }
@@ -1434,18 +1619,25 @@ int cldet_sort_candidates(const cldet_candidate* d_candidates, const uint64_t* d
         cldet_candidate* sel_cand = reinterpret_cast<cldet_candidate*>(p + off);
         off = align_up(off + (size_t)num_images * max_count * sizeof(cldet_candidate), 256);
         uint64_t* sel_keys = reinterpret_cast<uint64_t*>(p + off);
-        select_init_kernel<<<num_images, 256, 0, s>>>(d_counts, capacity, topk, state, hist, done, num_images);
-        CLDET_LAUNCH_CHECK();
-        const SelPass passes[3] = {{21, 11, 0}, {10, 11, 11}, {0, 10, 22}};
-        for (int ps = 0; ps < 3; ++ps) {
-            dim3 g((unsigned)std::max(1, std::min(blocks_x / 8, 16)), (unsigned)num_images);
-            select_hist_pick_kernel<<<g, 256, 0, s>>>(d_keys, d_counts, capacity, passes[ps], state, hist, done);
+        if (!select_multi_launch()) {
+            // one launch: init + three radix passes + compaction, one CTA per image
+            select_fused_kernel<<<num_images, kSelThreads, 0, s>>>(d_candidates, d_keys, d_counts, capacity, topk, state, sel_cand,
+                                                                   sel_keys, max_count);
+            CLDET_LAUNCH_CHECK();
+        } else {
+            select_init_kernel<<<num_images, 256, 0, s>>>(d_counts, capacity, topk, state, hist, done, num_images);
+            CLDET_LAUNCH_CHECK();
+            const SelPass passes[3] = {{21, 11, 0}, {10, 11, 11}, {0, 10, 22}};
+            for (int ps = 0; ps < 3; ++ps) {
+                dim3 g((unsigned)std::max(1, std::min(blocks_x / 8, 16)), (unsigned)num_images);
+                select_hist_pick_kernel<<<g, 256, 0, s>>>(d_keys, d_counts, capacity, passes[ps], state, hist, done);
+                CLDET_LAUNCH_CHECK();
+            }
+            const int64_t per_block = 256 * kCompactPerThread;
+            dim3 gc((unsigned)((max_count + per_block - 1) / per_block), (unsigned)num_images);
+            select_compact_kernel<<<gc, 256, 0, s>>>(d_candidates, d_keys, d_counts, capacity, state, sel_cand, sel_keys, max_count);
             CLDET_LAUNCH_CHECK();
         }
-        const int64_t per_block = 256 * kCompactPerThread;
-        dim3 gc((unsigned)((max_count + per_block - 1) / per_block), (unsigned)num_images);
-        select_compact_kernel<<<gc, 256, 0, s>>>(d_candidates, d_keys, d_counts, capacity, state, sel_cand, sel_keys, max_count);
-        CLDET_LAUNCH_CHECK();
         // survivors are ~topk (plus exact score ties): size the grid for 2*topk, the kernel strides if there are more
         dim3 gr((unsigned)std::max<int64_t>(1, std::min<int64_t>((max_count + kRankPerBlock - 1) / kRankPerBlock,
                                                                    (2 * (int64_t)topk + kRankPerBlock - 1) / kRankPerBlock)),
@@ -1475,9 +1667,31 @@ size_t cldet_nms_workspace_bytes(int num_images, int64_t max_count) {
     return nms_ws_layout(nullptr, num_images, max_count).total + 256;
 }
 
+static int nms_sorted_impl(const cldet_candidate* d_sorted, const int32_t* d_sorted_counts, int num_images, int64_t capacity,
+                           int64_t max_count, float iou_thresh, int mode, int64_t vanilla_numel_limit, int32_t* d_keep,
+                           int32_t* d_keep_counts, void* d_workspace, size_t workspace_bytes, void* stream, float* d_scores,
+                           int64_t* d_labels, float* d_boxes);
+
 int cldet_nms_sorted(const cldet_candidate* d_sorted, const int32_t* d_sorted_counts, int num_images, int64_t capacity,
                      int64_t max_count, float iou_thresh, int mode, int64_t vanilla_numel_limit, int32_t* d_keep,
                      int32_t* d_keep_counts, void* d_workspace, size_t workspace_bytes, void* stream) {
+    return nms_sorted_impl(d_sorted, d_sorted_counts, num_images, capacity, max_count, iou_thresh, mode, vanilla_numel_limit, d_keep,
+                           d_keep_counts, d_workspace, workspace_bytes, stream, nullptr, nullptr, nullptr);
+}
+
+int cldet_nms_gather_sorted(const cldet_candidate* d_sorted, const int32_t* d_sorted_counts, int num_images, int64_t capacity,
+                            int64_t max_count, float iou_thresh, int mode, int64_t vanilla_numel_limit, int32_t* d_keep,
+                            int32_t* d_keep_counts, float* d_scores, int64_t* d_labels, float* d_boxes, void* d_workspace,
+                            size_t workspace_bytes, void* stream) {
+    if (!d_scores || !d_labels || !d_boxes) return CLDET_ERR_INVALID_ARGUMENT;
+    return nms_sorted_impl(d_sorted, d_sorted_counts, num_images, capacity, max_count, iou_thresh, mode, vanilla_numel_limit, d_keep,
+                           d_keep_counts, d_workspace, workspace_bytes, stream, d_scores, d_labels, d_boxes);
+}
+
+static int nms_sorted_impl(const cldet_candidate* d_sorted, const int32_t* d_sorted_counts, int num_images, int64_t capacity,
+                           int64_t max_count, float iou_thresh, int mode, int64_t vanilla_numel_limit, int32_t* d_keep,
+                           int32_t* d_keep_counts, void* d_workspace, size_t workspace_bytes, void* stream, float* d_scores,
+                           int64_t* d_labels, float* d_boxes) {
     if (!d_sorted || !d_sorted_counts || !d_keep || !d_keep_counts || !d_workspace) return CLDET_ERR_INVALID_ARGUMENT;
     if (num_images <= 0 || num_images > 65535 || capacity <= 0 || mode < 0 || mode > 2) return CLDET_ERR_INVALID_ARGUMENT;
     if (max_count > capacity) max_count = capacity;
@@ -1504,17 +1718,22 @@ int cldet_nms_sorted(const cldet_candidate* d_sorted, const int32_t* d_sorted_co
         if (smem > 40 * 1024)
             CLDET_CUDA_TRY(cudaFuncSetAttribute(nms_resolve_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         nms_resolve_stream_kernel<<<num_images, kStreamThreads, smem, s>>>(d_sorted_counts, capacity, w.mask, w.mask_stride_img,
-                                                                         w.col_blocks, d_keep, d_keep_counts);
+                                                                         w.col_blocks, d_keep, d_keep_counts, d_sorted, d_scores,
+                                                                         d_labels, reinterpret_cast<float4*>(d_boxes));
     } else if (max_count <= kSmemResolveMax && resolve != 3) {
         const size_t cbm = (size_t)((max_count + 63) / 64);
         const size_t smem = 64 * cbm * cbm * sizeof(uint64_t);
         if (smem > 48 * 1024)
             CLDET_CUDA_TRY(cudaFuncSetAttribute(nms_resolve_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         nms_resolve_smem_kernel<<<num_images, kSmemResolveThreads, smem, s>>>(d_sorted_counts, capacity, w.mask, w.mask_stride_img, w.col_blocks,
-                                                              d_keep, d_keep_counts);
+                                                              d_keep, d_keep_counts, d_sorted, d_scores, d_labels,
+                                                              reinterpret_cast<float4*>(d_boxes));
     } else {
         nms_resolve_kernel<<<num_images, 256, 0, s>>>(d_sorted_counts, capacity, w.mask, w.mask_stride_img, w.col_blocks, w.remv,
                                                       d_keep, d_keep_counts);
+        CLDET_LAUNCH_CHECK();
+        if (d_scores) return cldet_gather_detections(d_sorted, d_keep, d_keep_counts, num_images, capacity, max_count, d_scores, d_labels,
+                                                     d_boxes, stream);
     }
     CLDET_LAUNCH_CHECK();
     return CLDET_OK;

@@ -328,6 +328,9 @@ std::vector<Tensor> detect(const Tensor& cls, const Tensor& reg, const Tensor& a
     // images that fit a fixed budget instead of sizing one workspace for the whole batch
     Tensor keep = at::empty({n, cap}, i32);
     Tensor keep_counts = at::empty({n}, i32);
+    Tensor scores = at::empty({n, cap}, f32);
+    Tensor labels = at::empty({n, cap}, f32.dtype(at::kLong));
+    Tensor boxes = at::empty({n, cap, 4}, f32);
     const size_t one_image = cldet_nms_workspace_bytes(1, cap);
     const size_t budget = (size_t)4 << 30;
     const int64_t group = std::max<int64_t>(1, std::min<int64_t>(n, (int64_t)(budget / std::max<size_t>(one_image, 1))));
@@ -335,18 +338,14 @@ std::vector<Tensor> detect(const Tensor& cls, const Tensor& reg, const Tensor& a
     Tensor nws = at::empty({(int64_t)nws_bytes}, u8);
     for (int64_t j0 = 0; j0 < n; j0 += group) {
         const int64_t cnt = std::min<int64_t>(group, n - j0);
-        check_status(cldet_nms_sorted((const cldet_candidate*)sorted.data_ptr() + j0 * cap, sorted_counts.data_ptr<int32_t>() + j0, (int)cnt,
-                                      cap, cap, (float)iou_thresh, (int)nms_mode, vanilla_numel_limit, keep.data_ptr<int32_t>() + j0 * cap,
-                                      keep_counts.data_ptr<int32_t>() + j0, nws.data_ptr(), nws_bytes, stream),
-                     "cldet_nms_sorted");
+        // NMS + gather of the kept candidates in one chain (the resolving block gathers its image)
+        check_status(cldet_nms_gather_sorted((const cldet_candidate*)sorted.data_ptr() + j0 * cap, sorted_counts.data_ptr<int32_t>() + j0,
+                                             (int)cnt, cap, cap, (float)iou_thresh, (int)nms_mode, vanilla_numel_limit,
+                                             keep.data_ptr<int32_t>() + j0 * cap, keep_counts.data_ptr<int32_t>() + j0,
+                                             scores.data_ptr<float>() + j0 * cap, labels.data_ptr<int64_t>() + j0 * cap,
+                                             boxes.data_ptr<float>() + j0 * cap * 4, nws.data_ptr(), nws_bytes, stream),
+                     "cldet_nms_gather_sorted");
     }
-    Tensor scores = at::empty({n, cap}, f32);
-    Tensor labels = at::empty({n, cap}, f32.dtype(at::kLong));
-    Tensor boxes = at::empty({n, cap, 4}, f32);
-    check_status(cldet_gather_detections((const cldet_candidate*)sorted.data_ptr(), keep.data_ptr<int32_t>(), keep_counts.data_ptr<int32_t>(),
-                                         (int)n, cap, cap, scores.data_ptr<float>(), labels.data_ptr<int64_t>(), boxes.data_ptr<float>(),
-                                         stream),
-                 "cldet_gather_detections");
     return {scores, labels, boxes, keep_counts, counts};
 }
 

@@ -190,14 +190,12 @@ def _detect_pipeline(run_filter, n, a, dev, iou_threshold, pre_nms_topk, nms_mod
         nws = torch.empty(nws_bytes, dtype=torch.uint8, device=dev)
         keep = torch.empty((n, cap), dtype=torch.int32, device=dev)
         keep_counts = torch.empty(n, dtype=torch.int32, device=dev)
-        _lib.check(lib.cldet_nms_sorted(sorted_c.data_ptr(), sorted_counts.data_ptr(), n, cap, cap, float(iou_threshold),
-                                        int(nms_mode), int(vanilla_numel_limit), keep.data_ptr(), keep_counts.data_ptr(),
-                                        nws.data_ptr(), nws_bytes, st))
         scores = torch.empty((n, cap), dtype=torch.float32, device=dev)
         labels = torch.empty((n, cap), dtype=torch.int64, device=dev)
         boxes = torch.empty((n, cap, 4), dtype=torch.float32, device=dev)
-        _lib.check(lib.cldet_gather_detections(sorted_c.data_ptr(), keep.data_ptr(), keep_counts.data_ptr(), n, cap, cap,
-                                               scores.data_ptr(), labels.data_ptr(), boxes.data_ptr(), st))
+        _lib.check(lib.cldet_nms_gather_sorted(sorted_c.data_ptr(), sorted_counts.data_ptr(), n, cap, cap, float(iou_threshold),
+                                               int(nms_mode), int(vanilla_numel_limit), keep.data_ptr(), keep_counts.data_ptr(),
+                                               scores.data_ptr(), labels.data_ptr(), boxes.data_ptr(), nws.data_ptr(), nws_bytes, st))
         if return_padded:
             return scores, labels, boxes, keep_counts
         kc = keep_counts.cpu().tolist()

@@ -353,10 +353,20 @@ size_t cldet_nms_workspace_bytes(int num_images, int64_t max_count);
  *   mode 1 = always coordinate trick  (boxes + label*(max_coord+1) in fp32, then plain NMS),
  *   mode 2 = always vanilla           (raw coordinates, only same-label pairs suppress).
  * Suppress iff inter / ((area_i + area_j) - inter) > iou_thresh (strict, fp32, no FMA).
- * Outputs: d_keep [N, capacity] int32 = positions (into the sorted list) of kept boxes in order; d_keep_counts [N]. */
+ * Outputs: d_keep [N, capacity] int32 = positions (into the sorted list) of kept boxes in order; d_keep_counts [N]
+ * (-1 = error marker: that image's count exceeds max_count, the size the workspace was made for). */
 int cldet_nms_sorted(const cldet_candidate* d_sorted, const int32_t* d_sorted_counts, int num_images, int64_t capacity,
                      int64_t max_count, float iou_thresh, int mode, int64_t vanilla_numel_limit, int32_t* d_keep,
                      int32_t* d_keep_counts, void* d_workspace, size_t workspace_bytes, void* stream);
+
+/* cldet_nms_sorted followed by cldet_gather_detections in the SAME launch chain: the block that resolves an image also
+ * gathers its kept candidates into d_scores [N,capacity], d_labels [N,capacity] int64, d_boxes [N,capacity,4] (one launch
+ * fewer on a latency-bound chain).  A negative d_keep_counts[j] is an error marker: image j held more candidates than
+ * max_count, for which the workspace was sized (nothing is truncated silently). */
+int cldet_nms_gather_sorted(const cldet_candidate* d_sorted, const int32_t* d_sorted_counts, int num_images, int64_t capacity,
+                            int64_t max_count, float iou_thresh, int mode, int64_t vanilla_numel_limit, int32_t* d_keep,
+                            int32_t* d_keep_counts, float* d_scores, int64_t* d_labels, float* d_boxes, void* d_workspace,
+                            size_t workspace_bytes, void* stream);
 
 /* torchvision.ops.nms / batched_nms on caller-provided boxes (drop-in for model.py:540, persuado_label.py:116):
  * d_boxes [K,4], d_scores [K], d_idxs [K] int64 (NULL = plain nms).  d_keep [K] int64 receives ORIGINAL indices in

@@ -1,0 +1,17 @@
+#!/bin/bash
+set -u
+mkdir -p gpurun_out
+python -m pytest tests -m gpu -x -q 2>&1 | tail -25
+python - <<'PY' 2>&1 | tail -20
+import json, sys, torch
+sys.path.insert(0, '.')
+from tools.bench_detect import measure_nms_h2h, measure_predict
+dev = torch.device('cuda', 0)
+for k in (1000, 8000, 40000):
+    print(json.dumps(measure_nms_h2h(dev, k)))
+for mu in (-10.5, -9.5, -8.5):
+    r = measure_predict(dev, mu, cpu_images=0)
+    print(json.dumps({k: r[k] for k in ('candidates_per_image', 'kept_per_image', 'e2e_ms_per_image', 'device_resident_ms_per_image', 'gpu_eager_ms_per_image')}))
+PY
+python tools/bench_detect.py --mu -10.5 > gpurun_out/detect_sparse_default.json 2>/dev/null; python -c "import json;d=json.load(open('gpurun_out/detect_sparse_default.json'));print('default',d['ms_per_step'],d['stage_ms'])"
+CLDET_NMS_RESOLVE=stream python tools/bench_detect.py --mu -10.5 > gpurun_out/detect_sparse_stream.json 2>/dev/null; python -c "import json;d=json.load(open('gpurun_out/detect_sparse_stream.json'));print('stream',d['ms_per_step'],d['stage_ms'])"
