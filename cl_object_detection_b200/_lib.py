@@ -21,7 +21,9 @@ class CldetError(RuntimeError):
 class PeerExchange(ctypes.Structure):
     """struct cldet_peer_exchange (include/cldet.h)."""
     _fields_ = [('d_peer_terms', ctypes.c_void_p), ('d_peer_flags', ctypes.c_void_p), ('rank', ctypes.c_int32),
-                ('world', ctypes.c_int32), ('parity', ctypes.c_int32)]
+                ('world', ctypes.c_int32), ('parity', ctypes.c_int32), ('timeout_ms', ctypes.c_int32),
+                ('target_arrivals', ctypes.c_uint32), ('reserved', ctypes.c_int32), ('d_flags_local', ctypes.c_void_p),
+                ('d_terms_local', ctypes.c_void_p), ('d_wait_out', ctypes.c_void_p), ('d_wait_status', ctypes.c_void_p)]
 
 
 class LossParams(ctypes.Structure):

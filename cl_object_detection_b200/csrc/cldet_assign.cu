@@ -6,12 +6,22 @@
 
 #include <algorithm>
 
+#include <stdlib.h>
+
 #include "cldet_common.cuh"
 
 namespace cldet {
 
 static thread_local cudaError_t g_last_cuda_error = cudaSuccess;
 void set_last_cuda_error(cudaError_t e) { g_last_cuda_error = e; }
+
+bool pdl_enabled() {
+    static const bool on = [] {
+        const char* e = getenv("CLDET_NO_PDL");
+        return !(e && e[0] == '1');
+    }();
+    return on;
+}
 
 // ------------------------------------------------------------------------------------------------
 // K1: anchors.  Reference: retinanet/anchors.py:21-40 (levels, ceil-div shapes), :42-73 (base boxes),
@@ -98,6 +108,7 @@ __global__ void __launch_bounds__(kAssignThreads, 5)
 iou_assign_kernel(const float4* __restrict__ anchors, int64_t A, const float* __restrict__ annotations, int G,
                   int num_classes, uint32_t* __restrict__ meta, int32_t* __restrict__ argmax_out,
                   float* __restrict__ iou_max_out, int32_t* __restrict__ npos, int32_t* __restrict__ nvalid) {
+    pdl_launch_dependents();
     // valid rows of the current tile, compacted in order: box, area, (label, raw row)
     __shared__ float4 s_box[kGtTile];
     __shared__ float s_area[kGtTile];
@@ -344,6 +355,7 @@ __global__ void __launch_bounds__(128)
 gt_scatter_kernel(const ScatterPlan plan, const float4* __restrict__ anchors, int64_t A, const float* __restrict__ annotations,
                   int G, unsigned long long* __restrict__ best, uint32_t* __restrict__ touched, int32_t* __restrict__ npos_acc,
                   int32_t* __restrict__ nvalid) {
+    pdl_launch_dependents();      // the loss kernel may be scheduled while this grid drains (it waits before reading)
     // grid = (GT row, image, pyramid level): one block visits the candidate anchors of one GT box on one level
     const int j = blockIdx.y;
     const int l = blockIdx.z;

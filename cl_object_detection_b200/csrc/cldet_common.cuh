@@ -65,6 +65,32 @@ int launch_gt_scatter(int height, int width, const float* d_anchors, int64_t num
                       int num_images, int gt_rows, unsigned long long* d_best, uint32_t* d_touched, int32_t* d_npos_acc,
                       int32_t* d_nvalid, cudaStream_t s);
 
+// ---- programmatic dependent launch (PDL) ----
+// A kernel launched with launch_pdl() may be scheduled while its predecessor on the stream is still draining (the
+// predecessor's blocks have all started and called pdl_launch_dependents(), or exited); it must call pdl_wait() -- in EVERY
+// block, before the first access to memory the predecessor touches -- which returns once the predecessor has completed and
+// its writes are visible.  Both instructions are no-ops in a kernel that was launched normally.  The chains here are bound by
+// the latency of short dependent launches, which this hides.  CLDET_NO_PDL=1 launches everything normally (A/B only).
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+bool pdl_enabled();
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 inline int sm_count() {
     int dev = 0, n = 148;
     if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);

@@ -10,6 +10,8 @@
 
 #include <algorithm>
 
+#include <cooperative_groups.h>
+
 #include "cldet_common.cuh"
 
 namespace cldet {
@@ -97,6 +99,7 @@ decode_filter_kernel(const float* __restrict__ cls, int is_logits, const float4*
                      const float4* __restrict__ anchors, int64_t A, int C, int rows_per_block, int stride, float img_w,
                      float img_h, float score_thresh, float prefilter, cldet_candidate* __restrict__ cand,
                      uint64_t* __restrict__ keys, int64_t capacity, int32_t* __restrict__ counts) {
+    pdl_launch_dependents();          // head of the chain: the select / sort kernel may be scheduled while this grid drains
     extern __shared__ float part[];          // [rows_per_block][stride] per-vector maxima; stride is odd: conflict-free
     __shared__ int warp_tot[kFilterThreads / 32];
     __shared__ int block_base;
@@ -258,6 +261,7 @@ __global__ void __launch_bounds__(kHeadFilterPos)
 decode_filter_head_kernel(const HeadFilterLevels lv, int is_logits, const float4* __restrict__ anchors, int64_t A, int C,
                           float img_w, float img_h, float score_thresh, float prefilter, cldet_candidate* __restrict__ cand,
                           uint64_t* __restrict__ keys, int64_t capacity, int32_t* __restrict__ counts) {
+    pdl_launch_dependents();
     __shared__ int warp_tot[kHeadFilterPos / 32];
     __shared__ int block_base;
     const int j = blockIdx.y;
@@ -472,28 +476,38 @@ select_hist_pick_kernel(const uint64_t* __restrict__ keys, const int32_t* __rest
     }
 }
 
-// The whole top-k SELECT of one image in ONE launch (one CTA per image): state init, the three radix passes on the score
-// bits and the compaction of the survivors.  An image that keeps everything (no top-k, fewer candidates than k, or few enough
-// for the rank sort to order them all) costs one block that returns at once -- the trained-model regime used to pay five
-// launches that did nothing (init + 3 passes + compaction, ~20 us of a 400 us pipeline).  Keys are streamed from L2 with
-// four independent loads per thread; the pick is the same descending cumulative-count walk as select_hist_pick_kernel.
-constexpr int kSelThreads = 1024;
+// The whole top-k SELECT of one image in ONE launch: state init, the three radix passes on the score bits and the compaction
+// of the survivors, by a thread-block CLUSTER of kSelCluster CTAs per image (co-scheduled by the hardware, synchronised with
+// the cluster barrier, histograms exchanged through distributed shared memory -- no global scratch, no inter-launch gaps).
+// An image that keeps everything (no top-k, fewer candidates than k, or few enough for the rank sort to order them all) costs
+// one cluster that returns at once: the trained-model regime used to pay five launches that did nothing (init + 3 passes +
+// compaction, ~20 us of a 400 us pipeline).  Each CTA streams its share of the keys from L2 with four independent loads per
+// thread; CTA 0 adds the cluster's histograms and picks the digit with the same descending cumulative-count walk as
+// select_hist_pick_kernel, then publishes (prefix, remaining k) into every CTA's shared memory.
+constexpr int kSelThreads = 512;       // two CTAs per SM: 32 images x 8 CTAs are one wave on 148 SMs
+constexpr int kSelCluster = 8;
+constexpr int kSelUnroll = 8;          // independent key loads in flight per thread
 
-__global__ void __launch_bounds__(kSelThreads)
+__global__ void __cluster_dims__(kSelCluster, 1, 1) __launch_bounds__(kSelThreads)
 select_fused_kernel(const cldet_candidate* __restrict__ cand, const uint64_t* __restrict__ keys, const int32_t* __restrict__ counts,
                     int64_t capacity, int topk, uint32_t* __restrict__ state, cldet_candidate* __restrict__ out_cand,
                     uint64_t* __restrict__ out_keys, int64_t out_capacity) {
+    pdl_wait();                       // may be scheduled while the previous kernel of the chain drains
+    pdl_launch_dependents();
+    namespace cg = cooperative_groups;
     __shared__ uint32_t sh[kSelBins];
     __shared__ uint32_t part[256];
     __shared__ uint32_t s_prefix, s_need;
     __shared__ int warp_tot[kSelThreads / 32];
     __shared__ int block_base;
-    const int j = blockIdx.x;
+    cg::cluster_group cluster = cg::this_cluster();
+    const int rank = (int)cluster.block_rank();
+    const int j = blockIdx.x / kSelCluster;
     const int tid = threadIdx.x;
     uint32_t* st = state + 4 * j;
     const int64_t cnt = min64(counts[j], capacity);
-    if (topk <= 0 || cnt <= topk || cnt <= kRankDirect) {       // keep everything: the rank sort reads the original arrays
-        if (tid == 0) {
+    if (topk <= 0 || cnt <= topk || cnt <= kRankDirect) {       // keep everything (uniform over the cluster)
+        if (tid == 0 && rank == 0) {
             st[0] = 0; st[1] = 0; st[2] = 0; st[3] = 1;
         }
         return;
@@ -501,8 +515,10 @@ select_fused_kernel(const cldet_candidate* __restrict__ cand, const uint64_t* __
     if (tid == 0) {
         s_prefix = 0;
         s_need = (uint32_t)topk;
+        if (rank == 0) st[2] = 0;                               // survivors written (global, atomically advanced below)
     }
     const uint64_t* k = keys + (int64_t)j * capacity;
+    const int64_t stride = (int64_t)kSelCluster * kSelUnroll * kSelThreads;
     const SelPass passes[3] = {{21, 11, 0}, {10, 11, 11}, {0, 10, 22}};
 #pragma unroll 1
     for (int ps = 0; ps < 3; ++ps) {
@@ -511,66 +527,79 @@ select_fused_kernel(const cldet_candidate* __restrict__ cand, const uint64_t* __
         for (int b = tid; b < kSelBins; b += kSelThreads) sh[b] = 0;
         __syncthreads();
         const uint32_t prefix = s_prefix;
-        for (int64_t i0 = 0; i0 < cnt; i0 += 4 * kSelThreads) {
-            uint32_t sc[4];
+        for (int64_t i0 = (int64_t)rank * kSelUnroll * kSelThreads; i0 < cnt; i0 += stride) {
+            uint32_t sc[kSelUnroll];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
+            for (int u = 0; u < kSelUnroll; ++u) {
                 const int64_t i = i0 + u * kSelThreads + tid;
                 sc[u] = (i < cnt) ? (uint32_t)(k[i] >> 32) : 0u;
             }
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
+            for (int u = 0; u < kSelUnroll; ++u) {
                 const int64_t i = i0 + u * kSelThreads + tid;
                 const bool match = P.hi_bits == 0 || (sc[u] >> (32 - P.hi_bits)) == (prefix >> (32 - P.hi_bits));
                 if (i < cnt && match) atomicAdd(&sh[(sc[u] >> P.shift) & (nb - 1)], 1u);
             }
         }
-        __syncthreads();
-        // pick: thread t < 256 owns bins [hi-7, hi], hi = kSelBins-1-8t (descending); suffix scan over the 256 partial sums
-        uint32_t mine = 0;
-        const int hi = kSelBins - 1 - 8 * (tid & 255);
-        if (tid < 256) {
+        cluster.sync();                                          // every CTA's histogram is complete
+        if (rank == 0) {
+            // add the other CTAs' histograms (distributed shared memory) into mine
+            for (int b = tid; b < nb; b += kSelThreads) {
+                uint32_t v = sh[b];
 #pragma unroll
-            for (int q = 0; q < 8; ++q) mine += sh[hi - q];
-            part[tid] = mine;
-        }
-        __syncthreads();
-        for (int off = 1; off < 256; off <<= 1) {
-            uint32_t add = 0;
-            if (tid < 256 && tid >= off) add = part[tid - off];
+                for (int r = 1; r < kSelCluster; ++r) v += cluster.map_shared_rank(sh, r)[b];
+                sh[b] = v;
+            }
             __syncthreads();
-            if (tid < 256) part[tid] += add;
+            // pick: thread t < 256 owns bins [hi-7, hi], hi = kSelBins-1-8t (descending); suffix scan over the 256 partial sums
+            uint32_t mine = 0;
+            const int hi = kSelBins - 1 - 8 * (tid & 255);
+            if (tid < 256) {
+#pragma unroll
+                for (int q = 0; q < 8; ++q) mine += sh[hi - q];
+                part[tid] = mine;
+            }
             __syncthreads();
-        }
-        const uint32_t need0 = s_need;
-        __syncthreads();
-        if (tid < 256) {
-            const uint32_t incl = part[tid], excl = incl - mine;
-            const bool owner = (excl < need0 && incl >= need0) || (tid == 255 && incl < need0);
-            if (owner) {
-                uint32_t need = need0 - excl;
-                int b = hi;
-                for (int q = 0; q < 8; ++q, --b) {
-                    if (sh[b] >= need || b == 0) break;
-                    need -= sh[b];
+            for (int off = 1; off < 256; off <<= 1) {
+                uint32_t add = 0;
+                if (tid < 256 && tid >= off) add = part[tid - off];
+                __syncthreads();
+                if (tid < 256) part[tid] += add;
+                __syncthreads();
+            }
+            const uint32_t need0 = s_need;
+            __syncthreads();
+            if (tid < 256) {
+                const uint32_t incl = part[tid], excl = incl - mine;
+                const bool owner = (excl < need0 && incl >= need0) || (tid == 255 && incl < need0);
+                if (owner) {
+                    uint32_t need = need0 - excl;
+                    int b = hi;
+                    for (int q = 0; q < 8; ++q, --b) {
+                        if (sh[b] >= need || b == 0) break;
+                        need -= sh[b];
+                    }
+                    if (b < 0) b = 0;
+                    const uint32_t np = prefix | ((uint32_t)b << P.shift);
+                    for (int r = 0; r < kSelCluster; ++r) {      // publish to every CTA of the cluster
+                        *cluster.map_shared_rank(&s_prefix, r) = np;
+                        *cluster.map_shared_rank(&s_need, r) = need;
+                    }
                 }
-                if (b < 0) b = 0;
-                s_prefix = prefix | ((uint32_t)b << P.shift);
-                s_need = need;
             }
         }
-        __syncthreads();
+        cluster.sync();                                          // (prefix, need) visible everywhere; remote reads of sh are done
     }
-    // compaction: every candidate whose score bits reach the k-th score (exact ties included; the ordering pass cuts at k)
+    // compaction: every candidate whose score bits reach the k-th score (exact ties included; the ordering pass cuts at k);
+    // order is arbitrary (the rank sort orders), so a tile appends with one global atomic
     const uint32_t thr = s_prefix;
     const int lane = tid & 31, warp = tid >> 5;
-    int written = 0;                                   // block-uniform running total
-    for (int64_t i0 = 0; i0 < cnt; i0 += 4 * kSelThreads) {
-        uint64_t key[4];
-        bool take[4];
+    for (int64_t i0 = (int64_t)rank * kSelUnroll * kSelThreads; i0 < cnt; i0 += stride) {
+        uint64_t key[kSelUnroll];
+        bool take[kSelUnroll];
         int mine = 0;
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
+        for (int u = 0; u < kSelUnroll; ++u) {
             const int64_t i = i0 + u * kSelThreads + tid;
             key[u] = (i < cnt) ? k[i] : 0ull;
             take[u] = (i < cnt) && (uint32_t)(key[u] >> 32) >= thr;
@@ -591,12 +620,12 @@ select_fused_kernel(const cldet_candidate* __restrict__ cand, const uint64_t* __
                 warp_tot[w] = tot;
                 tot += c;
             }
-            block_base = tot;
+            block_base = tot ? (int)atomicAdd(&st[2], (uint32_t)tot) : 0;
         }
         __syncthreads();
-        int64_t slot = (int64_t)written + warp_tot[warp] + (incl - mine);
+        int64_t slot = (int64_t)block_base + warp_tot[warp] + (incl - mine);
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
+        for (int u = 0; u < kSelUnroll; ++u) {
             if (take[u]) {
                 const int64_t i = i0 + u * kSelThreads + tid;
                 if (slot < out_capacity) {
@@ -609,11 +638,10 @@ select_fused_kernel(const cldet_candidate* __restrict__ cand, const uint64_t* __
                 ++slot;
             }
         }
-        written += block_base;
         __syncthreads();
     }
-    if (tid == 0) {
-        st[0] = thr; st[1] = 0; st[2] = (uint32_t)written; st[3] = 0;
+    if (tid == 0 && rank == 0) {
+        st[0] = thr; st[1] = 0; st[3] = 0;
     }
 }
 
@@ -689,6 +717,8 @@ rank_sort_kernel(const cldet_candidate* __restrict__ cand, const uint64_t* __res
                  const int32_t* __restrict__ counts_in, int64_t in_capacity, int topk, cldet_candidate* __restrict__ sorted,
                  int64_t out_capacity, int32_t* __restrict__ sorted_counts, const cldet_candidate* __restrict__ orig_cand = nullptr,
                  const uint64_t* __restrict__ orig_keys = nullptr, int64_t orig_capacity = 0) {
+    pdl_wait();                       // may be scheduled while the previous kernel of the chain drains
+    pdl_launch_dependents();
     __shared__ uint64_t tile[1024];
     const int j = blockIdx.y;
     int64_t n = state ? (int64_t)state[4 * j + 2] : (int64_t)counts_in[j];
@@ -753,6 +783,8 @@ __global__ void __launch_bounds__(kRsThreads)
 radix_sort_kernel(const cldet_candidate* __restrict__ cand, const uint64_t* __restrict__ keys, const int32_t* __restrict__ counts,
                   int64_t in_capacity, int64_t max_count, cldet_candidate* __restrict__ sorted, int64_t out_capacity,
                   int32_t* __restrict__ sorted_counts, uint64_t* __restrict__ kbuf, uint32_t* __restrict__ ibuf) {
+    pdl_wait();                       // may be scheduled while the previous kernel of the chain drains
+    pdl_launch_dependents();
     __shared__ uint32_t hist[8][kRsBins];
     __shared__ uint32_t cnt[kRsWarps][kRsBins];
     __shared__ uint32_t base[kRsBins];
@@ -875,6 +907,8 @@ radix_sort_kernel(const cldet_candidate* __restrict__ cand, const uint64_t* __re
 __global__ void __launch_bounds__(256)
 nms_prepare_kernel(const cldet_candidate* __restrict__ sorted, const int32_t* __restrict__ counts, int64_t capacity, int mode,
                    int64_t vanilla_numel_limit, uint32_t* __restrict__ info) {
+    pdl_wait();                       // may be scheduled while the previous kernel of the chain drains
+    pdl_launch_dependents();
     __shared__ float red[8];
     const int j = blockIdx.x;
     const int n = (int)min64(counts[j], capacity);
@@ -915,6 +949,8 @@ __global__ void __launch_bounds__(256)
 nms_mask_kernel(const cldet_candidate* __restrict__ sorted, const int32_t* __restrict__ counts, int64_t capacity,
                 const uint32_t* __restrict__ info, float thr, uint64_t* __restrict__ mask, int64_t mask_stride_img,
                 int col_blocks_alloc) {
+    pdl_wait();                       // may be scheduled while the previous kernel of the chain drains
+    pdl_launch_dependents();
     const int j = blockIdx.y;
     // never past what the mask workspace was sized for (max_count), even if the caller's counts are larger
     const int n = (int)min64(min64(counts[j], capacity), (int64_t)col_blocks_alloc * 64);
@@ -991,6 +1027,8 @@ __global__ void __launch_bounds__(256)
 nms_resolve_kernel(const int32_t* __restrict__ counts, int64_t capacity, const uint64_t* __restrict__ mask,
                    int64_t mask_stride_img, int col_blocks_alloc, uint64_t* __restrict__ remv_ws, int32_t* __restrict__ keep,
                    int32_t* __restrict__ keep_counts) {
+    pdl_wait();                       // may be scheduled while the previous kernel of the chain drains
+    pdl_launch_dependents();
     __shared__ uint64_t diag[64];
     __shared__ uint64_t kept_bits;
     __shared__ int kept_total;
@@ -1089,6 +1127,8 @@ nms_resolve_smem_kernel(const int32_t* __restrict__ counts, int64_t capacity, co
                         int32_t* __restrict__ keep_counts, const cldet_candidate* __restrict__ sorted = nullptr,
                         float* __restrict__ out_scores = nullptr, int64_t* __restrict__ out_labels = nullptr,
                         float4* __restrict__ out_boxes = nullptr) {
+    pdl_wait();                       // may be scheduled while the previous kernel of the chain drains
+    pdl_launch_dependents();
     extern __shared__ uint64_t sm_mask[];                                // [64*cb][cb], rows >= n zero
     __shared__ int kept_total_s;
     const int j = blockIdx.x;
@@ -1187,6 +1227,8 @@ nms_resolve_stream_kernel(const int32_t* __restrict__ counts, int64_t capacity, 
                           int32_t* __restrict__ keep_counts, const cldet_candidate* __restrict__ sorted = nullptr,
                           float* __restrict__ out_scores = nullptr, int64_t* __restrict__ out_labels = nullptr,
                           float4* __restrict__ out_boxes = nullptr) {
+    pdl_wait();                       // may be scheduled while the previous kernel of the chain drains
+    pdl_launch_dependents();
     extern __shared__ unsigned long long removed[];                      // [col_blocks]
     __shared__ int kept_total_s;
     __shared__ uint64_t diag[2][64];
@@ -1620,10 +1662,9 @@ int cldet_sort_candidates(const cldet_candidate* d_candidates, const uint64_t* d
         off = align_up(off + (size_t)num_images * max_count * sizeof(cldet_candidate), 256);
         uint64_t* sel_keys = reinterpret_cast<uint64_t*>(p + off);
         if (!select_multi_launch()) {
-            // one launch: init + three radix passes + compaction, one CTA per image
-            select_fused_kernel<<<num_images, kSelThreads, 0, s>>>(d_candidates, d_keys, d_counts, capacity, topk, state, sel_cand,
-                                                                   sel_keys, max_count);
-            CLDET_LAUNCH_CHECK();
+            // one launch: init + three radix passes + compaction, one cluster of kSelCluster CTAs per image
+            CLDET_CUDA_TRY(launch_pdl(select_fused_kernel, dim3(num_images * kSelCluster), dim3(kSelThreads), 0, s, d_candidates, d_keys,
+                                      d_counts, capacity, topk, state, sel_cand, sel_keys, max_count));
         } else {
             select_init_kernel<<<num_images, 256, 0, s>>>(d_counts, capacity, topk, state, hist, done, num_images);
             CLDET_LAUNCH_CHECK();
@@ -1642,22 +1683,21 @@ int cldet_sort_candidates(const cldet_candidate* d_candidates, const uint64_t* d
         dim3 gr((unsigned)std::max<int64_t>(1, std::min<int64_t>((max_count + kRankPerBlock - 1) / kRankPerBlock,
                                                                    (2 * (int64_t)topk + kRankPerBlock - 1) / kRankPerBlock)),
                 (unsigned)num_images);
-        rank_sort_kernel<<<gr, 256, 0, s>>>(sel_cand, sel_keys, state, d_counts, max_count, topk, d_sorted, sorted_capacity,
-                                             d_sorted_counts, d_candidates, d_keys, capacity);
-        CLDET_LAUNCH_CHECK();
+        CLDET_CUDA_TRY(launch_pdl(rank_sort_kernel, gr, dim3(256), 0, s, (const cldet_candidate*)sel_cand, (const uint64_t*)sel_keys,
+                                  (const uint32_t*)state, d_counts, max_count, topk, d_sorted, sorted_capacity, d_sorted_counts,
+                                  d_candidates, d_keys, capacity));
     } else if (max_count > kRadixMin && !force_rank_sort()) {
         // the reference's mode (no top-k) with long lists: one launch, one CTA per image, every radix pass inside it
         uint64_t* kbuf = reinterpret_cast<uint64_t*>(p + off);
         off = align_up(off + (size_t)num_images * 2 * max_count * sizeof(uint64_t), 256);
         uint32_t* ibuf = reinterpret_cast<uint32_t*>(p + off);
-        radix_sort_kernel<<<num_images, kRsThreads, 0, s>>>(d_candidates, d_keys, d_counts, capacity, max_count, d_sorted,
-                                                             sorted_capacity, d_sorted_counts, kbuf, ibuf);
-        CLDET_LAUNCH_CHECK();
+        CLDET_CUDA_TRY(launch_pdl(radix_sort_kernel, dim3(num_images), dim3(kRsThreads), 0, s, d_candidates, d_keys, d_counts, capacity,
+                                  max_count, d_sorted, sorted_capacity, d_sorted_counts, kbuf, ibuf));
     } else {
         dim3 gc((unsigned)std::min<int64_t>((max_count + kRankPerBlock - 1) / kRankPerBlock, 65535 * 16), (unsigned)num_images);
-        rank_sort_kernel<<<gc, 256, 0, s>>>(d_candidates, d_keys, nullptr, d_counts, capacity, 0, d_sorted, sorted_capacity,
-                                             d_sorted_counts);
-        CLDET_LAUNCH_CHECK();
+        CLDET_CUDA_TRY(launch_pdl(rank_sort_kernel, gc, dim3(256), 0, s, d_candidates, d_keys, (const uint32_t*)nullptr, d_counts, capacity,
+                                  0, d_sorted, sorted_capacity, d_sorted_counts, (const cldet_candidate*)nullptr,
+                                  (const uint64_t*)nullptr, (int64_t)0));
     }
     return CLDET_OK;
 }
@@ -1703,31 +1743,30 @@ static int nms_sorted_impl(const cldet_candidate* d_sorted, const int32_t* d_sor
     if (workspace_bytes < cldet_nms_workspace_bytes(num_images, max_count)) return CLDET_ERR_WORKSPACE_TOO_SMALL;
     const NmsWs w = nms_ws_layout(d_workspace, num_images, max_count);
     if (w.col_blocks > 65535) return CLDET_ERR_UNSUPPORTED;
-    nms_prepare_kernel<<<num_images, 256, 0, s>>>(d_sorted, d_sorted_counts, capacity, mode, vanilla_numel_limit, w.info);
-    CLDET_LAUNCH_CHECK();
+    CLDET_CUDA_TRY(launch_pdl(nms_prepare_kernel, dim3(num_images), dim3(256), 0, s, d_sorted, d_sorted_counts, capacity, mode,
+                              vanilla_numel_limit, w.info));
     const long long tiles = (long long)w.col_blocks * (w.col_blocks + 1) / 2;          // upper-triangular tiles per image
     if (tiles > 2147483647ll) return CLDET_ERR_UNSUPPORTED;
     dim3 grid((unsigned)tiles, (unsigned)num_images);
-    nms_mask_kernel<<<grid, 256, 0, s>>>(d_sorted, d_sorted_counts, capacity, w.info, iou_thresh, w.mask, w.mask_stride_img,
-                                        w.col_blocks);
-    CLDET_LAUNCH_CHECK();
+    CLDET_CUDA_TRY(launch_pdl(nms_mask_kernel, grid, dim3(256), 0, s, d_sorted, d_sorted_counts, capacity, (const uint32_t*)w.info, iou_thresh,
+                              w.mask, w.mask_stride_img, w.col_blocks));
     const int resolve = resolve_choice();          // 0 default, 1 stream, 2 whole mask in shared memory, 3 legacy (A/B experiments)
     if (resolve == 1 || (resolve == 0 && max_count > kSmemResolveMax)) {
         const size_t smem = (size_t)w.col_blocks * sizeof(unsigned long long);
         if (smem > 200 * 1024) return CLDET_ERR_UNSUPPORTED;
         if (smem > 40 * 1024)
             CLDET_CUDA_TRY(cudaFuncSetAttribute(nms_resolve_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        nms_resolve_stream_kernel<<<num_images, kStreamThreads, smem, s>>>(d_sorted_counts, capacity, w.mask, w.mask_stride_img,
-                                                                         w.col_blocks, d_keep, d_keep_counts, d_sorted, d_scores,
-                                                                         d_labels, reinterpret_cast<float4*>(d_boxes));
+        CLDET_CUDA_TRY(launch_pdl(nms_resolve_stream_kernel, dim3(num_images), dim3(kStreamThreads), smem, s, d_sorted_counts, capacity,
+                                  (const uint64_t*)w.mask, w.mask_stride_img, w.col_blocks, d_keep, d_keep_counts, d_sorted, d_scores,
+                                  d_labels, reinterpret_cast<float4*>(d_boxes)));
     } else if (max_count <= kSmemResolveMax && resolve != 3) {
         const size_t cbm = (size_t)((max_count + 63) / 64);
         const size_t smem = 64 * cbm * cbm * sizeof(uint64_t);
         if (smem > 48 * 1024)
             CLDET_CUDA_TRY(cudaFuncSetAttribute(nms_resolve_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        nms_resolve_smem_kernel<<<num_images, kSmemResolveThreads, smem, s>>>(d_sorted_counts, capacity, w.mask, w.mask_stride_img, w.col_blocks,
-                                                              d_keep, d_keep_counts, d_sorted, d_scores, d_labels,
-                                                              reinterpret_cast<float4*>(d_boxes));
+        CLDET_CUDA_TRY(launch_pdl(nms_resolve_smem_kernel, dim3(num_images), dim3(kSmemResolveThreads), smem, s, d_sorted_counts, capacity,
+                                  (const uint64_t*)w.mask, w.mask_stride_img, w.col_blocks, d_keep, d_keep_counts, d_sorted, d_scores,
+                                  d_labels, reinterpret_cast<float4*>(d_boxes)));
     } else {
         nms_resolve_kernel<<<num_images, 256, 0, s>>>(d_sorted_counts, capacity, w.mask, w.mask_stride_img, w.col_blocks, w.remv,
                                                       d_keep, d_keep_counts);

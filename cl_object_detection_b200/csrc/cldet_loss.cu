@@ -171,6 +171,8 @@ static int loss_stage(const float* d_cls, const float* d_reg, const float* d_anc
     a.npos_out = d_npos_out; a.npos_reset = d_npos_reset; a.rw_counters = nullptr;
     a.best = d_best; a.touched = d_touched; a.meta_out = d_meta; a.iou_out = d_iou_out; a.nvalid = d_nvalid;
     a.peer_terms = nullptr; a.peer_flags = nullptr; a.rank = 0; a.world = 1; a.parity = 0;
+    a.wait_flags = nullptr; a.wait_terms = nullptr; a.wait_out = nullptr; a.wait_status = nullptr; a.wait_target = 0;
+    a.wait_timeout_ns = 0;
     if (peer && peer->world > 1) {
         if (!peer->d_peer_terms || !peer->d_peer_flags || peer->rank < 0 || peer->rank >= peer->world || peer->world > 64 ||
             (peer->parity != 0 && peer->parity != 1))
@@ -178,6 +180,16 @@ static int loss_stage(const float* d_cls, const float* d_reg, const float* d_anc
         a.peer_terms = reinterpret_cast<float* const*>(peer->d_peer_terms);
         a.peer_flags = reinterpret_cast<unsigned int* const*>(peer->d_peer_flags);
         a.rank = peer->rank; a.world = peer->world; a.parity = peer->parity;
+        if (peer->d_wait_out) {
+            if (!peer->d_flags_local || !peer->d_terms_local || peer->timeout_ms <= 0 || kLossThreads < peer->world)
+                return CLDET_ERR_INVALID_ARGUMENT;
+            a.wait_flags = reinterpret_cast<const unsigned int*>(peer->d_flags_local);
+            a.wait_terms = reinterpret_cast<const float*>(peer->d_terms_local) + (size_t)peer->parity * peer->world * 4 * num_images;
+            a.wait_out = peer->d_wait_out;
+            a.wait_status = peer->d_wait_status;
+            a.wait_target = peer->target_arrivals;
+            a.wait_timeout_ns = (unsigned long long)peer->timeout_ms * 1000000ull;
+        }
     }
     a.counters = reinterpret_cast<unsigned int*>(d_workspace);
     a.partials = reinterpret_cast<float*>(reinterpret_cast<char*>(d_workspace) + workspace_header_bytes(num_images));
@@ -283,48 +295,7 @@ __global__ void __launch_bounds__(256)
 peer_wait_copy_kernel(const unsigned int* flags, int world, int parity, unsigned int target, unsigned long long timeout_ns,
                       const float* terms, int n, float* out, float* reg_mean, int32_t* status) {
     __shared__ int bad[64];
-    const int r = threadIdx.x;
-    if (r < world) {
-        const unsigned int* f = flags + parity * world + r;
-        bool ok = false;
-        unsigned long long t0 = 0;
-        for (unsigned int spins = 0;; ++spins) {
-            unsigned int v;
-            asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
-            if ((int)(v - target) >= 0) {
-                ok = true;
-                break;
-            }
-            __nanosleep(spins < 64 ? 32 : 256);
-            if ((spins & 255u) == 255u) {
-                unsigned long long now;
-                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
-                if (t0 == 0) t0 = now;
-                else if (now - t0 > timeout_ns) break;
-            }
-        }
-        bad[r] = ok ? 0 : 1;
-        if (!ok && status) {
-            *status = 2;
-            __threadfence_system();
-        }
-    }
-    __syncthreads();
-    if (!out) return;
-    const int total = world * 4 * n;
-    for (int i = threadIdx.x; i < total; i += blockDim.x) {
-        const int src = i / (4 * n), rem = i - src * 4 * n;
-        const int k = rem / n, j = rem - k * n;
-        // written by peers into this GPU's L2: read past L1 (a line of the previous use of this parity may still sit there)
-        out[(size_t)k * world * n + (size_t)src * n + j] = bad[src] ? __int_as_float(0x7fc00000) : __ldcg(terms + i);
-    }
-    if (reg_mean && threadIdx.x == 0) {
-        // reg_loss = mean over the GLOBAL batch of the per-image regression terms (losses.py:445), in global image order
-        float s = 0.0f;
-        for (int src = 0; src < world; ++src)
-            for (int j = 0; j < n; ++j) s += bad[src] ? __int_as_float(0x7fc00000) : __ldcg(terms + ((size_t)src * 4 + 2) * n + j);
-        *reg_mean = s / (float)(world * n);
-    }
+    peer_wait_copy_block(flags, world, parity, target, timeout_ns, terms, n, out, reg_mean, status, bad);
 }
 
 // Buffers every rank of a node can map: allocated with cudaMalloc (whole allocation = one IPC handle, offset 0), exported
@@ -482,6 +453,8 @@ static int reweight_impl(const float* d_cls, const float* d_reg, const float* d_
     a.npos_out = nullptr; a.npos_reset = nullptr;
     a.best = nullptr; a.touched = nullptr; a.meta_out = nullptr; a.iou_out = nullptr; a.nvalid = nullptr;
     a.peer_terms = nullptr; a.peer_flags = nullptr; a.rank = 0; a.world = 1; a.parity = 0;
+    a.wait_flags = nullptr; a.wait_terms = nullptr; a.wait_out = nullptr; a.wait_status = nullptr; a.wait_target = 0;
+    a.wait_timeout_ns = 0;
     a.counters = nullptr; a.partials = nullptr;
     a.rw_counters = reinterpret_cast<unsigned int*>(d_workspace) + 2 * (size_t)num_images;
     a.anchors_per_block = pl.anchors_per_block; a.bpi = pl.bpi; a.div_magic = pl.div_magic;

@@ -20,6 +20,8 @@
 #include <torch/csrc/autograd/custom_function.h>
 #include <torch/library.h>
 
+#include <stdlib.h>
+
 #include <algorithm>
 #include <string>
 #include <unordered_map>
@@ -159,23 +161,39 @@ struct FocalLossFn : public torch::autograd::Function<FocalLossFn> {
         int32_t* npos = counts.data_ptr<int32_t>();
         int32_t* nvalid = npos + n;
         auto opt = [](const Tensor& t) -> void* { return t.defined() ? t.data_ptr() : nullptr; };
+        // image-sharded run: the loss kernel pushes every image's terms into all ranks' buffers; its last block then waits for
+        // all ranks' arrivals and copies the GLOBAL rows into `global` -- a private tensor, never a view of the exchange
+        // buffer -- so no wait kernel is launched behind it (CLDET_PEER_SEPARATE_WAIT=1: the two-launch variant, A/B only)
+        Tensor global;
+        static const bool separate_wait = [] {
+            const char* e = getenv("CLDET_PEER_SEPARATE_WAIT");
+            return e && e[0] == '1';
+        }();
+        if (peer.on) {
+            global = at::empty({4, ng}, f32);
+            if (!separate_wait) {
+                peer.ex.timeout_ms = peer.timeout_ms;
+                peer.ex.target_arrivals = peer.target;
+                peer.ex.d_flags_local = peer.flags_local;
+                peer.ex.d_terms_local = peer.terms_local;
+                peer.ex.d_wait_out = global.data_ptr<float>();
+                peer.ex.d_wait_status = peer.status;
+            }
+        }
         int rc = cldet_focal_loss_sharded(
             cls.data_ptr<float>(), reg.data_ptr<float>(), anchors.data_ptr<float>(), ann.data_ptr<float>(), (int)n, a, (int)c,
             (int)g, &lp, need_grad ? hint.data_ptr<float>() : nullptr, (float*)opt(baked), (float*)opt(gcls), (float*)opt(greg),
             losses.data_ptr<float>(), (uint32_t*)meta.data_ptr(), (float*)opt(iou_max), npos, nvalid, (uint8_t*)opt(bg_mask),
-            (int32_t*)opt(status), ws.data_ptr(), (size_t)ws.numel(), peer.on ? &peer.ex : nullptr,
-            peer.on ? nullptr : reg_loss.data_ptr<float>(), stream);
+            (int32_t*)opt(status), ws.data_ptr(), (size_t)ws.numel(), peer.on ? &peer.ex : nullptr, reg_loss.data_ptr<float>(), stream);
         if (rc != CLDET_OK) {
             drop_workspaces();          // a failed call may leave the scratch header dirty
             check_status(rc, "cldet_focal_loss");
         }
         if (peer.on) {
-            // fused all-gather: the kernel pushed every image's terms into all ranks' buffers; wait and copy the GLOBAL rows
-            // into a private tensor (never a view of the exchange buffer)
-            Tensor global = at::empty({4, ng}, f32);
-            check_status(cldet_peer_wait(peer.flags_local, peer.terms_local, peer.ex.world, (int)n, peer.ex.parity, peer.target,
-                                         peer.timeout_ms, global.data_ptr<float>(), reg_loss.data_ptr<float>(), peer.status, stream),
-                         "cldet_peer_wait");
+            if (separate_wait)
+                check_status(cldet_peer_wait(peer.flags_local, peer.terms_local, peer.ex.world, (int)n, peer.ex.parity, peer.target,
+                                             peer.timeout_ms, global.data_ptr<float>(), reg_loss.data_ptr<float>(), peer.status, stream),
+                             "cldet_peer_wait");
             losses = global;
         }
         ctx->set_materialize_grads(false);          // absent upstream gradients stay undefined (= zero rows), no fill kernels

@@ -148,6 +148,17 @@ typedef struct cldet_peer_exchange {
     void* d_peer_terms;   /* device array of `world` float*  : rank p's gather buffer, as mapped in THIS process */
     void* d_peer_flags;   /* device array of `world` uint32* : rank p's arrival counters */
     int32_t rank, world, parity;
+    /* Optional FUSED WAIT (d_wait_out != NULL): the loss kernel's block that finishes this rank's last image then does what
+     * cldet_peer_wait does -- waits (bounded by timeout_ms) for target_arrivals on this rank's counters, copies this parity's
+     * terms into d_wait_out [4][world*N] and writes the global regression mean to the call's d_reg_mean -- so there is no wait
+     * launch behind the loss kernel at all.  Arguments as for cldet_peer_wait. */
+    int32_t timeout_ms;
+    uint32_t target_arrivals;
+    int32_t reserved;
+    const void* d_flags_local;
+    const void* d_terms_local;
+    float* d_wait_out;
+    int32_t* d_wait_status;
 } cldet_peer_exchange;
 int cldet_focal_loss_sharded(const float* d_cls, const float* d_reg, const float* d_anchors, const float* d_annotations,
                              int num_images, int64_t num_anchors, int num_classes, int gt_rows,
