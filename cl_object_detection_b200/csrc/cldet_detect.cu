@@ -730,6 +730,10 @@ rank_sort_kernel(const cldet_candidate* __restrict__ cand, const uint64_t* __res
         n = (int64_t)counts_in[j];
     }
     n = min64(n, in_capacity);
+    if (topk <= 0 && n > out_capacity) {     // no top-k and more candidates than the sorted list can hold: report an EMPTY list;
+        if (blockIdx.x == 0 && threadIdx.x == 0) sorted_counts[j] = 0;      // the caller sees counts[j] > capacity and re-runs
+        return;
+    }
     const int64_t limit = (topk > 0) ? min64(n, topk) : n;
     if (blockIdx.x == 0 && threadIdx.x == 0) sorted_counts[j] = (int32_t)min64(limit, out_capacity);
     const uint64_t* k = keys + (int64_t)j * in_capacity;
@@ -792,6 +796,10 @@ radix_sort_kernel(const cldet_candidate* __restrict__ cand, const uint64_t* __re
     __shared__ int skip[8];
     const int j = blockIdx.x;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (counts[j] > max_count) {            // more candidates than the buffers were sized for: report an EMPTY list; the caller
+        if (threadIdx.x == 0) sorted_counts[j] = 0;      // sees counts[j] > capacity and repeats the call at the exact size
+        return;
+    }
     const int n = (int)min64(min64(counts[j], in_capacity), max_count);
     const uint64_t* k_in = keys + (int64_t)j * in_capacity;
     uint64_t* kb[2] = {kbuf + (int64_t)j * 2 * max_count, kbuf + (int64_t)j * 2 * max_count + max_count};
@@ -957,13 +965,18 @@ nms_mask_kernel(const cldet_candidate* __restrict__ sorted, const int32_t* __res
     // blockIdx.x enumerates the UPPER-TRIANGULAR 64x64 tiles row by row: tile t of row r starts at r*cb - r(r-1)/2
     // (a square grid launched twice as many blocks, half of which only returned: this kernel is block-scheduling bound)
     const int cb = col_blocks_alloc;
-    const long long t = blockIdx.x;
+    const int cbn = (n + 63) / 64;                                    // column blocks that hold boxes
+    // tiles beyond the live ones belong to rows/columns >= n: blocks stride over the tile index space, which the host caps
+    const long long tiles_total = (long long)cb * (cb + 1) / 2;
+    for (long long t = blockIdx.x; t < tiles_total; t += gridDim.x) {
+    __syncthreads();                                                  // shared staging is reused by the next tile
     int row_blk = (int)floor(((2.0 * cb + 1.0) - sqrt((2.0 * cb + 1.0) * (2.0 * cb + 1.0) - 8.0 * (double)t)) * 0.5);
     row_blk = max(0, min(row_blk, cb - 1));
     while (row_blk > 0 && (long long)row_blk * cb - (long long)row_blk * (row_blk - 1) / 2 > t) --row_blk;
     while ((long long)(row_blk + 1) * cb - (long long)(row_blk + 1) * row_blk / 2 <= t) ++row_blk;
     const int col_blk = row_blk + (int)(t - ((long long)row_blk * cb - (long long)row_blk * (row_blk - 1) / 2));
-    if (row_blk * 64 >= n || col_blk * 64 >= n) return;
+    if (row_blk >= cbn) break;                                        // rows are enumerated in order: nothing live follows
+    if (col_blk >= cbn) continue;
     const int mode = (int)info[2 * j + 1];
     const float off_unit = __uint_as_float(info[2 * j]) + 1.0f;       // max_coordinate + 1
     const cldet_candidate* c = sorted + (int64_t)j * capacity;
@@ -1014,6 +1027,7 @@ nms_mask_kernel(const cldet_candidate* __restrict__ sorted, const int32_t* __res
         const uint64_t all = (uint64_t)part[0][rr] | ((uint64_t)part[1][rr] << 16) | ((uint64_t)part[2][rr] << 32) |
                              ((uint64_t)part[3][rr] << 48);
         mask[(int64_t)j * mask_stride_img + (int64_t)ri * col_blocks_alloc + col_blk] = all;
+    }
     }
 }
 
@@ -1219,7 +1233,7 @@ nms_resolve_smem_kernel(const int32_t* __restrict__ counts, int64_t capacity, co
 // nms_resolve_kernel (K > 1216) and, when it wins, the whole-mask-in-shared-memory variant.
 constexpr int kStreamThreads = 1024;
 constexpr int kStreamAbsorbWarps = 24;     // warps 1..24 absorb, 25..28 prefetch, warp 0 runs the chain
-constexpr int kStreamUnroll = 8;            // independent loads in flight per absorber thread
+constexpr int kStreamUnroll = 16;           // independent loads in flight per absorber thread (192 column words per round)
 
 __global__ void __launch_bounds__(kStreamThreads)
 nms_resolve_stream_kernel(const int32_t* __restrict__ counts, int64_t capacity, const uint64_t* __restrict__ mask,
@@ -1262,20 +1276,37 @@ nms_resolve_stream_kernel(const int32_t* __restrict__ counts, int64_t capacity, 
             const int rows = min(64, n - c * 64);
             uint64_t cur = removed[c];
             if (rows < 64) cur |= ~0ull << rows;                           // slots past the end can never be kept
-            uint64_t kept = 0;
+            // Greedy scan of the chunk: box b survives iff its bit is still clear when the scan reaches it; a survivor ORs
+            // its diagonal word (bits > b only) into the removed set.  Bit b is final once the scan has passed it, so the
+            // survivors are simply the clear bits at the end.  Done on 32-bit halves: the dependent chain is one bit test
+            // and one predicated OR per box.
+            uint32_t clo = (uint32_t)cur, chi = (uint32_t)(cur >> 32);
 #pragma unroll
-            for (int g = 0; g < 4; ++g) {
+            for (int g = 0; g < 2; ++g) {
                 uint64_t w[16];
 #pragma unroll
                 for (int q = 0; q < 16; ++q) w[q] = diag[buf][g * 16 + q];
 #pragma unroll
                 for (int q = 0; q < 16; ++q) {
                     const int b = g * 16 + q;
-                    const bool take = !((cur >> b) & 1ull);
-                    kept |= take ? (1ull << b) : 0ull;
-                    cur |= take ? w[q] : 0ull;
+                    const bool take = !((clo >> b) & 1u);
+                    clo |= take ? (uint32_t)w[q] : 0u;
+                    chi |= take ? (uint32_t)(w[q] >> 32) : 0u;
                 }
             }
+#pragma unroll
+            for (int g = 2; g < 4; ++g) {
+                uint32_t w[16];
+#pragma unroll
+                for (int q = 0; q < 16; ++q) w[q] = (uint32_t)(diag[buf][g * 16 + q] >> 32);
+#pragma unroll
+                for (int q = 0; q < 16; ++q) {
+                    const int b = g * 16 + q - 32;
+                    const bool take = !((chi >> b) & 1u);
+                    chi |= take ? w[q] : 0u;
+                }
+            }
+            const uint64_t kept = ~(((uint64_t)chi << 32) | clo);
             if (c + 1 < cb) {                                             // what chunk c+1 needs from this chunk
                 const uint64_t v = (((kept >> lane) & 1ull) ? nextb[buf][lane] : 0ull) |
                                    (((kept >> (lane + 32)) & 1ull) ? nextb[buf][lane + 32] : 0ull);
@@ -1302,29 +1333,25 @@ nms_resolve_stream_kernel(const int32_t* __restrict__ counts, int64_t capacity, 
         } else if (c >= 1 && c + 1 < cb) {
             // Absorb chunk c-1's kept rows into the column words c+1 ..  A warp = 8 rows x 4 consecutive words (one 32-byte
             // sector per row); the 24 warps = 8 row groups x 3 sector slots.  Every thread issues kStreamUnroll INDEPENDENT
-            // loads per round (one L2 latency per round, not per row), the 8 rows of a warp are OR-reduced with shuffles and
-            // 4 lanes publish the words with shared-memory atomics.
+            // loads per round (one L2 latency per round, not per row) and publishes the nonzero words -- few: a box
+            // suppresses a handful of others -- with shared-memory atomics.
             const int aw = warp - 1;
             const int b = (aw & 7) * 8 + (lane >> 2), wq = lane & 3, ss = aw >> 3;
             const uint64_t kp = kept_s[buf ^ 1];
             const bool on = (kp >> b) & 1ull;
             const uint64_t* rowp = m + ((int64_t)(c - 1) * 64 + b) * col_blocks_alloc;
             constexpr int kSlots = kStreamAbsorbWarps / 8;                // sector slots per round
-            for (int w0 = c + 1 + 4 * ss; w0 < cb; w0 += 4 * kSlots * kStreamUnroll) {
-                uint64_t v[kStreamUnroll];
+            if (on) {
+                for (int w0 = c + 1 + 4 * ss + wq; w0 < cb; w0 += 4 * kSlots * kStreamUnroll) {
+                    uint64_t v[kStreamUnroll];
 #pragma unroll
-                for (int u = 0; u < kStreamUnroll; ++u) {
-                    const int wd = w0 + 4 * kSlots * u + wq;
-                    v[u] = (on && wd < cb) ? rowp[wd] : 0ull;
-                }
+                    for (int u = 0; u < kStreamUnroll; ++u) {
+                        const int wd = w0 + 4 * kSlots * u;
+                        v[u] = (wd < cb) ? rowp[wd] : 0ull;
+                    }
 #pragma unroll
-                for (int u = 0; u < kStreamUnroll; ++u) {
-                    uint64_t x = v[u];
-                    x |= __shfl_xor_sync(0xffffffffu, x, 4);
-                    x |= __shfl_xor_sync(0xffffffffu, x, 8);
-                    x |= __shfl_xor_sync(0xffffffffu, x, 16);
-                    const int wd = w0 + 4 * kSlots * u + lane;
-                    if (lane < 4 && x && wd < cb) atomicOr(&removed[wd], (unsigned long long)x);
+                    for (int u = 0; u < kStreamUnroll; ++u)
+                        if (v[u]) atomicOr(&removed[w0 + 4 * kSlots * u], (unsigned long long)v[u]);     // rare: suppression is sparse
                 }
             }
         }
@@ -1747,7 +1774,8 @@ static int nms_sorted_impl(const cldet_candidate* d_sorted, const int32_t* d_sor
                               vanilla_numel_limit, w.info));
     const long long tiles = (long long)w.col_blocks * (w.col_blocks + 1) / 2;          // upper-triangular tiles per image
     if (tiles > 2147483647ll) return CLDET_ERR_UNSUPPORTED;
-    dim3 grid((unsigned)tiles, (unsigned)num_images);
+    // blocks stride over the tile index space: a generous capacity does not cost empty blocks
+    dim3 grid((unsigned)std::min<long long>(tiles, std::max<long long>(1, (long long)sm_count() * 64 / num_images)), (unsigned)num_images);
     CLDET_CUDA_TRY(launch_pdl(nms_mask_kernel, grid, dim3(256), 0, s, d_sorted, d_sorted_counts, capacity, (const uint32_t*)w.info, iou_thresh,
                               w.mask, w.mask_stride_img, w.col_blocks));
     const int resolve = resolve_choice();          // 0 default, 1 stream, 2 whole mask in shared memory, 3 legacy (A/B experiments)

@@ -23,6 +23,7 @@
 #include <stdlib.h>
 
 #include <algorithm>
+#include <cmath>
 #include <string>
 #include <unordered_map>
 #include <vector>
@@ -297,10 +298,18 @@ std::vector<Tensor> focal_loss(const Tensor& cls, const Tensor& reg, const Tenso
 // ---- eval-mode detection output for a batch: K4 decode+filter -> K5 ordering (+ optional top-k) -> K6 NMS -> gather ----
 // Returns the padded result (scores[N,cap], labels[N,cap] int64, boxes[N,cap,4], counts[N] int32, candidates[N] int32) and
 // NEVER synchronises.  With pre_nms_topk == 0 (the reference's mode) the per-image capacity `cap` is
-// `capacity` when > 0, else an optimistic kOptimisticCapacity: the caller reads counts and candidates back together (the one
+// `capacity` when > 0, else optimistic_capacity() (sized so that the batch's NMS masks stay small): the caller reads counts and candidates back together (the one
 // read it needs anyway to slice the results) and, only if some image had more candidates than cap, calls again with
 // capacity = that count.
-constexpr int64_t kOptimisticCapacity = 4096;
+constexpr int64_t kOptimisticCapacity = 4096;           // at least this many candidates per image fit the first attempt
+constexpr int64_t kOptimisticMaskBytes = 128ll << 20;   // ... and as many as keep the batch's suppression masks under this
+
+int64_t optimistic_capacity(int64_t n, int64_t a) {
+    // mask bytes of a batch = n * cap^2 / 8: one image gets ~32 k candidates, 32 images ~5.8 k each
+    int64_t cap = (int64_t)std::sqrt((double)kOptimisticMaskBytes * 8.0 / (double)std::max<int64_t>(n, 1));
+    cap = std::max<int64_t>(kOptimisticCapacity, cap / 64 * 64);
+    return std::min<int64_t>(a, cap);
+}
 
 std::vector<Tensor> detect(const Tensor& cls, const Tensor& reg, const Tensor& anchors, int64_t height, int64_t width, bool is_logits,
                            double score_thresh, double iou_thresh, int64_t pre_nms_topk, int64_t nms_mode,
@@ -332,7 +341,7 @@ std::vector<Tensor> detect(const Tensor& cls, const Tensor& reg, const Tensor& a
         max_count = a;
         cap = std::min<int64_t>(topk, a);
     } else {
-        cap = max_count = std::min<int64_t>(a, capacity > 0 ? capacity : kOptimisticCapacity);
+        cap = max_count = capacity > 0 ? std::min<int64_t>(a, capacity) : optimistic_capacity(n, a);
     }
     Tensor sorted = at::empty({n, cap, (int64_t)sizeof(cldet_candidate)}, u8);
     Tensor sorted_counts = at::empty({n}, i32);

@@ -14,9 +14,9 @@ Only tests/, __graft_entry__.smoke() and bench.py's baseline leg may import this
 cl_object_detection_b200/ does.
 
 Pinned (tests/test_oracle_golden.py::test_torch_eager_*) against the golden vectors generated from the unmodified
-reference: state-0 and default-flag incremental FocalLoss fixtures (losses, autograd gradients), decode + clip, and
-predict.  Covers the default CLI flags of main.py:116-177 (what every BASELINE config uses); the IL flag variants are
-checked through the numpy oracle.
+reference: state-0, default-flag incremental AND every IL-flag FocalLoss fixture (ignore_past_class, new_ignore_past_class,
+enhance_on_new, decrease_positive, decrease_positive_by_IOU, all together: losses and autograd gradients), decode + clip, and
+predict.
 
 Reference statements restated here (paths relative to /root/reference):
   pairwise_iou          retinanet/losses.py:4-21
@@ -41,28 +41,68 @@ def pairwise_iou(boxes_a, boxes_b):
     return (iw * ih) / union
 
 
-def _image_terms(prob, reg, anchor, geom, gt, alpha, gamma):
-    """(bg, fg, reg) of one image with at least one GT row; every line is one or two eager kernels."""
+class ILFlags:
+    """The incremental-state switches FocalLoss.forward reads from `params` (losses.py:317-384); all off = state 0."""
+
+    def __init__(self, past=0, ignore_past_class=False, new_ignore_past_class=False, enhance_on_new=False, decrease_positive=1.0,
+                 decrease_positive_by_iou=False):
+        self.past = int(past)
+        self.ignore_past_class = bool(ignore_past_class)
+        self.new_ignore_past_class = bool(new_ignore_past_class)
+        self.enhance_on_new = bool(enhance_on_new)
+        self.decrease_positive = float(decrease_positive)
+        self.decrease_positive_by_iou = bool(decrease_positive_by_iou)
+
+
+def _image_terms(prob, reg, anchor, geom, gt, alpha, gamma, il=None):
+    """(bg, fg, reg, enhance) of one image with at least one GT row; every line is one or two eager kernels.
+    il = ILFlags for an incremental state (losses.py:317-384), None for state 0."""
     dev = prob.device
     iou = pairwise_iou(anchor, gt[:, :4])
     best, which = torch.max(iou, dim=1)
     target = torch.full(prob.shape, -1.0, device=dev)
     background = best < 0.4
     positive = best >= 0.5
-    target[background, :] = 0
+    if il is None or not il.ignore_past_class:
+        target[background, :] = 0
+    else:
+        # old-class columns of background anchors stay "ignore" (:319-322) unless the anchor's old-class mass is small (:323-328)
+        target[background, il.past:] = 0
+        if il.new_ignore_past_class:
+            old_mass = prob[:, :il.past].sum(dim=1)
+            target[background & (old_mass < 0.5), :il.past] = 0
     npos = positive.sum()
     matched = gt[which, :]
     target[positive, :] = 0
     target[positive, matched[positive, 4].long()] = 1
     is_one = target == 1.0
-    weight = torch.full(prob.shape, alpha, device=dev) * torch.pow(torch.where(is_one, 1.0 - prob, prob), gamma)
+    if il is None:
+        base = torch.where(is_one, 1.0 - prob, prob)
+    elif il.decrease_positive_by_iou:
+        base = torch.where(is_one, 1.0 - prob, prob)
+        mid = positive & (best <= 0.7)                                   # :354
+        mid_one = torch.zeros(prob.shape, device=dev)
+        mid_one[mid, matched[mid, 4].long()] = 1
+        upper = torch.clip(best + 0.2, 1e-4, 1 - 1e-4).unsqueeze(1)      # :361
+        capped = torch.where(prob >= upper, torch.full(prob.shape, 1e-4, device=dev), torch.abs(prob - upper))
+        base = torch.where(mid_one == 1, capped, base)
+    else:
+        s = il.decrease_positive                                         # :365-366
+        base = torch.where(is_one, s - torch.clip(prob, 0, s), prob)
+    weight = torch.full(prob.shape, alpha, device=dev) * torch.pow(base, gamma)
     bce = -(target * torch.log(prob) + (1.0 - target) * torch.log(1.0 - prob))
     loss = torch.where(target != -1.0, weight * bce, torch.zeros(prob.shape, device=dev))
+    enhance = torch.zeros((), device=dev)
+    if il is not None and il.enhance_on_new:                             # :380-384
+        new_cols = prob[background, il.past:]
+        hot = new_cols > 0.05
+        if int(hot.sum()) != 0:
+            enhance = torch.pow(new_cols[hot], 2).sum()
     norm = torch.clamp(npos.float(), min=1.0)
     bg = loss[target == 0.0].sum() / norm
     fg = loss[is_one].sum() / norm
     if int(npos) == 0:                                   # host sync, as in the reference
-        return bg, fg, torch.zeros((), device=dev)
+        return bg, fg, torch.zeros((), device=dev), enhance
     aw, ah, acx, acy = (g[positive] for g in geom)
     rows = matched[positive, :]
     gw = rows[:, 2] - rows[:, 0]
@@ -75,17 +115,19 @@ def _image_terms(prob, reg, anchor, geom, gt, alpha, gamma):
     t = t / torch.tensor([[0.1, 0.1, 0.2, 0.2]], device=dev)
     diff = torch.abs(t - reg[positive, :])
     sl1 = torch.where(diff <= 1.0 / 9.0, 0.5 * 9.0 * torch.pow(diff, 2), diff - 0.5 / 9.0)
-    return bg, fg, sl1.mean()
+    return bg, fg, sl1.mean(), enhance
 
 
-def focal_loss(classifications, regressions, anchors, annotations, alpha=0.25, gamma=2.0):
-    """-> (bg[N], fg[N], reg_loss[1]); differentiable through torch autograd.  Default-flag FocalLoss.forward."""
+def focal_loss(classifications, regressions, anchors, annotations, alpha=0.25, gamma=2.0, il=None):
+    """-> (bg[N], fg[N], reg_loss[1]) -- plus the enhance_on_new sum as a 4th value when `il` (ILFlags) is given;
+    differentiable through torch autograd.  FocalLoss.forward for state 0 (il=None) or an incremental state."""
     dev = classifications.device
     anchor = anchors[0]
     aw = anchor[:, 2] - anchor[:, 0]
     ah = anchor[:, 3] - anchor[:, 1]
     geom = (aw, ah, anchor[:, 0] + 0.5 * aw, anchor[:, 1] + 0.5 * ah)
     bgs, fgs, regs = [], [], []
+    enhance = torch.zeros((), device=dev)
     for j in range(classifications.shape[0]):
         rows = annotations[j]
         gt = rows[rows[:, 4] != -1]
@@ -97,11 +139,13 @@ def focal_loss(classifications, regressions, anchors, annotations, alpha=0.25, g
             fgs.append(torch.zeros((), device=dev))
             regs.append(torch.zeros((), device=dev))
             continue
-        bg, fg, rg = _image_terms(prob, regressions[j], anchor, geom, gt, alpha, gamma)
+        bg, fg, rg, enh = _image_terms(prob, regressions[j], anchor, geom, gt, alpha, gamma, il)
         bgs.append(bg)
         fgs.append(fg)
         regs.append(rg)
-    return torch.stack(bgs), torch.stack(fgs), torch.stack(regs).mean(dim=0, keepdim=True)
+        enhance = enhance + enh
+    out = (torch.stack(bgs), torch.stack(fgs), torch.stack(regs).mean(dim=0, keepdim=True))
+    return out if il is None else out + (enhance,)
 
 
 def decode_boxes(anchors, deltas):

@@ -651,6 +651,54 @@ def test_full_size_vs_torch_eager_on_the_same_device(h, w, C, N, G, exact, empty
     assert ((gr - rr).abs() - 1e-5 * rr.abs()).max().item() <= 1e-5 * rr.abs().max().item()
 
 
+@pytest.mark.parametrize('flags', [dict(ignore_past_class=True, enhance_on_new=True),
+                                   dict(ignore_past_class=True, new_ignore_past_class=True, decrease_positive=0.8),
+                                   dict(decrease_positive_by_IOU=True, enhance_on_new=True)])
+def test_full_size_il_flags_vs_torch_eager_on_the_same_device(flags):
+    """BASELINE config 2 at full size (16 x 512x512, 15 old + 1 new class, pseudo-label GT rows, state 1) WITH incremental
+    flags switched on, against the torch-eager restatement (pinned bit-exactly on every IL fixture of the reference) on the
+    same GPU: per-image terms, the enhance_on_new sum, and every gradient element at 1e-5."""
+    from oracle import torch_eager as E
+    h, w, C, N, G, past = 512, 512, 16, 16, 20, 15
+    rng = np.random.default_rng(2 + len(flags))
+    A = O.num_anchors(h, w)
+    anchors = cld.generate_anchors(h, w, DEV)
+    gen = torch.Generator(device=DEV).manual_seed(1502)
+    probs = torch.sigmoid(torch.randn(N, A, C, device=DEV, generator=gen) * 2 - 3)
+    reg = torch.randn(N, A, 4, device=DEV, generator=gen)
+    ann = cu(synth_gt(rng, N, G, h, w, C, empty=(3,), pseudo_split=past))
+    wb = torch.rand(N, device=DEV, generator=gen) + 0.5
+    wf = torch.rand(N, device=DEV, generator=gen) + 0.5
+    params = cld.HeadParams([0, past], **flags)
+    il = E.ILFlags(past=past, ignore_past_class=flags.get('ignore_past_class', False),
+                   new_ignore_past_class=flags.get('new_ignore_past_class', False), enhance_on_new=flags.get('enhance_on_new', False),
+                   decrease_positive=flags.get('decrease_positive', 1.0),
+                   decrease_positive_by_iou=flags.get('decrease_positive_by_IOU', False))
+
+    def run(fn):
+        c = probs.clone().requires_grad_(True)
+        r = reg.clone().requires_grad_(True)
+        bg, fg, rl, enh = fn(c, r)
+        ((bg * wb).sum() + (fg * wf).sum() + 0.7 * rl.sum() + 0.3 * enh).backward()
+        return bg.detach(), fg.detach(), rl.detach(), enh.detach(), c.grad, r.grad
+
+    def ours(c, r):
+        out = cld.FocalLoss()(c, r, anchors, ann, 1, params)
+        return out['cls_loss'][0], out['cls_loss'][1], out['reg_loss'], out.get('enhance_on_new_loss', torch.zeros((), device=DEV))
+
+    got = run(ours)
+    ref = run(lambda c, r: E.focal_loss(c, r, anchors, ann, il=il))
+    for k in range(4):
+        check_rel(got[k].cpu().numpy(), ref[k].cpu().numpy())
+    gc, rc = got[4], ref[4]
+    assert torch.equal(gc == 0, rc == 0), 'zero-gradient pattern (ignore / out-of-band / old-class columns) differs'
+    err = ((gc - rc).abs() / (rc.abs() + 1e-12 * rc.abs().max() + 1e-45)).max().item()
+    assert err < 1e-5, err
+    gr, rr = got[5], ref[5]
+    assert torch.equal(gr == 0, rr == 0)
+    assert ((gr - rr).abs() - 1e-5 * rr.abs()).max().item() <= GRAD_REG_ABS * rr.abs().max().item()
+
+
 # ---- SURVEY 8(f) row f1, second half: the loss on the head's raw conv outputs (per-level NCHW) ----
 def _level_shapes(h, w):
     return [((h + 2 ** l - 1) // 2 ** l, (w + 2 ** l - 1) // 2 ** l) for l in range(3, 8)]

@@ -233,18 +233,37 @@ def test_a9_collate_and_pseudo_filter_match_reference():
 
 
 # ---- the torch-eager restatement (oracle/torch_eager.py): same fixtures, gradients through autograd ----
-@pytest.mark.parametrize('case', ['state0_voc', 'state0_allvalid', 'state0_allempty', 'state0_gamma15', 'il_default_pseudo'])
+def eager_flags(g, params):
+    """ILFlags of a focal fixture (None for state 0), as oracle/torch_eager.py takes them."""
+    from oracle import torch_eager as E
+    state = int(g['cur_state'])
+    if state == 0:
+        return None
+    return E.ILFlags(past=int(g['num_past_class'][state]), ignore_past_class=params['ignore_past_class'],
+                     new_ignore_past_class=params['new_ignore_past_class'], enhance_on_new=params['enhance_on_new'],
+                     decrease_positive=params['decrease_positive'], decrease_positive_by_iou=params['decrease_positive_by_IOU'])
+
+
+@pytest.mark.parametrize('case', FOCAL_CASES)
 def test_torch_eager_focal_matches_reference(case):
+    """The torch-eager restatement against EVERY focal fixture of the unmodified reference -- state 0 and all IL flag
+    variants -- so that the -m gpu tests can use it as a full-size, same-device oracle for the flags too."""
     import torch
     from oracle import torch_eager as E
     g = load('focal_' + case)
     params = golden_params(g)
+    il = eager_flags(g, params)
     anchors = torch.from_numpy(O.anchors_for_image(int(g['h']), int(g['w'])))
     cls = torch.from_numpy(g['cls']).requires_grad_(True)
     reg = torch.from_numpy(g['reg']).requires_grad_(True)
-    bg, fg, rl = E.focal_loss(cls, reg, anchors, torch.from_numpy(g['ann']), params['alpha'], params['gamma'])
-    # the fixture's upstream weights: dL/dbg_j = wb_j, dL/dfg_j = wf_j, dL/dreg_loss = wr
-    ((bg * torch.from_numpy(g['wb'])).sum() + (fg * torch.from_numpy(g['wf'])).sum() + rl.sum() * float(g['wr'])).backward()
+    out = E.focal_loss(cls, reg, anchors, torch.from_numpy(g['ann']), params['alpha'], params['gamma'], il)
+    bg, fg, rl = out[:3]
+    # the fixture's upstream weights: dL/dbg_j = wb_j, dL/dfg_j = wf_j, dL/dreg_loss = wr, dL/d(enhance_on_new_loss) = we
+    total = (bg * torch.from_numpy(g['wb'])).sum() + (fg * torch.from_numpy(g['wf'])).sum() + rl.sum() * float(g['wr'])
+    if il is not None and il.enhance_on_new:
+        total = total + out[3] * float(g['we'])
+        assert rel_err(out[3].detach().numpy(), g['enhance_on_new_loss'], 1e-30) < 1e-6
+    total.backward()
     # the same torch ops in the same order as the reference on the same CPU: identical bits
     assert np.array_equal(bg.detach().numpy(), g['bg'])
     assert np.array_equal(fg.detach().numpy(), g['fg'])
