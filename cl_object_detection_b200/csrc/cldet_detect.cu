@@ -101,8 +101,9 @@ decode_filter_kernel(const float* __restrict__ cls, int is_logits, const float4*
                      uint64_t* __restrict__ keys, int64_t capacity, int32_t* __restrict__ counts) {
     pdl_launch_dependents();          // head of the chain: the select / sort kernel may be scheduled while this grid drains
     extern __shared__ float part[];          // [rows_per_block][stride] per-vector maxima; stride is odd: conflict-free
-    __shared__ int warp_tot[kFilterThreads / 32];
-    __shared__ int block_base;
+    // per vector (VEC == 4): bits 0-1 = index of the FIRST element attaining the vector's maximum, bit 2 = another element of
+    // the vector comes within reach of it (could tie it in probability) -- lets phase 2 skip the re-read of the winning vector
+    unsigned char* vinfo = reinterpret_cast<unsigned char*>(part + (size_t)rows_per_block * stride);
 
     const int j = blockIdx.y;
     const int64_t a0 = (int64_t)blockIdx.x * rows_per_block;
@@ -136,7 +137,19 @@ decode_filter_kernel(const float* __restrict__ cls, int is_logits, const float4*
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
                     const int v = v0 + u * kFilterThreads;
-                    if (v < nvec) part[idx[u]] = fmaxf(fmaxf(x[u].x, x[u].y), fmaxf(x[u].z, x[u].w));
+                    if (v < nvec) {
+                        const float hi1 = fmaxf(x[u].x, x[u].y), lo1 = fminf(x[u].x, x[u].y);
+                        const float hi2 = fmaxf(x[u].z, x[u].w), lo2 = fminf(x[u].z, x[u].w);
+                        const float m = fmaxf(hi1, hi2);
+                        const float s2 = fmaxf(fminf(hi1, hi2), fmaxf(lo1, lo2));          // second largest of the four
+                        // first index attaining the maximum (ties go to the lower index, like torch.max)
+                        const int first = (hi1 >= hi2) ? ((x[u].x >= x[u].y) ? 0 : 1) : ((x[u].z >= x[u].w) ? 2 : 3);
+                        // logits: a runner-up within 0.05 (or both saturated) may tie the maximum's fp32 sigmoid;
+                        // probabilities: equal values tie and the first index already wins
+                        const bool reach = is_logits && (s2 >= ((m > 10.05f) ? 10.0f : m - 0.05f));
+                        part[idx[u]] = m;
+                        vinfo[idx[u]] = (unsigned char)(first | (reach ? 4 : 0));
+                    }
                 }
             }
         } else {
@@ -178,22 +191,30 @@ decode_filter_kernel(const float* __restrict__ cls, int is_logits, const float4*
             // when the max is) is evaluated exactly; anything lower is smaller by >= 2e-6 relative, far beyond rounding.
             const float t = is_logits ? ((m > 10.05f) ? 10.0f : m - 0.05f) : m;
             const float* row = base + (int64_t)r * C;
-            best = -1.0f;
-            // usually only the vector holding the maximum qualifies; otherwise walk every vector in class order
-            const int k_lo = (m2 >= t) ? 0 : kmax;
-            const int k_hi = (m2 >= t) ? ppr : kmax + 1;
-            for (int k = k_lo; k < k_hi; ++k) {
-                if (p[k] >= t) {
+            const int info = (VEC == 4) ? (int)vinfo[r * stride + kmax] : 4;
+            if (VEC == 4 && !(info & 4) && (is_logits ? (m2 < t) : true)) {
+                // the common case: one element can attain the maximum probability (for probabilities: the first of the equal
+                // maxima, and kmax is the first vector that holds it) -- known from phase 1, nothing is re-read
+                best = is_logits ? sigmoid_exact(m) : m;
+                best_c = kmax * VEC + (info & 3);
+            } else {
+                best = -1.0f;
+                // walk every vector that can hold a winner, in class order
+                const int k_lo = (m2 >= t) ? 0 : kmax;
+                const int k_hi = (m2 >= t) ? ppr : kmax + 1;
+                for (int k = k_lo; k < k_hi; ++k) {
+                    if (p[k] >= t) {
 #pragma unroll
-                    for (int e = 0; e < VEC; ++e) {
-                        const int c = k * VEC + e;
-                        if (c < C) {
-                            const float x = row[c];
-                            if (x >= t) {
-                                const float pr = is_logits ? sigmoid_exact(x) : x;
-                                if (pr > best) {          // strict: first maximal index, like torch.max(dim=1)
-                                    best = pr;
-                                    best_c = c;
+                        for (int e = 0; e < VEC; ++e) {
+                            const int c = k * VEC + e;
+                            if (c < C) {
+                                const float x = row[c];
+                                if (x >= t) {
+                                    const float pr = is_logits ? sigmoid_exact(x) : x;
+                                    if (pr > best) {          // strict: first maximal index, like torch.max(dim=1)
+                                        best = pr;
+                                        best_c = c;
+                                    }
                                 }
                             }
                         }
@@ -203,27 +224,19 @@ decode_filter_kernel(const float* __restrict__ cls, int is_logits, const float4*
             is_cand = best > score_thresh;                // model.py:536  scores > 0.05
         }
     }
-    // block-aggregated append: one atomic per block
+    // warp-aggregated append: one atomic per warp, issued BEFORE the survivors' decode so that its round trip to L2 overlaps
+    // the anchor / regression loads and the two exponentials (a block-wide atomic + barrier made every block wait ~1 us)
     const unsigned ballot = __ballot_sync(0xffffffffu, is_cand);
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    if (lane == 0) warp_tot[warp] = __popc(ballot);
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        int tot = 0;
-#pragma unroll
-        for (int w = 0; w < kFilterThreads / 32; ++w) {
-            const int c = warp_tot[w];
-            warp_tot[w] = tot;
-            tot += c;
-        }
-        block_base = tot ? atomicAdd(&counts[j], tot) : 0;
-    }
-    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    int warp_base = 0;
+    if (ballot != 0u && lane == 0) warp_base = atomicAdd(&counts[j], __popc(ballot));
+    float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+    const int64_t an = a0 + r;
+    if (is_cand) b = decode_clip(anchors[an], reg[(int64_t)j * A + an], img_w, img_h);
+    warp_base = __shfl_sync(0xffffffffu, warp_base, 0);
     if (is_cand) {
-        const int64_t slot = (int64_t)block_base + warp_tot[warp] + __popc(ballot & ((1u << lane) - 1u));
+        const int64_t slot = (int64_t)warp_base + __popc(ballot & ((1u << lane) - 1u));
         if (slot < capacity) {
-            const int64_t an = a0 + r;
-            const float4 b = decode_clip(anchors[an], reg[(int64_t)j * A + an], img_w, img_h);
             // 32-byte record as two 128-bit stores
             float4* dst = reinterpret_cast<float4*>(cand + (int64_t)j * capacity + slot);
             dst[0] = b;
@@ -262,8 +275,6 @@ decode_filter_head_kernel(const HeadFilterLevels lv, int is_logits, const float4
                           float img_w, float img_h, float score_thresh, float prefilter, cldet_candidate* __restrict__ cand,
                           uint64_t* __restrict__ keys, int64_t capacity, int32_t* __restrict__ counts) {
     pdl_launch_dependents();
-    __shared__ int warp_tot[kHeadFilterPos / 32];
-    __shared__ int block_base;
     const int j = blockIdx.y;
     int l = 0;
     while (l + 1 < lv.n && (int)blockIdx.x >= lv.chunk_off[l + 1]) ++l;
@@ -328,28 +339,22 @@ decode_filter_head_kernel(const HeadFilterLevels lv, int is_logits, const float4
             is_cand = best > score_thresh;                 // model.py:536  scores > 0.05
         }
     }
+    // warp-aggregated append; the atomic's round trip overlaps the survivors' decode (see decode_filter_kernel)
     const unsigned ballot = __ballot_sync(0xffffffffu, is_cand);
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    if (lane == 0) warp_tot[warp] = __popc(ballot);
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        int tot = 0;
-#pragma unroll
-        for (int w = 0; w < kHeadFilterPos / 32; ++w) {
-            const int cnt = warp_tot[w];
-            warp_tot[w] = tot;
-            tot += cnt;
-        }
-        block_base = tot ? atomicAdd(&counts[j], tot) : 0;
-    }
-    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    int warp_base = 0;
+    if (ballot != 0u && lane == 0) warp_base = atomicAdd(&counts[j], __popc(ballot));
+    float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+    const int64_t an = lv.anchor_off[l] + (int64_t)pp * kAnchorsPerCell + k;
     if (is_cand) {
-        const int64_t slot = (int64_t)block_base + warp_tot[warp] + __popc(ballot & ((1u << lane) - 1u));
+        const float* rp = lv.reg[l] + ((int64_t)j * (kAnchorsPerCell * 4) + k * 4) * hw + pp;
+        const float4 d = make_float4(rp[0], rp[hw], rp[2 * (int64_t)hw], rp[3 * (int64_t)hw]);
+        b = decode_clip(anchors[an], d, img_w, img_h);
+    }
+    warp_base = __shfl_sync(0xffffffffu, warp_base, 0);
+    if (is_cand) {
+        const int64_t slot = (int64_t)warp_base + __popc(ballot & ((1u << lane) - 1u));
         if (slot < capacity) {
-            const int64_t an = lv.anchor_off[l] + (int64_t)pp * kAnchorsPerCell + k;
-            const float* rp = lv.reg[l] + ((int64_t)j * (kAnchorsPerCell * 4) + k * 4) * hw + pp;
-            const float4 d = make_float4(rp[0], rp[hw], rp[2 * (int64_t)hw], rp[3 * (int64_t)hw]);
-            const float4 b = decode_clip(anchors[an], d, img_w, img_h);
             float4* dst = reinterpret_cast<float4*>(cand + (int64_t)j * capacity + slot);
             dst[0] = b;
             dst[1] = make_float4(best, __int_as_float(best_c), __int_as_float((int)an), 0.0f);
@@ -716,7 +721,7 @@ __global__ void __launch_bounds__(256)
 rank_sort_kernel(const cldet_candidate* __restrict__ cand, const uint64_t* __restrict__ keys, const uint32_t* __restrict__ state,
                  const int32_t* __restrict__ counts_in, int64_t in_capacity, int topk, cldet_candidate* __restrict__ sorted,
                  int64_t out_capacity, int32_t* __restrict__ sorted_counts, const cldet_candidate* __restrict__ orig_cand = nullptr,
-                 const uint64_t* __restrict__ orig_keys = nullptr, int64_t orig_capacity = 0) {
+                 const uint64_t* __restrict__ orig_keys = nullptr, int64_t orig_capacity = 0, int64_t max_n = 0) {
     pdl_wait();                       // may be scheduled while the previous kernel of the chain drains
     pdl_launch_dependents();
     __shared__ uint64_t tile[1024];
@@ -730,6 +735,7 @@ rank_sort_kernel(const cldet_candidate* __restrict__ cand, const uint64_t* __res
         n = (int64_t)counts_in[j];
     }
     n = min64(n, in_capacity);
+    if (max_n > 0 && n > max_n) return;      // a long list: the radix sort kernel launched next to this one orders it
     if (topk <= 0 && n > out_capacity) {     // no top-k and more candidates than the sorted list can hold: report an EMPTY list;
         if (blockIdx.x == 0 && threadIdx.x == 0) sorted_counts[j] = 0;      // the caller sees counts[j] > capacity and re-runs
         return;
@@ -786,7 +792,7 @@ constexpr int kRsBins = 256;
 __global__ void __launch_bounds__(kRsThreads)
 radix_sort_kernel(const cldet_candidate* __restrict__ cand, const uint64_t* __restrict__ keys, const int32_t* __restrict__ counts,
                   int64_t in_capacity, int64_t max_count, cldet_candidate* __restrict__ sorted, int64_t out_capacity,
-                  int32_t* __restrict__ sorted_counts, uint64_t* __restrict__ kbuf, uint32_t* __restrict__ ibuf) {
+                  int32_t* __restrict__ sorted_counts, uint64_t* __restrict__ kbuf, uint32_t* __restrict__ ibuf, int64_t min_n = 0) {
     pdl_wait();                       // may be scheduled while the previous kernel of the chain drains
     pdl_launch_dependents();
     __shared__ uint32_t hist[8][kRsBins];
@@ -796,6 +802,7 @@ radix_sort_kernel(const cldet_candidate* __restrict__ cand, const uint64_t* __re
     __shared__ int skip[8];
     const int j = blockIdx.x;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (min_n > 0 && min64(counts[j], in_capacity) <= min_n) return;      // a short list: the rank sort launched before this kernel ordered it
     if (counts[j] > max_count) {            // more candidates than the buffers were sized for: report an EMPTY list; the caller
         if (threadIdx.x == 0) sorted_counts[j] = 0;      // sees counts[j] > capacity and repeats the call at the exact size
         return;
@@ -1582,7 +1589,7 @@ int cldet_decode_filter(const float* d_cls, int is_logits, const float* d_reg, c
         prefilter = score_thresh;                // exact: the score IS the raw maximum
     }
     dim3 grid((unsigned)((num_anchors + rows - 1) / rows), (unsigned)num_images);
-    const size_t smem = (size_t)rows * stride * sizeof(float);
+    const size_t smem = (size_t)rows * stride * (sizeof(float) + 1) + 16;      // per-vector maxima + per-vector info bytes
     cudaStream_t s = (cudaStream_t)stream;
     if (vec == 4)
         decode_filter_kernel<4><<<grid, kFilterThreads, smem, s>>>(
@@ -1712,19 +1719,26 @@ int cldet_sort_candidates(const cldet_candidate* d_candidates, const uint64_t* d
                 (unsigned)num_images);
         CLDET_CUDA_TRY(launch_pdl(rank_sort_kernel, gr, dim3(256), 0, s, (const cldet_candidate*)sel_cand, (const uint64_t*)sel_keys,
                                   (const uint32_t*)state, d_counts, max_count, topk, d_sorted, sorted_capacity, d_sorted_counts,
-                                  d_candidates, d_keys, capacity));
+                                  d_candidates, d_keys, capacity, (int64_t)0));
     } else if (max_count > kRadixMin && !force_rank_sort()) {
         // the reference's mode (no top-k) with long lists: one launch, one CTA per image, every radix pass inside it
         uint64_t* kbuf = reinterpret_cast<uint64_t*>(p + off);
         off = align_up(off + (size_t)num_images * 2 * max_count * sizeof(uint64_t), 256);
         uint32_t* ibuf = reinterpret_cast<uint32_t*>(p + off);
+        // the host only knows an upper bound of the counts: short lists (the trained-model regime) go to the pairwise rank
+        // sort, whose grid is sized for kRadixMin candidates; lists longer than that are skipped there and ordered by the
+        // radix kernel -- each image takes exactly one of the two
+        dim3 gshort((unsigned)((kRadixMin + kRankPerBlock - 1) / kRankPerBlock), (unsigned)num_images);
+        CLDET_CUDA_TRY(launch_pdl(rank_sort_kernel, gshort, dim3(256), 0, s, d_candidates, d_keys, (const uint32_t*)nullptr, d_counts,
+                                  capacity, 0, d_sorted, sorted_capacity, d_sorted_counts, (const cldet_candidate*)nullptr,
+                                  (const uint64_t*)nullptr, (int64_t)0, (int64_t)kRadixMin));
         CLDET_CUDA_TRY(launch_pdl(radix_sort_kernel, dim3(num_images), dim3(kRsThreads), 0, s, d_candidates, d_keys, d_counts, capacity,
-                                  max_count, d_sorted, sorted_capacity, d_sorted_counts, kbuf, ibuf));
+                                  max_count, d_sorted, sorted_capacity, d_sorted_counts, kbuf, ibuf, (int64_t)kRadixMin));
     } else {
         dim3 gc((unsigned)std::min<int64_t>((max_count + kRankPerBlock - 1) / kRankPerBlock, 65535 * 16), (unsigned)num_images);
         CLDET_CUDA_TRY(launch_pdl(rank_sort_kernel, gc, dim3(256), 0, s, d_candidates, d_keys, (const uint32_t*)nullptr, d_counts, capacity,
                                   0, d_sorted, sorted_capacity, d_sorted_counts, (const cldet_candidate*)nullptr,
-                                  (const uint64_t*)nullptr, (int64_t)0));
+                                  (const uint64_t*)nullptr, (int64_t)0, (int64_t)0));
     }
     return CLDET_OK;
 }
@@ -1779,7 +1793,7 @@ static int nms_sorted_impl(const cldet_candidate* d_sorted, const int32_t* d_sor
     CLDET_CUDA_TRY(launch_pdl(nms_mask_kernel, grid, dim3(256), 0, s, d_sorted, d_sorted_counts, capacity, (const uint32_t*)w.info, iou_thresh,
                               w.mask, w.mask_stride_img, w.col_blocks));
     const int resolve = resolve_choice();          // 0 default, 1 stream, 2 whole mask in shared memory, 3 legacy (A/B experiments)
-    if (resolve == 1 || (resolve == 0 && max_count > kSmemResolveMax)) {
+    if (resolve == 0 || resolve == 1 || max_count > kSmemResolveMax) {          // default: the pipelined kernel, for every K
         const size_t smem = (size_t)w.col_blocks * sizeof(unsigned long long);
         if (smem > 200 * 1024) return CLDET_ERR_UNSUPPORTED;
         if (smem > 40 * 1024)
