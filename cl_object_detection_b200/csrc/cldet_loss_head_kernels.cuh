@@ -31,6 +31,16 @@ constexpr int kHeadMaskWords = kHeadPos / 32;
 #ifndef CLDET_HEAD_MINBLOCKS
 #define CLDET_HEAD_MINBLOCKS 5
 #endif
+// Bulk-copy (TMA) sweep: every warp owns a ring of kHeadStages row buffers (kHeadPos floats each) in dynamic shared memory
+#ifndef CLDET_HEAD_STAGES
+#define CLDET_HEAD_STAGES 3
+#endif
+#ifndef CLDET_HEAD_TMA_MINBLOCKS
+#define CLDET_HEAD_TMA_MINBLOCKS 4
+#endif
+constexpr int kHeadStages = CLDET_HEAD_STAGES;
+constexpr int kHeadWarps = kLossThreads / 32;
+constexpr size_t kHeadStageBytes = (size_t)kHeadWarps * kHeadStages * kHeadPos * sizeof(float);
 constexpr int kHeadMaxLevels = 8;
 constexpr int kHeadTypes = 9;           // anchors per position (3 ratios x 3 scales, retinanet/anchors.py:10-19)
 
@@ -57,7 +67,7 @@ __device__ __forceinline__ float head_element(float x, int c, uint32_t m, int64_
     float g;
     const bool target1 = (st == CLDET_STATE_POS) && ((uint32_t)c == meta_label(m));
     if (GAMMA2 && !VARIANTS && !target1) {
-        g = neg_element_raw<GRAD>(p, as_bg, acc.raw[lane4]);
+        g = neg_element_raw<GRAD>(p, as_bg, acc.raw);
     } else {
         float iou = 1.0f;
         if (need_iou && st == CLDET_STATE_POS) iou = a.iou_max[anchor_abs];
@@ -67,18 +77,48 @@ __device__ __forceinline__ float head_element(float x, int c, uint32_t m, int64_
     return g;
 }
 
-// Target-0 element with a 0/1 weight (0: the element is ignored or is a positive anchor's own class, handled separately):
-// neg_element_raw with the weight folded into the loss term and the gradient scale -- no branch.
+// Target-0 PAIR with 0/1 weights (0: the element is ignored or is a positive anchor's own class, handled separately):
+// neg_pair_raw with the weight folded into the loss term and the gradient scale -- no branch, packed arithmetic.
 template <bool GRAD>
-__device__ __forceinline__ float neg_element_raw_w(float p_raw, float as, float w, float& raw) {
-    const float p = fminf(fmaxf(p_raw, 1e-4f), 0.9999f);
-    const float q = 1.0f - p;
-    const float L = log_fast(q);
-    raw = fmaf(-(p * p) * w, L, raw);
-    if (!GRAD) return 0.0f;
-    const float t = fmaf(L, -2.0f, p * __frcp_rn_fast(q));
-    const float g = ((as * w) * p) * t;
-    return (p == p_raw) ? g : 0.0f;
+__device__ __forceinline__ f32x2 neg_pair_raw_w(float p0_raw, float p1_raw, float as, f32x2 w, f32x2& rawn) {
+    const float p0 = fminf(fmaxf(p0_raw, 1e-4f), 0.9999f);
+    const float p1 = fminf(fmaxf(p1_raw, 1e-4f), 0.9999f);
+    const f32x2 p = pk2(p0, p1);
+    const f32x2 q = fma2(p, bc2(-1.0f), bc2(1.0f));
+    float q0, q1;
+    upk2(q, q0, q1);
+    const f32x2 L = log_fast2(q0, q1);
+    rawn = fma2(mul2(mul2(p, p), w), L, rawn);
+    if (!GRAD) return 0ull;
+    const f32x2 t = fma2(L, bc2(-2.0f), mul2(p, pk2(__frcp_rn_fast(q0), __frcp_rn_fast(q1))));
+    const f32x2 g = mul2(mul2(mul2(bc2(as), w), p), t);
+    float g0, g1;
+    upk2(g, g0, g1);
+    return pk2((p0 == p0_raw) ? g0 : 0.0f, (p1 == p1_raw) ? g1 : 0.0f);
+}
+
+// Four consecutive positions of one class row whose anchors are ALL plain background (the common case by far): the bare
+// packed pairs, no weights, no look-ups.
+template <bool GRAD, bool LOGITS>
+__device__ __forceinline__ float4 head_vec_plain(const float4 x, float as_bg, Acc& acc) {
+    float p0 = x.x, p1 = x.y, p2 = x.z, p3 = x.w;
+    f32x2 pa = 0ull, pb = 0ull;
+    if (LOGITS) {
+        pa = sigmoid_exact2(p0, p1);
+        pb = sigmoid_exact2(p2, p3);
+        upk2(pa, p0, p1);
+        upk2(pb, p2, p3);
+    }
+    f32x2 ga = neg_pair_raw<GRAD>(p0, p1, as_bg, acc.rawn[0]);
+    f32x2 gb = neg_pair_raw<GRAD>(p2, p3, as_bg, acc.rawn[1]);
+    if (GRAD && LOGITS) {
+        ga = sigmoid_bwd2(ga, pa);
+        gb = sigmoid_bwd2(gb, pb);
+    }
+    float4 g;
+    upk2(ga, g.x, g.y);
+    upk2(gb, g.z, g.w);
+    return g;
 }
 
 // A positive anchor's own class (target 1) when no IL variant is active: f = 1 - p in all three reference branches
@@ -104,10 +144,14 @@ __device__ __forceinline__ float4 head_vec(const float4 x, int c, uint32_t plain
                                            const LossArgs& a, const ImageScales& sc, float as_bg, bool need_iou, Acc& acc) {
     float4 g;
     if (GAMMA2 && !VARIANTS) {
-        const float p0 = LOGITS ? sigmoid_exact(x.x) : x.x;
-        const float p1 = LOGITS ? sigmoid_exact(x.y) : x.y;
-        const float p2 = LOGITS ? sigmoid_exact(x.z) : x.z;
-        const float p3 = LOGITS ? sigmoid_exact(x.w) : x.w;
+        float p0 = x.x, p1 = x.y, p2 = x.z, p3 = x.w;
+        f32x2 pa = 0ull, pb = 0ull;
+        if (LOGITS) {
+            pa = sigmoid_exact2(p0, p1);
+            pb = sigmoid_exact2(p2, p3);
+            upk2(pa, p0, p1);
+            upk2(pb, p2, p3);
+        }
         float w0 = 1.0f, w1 = 1.0f, w2 = 1.0f, w3 = 1.0f;
         uint32_t own = 0;                                               // elements that are a positive anchor's own class
         if (plain4 != 0xFu) {
@@ -126,10 +170,10 @@ __device__ __forceinline__ float4 head_vec(const float4 x, int c, uint32_t plain
             }
             w0 = wgt[0]; w1 = wgt[1]; w2 = wgt[2]; w3 = wgt[3];
         }
-        g.x = neg_element_raw_w<GRAD>(p0, as_bg, w0, acc.raw[0]);
-        g.y = neg_element_raw_w<GRAD>(p1, as_bg, w1, acc.raw[1]);
-        g.z = neg_element_raw_w<GRAD>(p2, as_bg, w2, acc.raw[2]);
-        g.w = neg_element_raw_w<GRAD>(p3, as_bg, w3, acc.raw[3]);
+        const f32x2 ga = neg_pair_raw_w<GRAD>(p0, p1, as_bg, pk2(w0, w1), acc.rawn[0]);
+        const f32x2 gb = neg_pair_raw_w<GRAD>(p2, p3, as_bg, pk2(w2, w3), acc.rawn[1]);
+        upk2(ga, g.x, g.y);
+        upk2(gb, g.z, g.w);
         if (own) {
             const float pv[4] = {p0, p1, p2, p3};
             float gv[4] = {g.x, g.y, g.z, g.w};
@@ -144,10 +188,8 @@ __device__ __forceinline__ float4 head_vec(const float4 x, int c, uint32_t plain
             g = make_float4(gv[0], gv[1], gv[2], gv[3]);
         }
         if (GRAD && LOGITS) {
-            g.x = sigmoid_bwd(g.x, p0);
-            g.y = sigmoid_bwd(g.y, p1);
-            g.z = sigmoid_bwd(g.z, p2);
-            g.w = sigmoid_bwd(g.w, p3);
+            upk2(sigmoid_bwd2(pk2(g.x, g.y), pa), g.x, g.y);
+            upk2(sigmoid_bwd2(pk2(g.z, g.w), pb), g.z, g.w);
         }
     } else {
         g.x = head_element<GAMMA2, VARIANTS, GRAD, LOGITS>(x.x, c, mp[0], anchor_abs, a, sc, as_bg, need_iou, acc, 0);
@@ -158,9 +200,13 @@ __device__ __forceinline__ float4 head_vec(const float4 x, int c, uint32_t plain
     return g;
 }
 
-template <bool GAMMA2, bool VARIANTS, bool GRAD, bool LOGITS>
+// TMA: compile the bulk-copy sweep (fused forward+backward launch only; `stage` = the block's dynamic shared memory,
+// `bars` = kHeadWarps * kHeadStages mbarriers).  It is taken for chunks of planes whose rows are 16-byte aligned (H_l*W_l a
+// multiple of 4 floats: 94 % of a COCO-shaped batch); the other chunks run the register sweeps below.
+template <bool GAMMA2, bool VARIANTS, bool GRAD, bool LOGITS, bool TMA = false>
 __device__ __forceinline__ void head_chunk(const LossArgs& a, const HeadLevels& lv, int j, int chunk, int mode,
-                                           const ImageScales& sc, Acc& acc, uint32_t* smeta, uint32_t* plain) {
+                                           const ImageScales& sc, Acc& acc, uint32_t* smeta, uint32_t* plain,
+                                           float* stage = nullptr, unsigned long long* bars = nullptr) {
     const int tid = threadIdx.x;
     const int lane = tid & 31, warp = tid >> 5;
     constexpr int kWarps = kLossThreads / 32;
@@ -174,6 +220,36 @@ __device__ __forceinline__ void head_chunk(const LossArgs& a, const HeadLevels& 
     const int64_t an0 = lv.anchor_off[l] + (int64_t)p0 * kHeadTypes + k;    // anchor of position p0; stride kHeadTypes
     const int C = a.C;
     const bool need_iou = VARIANTS && a.p.incremental && a.p.decrease_positive_by_iou;
+    const float* src = lv.cls[l] + ((int64_t)j * (kHeadTypes * C) + (int64_t)k * C) * hw + p0;
+    float* dst = GRAD ? lv.gcls[l] + ((int64_t)j * (kHeadTypes * C) + (int64_t)k * C) * hw + p0 : nullptr;
+    // 128-bit / bulk accesses need 16-byte aligned addresses; a row starts at float offset (channel * hw + p0) from the tensor base
+    const bool base_ok = (((uintptr_t)lv.cls[l] | (uintptr_t)lv.gcls[l]) & 15) == 0;
+
+    // ---- bulk-copy sweep, part 1: this warp's first rows start moving into its ring before the prologue runs ----
+    bool use_tma = false;
+    int my_rows = 0;
+    uint32_t row_bytes = 0, bar0 = 0, buf0 = 0;
+    if constexpr (TMA) {
+        use_tma = base_ok && (hw & 3) == 0;                              // block-uniform
+        if (use_tma) {
+            my_rows = warp < C ? (C - warp + kWarps - 1) / kWarps : 0;   // rows warp, warp + kWarps, ...
+            row_bytes = (uint32_t)np * 4u;                               // np % 4 == 0 here
+            bar0 = smem_u32(bars + warp * kHeadStages);
+            buf0 = smem_u32(stage + (size_t)warp * kHeadStages * kHeadPos);
+            if (lane == 0) {
+#pragma unroll
+                for (int st = 0; st < kHeadStages; ++st) mbar_init(bar0 + 8u * st, 1u);
+                fence_async_smem();
+#pragma unroll
+                for (int i = 0; i < kHeadStages - 1; ++i) {
+                    if (i < my_rows) {
+                        mbar_expect_tx(bar0 + 8u * i, row_bytes);
+                        bulk_load(buf0 + (uint32_t)(i * kHeadPos * 4), src + (int64_t)(warp + kWarps * i) * hw, row_bytes, bar0 + 8u * i);
+                    }
+                }
+            }
+        }
+    }
 
     // ---- regression gradient rows of this type (4 rows of np floats): zero, positives overwrite theirs after the barrier ----
     float* greg_rows = GRAD ? lv.greg[l] + ((int64_t)j * (kHeadTypes * 4) + k * 4) * hw + p0 : nullptr;
@@ -189,7 +265,7 @@ __device__ __forceinline__ void head_chunk(const LossArgs& a, const HeadLevels& 
     const float* reg_rows = lv.reg[l] + ((int64_t)j * (kHeadTypes * 4) + k * 4) * hw + p0;
     for (int pp0 = 0; pp0 < kHeadPos; pp0 += kLossThreads) {                // uniform trip count: the ballot needs whole warps
         const int pp = pp0 + tid;
-        bool is_plain = false;
+        bool is_plain = pp >= np;                                           // positions past the end count as plain (never swept)
         if (pp < np) {
             const int64_t an = an0 + (int64_t)pp * kHeadTypes;
             const int64_t gi = (int64_t)j * a.A + an;
@@ -231,13 +307,72 @@ __device__ __forceinline__ void head_chunk(const LossArgs& a, const HeadLevels& 
     // ---- classification rows: C rows of np contiguous positions, one warp per row ----
     const float alpha_img = (meta_state(smeta[0]) == CLDET_STATE_EMPTY) ? 1.0f - a.p.alpha : a.p.alpha;
     const float as_bg = alpha_img * sc.s_bg;
-    const float* src = lv.cls[l] + ((int64_t)j * (kHeadTypes * C) + (int64_t)k * C) * hw + p0;
-    float* dst = GRAD ? lv.gcls[l] + ((int64_t)j * (kHeadTypes * C) + (int64_t)k * C) * hw + p0 : nullptr;
     const int64_t abs0 = (int64_t)j * a.A + an0;
-    // 128-bit accesses need 16-byte aligned addresses; a row starts at float offset row_off = (channel * hw + p0) from the
-    // (16-byte aligned) tensor base, so up to 3 leading and 3 trailing positions of a row are handled with 32-bit accesses.
-    const bool base_ok = (((uintptr_t)lv.cls[l] | (uintptr_t)lv.gcls[l]) & 15) == 0;
     constexpr int kU = kHeadPos / 128;                                   // kU x 32 lanes x 16 B = one full row per round
+    constexpr uint32_t kAllPlain = 0xFFFFFFFFu >> (32 - 4 * kU);
+    if constexpr (TMA) {
+        if (use_tma) {
+            // ---- bulk-copy sweep, part 2.  Row i of this warp lives in ring slot i % kHeadStages: wait for its bytes, compute
+            // the gradients IN PLACE in shared memory (every lane rewrites exactly the vectors it read), hand the slot to the
+            // copy engine as a bulk store, and refill the slot freed one iteration ago with row i + kHeadStages - 1.  No
+            // block-wide barrier and no register-held load in the loop: kHeadStages - 1 rows per warp are always in flight.
+            uint32_t pm = 0;
+#pragma unroll
+            for (int u = 0; u < kU; ++u) {
+                const int q = lane + 32 * u;
+                pm |= ((plain[q >> 3] >> ((q & 7) * 4)) & 0xFu) << (4 * u);
+            }
+            const bool all_plain = GAMMA2 && !VARIANTS && __all_sync(0xffffffffu, pm == kAllPlain);
+            const uint32_t* mp = smeta + 4 * lane;
+            const int64_t ab = abs0 + (int64_t)(4 * lane) * kHeadTypes;
+            float* ring = stage + (size_t)warp * kHeadStages * kHeadPos;
+            int slot = 0;
+            uint32_t parity = 0;
+            for (int i = 0; i < my_rows; ++i) {
+                const int c = warp + kWarps * i;
+                mbar_wait(bar0 + 8u * slot, parity);
+                float* b = ring + slot * kHeadPos + 4 * lane;
+                if (all_plain) {
+#pragma unroll
+                    for (int u = 0; u < kU; ++u) {
+                        if (4 * lane + 128 * u < np) {
+                            float4* v = reinterpret_cast<float4*>(b + 128 * u);
+                            *v = head_vec_plain<GRAD, LOGITS>(*v, as_bg, acc);
+                        }
+                    }
+                } else {
+#pragma unroll
+                    for (int u = 0; u < kU; ++u) {
+                        if (4 * lane + 128 * u < np) {
+                            float4* v = reinterpret_cast<float4*>(b + 128 * u);
+                            *v = head_vec<GAMMA2, VARIANTS, GRAD, LOGITS>(*v, c, (pm >> (4 * u)) & 0xFu, mp + 128 * u,
+                                                                         ab + (int64_t)(128 * u) * kHeadTypes, a, sc,
+                                                                         as_bg, need_iou, acc);
+                        }
+                    }
+                }
+                fence_async_smem();                                      // this lane's writes -> visible to the copy engine
+                __syncwarp();
+                if (lane == 0) {
+                    bulk_store(dst + (int64_t)c * hw, buf0 + (uint32_t)(slot * kHeadPos * 4), row_bytes);
+                    bulk_commit();
+                    const int r = i + kHeadStages - 1;                   // next row to fetch, into the slot of row i - 1
+                    if (r < my_rows) {
+                        if (i >= 1) bulk_wait_read<1>();                 // the store of row i - 1 has drained its slot
+                        const int rs = (slot == 0) ? kHeadStages - 1 : slot - 1;
+                        mbar_expect_tx(bar0 + 8u * rs, row_bytes);
+                        bulk_load(buf0 + (uint32_t)(rs * kHeadPos * 4), src + (int64_t)(warp + kWarps * r) * hw, row_bytes, bar0 + 8u * rs);
+                    }
+                }
+                if (++slot == kHeadStages) {
+                    slot = 0;
+                    parity ^= 1u;
+                }
+            }
+            if (lane == 0) bulk_wait_all<0>();                           // the ring must outlive the stores that read it
+            return;
+        }
+    }
     if (base_ok && (hw & 3) == 0 && np == kHeadPos) {
         // Full rows of an aligned plane (94 % of a COCO-shaped batch): no bounds checks, and the plain-background bits of this
         // lane's kU vectors do not depend on the class row, so they are looked up once per chunk.
@@ -246,6 +381,31 @@ __device__ __forceinline__ void head_chunk(const LossArgs& a, const HeadLevels& 
         for (int u = 0; u < kU; ++u) {
             const int q = lane + 32 * u;
             pm |= ((plain[q >> 3] >> ((q & 7) * 4)) & 0xFu) << (4 * u);
+        }
+        // Non-background anchors cluster around the GT boxes: for most blocks ALL kHeadPos positions of this anchor type are
+        // plain background, and then the sweep is the bare packed math (a warp-uniform choice made once per block, so each
+        // warp runs exactly one of the two loops).
+        if (GAMMA2 && !VARIANTS && __all_sync(0xffffffffu, pm == kAllPlain)) {
+            for (int c = warp; c < C; c += kWarps) {
+                const float* sp = src + (int64_t)c * hw + 4 * lane;
+                float* dp = GRAD ? dst + (int64_t)c * hw + 4 * lane : nullptr;
+                float4 x[kU];
+#pragma unroll
+                for (int u = 0; u < kU; ++u) {
+                    asm volatile(CLDET_LD_QUAL ".v4.f32 {%0,%1,%2,%3}, [%4];"
+                                 : "=f"(x[u].x), "=f"(x[u].y), "=f"(x[u].z), "=f"(x[u].w)
+                                 : "l"(sp + 128 * u));
+                }
+#pragma unroll
+                for (int u = 0; u < kU; ++u) {
+                    const float4 g = head_vec_plain<GRAD, LOGITS>(x[u], as_bg, acc);
+                    if (GRAD) {
+                        asm volatile(CLDET_ST_QUAL ".v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(dp + 128 * u), "f"(g.x), "f"(g.y), "f"(g.z), "f"(g.w)
+                                     : "memory");
+                    }
+                }
+            }
+            return;
         }
         const uint32_t* mp = smeta + 4 * lane;
         const int64_t ab = abs0 + (int64_t)(4 * lane) * kHeadTypes;
@@ -320,8 +480,13 @@ __device__ __forceinline__ void head_chunk(const LossArgs& a, const HeadLevels& 
     }
 }
 
+// The fused forward+backward launch (GRAD) carries the bulk-copy sweep: kHeadStageBytes of dynamic shared memory per block,
+// CLDET_HEAD_TMA_MINBLOCKS blocks per SM.  The forward-only launch keeps the register sweeps and needs no dynamic memory.
 template <bool GAMMA2, bool VARIANTS, bool GRAD, bool LOGITS>
-__global__ void __launch_bounds__(kLossThreads, CLDET_HEAD_MINBLOCKS) focal_loss_head_kernel(const LossArgs a, const HeadLevels lv) {
+__global__ void __launch_bounds__(kLossThreads, GRAD ? CLDET_HEAD_TMA_MINBLOCKS : CLDET_HEAD_MINBLOCKS)
+    focal_loss_head_kernel(const LossArgs a, const HeadLevels lv) {
+    extern __shared__ __align__(128) float head_stage[];
+    __shared__ __align__(8) unsigned long long bars[kHeadWarps * kHeadStages];
     __shared__ float red[4][kLossThreads / 32];
     __shared__ double fin[4][kLossThreads / 32];
     __shared__ bool is_last;
@@ -331,8 +496,8 @@ __global__ void __launch_bounds__(kLossThreads, CLDET_HEAD_MINBLOCKS) focal_loss
     const int j = blockIdx.y;
     const int npos = a.npos[j];
     const ImageScales sc = image_scales(a, j, npos);
-    Acc acc = {0.f, 0.f, 0.f, 0.f, {0.f, 0.f, 0.f, 0.f}};
-    head_chunk<GAMMA2, VARIANTS, GRAD, LOGITS>(a, lv, j, (int)blockIdx.x, 0, sc, acc, smeta, plain);
+    Acc acc = acc_zero();
+    head_chunk<GAMMA2, VARIANTS, GRAD, LOGITS, GRAD>(a, lv, j, (int)blockIdx.x, 0, sc, acc, smeta, plain, head_stage, bars);
     finish_block(a, j, (int)blockIdx.x, acc, npos, sc, red, fin, &is_last);
 }
 
@@ -351,7 +516,7 @@ __global__ void __launch_bounds__(kLossThreads, 4) focal_head_reweight_kernel(co
     if (!changed) return;
     const ImageScales sc = image_scales(a, j, a.npos[j]);
     for (int chunk = blockIdx.x; chunk < a.bpi; chunk += gridDim.x) {
-        Acc acc = {0.f, 0.f, 0.f, 0.f, {0.f, 0.f, 0.f, 0.f}};
+        Acc acc = acc_zero();
         head_chunk<GAMMA2, VARIANTS, true, LOGITS>(a, lv, j, chunk, 1, sc, acc, smeta, plain);
         __syncthreads();
     }
@@ -396,8 +561,15 @@ template <bool LOGITS>
 void run_head_loss_kernels(const LossArgs& a, const HeadLevels& lv, bool grad, bool gamma2, bool variants, dim3 grid, cudaStream_t s) {
 #define CLDET_HEAD_LAUNCH(G2, VAR)                                                                              \
     do {                                                                                                        \
-        if (grad) focal_loss_head_kernel<G2, VAR, true, LOGITS><<<grid, kLossThreads, 0, s>>>(a, lv);           \
-        else focal_loss_head_kernel<G2, VAR, false, LOGITS><<<grid, kLossThreads, 0, s>>>(a, lv);               \
+        if (grad) {                                                                                             \
+            static const cudaError_t attr = cudaFuncSetAttribute(focal_loss_head_kernel<G2, VAR, true, LOGITS>, \
+                                                                 cudaFuncAttributeMaxDynamicSharedMemorySize,  \
+                                                                 (int)kHeadStageBytes);                         \
+            (void)attr;                                                                                         \
+            focal_loss_head_kernel<G2, VAR, true, LOGITS><<<grid, kLossThreads, kHeadStageBytes, s>>>(a, lv);   \
+        } else {                                                                                                \
+            focal_loss_head_kernel<G2, VAR, false, LOGITS><<<grid, kLossThreads, 0, s>>>(a, lv);                \
+        }                                                                                                       \
     } while (0)
     if (gamma2) {
         if (variants) CLDET_HEAD_LAUNCH(true, true);
