@@ -200,6 +200,77 @@ __device__ __forceinline__ float4 head_vec(const float4 x, int c, uint32_t plain
     return g;
 }
 
+// State of one warp's bulk-copy row loop (see head_rows_bulk).
+struct BulkRows {
+    float* ring;            // this lane's first vector in ring slot 0 (generic address)
+    uint32_t buf0, bar0;    // shared-memory addresses of the warp's ring and of its mbarriers
+    uint32_t row_bytes;
+    int my_rows;            // rows c0, c0 + kHeadWarps, ...
+    int64_t stride;         // floats between two of this warp's rows: kHeadWarps * hw
+    float* dst_row;         // gradient row of the current iteration
+    const float* src_fetch; // class row to fetch next (row index i + kHeadStages - 1)
+    int c0;
+    int nvec;               // vectors of this lane inside the chunk (ragged chunks)
+    uint32_t pm;            // plain-background bits of the lane's kU vectors
+    const uint32_t* mp;
+    int64_t ab;
+};
+
+// The bulk-copy sweep of one warp.  Row i lives in ring slot i % kHeadStages: wait for its bytes, compute the gradients IN
+// PLACE in shared memory (every lane rewrites exactly the vectors it read), hand the slot to the copy engine as a bulk store,
+// and refill the slot freed one iteration ago with row i + kHeadStages - 1.  No block-wide barrier and no register-held load
+// in the loop: kHeadStages - 1 rows per warp are always in flight.  All addresses advance by constants.
+template <bool GAMMA2, bool VARIANTS, bool GRAD, bool LOGITS, bool PLAIN, bool FULL>
+__device__ __forceinline__ void head_rows_bulk(BulkRows br, const LossArgs& a, const ImageScales& sc, float as_bg, bool need_iou,
+                                               Acc& acc) {
+    constexpr int kU = kHeadPos / 128;
+    constexpr uint32_t kSlotBytes = kHeadPos * 4;
+    const bool lane0 = (threadIdx.x & 31) == 0;
+    int slot = 0;
+    uint32_t parity = 0;
+    int c = br.c0;
+    for (int i = 0; i < br.my_rows; ++i, c += kHeadWarps) {
+        mbar_wait(br.bar0 + 8u * slot, parity);
+        float* b = br.ring + slot * kHeadPos;
+#pragma unroll
+        for (int u = 0; u < kU; ++u) {
+            if (FULL || u < br.nvec) {
+                float4* v = reinterpret_cast<float4*>(b + 128 * u);
+                if (PLAIN) {
+                    *v = head_vec_plain<GRAD, LOGITS>(*v, as_bg, acc);
+                } else {
+                    *v = head_vec<GAMMA2, VARIANTS, GRAD, LOGITS>(*v, c, (br.pm >> (4 * u)) & 0xFu, br.mp + 128 * u,
+                                                                 br.ab + (int64_t)(128 * u) * kHeadTypes, a, sc, as_bg, need_iou, acc);
+                }
+            }
+        }
+        fence_async_smem();                                      // this lane's writes -> visible to the copy engine
+        __syncwarp();
+        if (lane0) {
+            bulk_store(br.dst_row, br.buf0 + kSlotBytes * slot, br.row_bytes);
+            bulk_commit();
+            if (i + kHeadStages - 1 < br.my_rows) {              // next row to fetch goes into the slot of row i - 1
+                if (i >= 1) bulk_wait_read<1>();                 // ... once the store of row i - 1 has drained it
+                const uint32_t rs = (slot == 0) ? kHeadStages - 1 : slot - 1;
+                mbar_expect_tx(br.bar0 + 8u * rs, br.row_bytes);
+                bulk_load(br.buf0 + kSlotBytes * rs, br.src_fetch, br.row_bytes, br.bar0 + 8u * rs);
+            }
+        }
+        br.dst_row += br.stride;
+        br.src_fetch += br.stride;
+        if (++slot == kHeadStages) {
+            slot = 0;
+            parity ^= 1u;
+        }
+    }
+    // the ring must outlive the stores that read it (their global writes complete with the grid)
+#ifdef CLDET_HEAD_WAIT_ALL
+    if (lane0) bulk_wait_all<0>();
+#else
+    if (lane0) bulk_wait_read<0>();
+#endif
+}
+
 // TMA: compile the bulk-copy sweep (fused forward+backward launch only; `stage` = the block's dynamic shared memory,
 // `bars` = kHeadWarps * kHeadStages mbarriers).  It is taken for chunks of planes whose rows are 16-byte aligned (H_l*W_l a
 // multiple of 4 floats: 94 % of a COCO-shaped batch); the other chunks run the register sweeps below.
@@ -251,51 +322,59 @@ __device__ __forceinline__ void head_chunk(const LossArgs& a, const HeadLevels& 
         }
     }
 
-    // ---- regression gradient rows of this type (4 rows of np floats): zero, positives overwrite theirs after the barrier ----
+    // ---- per-anchor prologue: assignment word, outputs keyed by anchor, smooth-L1 for the positives; every position writes its
+    // four regression-gradient values (zeros unless positive) itself -- coalesced across the block, no separate zero pass ----
     float* greg_rows = GRAD ? lv.greg[l] + ((int64_t)j * (kHeadTypes * 4) + k * 4) * hw + p0 : nullptr;
-    if (GRAD) {
-#pragma unroll
-        for (int i = 0; i < 4; ++i)
-            for (int pp = tid; pp < np; pp += kLossThreads) greg_rows[(int64_t)i * hw + pp] = 0.0f;
-    }
-    __syncthreads();
-
-    // ---- per-anchor prologue: assignment word, outputs keyed by anchor, smooth-L1 for the positives ----
     const int nvalid_j = (mode == 0 && a.best) ? a.nvalid[j] : 1;
     const float* reg_rows = lv.reg[l] + ((int64_t)j * (kHeadTypes * 4) + k * 4) * hw + p0;
-    for (int pp0 = 0; pp0 < kHeadPos; pp0 += kLossThreads) {                // uniform trip count: the ballot needs whole warps
-        const int pp = pp0 + tid;
+    constexpr int kRounds = kHeadPos / kLossThreads;                        // uniform trip count: the ballot needs whole warps
+    static_assert(kHeadPos % kLossThreads == 0, "kHeadPos must be a multiple of the block size");
+    // all of a thread's key / word loads are issued before the first is used: the prologue costs one memory latency
+    unsigned long long keys[kRounds];
+    uint32_t words[kRounds];
+#pragma unroll
+    for (int rd = 0; rd < kRounds; ++rd) {
+        const int pp = rd * kLossThreads + tid;
+        keys[rd] = 0ull;
+        words[rd] = 0u;
+        if (pp < np) {
+            const int64_t gi = (int64_t)j * a.A + an0 + (int64_t)pp * kHeadTypes;
+            if (mode == 0 && a.best) keys[rd] = a.best[gi];
+            else words[rd] = a.meta[gi];
+        }
+    }
+#pragma unroll
+    for (int rd = 0; rd < kRounds; ++rd) {
+        const int pp = rd * kLossThreads + tid;
         bool is_plain = pp >= np;                                           // positions past the end count as plain (never swept)
         if (pp < np) {
             const int64_t an = an0 + (int64_t)pp * kHeadTypes;
             const int64_t gi = (int64_t)j * a.A + an;
-            uint32_t m;
+            uint32_t m = words[rd];
             if (mode == 0 && a.best) {
-                const unsigned long long key = a.best[gi];
+                const unsigned long long key = keys[rd];
                 if (key) a.best[gi] = 0ull;                   // leave the scratch zeroed for the next call
                 m = word_from_best(a, j, key, nvalid_j);
                 a.meta_out[gi] = m;
                 if (a.iou_out) a.iou_out[gi] = __uint_as_float((uint32_t)(key >> 32));
-            } else {
-                m = a.meta[gi];
             }
             smeta[pp] = m;
             const uint32_t st = meta_state(m);
             is_plain = (st == CLDET_STATE_BG || st == CLDET_STATE_EMPTY);
             if (mode == 0 && a.bg_mask) a.bg_mask[gi] = (st != CLDET_STATE_POS) ? 1 : 0;
+            float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
             if (st == CLDET_STATE_POS) {
                 const float* rp = reg_rows + pp;
                 const float4 r = make_float4(rp[0], rp[hw], rp[2 * (int64_t)hw], rp[3 * (int64_t)hw]);
-                float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
                 acc.reg += reg_anchor<GRAD>(a, j, an, m, r, sc.s_reg, g);
                 if (mode == 0 && a.status && meta_label(m) == CLDET_BAD_LABEL) *a.status = 1;
-                if (GRAD) {
-                    float* gp = greg_rows + pp;
-                    gp[0] = g.x;
-                    gp[hw] = g.y;
-                    gp[2 * (int64_t)hw] = g.z;
-                    gp[3 * (int64_t)hw] = g.w;
-                }
+            }
+            if (GRAD) {
+                float* gp = greg_rows + pp;
+                gp[0] = g.x;
+                gp[hw] = g.y;
+                gp[2 * (int64_t)hw] = g.z;
+                gp[3 * (int64_t)hw] = g.w;
             }
         }
         const uint32_t bits = __ballot_sync(0xffffffffu, is_plain);
@@ -312,10 +391,8 @@ __device__ __forceinline__ void head_chunk(const LossArgs& a, const HeadLevels& 
     constexpr uint32_t kAllPlain = 0xFFFFFFFFu >> (32 - 4 * kU);
     if constexpr (TMA) {
         if (use_tma) {
-            // ---- bulk-copy sweep, part 2.  Row i of this warp lives in ring slot i % kHeadStages: wait for its bytes, compute
-            // the gradients IN PLACE in shared memory (every lane rewrites exactly the vectors it read), hand the slot to the
-            // copy engine as a bulk store, and refill the slot freed one iteration ago with row i + kHeadStages - 1.  No
-            // block-wide barrier and no register-held load in the loop: kHeadStages - 1 rows per warp are always in flight.
+            // ---- bulk-copy sweep, part 2 (head_rows_bulk): four loop bodies -- all-plain or not, full or ragged chunk --
+            // chosen once per block, so the row loop itself carries no per-vector tests.
             uint32_t pm = 0;
 #pragma unroll
             for (int u = 0; u < kU; ++u) {
@@ -323,53 +400,28 @@ __device__ __forceinline__ void head_chunk(const LossArgs& a, const HeadLevels& 
                 pm |= ((plain[q >> 3] >> ((q & 7) * 4)) & 0xFu) << (4 * u);
             }
             const bool all_plain = GAMMA2 && !VARIANTS && __all_sync(0xffffffffu, pm == kAllPlain);
-            const uint32_t* mp = smeta + 4 * lane;
-            const int64_t ab = abs0 + (int64_t)(4 * lane) * kHeadTypes;
-            float* ring = stage + (size_t)warp * kHeadStages * kHeadPos;
-            int slot = 0;
-            uint32_t parity = 0;
-            for (int i = 0; i < my_rows; ++i) {
-                const int c = warp + kWarps * i;
-                mbar_wait(bar0 + 8u * slot, parity);
-                float* b = ring + slot * kHeadPos + 4 * lane;
-                if (all_plain) {
-#pragma unroll
-                    for (int u = 0; u < kU; ++u) {
-                        if (4 * lane + 128 * u < np) {
-                            float4* v = reinterpret_cast<float4*>(b + 128 * u);
-                            *v = head_vec_plain<GRAD, LOGITS>(*v, as_bg, acc);
-                        }
-                    }
-                } else {
-#pragma unroll
-                    for (int u = 0; u < kU; ++u) {
-                        if (4 * lane + 128 * u < np) {
-                            float4* v = reinterpret_cast<float4*>(b + 128 * u);
-                            *v = head_vec<GAMMA2, VARIANTS, GRAD, LOGITS>(*v, c, (pm >> (4 * u)) & 0xFu, mp + 128 * u,
-                                                                         ab + (int64_t)(128 * u) * kHeadTypes, a, sc,
-                                                                         as_bg, need_iou, acc);
-                        }
-                    }
-                }
-                fence_async_smem();                                      // this lane's writes -> visible to the copy engine
-                __syncwarp();
-                if (lane == 0) {
-                    bulk_store(dst + (int64_t)c * hw, buf0 + (uint32_t)(slot * kHeadPos * 4), row_bytes);
-                    bulk_commit();
-                    const int r = i + kHeadStages - 1;                   // next row to fetch, into the slot of row i - 1
-                    if (r < my_rows) {
-                        if (i >= 1) bulk_wait_read<1>();                 // the store of row i - 1 has drained its slot
-                        const int rs = (slot == 0) ? kHeadStages - 1 : slot - 1;
-                        mbar_expect_tx(bar0 + 8u * rs, row_bytes);
-                        bulk_load(buf0 + (uint32_t)(rs * kHeadPos * 4), src + (int64_t)(warp + kWarps * r) * hw, row_bytes, bar0 + 8u * rs);
-                    }
-                }
-                if (++slot == kHeadStages) {
-                    slot = 0;
-                    parity ^= 1u;
-                }
+            BulkRows br;
+            br.ring = stage + (size_t)warp * kHeadStages * kHeadPos + 4 * lane;
+            br.buf0 = buf0;
+            br.bar0 = bar0;
+            br.row_bytes = row_bytes;
+            br.my_rows = my_rows;
+            br.stride = (int64_t)kWarps * hw;
+            br.dst_row = dst + (int64_t)warp * hw;
+            br.src_fetch = src + (int64_t)(warp + kWarps * (kHeadStages - 1)) * hw;
+            br.c0 = warp;
+            br.nvec = min(kU, max(0, (np - 4 * lane + 127) >> 7));          // this lane's vectors inside the chunk
+            br.pm = pm;
+            br.mp = smeta + 4 * lane;
+            br.ab = abs0 + (int64_t)(4 * lane) * kHeadTypes;
+            const bool full = np == kHeadPos;
+            if (all_plain) {
+                if (full) head_rows_bulk<GAMMA2, VARIANTS, GRAD, LOGITS, true, true>(br, a, sc, as_bg, need_iou, acc);
+                else head_rows_bulk<GAMMA2, VARIANTS, GRAD, LOGITS, true, false>(br, a, sc, as_bg, need_iou, acc);
+            } else {
+                if (full) head_rows_bulk<GAMMA2, VARIANTS, GRAD, LOGITS, false, true>(br, a, sc, as_bg, need_iou, acc);
+                else head_rows_bulk<GAMMA2, VARIANTS, GRAD, LOGITS, false, false>(br, a, sc, as_bg, need_iou, acc);
             }
-            if (lane == 0) bulk_wait_all<0>();                           // the ring must outlive the stores that read it
             return;
         }
     }
