@@ -11,11 +11,13 @@ value : device-resident throughput through the C ABI (inputs already in HBM), CU
 e2e   : the same metric through the public Python drop-in (FocalLoss.forward + autograd) with HOST inputs: every step
         copies cls/reg/annotations from pinned host memory and reads the loss back.
 roofline: the fused loss kernel's algorithmic bytes / its own CUDA-event time inside the timed loop.
-cpu_baseline: the numpy oracle port of the reference timed on this box's host cores (bounded sample), rank 0 only.
+cpu_baseline: the UNMODIFIED reference (byte-code snapshot oracle/_ref, built by oracle/build_ref.py where /root/reference exists)
+        timed on this box's host cores on a bounded sample, rank 0 only (kind "reference"); the numpy oracle port beside it as
+        cpu_baseline_port.  Without the snapshot the port is the baseline (kind "port").
 gpu_eager_baseline (N=1, baseline leg): the reference's own execution model (eager torch ops + autograd, oracle/torch_eager.py)
         on the same GPU and batch -- informative, like cpu_baseline.
 decode (N=1): BASELINE config 4, the other half of the metric: decode + threshold + top-1000 + per-class NMS over 32 images.
---impl reference: times that CPU port only (the reference is pure Python/torch and /root/reference is not on the box).
+--impl reference: times that CPU baseline only (the snapshot when present, else the port; /root/reference is not on the box).
 """
 import argparse
 import ctypes
@@ -272,29 +274,70 @@ def decode_section(dev, with_eager):
     return out
 
 
+def reference_snapshot_available():
+    return os.path.exists(os.path.join(ROOT, 'oracle', '_ref', 'retinanet', 'losses.pyc'))
+
+
+def time_unmodified_reference(images, frac, steps, warmup, threads, timeout=900):
+    """The UNMODIFIED reference (oracle/_ref: byte-code snapshot of retinanet/losses.py built by oracle/build_ref.py) on the host
+    cores, in its own process (its CPU shim patches torch globally).  Returns oracle.ref_runner's JSON dict."""
+    import subprocess
+    cmd = [sys.executable, '-m', 'oracle.ref_runner', '--images', str(images), '--frac', '%.6f' % frac, '--steps', str(steps),
+           '--warmup', str(warmup), '--threads', str(threads)]
+    r = subprocess.run(cmd, cwd=ROOT, capture_output=True, text=True, timeout=timeout)
+    if r.returncode != 0:
+        raise RuntimeError('oracle.ref_runner failed: %s' % r.stderr[-500:])
+    return json.loads(r.stdout.strip().splitlines()[-1])
+
+
 def run_reference(args):
+    """--impl reference: the reference's own CPU implementation of the path on the box's host cores.  With the byte-code snapshot
+    oracle/_ref present (built where /root/reference exists; it travels with the repo) this is the UNMODIFIED FocalLoss.forward +
+    autograd backward (kind "reference"); the numpy port is timed beside it as `cpu_baseline_port`.  Without the snapshot the
+    port is the arm (kind "port")."""
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return 0
     cores = os.cpu_count() or 1
     threads = max(1, min(cores, CPU_THREADS_CAP))
-    images_per_step = threads
-    # keep the whole run to a few minutes: probe a quarter-size step, then pick the anchor fraction of the per-step sample
-    _, probe_step, f0 = time_cpu_reference(1, 0, images_per_step, threads, 0.25)
-    full_step = probe_step / f0
     budget = float(os.environ.get('CLDET_BENCH_BUDGET_S', '150'))      # seconds of CPU work for the whole run (tests shrink it)
-    frac = max(0.02, min(1.0, budget / (full_step * (args.steps + args.warmup))))
-    val, per_step, f = time_cpu_reference(args.steps, args.warmup, images_per_step, threads, frac)
-    sample = ('%d images x %.0f%% of the anchors per step (800x1333, C=80, A=200700 full), numpy port of FocalLoss fwd+bwd, '
-              '%d threads' % (images_per_step, f * 100, threads))
+    total_steps = args.steps + args.warmup
+    port = None
+    if reference_snapshot_available():
+        kind = 'reference'
+        images_per_step = 1
+        probe = time_unmodified_reference(1, 0.1, 1, 0, threads)            # one image, 10 % of the anchors
+        full_step = probe['s_per_step'] / probe['anchor_fraction']
+        frac = max(0.02, min(1.0, 0.8 * budget / (full_step * total_steps)))
+        res = time_unmodified_reference(images_per_step, frac, args.steps, args.warmup, threads, timeout=max(900, 20 * budget))
+        val, per_step, f = res['value'], res['s_per_step'], res['anchor_fraction']
+        sample = ('%d image x %.0f%% of the anchors per step (800x1333, C=80, A=200700 full), UNMODIFIED reference FocalLoss.forward '
+                  '+ autograd backward (retinanet/losses.py byte-code snapshot oracle/_ref, CPU shim of SURVEY 8c), torch %s, '
+                  '%d intra-op threads' % (images_per_step, f * 100, res['torch'], res['threads']))
+        pv, pstep, pf = time_cpu_reference(1, 0, threads, threads, max(0.02, min(1.0, 0.2 * budget / max(full_step / 15.0, 1e-3))))
+        port = {'value': pv, 'unit': 'images/s', 'cores': threads, 'kind': 'port', 'host_cores': cores,
+                'sample': '1 step x %d images x %.0f%% of the anchors, numpy port of FocalLoss fwd+bwd, %d threads'
+                          % (threads, pf * 100, threads)}
+    else:
+        kind = 'port'
+        images_per_step = threads
+        # keep the whole run to a few minutes: probe a quarter-size step, then pick the anchor fraction of the per-step sample
+        _, probe_step, f0 = time_cpu_reference(1, 0, images_per_step, threads, 0.25)
+        full_step = probe_step / f0
+        frac = max(0.02, min(1.0, budget / (full_step * total_steps)))
+        val, per_step, f = time_cpu_reference(args.steps, args.warmup, images_per_step, threads, frac)
+        sample = ('%d images x %.0f%% of the anchors per step (800x1333, C=80, A=200700 full), numpy port of FocalLoss fwd+bwd, '
+                  '%d threads' % (images_per_step, f * 100, threads))
     line = {'impl': 'reference', 'metric': METRIC, 'value': val, 'unit': 'images/s', 'n_gpus': args.gpus, 'steps': args.steps,
             'warmup': args.warmup, 'ms_per_step': per_step * 1e3, 'higher_is_better': True, 'scaling': 'weak',
             'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
             'config': {'workload': WORKLOAD, 'images_per_step': images_per_step * f},
-            'cpu_baseline': {'value': val, 'unit': 'images/s', 'cores': threads, 'kind': 'port', 'sample': sample,
+            'cpu_baseline': {'value': val, 'unit': 'images/s', 'cores': threads, 'kind': kind, 'sample': sample,
                              'host_cores': cores},
             'e2e': {'value': val, 'unit': 'images/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
             'gpu_launches': 0}
+    if port is not None:
+        line['cpu_baseline_port'] = port
     emit(line)
     return 0
 
@@ -670,9 +713,19 @@ def run_ours(args):
         if world == 1 and not args.no_cpu_baseline:
             thr = max(1, min(cores, CPU_THREADS_CAP))
             v, per, _ = time_cpu_reference(steps=2, warmup=0, images_per_step=thr, threads=thr)
-            cpu = {'value': v, 'unit': 'images/s', 'cores': thr, 'kind': 'port', 'host_cores': cores,
-                   'sample': '2 steps x %d COCO-shaped images (800x1333, C=80, A=200700), numpy port of FocalLoss fwd+bwd, '
-                             '%d threads' % (thr, thr)}
+            cpu_port = {'value': v, 'unit': 'images/s', 'cores': thr, 'kind': 'port', 'host_cores': cores,
+                        'sample': '2 steps x %d COCO-shaped images (800x1333, C=80, A=200700), numpy port of FocalLoss fwd+bwd, '
+                                  '%d threads' % (thr, thr)}
+            cpu = cpu_port
+            if reference_snapshot_available():
+                try:
+                    res = time_unmodified_reference(2, 1.0, 2, 1, thr)
+                    cpu = {'value': res['value'], 'unit': 'images/s', 'cores': thr, 'kind': 'reference', 'host_cores': cores,
+                           'sample': '2 steps x 2 COCO-shaped images (800x1333, C=80, A=200700), UNMODIFIED reference FocalLoss.forward '
+                                     '+ autograd backward (byte-code snapshot oracle/_ref), torch %s, %d intra-op threads'
+                                     % (res['torch'], res['threads'])}
+                except Exception as e:  # noqa: BLE001
+                    cpu_port['reference_snapshot_error'] = repr(e)[:200]
         eager = None
         if world == 1 and not args.no_cpu_baseline:
             eager = time_gpu_eager(probs, reg, anchors, ann, n)
@@ -699,6 +752,8 @@ def run_ours(args):
             line['sharded_parity'] = parity
         if cpu is not None:
             line['cpu_baseline'] = cpu
+            if cpu is not cpu_port:
+                line['cpu_baseline_port'] = cpu_port
         if eager is not None:
             line['gpu_eager_baseline'] = eager
         if world == 1 and not args.no_decode:

@@ -1,0 +1,160 @@
+"""TEST / BASELINE INFRASTRUCTURE -- never imported by the product path.
+
+Runs the UNMODIFIED reference (the byte-code snapshot oracle/_ref, see oracle/build_ref.py) on the HOST cores:
+FocalLoss.forward + autograd backward (retinanet/losses.py:252-452) with the caller's reduction (IL_Loss: .mean() of every
+term, losses.py:584-588).  The reference hard-codes cuda:0 (`torch.ones(..., device=torch.device('cuda:0'))`, `.cuda()`);
+SURVEY 8(c)'s shim makes it run on a CPU without touching its code: torch.ones / torch.zeros drop the `device=` keyword
+and Tensor.cuda() is the identity.  The shim patches torch globally, so this module is meant to run in its OWN process:
+
+    python -m oracle.ref_runner --images 2 --frac 0.25 --steps 1 --warmup 0 --threads 16      -> one JSON line
+"""
+import argparse
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+REF = os.path.join(HERE, '_ref')
+
+
+def install_cpu_shim():
+    import torch
+    if getattr(torch, '_cldet_ref_shim', False):
+        return
+    for name in ('ones', 'zeros'):
+        orig = getattr(torch, name)
+
+        def wrapped(*a, _orig=orig, **k):
+            k.pop('device', None)
+            return _orig(*a, **k)
+        setattr(torch, name, wrapped)
+    torch.Tensor.cuda = lambda self, *a, **k: self
+    torch._cldet_ref_shim = True
+
+
+def load_reference():
+    """(FocalLoss class, calc_iou, Anchors class) of the snapshot; raises if it was never built."""
+    if not os.path.exists(os.path.join(REF, 'retinanet', 'losses.pyc')):
+        raise RuntimeError('oracle/_ref is missing: run `python -m oracle.build_ref` where /root/reference exists')
+    install_cpu_shim()
+    if REF not in sys.path:
+        sys.path.insert(0, REF)
+    from retinanet.anchors import Anchors
+    from retinanet.losses import FocalLoss, calc_iou
+    return FocalLoss, calc_iou, Anchors
+
+
+class Params:
+    """Duck type of the reference's preprocessing/params.py Params with main.py:116-177's CLI defaults."""
+
+    def __init__(self, num_past_class=(0,), **kw):
+        self.d = dict(alpha=0.25, gamma=2.0, distill=False, enhance_on_new=False, ignore_past_class=False,
+                      new_ignore_past_class=False, decrease_positive_by_IOU=False, decrease_positive=1.0, persuado_label=False)
+        self.d.update(kw)
+        self.states = [{'num_past_class': n} for n in num_past_class]
+
+    def __getitem__(self, k):
+        return self.d.get(k, None)
+
+
+def focal_step(focal, cls, reg, anchors, ann, cur_state=0, params=None):
+    """One fwd + bwd of the reference module; returns (bg[N], fg[N], reg_loss[1], dL/dcls, dL/dreg) as numpy."""
+    import torch
+    p = torch.from_numpy(cls).requires_grad_(True)
+    r = torch.from_numpy(reg).requires_grad_(True)
+    out = focal(p, r, torch.from_numpy(anchors), torch.from_numpy(ann), cur_state, params or Params())
+    bg, fg = out['cls_loss']
+    (bg.mean() + fg.mean() + out['reg_loss'].mean()).backward()
+    # no positive anchor anywhere: the reference's regression terms are constants and autograd leaves r.grad unset
+    gr = r.grad.numpy() if r.grad is not None else np.zeros_like(reg)
+    return bg.detach().numpy(), fg.detach().numpy(), out['reg_loss'].detach().numpy(), p.grad.numpy(), gr
+
+
+def time_reference(images, frac, steps, warmup, threads, height=800, width=1333, classes=80, gmax=20, seed=1234):
+    """`images` COCO-shaped images per step, the first frac*A anchors of each (every anchor is independent work, so the
+    rate in images/s is images*frac*steps / time); same generator as bench.make_cpu_images."""
+    import torch
+    sys.path.insert(0, ROOT)
+    from bench import synth_annotations
+    from oracle import head_oracle as O
+    FocalLoss, _, _ = load_reference()
+    torch.set_num_threads(max(1, threads))
+    rng = np.random.default_rng(seed)
+    a_full = O.num_anchors(height, width)
+    a = max(1, int(a_full * frac))
+    anchors = O.anchors_for_image(height, width)[:, :a].copy()
+    logits = rng.normal(-4.0, 2.0, (images, a, classes)).astype(np.float32)
+    cls = (1.0 / (1.0 + np.exp(-logits))).astype(np.float32)
+    reg = rng.normal(0, 1, (images, a, 4)).astype(np.float32)
+    ann = synth_annotations(rng, images, gmax, height, width, classes, empty=())
+    focal = FocalLoss()
+    for _ in range(warmup):
+        focal_step(focal, cls, reg, anchors, ann)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        focal_step(focal, cls, reg, anchors, ann)
+    dt = time.perf_counter() - t0
+    f = a / a_full
+    return {'value': images * f * steps / dt, 'unit': 'images/s', 's_per_step': dt / steps, 'images': images, 'anchor_fraction': f,
+            'steps': steps, 'threads': torch.get_num_threads(), 'torch': torch.__version__}
+
+
+def run_npz(path_in, path_out, device):
+    """Parity mode: inputs from an .npz (cls, reg, anchors, ann, cur_state, num_past_class, params_keys, params_vals), outputs of
+    the unmodified reference to another .npz.  device='cuda' runs the reference exactly as written (it hard-codes cuda:0 --
+    the oracle of record on a GPU box); device='cpu' goes through the shim."""
+    import torch
+    d = np.load(path_in, allow_pickle=False)
+    if device == 'cpu':
+        FocalLoss, _, _ = load_reference()
+    else:
+        if REF not in sys.path:
+            sys.path.insert(0, REF)
+        from retinanet.losses import FocalLoss
+    kw = {}
+    for k, v in zip(d['params_keys'], d['params_vals']):
+        k = str(k)
+        kw[k] = float(v) if k in ('alpha', 'gamma', 'decrease_positive') else bool(v)
+    params = Params([int(x) for x in d['num_past_class']], **kw)
+    dev = torch.device('cuda:0' if device == 'cuda' else 'cpu')
+    p = torch.from_numpy(d['cls']).to(dev).requires_grad_(True)
+    r = torch.from_numpy(d['reg']).to(dev).requires_grad_(True)
+    out = FocalLoss()(p, r, torch.from_numpy(d['anchors']).to(dev), torch.from_numpy(d['ann']).to(dev), int(d['cur_state']), params)
+    bg, fg = out['cls_loss']
+    w_bg = torch.from_numpy(d['w_bg']).to(dev)
+    w_fg = torch.from_numpy(d['w_fg']).to(dev)
+    loss = (bg * w_bg).sum() + (fg * w_fg).sum() + out['reg_loss'].sum() * float(d['w_reg'])
+    if 'enhance_on_new_loss' in out:
+        loss = loss + out['enhance_on_new_loss']
+    loss.backward()
+    res = {'bg': bg.detach().cpu().numpy(), 'fg': fg.detach().cpu().numpy(), 'reg_loss': out['reg_loss'].detach().cpu().numpy(),
+           'grad_cls': p.grad.cpu().numpy(), 'grad_reg': (r.grad.cpu().numpy() if r.grad is not None else np.zeros_like(d['reg']))}
+    if 'enhance_on_new_loss' in out:
+        res['enhance'] = np.asarray(float(out['enhance_on_new_loss']), np.float32)
+    if 'bg_masks' in out:
+        res['bg_masks'] = out['bg_masks'].cpu().numpy()
+    np.savez(path_out, **res)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--npz', nargs=2, metavar=('IN', 'OUT'), help='parity mode: run the reference on the inputs of IN, write OUT')
+    ap.add_argument('--device', default='cpu', choices=['cpu', 'cuda'])
+    ap.add_argument('--images', type=int, default=1)
+    ap.add_argument('--frac', type=float, default=1.0)
+    ap.add_argument('--steps', type=int, default=1)
+    ap.add_argument('--warmup', type=int, default=0)
+    ap.add_argument('--threads', type=int, default=os.cpu_count() or 1)
+    a = ap.parse_args()
+    if a.npz:
+        run_npz(a.npz[0], a.npz[1], a.device)
+        return
+    print(json.dumps(time_reference(a.images, a.frac, a.steps, a.warmup, a.threads)))
+
+
+if __name__ == '__main__':
+    main()

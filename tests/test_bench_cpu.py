@@ -17,7 +17,11 @@ def test_reference_arm_prints_one_json_line():
     assert len(lines) == 1
     d = json.loads(lines[0])
     assert d['impl'] == 'reference' and d['unit'] == 'images/s' and d['higher_is_better'] is True and d['value'] > 0
-    assert d['cpu_baseline']['kind'] == 'port' and d['cpu_baseline']['cores'] >= 1 and d['cpu_baseline']['value'] == d['value']
+    snapshot = os.path.exists(os.path.join(ROOT, 'oracle', '_ref', 'retinanet', 'losses.pyc'))
+    assert d['cpu_baseline']['kind'] == ('reference' if snapshot else 'port')
+    assert d['cpu_baseline']['cores'] >= 1 and d['cpu_baseline']['value'] == d['value']
+    if snapshot:          # the numpy port is reported beside the unmodified reference
+        assert d['cpu_baseline_port']['kind'] == 'port' and d['cpu_baseline_port']['value'] > 0
     assert d['e2e'] == {'value': d['value'], 'unit': 'images/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}
     assert d['gpu_launches'] == 0 and d['vs_baseline'] is None and 'workload' in d['config']
 

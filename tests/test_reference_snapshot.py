@@ -1,0 +1,134 @@
+"""Parity against the LIVE reference, beyond the committed fixtures: oracle/_ref is a byte-code snapshot of the reference's
+own retinanet/losses.py (built by oracle/build_ref.py where /root/reference exists; it travels with the repo to the GPU
+box, /root/reference does not).  Fresh seeded inputs that no fixture holds go through the UNMODIFIED FocalLoss.forward +
+autograd backward in a separate process (oracle/ref_runner.py --npz), and
+
+  * CPU  : the numpy oracle must agree with it (pins the oracle on inputs it was not written against);
+  * GPU  : the CUDA path (through the public drop-in -> C++ op layer -> C ABI) must agree with the reference running
+           exactly as written on cuda:0 of the same box -- the parity oracle of record of SURVEY 8(c).
+
+Bars as everywhere: zero-gradient pattern (= ignore / out-of-band / assignment) identical, losses and gradients 1e-5
+relative.  The tests skip (loudly) when the snapshot was never built."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from oracle import head_oracle as O
+from tests.helpers import synth_gt
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+SNAPSHOT = os.path.join(ROOT, 'oracle', '_ref', 'retinanet', 'losses.pyc')
+needs_snapshot = pytest.mark.skipif(not os.path.exists(SNAPSHOT), reason='oracle/_ref not built (python -m oracle.build_ref)')
+
+FLOAT_KEYS = ('alpha', 'gamma', 'decrease_positive')
+# (name, H, W, C, N, G, cur_state, num_past_class, params, empty images, seed)
+CASES = [
+    ('state0', 160, 224, 12, 3, 9, 0, (0,), {}, (1,), 11),
+    ('state0_gamma', 128, 160, 8, 2, 6, 0, (0,), {'gamma': 1.5, 'alpha': 0.3}, (), 12),
+    ('il_pseudo_ignore_past', 160, 160, 10, 3, 8, 1, (0, 6), {'ignore_past_class': True, 'persuado_label': True}, (2,), 13),
+    ('il_all_flags', 128, 192, 10, 3, 8, 1, (0, 6), {'ignore_past_class': True, 'new_ignore_past_class': True, 'distill': True,
+                                                      'enhance_on_new': True, 'decrease_positive_by_IOU': True,
+                                                      'decrease_positive': 0.8}, (), 14),
+]
+
+
+def make_case(H, W, C, N, G, past, seed, empty):
+    rng = np.random.default_rng(seed)
+    anchors = O.anchors_for_image(H, W)
+    A = anchors.shape[1]
+    logits = rng.normal(-3.0, 3.0, (N, A, C)).astype(np.float32)
+    cls = (1.0 / (1.0 + np.exp(-logits.astype(np.float64)))).astype(np.float32)
+    flat = cls.reshape(-1)
+    flat[rng.choice(flat.size, 64, replace=False)] = np.float32(1e-4)           # clamp-boundary values (inclusive pass-band)
+    flat[rng.choice(flat.size, 64, replace=False)] = np.float32(1.0 - 1e-4)
+    flat[rng.choice(flat.size, 64, replace=False)] = np.float32(3e-5)
+    reg = rng.normal(0, 1, (N, A, 4)).astype(np.float32)
+    ann = synth_gt(rng, N, G, H, W, C, empty=empty, pseudo_split=past if past else None)
+    # a few GT boxes equal to anchors so that positives certainly exist
+    for j in range(N):
+        if j not in empty:
+            ann[j, 0, :4] = anchors[0, rng.integers(0, A)]
+    w_bg = rng.uniform(0.1, 1.0, N).astype(np.float32)
+    w_fg = rng.uniform(0.1, 1.0, N).astype(np.float32)
+    w_fg[0] = 0.0                                                                # a clip_loss-masked image
+    return anchors, cls, reg, ann, w_bg, w_fg, np.float32(0.7)
+
+
+def run_reference(tmp_path, name, device, anchors, cls, reg, ann, w_bg, w_fg, w_reg, cur_state, past, params):
+    keys = sorted(params)
+    fin, fout = str(tmp_path / (name + '_in.npz')), str(tmp_path / (name + '_out.npz'))
+    np.savez(fin, cls=cls, reg=reg, anchors=anchors, ann=ann, cur_state=np.int64(cur_state), num_past_class=np.asarray(past, np.int64),
+             params_keys=np.asarray(keys, dtype='U32'), params_vals=np.asarray([float(params[k]) for k in keys], np.float64),
+             w_bg=w_bg, w_fg=w_fg, w_reg=w_reg)
+    r = subprocess.run([sys.executable, '-m', 'oracle.ref_runner', '--npz', fin, fout, '--device', device], cwd=ROOT,
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-3000:]
+    return dict(np.load(fout))
+
+
+def assert_rel(got, want, tol=1e-5, what=''):
+    got, want = np.asarray(got, np.float64), np.asarray(want, np.float64)
+    assert got.shape == want.shape, (what, got.shape, want.shape)
+    assert np.all(np.abs(got - want) <= tol * np.abs(want) + 1e-30), (what, got, want)
+
+
+def assert_grads(got, want, what, abs_scale=0.0):
+    got, want = np.asarray(got), np.asarray(want)
+    assert np.array_equal(got == 0, want == 0), what + ': zero-gradient pattern differs'
+    excess = np.abs(got.astype(np.float64) - want) - 1e-5 * np.abs(want)
+    assert float(excess.max()) <= abs_scale * float(np.abs(want).max()) + 1e-12 * float(np.abs(want).max()), (what, float(excess.max()))
+
+
+@needs_snapshot
+@pytest.mark.parametrize('case', CASES, ids=[c[0] for c in CASES])
+def test_oracle_matches_live_reference_on_fresh_inputs(case, tmp_path):
+    name, H, W, C, N, G, cur_state, past, params, empty, seed = case
+    anchors, cls, reg, ann, w_bg, w_fg, w_reg = make_case(H, W, C, N, G, past[-1], seed, empty)
+    ref = run_reference(tmp_path, name, 'cpu', anchors, cls, reg, ann, w_bg, w_fg, w_reg, cur_state, past, params)
+    kw = {k: (float(v) if k in FLOAT_KEYS else bool(v)) for k, v in params.items()}
+    got = O.focal_loss(cls, reg, anchors, ann, cur_state, O.OracleParams(num_past_class=past, **kw), w_bg=w_bg, w_fg=w_fg,
+                       w_reg=float(w_reg), w_enh=1.0)
+    assert_rel(got['bg'], ref['bg'], what='bg')
+    assert_rel(got['fg'], ref['fg'], what='fg')
+    assert_rel(got['reg_loss'], ref['reg_loss'], what='reg')
+    assert_grads(got['grad_cls'], ref['grad_cls'], 'grad_cls')
+    assert_grads(got['grad_reg'], ref['grad_reg'], 'grad_reg', abs_scale=3e-6)
+    if 'bg_masks' in ref:
+        assert np.array_equal(got['bg_masks'], ref['bg_masks'])
+    if 'enhance' in ref:
+        assert_rel(got['enhance_on_new_loss'], ref['enhance'], what='enhance')
+
+
+@needs_snapshot
+@pytest.mark.gpu
+@pytest.mark.parametrize('case', CASES + [('voc_config1', 512, 512, 20, 2, 10, 0, (0,), {}, (), 15)], ids=[c[0] for c in CASES] + ['voc_config1'])
+def test_cuda_path_matches_reference_running_on_the_same_gpu(case, tmp_path):
+    import torch
+
+    import cl_object_detection_b200 as cld
+    name, H, W, C, N, G, cur_state, past, params, empty, seed = case
+    anchors, cls, reg, ann, w_bg, w_fg, w_reg = make_case(H, W, C, N, G, past[-1], seed, empty)
+    ref = run_reference(tmp_path, name, 'cuda', anchors, cls, reg, ann, w_bg, w_fg, w_reg, cur_state, past, params)
+    kw = {k: (float(v) if k in FLOAT_KEYS else bool(v)) for k, v in params.items()}
+    dev = 'cuda:0'
+    p = torch.from_numpy(cls).to(dev).requires_grad_(True)
+    r = torch.from_numpy(reg).to(dev).requires_grad_(True)
+    out = cld.FocalLoss()(p, r, cld.generate_anchors(H, W, dev), torch.from_numpy(ann).to(dev), cur_state,
+                          cld.HeadParams(list(past), **kw))
+    bg, fg = out['cls_loss']
+    loss = (bg * torch.from_numpy(w_bg).to(dev)).sum() + (fg * torch.from_numpy(w_fg).to(dev)).sum() + out['reg_loss'].sum() * float(w_reg)
+    if 'enhance_on_new_loss' in out:
+        loss = loss + out['enhance_on_new_loss']
+    loss.backward()
+    assert_rel(bg.detach().cpu().numpy(), ref['bg'], what='bg')
+    assert_rel(fg.detach().cpu().numpy(), ref['fg'], what='fg')
+    assert_rel(out['reg_loss'].detach().cpu().numpy(), ref['reg_loss'], what='reg')
+    assert_grads(p.grad.cpu().numpy(), ref['grad_cls'], 'grad_cls')
+    assert_grads(r.grad.cpu().numpy(), ref['grad_reg'], 'grad_reg', abs_scale=3e-6)
+    if 'bg_masks' in ref:
+        assert np.array_equal(out['bg_masks'].cpu().numpy(), ref['bg_masks'])
+    if 'enhance' in ref:
+        assert_rel(out['enhance_on_new_loss'].detach().cpu().numpy(), ref['enhance'], what='enhance')
