@@ -275,7 +275,7 @@ def decode_section(dev, with_eager):
 
 
 def reference_snapshot_available():
-    return os.path.exists(os.path.join(ROOT, 'oracle', '_ref', 'retinanet', 'losses.pyc'))
+    return os.path.exists(os.path.join(ROOT, 'oracle', '_ref', 'retinanet', 'losses.bytecode'))
 
 
 def time_unmodified_reference(images, frac, steps, warmup, threads, timeout=900):

@@ -282,7 +282,9 @@ class FocalLoss(nn.Module):
                 result['bg_masks'] = outs[8].bool()[nvalid > 0]
             if params['enhance_on_new']:
                 result['enhance_on_new_loss'] = enh_j.sum()
-        self.last_npos, self.last_nvalid, self.last_reg_per_image, self.last_meta = npos, nvalid, reg_j, meta
+        # plain attributes, set past nn.Module.__setattr__ (its parameter / buffer / submodule bookkeeping costs ~2 us per tensor)
+        d = self.__dict__
+        d['last_npos'], d['last_nvalid'], d['last_reg_per_image'], d['last_meta'] = npos, nvalid, reg_j, meta
         return result
 
     def forward_head(self, cls_levels, reg_levels, anchors, annotations, cur_state: int, params, image_size, progress=-1):
@@ -332,5 +334,6 @@ class FocalLoss(nn.Module):
                 result['bg_masks'] = outs[6].bool()[nvalid > 0]
             if params['enhance_on_new']:
                 result['enhance_on_new_loss'] = enh_j.sum()
-        self.last_npos, self.last_nvalid, self.last_reg_per_image = npos, nvalid, reg_j
+        d = self.__dict__
+        d['last_npos'], d['last_nvalid'], d['last_reg_per_image'] = npos, nvalid, reg_j
         return result

@@ -36,16 +36,37 @@ def install_cpu_shim():
     torch._cldet_ref_shim = True
 
 
-def load_reference():
-    """(FocalLoss class, calc_iou, Anchors class) of the snapshot; raises if it was never built."""
-    if not os.path.exists(os.path.join(REF, 'retinanet', 'losses.pyc')):
+EXT = '.bytecode'
+
+
+def import_snapshot():
+    """Import the snapshot's modules as the package `retinanet` (byte-code files under a neutral extension, loaded with
+    importlib's SourcelessFileLoader); raises if the snapshot was never built."""
+    import importlib.machinery
+    import importlib.util
+    if 'retinanet.losses' in sys.modules:
+        return sys.modules['retinanet.losses'], sys.modules['retinanet.anchors']
+    pkg_dir = os.path.join(REF, 'retinanet')
+    if not os.path.exists(os.path.join(pkg_dir, 'losses' + EXT)):
         raise RuntimeError('oracle/_ref is missing: run `python -m oracle.build_ref` where /root/reference exists')
+
+    def load(name, fname, is_pkg=False):
+        path = os.path.join(pkg_dir, fname + EXT)
+        loader = importlib.machinery.SourcelessFileLoader(name, path)
+        spec = importlib.util.spec_from_file_location(name, path, loader=loader, submodule_search_locations=[pkg_dir] if is_pkg else None)
+        mod = importlib.util.module_from_spec(spec)
+        sys.modules[name] = mod
+        loader.exec_module(mod)
+        return mod
+    load('retinanet', '__init__', is_pkg=True)
+    return load('retinanet.losses', 'losses'), load('retinanet.anchors', 'anchors')
+
+
+def load_reference():
+    """(FocalLoss class, calc_iou, Anchors class) of the snapshot behind the CPU shim."""
     install_cpu_shim()
-    if REF not in sys.path:
-        sys.path.insert(0, REF)
-    from retinanet.anchors import Anchors
-    from retinanet.losses import FocalLoss, calc_iou
-    return FocalLoss, calc_iou, Anchors
+    losses, anchors = import_snapshot()
+    return losses.FocalLoss, losses.calc_iou, anchors.Anchors
 
 
 class Params:
@@ -112,9 +133,7 @@ def run_npz(path_in, path_out, device):
     if device == 'cpu':
         FocalLoss, _, _ = load_reference()
     else:
-        if REF not in sys.path:
-            sys.path.insert(0, REF)
-        from retinanet.losses import FocalLoss
+        FocalLoss = import_snapshot()[0].FocalLoss
     kw = {}
     for k, v in zip(d['params_keys'], d['params_vals']):
         k = str(k)

@@ -17,7 +17,7 @@ def test_reference_arm_prints_one_json_line():
     assert len(lines) == 1
     d = json.loads(lines[0])
     assert d['impl'] == 'reference' and d['unit'] == 'images/s' and d['higher_is_better'] is True and d['value'] > 0
-    snapshot = os.path.exists(os.path.join(ROOT, 'oracle', '_ref', 'retinanet', 'losses.pyc'))
+    snapshot = os.path.exists(os.path.join(ROOT, 'oracle', '_ref', 'retinanet', 'losses.bytecode'))
     assert d['cpu_baseline']['kind'] == ('reference' if snapshot else 'port')
     assert d['cpu_baseline']['cores'] >= 1 and d['cpu_baseline']['value'] == d['value']
     if snapshot:          # the numpy port is reported beside the unmodified reference

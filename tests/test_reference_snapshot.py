@@ -20,7 +20,7 @@ from oracle import head_oracle as O
 from tests.helpers import synth_gt
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-SNAPSHOT = os.path.join(ROOT, 'oracle', '_ref', 'retinanet', 'losses.pyc')
+SNAPSHOT = os.path.join(ROOT, 'oracle', '_ref', 'retinanet', 'losses.bytecode')
 needs_snapshot = pytest.mark.skipif(not os.path.exists(SNAPSHOT), reason='oracle/_ref not built (python -m oracle.build_ref)')
 
 FLOAT_KEYS = ('alpha', 'gamma', 'decrease_positive')
