@@ -91,6 +91,7 @@ class ClockSampler:
 
     def __init__(self, index):
         self.samples, self.reasons, self.ok = [], set(), False
+        self.recording = False
         self._stop = threading.Event()
         try:
             import pynvml
@@ -106,22 +107,32 @@ class ClockSampler:
     def _run(self):
         while not self._stop.is_set():
             try:
-                self.samples.append(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM))
+                mhz = self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM)
                 r = self.nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
-                for bit, name in self.REASONS.items():
-                    if r & bit:
-                        self.reasons.add(name)
+                if self.recording:          # the thread is started (and its first NVML calls paid) BEFORE the timed region
+                    self.samples.append(mhz)
+                    for bit, name in self.REASONS.items():
+                        if r & bit:
+                            self.reasons.add(name)
             except Exception:
                 pass
             time.sleep(0.002)
 
-    def start(self):
-        if self.ok:
+    def warm(self):
+        """Start polling without recording: thread start-up and NVML's first-call costs (measured: one rank's main thread lost
+        11 ms to them, and on N > 1 every rank waits for the slowest one every step) stay outside the timed region."""
+        self.recording = False
+        self.start(record=False)
+
+    def start(self, record=True):
+        self.recording = record
+        if self.ok and self.t is None:
             self._stop.clear()
             self.t = threading.Thread(target=self._run, daemon=True)
             self.t.start()
 
     def stop(self):
+        self.recording = False
         if self.t is not None:
             self._stop.set()
             self.t.join()
@@ -418,22 +429,39 @@ def time_loop(step, steps, warmup, barrier, hook=None, sampler=None):
     """`steps` timed iterations after `warmup`, CUDA events on the current stream, barrier + synchronize on both sides; one
     more untimed step directly before the timed region aligns the ranks (on N > 1 it ends in the peer exchange)."""
     import torch
-    for _ in range(max(warmup, 3)):
+    if sampler is not None:
+        sampler.warm()           # polling thread up and NVML warm before anything is timed
+    for i in range(max(warmup, 3)):
+        if hook is not None and i == 0:
+            hook(0)              # the in-call event records pay their first-use cost here, not in timed step 0
         step()
     barrier()
     step()
     if sampler is not None:
-        sampler.start()          # SM clock + throttle reasons are sampled DURING the timed region
+        sampler.start()          # SM clock + throttle reasons are RECORDED during the timed region only
     t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    trace = os.environ.get('CLDET_BENCH_TRACE')          # diagnostics: per-step device and host time lines of every rank
+    marks, host = [], []
     t0.record()
     for i in range(steps):
         if hook is not None:
             hook(i)
+        if trace:
+            host.append(time.perf_counter())
         step()
+        if trace:
+            e = torch.cuda.Event(enable_timing=True)
+            e.record()
+            marks.append(e)
     t1.record()
     barrier()
     if sampler is not None:
         sampler.stop()
+    if trace:
+        os.makedirs(os.path.join(ROOT, 'gpurun_out'), exist_ok=True)
+        with open(os.path.join(ROOT, 'gpurun_out', 'trace_%s_rank%s.json' % (trace, os.environ.get('RANK', '0'))), 'w') as f:
+            json.dump({'device_ms_since_t0': [t0.elapsed_time(e) for e in marks],
+                       'host_ms_since_first': [(h - host[0]) * 1e3 for h in host]}, f)
     return t0.elapsed_time(t1)
 
 
@@ -621,8 +649,18 @@ def run_ours(args):
         if i % HOOK_EVERY == 0:
             lib.cldet_focal_loss_profile_events(ev[i][0].cuda_event, ev[i][1].cuda_event, ev[i][2].cuda_event)
 
-    sampler = ClockSampler(local_rank)
-    total_ms = time_loop(step, args.steps, args.warmup, barrier, hook, sampler)
+    sampler = ClockSampler(local_rank) if not args.no_clock_sampler else None
+    total_ms = time_loop(step, args.steps, args.warmup, barrier, hook if not args.no_kernel_events else None, sampler)
+    if args.quick:          # diagnostics: the timed loop only
+        total_ms = reduce_max(total_ms)
+        if rank == 0:
+            emit({'quick': True, 'n_gpus': world, 'steps': args.steps, 'ms_per_step': total_ms / args.steps,
+                  'value': n_global / (total_ms / args.steps * 1e-3), 'collective': args.collective})
+        if world > 1:
+            dist.barrier()
+            module.close()
+            dist.destroy_process_group()
+        return 0
     collective = 'none'
     if world > 1:
         used_peer = bool(module._peer and any(v for v in module._peer.values()))
@@ -801,6 +839,9 @@ def main():
     ap.add_argument('--no-decode', action='store_true', help='skip the BASELINE config 4 (decode + NMS) section')
     ap.add_argument('--no-configs', action='store_true', help='skip the lines for BASELINE configs 1, 2 and 5')
     ap.add_argument('--collective', default='peer', choices=['peer', 'nccl'])
+    ap.add_argument('--quick', action='store_true', help='diagnostics: run the timed loop only and print a short line')
+    ap.add_argument('--no-clock-sampler', action='store_true', help='diagnostics: do not poll NVML during the timed region')
+    ap.add_argument('--no-kernel-events', action='store_true', help='diagnostics: no in-call event records (kernel_ms unavailable)')
     args = ap.parse_args()
     if args.impl == 'reference':
         return run_reference(args)

@@ -106,7 +106,8 @@ decode_filter_kernel(const float* __restrict__ cls, int is_logits, const float4*
     unsigned char* vinfo = reinterpret_cast<unsigned char*>(part + (size_t)rows_per_block * stride);
 
     const int j = blockIdx.y;
-    const int64_t a0 = (int64_t)blockIdx.x * rows_per_block;
+    const int chunk = blockIdx.x;
+    const int64_t a0 = (int64_t)chunk * rows_per_block;
     const int nrows = (int)min64(rows_per_block, A - a0);
     const int ppr = (C + VEC - 1) / VEC;
     const int nvec = nrows * ppr;
@@ -208,6 +209,23 @@ decode_filter_kernel(const float* __restrict__ cls, int is_logits, const float4*
                 const int k_hi = (m2 >= t) ? ppr : kmax + 1;
                 for (int k = k_lo; k < k_hi; ++k) {
                     if (p[k] >= t) {
+                        if (VEC == 4 && p[k] > prefilter) {
+                            // phase 1 left this vector's record: unless a second element of the vector is within reach of its
+                            // maximum, the maximum (p[k], at a known index) is the vector's only contender -- nothing is re-read.
+                            // (A vector at or below the prefilter has no record; it cannot hold a CANDIDATE's class either: a
+                            // candidate's best logit lies >= 0.01 above it, far beyond a tie of the fp32 sigmoids.)
+                            const int vi = (int)vinfo[r * stride + k];
+                            if (!(vi & 4)) {
+                                const float pr = is_logits ? sigmoid_exact(p[k]) : p[k];
+                                if (pr > best) {
+                                    best = pr;
+                                    best_c = k * VEC + (vi & 3);
+                                }
+                                continue;
+                            }
+                        } else if (VEC == 4 && is_logits) {
+                            continue;
+                        }
 #pragma unroll
                         for (int e = 0; e < VEC; ++e) {
                             const int c = k * VEC + e;
