@@ -169,6 +169,10 @@ def main():
     ap.add_argument('--warmup', type=int, default=0)
     ap.add_argument('--threads', type=int, default=os.cpu_count() or 1)
     a = ap.parse_args()
+    if a.device == 'cpu':
+        # the CPU runs must take the reference's OWN CPU branches (`if torch.cuda.is_available(): ... torch.cuda.FloatTensor(...)`,
+        # losses.py:116, 146, 193, 424, 439): hide the GPUs of a GPU box from this process before torch is imported
+        os.environ['CUDA_VISIBLE_DEVICES'] = ''
     if a.npz:
         run_npz(a.npz[0], a.npz[1], a.device)
         return

@@ -6,7 +6,7 @@
 
 --launches: the CSV log of `ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file ...`
             -> <out>_launches.csv (copy) + <out>_launch_summary.csv (kernel, launches, avg_us, total_us, share)
---full    : an `ncu --set full` report -> key metrics per kernel as CSV, and profiles/traffic.json
+--full    : an `ncu --set full` report (or its `--page raw --csv` export) -> key metrics per kernel as CSV, and profiles/traffic.json
             (dram__bytes_read.sum + dram__bytes_write.sum per launch; bench.py reads it for roofline.traffic)
 """
 import argparse
@@ -71,7 +71,10 @@ def launches(path, out):
 
 
 def full(path, out):
-    txt = subprocess.run(['ncu', '-i', path, '--page', 'raw', '--csv'], capture_output=True, text=True, check=True).stdout
+    if path.endswith('.csv'):          # the raw page exported on the GPU box (the .ncu-rep with sources is ~32 MB per kernel)
+        txt = open(path).read()
+    else:
+        txt = subprocess.run(['ncu', '-i', path, '--page', 'raw', '--csv'], capture_output=True, text=True, check=True).stdout
     rows = csv_rows(txt)
     hdr, units = rows[0], rows[1]
     kn = hdr.index('Kernel Name')
