@@ -2,8 +2,8 @@
 
 Recipe for `oracle/_ref/`: the reference's OWN implementation of the path, built from the sources where they lie under
 /root/reference (read-only) into byte-code only.  The reference is pure Python, so "compiling" it means py_compile: the
-three modules the path lives in (retinanet/losses.py FocalLoss + calc_iou, retinanet/anchors.py, retinanet/utils.py
-BBoxTransform / ClipBoxes) become byte-code files `oracle/_ref/retinanet/<module>.bytecode` (the .pyc format under another
+modules the path lives in (retinanet/losses.py FocalLoss + calc_iou, retinanet/anchors.py, retinanet/utils.py
+BBoxTransform / ClipBoxes, retinanet/model.py ResNet.predict and the print helper it imports) become byte-code files `oracle/_ref/retinanet/<module>.bytecode` (the .pyc format under another
 extension: snapshot tools that skip `*.pyc` as caches would drop them; oracle/ref_runner.py imports them with
 importlib's SourcelessFileLoader).  No reference SOURCE is copied
 into the repo; oracle/_ref/ is git-ignored (it is a build output) but not gpurun-ignored, so it travels to the GPU box like
@@ -22,7 +22,9 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 OUT = os.path.join(HERE, '_ref')
 REFERENCE = os.environ.get('CLDET_REFERENCE', '/root/reference')
 EXT = '.bytecode'
-MODULES = ('retinanet/__init__.py', 'retinanet/losses.py', 'retinanet/anchors.py', 'retinanet/utils.py')
+MODULES = ('retinanet/__init__.py', 'retinanet/losses.py', 'retinanet/anchors.py', 'retinanet/utils.py',
+           # the eval half: ResNet.predict lives in model.py, which imports preprocessing.debug (a print helper)
+           'retinanet/model.py', 'preprocessing/__init__.py', 'preprocessing/debug.py')
 
 
 def build_ref(force=False):

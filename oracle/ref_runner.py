@@ -62,6 +62,97 @@ def import_snapshot():
     return load('retinanet.losses', 'losses'), load('retinanet.anchors', 'anchors')
 
 
+def import_snapshot_model():
+    """retinanet.model of the snapshot (ResNet.predict, model.py:494-605) with the modules it imports."""
+    import importlib.machinery
+    import importlib.util
+    import_snapshot()
+    if 'retinanet.model' in sys.modules:
+        return sys.modules['retinanet.model']
+
+    def load(name, rel, is_pkg=False):
+        path = os.path.join(REF, rel + EXT)
+        loader = importlib.machinery.SourcelessFileLoader(name, path)
+        spec = importlib.util.spec_from_file_location(name, path, loader=loader,
+                                                      submodule_search_locations=[os.path.dirname(path)] if is_pkg else None)
+        mod = importlib.util.module_from_spec(spec)
+        sys.modules[name] = mod
+        loader.exec_module(mod)
+        return mod
+    load('preprocessing', 'preprocessing/__init__', is_pkg=True)
+    load('preprocessing.debug', 'preprocessing/debug')
+    load('retinanet.utils', 'retinanet/utils')
+    return load('retinanet.model', 'retinanet/model')
+
+
+def stub_model():
+    """The reference's ResNet with its constructor and forward stubbed (no backbone): predict() itself -- everything after
+    self.forward, model.py:507-605 -- is the unmodified reference code.  Same stub as tests/golden/make_golden.py."""
+    import torch
+    ref_model = import_snapshot_model()
+    utils = sys.modules['retinanet.utils']
+
+    class StubModel(ref_model.ResNet):
+        def __init__(self):
+            torch.nn.Module.__init__(self)
+            self.regressBoxes = utils.BBoxTransform()
+            self.clipBoxes = utils.ClipBoxes()
+
+        def forward(self, img_batch, return_feat=False, return_anchor=True, enable_act=False):
+            return self._cls, self._reg, self._anchors
+    return StubModel()
+
+
+def run_predict_npz(path_in, path_out, device):
+    """Parity mode for the eval half: logits [1,A,C], reg [1,A,4], h, w from an .npz -> the unmodified ResNet.predict's
+    [scores, labels, boxes].  device='cuda': exactly as written, on cuda:0; 'cpu': GPUs hidden, the reference's CPU branches."""
+    import torch
+    d = np.load(path_in, allow_pickle=False)
+    if device == 'cpu':
+        install_cpu_shim()
+    dev = torch.device('cuda:0' if device == 'cuda' else 'cpu')
+    m = stub_model()
+    h, w = int(d['h']), int(d['w'])
+    img = torch.zeros(1, 3, h, w, device=dev)
+    m._cls, m._reg = torch.from_numpy(d['logits']).to(dev), torch.from_numpy(d['reg']).to(dev)
+    m._anchors = sys.modules['retinanet.anchors'].Anchors()(img)
+    with torch.no_grad():
+        scores, labels, boxes = m.predict(img)
+    np.savez(path_out, scores=scores.cpu().numpy(), labels=labels.cpu().numpy(), boxes=boxes.cpu().numpy())
+
+
+def time_predict(mu, images, device, height=800, width=1333, classes=80, seed=7):
+    """Wall time per predict() call of the unmodified reference (forward stubbed) on COCO-shaped head outputs,
+    logits ~ N(mu, 2): what evaluator.py:324-329 pays per image after the network, detections read back with .cpu()."""
+    import torch
+    if device == 'cpu':
+        install_cpu_shim()
+    dev = torch.device('cuda:0' if device == 'cuda' else 'cpu')
+    m = stub_model()
+    img = torch.zeros(1, 3, height, width, device=dev)
+    m._anchors = sys.modules['retinanet.anchors'].Anchors()(img)
+    a = m._anchors.shape[1]
+    gen = torch.Generator(device=dev).manual_seed(seed)
+    logits = torch.randn(images + 1, a, classes, device=dev, generator=gen) * 2.0 + mu
+    reg = torch.randn(images + 1, a, 4, device=dev, generator=gen) * 0.3
+    kept = 0
+    t0 = 0.0
+    with torch.no_grad():
+        for j in range(images + 1):          # the first call is the warm-up
+            if j == 1:
+                if dev.type == 'cuda':
+                    torch.cuda.synchronize()
+                t0 = time.perf_counter()
+            m._cls, m._reg = logits[j:j + 1], reg[j:j + 1]
+            s, l, b = m.predict(img)
+            s, l, b = s.cpu(), l.cpu(), b.cpu()
+            if j >= 1:
+                kept += s.shape[0]
+    dt = (time.perf_counter() - t0) / images
+    return {'ms_per_image': dt * 1e3, 'value': 1.0 / dt, 'unit': 'images/s', 'images': images, 'kept_per_image': kept / images,
+            'device': device, 'threads': torch.get_num_threads(), 'torch': torch.__version__}
+
+
 def load_reference():
     """(FocalLoss class, calc_iou, Anchors class) of the snapshot behind the CPU shim."""
     install_cpu_shim()
@@ -163,6 +254,8 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--npz', nargs=2, metavar=('IN', 'OUT'), help='parity mode: run the reference on the inputs of IN, write OUT')
     ap.add_argument('--device', default='cpu', choices=['cpu', 'cuda'])
+    ap.add_argument('--predict-npz', nargs=2, metavar=('IN', 'OUT'), help='parity mode of the eval half (ResNet.predict)')
+    ap.add_argument('--predict-time', type=float, metavar='MU', help='time predict() on logits ~ N(MU, 2), --images calls')
     ap.add_argument('--images', type=int, default=1)
     ap.add_argument('--frac', type=float, default=1.0)
     ap.add_argument('--steps', type=int, default=1)
@@ -175,6 +268,14 @@ def main():
         os.environ['CUDA_VISIBLE_DEVICES'] = ''
     if a.npz:
         run_npz(a.npz[0], a.npz[1], a.device)
+        return
+    if a.predict_npz:
+        run_predict_npz(a.predict_npz[0], a.predict_npz[1], a.device)
+        return
+    if a.predict_time is not None:
+        import torch
+        torch.set_num_threads(max(1, a.threads))
+        print(json.dumps(time_predict(a.predict_time, a.images, a.device)))
         return
     print(json.dumps(time_reference(a.images, a.frac, a.steps, a.warmup, a.threads)))
 

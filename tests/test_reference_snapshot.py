@@ -132,3 +132,45 @@ def test_cuda_path_matches_reference_running_on_the_same_gpu(case, tmp_path):
         assert np.array_equal(out['bg_masks'].cpu().numpy(), ref['bg_masks'])
     if 'enhance' in ref:
         assert_rel(out['enhance_on_new_loss'].detach().cpu().numpy(), ref['enhance'], what='enhance')
+
+
+# ---- eval half: predict() against the unmodified ResNet.predict (model.py:494-605, forward stubbed) on the same GPU ----
+PREDICT_CASES = [
+    # name, H, W, C, logit mean, seed
+    ('few_candidates_trick', 128, 160, 20, -6.0, 21),
+    ('no_candidate_but_saturated_row', 64, 96, 6, -14.0, 22),
+    ('coco_shape_trained_like', 800, 1333, 80, -10.5, 23),
+    ('vanilla_branch_over_25k_candidates', 512, 512, 20, -3.0, 24),      # 4*K > 100 000: torchvision switches to per-class NMS
+]
+
+
+@pytest.mark.skipif(not os.path.exists(os.path.join(ROOT, 'oracle', '_ref', 'retinanet', 'model.bytecode')),
+                    reason='oracle/_ref not built (python -m oracle.build_ref)')
+@pytest.mark.gpu
+@pytest.mark.parametrize('case', PREDICT_CASES, ids=[c[0] for c in PREDICT_CASES])
+def test_predict_matches_reference_predict_running_on_the_same_gpu(case, tmp_path):
+    """Bit-exact: scores, labels and boxes of the detection output, in the reference's order."""
+    import torch
+
+    import cl_object_detection_b200 as cld
+    from cl_object_detection_b200 import detect as D
+    name, H, W, C, mu, seed = case
+    rng = np.random.default_rng(seed)
+    A = O.num_anchors(H, W)
+    logits = rng.normal(mu, 2.0, (1, A, C)).astype(np.float32)
+    logits.reshape(-1)[:C] = 30.0                      # a row of saturated ties -> first-index argmax
+    reg = rng.normal(0, 0.3, (1, A, 4)).astype(np.float32)
+    fin, fout = str(tmp_path / 'in.npz'), str(tmp_path / 'out.npz')
+    np.savez(fin, logits=logits, reg=reg, h=np.int64(H), w=np.int64(W))
+    r = subprocess.run([sys.executable, '-m', 'oracle.ref_runner', '--predict-npz', fin, fout, '--device', 'cuda'], cwd=ROOT,
+                       capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stderr[-3000:]
+    ref = np.load(fout)
+    dev = 'cuda:0'
+    img = torch.zeros(1, 3, H, W, device=dev)
+    s, l, b = D.predict_from_head(torch.from_numpy(logits).to(dev), torch.from_numpy(reg).to(dev), cld.generate_anchors(H, W, dev), img)
+    assert l.dtype == torch.int64
+    assert np.array_equal(s.cpu().numpy(), ref['scores'])
+    assert np.array_equal(l.cpu().numpy(), ref['labels'])
+    assert np.array_equal(b.cpu().numpy(), ref['boxes'])
+    assert s.shape[0] > 0
