@@ -267,14 +267,20 @@ def decode_section(dev, with_eager):
         del logits, reg
         torch.cuda.empty_cache()
     # the boundary as the reference calls it: predict, one image per call, no top-k, host head outputs in, detections out
-    from tools.bench_detect import measure_nms_h2h, measure_predict
+    from tools.bench_detect import measure_nms_h2h, measure_predict, reference_predict_times
     out['predict_batch1_reference_mode'] = {}
-    for label, mu in (('~1.3k candidates', -10.5), ('~8k candidates', -9.5), ('~40k candidates', -8.5)):
+    levels = (('~1.3k candidates', -10.5), ('~8k candidates', -9.5), ('~40k candidates', -8.5))
+    for label, mu in levels:
         try:
             out['predict_batch1_reference_mode'][label] = measure_predict(dev, mu, cpu_images=2 if with_eager else 0)
         except Exception as e:  # noqa: BLE001
             out['predict_batch1_reference_mode'][label] = {'unavailable': repr(e)[:200]}
         torch.cuda.empty_cache()
+    if with_eager:
+        # the UNMODIFIED ResNet.predict on the same head-output distribution: on this GPU as written, and on the host cores
+        ref = reference_predict_times([mu for _, mu in levels])
+        for label, mu in levels:
+            out['predict_batch1_reference_mode'][label].update(ref[mu])
     # K6 (+ its sort) against torchvision's own CUDA nms on identical inputs
     out['nms_vs_torchvision'] = {}
     for k in (1000, 8000, 40000):

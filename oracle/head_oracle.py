@@ -10,7 +10,8 @@ Parity pin: the reference ships no tests or golden vectors
 oracle is pinned against outputs of the reference ITSELF, imported from /root/reference in
 the build container by tests/golden/make_golden.py (committed) and stored as small
 fixtures under tests/golden/*.npz.  tests/test_oracle_golden.py checks every function here
-against those fixtures.
+against those fixtures; tests/test_reference_snapshot.py checks the loss half against the LIVE
+reference (byte-code snapshot oracle/_ref, oracle/build_ref.py) on fresh seeded inputs.
 
 Arithmetic notes.  Everything that decides an integer/boolean result (anchors, IoU,
 assignment thresholds, argmax, NMS) follows the reference's fp32 op order exactly, one

@@ -255,7 +255,8 @@ def main():
     ap.add_argument('--npz', nargs=2, metavar=('IN', 'OUT'), help='parity mode: run the reference on the inputs of IN, write OUT')
     ap.add_argument('--device', default='cpu', choices=['cpu', 'cuda'])
     ap.add_argument('--predict-npz', nargs=2, metavar=('IN', 'OUT'), help='parity mode of the eval half (ResNet.predict)')
-    ap.add_argument('--predict-time', type=float, metavar='MU', help='time predict() on logits ~ N(MU, 2), --images calls')
+    ap.add_argument('--predict-time', type=float, nargs='+', metavar='MU',
+                    help='time predict() on logits ~ N(MU, 2), --images calls per MU; prints one JSON list')
     ap.add_argument('--images', type=int, default=1)
     ap.add_argument('--frac', type=float, default=1.0)
     ap.add_argument('--steps', type=int, default=1)
@@ -275,7 +276,7 @@ def main():
     if a.predict_time is not None:
         import torch
         torch.set_num_threads(max(1, a.threads))
-        print(json.dumps(time_predict(a.predict_time, a.images, a.device)))
+        print(json.dumps([time_predict(mu, a.images, a.device) for mu in a.predict_time]))
         return
     print(json.dumps(time_reference(a.images, a.frac, a.steps, a.warmup, a.threads)))
 

@@ -214,23 +214,6 @@ def measure_predict(dev, mu, images=6, cpu_images=2):
         s, l, b = E.predict(logits[j:j + 1], reg[j:j + 1], anchors, h, w)
         s.cpu(), l.cpu(), b.cpu()
     out['gpu_eager_ms_per_image'] = (time.perf_counter() - t0) / images * 1e3
-    if cpu_images and os.path.exists(os.path.join(ROOT, 'oracle', '_ref', 'retinanet', 'model.bytecode')):
-        # the UNMODIFIED ResNet.predict (oracle/_ref snapshot, forward stubbed) in its own process: as written on cuda:0, and on
-        # the host cores with the GPUs hidden
-        import subprocess
-        for device, key in (('cuda', 'reference_predict_same_gpu'), ('cpu', 'reference_predict_cpu')):
-            try:
-                r = subprocess.run([sys.executable, '-m', 'oracle.ref_runner', '--predict-time', str(mu), '--images', str(cpu_images),
-                                    '--device', device, '--threads', str(min(os.cpu_count() or 1, 16))], cwd=ROOT,
-                                   capture_output=True, text=True, timeout=600)
-                res = json.loads(r.stdout.strip().splitlines()[-1])
-                out[key] = {'value': res['value'], 'unit': 'images/s', 'ms_per_image': res['ms_per_image'], 'kind': 'reference',
-                            'cores': res['threads'], 'kept_per_image': res['kept_per_image'],
-                            'sample': '%d predict() calls of the unmodified reference (model.py:494-605, forward stubbed), %s, '
-                                      'detections read back with .cpu()' % (res['images'], 'cuda:0 as written' if device == 'cuda'
-                                                                            else 'host cores, GPUs hidden')}
-            except Exception as e:  # noqa: BLE001
-                out[key] = {'unavailable': repr(e)[:200]}
     if cpu_images:
         cl, cr, ca = [x.cpu() for x in (logits[:cpu_images], reg[:cpu_images], anchors)]
         t0 = time.perf_counter()
@@ -240,6 +223,31 @@ def measure_predict(dev, mu, images=6, cpu_images=2):
         out['cpu_baseline'] = {'value': 1.0 / cdt, 'unit': 'images/s', 'ms_per_image': cdt * 1e3, 'cores': torch.get_num_threads(),
                                'kind': 'port', 'sample': '%d images, torch-eager restatement of ResNet.predict + torchvision CPU '
                                                          'batched_nms on the host cores' % cpu_images}
+    return out
+
+
+def reference_predict_times(mus, images=2):
+    """The UNMODIFIED ResNet.predict (oracle/_ref snapshot, forward stubbed) on COCO-shaped head outputs, one process per
+    device: as written on cuda:0, and on the host cores with the GPUs hidden.  Returns {mu: {key: entry}} (empty without the
+    snapshot)."""
+    import subprocess
+    out = {mu: {} for mu in mus}
+    if not os.path.exists(os.path.join(ROOT, 'oracle', '_ref', 'retinanet', 'model.bytecode')):
+        return out
+    for device, key in (('cuda', 'reference_predict_same_gpu'), ('cpu', 'reference_predict_cpu')):
+        try:
+            r = subprocess.run([sys.executable, '-m', 'oracle.ref_runner', '--predict-time'] + [str(m) for m in mus] +
+                               ['--images', str(images), '--device', device, '--threads', str(min(os.cpu_count() or 1, 16))],
+                               cwd=ROOT, capture_output=True, text=True, timeout=900)
+            for mu, res in zip(mus, json.loads(r.stdout.strip().splitlines()[-1])):
+                out[mu][key] = {'value': res['value'], 'unit': 'images/s', 'ms_per_image': res['ms_per_image'], 'kind': 'reference',
+                                'cores': res['threads'], 'kept_per_image': res['kept_per_image'],
+                                'sample': '%d predict() calls of the unmodified reference (model.py:494-605, forward stubbed), %s, '
+                                          'detections read back with .cpu()' % (res['images'], 'cuda:0 as written' if device == 'cuda'
+                                                                                else 'host cores, GPUs hidden')}
+        except Exception as e:  # noqa: BLE001
+            for mu in mus:
+                out[mu][key] = {'unavailable': repr(e)[:200]}
     return out
 
 
