@@ -323,7 +323,7 @@ def run_reference(args):
     if reference_snapshot_available():
         kind = 'reference'
         images_per_step = 1
-        probe = time_unmodified_reference(1, 0.1, 1, 0, threads)            # one image, 10 % of the anchors
+        probe = time_unmodified_reference(1, 0.25, 1, 1, threads)           # one image, a quarter of the anchors, after a warm-up call
         full_step = probe['s_per_step'] / probe['anchor_fraction']
         frac = max(0.02, min(1.0, 0.8 * budget / (full_step * total_steps)))
         res = time_unmodified_reference(images_per_step, frac, args.steps, args.warmup, threads, timeout=max(900, 20 * budget))
