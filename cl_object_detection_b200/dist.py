@@ -154,6 +154,12 @@ class _GatherTerms(torch.autograd.Function):
         k = local.shape[0]
         nmax = max(sizes)
         world = len(sizes)
+        ctx.sizes, ctx.rank = sizes, rank
+        if world > 1 and min(sizes) == nmax:
+            # equal shards (the usual case): no padding, no per-rank slicing -- one collective and one strided copy
+            flat = local.new_empty((world * k, nmax))
+            dist.all_gather_into_tensor(flat, local.contiguous(), group=group)
+            return flat.view(world, k, nmax).permute(1, 0, 2).reshape(k, world * nmax)
         padded = local.new_zeros((k, nmax))
         padded[:, :local.shape[1]] = local
         if world > 1:
@@ -162,7 +168,6 @@ class _GatherTerms(torch.autograd.Function):
             out = flat.view(world, k, nmax)
         else:
             out = padded.unsqueeze(0)
-        ctx.sizes, ctx.rank = sizes, rank
         return torch.cat([out[r, :, :sizes[r]] for r in range(world)], dim=1)
 
     @staticmethod
