@@ -939,32 +939,60 @@ radix_sort_kernel(const cldet_candidate* __restrict__ cand, const uint64_t* __re
 // ------------------------------------------------------------------------------------------------
 // K6: NMS.  (1) per-image max coordinate + mode (2) 64x64 suppression bitmask over the SORTED list
 // (3) sequential resolve, one block per image, 64 boxes per step.
-// nms_info per image: [0] max coordinate (float bits), [1] mode actually used (1 trick, 2 vanilla)
+// nms_info per image: [0] max coordinate (float bits), [1] mode actually used (1 trick, 2 vanilla) | kNmsLabelsDisjoint
 // ------------------------------------------------------------------------------------------------
+constexpr uint32_t kNmsLabelsDisjoint = 0x100u;
+
 __global__ void __launch_bounds__(256)
 nms_prepare_kernel(const cldet_candidate* __restrict__ sorted, const int32_t* __restrict__ counts, int64_t capacity, int mode,
                    int64_t vanilla_numel_limit, uint32_t* __restrict__ info) {
     pdl_wait();                       // may be scheduled while the previous kernel of the chain drains
     pdl_launch_dependents();
-    __shared__ float red[8];
+    __shared__ float red[8], red_min[8];
+    __shared__ int red_lab[8];
     const int j = blockIdx.x;
     const int n = (int)min64(counts[j], capacity);
-    float m = -INFINITY;
+    float m = -INFINITY, mn = INFINITY;
+    int lab_max = 0, lab_min = 0;
     const cldet_candidate* c = sorted + (int64_t)j * capacity;
     for (int i = threadIdx.x; i < n; i += blockDim.x) {
         const cldet_candidate b = c[i];
         m = fmaxf(m, fmaxf(fmaxf(b.x1, b.y1), fmaxf(b.x2, b.y2)));
+        mn = fminf(mn, fminf(fminf(b.x1, b.y1), fminf(b.x2, b.y2)));
+        lab_max = max(lab_max, b.label);
+        lab_min = min(lab_min, b.label);
     }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
-    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+    for (int o = 16; o > 0; o >>= 1) {
+        m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+        mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+        lab_max = max(lab_max, __shfl_xor_sync(0xffffffffu, lab_max, o));
+        lab_min = min(lab_min, __shfl_xor_sync(0xffffffffu, lab_min, o));
+    }
+    if ((threadIdx.x & 31) == 0) {
+        red[threadIdx.x >> 5] = m;
+        red_min[threadIdx.x >> 5] = mn;
+        red_lab[threadIdx.x >> 5] = (lab_min < 0) ? 0x7fffffff : lab_max;      // a negative label disables the shortcut below
+    }
     __syncthreads();
     if (threadIdx.x == 0) {
-        for (int w = 1; w < 8; ++w) m = fmaxf(m, red[w]);
+        for (int w = 1; w < 8; ++w) {
+            m = fmaxf(m, red[w]);
+            mn = fminf(mn, red_min[w]);
+        }
+        int lmax = red_lab[0];
+        for (int w = 1; w < 8; ++w) lmax = max(lmax, red_lab[w]);
         info[2 * j] = __float_as_uint(m);
         int used = mode;
         if (mode == 0) used = ((int64_t)n * 4 > vanilla_numel_limit) ? 2 : 1;   // torchvision ops/boxes.py batched_nms
-        info[2 * j + 1] = (uint32_t)used;
+        // Coordinate trick, provably disjoint classes: with every coordinate in [0, M] and (label_max + 1) * (M + 1) <= 2^21 the
+        // fp32 offsets label * (M + 1) and the shifted coordinates are rounded by at most 0.125 each, so boxes of different
+        // labels stay >= 0.5 apart in x: their intersection width is negative and torchvision's kernel never suppresses across
+        // labels (for thr >= 0).  The mask kernel may then skip such pairs on the label test alone.  (With huge offsets the
+        // trick DOES let rounding merge classes; those inputs keep the full test.)
+        const bool disjoint = (used == 1) && n > 0 && mn >= 0.0f && lmax < 0x7fffffff &&
+                              ((double)lmax + 1.0) * ((double)m + 1.0) <= 2097152.0;
+        info[2 * j + 1] = (uint32_t)used | (disjoint ? kNmsLabelsDisjoint : 0u);
     }
 }
 
@@ -1006,7 +1034,9 @@ nms_mask_kernel(const cldet_candidate* __restrict__ sorted, const int32_t* __res
     const int col_blk = row_blk + (int)(t - ((long long)row_blk * cb - (long long)row_blk * (row_blk - 1) / 2));
     if (row_blk >= cbn) break;                                        // rows are enumerated in order: nothing live follows
     if (col_blk >= cbn) continue;
-    const int mode = (int)info[2 * j + 1];
+    const int mode = (int)(info[2 * j + 1] & 0xffu);
+    // labels provably never interact (see nms_prepare_kernel): pairs of different labels are skipped on the label test alone
+    const bool by_label = (mode == 2) || ((info[2 * j + 1] & kNmsLabelsDisjoint) != 0u && thr >= 0.0f);
     const float off_unit = __uint_as_float(info[2 * j]) + 1.0f;       // max_coordinate + 1
     const cldet_candidate* c = sorted + (int64_t)j * capacity;
 
@@ -1046,7 +1076,7 @@ nms_mask_kernel(const cldet_candidate* __restrict__ sorted, const int32_t* __res
     const int t_lo = max(start, 16 * qq), t_hi = min(ncol, 16 * qq + 16);
     if (live) {
         for (int t = t_lo; t < t_hi; ++t) {
-            if (mode == 2 && clab[t] != my_lab) continue;
+            if (by_label && clab[t] != my_lab) continue;
             if (suppresses(me, my_area, cbox[t], carea[t], thr)) bits |= 1u << (t - 16 * qq);
         }
     }
