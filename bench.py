@@ -849,6 +849,8 @@ def main():
     ap.add_argument('--no-clock-sampler', action='store_true', help='diagnostics: do not poll NVML during the timed region')
     ap.add_argument('--no-kernel-events', action='store_true', help='diagnostics: no in-call event records (kernel_ms unavailable)')
     args = ap.parse_args()
+    if (args.no_clock_sampler or args.no_kernel_events) and not args.quick:
+        ap.error('--no-clock-sampler / --no-kernel-events are diagnostics of the --quick mode (the full line needs both)')
     if args.impl == 'reference':
         return run_reference(args)
     return run_ours(args)
