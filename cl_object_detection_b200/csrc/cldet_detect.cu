@@ -393,6 +393,8 @@ decode_filter_head_kernel(const HeadFilterLevels lv, int is_logits, const float4
 constexpr int kSelBins = 2048;
 constexpr int kRankPerBlock = 64;       // candidates ranked by one 256-thread block of rank_sort_kernel (4 threads each)
 constexpr int kRankDirect = 2048;      // up to this many candidates per image the O(n^2) rank sort beats radix select + compaction
+constexpr int kBucketMax = 2048;       // lists up to this length are ranked by ONE block of rank_sort_kernel through a bucket pass
+constexpr int kBuckets = 2048;
 constexpr int kRadixMin = 4096;        // longer lists (no top-k) are ordered by the one-launch radix sort instead of the pairwise rank sort
 
 struct SelPass {
@@ -743,10 +745,10 @@ __global__ void __launch_bounds__(256)
 rank_sort_kernel(const cldet_candidate* __restrict__ cand, const uint64_t* __restrict__ keys, const uint32_t* __restrict__ state,
                  const int32_t* __restrict__ counts_in, int64_t in_capacity, int topk, cldet_candidate* __restrict__ sorted,
                  int64_t out_capacity, int32_t* __restrict__ sorted_counts, const cldet_candidate* __restrict__ orig_cand = nullptr,
-                 const uint64_t* __restrict__ orig_keys = nullptr, int64_t orig_capacity = 0, int64_t max_n = 0) {
+                 const uint64_t* __restrict__ orig_keys = nullptr, int64_t orig_capacity = 0, int64_t max_n = 0, int64_t bucket_n = 0) {
     pdl_wait();                       // may be scheduled while the previous kernel of the chain drains
     pdl_launch_dependents();
-    __shared__ uint64_t tile[1024];
+    __shared__ uint64_t tile[kBucketMax];       // pairwise path: a tile of 1024 keys; bucket path: the keys in bucket order
     const int j = blockIdx.y;
     int64_t n = state ? (int64_t)state[4 * j + 2] : (int64_t)counts_in[j];
     if (state && state[4 * j + 3] && orig_cand) {
@@ -765,8 +767,110 @@ rank_sort_kernel(const cldet_candidate* __restrict__ cand, const uint64_t* __res
     const int64_t limit = (topk > 0) ? min64(n, topk) : n;
     if (blockIdx.x == 0 && threadIdx.x == 0) sorted_counts[j] = (int32_t)min64(limit, out_capacity);
     const uint64_t* k = keys + (int64_t)j * in_capacity;
+    if (n <= bucket_n) {
+        // Short list (the trained-model regime, with or without a top-k): ONE block ranks the whole image through a bucket pass
+        // instead of n^2 64-bit compares spread over the grid (23 us for 32 x ~1300 candidates, issue-bound on every SM -- the
+        // longest kernel of the post-filter chain).  bucket = (key - min) >> shift with shift chosen so that the image's key
+        // range spans kBuckets buckets; rank = (keys in higher buckets) + (larger keys of the own bucket).  Keys are distinct,
+        // so this is the pairwise rank exactly; only the own bucket (a few keys, unless scores tie en masse) is compared.
+        if (blockIdx.x != 0) return;
+        __shared__ uint32_t bcnt[kBuckets], bstart[kBuckets];
+        __shared__ uint64_t red_lo[8], red_hi[8];
+        __shared__ uint32_t scan_s[8];
+        constexpr int kPer = kBucketMax / 256;
+        constexpr int kOwn = kBuckets / 256;
+        const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+        const int nn = (int)n;
+        uint64_t kreg[kPer];
+        uint64_t lo = ~0ull, hi = 0ull;
+#pragma unroll
+        for (int u = 0; u < kPer; ++u) {
+            const int i = tid + 256 * u;
+            kreg[u] = (i < nn) ? k[i] : 0ull;
+            if (i < nn) {
+                lo = (kreg[u] < lo) ? kreg[u] : lo;
+                hi = (kreg[u] > hi) ? kreg[u] : hi;
+            }
+        }
+        for (int b = tid; b < kBuckets; b += 256) bcnt[b] = 0u;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const uint64_t ol = __shfl_xor_sync(0xffffffffu, lo, o), oh = __shfl_xor_sync(0xffffffffu, hi, o);
+            lo = (ol < lo) ? ol : lo;
+            hi = (oh > hi) ? oh : hi;
+        }
+        if (lane == 0) {
+            red_lo[warp] = lo;
+            red_hi[warp] = hi;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int w = 0; w < 8; ++w) {
+            lo = (red_lo[w] < lo) ? red_lo[w] : lo;
+            hi = (red_hi[w] > hi) ? red_hi[w] : hi;
+        }
+        const uint64_t range = (hi >= lo) ? hi - lo : 0ull;                   // nn == 0: every loop below is empty
+        const int shift = (range < (uint64_t)kBuckets) ? 0 : (64 - __clzll((long long)range)) - 11;      // range >> shift < 2048
+        int bkt[kPer], loc[kPer];
+#pragma unroll
+        for (int u = 0; u < kPer; ++u) {
+            const int i = tid + 256 * u;
+            bkt[u] = (i < nn) ? (int)((kreg[u] - lo) >> shift) : 0;
+            loc[u] = (i < nn) ? (int)atomicAdd(&bcnt[bkt[u]], 1u) : 0;       // arrival order inside the bucket (arbitrary)
+        }
+        __syncthreads();
+        // bstart[b] = number of keys in HIGHER buckets (descending order): thread t owns buckets kOwn*t .. kOwn*t + kOwn-1
+        uint32_t mine[kOwn], tot = 0;
+#pragma unroll
+        for (int q = 0; q < kOwn; ++q) {
+            mine[q] = bcnt[tid * kOwn + q];
+            tot += mine[q];
+        }
+        uint32_t incl = tot;                                                  // inclusive SUFFIX sum over the warp's threads
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t v = __shfl_down_sync(0xffffffffu, incl, o);
+            if (lane + o < 32) incl += v;
+        }
+        if (lane == 0) scan_s[warp] = incl;
+        __syncthreads();
+        uint32_t above = incl - tot;                                          // keys owned by later threads of this warp
+        for (int w = warp + 1; w < 8; ++w) above += scan_s[w];
+#pragma unroll
+        for (int q = kOwn - 1; q >= 0; --q) {
+            bstart[tid * kOwn + q] = above;
+            above += mine[q];
+        }
+        __syncthreads();
+#pragma unroll
+        for (int u = 0; u < kPer; ++u) {
+            const int i = tid + 256 * u;
+            if (i < nn) {
+                const int pos = (int)bstart[bkt[u]] + loc[u];
+                tile[pos] = kreg[u];
+            }
+        }
+        __syncthreads();
+        const float4* src = reinterpret_cast<const float4*>(cand + (int64_t)j * in_capacity);
+        float4* dst = reinterpret_cast<float4*>(sorted + (int64_t)j * out_capacity);
+#pragma unroll
+        for (int u = 0; u < kPer; ++u) {
+            const int i = tid + 256 * u;
+            if (i < nn) {
+                const int b0 = (int)bstart[bkt[u]], b1 = b0 + (int)bcnt[bkt[u]];
+                int r = b0;
+                for (int q = b0; q < b1; ++q) r += (tile[q] > kreg[u]) ? 1 : 0;
+                if (r < limit && r < out_capacity) {
+                    dst[2 * (int64_t)r] = src[2 * (int64_t)i];
+                    dst[2 * (int64_t)r + 1] = src[2 * (int64_t)i + 1];
+                }
+            }
+        }
+        return;
+    }
     // a block ranks kRankPerBlock candidates; the four threads of a candidate count a quarter of every tile each
     __shared__ int rank_s[kRankPerBlock];
+
     const int c = threadIdx.x & (kRankPerBlock - 1), q = threadIdx.x / kRankPerBlock;
     for (int64_t i0 = (int64_t)blockIdx.x * kRankPerBlock; i0 < n; i0 += (int64_t)gridDim.x * kRankPerBlock) {   // block-uniform
         const int64_t i = i0 + c;
@@ -1425,6 +1529,253 @@ nms_resolve_stream_kernel(const int32_t* __restrict__ counts, int64_t capacity, 
     gather_image(sorted, keep, j, capacity, kept_total_s, out_scores, out_labels, out_boxes);
 }
 
+// ------------------------------------------------------------------------------------------------
+// K6 in ONE launch for short lists (<= kFuseMax boxes per image: the pre-NMS top-k regime): a thread-block CLUSTER of
+// kFuseCluster CTAs per image does what nms_prepare + nms_mask + the resolve + the gather do as three dependent launches.
+//   every CTA   stages the image's sorted boxes in its own shared memory, forms the per-image facts of nms_prepare_kernel
+//               (max coordinate, mode, "labels provably disjoint") redundantly -- max/min are order-independent, so the four
+//               CTAs agree bit for bit -- and applies the coordinate-trick offsets;
+//   mask        the upper-triangular 64x64 tiles are dealt round-robin to the cluster's 64 two-warp slots; a thread owns one
+//               row of its tile.  When only equal labels can interact it first builds the 64-bit set of equal-label columns
+//               (16 broadcast 128-bit loads of labels, no divergence) and then visits only those columns -- the tile kernel
+//               above pays a divergent branch per column and runs the IoU test whenever ANY lane's label matches.  The row's
+//               64-bit word goes straight into CTA 0's shared memory (distributed shared memory store);
+//   resolve     after one cluster barrier CTA 0 holds the whole mask (<= 128 KB) on chip: warp 0 runs the greedy chain of
+//               nms_resolve_stream_kernel (32-bit halves, branch-free) with no global-memory latency anywhere, folds the kept
+//               rows' words of the next column block itself and leaves the later column words to warp 1, one chunk behind;
+//               the two warps meet at a 64-thread named barrier per chunk, the other warps wait for the gather.
+// Same arithmetic as the three-kernel path (suppresses(), the offsets, the areas), so keep lists are bit-identical to it.
+// ------------------------------------------------------------------------------------------------
+constexpr int kFuseMax = 1024;
+constexpr int kFuseCb = kFuseMax / 64;         // column words per mask row
+constexpr int kFuseCluster = 4;                // 32 images x 4 CTAs: one wave on 148 SMs (one CTA per SM: 156 KB of shared memory)
+constexpr int kFuseThreads = 1024;
+constexpr int kFuseSlots = kFuseThreads / 64;  // two-warp tile slots per CTA
+constexpr size_t kFuseSmemBytes = (size_t)kFuseMax * (kFuseCb * sizeof(uint64_t) + sizeof(float4) + sizeof(float) + 2 * sizeof(int));
+
+__global__ void __cluster_dims__(kFuseCluster, 1, 1) __launch_bounds__(kFuseThreads)
+nms_fused_kernel(const cldet_candidate* __restrict__ sorted, const int32_t* __restrict__ counts, int64_t capacity, int mode,
+                 int64_t vanilla_numel_limit, float thr, int max_rows, int32_t* __restrict__ keep, int32_t* __restrict__ keep_counts,
+                 float* __restrict__ out_scores, int64_t* __restrict__ out_labels, float4* __restrict__ out_boxes) {
+    pdl_wait();                       // may be scheduled while the previous kernel of the chain drains
+    pdl_launch_dependents();
+    namespace cg = cooperative_groups;
+    cg::cluster_group cluster = cg::this_cluster();
+    extern __shared__ __align__(16) unsigned char fuse_smem[];
+    uint64_t* s_mask = reinterpret_cast<uint64_t*>(fuse_smem);                       // [kFuseMax][kFuseCb], used in CTA 0 only
+    float4* s_box = reinterpret_cast<float4*>(fuse_smem + (size_t)kFuseMax * kFuseCb * sizeof(uint64_t));
+    float* s_area = reinterpret_cast<float*>(s_box + kFuseMax);
+    int* s_lab = reinterpret_cast<int*>(s_area + kFuseMax);
+    int* s_keep = s_lab + kFuseMax;
+    __shared__ float red_max[32], red_min[32];
+    __shared__ int red_lab[32];
+    __shared__ unsigned long long s_removed[kFuseCb];
+    __shared__ unsigned long long s_kept[2];
+    __shared__ int s_kept_total;
+    const int rank = (int)cluster.block_rank();
+    const int j = blockIdx.x / kFuseCluster;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int64_t cnt_j = min64(counts[j], capacity);
+    if (cnt_j > max_rows) {                                   // more boxes than the caller's max_count (rounded up to 64, <= kFuseMax):
+        if (rank == 0 && tid == 0) keep_counts[j] = -1;       // report, never truncate silently (uniform over the cluster)
+        return;
+    }
+    const int n = (int)cnt_j;
+    if (n <= 0) {
+        if (rank == 0 && tid == 0) keep_counts[j] = 0;
+        return;
+    }
+    // ---- stage the boxes; the facts nms_prepare_kernel publishes ----
+    float4 me = make_float4(0.f, 0.f, 0.f, 0.f);
+    int my_lab = 0;
+    float m = -INFINITY, mn = INFINITY;
+    int lab_max = 0, lab_min = 0;
+    if (tid < n) {
+        const float4* rec = reinterpret_cast<const float4*>(sorted + (int64_t)j * capacity + tid);
+        me = rec[0];
+        my_lab = __float_as_int(rec[1].y);
+        m = fmaxf(fmaxf(me.x, me.y), fmaxf(me.z, me.w));
+        mn = fminf(fminf(me.x, me.y), fminf(me.z, me.w));
+        lab_max = max(0, my_lab);
+        lab_min = min(0, my_lab);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+        mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+        lab_max = max(lab_max, __shfl_xor_sync(0xffffffffu, lab_max, o));
+        lab_min = min(lab_min, __shfl_xor_sync(0xffffffffu, lab_min, o));
+    }
+    if (lane == 0) {
+        red_max[warp] = m;
+        red_min[warp] = mn;
+        red_lab[warp] = (lab_min < 0) ? 0x7fffffff : lab_max;      // a negative label disables the label shortcut
+    }
+    if (tid < kFuseCb) s_removed[tid] = 0ull;
+    if (tid < 2) s_kept[tid] = 0ull;
+    __syncthreads();
+    m = red_max[lane];
+    mn = red_min[lane];
+    int lmax = red_lab[lane];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+        mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+        lmax = max(lmax, __shfl_xor_sync(0xffffffffu, lmax, o));
+    }
+    int used = mode;
+    if (mode == 0) used = ((int64_t)n * 4 > vanilla_numel_limit) ? 2 : 1;       // torchvision ops/boxes.py batched_nms
+    const bool disjoint = (used == 1) && mn >= 0.0f && lmax < 0x7fffffff && ((double)lmax + 1.0) * ((double)m + 1.0) <= 2097152.0;
+    const bool by_label = (used == 2) || (disjoint && thr >= 0.0f);              // see nms_prepare_kernel / nms_mask_kernel
+    if (tid < n) {
+        if (used == 1) {                                                         // boxes + (label * (max + 1))[:, None]
+            const float off = (float)my_lab * (m + 1.0f);
+            me.x += off; me.y += off; me.z += off; me.w += off;
+        }
+        s_box[tid] = me;
+        s_area[tid] = (me.z - me.x) * (me.w - me.y);
+    }
+    s_lab[tid] = (tid < n) ? my_lab : 0;
+    __syncthreads();
+    // ---- suppression mask, written into CTA 0's shared memory ----
+    const int cbn = (n + 63) >> 6;
+    const int tiles = cbn * (cbn + 1) / 2;
+    uint64_t* mask0 = cluster.map_shared_rank(s_mask, 0);
+    const int rr = tid & 63;
+    for (int t = rank * kFuseSlots + (tid >> 6); t < tiles; t += kFuseCluster * kFuseSlots) {
+        int row_blk = 0, rem = t, len = cbn;                  // upper-triangular tiles, row by row
+        while (rem >= len) {
+            rem -= len;
+            --len;
+            ++row_blk;
+        }
+        const int col_blk = row_blk + rem;
+        const int ri = row_blk * 64 + rr;
+        if (ri >= n) continue;
+        const int c0 = col_blk * 64;
+        const int ncol = min(64, n - c0);
+        uint64_t todo = (ncol == 64) ? ~0ull : ((1ull << ncol) - 1ull);
+        if (row_blk == col_blk) todo &= (rr == 63) ? 0ull : (~0ull << (rr + 1));      // only later boxes of the own block
+        const int lab = s_lab[ri];
+        if (by_label) {
+            const int4* l4 = reinterpret_cast<const int4*>(s_lab + c0);
+            uint32_t elo = 0, ehi = 0;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                const int4 a = l4[q], b = l4[q + 8];
+                elo |= ((a.x == lab) ? 1u : 0u) << (4 * q) | ((a.y == lab) ? 2u : 0u) << (4 * q) | ((a.z == lab) ? 4u : 0u) << (4 * q) |
+                       ((a.w == lab) ? 8u : 0u) << (4 * q);
+                ehi |= ((b.x == lab) ? 1u : 0u) << (4 * q) | ((b.y == lab) ? 2u : 0u) << (4 * q) | ((b.z == lab) ? 4u : 0u) << (4 * q) |
+                       ((b.w == lab) ? 8u : 0u) << (4 * q);
+            }
+            todo &= ((uint64_t)ehi << 32) | elo;
+        }
+        const float4 mine = s_box[ri];
+        const float my_area = s_area[ri];
+        uint64_t bits = 0ull;
+        while (todo) {
+            const int tc = __ffsll((long long)todo) - 1;
+            todo &= todo - 1ull;
+            if (suppresses(mine, my_area, s_box[c0 + tc], s_area[c0 + tc], thr)) bits |= 1ull << tc;
+        }
+        mask0[(size_t)ri * kFuseCb + col_blk] = bits;
+    }
+    cluster.sync();                                           // every word of the mask has landed in CTA 0
+    if (rank != 0) return;
+    // ---- greedy resolve from shared memory: warp 0 = the chain, warp 1 = absorbs one chunk behind ----
+    if (warp < 2) {
+        int kept_total = 0;
+        for (int c = 0; c < cbn; ++c) {
+            const int buf = c & 1;
+            if (warp == 0) {
+                const int rows = min(64, n - c * 64);
+                uint64_t cur = s_removed[c];
+                if (rows < 64) cur |= ~0ull << rows;                          // slots past the end can never be kept
+                const uint64_t* diag = s_mask + (size_t)(c * 64) * kFuseCb + c;
+                uint32_t clo = (uint32_t)cur, chi = (uint32_t)(cur >> 32);
+#pragma unroll
+                for (int g = 0; g < 2; ++g) {
+                    uint64_t w[16];
+#pragma unroll
+                    for (int q = 0; q < 16; ++q) w[q] = diag[(g * 16 + q) * kFuseCb];
+#pragma unroll
+                    for (int q = 0; q < 16; ++q) {
+                        const int b = g * 16 + q;
+                        const bool take = !((clo >> b) & 1u);
+                        clo |= take ? (uint32_t)w[q] : 0u;
+                        chi |= take ? (uint32_t)(w[q] >> 32) : 0u;
+                    }
+                }
+#pragma unroll
+                for (int g = 2; g < 4; ++g) {
+                    uint32_t w[16];
+#pragma unroll
+                    for (int q = 0; q < 16; ++q) w[q] = (uint32_t)(diag[(g * 16 + q) * kFuseCb] >> 32);
+#pragma unroll
+                    for (int q = 0; q < 16; ++q) {
+                        const int b = g * 16 + q - 32;
+                        const bool take = !((chi >> b) & 1u);
+                        chi |= take ? w[q] : 0u;
+                    }
+                }
+                const uint64_t kept = ~(((uint64_t)chi << 32) | clo);
+                if (c + 1 < cbn) {                                            // what chunk c+1 needs from this chunk
+                    const uint64_t* nxt = s_mask + (size_t)(c * 64) * kFuseCb + (c + 1);
+                    const uint64_t v = (((kept >> lane) & 1ull) ? nxt[lane * kFuseCb] : 0ull) |
+                                       (((kept >> (lane + 32)) & 1ull) ? nxt[(lane + 32) * kFuseCb] : 0ull);
+                    const unsigned lo = __reduce_or_sync(0xffffffffu, (unsigned)v);
+                    const unsigned hi = __reduce_or_sync(0xffffffffu, (unsigned)(v >> 32));
+                    if (lane == 0) atomicOr(&s_removed[c + 1], ((unsigned long long)hi << 32) | lo);
+                }
+                if (lane == 0) s_kept[buf] = kept;
+                const uint64_t lo0 = (1ull << lane) - 1ull;
+                if ((kept >> lane) & 1ull) {
+                    const int pos = kept_total + __popcll(kept & lo0);
+                    keep[(int64_t)j * capacity + pos] = c * 64 + lane;
+                    s_keep[pos] = c * 64 + lane;
+                }
+                const uint64_t lo1 = (1ull << (lane + 32)) - 1ull;
+                if ((kept >> (lane + 32)) & 1ull) {
+                    const int pos = kept_total + __popcll(kept & lo1);
+                    keep[(int64_t)j * capacity + pos] = c * 64 + lane + 32;
+                    s_keep[pos] = c * 64 + lane + 32;
+                }
+                kept_total += __popcll(kept);
+            } else if (c >= 1 && c + 1 < cbn) {
+                // chunk c-1's kept rows into the column words c+1 ..: lane = (word, half of the 64 rows)
+                const int wd = c + 1 + (lane & 15), half = lane >> 4;
+                if (wd < cbn) {
+                    const uint64_t kp = s_kept[buf ^ 1] >> (32 * half);
+                    const uint64_t* rowp = s_mask + (size_t)((c - 1) * 64 + 32 * half) * kFuseCb + wd;
+                    uint64_t v0 = 0ull, v1 = 0ull;
+#pragma unroll
+                    for (int b = 0; b < 32; b += 2) {                         // unconditional independent loads, masked by the bit
+                        v0 |= rowp[b * kFuseCb] & (0ull - ((kp >> b) & 1ull));
+                        v1 |= rowp[(b + 1) * kFuseCb] & (0ull - ((kp >> (b + 1)) & 1ull));
+                    }
+                    const uint64_t v = v0 | v1;
+                    if (v) atomicOr(&s_removed[wd], (unsigned long long)v);
+                }
+            }
+            asm volatile("bar.sync 1, 64;" ::: "memory");                      // warps 0 and 1 only
+        }
+        if (tid == 0) {
+            keep_counts[j] = kept_total;
+            s_kept_total = kept_total;
+        }
+    }
+    if (!out_scores) return;
+    __syncthreads();
+    const int kept_n = s_kept_total;
+    for (int i = tid; i < kept_n; i += kFuseThreads) {
+        const float4* rec = reinterpret_cast<const float4*>(sorted + (int64_t)j * capacity + s_keep[i]);
+        const float4 b = rec[0], t = rec[1];
+        out_scores[(int64_t)j * capacity + i] = t.x;
+        out_labels[(int64_t)j * capacity + i] = (int64_t)__float_as_int(t.y);
+        out_boxes[(int64_t)j * capacity + i] = b;
+    }
+}
+
 __global__ void __launch_bounds__(256)
 gather_detections_kernel(const cldet_candidate* __restrict__ sorted, const int32_t* __restrict__ keep,
                          const int32_t* __restrict__ keep_counts, int64_t capacity, float* __restrict__ scores,
@@ -1548,6 +1899,21 @@ static bool select_multi_launch() {          // CLDET_SELECT_MULTI=1: the round-
     static const bool v = [] {
         const char* e = getenv("CLDET_SELECT_MULTI");
         return e && e[0] == '1';
+    }();
+    return v;
+}
+static bool nms_fused_enabled() {             // CLDET_NMS_FUSED=0: the three-launch K6 for short lists too (A/B only)
+    static const bool v = [] {
+        const char* e = getenv("CLDET_NMS_FUSED");
+        return !(e && e[0] == '0');
+    }();
+    return v;
+}
+static int64_t bucket_n() {                   // CLDET_BUCKET_RANK=0: the pairwise rank for short lists too (A/B only)
+    static const int64_t v = [] {
+        const char* e = getenv("CLDET_BUCKET_RANK");
+        const char* f = getenv("CLDET_FORCE_RANK_SORT");
+        return ((e && e[0] == '0') || (f && f[0] == '1')) ? (int64_t)0 : (int64_t)kBucketMax;
     }();
     return v;
 }
@@ -1771,7 +2137,7 @@ int cldet_sort_candidates(const cldet_candidate* d_candidates, const uint64_t* d
                 (unsigned)num_images);
         CLDET_CUDA_TRY(launch_pdl(rank_sort_kernel, gr, dim3(256), 0, s, (const cldet_candidate*)sel_cand, (const uint64_t*)sel_keys,
                                   (const uint32_t*)state, d_counts, max_count, topk, d_sorted, sorted_capacity, d_sorted_counts,
-                                  d_candidates, d_keys, capacity, (int64_t)0));
+                                  d_candidates, d_keys, capacity, (int64_t)0, bucket_n()));
     } else if (max_count > kRadixMin && !force_rank_sort()) {
         // the reference's mode (no top-k) with long lists: one launch, one CTA per image, every radix pass inside it
         uint64_t* kbuf = reinterpret_cast<uint64_t*>(p + off);
@@ -1783,14 +2149,14 @@ int cldet_sort_candidates(const cldet_candidate* d_candidates, const uint64_t* d
         dim3 gshort((unsigned)((kRadixMin + kRankPerBlock - 1) / kRankPerBlock), (unsigned)num_images);
         CLDET_CUDA_TRY(launch_pdl(rank_sort_kernel, gshort, dim3(256), 0, s, d_candidates, d_keys, (const uint32_t*)nullptr, d_counts,
                                   capacity, 0, d_sorted, sorted_capacity, d_sorted_counts, (const cldet_candidate*)nullptr,
-                                  (const uint64_t*)nullptr, (int64_t)0, (int64_t)kRadixMin));
+                                  (const uint64_t*)nullptr, (int64_t)0, (int64_t)kRadixMin, bucket_n()));
         CLDET_CUDA_TRY(launch_pdl(radix_sort_kernel, dim3(num_images), dim3(kRsThreads), 0, s, d_candidates, d_keys, d_counts, capacity,
                                   max_count, d_sorted, sorted_capacity, d_sorted_counts, kbuf, ibuf, (int64_t)kRadixMin));
     } else {
         dim3 gc((unsigned)std::min<int64_t>((max_count + kRankPerBlock - 1) / kRankPerBlock, 65535 * 16), (unsigned)num_images);
-        CLDET_CUDA_TRY(launch_pdl(rank_sort_kernel, gc, dim3(256), 0, s, d_candidates, d_keys, (const uint32_t*)nullptr, d_counts, capacity,
-                                  0, d_sorted, sorted_capacity, d_sorted_counts, (const cldet_candidate*)nullptr,
-                                  (const uint64_t*)nullptr, (int64_t)0, (int64_t)0));
+            CLDET_CUDA_TRY(launch_pdl(rank_sort_kernel, gc, dim3(256), 0, s, d_candidates, d_keys, (const uint32_t*)nullptr, d_counts, capacity,
+                                      0, d_sorted, sorted_capacity, d_sorted_counts, (const cldet_candidate*)nullptr,
+                                      (const uint64_t*)nullptr, (int64_t)0, (int64_t)0, bucket_n()));
     }
     return CLDET_OK;
 }
@@ -1834,6 +2200,15 @@ static int nms_sorted_impl(const cldet_candidate* d_sorted, const int32_t* d_sor
         return CLDET_OK;
     }
     if (workspace_bytes < cldet_nms_workspace_bytes(num_images, max_count)) return CLDET_ERR_WORKSPACE_TOO_SMALL;
+    if (max_count <= kFuseMax && nms_fused_enabled()) {
+        // short lists (the pre-NMS top-k regime): prepare + mask + resolve + gather in one launch, one cluster per image
+        CLDET_CUDA_TRY(cudaFuncSetAttribute(nms_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFuseSmemBytes));
+        CLDET_CUDA_TRY(launch_pdl(nms_fused_kernel, dim3((unsigned)num_images * kFuseCluster), dim3(kFuseThreads), kFuseSmemBytes, s, d_sorted,
+                                  d_sorted_counts, capacity, mode, vanilla_numel_limit, iou_thresh, (int)((max_count + 63) / 64 * 64), d_keep,
+                                  d_keep_counts, d_scores, d_labels,
+                                  reinterpret_cast<float4*>(d_boxes)));
+        return CLDET_OK;
+    }
     const NmsWs w = nms_ws_layout(d_workspace, num_images, max_count);
     if (w.col_blocks > 65535) return CLDET_ERR_UNSUPPORTED;
     CLDET_CUDA_TRY(launch_pdl(nms_prepare_kernel, dim3(num_images), dim3(256), 0, s, d_sorted, d_sorted_counts, capacity, mode,
@@ -1958,7 +2333,8 @@ int cldet_batched_nms(const float* d_boxes, const float* d_scores, const int64_t
         radix_sort_kernel<<<1, kRsThreads, 0, s>>>(packed, keys, cnts, num_boxes, num_boxes, sorted, num_boxes, cnts + 1, kbuf, ibuf);
     } else {
         dim3 g((unsigned)((num_boxes + kRankPerBlock - 1) / kRankPerBlock), 1);
-        rank_sort_kernel<<<g, 256, 0, s>>>(packed, keys, nullptr, cnts, num_boxes, 0, sorted, num_boxes, cnts + 1);
+        rank_sort_kernel<<<g, 256, 0, s>>>(packed, keys, nullptr, cnts, num_boxes, 0, sorted, num_boxes, cnts + 1, nullptr, nullptr, 0, 0,
+                                           bucket_n());
     }
     CLDET_LAUNCH_CHECK();
     int rc = cldet_nms_sorted(sorted, cnts + 1, 1, num_boxes, num_boxes, iou_thresh, d_idxs ? mode : 1, vanilla_numel_limit,

@@ -70,7 +70,8 @@ def test_nms_golden_torchvision(t):
     assert np.array_equal(auto, g[f'vanilla{t}'] if boxes.numel() > 4000 else g[f'trick{t}_unique'])
 
 
-@pytest.mark.parametrize('K,ncls,seed', [(0, 1, 0), (1, 1, 1), (63, 3, 2), (64, 3, 3), (65, 3, 4), (1000, 20, 5), (4097, 80, 6)])
+@pytest.mark.parametrize('K,ncls,seed', [(0, 1, 0), (1, 1, 1), (63, 3, 2), (64, 3, 3), (65, 3, 4), (1000, 20, 5), (4097, 80, 6),
+                                          (1023, 1, 7), (1024, 7, 8), (1025, 7, 9), (2048, 40, 10), (2049, 40, 11)])
 def test_nms_random_vs_oracle(K, ncls, seed):
     rng = np.random.default_rng(seed)
     x1, y1 = rng.uniform(0, 300, K), rng.uniform(0, 300, K)
@@ -346,6 +347,62 @@ def test_radix_sort_orders_like_a_stable_descending_sort(counts, kind):
         order = torch.argsort(keys[j, :c] ^ (-0x8000000000000000), descending=True, stable=True)
         assert torch.equal(got_ids[j, :c], ids[j, :c][order]), (kind, j, c)
         assert torch.equal(got_scores[j, :c].view(torch.int32), scores[j, :c][order].view(torch.int32))
+
+
+@pytest.mark.parametrize('counts', [[1, 2, 3, 1000], [2047, 2048, 1025, 0], [1500, 3000, 5000, 64]])
+@pytest.mark.parametrize('kind', ['random', 'all_equal', 'few_values'])
+@pytest.mark.parametrize('topk', [0, 1000])
+def test_short_list_sort_and_topk(counts, kind, topk):
+    """Lists of <= 2048 candidates are ranked by one block through a bucket pass, longer ones by the pairwise rank / radix sort, and with a
+    top-k by radix select first (ties at the k-th score survive the select, so an all-equal list reaches the ordering pass whole):
+    every image of a ragged batch must come out in the order of a stable descending sort of the keys, cut at top-k."""
+    n, cap = len(counts), max(max(counts), 1)
+    gen = torch.Generator(device=DEV).manual_seed(sum(counts) + len(kind) + topk)
+    if kind == 'random':
+        scores = torch.rand(n, cap, device=DEV, generator=gen)
+    elif kind == 'all_equal':
+        scores = torch.full((n, cap), 0.75, device=DEV)
+    else:
+        scores = torch.randint(0, 7, (n, cap), device=DEV, generator=gen).float() / 8 + 0.06
+    ids = torch.stack([torch.randperm(cap + 1000, device=DEV, generator=gen)[:cap] for _ in range(n)]).to(torch.int32)
+    got_ids, got_scores, got_counts, keys = _sort_through_abi(scores, ids, counts, topk=topk)
+    want_counts = [min(c, topk) if topk else c for c in counts]
+    assert got_counts.tolist() == want_counts
+    for j, c in enumerate(counts):
+        if c == 0:
+            continue
+        order = torch.argsort(keys[j, :c] ^ (-0x8000000000000000), descending=True, stable=True)[:want_counts[j]]
+        assert torch.equal(got_ids[j, :want_counts[j]], ids[j, :c][order]), (kind, j, c)
+        assert torch.equal(got_scores[j, :want_counts[j]].view(torch.int32), scores[j, :c][order].view(torch.int32))
+
+
+@pytest.mark.parametrize('k', [500, 1024, 3000])
+@pytest.mark.parametrize('case', ['negative', 'huge', 'many_labels', 'plain'])
+def test_coordinate_trick_corner_cases_vs_torchvision_same_device(k, case):
+    """torchvision's coordinate trick adds label * (max + 1) in fp32.  With ordinary boxes that keeps classes apart and the mask
+    kernels skip cross-label pairs on the label compare; with negative coordinates, huge coordinates (the offsets round and
+    classes DO interact) or huge label values that proof fails and the full test must run.  Either way the keep list has to equal
+    torchvision's own kernel on the same GPU -- for the one-launch short-list path (k <= 1024) and the three-launch path."""
+    import torchvision
+    gen = torch.Generator(device=DEV).manual_seed(k + len(case))
+    centers = torch.rand(k // 15 + 1, 2, device=DEV, generator=gen) * 500
+    which = torch.randint(0, centers.shape[0], (k,), device=DEV, generator=gen)
+    xy = centers[which] + torch.randn(k, 2, device=DEV, generator=gen) * 5
+    wh = torch.rand(k, 2, device=DEV, generator=gen) * 50 + 8
+    idxs = torch.randint(0, 6, (k,), device=DEV, generator=gen)
+    if case == 'negative':
+        xy = xy - 250.0
+    elif case == 'huge':
+        xy = xy + 3.0e7          # fp32 spacing 2 at this magnitude: offsets and boxes round, classes merge
+        wh = wh * 4
+    elif case == 'many_labels':
+        idxs = idxs * 100000     # (label_max + 1) * (max + 1) far beyond 2^21
+    boxes = torch.cat([xy, xy + wh], dim=1).contiguous()
+    scores = ((torch.randperm(k, device=DEV, generator=gen).float() + 1) / (k + 1)).contiguous()      # distinct
+    ref = torchvision.ops.boxes._batched_nms_coordinate_trick(boxes, scores, idxs, 0.5)
+    got = D.batched_nms(boxes, scores, idxs, 0.5, mode=D.NMS_MODE_TRICK)
+    assert torch.equal(got, ref), (got.shape, ref.shape)
+    assert 0 < got.shape[0] < k
 
 
 @pytest.mark.parametrize('k,trick', [(3000, True), (10000, True), (10000, False), (30000, False)])
