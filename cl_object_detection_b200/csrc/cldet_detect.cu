@@ -853,16 +853,34 @@ rank_sort_kernel(const cldet_candidate* __restrict__ cand, const uint64_t* __res
         __syncthreads();
         const float4* src = reinterpret_cast<const float4*>(cand + (int64_t)j * in_capacity);
         float4* dst = reinterpret_cast<float4*>(sorted + (int64_t)j * out_capacity);
+        int rk[kPer];
 #pragma unroll
         for (int u = 0; u < kPer; ++u) {
             const int i = tid + 256 * u;
+            rk[u] = 0x7fffffff;
             if (i < nn) {
                 const int b0 = (int)bstart[bkt[u]], b1 = b0 + (int)bcnt[bkt[u]];
                 int r = b0;
                 for (int q = b0; q < b1; ++q) r += (tile[q] > kreg[u]) ? 1 : 0;
-                if (r < limit && r < out_capacity) {
-                    dst[2 * (int64_t)r] = src[2 * (int64_t)i];
-                    dst[2 * (int64_t)r + 1] = src[2 * (int64_t)i + 1];
+                rk[u] = r;
+            }
+        }
+        // the 32-byte records: all loads of a half in flight before the first store (one L2 round trip per half, not per record)
+#pragma unroll
+        for (int h = 0; h < kPer; h += 4) {
+            float4 a[4], b[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int i = tid + 256 * (h + u);
+                const bool on = rk[h + u] < limit && rk[h + u] < out_capacity;
+                a[u] = on ? src[2 * (int64_t)i] : make_float4(0.f, 0.f, 0.f, 0.f);
+                b[u] = on ? src[2 * (int64_t)i + 1] : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                if (rk[h + u] < limit && rk[h + u] < out_capacity) {
+                    dst[2 * (int64_t)rk[h + u]] = a[u];
+                    dst[2 * (int64_t)rk[h + u] + 1] = b[u];
                 }
             }
         }
@@ -1542,8 +1560,9 @@ nms_resolve_stream_kernel(const int32_t* __restrict__ counts, int64_t capacity, 
 //               64-bit word goes straight into CTA 0's shared memory (distributed shared memory store);
 //   resolve     after one cluster barrier CTA 0 holds the whole mask (<= 128 KB) on chip: warp 0 runs the greedy chain of
 //               nms_resolve_stream_kernel (32-bit halves, branch-free) with no global-memory latency anywhere, folds the kept
-//               rows' words of the next column block itself and leaves the later column words to warp 1, one chunk behind;
-//               the two warps meet at a 64-thread named barrier per chunk, the other warps wait for the gather.
+//               rows' words of the next column block itself and leaves the later column words to warps 1..4, one chunk behind;
+//               the five warps meet at a named barrier per chunk, the other warps wait for the gather.  The chain decides a
+//               64-box chunk in parallel rounds (see below) instead of 64 dependent steps.
 // Same arithmetic as the three-kernel path (suppresses(), the offsets, the areas), so keep lists are bit-identical to it.
 // ------------------------------------------------------------------------------------------------
 constexpr int kFuseMax = 1024;
@@ -1551,7 +1570,10 @@ constexpr int kFuseCb = kFuseMax / 64;         // column words per mask row
 constexpr int kFuseCluster = 4;                // 32 images x 4 CTAs: one wave on 148 SMs (one CTA per SM: 156 KB of shared memory)
 constexpr int kFuseThreads = 1024;
 constexpr int kFuseSlots = kFuseThreads / 64;  // two-warp tile slots per CTA
-constexpr size_t kFuseSmemBytes = (size_t)kFuseMax * (kFuseCb * sizeof(uint64_t) + sizeof(float4) + sizeof(float) + 2 * sizeof(int));
+constexpr int kFuseChainWarps = 5;             // warp 0 runs the chain, warps 1..4 absorb 16 rows each, one chunk behind
+constexpr int kFuseRounds = 8;                 // parallel decision rounds per 64-box chunk before the serial fallback
+constexpr size_t kFuseSmemBytes =
+    (size_t)kFuseMax * ((kFuseCb + 2) * sizeof(uint64_t) + sizeof(float4) + sizeof(float) + 2 * sizeof(int));
 
 __global__ void __cluster_dims__(kFuseCluster, 1, 1) __launch_bounds__(kFuseThreads)
 nms_fused_kernel(const cldet_candidate* __restrict__ sorted, const int32_t* __restrict__ counts, int64_t capacity, int mode,
@@ -1563,7 +1585,9 @@ nms_fused_kernel(const cldet_candidate* __restrict__ sorted, const int32_t* __re
     cg::cluster_group cluster = cg::this_cluster();
     extern __shared__ __align__(16) unsigned char fuse_smem[];
     uint64_t* s_mask = reinterpret_cast<uint64_t*>(fuse_smem);                       // [kFuseMax][kFuseCb], used in CTA 0 only
-    float4* s_box = reinterpret_cast<float4*>(fuse_smem + (size_t)kFuseMax * kFuseCb * sizeof(uint64_t));
+    uint64_t* s_diag = s_mask + (size_t)kFuseMax * kFuseCb;                          // [kFuseMax] word (row block, row block) of every row
+    uint64_t* s_next = s_diag + kFuseMax;                                            // [kFuseMax] word (row block, row block + 1)
+    float4* s_box = reinterpret_cast<float4*>(s_next + kFuseMax);
     float* s_area = reinterpret_cast<float*>(s_box + kFuseMax);
     int* s_lab = reinterpret_cast<int*>(s_area + kFuseMax);
     int* s_keep = s_lab + kFuseMax;
@@ -1641,6 +1665,8 @@ nms_fused_kernel(const cldet_candidate* __restrict__ sorted, const int32_t* __re
     const int cbn = (n + 63) >> 6;
     const int tiles = cbn * (cbn + 1) / 2;
     uint64_t* mask0 = cluster.map_shared_rank(s_mask, 0);
+    uint64_t* diag0 = cluster.map_shared_rank(s_diag, 0);
+    uint64_t* next0 = cluster.map_shared_rank(s_next, 0);
     const int rr = tid & 63;
     for (int t = rank * kFuseSlots + (tid >> 6); t < tiles; t += kFuseCluster * kFuseSlots) {
         int row_blk = 0, rem = t, len = cbn;                  // upper-triangular tiles, row by row
@@ -1678,12 +1704,15 @@ nms_fused_kernel(const cldet_candidate* __restrict__ sorted, const int32_t* __re
             todo &= todo - 1ull;
             if (suppresses(mine, my_area, s_box[c0 + tc], s_area[c0 + tc], thr)) bits |= 1ull << tc;
         }
-        mask0[(size_t)ri * kFuseCb + col_blk] = bits;
+        // the two words the chain itself reads go to compact arrays (conflict-free for a warp), the rest into the row-major mask
+        if (col_blk == row_blk) diag0[ri] = bits;
+        else if (col_blk == row_blk + 1) next0[ri] = bits;
+        else mask0[(size_t)ri * kFuseCb + col_blk] = bits;
     }
     cluster.sync();                                           // every word of the mask has landed in CTA 0
     if (rank != 0) return;
-    // ---- greedy resolve from shared memory: warp 0 = the chain, warp 1 = absorbs one chunk behind ----
-    if (warp < 2) {
+    // ---- greedy resolve from shared memory: warp 0 = the chain, warps 1..4 = absorb one chunk behind ----
+    if (warp < kFuseChainWarps) {
         int kept_total = 0;
         for (int c = 0; c < cbn; ++c) {
             const int buf = c & 1;
@@ -1691,38 +1720,41 @@ nms_fused_kernel(const cldet_candidate* __restrict__ sorted, const int32_t* __re
                 const int rows = min(64, n - c * 64);
                 uint64_t cur = s_removed[c];
                 if (rows < 64) cur |= ~0ull << rows;                          // slots past the end can never be kept
-                const uint64_t* diag = s_mask + (size_t)(c * 64) * kFuseCb + c;
-                uint32_t clo = (uint32_t)cur, chi = (uint32_t)(cur >> 32);
-#pragma unroll
-                for (int g = 0; g < 2; ++g) {
-                    uint64_t w[16];
-#pragma unroll
-                    for (int q = 0; q < 16; ++q) w[q] = diag[(g * 16 + q) * kFuseCb];
-#pragma unroll
-                    for (int q = 0; q < 16; ++q) {
-                        const int b = g * 16 + q;
-                        const bool take = !((clo >> b) & 1u);
-                        clo |= take ? (uint32_t)w[q] : 0u;
-                        chi |= take ? (uint32_t)(w[q] >> 32) : 0u;
+                // Lane l holds the diagonal words of rows l and l+32 (bits > own row only).  Decide the chunk in parallel rounds:
+                // an undecided box that NO undecided box could suppress is kept (the first undecided one always is); the boxes
+                // the newly kept ones suppress leave the undecided set.  Identical to the sequential greedy scan; sparse
+                // suppression takes 1-3 rounds (4 warp-wide ORs each) instead of 64 dependent steps.
+                const uint64_t d0 = s_diag[c * 64 + lane], d1 = s_diag[c * 64 + 32 + lane];
+                uint64_t und = ~cur, kept = 0ull;
+                int round = 0;
+                while (und) {
+                    if (++round > kFuseRounds) {                              // a long dependency chain: finish it box by box
+                        while (und) {
+                            const int b = __ffsll((long long)und) - 1;
+                            const uint64_t dsel = (b < 32) ? d0 : d1;
+                            const uint64_t d = __shfl_sync(0xffffffffu, dsel, b & 31);
+                            kept |= 1ull << b;
+                            und &= ~((1ull << b) | d);
+                        }
+                        break;
                     }
-                }
-#pragma unroll
-                for (int g = 2; g < 4; ++g) {
-                    uint32_t w[16];
-#pragma unroll
-                    for (int q = 0; q < 16; ++q) w[q] = (uint32_t)(diag[(g * 16 + q) * kFuseCb] >> 32);
-#pragma unroll
-                    for (int q = 0; q < 16; ++q) {
-                        const int b = g * 16 + q - 32;
-                        const bool take = !((chi >> b) & 1u);
-                        chi |= take ? w[q] : 0u;
+                    const uint64_t mine = (((und >> lane) & 1ull) ? d0 : 0ull) | (((und >> (lane + 32)) & 1ull) ? d1 : 0ull);
+                    const uint64_t threat = ((uint64_t)__reduce_or_sync(0xffffffffu, (unsigned)(mine >> 32)) << 32) |
+                                            __reduce_or_sync(0xffffffffu, (unsigned)mine);
+                    if (!(threat & und)) {                                    // nobody undecided is threatened: keep them all (the
+                        kept |= und;                                          // common chunk: one reduction stage instead of two)
+                        break;
                     }
+                    const uint64_t fresh = und & ~threat;                      // never empty: the first undecided box is in it
+                    const uint64_t hit = (((fresh >> lane) & 1ull) ? d0 : 0ull) | (((fresh >> (lane + 32)) & 1ull) ? d1 : 0ull);
+                    const uint64_t gone = ((uint64_t)__reduce_or_sync(0xffffffffu, (unsigned)(hit >> 32)) << 32) |
+                                          __reduce_or_sync(0xffffffffu, (unsigned)hit);
+                    kept |= fresh;
+                    und &= ~(fresh | gone);
                 }
-                const uint64_t kept = ~(((uint64_t)chi << 32) | clo);
                 if (c + 1 < cbn) {                                            // what chunk c+1 needs from this chunk
-                    const uint64_t* nxt = s_mask + (size_t)(c * 64) * kFuseCb + (c + 1);
-                    const uint64_t v = (((kept >> lane) & 1ull) ? nxt[lane * kFuseCb] : 0ull) |
-                                       (((kept >> (lane + 32)) & 1ull) ? nxt[(lane + 32) * kFuseCb] : 0ull);
+                    const uint64_t v = (((kept >> lane) & 1ull) ? s_next[c * 64 + lane] : 0ull) |
+                                       (((kept >> (lane + 32)) & 1ull) ? s_next[c * 64 + 32 + lane] : 0ull);
                     const unsigned lo = __reduce_or_sync(0xffffffffu, (unsigned)v);
                     const unsigned hi = __reduce_or_sync(0xffffffffu, (unsigned)(v >> 32));
                     if (lane == 0) atomicOr(&s_removed[c + 1], ((unsigned long long)hi << 32) | lo);
@@ -1742,14 +1774,14 @@ nms_fused_kernel(const cldet_candidate* __restrict__ sorted, const int32_t* __re
                 }
                 kept_total += __popcll(kept);
             } else if (c >= 1 && c + 1 < cbn) {
-                // chunk c-1's kept rows into the column words c+1 ..: lane = (word, half of the 64 rows)
-                const int wd = c + 1 + (lane & 15), half = lane >> 4;
+                // chunk c-1's kept rows into the column words c+1 ..: warp w takes 16 of the 64 rows, lane = (word, 8 of those rows)
+                const int wd = c + 1 + (lane & 15), r0 = (warp - 1) * 16 + (lane >> 4) * 8;
                 if (wd < cbn) {
-                    const uint64_t kp = s_kept[buf ^ 1] >> (32 * half);
-                    const uint64_t* rowp = s_mask + (size_t)((c - 1) * 64 + 32 * half) * kFuseCb + wd;
+                    const uint64_t kp = s_kept[buf ^ 1] >> r0;
+                    const uint64_t* rowp = s_mask + (size_t)((c - 1) * 64 + r0) * kFuseCb + wd;
                     uint64_t v0 = 0ull, v1 = 0ull;
 #pragma unroll
-                    for (int b = 0; b < 32; b += 2) {                         // unconditional independent loads, masked by the bit
+                    for (int b = 0; b < 8; b += 2) {                          // unconditional independent loads, masked by the bit
                         v0 |= rowp[b * kFuseCb] & (0ull - ((kp >> b) & 1ull));
                         v1 |= rowp[(b + 1) * kFuseCb] & (0ull - ((kp >> (b + 1)) & 1ull));
                     }
@@ -1757,7 +1789,7 @@ nms_fused_kernel(const cldet_candidate* __restrict__ sorted, const int32_t* __re
                     if (v) atomicOr(&s_removed[wd], (unsigned long long)v);
                 }
             }
-            asm volatile("bar.sync 1, 64;" ::: "memory");                      // warps 0 and 1 only
+            asm volatile("bar.sync 1, %0;" ::"n"(32 * kFuseChainWarps) : "memory");      // the chain warp and the absorbers only
         }
         if (tid == 0) {
             keep_counts[j] = kept_total;
