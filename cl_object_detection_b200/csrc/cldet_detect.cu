@@ -98,7 +98,7 @@ __global__ void __launch_bounds__(kFilterThreads)
 decode_filter_kernel(const float* __restrict__ cls, int is_logits, const float4* __restrict__ reg,
                      const float4* __restrict__ anchors, int64_t A, int C, int rows_per_block, int stride, float img_w,
                      float img_h, float score_thresh, float prefilter, cldet_candidate* __restrict__ cand,
-                     uint64_t* __restrict__ keys, int64_t capacity, int32_t* __restrict__ counts) {
+                     uint64_t* __restrict__ keys, int64_t capacity, int32_t* __restrict__ counts, int block_append) {
     pdl_launch_dependents();          // head of the chain: the select / sort kernel may be scheduled while this grid drains
     extern __shared__ float part[];          // [rows_per_block][stride] per-vector maxima; stride is odd: conflict-free
     // per vector (VEC == 4): bits 0-1 = index of the FIRST element attaining the vector's maximum, bit 2 = another element of
@@ -246,16 +246,41 @@ decode_filter_kernel(const float* __restrict__ cls, int is_logits, const float4*
             is_cand = best > score_thresh;                // model.py:536  scores > 0.05
         }
     }
-    // warp-aggregated append: one atomic per warp, issued BEFORE the survivors' decode so that its round trip to L2 overlaps
-    // the anchor / regression loads and the two exponentials (a block-wide atomic + barrier made every block wait ~1 us)
+    // aggregated append: the atomic is issued BEFORE the survivors' decode so that its round trip to L2 overlaps the anchor /
+    // regression loads and the two exponentials
     const unsigned ballot = __ballot_sync(0xffffffffu, is_cand);
     const int lane = threadIdx.x & 31;
     int warp_base = 0;
-    if (ballot != 0u && lane == 0) warp_base = atomicAdd(&counts[j], __popc(ballot));
     float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
     const int64_t an = a0 + r;
-    if (is_cand) b = decode_clip(anchors[an], reg[(int64_t)j * A + an], img_w, img_h);
-    warp_base = __shfl_sync(0xffffffffu, warp_base, 0);
+    if (block_append) {
+        // Block-aggregated form (the default): ONE atomic per block that has candidates.  The N per-image counters share one
+        // 128-byte line, so every append of the launch is serialised by one L2 slice.  When every anchor is a candidate (an
+        // untrained model) one atomic per WARP is 200 k atomics per launch, as long as the whole stream: the kernel then ran
+        // 0.40 or 0.62 ms from one process to the next on the same GPU (where the allocator put the counters); per block it is
+        // 0.417 ms every time, for +0.3 % on a trained-like batch (two barriers per block).
+        __shared__ int warp_cnt[kFilterThreads / 32];
+        __shared__ int block_base;
+        const int warp = threadIdx.x >> 5;
+        if (lane == 0) warp_cnt[warp] = __popc(ballot);
+        __syncthreads();
+        int total = 0, before = 0;
+#pragma unroll
+        for (int w = 0; w < kFilterThreads / 32; ++w) {
+            const int c = warp_cnt[w];
+            before += (w < warp) ? c : 0;
+            total += c;
+        }
+        if (total == 0) return;                                  // block-uniform
+        if (threadIdx.x == 0) block_base = atomicAdd(&counts[j], total);
+        if (is_cand) b = decode_clip(anchors[an], reg[(int64_t)j * A + an], img_w, img_h);
+        __syncthreads();
+        warp_base = block_base + before;
+    } else {
+        if (ballot != 0u && lane == 0) warp_base = atomicAdd(&counts[j], __popc(ballot));
+        if (is_cand) b = decode_clip(anchors[an], reg[(int64_t)j * A + an], img_w, img_h);
+        warp_base = __shfl_sync(0xffffffffu, warp_base, 0);
+    }
     if (is_cand) {
         const int64_t slot = (int64_t)warp_base + __popc(ballot & ((1u << lane) - 1u));
         if (slot < capacity) {
@@ -1949,6 +1974,13 @@ static int64_t bucket_n() {                   // CLDET_BUCKET_RANK=0: the pairwi
     }();
     return v;
 }
+static int k4_block_append() {                // CLDET_K4_BLOCK_APPEND=0: one append atomic per warp instead of per block (A/B only)
+    static const int v = [] {
+        const char* e = getenv("CLDET_K4_BLOCK_APPEND");
+        return (e && e[0] == '0') ? 0 : 1;
+    }();
+    return v;
+}
 static bool force_rank_sort() {
     static const bool v = [] {
         const char* e = getenv("CLDET_FORCE_RANK_SORT");
@@ -2045,12 +2077,12 @@ int cldet_decode_filter(const float* d_cls, int is_logits, const float* d_reg, c
         decode_filter_kernel<4><<<grid, kFilterThreads, smem, s>>>(
             d_cls, is_logits, reinterpret_cast<const float4*>(d_reg), reinterpret_cast<const float4*>(d_anchors), num_anchors,
             num_classes, rows, stride, (float)width, (float)height, score_thresh, prefilter, d_candidates, d_keys, capacity,
-            d_counts);
+            d_counts, k4_block_append());
     else
         decode_filter_kernel<1><<<grid, kFilterThreads, smem, s>>>(
             d_cls, is_logits, reinterpret_cast<const float4*>(d_reg), reinterpret_cast<const float4*>(d_anchors), num_anchors,
             num_classes, rows, stride, (float)width, (float)height, score_thresh, prefilter, d_candidates, d_keys, capacity,
-            d_counts);
+            d_counts, k4_block_append());
     CLDET_LAUNCH_CHECK();
     return CLDET_OK;
 }
