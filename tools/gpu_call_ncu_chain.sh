@@ -1,9 +1,9 @@
 #!/bin/bash
-# ncu --set full of the post-filter chain (K5/K6) on the trained-like config-4 batch; raw page exported on the box
+# ncu --set full of the long-list resolve (predict, one image, ~8 k candidates); raw page exported on the box
 set -u
 mkdir -p gpurun_out
-D="python tools/bench_detect.py --mu -10.5 --steps 3 --warmup 3"
-$D > gpurun_out/plain_chain.log 2>&1 && \
-  ncu --set full --clock-control none --import-source on -k regex:'rank_sort_kernel|nms_fused_kernel|select_fused_kernel' -s 9 -c 3 -o gpurun_out/r02_chain --force-overwrite $D > gpurun_out/ncu_chain.log 2>&1
-ncu -i gpurun_out/r02_chain.ncu-rep --page raw --csv > gpurun_out/r02_chain_raw.csv 2>/dev/null
-tail -3 gpurun_out/ncu_chain.log; ls -la gpurun_out/r02_chain_raw.csv gpurun_out/r02_chain.ncu-rep
+P="python tools/profile_predict.py --mu -9.5 --calls 3"
+$P > gpurun_out/plain_pred.log 2>&1 && \
+  ncu --set full --clock-control none --import-source on -k regex:'nms_resolve_stream_kernel|nms_mask_kernel|radix_sort_kernel' -s 3 -c 3 -o gpurun_out/r02_long --force-overwrite $P > gpurun_out/ncu_long.log 2>&1
+ncu -i gpurun_out/r02_long.ncu-rep --page raw --csv > gpurun_out/r02_long_raw.csv 2>/dev/null
+tail -2 gpurun_out/ncu_long.log; ls -la gpurun_out/r02_long_raw.csv gpurun_out/r02_long.ncu-rep
