@@ -1604,16 +1604,16 @@ nms_resolve_stream_kernel(const int32_t* __restrict__ counts, int64_t capacity, 
 //               (16 broadcast 128-bit loads of labels, no divergence) and then visits only those columns -- the tile kernel
 //               above pays a divergent branch per column and runs the IoU test whenever ANY lane's label matches.  The row's
 //               64-bit word goes straight into CTA 0's shared memory (distributed shared memory store);
-//   resolve     after one cluster barrier CTA 0 holds the whole mask (<= 128 KB) on chip: warp 0 runs the greedy chain of
-//               nms_resolve_stream_kernel (32-bit halves, branch-free) with no global-memory latency anywhere, folds the kept
-//               rows' words of the next column block itself and leaves the later column words to warps 1..4, one chunk behind;
-//               the five warps meet at a named barrier per chunk, the other warps wait for the gather.  The chain decides a
-//               64-box chunk in parallel rounds (see below) instead of 64 dependent steps.
+//   resolve     after one cluster barrier CTA 0 holds the whole mask (<= 144 KB) on chip: warp 0 runs the greedy chain with
+//               no global-memory latency anywhere -- a 64-box chunk is decided in parallel rounds of warp-wide ORs (see below)
+//               instead of 64 dependent steps --, folds the kept rows' words of the next column block itself and leaves the
+//               later column words to warps 1..4, one chunk behind; the five warps meet at a named barrier per chunk, the
+//               other warps wait for the gather.
 // Same arithmetic as the three-kernel path (suppresses(), the offsets, the areas), so keep lists are bit-identical to it.
 // ------------------------------------------------------------------------------------------------
 constexpr int kFuseMax = 1024;
 constexpr int kFuseCb = kFuseMax / 64;         // column words per mask row
-constexpr int kFuseCluster = 4;                // 32 images x 4 CTAs: one wave on 148 SMs (one CTA per SM: 156 KB of shared memory)
+constexpr int kFuseCluster = 4;                // 32 images x 4 CTAs: one wave on 148 SMs (one CTA per SM: 172 KB of shared memory)
 constexpr int kFuseThreads = 1024;
 constexpr int kFuseSlots = kFuseThreads / 64;  // two-warp tile slots per CTA
 constexpr int kFuseChainWarps = 5;             // warp 0 runs the chain, warps 1..4 absorb 16 rows each, one chunk behind
