@@ -541,6 +541,7 @@ select_hist_pick_kernel(const uint64_t* __restrict__ keys, const int32_t* __rest
 constexpr int kSelThreads = 512;       // two CTAs per SM: 32 images x 8 CTAs are one wave on 148 SMs
 constexpr int kSelCluster = 8;
 constexpr int kSelUnroll = 8;          // independent key loads in flight per thread
+constexpr int kSelSub = 4;             // private histogram copies per CTA (by lane & 3)
 
 __global__ void __cluster_dims__(kSelCluster, 1, 1) __launch_bounds__(kSelThreads)
 select_fused_kernel(const cldet_candidate* __restrict__ cand, const uint64_t* __restrict__ keys, const int32_t* __restrict__ counts,
@@ -549,7 +550,10 @@ select_fused_kernel(const cldet_candidate* __restrict__ cand, const uint64_t* __
     pdl_wait();                       // may be scheduled while the previous kernel of the chain drains
     pdl_launch_dependents();
     namespace cg = cooperative_groups;
-    __shared__ uint32_t sh[kSelBins];
+    // kSelSub private copies of the histogram, chosen by lane: the high score bits of a whole image fall into a handful of bins
+    // (sign, exponent, two mantissa bits), so without them most of a warp's 32 atomics serialise on the same few words
+    __shared__ uint32_t shs[kSelSub][kSelBins];
+    uint32_t* const sh = shs[0];
     __shared__ uint32_t part[256];
     __shared__ uint32_t s_prefix, s_need;
     __shared__ int warp_tot[kSelThreads / 32];
@@ -578,9 +582,10 @@ select_fused_kernel(const cldet_candidate* __restrict__ cand, const uint64_t* __
     for (int ps = 0; ps < 3; ++ps) {
         const SelPass P = passes[ps];
         const int nb = 1 << P.bits;
-        for (int b = tid; b < kSelBins; b += kSelThreads) sh[b] = 0;
+        for (int b = tid; b < kSelSub * kSelBins; b += kSelThreads) shs[0][b] = 0;
         __syncthreads();
         const uint32_t prefix = s_prefix;
+        uint32_t* const mysh = shs[tid & (kSelSub - 1)];
         for (int64_t i0 = (int64_t)rank * kSelUnroll * kSelThreads; i0 < cnt; i0 += stride) {
             uint32_t sc[kSelUnroll];
 #pragma unroll
@@ -592,8 +597,15 @@ select_fused_kernel(const cldet_candidate* __restrict__ cand, const uint64_t* __
             for (int u = 0; u < kSelUnroll; ++u) {
                 const int64_t i = i0 + u * kSelThreads + tid;
                 const bool match = P.hi_bits == 0 || (sc[u] >> (32 - P.hi_bits)) == (prefix >> (32 - P.hi_bits));
-                if (i < cnt && match) atomicAdd(&sh[(sc[u] >> P.shift) & (nb - 1)], 1u);
+                if (i < cnt && match) atomicAdd(&mysh[(sc[u] >> P.shift) & (nb - 1)], 1u);
             }
+        }
+        __syncthreads();
+        for (int b = tid; b < nb; b += kSelThreads) {            // fold the private copies into copy 0
+            uint32_t v = shs[0][b];
+#pragma unroll
+            for (int q = 1; q < kSelSub; ++q) v += shs[q][b];
+            shs[0][b] = v;
         }
         cluster.sync();                                          // every CTA's histogram is complete
         if (rank == 0) {
